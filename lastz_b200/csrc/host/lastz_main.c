@@ -1,0 +1,237 @@
+/*
+ * lastz_main.c -- the `lastz` command line (subset) over the lastz_b200 C-ABI.
+ *
+ * Mirrors the driver in the reference's lastz.c: option parsing (parse_options_loop :5357ff),
+ * derived defaults (:9313-9339), the query/strand loop (main :1453-1760), start_one_strand
+ * (:3006) and finish_one_strand (:3262).  All seed-and-extend work is done by whichever library
+ * implementing include/lastz_b200.h this binary is linked with: liblastz_b200.so (CUDA, the
+ * product, `lastz_b200`) or oracle/liblzb_oracle.so (CPU restatement, test tool `lastz_oracle`).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "lzb_host.h"
+
+typedef struct {
+    const char* targetSpec; const char* querySpec;
+    const char* seedPattern; int withTrans, haveTrans;
+    uint32_t step; int haveStep;
+    int whichStrand;               /* 0 plus, 1 both, -1 minus */
+    int gfExtend, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
+    int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
+    uint32_t tracebackBytes;
+    int hashBits;
+    const char* scoresFile; const char* segmentsFile; const char* outputFile;
+    int format;                    /* 0 lav, 1 segments */
+    int device, showStats, speculation;
+    char args[4096];
+} options;
+
+static int starts(const char* a, const char* p) { return strncmp(a, p, strlen(p)) == 0; }
+
+static long unitized(const char* s) {       /* string_to_unitized_int, units of 1024 */
+    char* e; double v = strtod(s, &e);
+    if (*e == 'K' || *e == 'k') v *= 1024; else if (*e == 'M' || *e == 'm') v *= 1024 * 1024;
+    else if (*e == 'G' || *e == 'g') v *= 1024.0 * 1024 * 1024;
+    return (long)v;
+}
+
+static void parse_options(options* o, int argc, char** argv) {
+    memset(o, 0, sizeof *o);
+    o->withTrans = 1; o->step = 1; o->whichStrand = 1; o->gfExtend = LZB_GFEX_XDROP; o->gapped = 1;
+    o->entropy = 1; o->trimToPeak = 1; o->tracebackBytes = 80u * 1024 * 1024; o->hashBits = 16;
+    o->speculation = 16;
+    char* wordSeed = NULL;
+    for (int i = 1; i < argc; i++) {
+        const char* a = argv[i]; const char* v = strchr(a, '='); v = v ? v + 1 : "";
+        if (a[0] != '-' && !(strlen(a) > 1 && a[1] == '=' && strchr("CTWKLXYOEZ", a[0]))) {
+            if (!o->targetSpec) o->targetSpec = a; else if (!o->querySpec) o->querySpec = a;
+            else lzb_die("Can't understand \"%s\"", a);
+            continue;
+        }
+        if (strlen(o->args) + strlen(a) + 2 < sizeof o->args) { strcat(o->args, a); strcat(o->args, " "); }
+        if (!strcmp(a, "T=0")) { o->withTrans = 0; o->haveTrans = 1; }
+        else if (!strcmp(a, "T=1")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 1; }
+        else if (!strcmp(a, "T=2")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 0; }
+        else if (!strcmp(a, "T=3")) { o->seedPattern = LZB_SEED_14OF22; o->withTrans = 1; }
+        else if (!strcmp(a, "T=4")) { o->seedPattern = LZB_SEED_14OF22; o->withTrans = 0; }
+        else if (starts(a, "W=") || starts(a, "--word=") || starts(a, "--seed=match")) {
+            int w = atoi(starts(a, "--seed=match") ? a + 12 : v);
+            if (w < 1 || w > 15) lzb_die("%d is not a valid word length", w);
+            wordSeed = malloc((size_t)w + 1); memset(wordSeed, '1', (size_t)w); wordSeed[w] = 0;
+            o->seedPattern = wordSeed;
+            if (!o->haveTrans) { o->withTrans = 0; o->haveTrans = 1; }
+        }
+        else if (!strcmp(a, "--seed=12of19")) o->seedPattern = LZB_SEED_12OF19;
+        else if (!strcmp(a, "--seed=14of22")) o->seedPattern = LZB_SEED_14OF22;
+        else if (starts(a, "--seed=")) o->seedPattern = v;
+        else if (!strcmp(a, "--notransition") || !strcmp(a, "--notrans")) { o->withTrans = 0; o->haveTrans = 1; }
+        else if (!strcmp(a, "--transition")) { o->withTrans = 1; o->haveTrans = 1; }
+        else if (starts(a, "--transition=")) { o->withTrans = atoi(v); o->haveTrans = 1; }
+        else if (starts(a, "--step=") || starts(a, "Z=")) { o->step = (uint32_t)atoi(v); o->haveStep = 1; }
+        else if (!strcmp(a, "--strand=both")) o->whichStrand = 1;
+        else if (!strcmp(a, "--strand=plus") || !strcmp(a, "--plus")) o->whichStrand = 0;
+        else if (!strcmp(a, "--strand=minus")) o->whichStrand = -1;
+        else if (!strcmp(a, "--self")) { o->selfCompare = 1; o->inhibitTrivial = 1; }
+        else if (!strcmp(a, "--notrivial")) o->inhibitTrivial = 1;
+        else if (!strcmp(a, "--nogfextend")) o->gfExtend = LZB_GFEX_NONE;
+        else if (!strcmp(a, "--gfextend")) o->gfExtend = LZB_GFEX_XDROP;
+        else if (!strcmp(a, "--nogapped") || !strcmp(a, "--ungapped")) o->gapped = 0;
+        else if (!strcmp(a, "--gapped")) o->gapped = 1;
+        else if (!strcmp(a, "C=0")) { o->chain = 0; o->gapped = 1; }
+        else if (!strcmp(a, "C=1")) { o->chain = 1; o->gapped = 0; }
+        else if (!strcmp(a, "C=2")) { o->chain = 1; o->gapped = 1; }
+        else if (!strcmp(a, "C=3")) { o->chain = 0; o->gapped = 0; }
+        else if (!strcmp(a, "--chain")) o->chain = 1;
+        else if (!strcmp(a, "--nochain")) o->chain = 0;
+        else if (!strcmp(a, "--noentropy")) o->entropy = 0;
+        else if (!strcmp(a, "--entropy")) o->entropy = 1;
+        else if (!strcmp(a, "--allgappedbounds")) o->allBounds = 1;
+        else if (!strcmp(a, "--noytrim")) o->trimToPeak = 0;
+        else if (starts(a, "--hspthresh=") || starts(a, "K=")) { o->K = atoi(v); o->haveK = 1; }
+        else if (starts(a, "--gappedthresh=") || starts(a, "L=")) { o->L = atoi(v); o->haveL = 1; }
+        else if (starts(a, "--xdrop=") || starts(a, "X=")) { o->X = atoi(v); o->haveX = 1; }
+        else if (starts(a, "--ydrop=") || starts(a, "Y=")) { o->Y = atoi(v); o->haveY = 1; }
+        else if (starts(a, "O=")) { o->O = atoi(v); o->haveO = 1; }
+        else if (starts(a, "E=")) { o->E = atoi(v); o->haveE = 1; }
+        else if (starts(a, "--gap=")) { if (sscanf(v, "%d,%d", &o->O, &o->E) != 2) lzb_die("can't understand %s", a); o->haveO = o->haveE = 1; }
+        else if (starts(a, "--scores=") || starts(a, "Q=")) o->scoresFile = v;
+        else if (starts(a, "--segments=")) o->segmentsFile = v;
+        else if (starts(a, "--allocate:traceback=") || starts(a, "--traceback=")) o->tracebackBytes = (uint32_t)unitized(v);
+        else if (starts(a, "--output=")) o->outputFile = v;
+        else if (!strcmp(a, "--format=lav")) o->format = 0;
+        else if (!strcmp(a, "--format=segments")) o->format = 1;
+        /* lastz_b200 additions */
+        else if (starts(a, "--device=")) o->device = atoi(v);
+        else if (starts(a, "--diaghash=")) o->hashBits = atoi(v);
+        else if (starts(a, "--speculation=")) o->speculation = atoi(v);
+        else if (!strcmp(a, "--stats")) o->showStats = 1;
+        else lzb_die("lastz_b200 does not implement option \"%s\" (seed-and-extend hot path only)", a);
+    }
+    if (!o->targetSpec) lzb_die("You must specify a target file");
+    if (o->selfCompare && !o->querySpec) o->querySpec = o->targetSpec;
+    if (!o->querySpec) lzb_die("You must specify a query file (reading from stdin is not supported)");
+}
+
+/* read_segment_table segment.c:456: rows name1 start1 end1 name2 start2 end2 strand [score] */
+static uint64_t read_segments(const char* path, const lzb_seq* t, const lzb_seq* q, lzb_segment** out) {
+    FILE* f = fopen(path, "rt");
+    if (!f) lzb_die("fopen_or_die failed to open \"%s\" for \"rt\"", path);
+    uint64_t n = 0, cap = 0; lzb_segment* g = NULL; char line[1024];
+    char want = (q->revCompFlags & LZB_RCF_REV) ? '-' : '+';
+    while (fgets(line, sizeof line, f)) {
+        if (line[0] == '#') continue;
+        char n1[256], n2[256], st; unsigned s1, e1, s2, e2; int sc = 0;
+        int items = sscanf(line, "%255s %u %u %255s %u %u %c %d", n1, &s1, &e1, n2, &s2, &e2, &st, &sc);
+        if (items < 7) continue;
+        if (strcmp(n1, t->shortHeader) || strcmp(n2, q->shortHeader) || st != want) continue;
+        if (n == cap) { cap = cap * 2 + 256; g = realloc(g, cap * sizeof *g); }
+        memset(&g[n], 0, sizeof *g);
+        g[n].pos1 = s1 - t->startLoc; g[n].pos2 = s2 - q->startLoc; g[n].length = e1 + 1 - s1;
+        g[n].s = sc; g[n].id = q->revCompFlags; g[n].scoreCov = g[n].length;
+        n++;
+    }
+    fclose(f);
+    *out = g; return n;
+}
+
+int main(int argc, char** argv) {
+    options o; parse_options(&o, argc, argv);
+    /* scoring + derived defaults, lastz.c:9127-9339 */
+    static lzb_scoreset ss;
+    if (o.scoresFile) lzb_scores_read_file(&ss, o.scoresFile); else lzb_scores_default(&ss);
+    if (o.haveO) ss.gapOpen = o.O;
+    if (o.haveE) ss.gapExtend = o.E;
+    if (!o.haveK) o.K = ss.hspThresholdSet ? ss.hspThreshold : 3000;
+    if (o.gfExtend == LZB_GFEX_NONE && !o.haveK) o.K = 0;          /* lastz.c:8984-9010 */
+    if (!o.haveX) o.X = ss.xDropSet ? ss.xDrop : 10 * ss.sub['A' * 256 + 'A'];
+    if (!o.haveY) o.Y = ss.yDropSet ? ss.yDrop : ss.gapOpen + 300 * ss.gapExtend;
+    if (!o.haveL) o.L = ss.gappedThresholdSet ? ss.gappedThreshold : (o.gfExtend == LZB_GFEX_XDROP ? o.K : 3000);
+    if (!o.haveStep && ss.stepSet) o.step = ss.step;
+    if (o.chain) lzb_die("--chain is not implemented yet in lastz_b200");
+    lzb_seed seed; lzb_seed_parse(&seed, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, o.withTrans);
+
+    FILE* out = stdout;
+    if (o.outputFile) { out = fopen(o.outputFile, "wt"); if (!out) lzb_die("can't open %s", o.outputFile); }
+
+    lzb_seqfile* tf = lzb_seqfile_open(o.targetSpec);
+    lzb_seq target;
+    if (!lzb_seqfile_next(tf, &target)) lzb_die("%s contains no sequence", o.targetSpec);
+    { lzb_seq extra; if (lzb_seqfile_next(tf, &extra)) lzb_die("%s contains more than one sequence, consider using the \"multiple\" action", o.targetSpec); }
+
+    lzb_ctx* ctx = lzb_open(o.device);
+    if (!ctx) lzb_die("%s", lzb_last_error());
+    if (lzb_set_scoring(ctx, ss.sub, ss.masked, ss.gapOpen, ss.gapExtend)) lzb_die("%s", lzb_last_error());
+    lzb_target* T = lzb_target_build(ctx, target.v, target.len, 0, 0, lzb_upper_nuc_to_bits, &seed, o.step);
+    if (!T) lzb_die("%s", lzb_last_error());
+
+    if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, o.K, o.L);
+    else fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
+
+    lzb_seed_stats sst; lzb_gapped_stats gst;
+    uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
+    lzb_seqfile* qf = lzb_seqfile_open(o.querySpec);
+    lzb_seq query;
+    while (lzb_seqfile_next(qf, &query)) {
+        if (query.len == 0) { lzb_seq_free(&query); continue; }
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 0 && o.whichStrand < 0) continue;
+            if (pass == 1 && o.whichStrand == 0) continue;
+            if (pass == 1) lzb_seq_revcomp(&query);
+            lzb_query* Q = lzb_query_load(ctx, query.v, query.len);
+            if (!Q) lzb_die("%s", lzb_last_error());
+            lzb_segment* segs = NULL; uint64_t nsegs = 0;
+            if (o.segmentsFile) nsegs = read_segments(o.segmentsFile, &target, &query, &segs);
+            else {
+                lzb_seed_params sp; memset(&sp, 0, sizeof sp);
+                sp.gfExtend = o.gfExtend; sp.xDrop = o.X; sp.hspThreshold = o.K; sp.entropy = o.entropy;
+                sp.hashBits = o.hashBits; sp.selfCompare = o.selfCompare;
+                sp.sameStrand = o.selfCompare && query.revCompFlags == target.revCompFlags;
+                sp.strandId = query.revCompFlags;
+                sp.plainHits = (o.gfExtend == LZB_GFEX_NONE && !o.gapped);
+                if (lzb_seed_hit_search(ctx, T, Q, &seed, lzb_upper_nuc_to_bits, &sp, &segs, &nsegs, &sst))
+                    lzb_die("%s", lzb_last_error());
+                totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
+            }
+            int headerDone = 0;
+            if (!o.gapped) {
+                for (uint64_t k = 0; k < nsegs; k++) {
+                    if (o.format == 0) {
+                        if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
+                        lzb_lav_match(out, &target, &query, &segs[k]);
+                    }
+                }
+                if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
+            } else {
+                lzb_gapped_params gp; memset(&gp, 0, sizeof gp);
+                gp.yDrop = o.Y; gp.trimToPeak = o.trimToPeak; gp.scoreThreshold = o.L; gp.allBounds = o.allBounds;
+                gp.inhibitTrivial = o.inhibitTrivial; gp.tracebackBytes = o.tracebackBytes;
+                gp.identityCheck = query.revCompFlags == target.revCompFlags;
+                gp.speculation = o.speculation;
+                if (lzb_reduce_to_points(ctx, T, Q, segs, nsegs)) lzb_die("%s", lzb_last_error());
+                lzb_alignel* list = NULL;
+                if (lzb_gapped_extend(ctx, T, Q, target.v, query.v, segs, nsegs, &gp, &list, &gst))
+                    lzb_die("%s", lzb_last_error());
+                totCells += gst.dpCells; gapSec += gst.seconds;
+                for (lzb_alignel* a = list; a; a = a->next) {
+                    if (o.format == 0) {
+                        if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
+                        lzb_lav_align(out, &target, &query, a);
+                    } else lzb_die("--format=segments needs --nogapped");
+                }
+                lzb_free_align_list(list);
+            }
+            lzb_free(segs);
+            lzb_query_free(Q);
+        }
+        lzb_seq_free(&query);
+    }
+    if (o.format == 0) lzb_lav_footer(out);
+    if (o.showStats)
+        fprintf(stderr, "backend=%s raw_seed_hits=%llu hsps=%llu dp_cells=%llu seed_seconds=%.6f gapped_seconds=%.6f\n",
+                lzb_backend(), (unsigned long long)totHits, (unsigned long long)totHsps,
+                (unsigned long long)totCells, seedSec, gapSec);
+    lzb_seqfile_close(qf); lzb_seqfile_close(tf);
+    lzb_target_free(T); lzb_close(ctx); lzb_seq_free(&target);
+    if (out != stdout) fclose(out);
+    return 0;
+}

@@ -1,0 +1,77 @@
+/*
+ * lzb_host.h -- host-side (plain C) front end of lastz_b200: the data contracts on either side
+ * of the hot path (sequence files, scoring sets, seeds, output writers) and the `lastz` command
+ * line subset.  Everything here is reference-compatible plumbing; all seed-and-extend work goes
+ * through the C-ABI in include/lastz_b200.h.
+ */
+#ifndef LZB_HOST_H
+#define LZB_HOST_H
+
+#include <stdint.h>
+#include <stdio.h>
+#include "../../../include/lastz_b200.h"
+
+/* strand flags, sequences.h:345-350 */
+#define LZB_RCF_FORWARD 0
+#define LZB_RCF_COMP    1
+#define LZB_RCF_REV     2
+#define LZB_RCF_REVCOMP 3
+
+/* the subset of `seq` (sequences.h:381-588) the path and the writers need */
+typedef struct lzb_seq {
+    uint8_t* v;          /* bases, NUL terminated (v[len] == 0) */
+    uint32_t len;        /* bases held in v */
+    uint32_t startLoc;   /* 1-based position of v[0] in the full sequence */
+    uint32_t trueLen;    /* length of the full sequence */
+    int      revCompFlags;
+    uint32_t contig;     /* 1-based ordinal within the file */
+    char*    filename;   /* as given on the command line, actions stripped */
+    char*    header;     /* full header line (FASTA: including '>') */
+    char*    shortHeader;/* first word of the header */
+} lzb_seq;
+
+/* a sequence file + bracketed actions; load successive sequences with lzb_seqfile_next */
+typedef struct lzb_seqfile lzb_seqfile;
+lzb_seqfile* lzb_seqfile_open(const char* spec);       /* "file[actions]" or "file.2bit/name[...]" */
+int          lzb_seqfile_next(lzb_seqfile*, lzb_seq* out);   /* 1 = loaded, 0 = no more */
+void         lzb_seqfile_close(lzb_seqfile*);
+void         lzb_seq_free(lzb_seq*);
+void         lzb_seq_revcomp(lzb_seq*);                /* rev_comp_sequence sequences.c:7511 */
+void         lzb_die(const char* fmt, ...);            /* suicidef utilities.c:1866 */
+
+/* scoreset (dna_utilities.h:176-212): the two matrices + gap penalties + embedded parameters */
+typedef struct lzb_scoreset {
+    int32_t sub[256 * 256];
+    int32_t masked[256 * 256];
+    int32_t gapOpen, gapExtend;
+    int gapOpenSet, gapExtendSet;
+    int hspThresholdSet, gappedThresholdSet, xDropSet, yDropSet, stepSet;
+    int32_t hspThreshold, gappedThreshold, xDrop, yDrop; uint32_t step;
+} lzb_scoreset;
+void lzb_scores_default(lzb_scoreset*);                        /* HOXD70, dna_utilities.c:137-148 */
+void lzb_scores_from_template(lzb_scoreset*, int32_t tmpl[4][4], int32_t bad, int32_t fill,
+                              int32_t gapOpen, int32_t gapExtend);   /* new_dna_score_set :215 */
+void lzb_scores_mask(lzb_scoreset*);                           /* masked_score_set :497 */
+void lzb_scores_read_file(lzb_scoreset*, const char* path);    /* read_score_set_by_name :657 */
+
+/* seeds (seeds.c:321-632) */
+#define LZB_SEED_12OF19 "1110100110010101111"
+#define LZB_SEED_14OF22 "1110101100110010101111"
+void lzb_seed_parse(lzb_seed* out, const char* pattern, int withTrans);
+extern const int8_t lzb_upper_nuc_to_bits[256];                /* dna_utilities.c:76-94 */
+extern const int8_t lzb_nuc_to_bits[256];                      /* dna_utilities.c:56-74 */
+
+/* output writers */
+void lzb_lav_job_header(FILE*, const char* prog, const char* name1, const char* name2,
+                        const char* args, const lzb_scoreset*, int32_t K, int32_t L);  /* lav.c:40 */
+void lzb_lav_strand_header(FILE*, const lzb_seq* s1, const lzb_seq* s2);               /* lav.c:101 */
+void lzb_lav_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);   /* lav.c:187 */
+void lzb_lav_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);   /* lav.c:327 */
+void lzb_lav_footer(FILE*);                                                            /* m stanza + #:eof */
+void lzb_segments_write(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, uint64_t n);
+                                                                                       /* write_segments segment.c:1930 */
+void lzb_general_header(FILE*);
+void lzb_general_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
+void lzb_general_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
+
+#endif

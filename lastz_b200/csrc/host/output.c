@@ -1,0 +1,91 @@
+/*
+ * output.c -- the wire formats on the output side of the hot path: LAV (lav.c:40-360) and the
+ * segments file (--format=segments; output.c fmtSegments -> genpaf.c with the fields
+ * name1 start1 end1 name2 start2 end2 strand2 score).
+ */
+#include <ctype.h>
+#include <string.h>
+#include "lzb_host.h"
+
+void lzb_lav_job_header(FILE* f, const char* prog, const char* name1, const char* name2,
+                        const char* args, const lzb_scoreset* ss, int32_t K, int32_t L) {
+    const char* nuc = "ACGT";
+    fprintf(f, "#:lav\nd {\n  \"%s %s %s %s\n", prog, name1, name2, args);
+    /* print_score_matrix dna_utilities.c: column header, then one row per nucleotide */
+    fprintf(f, "  ");
+    for (int c = 0; c < 4; c++) fprintf(f, "%s%4c", c ? " " : "", nuc[c]);
+    fprintf(f, "\n");
+    for (int r = 0; r < 4; r++) {
+        fprintf(f, "  ");
+        for (int c = 0; c < 4; c++) fprintf(f, "%s%4d", c ? " " : "", ss->sub[nuc[r] * 256 + nuc[c]]);
+        fprintf(f, "\n");
+    }
+    fprintf(f, "  O = %d, E = %d, K = %d, L = %d, M = %d\"\n}\n", ss->gapOpen, ss->gapExtend, K, L, 0);
+}
+
+void lzb_lav_strand_header(FILE* f, const lzb_seq* s1, const lzb_seq* s2) {
+    static const char* shortSfx[4] = { "", "~", "~-", "-" };
+    static const char* longSfx[4] = { "", "~", "~ (reverse complement)", " (reverse complement)" };
+    fprintf(f, "#:lav\ns {\n");
+    fprintf(f, "  \"%s%s\" %u %u %d %u\n", s1->filename, shortSfx[s1->revCompFlags], s1->startLoc,
+            s1->startLoc + s1->len - 1, (s1->revCompFlags & LZB_RCF_REV) ? 1 : 0, s1->contig);
+    fprintf(f, "  \"%s%s\" %u %u %d %u\n", s2->filename, shortSfx[s2->revCompFlags], s2->startLoc,
+            s2->startLoc + s2->len - 1, (s2->revCompFlags & LZB_RCF_REV) ? 1 : 0, s2->contig);
+    fprintf(f, "}\nh {\n   \"%s%s\"\n   \"%s%s\"\n}\n", s1->header, longSfx[s1->revCompFlags],
+            s2->header, longSfx[s2->revCompFlags]);
+}
+
+/* print_lav_align lav.c:187-245: one l-line per gap-free run, percent identity rounded */
+void lzb_lav_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a) {
+    uint32_t beg1 = a->beg1, beg2 = a->beg2, end1 = a->end1, end2 = a->end2;
+    uint32_t height = end1 - beg1 + 1, width = end2 - beg2 + 1;
+    const lzb_editscript* sc = a->script;
+    fprintf(f, "a {\n  s %d\n  b %u %u\n  e %u %u\n", a->s, beg1, beg2, end1, end2);
+    uint32_t k = 0;
+    for (uint32_t i = 0, j = 0; i < height || j < width;) {
+        uint32_t pi = i, pj = j, run = 0, match = 0;
+        const uint8_t* p = s1->v + beg1 + i - 1; const uint8_t* q = s2->v + beg2 + j - 1;
+        while (k < sc->len && (sc->op[k] & 3) == LZB_OP_SUB) {
+            uint32_t rpt = sc->op[k] >> 2; k++; run += rpt;
+            while (rpt-- > 0) { if (toupper(*p) == toupper(*q)) match++; p++; q++; }
+        }
+        i += run; j += run;
+        int pct = run ? (int)((200ull * match + run) / (2ull * run)) : 0;
+        fprintf(f, "  l %u %u %u %u %d\n", beg1 + pi, beg2 + pj, beg1 + i - 1, beg2 + j - 1, pct);
+        if (i < height || j < width) {
+            if (k < sc->len) {
+                uint32_t op = sc->op[k] & 3, rpt = sc->op[k] >> 2;
+                if (op == LZB_OP_INS) j += rpt; else if (op == LZB_OP_DEL) i += rpt;
+                k++;
+            }
+        }
+    }
+    fprintf(f, "}\n");
+}
+
+/* percent_identical sequences.c:9623-9659 */
+static int pct_identical(const uint8_t* a, const uint8_t* b, uint32_t len) {
+    uint32_t m = 0, d = 0;
+    for (uint32_t i = 0; i < len; i++) {
+        int x = lzb_nuc_to_bits[a[i]], y = lzb_nuc_to_bits[b[i]];
+        if (x >= 0 && y >= 0) { if (x == y) m++; d++; }
+    }
+    return d ? (int)((200ull * m + d) / (2ull * d)) : 0;
+}
+
+void lzb_lav_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g) {
+    uint32_t e1 = g->pos1 + g->length, e2 = g->pos2 + g->length;
+    int pct = g->length ? pct_identical(s1->v + g->pos1, s2->v + g->pos2, g->length) : 0;
+    fprintf(f, "a {\n  s %d\n  b %u %u\n  e %u %u\n  l %u %u %u %u %d\n}\n", g->s,
+            g->pos1 + 1, g->pos2 + 1, e1, e2, g->pos1 + 1, g->pos2 + 1, e1, e2, pct);
+}
+
+void lzb_lav_footer(FILE* f) { fprintf(f, "m {\n  n 0\n}\n#:eof\n"); }
+
+void lzb_segments_write(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g, uint64_t n) {
+    char strand = (s2->revCompFlags & LZB_RCF_REV) ? '-' : '+';
+    for (uint64_t i = 0; i < n; i++)
+        fprintf(f, "%s\t%u\t%u\t%s\t%u\t%u\t%c\t%d\n", s1->shortHeader, g[i].pos1 + s1->startLoc,
+                g[i].pos1 + g[i].length + s1->startLoc - 1, s2->shortHeader, g[i].pos2 + s2->startLoc,
+                g[i].pos2 + g[i].length + s2->startLoc - 1, strand, g[i].s);
+}

@@ -1,0 +1,62 @@
+/*
+ * seeds.c -- spaced-seed parsing and packing recipe.  Reference: seeds.c:321-632
+ * (parse_one_seed), :1399-1418 (best_shift).  The packing (which unpacked bit lands on which index
+ * bit) must be the reference's own greedy recipe: transition variants are probed in ascending
+ * PACKED bit order (seeds.c:615-625, seed_search.c:528-533), so the recipe decides the order in
+ * which seed hits are discovered.
+ */
+#include <string.h>
+#include "lzb_host.h"
+
+static int popcount64(uint64_t x) { return __builtin_popcountll(x); }
+
+/* the shift that brings the most not-yet-covered index bits into place; first best wins */
+static int greedy_shift(uint32_t uncovered, uint64_t remaining) {
+    int best = -1, bestShift = -1;
+    for (int sh = 0; remaining != 0; remaining >>= 1, sh++) {
+        int cover = popcount64(remaining & uncovered);
+        if (cover > best) { best = cover; bestShift = sh; }
+    }
+    return bestShift;
+}
+
+void lzb_seed_parse(lzb_seed* out, const char* pattern, int withTrans) {
+    const char* s = pattern; const char* e = pattern + strlen(pattern);
+    while (s < e && (*s == '0' || *s == 'X' || *s == 'x')) s++;
+    if (s == e) lzb_die("seed string is empty!");
+    while (e[-1] == '0' || e[-1] == 'X' || e[-1] == 'x') e--;
+    uint64_t bits = 0, flips = 0; int length = 0, weight = 0;
+    for (const char* p = s; p < e; p++) {
+        switch (*p) {
+            case '1': bits = (bits << 2) + 3; flips = (flips << 2) + 2; weight += 2; length++; break;
+            case '0': case 'X': case 'x': bits <<= 2; flips <<= 2; length++; break;
+            case 'T': case 't':
+                lzb_die("lastz_b200 supports strict seeds only (1s and 0s); \"%s\" has a transition position", pattern);
+                break;
+            default: lzb_die("seed string %s contains illegal character %c", pattern, *p);
+        }
+    }
+    if (length > 31) lzb_die("seed string (%s) cannot have length exceeding 31 (it's %d).", pattern, length);
+    if (weight > 28) lzb_die("seed (%s) needs %d index bits; lastz_b200 does not implement overweight seeds (max 28)", pattern, weight);
+    memset(out, 0, sizeof *out);
+    out->length = length; out->weight = weight; out->withTrans = withTrans;
+    uint32_t wbits = (uint32_t)((1ull << weight) - 1);
+    uint32_t covered = (uint32_t)bits & wbits;
+    uint64_t rem = bits - covered;
+    out->shift[0] = 0; out->mask[0] = covered; out->numParts = 1;
+    while (covered != wbits) {
+        int sh = greedy_shift(~covered & wbits, rem);
+        uint32_t m = (uint32_t)(rem >> sh) & ~covered & wbits;
+        covered += m; rem -= (uint64_t)m << sh;
+        if (out->numParts >= LZB_MAX_SEED_PARTS) lzb_die("seed (%s) needs too many shift/mask parts", pattern);
+        out->shift[out->numParts] = sh; out->mask[out->numParts] = m; out->numParts++;
+    }
+    /* single-bit transition flips, lowest packed bit first */
+    uint32_t packed = 0;
+    for (int i = 0; i < out->numParts; i++) packed |= (uint32_t)(flips >> out->shift[i]) & out->mask[i];
+    while (packed) {
+        uint32_t low = packed & (~packed + 1);
+        packed -= low;
+        out->transFlips[out->numFlips++] = low;
+    }
+}

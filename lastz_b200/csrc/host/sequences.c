@@ -1,0 +1,220 @@
+/*
+ * sequences.c -- minimal sequence ingest for lastz_b200: FASTA and 2bit, with the bracketed
+ * actions the hot-path tests need ([a..b], [a,b], [a#len], [unmask]) and 2bit contig selection
+ * (file.2bit/name).  Reference: sequences.c:2167 (FASTA), :3677 (2bit), :6700ff (actions),
+ * :7511 (rev_comp_sequence).  seq->v keeps the bytes exactly as the reference does: case is
+ * preserved (lowercase = soft-masked), N stays N, v[len] = 0.
+ */
+#include <ctype.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include "lzb_host.h"
+
+void lzb_die(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    fprintf(stderr, "FAILURE: "); vfprintf(stderr, fmt, ap); fprintf(stderr, "\n");
+    va_end(ap);
+    exit(EXIT_FAILURE);
+}
+
+struct lzb_seqfile {
+    char* filename; char* contigName;
+    FILE* f;
+    int is2bit, bigEndian;
+    uint32_t start, end;        /* 1-based inclusive limits, 0 = none */
+    int unmask;
+    uint32_t contig;            /* sequences delivered so far */
+    /* 2bit index */
+    uint32_t n2; char** names; uint32_t* offsets;
+    int pendingCh;
+};
+
+static char* dupstr(const char* s) { char* d = malloc(strlen(s) + 1); strcpy(d, s); return d; }
+
+static uint32_t rd4(lzb_seqfile* sf) {
+    unsigned char b[4];
+    if (fread(b, 1, 4, sf->f) != 4) lzb_die("premature end of file in %s", sf->filename);
+    if (sf->bigEndian) return ((uint32_t)b[0] << 24) | (b[1] << 16) | (b[2] << 8) | b[3];
+    return ((uint32_t)b[3] << 24) | (b[2] << 16) | (b[1] << 8) | b[0];
+}
+
+static void parse_actions(lzb_seqfile* sf, char* act) {
+    /* comma/bracket separated actions; "a,b" is an interval when both parts are numbers */
+    for (char* tok = act; *tok;) {
+        char* e = tok; int depth = 0;
+        while (*e && !(*e == ']' && depth == 0)) e++;
+        char save = *e; *e = 0;
+        /* split on commas unless the whole thing is "num,num" */
+        unsigned a, b; char x;
+        if (sscanf(tok, "%u..%u%c", &a, &b, &x) == 2 || sscanf(tok, "%u,%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = b; }
+        else if (sscanf(tok, "%u#%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = a + b - 1; }
+        else {
+            for (char* p = strtok(tok, ","); p; p = strtok(NULL, ",")) {
+                if (!strcmp(p, "unmask")) sf->unmask = 1;
+                else if (sscanf(p, "%u..%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = b; }
+                else if (sscanf(p, "%u#%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = a + b - 1; }
+                else lzb_die("sequence action \"%s\" is not supported by lastz_b200 (file %s)", p, sf->filename);
+            }
+        }
+        if (!save) break;
+        tok = e + 1;
+        while (*tok == '[') tok++;
+    }
+}
+
+lzb_seqfile* lzb_seqfile_open(const char* spec) {
+    lzb_seqfile* sf = calloc(1, sizeof *sf);
+    char* s = dupstr(spec);
+    char* br = strchr(s, '[');
+    if (br) { *br = 0; parse_actions(sf, br + 1); }
+    /* file.2bit/contig */
+    char* tb = strstr(s, ".2bit/");
+    if (tb) { sf->contigName = dupstr(tb + 6); tb[5] = 0; }
+    sf->filename = s;
+    sf->f = fopen(s, "rb");
+    if (!sf->f) lzb_die("fopen_or_die failed to open \"%s\" for \"rb\"", s);
+    unsigned char magic[4];
+    size_t got = fread(magic, 1, 4, sf->f);
+    uint32_t be = got == 4 ? (((uint32_t)magic[0] << 24) | (magic[1] << 16) | (magic[2] << 8) | magic[3]) : 0;
+    uint32_t le = got == 4 ? (((uint32_t)magic[3] << 24) | (magic[2] << 16) | (magic[1] << 8) | magic[0]) : 0;
+    if (be == 0x1A412743u || le == 0x1A412743u) {
+        sf->is2bit = 1; sf->bigEndian = (be == 0x1A412743u);
+        rd4(sf);                               /* version */
+        sf->n2 = rd4(sf); rd4(sf);             /* count, reserved */
+        sf->names = calloc(sf->n2, sizeof(char*)); sf->offsets = calloc(sf->n2, 4);
+        for (uint32_t i = 0; i < sf->n2; i++) {
+            int nl = fgetc(sf->f);
+            sf->names[i] = calloc((size_t)nl + 1, 1);
+            if (fread(sf->names[i], 1, (size_t)nl, sf->f) != (size_t)nl) lzb_die("bad 2bit index in %s", s);
+            sf->offsets[i] = rd4(sf);
+        }
+    } else {
+        rewind(sf->f);
+    }
+    return sf;
+}
+
+void lzb_seqfile_close(lzb_seqfile* sf) {
+    if (!sf) return;
+    if (sf->f) fclose(sf->f);
+    for (uint32_t i = 0; i < sf->n2; i++) free(sf->names[i]);
+    free(sf->names); free(sf->offsets); free(sf->filename); free(sf->contigName); free(sf);
+}
+
+void lzb_seq_free(lzb_seq* s) {
+    free(s->v); free(s->filename); free(s->header); free(s->shortHeader);
+    memset(s, 0, sizeof *s);
+}
+
+/* create_short_header sequences.c: first word of the header, '>' and leading blanks skipped */
+static char* short_header(const char* h) {
+    while (*h == '>' || *h == ' ' || *h == '\t') h++;
+    size_t n = 0; while (h[n] && !isspace((unsigned char)h[n])) n++;
+    char* d = malloc(n + 1); memcpy(d, h, n); d[n] = 0; return d;
+}
+
+static void apply_limits(lzb_seqfile* sf, lzb_seq* out, uint8_t* all, uint32_t total) {
+    uint32_t a = sf->start ? sf->start : 1, b = sf->end ? sf->end : total;
+    if (a > total) lzb_die("beyond end of sequence in %s (start limit %u, length %u)", sf->filename, a, total);
+    if (b > total) lzb_die("beyond end of sequence in %s (end limit %u, length %u)", sf->filename, b, total);
+    if (b < a) lzb_die("bad sequence interval in %s (%u..%u)", sf->filename, a, b);
+    out->len = b - a + 1; out->startLoc = a; out->trueLen = total;
+    out->v = malloc((size_t)out->len + 1);
+    memcpy(out->v, all + a - 1, out->len); out->v[out->len] = 0;
+    if (sf->unmask) for (uint32_t i = 0; i < out->len; i++) out->v[i] = (uint8_t)toupper(out->v[i]);
+    free(all);
+}
+
+static int next_fasta(lzb_seqfile* sf, lzb_seq* out) {
+    int ch;
+    do ch = fgetc(sf->f); while (ch != EOF && isspace(ch));
+    if (ch == EOF) return 0;
+    size_t hcap = 256, hl = 0; char* hdr = malloc(hcap);
+    if (ch == '>') {
+        hdr[hl++] = '>';
+        while ((ch = fgetc(sf->f)) != EOF && ch != '\n' && ch != '\r') {
+            if (hl + 2 > hcap) { hcap *= 2; hdr = realloc(hdr, hcap); }
+            hdr[hl++] = (char)ch;
+        }
+        hdr[hl] = 0;
+    } else { ungetc(ch, sf->f); hdr[0] = 0; }
+    size_t cap = 1 << 20, n = 0; uint8_t* v = malloc(cap);
+    int prev = '\n';
+    while ((ch = fgetc(sf->f)) != EOF) {
+        if (prev == '\n' && ch == '>') { ungetc(ch, sf->f); break; }
+        if (ch == '\n' || ch == '\r') { prev = '\n'; continue; }
+        if (isspace(ch)) { prev = ch; continue; }
+        if (!isalpha(ch)) lzb_die("bad fasta character in %s (ascii %02X)", sf->filename, ch);
+        if (n + 1 > cap) { cap *= 2; v = realloc(v, cap); }
+        v[n++] = (uint8_t)ch; prev = ch;
+    }
+    if (n > 0x7FFFFFFFu) lzb_die("sequence length %zu exceeds maximum", n);
+    apply_limits(sf, out, v, (uint32_t)n);
+    out->header = hdr; out->shortHeader = short_header(hdr);
+    return 1;
+}
+
+static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
+    uint32_t ix;
+    if (sf->contigName) {
+        if (sf->contig > 0) return 0;
+        for (ix = 0; ix < sf->n2; ix++) if (!strcmp(sf->names[ix], sf->contigName)) break;
+        if (ix == sf->n2) lzb_die("2bit file %s doesn't contain %s", sf->filename, sf->contigName);
+    } else {
+        ix = sf->contig;
+        if (ix >= sf->n2) return 0;
+    }
+    fseek(sf->f, (long)sf->offsets[ix], SEEK_SET);
+    uint32_t dna = rd4(sf);
+    uint32_t nb = rd4(sf);
+    uint32_t* ns = malloc(((size_t)nb * 2 + 1) * 4);
+    for (uint32_t i = 0; i < nb; i++) ns[i] = rd4(sf);
+    for (uint32_t i = 0; i < nb; i++) ns[nb + i] = rd4(sf);
+    uint32_t mb = rd4(sf);
+    uint32_t* ms = malloc(((size_t)mb * 2 + 1) * 4);
+    for (uint32_t i = 0; i < mb; i++) ms[i] = rd4(sf);
+    for (uint32_t i = 0; i < mb; i++) ms[mb + i] = rd4(sf);
+    rd4(sf);
+    size_t pb = ((size_t)dna + 3) / 4;
+    uint8_t* packed = malloc(pb + 1);
+    if (fread(packed, 1, pb, sf->f) != pb) lzb_die("premature end of file in %s", sf->filename);
+    uint8_t* v = malloc((size_t)dna + 1);
+    static const char code[4] = { 'T', 'C', 'A', 'G' };
+    for (uint32_t i = 0; i < dna; i++) v[i] = (uint8_t)code[(packed[i >> 2] >> (6 - 2 * (i & 3))) & 3];
+    for (uint32_t k = 0; k < nb; k++) for (uint32_t i = 0; i < ns[nb + k]; i++) v[ns[k] + i] = 'N';
+    for (uint32_t k = 0; k < mb; k++) for (uint32_t i = 0; i < ms[mb + k]; i++) v[ms[k] + i] = (uint8_t)tolower(v[ms[k] + i]);
+    free(packed); free(ns); free(ms);
+    apply_limits(sf, out, v, dna);
+    out->header = dupstr(sf->names[ix]); out->shortHeader = short_header(sf->names[ix]);
+    return 1;
+}
+
+int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
+    memset(out, 0, sizeof *out);
+    int ok = sf->is2bit ? next_2bit(sf, out) : next_fasta(sf, out);
+    if (!ok) return 0;
+    sf->contig++;
+    out->contig = sf->is2bit && sf->contigName ? 1 : sf->contig;
+    out->filename = dupstr(sf->filename);
+    out->revCompFlags = LZB_RCF_FORWARD;
+    return 1;
+}
+
+/* rev_comp_sequence sequences.c:7511-7559 with nuc_to_complement dna_utilities.c:96-114 */
+void lzb_seq_revcomp(lzb_seq* s) {
+    static uint8_t comp[256]; static int init = 0;
+    if (!init) {
+        for (int i = 0; i < 256; i++) comp[i] = (uint8_t)i;
+        const char* a = "ACGTRYMKBDHVNSW", *b = "TGCAYRKMVHDBNSW";
+        for (int i = 0; a[i]; i++) { comp[(int)a[i]] = (uint8_t)b[i]; comp[tolower(a[i])] = (uint8_t)tolower(b[i]); }
+        init = 1;
+    }
+    uint32_t n = s->len;
+    for (uint32_t i = 0, j = n ? n - 1 : 0; n && i <= j; i++, j--) {
+        uint8_t x = comp[s->v[i]], y = comp[s->v[j]];
+        s->v[i] = y; s->v[j] = x;
+        if (j == 0) break;
+    }
+    s->revCompFlags ^= LZB_RCF_REVCOMP;
+}
