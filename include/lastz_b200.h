@@ -141,7 +141,9 @@ typedef struct lzb_gapped_stats {
     uint64_t truncated;        /* one-sided DPs stopped by traceback capacity */
     uint64_t speculated;       /* product: DPs launched speculatively */
     uint64_t redone;           /* product: speculative DPs invalidated and recomputed */
-    double   seconds;
+    double   seconds;          /* wall time of the call (host clock around the device work) */
+    double   kernelSeconds[4]; /* [0] Y-drop DP kernel, [1] traceback kernel (CUDA events), see DESIGN.md */
+    uint64_t launches;         /* kernels launched by this call */
 } lzb_gapped_stats;
 
 typedef struct lzb_ctx    lzb_ctx;     /* one device + stream + scratch */
@@ -198,6 +200,9 @@ int lzb_gapped_extend(lzb_ctx*, lzb_target*, lzb_query*,
                       lzb_alignel** list, lzb_gapped_stats* stats);
 
 void lzb_free_align_list(lzb_alignel*);   /* free_align_list edit_script.c:53 */
+
+/* kernels launched so far through this context (0 for the oracle): bench.py's gpu_launches */
+uint64_t lzb_launch_count(lzb_ctx*);
 void lzb_free(void*);
 
 #ifdef __cplusplus

@@ -1,0 +1,138 @@
+/*
+ * context.cu -- device context, scoring classes, sequence residency.
+ * Part of liblastz_b200.so (sm_100a only; there is no CPU path: lzb_open fails without a GPU).
+ */
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include "lzb_cuda.h"
+
+static thread_local char g_err[1024];
+
+int lzb_fail(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return -1;
+}
+
+extern "C" const char* lzb_last_error(void) { return g_err; }
+extern "C" const char* lzb_backend(void) { return "cuda-sm_100a"; }
+extern "C" void lzb_free(void* p) { free(p); }
+extern "C" uint64_t lzb_launch_count(lzb_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" lzb_ctx* lzb_open(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        lzb_fail("lastz_b200 needs an sm_100 GPU and found none (%s); there is no CPU fallback",
+                 e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+        return NULL;
+    }
+    if (device < 0 || device >= n) { lzb_fail("cuda device %d does not exist (%d present)", device, n); return NULL; }
+    cudaDeviceProp prop;
+    CUDA_TRYP(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        lzb_fail("device %d is sm_%d%d; liblastz_b200 carries sm_100a code only", device, prop.major, prop.minor);
+        return NULL;
+    }
+    CUDA_TRYP(cudaSetDevice(device));
+    lzb_ctx* c = (lzb_ctx*)calloc(1, sizeof *c);
+    c->device = device; c->smCount = prop.multiProcessorCount;
+    CUDA_TRYP(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRYP(cudaMalloc(&c->d_sc, sizeof(lzb_scoring_dev)));
+    return c;
+}
+
+extern "C" void lzb_close(lzb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamDestroy(c->stream);
+    cudaFree(c->d_sc);
+    free(c->hostSub); free(c->hostMsub);
+    free(c);
+}
+
+/* group bytes whose rows and columns agree in both matrices */
+extern "C" int lzb_set_scoring(lzb_ctx* c, const int32_t* sub, const int32_t* msub, int32_t go, int32_t ge) {
+    cudaSetDevice(c->device);
+    free(c->hostSub); free(c->hostMsub);
+    c->hostSub = (s32*)malloc(65536 * 4); c->hostMsub = (s32*)malloc(65536 * 4);
+    memcpy(c->hostSub, sub, 65536 * 4); memcpy(c->hostMsub, msub, 65536 * 4);
+    lzb_scoring_dev* sc = &c->sc;
+    memset(sc, 0, sizeof *sc);
+    int rep[LZB_MAX_CLASSES]; int nc = 0;
+    for (int b = 0; b < 256; b++) {
+        int found = -1;
+        for (int k = 0; k < nc && found < 0; k++) {
+            int r = rep[k]; bool same = true;
+            for (int x = 0; x < 256 && same; x++)
+                same = sub[b * 256 + x] == sub[r * 256 + x] && sub[x * 256 + b] == sub[x * 256 + r] &&
+                       msub[b * 256 + x] == msub[r * 256 + x] && msub[x * 256 + b] == msub[x * 256 + r];
+            if (same) found = k;
+        }
+        if (found < 0) {
+            if (nc == LZB_MAX_CLASSES)
+                return lzb_fail("the scoring set distinguishes more than %d byte classes; lastz_b200 supports DNA score sets only", LZB_MAX_CLASSES);
+            rep[nc] = b; found = nc++;
+        }
+        sc->cls[b] = (u8)found;
+    }
+    sc->numClasses = nc;
+    for (int i = 0; i < nc; i++) for (int j = 0; j < nc; j++) {
+        sc->subC[i * LZB_MAX_CLASSES + j] = sub[rep[i] * 256 + rep[j]];
+        sc->msubC[i * LZB_MAX_CLASSES + j] = msub[rep[i] * 256 + rep[j]];
+    }
+    sc->gapOpen = go; sc->gapExtend = ge;
+    CUDA_TRY(cudaMemcpyAsync(c->d_sc, sc, sizeof *sc, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->haveScoring = true;
+    return 0;
+}
+
+/* K0: ASCII -> class codes, 16 bytes per thread (128-bit loads/stores) */
+__global__ void k_classify(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n16,
+                           const lzb_scoring_dev* __restrict__ sc) {
+    __shared__ u8 lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = sc->cls[i];
+    __syncthreads();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v = in[i]; u32 w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 x = w[k];
+            w[k] = (u32)lut[x & 255] | ((u32)lut[(x >> 8) & 255] << 8) | ((u32)lut[(x >> 16) & 255] << 16) | ((u32)lut[x >> 24] << 24);
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+/* copies len bytes (+ NUL + zero pad to 16) to the device and derives the class-code copy */
+int lzb_upload_classes(lzb_ctx* c, const u8* h_seq, u32 len, u8** d_seq, u8** d_cls) {
+    if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
+    size_t padded = (((size_t)len + 1 + 15) / 16) * 16 + 16;
+    CUDA_TRY(cudaMalloc(d_seq, padded));
+    CUDA_TRY(cudaMalloc(d_cls, padded));
+    CUDA_TRY(cudaMemsetAsync(*d_seq, 0, padded, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(*d_seq, h_seq, len, cudaMemcpyHostToDevice, c->stream));
+    size_t n16 = padded / 16;
+    int blocks = (int)((n16 + 255) / 256); if (blocks > c->smCount * 8) blocks = c->smCount * 8;
+    k_classify<<<blocks, 256, 0, c->stream>>>((const uint4*)*d_seq, (uint4*)*d_cls, n16, c->d_sc);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" lzb_query* lzb_query_load(lzb_ctx* c, const uint8_t* seq2, uint32_t len2) {
+    cudaSetDevice(c->device);
+    lzb_query* q = (lzb_query*)calloc(1, sizeof *q);
+    q->ctx = c; q->len = len2;
+    q->h_seq = (u8*)malloc((size_t)len2 + 1); memcpy(q->h_seq, seq2, len2); q->h_seq[len2] = 0;
+    if (lzb_upload_classes(c, q->h_seq, len2, &q->d_seq, &q->d_cls)) { free(q->h_seq); free(q); return NULL; }
+    return q;
+}
+
+extern "C" void lzb_query_free(lzb_query* q) {
+    if (!q) return;
+    cudaSetDevice(q->ctx->device);
+    cudaStreamSynchronize(q->ctx->stream);
+    cudaFree(q->d_seq); cudaFree(q->d_cls); free(q->h_seq); free(q);
+}

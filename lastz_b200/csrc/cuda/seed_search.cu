@@ -1,0 +1,477 @@
+/*
+ * seed_search.cu -- K2/K3: seed-hit enumeration, diagonal-hash filtering and x-drop extension.
+ *
+ * Replaces seed_hit_search / private_hit_search / find_table_matches (seed_search.c:322, :464,
+ * :810), the default hit processor process_for_simple_hit (:1056) with the diag-hash protocol of
+ * diag_hash.h:61-101, xdrop_extend_seed_hit (:2528) and the collect_hsps reporter
+ * (lastz.c:3991).
+ *
+ * The reference handles hits one at a time in discovery order (query position up, seed variant,
+ * target position down) and threads every hit through diagEnd[(pos1-pos2) & 0xFFFF].  That state
+ * is the ONLY coupling between hits, and it couples only hits in the same bucket.  So:
+ *
+ *   k_query_words   pack the seed word at every query position                    (hot loop B)
+ *   k_count_hits    hits per 1024 query positions -> host cuts the query into chunks that fit
+ *   per chunk:
+ *     k_slot_count  hits per (position, variant) slot; cub exclusive scan
+ *     k_expand      CSR lists -> (pos1,pos2) records in discovery order, key = bucket  (loop C)
+ *     cub radix sort on the bucket bits, STABLE => each bucket keeps discovery order
+ *     k_bucket_bounds
+ *     k_extend      one warp per bucket: 32 hits at a time; right x-drop scans in parallel (they
+ *                   do not depend on the bucket state), a 32-step register walk that replays the
+ *                   diagEnd test/update exactly, then left scans for the surviving hits (loop D)
+ *
+ * diagEnd persists in HBM across chunks.  HSP candidates come back with the integer match counts
+ * the entropy factor needs; the double/libm part of entropy (dna_utilities.c:2926-2936) and the
+ * final ordering are O(#HSPs) host work in lzb_seed_hit_search.
+ */
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "lzb_cuda.h"
+
+#define POS_PER_BLOCK 1024            /* granularity of the chunk planner */
+#define MAX_VARIANTS 512
+
+struct ctb_dev2 { int8_t v[256]; };
+
+struct sp_dev {
+    u32 qstart, qend, len1, len2;
+    int L, V, hashBits;
+    int selfCompare, sameStrand;
+    s32 xDrop, K;
+    int gfExtend, plain, entropy;
+};
+
+struct cand_rec {                      /* one HSP candidate, 40 bytes */
+    u32 hit1, hit2;                    /* the seed hit (one past its end) that produced it */
+    u32 pos1, pos2, length;            /* HSP start + length */
+    s32 score;
+    u32 cA, cC, cG, cT;                /* exact-match counts by base (entropy) */
+};
+
+struct search_counters {
+    unsigned long long words, extensions, bpExtended, ncand, overflow;
+};
+
+/* ---- K2a: the packed seed word at every query position (invalid => 0xFFFFFFFF) ---- */
+__global__ void k_query_words(const u8* __restrict__ seq, sp_dev P, seed_dev sd, ctb_dev2 ctb,
+                              u32* __restrict__ qword, search_counters* cnt) {
+    u32 n = P.qend - P.qstart;
+    unsigned long long valid = 0;
+    for (u64 k = blockIdx.x * (u64)blockDim.x + threadIdx.x; k < n; k += (u64)gridDim.x * blockDim.x) {
+        u32 i = P.qstart + (u32)k;                 /* index of the last base of the window */
+        u32 word = 0xFFFFFFFFu;
+        if (i + 1 >= P.qstart + (u32)sd.length) {
+            u64 w = 0; bool ok = true;
+            u32 first = i + 1 - (u32)sd.length;
+            for (int j = 0; j < sd.length; j++) {
+                int b = ctb.v[seq[first + j]];
+                ok = ok && (b >= 0);
+                w = (w << 2) | (u64)(b & 3);
+            }
+            if (ok) {
+                word = 0;
+                for (int p = 0; p < sd.numParts; p++) word |= (u32)(w >> sd.shift[p]) & sd.mask[p];
+                valid++;
+            }
+        }
+        qword[k] = word;
+    }
+    valid = __reduce_add_sync(0xFFFFFFFFu, (unsigned)valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&cnt->words, valid);
+}
+
+/* the part of a word's position list a hit at pos2 may use.  Lists are in decreasing position
+ * order; --self keeps only positions below a limit (seed_hit_below_diagonal seed_search.c:2182),
+ * i.e. a suffix of the list, found by binary search. */
+__device__ __forceinline__ void list_range(const u32* __restrict__ off, const u32* __restrict__ pos,
+                                           u32 key, u32 pos2, const sp_dev& P, u32& lo, u32& n) {
+    u32 a = off[key], b = off[key + 1];
+    if (P.selfCompare && b > a) {
+        s64 limit = P.sameStrand ? (s64)pos2 : (s64)P.len2 - 1 - (s64)pos2 + 2 * (s64)P.L;
+        u32 x = a, y = b;                           /* first index whose position < limit */
+        while (x < y) { u32 m = (x + y) >> 1; if ((s64)pos[m] < limit) y = m; else x = m + 1; }
+        a = x;
+    }
+    lo = a; n = b - a;
+}
+
+/* ---- K2b: hits per POS_PER_BLOCK query positions (for the chunk planner) ---- */
+__global__ void k_count_hits(const u32* __restrict__ qword, const u32* __restrict__ off,
+                             const u32* __restrict__ pos, const u32* __restrict__ flips, sp_dev P,
+                             unsigned long long* __restrict__ blkcnt) {
+    u32 n = P.qend - P.qstart;
+    u32 base = blockIdx.x * POS_PER_BLOCK;
+    unsigned long long mine = 0;
+    for (u32 k = base + threadIdx.x; k < base + POS_PER_BLOCK && k < n; k += blockDim.x) {
+        u32 w = qword[k];
+        if (w == 0xFFFFFFFFu) continue;
+        u32 pos2 = P.qstart + k + 1;
+        for (int v = 0; v < P.V; v++) { u32 lo, c; list_range(off, pos, w ^ flips[v], pos2, P, lo, c); mine += c; }
+    }
+    typedef cub::BlockReduce<unsigned long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    unsigned long long tot = BR(tmp).Sum(mine);
+    if (threadIdx.x == 0) blkcnt[blockIdx.x] = tot;
+}
+
+/* ---- K2c: hits per slot inside one chunk; slot = (k - k0) * V + v ---- */
+__global__ void k_slot_count(const u32* __restrict__ qword, const u32* __restrict__ off,
+                             const u32* __restrict__ pos, const u32* __restrict__ flips, sp_dev P,
+                             u32 k0, u32 nslots, u32* __restrict__ slotcnt) {
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+        u32 k = k0 + s / (u32)P.V; int v = (int)(s % (u32)P.V);
+        u32 w = qword[k], c = 0;
+        if (w != 0xFFFFFFFFu) { u32 lo; list_range(off, pos, w ^ flips[v], P.qstart + k + 1, P, lo, c); }
+        slotcnt[s] = c;
+    }
+}
+
+/* ---- K2d: expand the CSR lists into hit records, in discovery order ----
+ * A warp owns 32 consecutive slots and copies their lists as one concatenated array, so lanes
+ * stay busy whatever the individual list lengths are.  key = diag-hash bucket. */
+__global__ void k_expand(const u32* __restrict__ qword, const u32* __restrict__ off,
+                         const u32* __restrict__ pos, const u32* __restrict__ flips, sp_dev P,
+                         u32 k0, u32 nslots, const u32* __restrict__ slotoff,
+                         u32* __restrict__ keys, u64* __restrict__ vals) {
+    const u32 lane = threadIdx.x & 31;
+    const u32 hmask = (1u << P.hashBits) - 1;
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 s0 = warp * 32; s0 < nslots; s0 += nwarps * 32) {
+        u32 s = s0 + lane;
+        u32 base = 0, lo = 0, pos2 = 0, c = 0;
+        if (s < nslots) {
+            u32 k = k0 + s / (u32)P.V; int v = (int)(s % (u32)P.V);
+            u32 w = qword[k];
+            pos2 = P.qstart + k + 1;
+            base = slotoff[s];
+            if (w != 0xFFFFFFFFu) list_range(off, pos, w ^ flips[v], pos2, P, lo, c);
+        }
+        u32 wbase = __shfl_sync(0xFFFFFFFFu, base, 0);
+        u32 last = min(s0 + 31, nslots - 1) - s0;
+        u32 total = __shfl_sync(0xFFFFFFFFu, base + c, last) - wbase;
+        u32 rel = (s < nslots) ? base - wbase : 0xFFFFFFFFu;   /* start of my list in the warp's array */
+        for (u32 t = lane; t < ((total + 31) & ~31u); t += 32) {
+            /* owner = last lane whose rel <= t (rel is non-decreasing over lanes) */
+            u32 owner = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                u32 cand = owner + step;
+                u32 r = __shfl_sync(0xFFFFFFFFu, rel, cand & 31);
+                if (cand < 32 && r <= t) owner = cand;
+            }
+            u32 orel = __shfl_sync(0xFFFFFFFFu, rel, owner);
+            u32 olo  = __shfl_sync(0xFFFFFFFFu, lo, owner);
+            u32 op2  = __shfl_sync(0xFFFFFFFFu, pos2, owner);
+            if (t < total) {
+                u32 p1 = pos[olo + (t - orel)];
+                keys[wbase + t] = (p1 - op2) & hmask;
+                vals[wbase + t] = ((u64)op2 << 32) | p1;
+            }
+        }
+    }
+}
+
+/* ---- K3a: first record of every bucket in the sorted array ---- */
+__global__ void k_bucket_bounds(const u32* __restrict__ keys, u32 nhits, u32 nbuckets, u32* __restrict__ bstart) {
+    for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h <= nbuckets; h += gridDim.x * blockDim.x) {
+        u32 x = 0, y = nhits;                       /* lower_bound(keys, h) */
+        while (x < y) { u32 m = (x + y) >> 1; if (keys[m] < h) x = m + 1; else y = m; }
+        bstart[h] = x;
+    }
+}
+
+/* ---- K3b: replay each bucket in discovery order; x-drop extension ---- */
+__global__ void __launch_bounds__(256)
+k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuckets,
+         const u8* __restrict__ cls1, const u8* __restrict__ cls2,
+         const u8* __restrict__ asc1, const u8* __restrict__ asc2,
+         const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32* __restrict__ diagEnd,
+         cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt) {
+    __shared__ s32 msub[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
+    for (int i = threadIdx.x; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += blockDim.x) msub[i] = sc->msubC[i];
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    const u32 L = (u32)P.L;
+    u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long nExt = 0, nBp = 0;
+    for (u32 h = warp; h < nbuckets; h += nwarps) {
+        u32 b0 = bstart[h], b1 = bstart[h + 1];
+        if (b0 == b1) continue;
+        u32 E = diagEnd[h];
+        for (u32 base = b0; base < b1; base += 32) {
+            u32 idx = base + lane;
+            bool have = idx < b1;
+            u64 rec = have ? hits[idx] : 0;
+            u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
+            s64 diag = (s64)pos1 - (s64)pos2;
+            if (P.plain) {                          /* process_for_plain_hit seed_search.c:995 */
+                if (have) {
+                    u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+                    if (slot < candCap) { cand_rec r = { pos1, pos2, pos1 - L, pos2 - L, L, 0, 0, 0, 0, 0 }; cand[slot] = r; }
+                }
+                continue;
+            }
+            /* right scan (seed_search.c:2663-2693): independent of the bucket state.  Hits the
+             * bucket has already passed (diagEnd only grows) are skipped outright. */
+            bool maybe = have && !(E > pos2 - L);
+            u32 rightStop = pos1, rightBlock = pos1; s32 rightScore = 0;
+            if (maybe && P.gfExtend == LZB_GFEX_XDROP) {
+                s64 lim = (s64)P.len2 + diag;
+                u32 rstop = ((s64)P.len1 <= lim) ? P.len1 : (u32)lim;
+                u32 a = pos1, b = pos2; s32 run = 0;
+                while (a < rstop && run >= rightScore - P.xDrop) {
+                    run += msub[cls1[a] * LZB_MAX_CLASSES + cls2[b]];
+                    a++; b++;
+                    if (run > rightScore) { rightStop = a; rightScore = run; }
+                }
+                rightBlock = a;
+            }
+            u32 ext = (P.gfExtend == LZB_GFEX_XDROP) ? (u32)((s64)rightBlock - diag) : pos2;
+            /* replay process_for_simple_hit's test/update (seed_search.c:1113, :2785-2789) in
+             * discovery order: lane k sees the bucket exactly as hit k would have */
+            bool live = false; u32 myStop = 0;
+            u32 active = __ballot_sync(0xFFFFFFFFu, maybe);
+            while (active) {
+                int k = __ffs(active) - 1; active &= active - 1;
+                u32 p2 = __shfl_sync(0xFFFFFFFFu, pos2, k);
+                u32 ex = __shfl_sync(0xFFFFFFFFu, ext, k);
+                bool lv = !(E > p2 - L);
+                if ((int)lane == k) { live = lv; myStop = E; }
+                if (lv && ex > E) E = ex;
+            }
+            if (!live) continue;
+            if (P.gfExtend != LZB_GFEX_XDROP) {     /* --nogfextend with gapped stage: raw hit, score 0 */
+                u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+                if (slot < candCap) { cand_rec r = { pos1, pos2, pos1 - L, pos2 - L, L, 0, 0, 0, 0, 0 }; cand[slot] = r; }
+                continue;
+            }
+            /* left scan (seed_search.c:2598-2632), blocked by the bucket's previous extent */
+            s64 blk = (s64)myStop + diag;
+            u32 stop = blk > 0 ? (u32)blk : 0;
+            u32 a = pos1, b = pos2, leftStart = pos1; s32 run = 0, leftScore = 0;
+            while (a > stop && run >= leftScore - P.xDrop) {
+                a--; b--;
+                run += msub[cls1[a] * LZB_MAX_CLASSES + cls2[b]];
+                if (run > leftScore) { leftStart = a; leftScore = run; }
+            }
+            nExt++; nBp += rightBlock - a;
+            s32 sim = leftScore + rightScore;
+            if (sim < P.K) continue;                /* entropy can only lower the score */
+            cand_rec r;
+            r.hit1 = pos1; r.hit2 = pos2; r.pos1 = leftStart; r.pos2 = (u32)((s64)leftStart - diag);
+            r.length = rightStop - leftStart; r.score = sim; r.cA = r.cC = r.cG = r.cT = 0;
+            if (P.entropy && sim <= 3 * P.K) {      /* match counts for entropy(), dna_utilities.c:2905-2915 */
+                for (u32 i = 0; i < r.length; i++) {
+                    u8 x = asc1[r.pos1 + i];
+                    if (x == asc2[r.pos2 + i]) { r.cA += x == 'A'; r.cC += x == 'C'; r.cG += x == 'G'; r.cT += x == 'T'; }
+                }
+            }
+            u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+            if (slot < candCap) cand[slot] = r;
+        }
+        if (lane == 0) diagEnd[h] = E;
+    }
+    nExt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)nExt);
+    unsigned long long bpw = nBp;
+    for (int o = 16; o > 0; o >>= 1) bpw += __shfl_down_sync(0xFFFFFFFFu, bpw, o);
+    if (lane == 0) { if (nExt) atomicAdd(&cnt->extensions, nExt); if (bpw) atomicAdd(&cnt->bpExtended, bpw); }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+
+static inline u32 host_pack(const lzb_seed* sd, u64 w) {
+    u32 p = 0;
+    for (int i = 0; i < sd->numParts; i++) p |= (u32)(w >> sd->shift[i]) & sd->mask[i];
+    return p;
+}
+static u32 host_word_at(const u8* v, u32 endPos, const lzb_seed* sd, const int8_t* ctb) {
+    u64 w = 0;
+    for (int j = 0; j < sd->length; j++) w = (w << 2) | (u64)(ctb[v[endPos - sd->length + j]] & 3);
+    return host_pack(sd, w);
+}
+
+struct ev_pair { cudaEvent_t a, b; int which; };
+
+extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed* seed,
+                                   const int8_t ctb[256], const lzb_seed_params* prm,
+                                   lzb_segment** segs, uint64_t* nsegs, lzb_seed_stats* stats) {
+    cudaSetDevice(c->device);
+    if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
+    u32 qstart = prm->start, qend = prm->end ? prm->end : q->len;
+    if (qend <= qstart) return lzb_fail("in seed_hit_search(), interval is void (%u-%u)", qstart, qend);
+    if (qend > q->len) return lzb_fail("in seed_hit_search(), interval end is bad (%u>%u)", qend, q->len);
+    if (seed->length < 2) return lzb_fail("seed length must be at least two (yours is %d)", seed->length);
+    if (seed->weight != t->wordBits || seed->length != t->seedLength)
+        return lzb_fail("the seed does not match the one the target index was built with");
+    int hashBits = prm->hashBits ? prm->hashBits : 16;
+    if (hashBits < 4 || hashBits > 26) return lzb_fail("diag hash size 2^%d is not supported", hashBits);
+    *segs = NULL; *nsegs = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    cudaStream_t st = c->stream;
+
+    /* seed variants in probing order (seed_search.c:522-549) */
+    std::vector<u32> flips; flips.push_back(0);
+    if (seed->withTrans == 1) for (int f = 0; f < seed->numFlips; f++) flips.push_back(seed->transFlips[f]);
+    else if (seed->withTrans >= 2)
+        for (int f = 0; f < seed->numFlips; f++) {
+            flips.push_back(seed->transFlips[f]);
+            for (int g = f + 1; g < seed->numFlips; g++) flips.push_back(seed->transFlips[f] ^ seed->transFlips[g]);
+        }
+    if (flips.size() > MAX_VARIANTS) return lzb_fail("too many seed variants (%zu)", flips.size());
+    sp_dev P; memset(&P, 0, sizeof P);
+    P.qstart = qstart; P.qend = qend; P.len1 = t->len; P.len2 = q->len; P.L = seed->length; P.V = (int)flips.size();
+    P.hashBits = hashBits; P.selfCompare = prm->selfCompare; P.sameStrand = prm->sameStrand;
+    P.xDrop = prm->xDrop; P.K = prm->hspThreshold; P.gfExtend = prm->gfExtend; P.plain = prm->plainHits; P.entropy = prm->entropy;
+    seed_dev sd; seed_to_dev(&sd, seed);
+    ctb_dev2 cd; memcpy(cd.v, ctb, 256);
+
+    u32 n = qend - qstart;
+    u32 nblk = (n + POS_PER_BLOCK - 1) / POS_PER_BLOCK;
+    u32 nbuckets = 1u << hashBits;
+    u32 *d_qword = NULL, *d_flips = NULL, *d_E = NULL, *d_bstart = NULL;
+    unsigned long long* d_blkcnt = NULL; search_counters* d_cnt = NULL;
+    std::vector<ev_pair> evs;
+    cudaEvent_t evBegin, evEnd;
+    CUDA_TRY(cudaEventCreate(&evBegin)); CUDA_TRY(cudaEventCreate(&evEnd));
+    CUDA_TRY(cudaMalloc(&d_qword, (size_t)n * 4 + 16));
+    CUDA_TRY(cudaMalloc(&d_flips, flips.size() * 4));
+    CUDA_TRY(cudaMalloc(&d_blkcnt, (size_t)nblk * 8));
+    CUDA_TRY(cudaMalloc(&d_cnt, sizeof(search_counters)));
+    CUDA_TRY(cudaMalloc(&d_E, (size_t)nbuckets * 4));
+    CUDA_TRY(cudaMalloc(&d_bstart, ((size_t)nbuckets + 2) * 4));
+    CUDA_TRY(cudaMemcpyAsync(d_flips, flips.data(), flips.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(search_counters), st));
+    CUDA_TRY(cudaMemsetAsync(d_E, 0, (size_t)nbuckets * 4, st));        /* empty_diag_hash diag_hash.c:125 */
+    CUDA_TRY(cudaEventRecord(evBegin, st));
+    int grid = c->smCount * 8;
+#define TIMED(which_, launch_)                                                          \
+    do { ev_pair e_; e_.which = (which_); cudaEventCreate(&e_.a); cudaEventCreate(&e_.b); \
+         cudaEventRecord(e_.a, st); launch_; cudaEventRecord(e_.b, st); evs.push_back(e_); \
+         c->launches++; } while (0)
+    TIMED(0, (k_query_words<<<grid, 256, 0, st>>>(q->d_seq, P, sd, cd, d_qword, d_cnt)));
+    TIMED(1, (k_count_hits<<<nblk, 256, 0, st>>>(d_qword, t->d_off, t->d_pos, d_flips, P, d_blkcnt)));
+    CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned long long> blkcnt(nblk);
+    CUDA_TRY(cudaMemcpyAsync(blkcnt.data(), d_blkcnt, (size_t)nblk * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    u64 totalHits = 0, maxBlk = 0;
+    for (u32 b = 0; b < nblk; b++) { totalHits += blkcnt[b]; if (blkcnt[b] > maxBlk) maxBlk = blkcnt[b]; }
+
+    const char* capEnv = getenv("LZB_HIT_CAP");
+    u64 hitCap = capEnv ? strtoull(capEnv, 0, 10) : (1ull << 27);
+    if (hitCap > 0xFFFFFFF0ull) hitCap = 0xFFFFFFF0ull;
+    if (maxBlk > hitCap) hitCap = maxBlk;
+    if (hitCap > 0xFFFFFFF0ull) return lzb_fail("%llu seed hits within %d query positions; use --step or mask repeats", (unsigned long long)maxBlk, POS_PER_BLOCK);
+    if (totalHits < hitCap) hitCap = totalHits ? totalHits : 1;
+    u64 slotCap = 1ull << 26;
+    { u64 allSlots = (u64)nblk * POS_PER_BLOCK * P.V; if (allSlots < slotCap) slotCap = allSlots; }
+    if (slotCap < (u64)POS_PER_BLOCK * P.V) slotCap = (u64)POS_PER_BLOCK * P.V;
+    u32 candCap = prm->plainHits || prm->gfExtend != LZB_GFEX_XDROP ? (u32)std::min<u64>(totalHits + 1, 1ull << 26) : (1u << 22);
+
+    u32 *d_slotcnt = NULL, *d_slotoff = NULL, *keysA = NULL, *keysB = NULL; u64 *valsA = NULL, *valsB = NULL;
+    cand_rec* d_cand = NULL; void* d_tmp = NULL; size_t tmpBytes = 0, tmpScan = 0;
+    CUDA_TRY(cudaMalloc(&d_slotcnt, (slotCap + 2) * 4)); CUDA_TRY(cudaMalloc(&d_slotoff, (slotCap + 2) * 4));
+    CUDA_TRY(cudaMalloc(&keysA, hitCap * 4)); CUDA_TRY(cudaMalloc(&keysB, hitCap * 4));
+    CUDA_TRY(cudaMalloc(&valsA, hitCap * 8)); CUDA_TRY(cudaMalloc(&valsB, hitCap * 8));
+    CUDA_TRY(cudaMalloc(&d_cand, (size_t)candCap * sizeof(cand_rec)));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(NULL, tmpBytes, keysA, keysB, valsA, valsB, hitCap, 0, hashBits, st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmpScan, d_slotcnt, d_slotoff, slotCap + 1, st));
+    if (tmpScan > tmpBytes) tmpBytes = tmpScan;
+    CUDA_TRY(cudaMalloc(&d_tmp, tmpBytes));
+
+    /* chunk loop */
+    u64 chunks = 0;
+    for (u32 b0 = 0; b0 < nblk;) {
+        u64 h = 0; u32 b1 = b0;
+        while (b1 < nblk && h + blkcnt[b1] <= hitCap && (u64)(b1 + 1 - b0) * POS_PER_BLOCK * P.V <= slotCap) { h += blkcnt[b1]; b1++; }
+        if (b1 == b0) return lzb_fail("internal error: seed-hit chunk planner made no progress");
+        u32 k0 = b0 * POS_PER_BLOCK, k1 = std::min<u64>((u64)b1 * POS_PER_BLOCK, n);
+        if (h > 0) {
+            u32 nslots = (k1 - k0) * (u32)P.V, nh = (u32)h;
+            size_t tb = tmpBytes;
+            TIMED(2, (k_slot_count<<<grid, 256, 0, st>>>(d_qword, t->d_off, t->d_pos, d_flips, P, k0, nslots, d_slotcnt)));
+            TIMED(3, cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_slotcnt, d_slotoff, nslots + 1, st));
+            TIMED(4, (k_expand<<<grid, 256, 0, st>>>(d_qword, t->d_off, t->d_pos, d_flips, P, k0, nslots, d_slotoff, keysA, valsA)));
+            tb = tmpBytes;
+            TIMED(5, cub::DeviceRadixSort::SortPairs(d_tmp, tb, keysA, keysB, valsA, valsB, nh, 0, hashBits, st));
+            TIMED(6, (k_bucket_bounds<<<(nbuckets + 256) / 256, 256, 0, st>>>(keysB, nh, nbuckets, d_bstart)));
+            TIMED(7, (k_extend<<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
+                                                     c->d_sc, P, d_E, d_cand, candCap, d_cnt)));
+            CUDA_TRY(cudaGetLastError());
+            chunks++;
+        }
+        b0 = b1;
+    }
+    CUDA_TRY(cudaEventRecord(evEnd, st));
+    search_counters hc;
+    CUDA_TRY(cudaMemcpyAsync(&hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (hc.ncand > candCap) {
+        lzb_fail("%llu HSP candidates exceed the %u-entry result buffer; raise the threshold (--hspthresh)", hc.ncand, candCap);
+        goto cleanup_fail;
+    }
+    {
+        std::vector<cand_rec> cand(hc.ncand);
+        if (hc.ncand) CUDA_TRY(cudaMemcpy(cand.data(), d_cand, (size_t)hc.ncand * sizeof(cand_rec), cudaMemcpyDeviceToHost));
+        /* discovery order = (query position, variant index, target position descending) */
+        struct keyed { u32 hit2; u32 variant; u32 hit1; u32 ix; };
+        std::vector<keyed> order(cand.size());
+        for (size_t i = 0; i < cand.size(); i++) {
+            u32 qw = host_word_at(q->h_seq, cand[i].hit2, seed, ctb), tw = host_word_at(t->h_seq, cand[i].hit1, seed, ctb);
+            u32 x = qw ^ tw, v = 0;
+            for (; v < flips.size(); v++) if (flips[v] == x) break;
+            order[i] = { cand[i].hit2, v, cand[i].hit1, (u32)i };
+        }
+        std::sort(order.begin(), order.end(), [](const keyed& a, const keyed& b) {
+            if (a.hit2 != b.hit2) return a.hit2 < b.hit2;
+            if (a.variant != b.variant) return a.variant < b.variant;
+            return a.hit1 > b.hit1;
+        });
+        lzb_segment* out = (lzb_segment*)malloc((cand.size() + 1) * sizeof(lzb_segment));
+        u64 m = 0;
+        for (size_t i = 0; i < order.size(); i++) {
+            const cand_rec& r = cand[order[i].ix];
+            s32 sim = r.score;
+            if (!prm->plainHits && prm->gfExtend == LZB_GFEX_XDROP && prm->entropy &&
+                sim >= prm->hspThreshold && sim <= 3 * prm->hspThreshold) {
+                /* entropy() dna_utilities.c:2918-2936 on the device's integer counts */
+                double qf = 1.0;
+                if (r.cA + r.cC + r.cG + r.cT >= 20) {
+                    double len = (double)(int)r.length;
+                    double pA = (double)(int)r.cA / len, pC = (double)(int)r.cC / len, pG = (double)(int)r.cG / len, pT = (double)(int)r.cT / len;
+                    double qA = r.cA ? log(pA) : 0.0, qC = r.cC ? log(pC) : 0.0, qG = r.cG ? log(pG) : 0.0, qT = r.cT ? log(pT) : 0.0;
+                    qf = -(pA * qA + pC * qC + pG * qG + pT * qT) / log(4.0);
+                }
+                sim = (s32)((double)sim * qf);
+                if (sim < prm->hspThreshold) continue;
+            }
+            lzb_segment* g = &out[m++];
+            memset(g, 0, sizeof *g);
+            g->pos1 = r.pos1; g->pos2 = r.pos2; g->length = r.length; g->s = sim; g->id = prm->strandId; g->scoreCov = r.length;
+        }
+        *segs = out; *nsegs = m;
+        if (stats) {
+            stats->wordsInQuery = hc.words; stats->rawSeedHits = totalHits; stats->extensions = hc.extensions;
+            stats->bpExtended = hc.bpExtended; stats->hsps = m;
+            float ms = 0; cudaEventElapsedTime(&ms, evBegin, evEnd); stats->seconds = ms / 1e3;
+            for (auto& e : evs) { float x = 0; cudaEventElapsedTime(&x, e.a, e.b); stats->kernelSeconds[e.which] += x / 1e3; }
+        }
+    }
+    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaEventDestroy(evBegin); cudaEventDestroy(evEnd);
+    cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
+    cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
+    cudaFree(d_cand); cudaFree(d_tmp);
+    return 0;
+cleanup_fail:
+    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
+    cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
+    cudaFree(d_cand); cudaFree(d_tmp);
+    return -1;
+}

@@ -1,0 +1,59 @@
+"""The oracle (CPU restatement + host front end) against the reference's own golden files.
+
+These are the reference's `make test` / `make base_tests` cases that pin the hot path
+(src/Makefile:208-217, :295, :306, :329, :384, :465); fixtures copied verbatim from test_data/.
+"""
+import os
+
+import pytest
+
+from conftest import GOLDEN, ORACLE_CLI, REF_CLI, lav_body, run_cli
+
+CAT = os.path.join(GOLDEN, "pseudocat.fa")
+PIG = os.path.join(GOLDEN, "pseudopig.fa")
+
+CASES = [
+    ("base_test.default.lav", []),                                                  # Makefile:208
+    ("base_test.hits.lav", ["W=8", "T=0", "--plus", "--nogfextend", "--nogapped"]),  # Makefile:295
+    ("base_test.hsp.lav", ["C=3", "W=8", "T=0"]),                                    # Makefile:306
+    ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),                        # Makefile:465
+]
+
+
+@pytest.mark.parametrize("golden,opts", CASES)
+def test_oracle_reproduces_golden_lav(golden, opts):
+    out, _ = run_cli(ORACLE_CLI, [CAT, PIG] + opts)
+    want = open(os.path.join(GOLDEN, golden)).read()
+    # paths differ (../test_data/...), the comparator strips them the same way lav_compare.py does
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(want)
+
+
+def test_oracle_segments_round_trip(tmp_path):
+    """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
+    segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
+    f = tmp_path / "hsps.segments"
+    f.write_text(segs)
+    out, _ = run_cli(ORACLE_CLI, [CAT, PIG, f"--segments={f}"])
+    want = open(os.path.join(GOLDEN, "base_test.default.lav")).read()
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(want)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("size,opts", [
+    (200000, []),
+    (200000, ["--nogapped", "--format=segments"]),
+    (300000, ["--allocate:traceback=2M"]),       # forces truncation + many bounded alignments
+    (200000, ["--seed=14of22", "--notransition", "--step=3"]),
+    (200000, ["--transition=2", "--hspthresh=2500", "--noentropy"]),
+    (200000, ["--ydrop=4000", "--gappedthresh=5000", "--xdrop=400"]),
+])
+def test_oracle_matches_reference_on_synthetic(synth, size, opts):
+    t, q = synth(size)
+    got, _ = run_cli(ORACLE_CLI, [t, q] + opts)
+    want, _ = run_cli(REF_CLI, [t, q] + opts)
+    if "--format=segments" in opts:
+        assert got == want
+    else:
+        assert lav_body(got) == lav_body(want)
