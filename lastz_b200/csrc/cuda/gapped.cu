@@ -1,6 +1,926 @@
-/* gapped.cu -- placeholder until the Y-drop kernels land (next commit) */
+/*
+ * gapped.cu -- K4/K5: anchor peaks, Y-drop banded gapped DP with traceback, and the
+ * best-score-first anchor loop.
+ *
+ * Replaces reduce_to_points / segment_peak (gapped_extend.c:463, :515), gapped_extend (:1012),
+ * ydrop_align (:2459), ydrop_one_sided_align (:3388), update_LR_bounds (:4588),
+ * update_active_segs (:4885) and format_alignment (:5153).
+ *
+ * DP kernel (k_ydrop): one warp per one-sided alignment, many alignments per launch.  A sweep row
+ * lives in shared memory (ring-indexed by column); the 32 lanes own contiguous column chunks.
+ * The reference visits a row left to right with three loop-carried values: the insertion score
+ * I, the running bestScore (which moves the prune threshold WITHIN the row) and the band edges.
+ * Here a row is three short passes joined by warp scans:
+ *   1. max-plus scan of the insertion chain I (affine maps x -> max(a, x - e), reset at cells
+ *      masked by earlier alignments),
+ *   2. cell values + traceback links, then an exclusive prefix-max of the cells that may raise
+ *      bestScore (diagonal winners) => the exact threshold each cell saw in the reference,
+ *   3. pruning against that threshold, band edges, new best / end cell.
+ * Pruned cells are kept out of the result exactly as in the reference: a pruned cell's score is
+ * below the threshold, the threshold never decreases, so anything derived from it stays below
+ * every later threshold and can neither survive nor be traced back through.
+ * One traceback byte per visited cell goes to HBM (the path's only unavoidable traffic); the
+ * same warp then walks it back 32 diagonal steps at a time and emits run-length edit ops.
+ *
+ * Anchor loop (host, C++): identical order and bookkeeping to the reference.  Because each
+ * alignment constrains later ones, anchors are extended SPECULATIVELY in batches against the
+ * alignments committed so far and committed strictly in score order; a speculative result is
+ * used only if no alignment committed after its launch overlaps the rows its DP examined,
+ * otherwise it is recomputed -- so the output equals the sequential algorithm's.
+ */
+#include <algorithm>
+#include <chrono>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
 #include "lzb_cuda.h"
-extern "C" int lzb_reduce_to_points(lzb_ctx*, lzb_target*, lzb_query*, lzb_segment*, uint64_t) { return lzb_fail("gapped stage not built yet"); }
-extern "C" int lzb_gapped_extend(lzb_ctx*, lzb_target*, lzb_query*, const uint8_t*, const uint8_t*, lzb_segment*, uint64_t,
-                                 const lzb_gapped_params*, lzb_alignel**, lzb_gapped_stats*) { return lzb_fail("gapped stage not built yet"); }
-extern "C" void lzb_free_align_list(lzb_alignel*) {}
+
+enum { SEG_DIAG = 0, SEG_HORZ = 1, SEG_VERT = 2 };
+
+struct dseg { u32 b1, b2, e1, e2; int type; };
+struct segref { int al, sg; };
+struct dalign {                       /* device view of a committed alignment (galign :214-245) */
+    u32 pos1, end1;
+    int segBegin, segCount;
+    segref left1, right1, left2, right2;
+    int next, prev;                   /* obi / oed links */
+};
+
+enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_ACT = 5 };
+
+struct dp_job {
+    int reversed; u32 a1, a2, M, N;
+    s32 L0, R0;
+    segref leftSeg, rightSeg;
+    int alignList;
+    u8* tb; u32 tbLen; u32* tbRow; u32 tbRowCap; u32* ops; u32 opsCap;
+    int* act; u32 actCap;             /* 5 ints per active segment */
+    /* results */
+    s32 score; u32 end1, end2, nops, rows; int status; unsigned long long cells;
+};
+
+struct xf { s32 A; s32 S; int r; };   /* x -> r ? A : max(A, x + S) */
+
+__device__ __forceinline__ s32 satadd(s32 a, s32 s) { s32 v = a + s; return v < LZB_NEG_INF ? LZB_NEG_INF : v; }
+__device__ __forceinline__ xf xf_then(xf f, xf g) {      /* apply f, then g */
+    xf o;
+    if (g.r) return g;
+    o.A = max(g.A, satadd(f.A, g.S)); o.S = f.S + g.S; o.r = f.r;
+    return o;
+}
+
+#define LINK_I 1
+#define LINK_D 2
+#define LINK_IEXT 4
+#define LINK_DEXT 8
+#define F_CAND 16
+#define F_MASK 32
+
+/* next_sweep_seg / prev_sweep_seg gapped_extend.c:4754-4853 */
+__device__ s32 sweep_step(const dalign* al, const dseg* segs, int rev, int lookRight, segref* bp,
+                          u32 row, u32 a1, u32 a2) {
+    const dalign m = al[bp->al];
+    if (!rev) {
+        if (bp->sg + 1 < m.segCount) {
+            bp->sg++;
+            if (segs[m.segBegin + bp->sg].type == SEG_HORZ) bp->sg++;
+            return (s32)(segs[m.segBegin + bp->sg].b2 - a2);
+        }
+        *bp = lookRight ? m.right2 : m.left2;
+        if (bp->al < 0) return 0;
+        const dseg s = segs[al[bp->al].segBegin + bp->sg];
+        if (s.type == SEG_DIAG) return (s32)row + (s32)(s.b2 - a2) - (s32)(s.b1 - a1);
+        return (s32)(s.b2 - a2);
+    }
+    if (bp->sg - 1 >= 0) {
+        bp->sg--;
+        if (segs[m.segBegin + bp->sg].type == SEG_HORZ) bp->sg--;
+        return (s32)(a2 - segs[m.segBegin + bp->sg].e2);
+    }
+    *bp = lookRight ? m.right1 : m.left1;
+    if (bp->al < 0) return 0;
+    const dseg s = segs[al[bp->al].segBegin + bp->sg];
+    if (s.type == SEG_DIAG) return (s32)row + (s32)(a2 - s.e2) - (s32)(a1 - s.e1);
+    return (s32)(a2 - s.e2);
+}
+
+/* build_active_seg gapped_extend.c:4989-5040; act record = {al, sg, x, lastRow, type} */
+__device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u32* stamp, u32 msk,
+                          u32 row, u32 a1, u32 a2, u32 LY, u32 RY) {
+    const dseg s = segs[al[a[0]].segBegin + a[1]];
+    a[4] = s.type;
+    u32 x, lastRow;
+    if (!rev) { x = s.b2 - a2; lastRow = s.e1 - a1; } else { x = a2 - s.e2; lastRow = a1 - s.b1; }
+    a[2] = (int)x; a[3] = (int)lastRow;
+    if (s.type != SEG_HORZ) { if (x >= LY && x <= RY) stamp[x & msk] = row; }
+    else {
+        u32 hend = !rev ? s.e2 - a2 : a2 - s.b2;
+        u32 lo = x > LY ? x : LY, hi = hend < RY ? hend : RY;
+        for (u32 i = lo; i <= hi && i >= lo; i++) stamp[i & msk] = row;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ segs,
+        const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
+        const lzb_scoring_dev* __restrict__ sc, s32 yDrop, int trim, u32 cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    s32* C0 = (s32*)smem_raw; s32* C1 = C0 + cap; s32* Dv = C1 + cap;
+    u32* stamp = (u32*)(Dv + cap); s32* subC = (s32*)(stamp + cap); u8* flg = (u8*)(subC + LZB_MAX_CLASSES * LZB_MAX_CLASSES);
+    const u32 msk = cap - 1;
+    const u32 lane = threadIdx.x;
+    const u32 FULL = 0xFFFFFFFFu;
+    dp_job* J = &jobs[blockIdx.x];
+    for (u32 i = lane; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += 32) subC[i] = sc->subC[i];
+    for (u32 i = lane; i < cap; i += 32) stamp[i] = 0;
+    const int rev = J->reversed; const u32 a1 = J->a1, a2 = J->a2, M = J->M, N = J->N;
+    const s32 gapE = sc->gapExtend, gapOE = sc->gapOpen + sc->gapExtend;
+    const u8 cls0 = sc->cls[0];
+    u8* tb = J->tb; const s64 tbLen = J->tbLen; u32* tbRow = J->tbRow;
+    int status = DP_OK;
+    s32 best = 0, bnd = LZB_NEG_INF; u32 end1 = 0, end2 = 0; int endIsBnd = 0;
+    unsigned long long cells = 0; u32 row = 0;
+    if (N == 0 || M == 0) {
+        if (lane == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; }
+        return;
+    }
+    s32 yTail = gapE != 0 ? yDrop / gapE + 6 : (N < 500000u ? (s32)N + 1 : 500000);
+    s32 L = J->L0, R = J->R0;
+    segref leftSeg = J->leftSeg, rightSeg = J->rightSeg;
+    int alignList = J->alignList;
+    int* act = J->act; int nact = 0;
+    s64 used = 0;
+    __syncwarp();
+    /* ---- first row, gapped_extend.c:3576-3591 ---- */
+    u32 LY = 0, RY;
+    {
+        /* C[0][c] = -(oe + (c-1)e); col c (>=1) exists iff c <= N and C[0][c-1] >= -yDrop */
+        u32 last = 1;                                  /* col 1 always exists when N >= 1 */
+        if (gapE > 0) { if (yDrop >= gapOE) last = (u32)(((s64)yDrop - gapOE) / gapE) + 2; }
+        else if (yDrop >= gapOE) last = N;
+        if (last > N) last = N;
+        if ((s64)last + 1 + yTail + 40 >= (s64)cap) status = DP_RING;
+        else {
+            for (u32 c = lane; c <= last; c += 32) {
+                s32 v = c == 0 ? 0 : -gapOE - (s32)(c - 1) * gapE;
+                C0[c & msk] = v; Dv[c & msk] = v - gapOE;
+                tb[c] = c == 0 ? 0 : LINK_I;
+            }
+            used = (s64)last + 1;
+        }
+        RY = last + 1;
+        if (lane == 0 && J->tbRowCap > 0) tbRow[0] = 0;
+    }
+    __syncwarp();
+    s32* Cprev = C0; s32* Ccur = C1;
+    if (status == DP_OK)
+    for (row = 1; row <= M; row++) {
+        u32 prevLY = LY;
+        /* ---- update_LR_bounds gapped_extend.c:4588-4724 (uniform across lanes) ---- */
+        if (!rev) {
+            if (leftSeg.al >= 0) {
+                const dseg s = segs[al[leftSeg.al].segBegin + leftSeg.sg];
+                if (s.e1 >= row + a1) { if (s.type == SEG_DIAG) L++; }
+                else L = sweep_step(al, segs, 0, 0, &leftSeg, row, a1, a2) + 1;
+            }
+            if (leftSeg.al >= 0) { if ((s32)LY < L) LY = (u32)L; }
+            if (rightSeg.al >= 0) {
+                const dseg s = segs[al[rightSeg.al].segBegin + rightSeg.sg];
+                if (s.e1 >= row + a1) { if (s.type == SEG_DIAG) R++; }
+                else R = sweep_step(al, segs, 0, 1, &rightSeg, row, a1, a2) - 1;
+            }
+            if (rightSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
+        } else {
+            if (rightSeg.al >= 0) {
+                const dseg s = segs[al[rightSeg.al].segBegin + rightSeg.sg];
+                if (s.b1 <= a1 - row) { if (s.type == SEG_DIAG) L++; }
+                else L = sweep_step(al, segs, 1, 1, &rightSeg, row, a1, a2) + 1;
+            }
+            if (rightSeg.al >= 0) { if ((s32)LY < L) LY = (u32)L; }
+            if (leftSeg.al >= 0) {
+                const dseg s = segs[al[leftSeg.al].segBegin + leftSeg.sg];
+                if (s.b1 <= a1 - row) { if (s.type == SEG_DIAG) R++; }
+                else R = sweep_step(al, segs, 1, 0, &leftSeg, row, a1, a2) - 1;
+            }
+            if (leftSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
+        }
+        if ((s64)(RY > prevLY ? RY - prevLY : 0) + yTail + 40 >= (s64)cap) { status = DP_RING; break; }
+        /* ---- update_active_segs gapped_extend.c:4885-4962 (lane 0; the list is tiny) ---- */
+        if (nact > 0 || alignList >= 0) {
+            if (lane == 0) {
+                for (int k = 0; k < nact; k++) {
+                    int* a = act + 5 * k;
+                    if ((u32)a[3] >= row) {
+                        if (a[4] == SEG_DIAG) a[2]++;
+                        u32 x = (u32)a[2];
+                        if (x >= LY && x <= RY) stamp[x & msk] = row;
+                    } else {
+                        int cnt = al[a[0]].segCount;
+                        bool more = !rev ? (a[1] + 1 < cnt) : (a[1] - 1 >= 0);
+                        if (more) {
+                            a[1] += !rev ? 1 : -1;
+                            act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
+                            if (a[4] == SEG_HORZ) { a[1] += !rev ? 1 : -1; act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY); }
+                        } else a[4] = -1;
+                    }
+                }
+                while (alignList >= 0) {
+                    const dalign x = al[alignList];
+                    if (!rev) { if (x.pos1 - a1 != row) break; } else { if (a1 - x.end1 != row) break; }
+                    if ((u32)nact >= J->actCap) { status = DP_ACT; break; }
+                    int* a = act + 5 * nact; nact++;
+                    a[0] = alignList; a[1] = !rev ? 0 : x.segCount - 1;
+                    act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
+                    alignList = !rev ? x.next : x.prev;
+                }
+                int w = 0;
+                for (int k = 0; k < nact; k++) if (act[5 * k + 4] >= 0) { if (w != k) for (int z = 0; z < 5; z++) act[5 * w + z] = act[5 * k + z]; w++; }
+                nact = w;
+            }
+            nact = __shfl_sync(FULL, nact, 0); alignList = __shfl_sync(FULL, alignList, 0); status = __shfl_sync(FULL, status, 0);
+            if (status != DP_OK) break;
+        }
+        __syncwarp();
+        /* ---- traceback capacity gapped_extend.c:3636-3662 ---- */
+        if (RY < LY) RY = LY;
+        s64 need = (s64)(RY - LY) + yTail;
+        if (used + need >= tbLen) { status = DP_TRUNCATED; break; }
+        if (row >= J->tbRowCap) { status = DP_TBROW; break; }
+        const u32 tbBase = (u32)((u64)used - (u64)LY);            /* tbRow[row], modulo 2^32 like the walk */
+        if (lane == 0) tbRow[row] = tbBase;
+        /* ---- the sweep, gapped_extend.c:3669-3774 ---- */
+        const u32 leftCol = LY;
+        const u32 colEnd = RY < N + 1 ? RY : N + 1;
+        const u32 width = colEnd > LY ? colEnd - LY : 0;
+        const u32 k = ((width + 31) / 32) | 1;
+        const u32 j0 = LY + lane * k;
+        const u32 j1 = (j0 + k < colEnd) ? j0 + k : colEnd;       /* may be <= j0: idle lane */
+        s64 ai = !rev ? (s64)a1 + row : (s64)a1 + 1 - (s64)row;
+        const u8 ac = (ai < 0 || ai >= (s64)len1) ? cls0 : cls1[ai];
+        const s32* subRow = subC + ac * LZB_MAX_CLASSES;
+        const bool masking = nact > 0;
+        /* pass 1: this lane's insertion-chain map */
+        xf mine; mine.A = LZB_NEG_INF; mine.S = 0; mine.r = 0;
+        {
+            s32 pc = (j0 > LY && j0 < colEnd) ? Cprev[(j0 - 1) & msk] : LZB_NEG_INF;
+            for (u32 j = j0; j < j1; j++) {
+                s64 bi = !rev ? (s64)a2 + j : (s64)a2 + 1 - (s64)j;
+                u8 bc = (bi < 0) ? cls0 : cls2[bi];
+                s32 diag = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];
+                pc = Cprev[j & msk];
+                s32 d = Dv[j & msk];
+                xf g;
+                if (masking && stamp[j & msk] == row) { g.A = LZB_NEG_INF; g.S = 0; g.r = 1; }
+                else { g.A = diag >= d ? satadd(diag, -gapOE) : LZB_NEG_INF; g.S = -gapE; g.r = 0; }
+                mine = xf_then(mine, g);
+            }
+        }
+        /* exclusive scan of the maps over lanes; I enters the row as -inf */
+        xf inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            xf up; up.A = __shfl_up_sync(FULL, inc.A, o); up.S = __shfl_up_sync(FULL, inc.S, o); up.r = __shfl_up_sync(FULL, inc.r, o);
+            if ((int)lane >= o) inc = xf_then(up, inc);
+        }
+        s32 Iin = __shfl_up_sync(FULL, inc.A, 1);
+        if (lane == 0) Iin = LZB_NEG_INF;
+        /* the value of I leaving the row's last cell */
+        s32 Iout = __shfl_sync(FULL, inc.A, 31);
+        /* pass 2: cell values, links, next row's D; candidates for bestScore */
+        s32 candMax = LZB_NEG_INF;
+        {
+            s32 I = Iin;
+            s32 pc = (j0 > LY && j0 < colEnd) ? Cprev[(j0 - 1) & msk] : LZB_NEG_INF;
+            for (u32 j = j0; j < j1; j++) {
+                s64 bi = !rev ? (s64)a2 + j : (s64)a2 + 1 - (s64)j;
+                u8 bc = (bi < 0) ? cls0 : cls2[bi];
+                s32 c = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];
+                pc = Cprev[j & msk];
+                s32 d = Dv[j & msk];
+                u32 f; s32 Dn, In;
+                if (masking && stamp[j & msk] == row) { f = F_MASK; c = LZB_NEG_INF; Dn = LZB_NEG_INF; In = LZB_NEG_INF; }
+                else if (d > c || I > c) {
+                    if (d >= I) { c = d; f = LINK_D | LINK_IEXT | LINK_DEXT; } else { c = I; f = LINK_I | LINK_IEXT | LINK_DEXT; }
+                    In = satadd(I, -gapE); Dn = satadd(d, -gapE);
+                } else {
+                    s32 open = satadd(c, -gapOE), dd = satadd(d, -gapE), ii = satadd(I, -gapE);
+                    if (open > dd) { Dn = open; f = 0; } else { Dn = dd; f = LINK_DEXT; }
+                    if (open > ii) In = open; else { In = ii; f |= LINK_IEXT; }
+                    f |= F_CAND;
+                    candMax = max(candMax, c);
+                }
+                Ccur[j & msk] = c; Dv[j & msk] = Dn; flg[j & msk] = (u8)f;
+                I = In;
+            }
+        }
+        /* exclusive prefix max of the candidates, seeded with bestScore */
+        s32 pm = candMax;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { s32 u = __shfl_up_sync(FULL, pm, o); if ((int)lane >= o) pm = max(pm, u); }
+        s32 B = __shfl_up_sync(FULL, pm, 1);
+        if (lane == 0) B = LZB_NEG_INF;
+        B = max(B, best);
+        /* pass 3: prune, band edges, best/end */
+        u32 firstAlive = 0xFFFFFFFFu, lastAlive = 0; bool anyAlive = false;
+        s32 upVal = LZB_NEG_INF; u32 upCol = 0; bool upd = false;
+        for (u32 j = j0; j < j1; j++) {
+            s32 c = Ccur[j & msk]; u32 f = flg[j & msk];
+            bool alive = !(f & F_MASK) && c >= B - yDrop;
+            if (!alive) { Ccur[j & msk] = LZB_NEG_INF; Dv[j & msk] = LZB_NEG_INF; tb[(u32)(tbBase + j)] = 0; continue; }
+            tb[(u32)(tbBase + j)] = (u8)(f & 15);
+            if (!anyAlive) { firstAlive = j; anyAlive = true; }
+            lastAlive = j;
+            if ((f & F_CAND) && c >= B) { B = c; upVal = c; upCol = j; upd = true; }
+        }
+        /* reduce across lanes */
+        u32 fa = firstAlive, la = anyAlive ? lastAlive + 1 : 0;       /* la = lastAlive+1, 0 = none */
+        s32 nb = upd ? upVal : LZB_NEG_INF;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fa = min(fa, __shfl_xor_sync(FULL, fa, o)); la = max(la, __shfl_xor_sync(FULL, la, o));
+            nb = max(nb, __shfl_xor_sync(FULL, nb, o));
+        }
+        /* bestScore moves to the LAST cell (row-major) that equalled the row's final best (:3742) */
+        u32 bestCol = 0; bool bestMoved = false;
+        if (nb > LZB_NEG_INF) {
+            u32 cnd = (upd && upVal == nb) ? upCol + 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnd = max(cnd, __shfl_xor_sync(FULL, cnd, o));
+            bestCol = cnd - 1; bestMoved = true; best = nb;
+        }
+        /* boundaryScore (:3747-3750, only without y-drop trimming) moves the same way over the
+         * surviving diagonal winners on the last row / last column */
+        u32 bndCol = 0; bool bndMoved = false;
+        if (!trim) {
+            s32 lm = LZB_NEG_INF; u32 lc = 0; bool lu = false;
+            for (u32 j = j0; j < j1; j++) {
+                u32 f = flg[j & msk]; s32 c = Ccur[j & msk];
+                if ((f & F_CAND) && c > LZB_NEG_INF && (row == M || j == N) && c >= lm) { lm = c; lc = j; lu = true; }
+            }
+            s32 gm = lu ? lm : LZB_NEG_INF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gm = max(gm, __shfl_xor_sync(FULL, gm, o));
+            u32 gc = (lu && lm == gm) ? lc + 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gc = max(gc, __shfl_xor_sync(FULL, gc, o));
+            if (gm > LZB_NEG_INF && gm >= bnd) { bnd = gm; bndCol = gc - 1; bndMoved = true; }
+        }
+        /* the later event in row-major order owns the end cell; in one cell the boundary test runs second */
+        if (bestMoved && (!bndMoved || bestCol > bndCol)) { end1 = row; end2 = bestCol; endIsBnd = 0; }
+        else if (bndMoved) { end1 = row; end2 = bndCol; endIsBnd = 1; }
+        cells += colEnd - leftCol;
+        used += colEnd - leftCol;
+        u32 npCol;
+        if (la) { LY = fa; npCol = la - 1; } else { LY = colEnd; npCol = leftCol; }
+        __syncwarp();
+        s32* t = Cprev; Cprev = Ccur; Ccur = t;
+        if (LY >= RY) break;
+        /* ---- row end, gapped_extend.c:3789-3827 ---- */
+        s32 NN = (rightSeg.al >= 0 && R > 0) ? R - 1 : (s32)N;
+        u32 wcol = colEnd;
+        if (RY > npCol + 1) RY = npCol + 1;
+        else {
+            s32 thr = best - yDrop; u32 p = 0;
+            if (Iout >= thr && (s32)RY <= NN) {
+                u32 room = (u32)(NN - (s32)RY) + 1;
+                u32 byScore = gapE > 0 ? (u32)((Iout - thr) / gapE) + 1 : room;
+                p = byScore < room ? byScore : room;
+            }
+            if ((s64)(RY + p + 2 - LY) + 8 >= (s64)cap) { status = DP_RING; break; }
+            for (u32 q = lane; q < p; q += 32) {
+                s32 v = Iout - (s32)q * gapE;
+                Cprev[(wcol + q) & msk] = v; Dv[(wcol + q) & msk] = v - gapOE;
+                tb[(u32)(tbBase + wcol + q)] = LINK_I;
+            }
+            wcol += p; RY += p; used += p;
+        }
+        if ((s32)RY <= NN) {
+            if (lane == 0) { Cprev[wcol & msk] = LZB_NEG_INF; Dv[wcol & msk] = LZB_NEG_INF; }
+            RY++;
+        }
+        __syncwarp();
+    }
+    /* ---- traceback, gapped_extend.c:3847-3859: 32 diagonal steps per iteration ---- */
+    __syncwarp();
+    __threadfence_block();
+    u32 nops = 0;
+    if (status == DP_OK || status == DP_TRUNCATED) {
+        u32 r = end1, c = end2; u32 prevOp = 0;
+        u32 curOp = 0, curCnt = 0; u32* ops = J->ops; const u32 opsCap = J->opsCap; bool ovf = false;
+        while (r >= 1 || c > 0) {
+            /* speculate a diagonal run: lane t looks at (r-t, c-t) */
+            bool inb = (r >= lane) && (c >= lane) && ((r - lane) >= 1 || (c - lane) > 0);
+            u32 link = 0;
+            if (inb) link = tb[(u32)(tbRow[r - lane] + (c - lane))];
+            u32 op = link & 3;
+            if (lane == 0) {
+                if (prevOp == LINK_I && (link & LINK_IEXT)) op = LINK_I;
+                if (prevOp == LINK_D && (link & LINK_DEXT)) op = LINK_D;
+            }
+            /* lane t>0 assumes the step before it was a substitution, true iff all earlier lanes are subs.
+             * a diagonal step needs r-t >= 1 and c-t >= 1 */
+            bool isSub = inb && op == 0 && (r - lane) >= 1 && (c - lane) >= 1;
+            u32 notSub = __ballot_sync(FULL, !isSub);
+            u32 run = notSub ? (u32)(__ffs(notSub) - 1) : 32;
+            if (run > 0) {
+                if (curOp == LZB_OP_SUB) curCnt += run;
+                else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = LZB_OP_SUB; curCnt = run; }
+                r -= run; c -= run; prevOp = 0;
+                continue;
+            }
+            /* lane 0's step is a gap step (or a substitution forced at the matrix edge) */
+            u32 op0 = __shfl_sync(FULL, op, 0);
+            u32 eop;
+            if (op0 == LINK_I) { c--; eop = LZB_OP_INS; }
+            else if (op0 == LINK_D) { r--; eop = LZB_OP_DEL; }
+            else { r--; c--; eop = LZB_OP_SUB; }
+            if (curOp == eop) curCnt++;
+            else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = eop; curCnt = 1; }
+            prevOp = op0;
+        }
+        if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; }
+        if (ovf) status = DP_OPS;
+    }
+    if (lane == 0) {
+        J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2; J->nops = nops;
+        J->rows = row; J->cells = cells; J->status = status;
+    }
+}
+
+/* ---- K4: segment_peak gapped_extend.c:515-559, one thread per HSP ---- */
+__global__ void k_peaks(lzb_segment* __restrict__ seg, u64 n, const u8* __restrict__ cls1,
+                        const u8* __restrict__ cls2, const lzb_scoring_dev* __restrict__ sc) {
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        lzb_segment g = seg[i];
+        u32 peak;
+        if (g.length <= 31) peak = g.length / 2;
+        else {
+            const u8* s1 = cls1 + g.pos1; const u8* s2 = cls2 + g.pos2;
+            s32 sum = 0;
+            for (u32 k = 0; k < 31; k++) sum += sc->subC[s1[k] * LZB_MAX_CLASSES + s2[k]];
+            s32 bestv = sum; peak = 15;
+            for (u32 k = 31; k < g.length; k++) {
+                sum -= sc->subC[s1[k - 31] * LZB_MAX_CLASSES + s2[k - 31]];
+                sum += sc->subC[s1[k] * LZB_MAX_CLASSES + s2[k]];
+                if (sum > bestv) { bestv = sum; peak = k - 15; }
+            }
+        }
+        g.pos1 += peak; g.pos2 += peak; g.length = 0;
+        seg[i] = g;
+    }
+}
+
+extern "C" int lzb_reduce_to_points(lzb_ctx* c, lzb_target* t, lzb_query* q, lzb_segment* anchors, uint64_t n) {
+    cudaSetDevice(c->device);
+    if (n == 0) return 0;
+    lzb_segment* d = NULL;
+    CUDA_TRY(cudaMalloc(&d, n * sizeof(lzb_segment)));
+    CUDA_TRY(cudaMemcpyAsync(d, anchors, n * sizeof(lzb_segment), cudaMemcpyHostToDevice, c->stream));
+    int blocks = (int)((n + 127) / 128); if (blocks > c->smCount * 16) blocks = c->smCount * 16;
+    k_peaks<<<blocks, 128, 0, c->stream>>>(d, n, t->d_cls, q->d_cls, c->d_sc);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(anchors, d, n * sizeof(lzb_segment), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * host side of gapped_extend
+ * ---------------------------------------------------------------------------------------- */
+
+struct hseg { int type; u32 b1, b2, e1, e2; };
+static const segref NOSEG = { -1, -1 };
+
+struct galn {                          /* galign gapped_extend.c:214-245 */
+    u32 pos1, pos2, end1, end2; u64 hspId;
+    std::vector<hseg> segs;
+    segref left1, right1, left2, right2;
+    lzb_alignel* align;
+    int next, prev;
+    int devIx;                         /* index in the device alignment table once committed */
+};
+
+#define MAX_RPT ((1u << 30) - 1)
+static lzb_editscript* es_new(u32 cap) {
+    if (cap < 16) cap = 16;
+    lzb_editscript* s = (lzb_editscript*)calloc(1, sizeof(lzb_editscript) + (size_t)(cap - 1) * 4);
+    s->size = cap; return s;
+}
+/* edit_script_add edit_script.c:261 applied to an already run-length-encoded op */
+static void es_add(lzb_editscript** ps, u32 op, u32 rpt) {
+    lzb_editscript* s = *ps;
+    if (s->len > 0 && (s->tailOp & 3) == op) {
+        u32 tr = s->op[s->len - 1] >> 2;
+        if ((u64)tr + rpt <= MAX_RPT) { s->op[s->len - 1] += rpt << 2; return; }
+        s->op[s->len - 1] = op | (MAX_RPT << 2); rpt = tr + rpt - MAX_RPT;
+    }
+    if (s->len + 2 > s->size) {
+        u32 nsz = s->size * 2 + 16;
+        s = (lzb_editscript*)realloc(s, sizeof(lzb_editscript) + (size_t)(nsz - 1) * 4); s->size = nsz; *ps = s;
+    }
+    while (rpt > MAX_RPT) { s->op[s->len++] = op | (MAX_RPT << 2); rpt -= MAX_RPT; }
+    s->op[s->len++] = op | (rpt << 2); s->tailOp = op;
+}
+
+struct dp_result { s32 score; u32 end1, end2, rows; int status; unsigned long long cells; std::vector<u32> ops; };
+
+struct gx {                             /* state of one lzb_gapped_extend call */
+    lzb_ctx* c; lzb_target* t; lzb_query* q;
+    const lzb_gapped_params* P;
+    std::vector<galn> al; int obi, oed;
+    std::vector<int> committed;         /* host alignment indices in commit order = device table order */
+    std::vector<dseg> hsegs;            /* device segment table (host mirror) */
+    std::vector<dalign> haligns;
+    dseg* d_segs; size_t d_segsCap; dalign* d_aligns; size_t d_alignsCap;
+    lzb_gapped_stats st;
+};
+
+/* msp_left_right gapped_extend.c:3953-4040 */
+static bool anchor_neighbours(gx& G, galn& m) {
+    u32 pos1 = m.pos1, pos2 = m.pos2, right = 0xFFFFFFFFu, left = 0xFFFFFFFFu;
+    segref R = NOSEG, Lf = NOSEG;
+    for (int o = G.obi; o >= 0 && G.al[o].pos1 <= pos1; o = G.al[o].next) {
+        galn& x = G.al[o];
+        if (x.end1 < pos1) continue;
+        int k = 0, ns = (int)x.segs.size();
+        while (k < ns && x.segs[k].e1 < pos1) k++;
+        if (k == ns) continue;
+        hseg& bp = x.segs[k]; s32 d;
+        if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - pos2) + (s32)(pos1 - bp.b1); else d = (s32)(bp.b2 - pos2);
+        if (d == 0) return false;
+        if (d > 0 && (u32)d < right) { right = (u32)d; R.al = o; R.sg = k; }
+        else if (d < 0 && (u32)-d < left) { left = (u32)-d; Lf.al = o; Lf.sg = k; }
+    }
+    m.right1 = m.right2 = R; m.left1 = m.left2 = Lf;
+    return true;
+}
+
+/* align_left_right gapped_extend.c:4078-4175 */
+static void alignment_neighbours(gx& G, galn& m) {
+    u32 pos1 = m.pos1, pos2 = m.pos2, end1 = m.end1, end2 = m.end2;
+    u32 rB = 0xFFFFFFFFu, rT = rB, lB = rB, lT = rB;
+    segref RB = NOSEG, RT = NOSEG, LB = NOSEG, LT = NOSEG;
+    for (int o = G.obi; o >= 0; o = G.al[o].next) {
+        galn& x = G.al[o];
+        if (x.pos1 > end1 || x.end1 < pos1) continue;
+        int k = 0, ns = (int)x.segs.size();
+        while (k < ns && !(x.segs[k].type != SEG_HORZ && x.segs[k].e1 >= pos1)) k++;
+        if (k < ns && x.segs[k].b1 <= pos1) {
+            hseg& bp = x.segs[k]; s32 d;
+            if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - pos2) + (s32)(pos1 - bp.b1); else d = (s32)(bp.b2 - pos2);
+            if (d > 0 && (u32)d < rB) { rB = (u32)d; RB.al = o; RB.sg = k; }
+            else if (d < 0 && (u32)-d < lB) { lB = (u32)-d; LB.al = o; LB.sg = k; }
+        }
+        while (k < ns && !(x.segs[k].type != SEG_HORZ && x.segs[k].e1 >= end1)) k++;
+        if (k < ns) {
+            hseg& bp = x.segs[k]; s32 d;
+            if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - end2) + (s32)(end1 - bp.b1); else d = (s32)(bp.b2 - end2);
+            if (d > 0 && (u32)d < rT) { rT = (u32)d; RT.al = o; RT.sg = k; }
+            else if (d < 0 && (u32)-d < lT) { lT = (u32)-d; LT.al = o; LT.sg = k; }
+        }
+    }
+    m.right1 = RB; m.right2 = RT; m.left1 = LB; m.left2 = LT;
+}
+
+/* insert_align gapped_extend.c:4210-4240 */
+static void list_insert(gx& G, int mi) {
+    galn& m = G.al[mi];
+    int qq = -1, p = G.obi;
+    while (p >= 0 && G.al[p].pos1 < m.pos1) { qq = p; p = G.al[p].next; }
+    if (qq >= 0) { G.al[qq].next = mi; m.next = p; } else { m.next = G.obi; G.obi = mi; }
+    qq = -1; p = G.oed;
+    while (p >= 0 && G.al[p].end1 > m.end1) { qq = p; p = G.al[p].prev; }
+    if (qq >= 0) { G.al[qq].prev = mi; m.prev = p; } else { m.prev = G.oed; G.oed = mi; }
+}
+
+/* save_seg gapped_extend.c:5220-5262 */
+static void add_diag(galn& m, u32 b1, u32 b2, u32 e1, u32 e2) {
+    if (!m.segs.empty()) {
+        hseg& last = m.segs.back();
+        hseg g; g.type = (b1 == last.e1 + 1) ? SEG_HORZ : SEG_VERT;
+        g.b1 = last.e1 + 1; g.b2 = last.e2 + 1; g.e1 = b1 - 1; g.e2 = b2 - 1;
+        m.segs.push_back(g);
+    }
+    hseg d = { SEG_DIAG, b1, b2, e1, e2 };
+    m.segs.push_back(d);
+}
+
+/* score_alignment gapped_extend.c:5631-5690 (host bytes; O(alignment length), only after lopping) */
+static s32 rescore(gx& G, u32 p1, u32 p2, lzb_editscript* s) {
+    const s32* sub = G.c->hostSub; s32 sim = 0;
+    const u8* s1 = G.t->h_seq; const u8* s2 = G.q->h_seq;
+    for (u32 k = 0; k < s->len; k++) {
+        u32 rpt = s->op[k] >> 2, op = s->op[k] & 3;
+        if (!rpt) continue;
+        if (op == LZB_OP_SUB) { for (u32 j = 0; j < rpt; j++) sim += sub[(u32)s1[p1 + j] * 256 + s2[p2 + j]]; p1 += rpt; p2 += rpt; }
+        else if (op == LZB_OP_INS) { sim -= G.c->sc.gapOpen + (s32)rpt * G.c->sc.gapExtend; p2 += rpt; }
+        else { sim -= G.c->sc.gapOpen + (s32)rpt * G.c->sc.gapExtend; p1 += rpt; }
+    }
+    return sim;
+}
+
+static segref dev_ref(gx& G, segref r) { segref o = NOSEG; if (r.al >= 0) { o.al = G.al[r.al].devIx; o.sg = r.sg; } return o; }
+
+/* push the committed alignments the device has not seen yet, and refresh the list links */
+static int sync_device_tables(gx& G) {
+    lzb_ctx* c = G.c;
+    size_t haveA = G.haligns.size();
+    for (size_t k = haveA; k < G.committed.size(); k++) {
+        galn& m = G.al[G.committed[k]];
+        dalign d; memset(&d, 0, sizeof d);
+        d.segBegin = (int)G.hsegs.size(); d.segCount = (int)m.segs.size();
+        for (auto& s : m.segs) { dseg x = { s.b1, s.b2, s.e1, s.e2, s.type }; G.hsegs.push_back(x); }
+        G.haligns.push_back(d);
+    }
+    for (size_t k = 0; k < G.committed.size(); k++) {
+        galn& m = G.al[G.committed[k]]; dalign& d = G.haligns[k];
+        d.pos1 = m.pos1; d.end1 = m.end1;
+        d.left1 = dev_ref(G, m.left1); d.right1 = dev_ref(G, m.right1); d.left2 = dev_ref(G, m.left2); d.right2 = dev_ref(G, m.right2);
+        d.next = m.next >= 0 ? G.al[m.next].devIx : -1; d.prev = m.prev >= 0 ? G.al[m.prev].devIx : -1;
+    }
+    if (G.hsegs.size() > G.d_segsCap) {
+        cudaFree(G.d_segs); G.d_segsCap = G.hsegs.size() * 2 + 1024;
+        CUDA_TRY(cudaMalloc(&G.d_segs, G.d_segsCap * sizeof(dseg)));
+    }
+    if (G.haligns.size() > G.d_alignsCap) {
+        cudaFree(G.d_aligns); G.d_alignsCap = G.haligns.size() * 2 + 256;
+        CUDA_TRY(cudaMalloc(&G.d_aligns, G.d_alignsCap * sizeof(dalign)));
+    }
+    if (!G.hsegs.empty()) CUDA_TRY(cudaMemcpyAsync(G.d_segs, G.hsegs.data(), G.hsegs.size() * sizeof(dseg), cudaMemcpyHostToDevice, c->stream));
+    if (!G.haligns.empty()) CUDA_TRY(cudaMemcpyAsync(G.d_aligns, G.haligns.data(), G.haligns.size() * sizeof(dalign), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+struct slot_bufs { u8* tb; u32* tbRow; u32 tbRowCap; u32* ops; u32 opsCap; int* act; u32 actCap; };
+
+struct spec_result {                    /* a finished (possibly speculative) two-sided extension */
+    bool have; size_t snapshot;         /* committed.size() when it was launched */
+    segref left1, right1;               /* anchor neighbours it was computed with */
+    dp_result L, R;
+};
+
+extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const uint8_t* h1, const uint8_t* h2,
+                                 lzb_segment* anchors, uint64_t n, const lzb_gapped_params* P,
+                                 lzb_alignel** list, lzb_gapped_stats* stats) {
+    cudaSetDevice(c->device);
+    if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
+    if (P->tracebackBytes < 8) return lzb_fail("in new_traceback(), size can't be %u", P->tracebackBytes);
+    auto wall0 = std::chrono::steady_clock::now();
+    u64 launches0 = c->launches;
+    *list = NULL;
+    gx G; G.c = c; G.t = t; G.q = q; G.P = P; G.obi = G.oed = -1;
+    G.d_segs = NULL; G.d_segsCap = 0; G.d_aligns = NULL; G.d_alignsCap = 0;
+    memset(&G.st, 0, sizeof G.st); G.st.anchors = n;
+    const u32 tbLen = 1 + (P->tracebackBytes - 8);                    /* new_traceback :2272-2290 */
+    const u32 len1 = t->len, len2 = q->len;
+
+    /* qSegmentsByDecreasingScore segment.c:1748-1771 (a total order, so any sort gives the same result) */
+    std::sort(anchors, anchors + n, [](const lzb_segment& a, const lzb_segment& b) {
+        if (a.s != b.s) return a.s > b.s;
+        if (a.length != b.length) return a.length < b.length;
+        if (a.pos2 != b.pos2) return a.pos2 < b.pos2;
+        if (a.pos1 != b.pos1) return a.pos1 < b.pos1;
+        return a.id < b.id;
+    });
+    G.al.resize(n + 1);
+    for (u64 i = 0; i <= n; i++) { galn& m = G.al[i]; m.align = NULL; m.next = m.prev = -1; m.devIx = -1; m.left1 = m.right1 = m.left2 = m.right2 = NOSEG; m.pos1 = m.pos2 = m.end1 = m.end2 = 0; m.hspId = 0; }
+    for (u64 i = 0; i < n; i++) { G.al[i].pos1 = anchors[i].pos1; G.al[i].pos2 = anchors[i].pos2; G.al[i].hspId = anchors[i].hspId; }
+
+    /* identical_sequences gapped_extend.c:1886-1930 -> trivial self alignment :1113-1151 */
+    if (P->identityCheck && len1 == len2) {
+        bool same = true; s32 s = 0; const s32* sub = c->hostSub;
+        for (u32 i = 0; i < len1 && same; i++) {
+            u8 a = t->h_seq[i], b = q->h_seq[i];
+            if (a >= 'a' && a <= 'z') a -= 32;
+            if (b >= 'a' && b <= 'z') b -= 32;
+            if (a != b) { same = false; break; }
+            s32 v = sub[(u32)a * 256 + b];
+            if (s == 0x7FFFFFFF) ; else if (v <= 0 || s < 0x7FFFFFFF - v) s += v; else s = 0x7FFFFFFF;
+        }
+        if (same) {
+            galn& m = G.al[n];
+            m.pos1 = m.pos2 = 0; m.end1 = m.end2 = len1 - 1;
+            add_diag(m, 0, 0, m.end1, m.end2);
+            list_insert(G, (int)n);
+            m.devIx = (int)G.committed.size(); G.committed.push_back((int)n);
+            lzb_alignel* a = (lzb_alignel*)calloc(1, sizeof *a);
+            a->script = es_new(4); es_add(&a->script, LZB_OP_SUB, len1);
+            a->beg1 = a->beg2 = 1; a->end1 = a->end2 = len1; a->seq1 = h1; a->seq2 = h2;
+            a->s = s < P->scoreThreshold ? P->scoreThreshold : s; a->isTrivial = 1; m.align = a;
+        }
+    }
+
+    /* ---- device buffers: two slots (left, right) per speculative anchor ---- */
+    int W = P->speculation < 1 ? 1 : (P->speculation > 64 ? 64 : P->speculation);
+    const char* wenv = getenv("LZB_SPECULATION"); if (wenv) { W = atoi(wenv); if (W < 1) W = 1; if (W > 64) W = 64; }
+    if ((u64)W > n) W = n ? (int)n : 1;
+    u32 cap = 4096;                                         /* sweep-row ring, columns */
+    const char* cenv = getenv("LZB_RING"); if (cenv) cap = (u32)atoi(cenv);
+    u32 tbRowCap = tbLen / 24 + 4096, opsCap = 1u << 20, actCap = 256;
+    std::vector<slot_bufs> slots(2 * W);
+    std::vector<dp_job> hjobs(2 * W);
+    dp_job* d_jobs = NULL;
+    auto free_slots = [&]() { for (auto& s : slots) { cudaFree(s.tb); cudaFree(s.tbRow); cudaFree(s.ops); cudaFree(s.act); } cudaFree(d_jobs); cudaFree(G.d_segs); cudaFree(G.d_aligns); };
+    for (auto& s : slots) { memset(&s, 0, sizeof s); }
+    for (auto& s : slots) {
+        CUDA_TRY(cudaMalloc(&s.tb, (size_t)P->tracebackBytes + 64));
+        s.tbRowCap = tbRowCap; CUDA_TRY(cudaMalloc(&s.tbRow, (size_t)tbRowCap * 4));
+        s.opsCap = opsCap; CUDA_TRY(cudaMalloc(&s.ops, (size_t)opsCap * 4));
+        s.actCap = actCap; CUDA_TRY(cudaMalloc(&s.act, (size_t)actCap * 5 * 4));
+    }
+    CUDA_TRY(cudaMalloc(&d_jobs, (size_t)2 * W * sizeof(dp_job)));
+    cudaEvent_t evA, evB; CUDA_TRY(cudaEventCreate(&evA)); CUDA_TRY(cudaEventCreate(&evB));
+    CUDA_TRY(cudaFuncSetAttribute(k_ydrop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+
+    std::vector<spec_result> spec(n);
+    for (auto& s : spec) s.have = false;
+    u64 reach = tbLen / 300 + 1000;                          /* rows a DP is expected to cover, for batch selection */
+
+    /* runs the DPs of the chosen anchors (left+right each) and stores their results */
+    auto run_batch = [&](const std::vector<u64>& pick) -> int {
+        if (sync_device_tables(G)) return -1;
+        size_t snap = G.committed.size();
+        std::vector<int> todo;                               /* job indices still to run */
+        for (size_t b = 0; b < pick.size(); b++) {
+            galn& m = G.al[pick[b]];
+            /* get_above_below :4043-4060 */
+            int below = G.oed; while (below >= 0 && !(G.al[below].end1 < m.pos1)) below = G.al[below].prev;
+            int above = G.obi; while (above >= 0 && !(G.al[above].pos1 > m.pos1)) above = G.al[above].next;
+            for (int side = 0; side < 2; side++) {
+                dp_job& J = hjobs[2 * b + side]; memset(&J, 0, sizeof J);
+                int rev = side == 0;
+                J.reversed = rev; J.a1 = m.pos1; J.a2 = m.pos2;
+                J.M = rev ? m.pos1 + 1 : len1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 : len2 - (m.pos2 + 1);
+                /* initial L/R, gapped_extend.c:3500-3543 */
+                s32 L = 0, R = (s32)(J.N + 1);
+                if (m.left1.al >= 0) { hseg& s = G.al[m.left1.al].segs[m.left1.sg]; L = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) L -= (s32)(s.b1 - m.pos1); }
+                if (m.right1.al >= 0) { hseg& s = G.al[m.right1.al].segs[m.right1.sg]; R = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) R -= (s32)(s.b1 - m.pos1); }
+                if (rev) {
+                    if (m.left1.al < 0 && m.right1.al >= 0) { L = -R + 1; R = (s32)(J.N + 1); }
+                    else if (m.left1.al >= 0 && m.right1.al < 0) { R = -L - 1; L = 0; }
+                    else if (m.left1.al >= 0 && m.right1.al >= 0) { s32 tt = -L - 1; L = -R + 1; R = tt; }
+                }
+                J.L0 = L; J.R0 = R;
+                J.leftSeg = dev_ref(G, m.left1); J.rightSeg = dev_ref(G, m.right1);
+                int lst = rev ? below : above;
+                J.alignList = lst >= 0 ? G.al[lst].devIx : -1;
+                todo.push_back((int)(2 * b + side));
+            }
+        }
+        u32 ring = cap;
+        while (!todo.empty()) {
+            /* compact the jobs to run into the front of the device array */
+            std::vector<dp_job> run(todo.size());
+            for (size_t k = 0; k < todo.size(); k++) {
+                dp_job J = hjobs[todo[k]]; slot_bufs& s = slots[todo[k]];
+                J.tb = s.tb; J.tbLen = tbLen; J.tbRow = s.tbRow; J.tbRowCap = s.tbRowCap; J.ops = s.ops; J.opsCap = s.opsCap; J.act = s.act; J.actCap = s.actCap;
+                run[k] = J;
+            }
+            CUDA_TRY(cudaMemcpyAsync(d_jobs, run.data(), run.size() * sizeof(dp_job), cudaMemcpyHostToDevice, c->stream));
+            size_t smem = (size_t)ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 64;
+            CUDA_TRY(cudaEventRecord(evA, c->stream));
+            k_ydrop<<<(int)run.size(), 32, smem, c->stream>>>(d_jobs, G.d_aligns, G.d_segs, t->d_cls, q->d_cls, len1, len2,
+                                                            c->d_sc, P->yDrop, P->trimToPeak, ring);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(evB, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(run.data(), d_jobs, run.size() * sizeof(dp_job), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            float ms = 0; cudaEventElapsedTime(&ms, evA, evB); G.st.kernelSeconds[0] += ms / 1e3;
+            std::vector<int> again; bool growRing = false;
+            for (size_t k = 0; k < todo.size(); k++) {
+                dp_job& J = run[k]; int ji = todo[k]; slot_bufs& s = slots[ji];
+                if (J.status == DP_RING) { growRing = true; again.push_back(ji); continue; }
+                if (J.status == DP_TBROW) {
+                    cudaFree(s.tbRow); s.tbRowCap = s.tbRowCap * 4 < tbLen ? s.tbRowCap * 4 : tbLen + 8;
+                    CUDA_TRY(cudaMalloc(&s.tbRow, (size_t)s.tbRowCap * 4)); again.push_back(ji); continue;
+                }
+                if (J.status == DP_OPS) { cudaFree(s.ops); s.opsCap *= 4; CUDA_TRY(cudaMalloc(&s.ops, (size_t)s.opsCap * 4)); again.push_back(ji); continue; }
+                if (J.status == DP_ACT) { cudaFree(s.act); s.actCap *= 4; CUDA_TRY(cudaMalloc(&s.act, (size_t)s.actCap * 5 * 4)); again.push_back(ji); continue; }
+                spec_result& sr = spec[pick[ji / 2]];
+                dp_result& r = (ji & 1) ? sr.R : sr.L;
+                r.score = J.score; r.end1 = J.end1; r.end2 = J.end2; r.rows = J.rows; r.status = J.status; r.cells = J.cells;
+                r.ops.resize(J.nops);
+                if (J.nops) CUDA_TRY(cudaMemcpy(r.ops.data(), s.ops, (size_t)J.nops * 4, cudaMemcpyDeviceToHost));
+            }
+            if (growRing) {
+                if (ring >= 8192) { free_slots(); return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ring); }
+                ring *= 2;
+            }
+            todo.swap(again);
+        }
+        for (size_t b = 0; b < pick.size(); b++) {
+            spec_result& sr = spec[pick[b]]; galn& m = G.al[pick[b]];
+            sr.have = true; sr.snapshot = snap; sr.left1 = m.left1; sr.right1 = m.right1;
+            G.st.dpCells += sr.L.cells + sr.R.cells; G.st.dpRows += sr.L.rows + sr.R.rows;
+            G.st.truncated += (sr.L.status == DP_TRUNCATED) + (sr.R.status == DP_TRUNCATED);
+        }
+        return 0;
+    };
+
+    /* ---- the anchor loop, gapped_extend.c:1300-1470, committed strictly in score order ---- */
+    u64 i = 0;
+    while (i < n) {
+        galn& m = G.al[i];
+        if (!anchor_neighbours(G, m)) { spec[i].have = false; spec[i].L.ops.clear(); spec[i].R.ops.clear(); i++; continue; }
+        spec_result& sr = spec[i];
+        bool usable = sr.have;
+        if (usable && sr.snapshot != G.committed.size()) {
+            /* valid only if nothing committed since its launch touches the rows its DPs examined */
+            u64 lo = (u64)m.pos1 + 1 >= (u64)sr.L.rows + 2 ? (u64)m.pos1 + 1 - sr.L.rows - 2 : 0;
+            u64 hi = (u64)m.pos1 + sr.R.rows + 2;
+            for (size_t k = sr.snapshot; k < G.committed.size() && usable; k++) {
+                galn& x = G.al[G.committed[k]];
+                if (!((u64)x.end1 < lo || (u64)x.pos1 > hi)) usable = false;
+            }
+            if (usable && (sr.left1.al != m.left1.al || sr.left1.sg != m.left1.sg || sr.right1.al != m.right1.al || sr.right1.sg != m.right1.sg)) usable = false;
+            if (!usable) G.st.redone++;
+        }
+        if (!usable) {
+            /* launch a batch: this anchor plus later uncovered anchors that are unlikely to interact */
+            std::vector<u64> pick; pick.push_back(i);
+            for (u64 j = i + 1; j < n && (int)pick.size() < W; j++) {
+                if (spec[j].have) continue;                 /* validated (or redone) at its turn */
+                galn& y = G.al[j];
+                bool far = true;
+                for (u64 pj : pick) { u64 a = G.al[pj].pos1, b = y.pos1; if ((a > b ? a - b : b - a) < 2 * reach) { far = false; break; } }
+                if (!far) continue;
+                if (!anchor_neighbours(G, y)) continue;
+                pick.push_back(j);
+                if (j - i > 4096) break;
+            }
+            G.st.speculated += pick.size() - 1;
+            if (run_batch(pick)) { free_slots(); return -1; }
+            { u64 r = std::max<u64>(spec[i].L.rows, spec[i].R.rows); reach = (reach * 3 + r) / 4 + 1; }
+            continue;                                      /* re-enter: now usable */
+        }
+        /* ---- commit: ydrop_align's script assembly :2529-2580, format_alignment :5153 ---- */
+        G.st.anchorsExtended++;
+        u32 a1 = m.pos1, a2 = m.pos2;
+        u32 start1 = a1 + 1 - sr.L.end1, start2 = a2 + 1 - sr.L.end2, stop1 = a1 + sr.R.end1, stop2 = a2 + sr.R.end2;
+        lzb_editscript* sl = es_new((u32)(sr.L.ops.size() + sr.R.ops.size() + 4));
+        /* left script: ops in emission order; right script: emitted far-end first, so reversed */
+        for (size_t k = 0; k < sr.L.ops.size(); k++) es_add(&sl, sr.L.ops[k] & 3, sr.L.ops[k] >> 2);
+        for (size_t k = sr.R.ops.size(); k-- > 0;) es_add(&sl, sr.R.ops[k] & 3, sr.R.ops[k] >> 2);
+        if (sl->len > 0 && sr.R.ops.size() > 0) sl->tailOp = sr.R.ops.back() & 3;    /* edit_script_append keeps src->tailOp (unreversed) */
+        s32 score = sr.L.score + sr.R.score;
+        if (sl->len != 0) {
+            if ((sl->op[0] & 3) != LZB_OP_SUB) {             /* lop_initial_indels :2589 */
+                u32 p1 = start1, p2 = start2, k = 0;
+                for (; k < sl->len; k++) { u32 op = sl->op[k] & 3, rpt = sl->op[k] >> 2; if (op == LZB_OP_SUB) break; if (op == LZB_OP_INS) p2 += rpt; else p1 += rpt; }
+                if (k == sl->len) score = (s32)(-0x7FFFFFFF - 1);
+                else { start1 = p1; start2 = p2; sl->len -= k; memmove(sl->op, sl->op + k, (size_t)sl->len * 4); score = rescore(G, start1, start2, sl); }
+            }
+            if (score != (s32)(-0x7FFFFFFF - 1) && (sl->op[sl->len - 1] & 3) != LZB_OP_SUB) {   /* lop_final_indels :2640 */
+                u32 p1 = stop1, p2 = stop2, k = sl->len;
+                while (k > 0) { k--; u32 op = sl->op[k] & 3, rpt = sl->op[k] >> 2; if (op == LZB_OP_SUB) { k++; break; } if (op == LZB_OP_INS) p2 -= rpt; else p1 -= rpt; }
+                if (k == 0) score = (s32)(-0x7FFFFFFF - 1);
+                else { stop1 = p1; stop2 = p2; sl->len = k; score = rescore(G, start1, start2, sl); }
+            }
+        }
+        u32 beg1 = start1 + 1, end1 = stop1 + 1, beg2 = start2 + 1, end2 = stop2 + 1;
+        u32 height = end1 - beg1 + 1, width = end2 - beg2 + 1, k = 0;
+        m.segs.clear();
+        for (u32 ii = 0, jj = 0; ii < height || jj < width;) {
+            u32 si = ii, sj = jj, run = 0;
+            while (k < sl->len && (sl->op[k] & 3) == LZB_OP_SUB) { run += sl->op[k] >> 2; k++; }
+            ii += run; jj += run;
+            add_diag(m, beg1 + si - 1, beg2 + sj - 1, beg1 + ii - 2, beg2 + jj - 2);
+            if (ii < height || jj < width) {
+                if (k < sl->len) { u32 op = sl->op[k] & 3, rpt = sl->op[k] >> 2; if (op == LZB_OP_INS) jj += rpt; else if (op == LZB_OP_DEL) ii += rpt; k++; }
+                else break;
+            }
+        }
+        lzb_alignel* a = (lzb_alignel*)calloc(1, sizeof *a);
+        a->script = sl; a->beg1 = beg1; a->beg2 = beg2; a->end1 = end1; a->end2 = end2;
+        a->seq1 = h1; a->seq2 = h2; a->s = score; a->hspId = m.hspId;
+        m.align = a; m.pos1 = start1; m.pos2 = start2; m.end1 = stop1; m.end2 = stop2;
+        sr.have = false; sr.L.ops.clear(); sr.L.ops.shrink_to_fit(); sr.R.ops.clear(); sr.R.ops.shrink_to_fit();
+        if (m.segs.empty()) { i++; continue; }
+        if (!P->allBounds && a->s < P->scoreThreshold) { free(a->script); free(a); m.align = NULL; m.segs.clear(); i++; continue; }
+        alignment_neighbours(G, m);
+        list_insert(G, (int)i);
+        m.devIx = (int)G.committed.size(); G.committed.push_back((int)i);
+        i++;
+    }
+    lzb_alignel* head = NULL, *last = NULL;
+    for (int o = G.obi; o >= 0; o = G.al[o].next) {
+        galn& m = G.al[o];
+        bool drop = m.align->s < P->scoreThreshold || (P->inhibitTrivial && m.align->isTrivial);
+        if (drop) { free(m.align->script); free(m.align); }
+        else { if (!head) head = last = m.align; else { last->next = m.align; last = m.align; } }
+    }
+    cudaEventDestroy(evA); cudaEventDestroy(evB);
+    free_slots();
+    *list = head;
+    G.st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    G.st.launches = c->launches - launches0;
+    if (stats) *stats = G.st;
+    return 0;
+}
+
+extern "C" void lzb_free_align_list(lzb_alignel* a) {
+    while (a) { lzb_alignel* nx = a->next; free(a->script); free(a); a = nx; }
+}
