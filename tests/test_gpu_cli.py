@@ -1,0 +1,52 @@
+"""End to end through the lastz_b200 command line on the GPU: golden LAVs of the reference and,
+where oracle/_ref exists, the unmodified reference binary on synthetic pairs."""
+import os
+
+import pytest
+
+from conftest import GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, lav_body, run_cli
+
+pytestmark = pytest.mark.gpu
+
+CAT = os.path.join(GOLDEN, "pseudocat.fa")
+PIG = os.path.join(GOLDEN, "pseudopig.fa")
+
+
+def norm(t):
+    return [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+
+
+@pytest.mark.parametrize("golden,opts", [
+    ("base_test.default.lav", []),
+    ("base_test.hits.lav", ["W=8", "T=0", "--plus", "--nogfextend", "--nogapped"]),
+    ("base_test.hsp.lav", ["C=3", "W=8", "T=0"]),
+    ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),
+])
+def test_cli_reproduces_golden_lav(golden, opts):
+    out, _ = run_cli(PRODUCT_CLI, [CAT, PIG] + opts)
+    assert norm(out) == norm(open(os.path.join(GOLDEN, golden)).read())
+
+
+def test_cli_segments_round_trip(tmp_path):
+    segs, _ = run_cli(PRODUCT_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
+    f = tmp_path / "hsps.segments"
+    f.write_text(segs)
+    out, _ = run_cli(PRODUCT_CLI, [CAT, PIG, f"--segments={f}"])
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.default.lav")).read())
+
+
+@pytest.mark.parametrize("size,opts", [
+    (1000000, []),
+    (1000000, ["--nogapped", "--format=segments"]),
+    (1000000, ["--allocate:traceback=8M"]),
+    (500000, ["--seed=14of22", "--notransition", "--step=2", "--hspthresh=2200"]),
+])
+def test_cli_matches_reference_on_synthetic(synth, size, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    t, q = synth(size)
+    got, _ = run_cli(PRODUCT_CLI, [t, q] + opts)
+    want, _ = run_cli(ref, [t, q] + opts)
+    if "--format=segments" in opts:
+        assert got == want
+    else:
+        assert lav_body(got) == lav_body(want)
