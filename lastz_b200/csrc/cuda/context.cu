@@ -45,6 +45,7 @@ extern "C" lzb_ctx* lzb_open(int device) {
 extern "C" void lzb_close(lzb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    lzb_gapped_cache_free(c);
     cudaStreamDestroy(c->stream);
     cudaFree(c->d_sc);
     free(c->hostSub); free(c->hostMsub);

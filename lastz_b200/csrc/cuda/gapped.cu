@@ -6,11 +6,11 @@
  * ydrop_align (:2459), ydrop_one_sided_align (:3388), update_LR_bounds (:4588),
  * update_active_segs (:4885) and format_alignment (:5153).
  *
- * DP kernel (k_ydrop): one warp per one-sided alignment, many alignments per launch.  A sweep row
- * lives in shared memory (ring-indexed by column); the 32 lanes own contiguous column chunks.
+ * DP kernel (k_ydrop): one 256-thread CTA per one-sided alignment.  A sweep row lives in shared
+ * memory (ring-indexed by column); the threads own contiguous column chunks.
  * The reference visits a row left to right with three loop-carried values: the insertion score
  * I, the running bestScore (which moves the prune threshold WITHIN the row) and the band edges.
- * Here a row is three short passes joined by warp scans:
+ * Here a row is three short passes joined by block-wide scans:
  *   1. max-plus scan of the insertion chain I (affine maps x -> max(a, x - e), reset at cells
  *      masked by earlier alignments),
  *   2. cell values + traceback links, then an exclusive prefix-max of the cells that may raise
@@ -23,8 +23,8 @@
  * same warp then walks it back 32 diagonal steps at a time and emits run-length edit ops.
  *
  * Anchor loop (host, C++): identical order and bookkeeping to the reference.  Because each
- * alignment constrains later ones, anchors are extended SPECULATIVELY in batches against the
- * alignments committed so far and committed strictly in score order; a speculative result is
+ * alignment constrains later ones, anchors are extended SPECULATIVELY on a pool of streams
+ * ("lanes") against the alignments committed so far, and committed strictly in score order; a speculative result is
  * used only if no alignment committed after its launch overlaps the rows its DP examined,
  * otherwise it is recomputed -- so the output equals the sequential algorithm's.
  */
@@ -32,6 +32,7 @@
 #include <chrono>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 #include "lzb_cuda.h"
 
@@ -55,6 +56,8 @@ struct dp_job {
     int alignList;
     u8* tb; u32 tbLen; u32* tbRow; u32 tbRowCap; u32* ops; u32 opsCap;
     int* act; u32 actCap;             /* 5 ints per active segment */
+    const dalign* al;                 /* alignment table snapshot this job runs against */
+    int skip;                         /* nonzero: nothing to do (the other side of a rerun) */
     /* results */
     s32 score; u32 end1, end2, nops, rows; int status; unsigned long long cells;
 };
@@ -120,19 +123,34 @@ __device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u
     }
 }
 
-__global__ void __launch_bounds__(32)
-k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ segs,
+#define DP_THREADS 256
+#define DP_WARPS (DP_THREADS / 32)
+
+struct dp_shared {                    /* small block-wide exchange area */
+    xf  wagg[DP_WARPS];
+    s32 wmax[DP_WARPS];
+    u32 wfa[DP_WARPS], wla[DP_WARPS];
+    unsigned long long wkey[DP_WARPS], wbkey[DP_WARPS];
+    int nact, alignList, status;
+};
+
+__global__ void __launch_bounds__(DP_THREADS)
+k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
         const lzb_scoring_dev* __restrict__ sc, s32 yDrop, int trim, u32 cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     s32* C0 = (s32*)smem_raw; s32* C1 = C0 + cap; s32* Dv = C1 + cap;
-    u32* stamp = (u32*)(Dv + cap); s32* subC = (s32*)(stamp + cap); u8* flg = (u8*)(subC + LZB_MAX_CLASSES * LZB_MAX_CLASSES);
+    u32* stamp = (u32*)(Dv + cap); s32* subC = (s32*)(stamp + cap);
+    dp_shared* sh = (dp_shared*)(subC + LZB_MAX_CLASSES * LZB_MAX_CLASSES);
+    u8* flg = (u8*)(sh + 1);
     const u32 msk = cap - 1;
-    const u32 lane = threadIdx.x;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 FULL = 0xFFFFFFFFu;
     dp_job* J = &jobs[blockIdx.x];
-    for (u32 i = lane; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += 32) subC[i] = sc->subC[i];
-    for (u32 i = lane; i < cap; i += 32) stamp[i] = 0;
+    if (J->skip) return;
+    const dalign* __restrict__ al = J->al;
+    for (u32 i = tid; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += DP_THREADS) subC[i] = sc->subC[i];
+    for (u32 i = tid; i < cap; i += DP_THREADS) stamp[i] = 0;
     const int rev = J->reversed; const u32 a1 = J->a1, a2 = J->a2, M = J->M, N = J->N;
     const s32 gapE = sc->gapExtend, gapOE = sc->gapOpen + sc->gapExtend;
     const u8 cls0 = sc->cls[0];
@@ -141,7 +159,7 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
     s32 best = 0, bnd = LZB_NEG_INF; u32 end1 = 0, end2 = 0; int endIsBnd = 0;
     unsigned long long cells = 0; u32 row = 0;
     if (N == 0 || M == 0) {
-        if (lane == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; }
+        if (tid == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; }
         return;
     }
     s32 yTail = gapE != 0 ? yDrop / gapE + 6 : (N < 500000u ? (s32)N + 1 : 500000);
@@ -150,18 +168,18 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
     int alignList = J->alignList;
     int* act = J->act; int nact = 0;
     s64 used = 0;
-    __syncwarp();
+    __syncthreads();
     /* ---- first row, gapped_extend.c:3576-3591 ---- */
     u32 LY = 0, RY;
     {
         /* C[0][c] = -(oe + (c-1)e); col c (>=1) exists iff c <= N and C[0][c-1] >= -yDrop */
-        u32 last = 1;                                  /* col 1 always exists when N >= 1 */
+        u32 last = 1;
         if (gapE > 0) { if (yDrop >= gapOE) last = (u32)(((s64)yDrop - gapOE) / gapE) + 2; }
         else if (yDrop >= gapOE) last = N;
         if (last > N) last = N;
         if ((s64)last + 1 + yTail + 40 >= (s64)cap) status = DP_RING;
         else {
-            for (u32 c = lane; c <= last; c += 32) {
+            for (u32 c = tid; c <= last; c += DP_THREADS) {
                 s32 v = c == 0 ? 0 : -gapOE - (s32)(c - 1) * gapE;
                 C0[c & msk] = v; Dv[c & msk] = v - gapOE;
                 tb[c] = c == 0 ? 0 : LINK_I;
@@ -169,14 +187,14 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
             used = (s64)last + 1;
         }
         RY = last + 1;
-        if (lane == 0 && J->tbRowCap > 0) tbRow[0] = 0;
+        if (tid == 0 && J->tbRowCap > 0) tbRow[0] = 0;
     }
-    __syncwarp();
+    __syncthreads();
     s32* Cprev = C0; s32* Ccur = C1;
     if (status == DP_OK)
     for (row = 1; row <= M; row++) {
         u32 prevLY = LY;
-        /* ---- update_LR_bounds gapped_extend.c:4588-4724 (uniform across lanes) ---- */
+        /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every thread, same values) ---- */
         if (!rev) {
             if (leftSeg.al >= 0) {
                 const dseg s = segs[al[leftSeg.al].segBegin + leftSeg.sg];
@@ -205,9 +223,9 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
             if (leftSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
         }
         if ((s64)(RY > prevLY ? RY - prevLY : 0) + yTail + 40 >= (s64)cap) { status = DP_RING; break; }
-        /* ---- update_active_segs gapped_extend.c:4885-4962 (lane 0; the list is tiny) ---- */
+        /* ---- update_active_segs gapped_extend.c:4885-4962 (thread 0; the list is tiny) ---- */
         if (nact > 0 || alignList >= 0) {
-            if (lane == 0) {
+            if (tid == 0) {
                 for (int k = 0; k < nact; k++) {
                     int* a = act + 5 * k;
                     if ((u32)a[3] >= row) {
@@ -236,30 +254,31 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
                 int w = 0;
                 for (int k = 0; k < nact; k++) if (act[5 * k + 4] >= 0) { if (w != k) for (int z = 0; z < 5; z++) act[5 * w + z] = act[5 * k + z]; w++; }
                 nact = w;
+                sh->nact = nact; sh->alignList = alignList; sh->status = status;
             }
-            nact = __shfl_sync(FULL, nact, 0); alignList = __shfl_sync(FULL, alignList, 0); status = __shfl_sync(FULL, status, 0);
+            __syncthreads();
+            nact = sh->nact; alignList = sh->alignList; status = sh->status;
             if (status != DP_OK) break;
         }
-        __syncwarp();
         /* ---- traceback capacity gapped_extend.c:3636-3662 ---- */
         if (RY < LY) RY = LY;
         s64 need = (s64)(RY - LY) + yTail;
         if (used + need >= tbLen) { status = DP_TRUNCATED; break; }
         if (row >= J->tbRowCap) { status = DP_TBROW; break; }
         const u32 tbBase = (u32)((u64)used - (u64)LY);            /* tbRow[row], modulo 2^32 like the walk */
-        if (lane == 0) tbRow[row] = tbBase;
+        if (tid == 0) tbRow[row] = tbBase;
         /* ---- the sweep, gapped_extend.c:3669-3774 ---- */
         const u32 leftCol = LY;
         const u32 colEnd = RY < N + 1 ? RY : N + 1;
         const u32 width = colEnd > LY ? colEnd - LY : 0;
-        const u32 k = ((width + 31) / 32) | 1;
-        const u32 j0 = LY + lane * k;
-        const u32 j1 = (j0 + k < colEnd) ? j0 + k : colEnd;       /* may be <= j0: idle lane */
+        const u32 k = ((width + DP_THREADS - 1) / DP_THREADS) | 1;
+        const u32 j0 = LY + tid * k;
+        const u32 j1 = (j0 + k < colEnd) ? j0 + k : colEnd;       /* may be <= j0: idle thread */
         s64 ai = !rev ? (s64)a1 + row : (s64)a1 + 1 - (s64)row;
         const u8 ac = (ai < 0 || ai >= (s64)len1) ? cls0 : cls1[ai];
         const s32* subRow = subC + ac * LZB_MAX_CLASSES;
         const bool masking = nact > 0;
-        /* pass 1: this lane's insertion-chain map */
+        /* pass 1: this thread's insertion-chain map */
         xf mine; mine.A = LZB_NEG_INF; mine.S = 0; mine.r = 0;
         {
             s32 pc = (j0 > LY && j0 < colEnd) ? Cprev[(j0 - 1) & msk] : LZB_NEG_INF;
@@ -275,17 +294,23 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
                 mine = xf_then(mine, g);
             }
         }
-        /* exclusive scan of the maps over lanes; I enters the row as -inf */
+        /* block-wide exclusive scan of the maps; I enters the row as -inf */
         xf inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             xf up; up.A = __shfl_up_sync(FULL, inc.A, o); up.S = __shfl_up_sync(FULL, inc.S, o); up.r = __shfl_up_sync(FULL, inc.r, o);
             if ((int)lane >= o) inc = xf_then(up, inc);
         }
-        s32 Iin = __shfl_up_sync(FULL, inc.A, 1);
-        if (lane == 0) Iin = LZB_NEG_INF;
-        /* the value of I leaving the row's last cell */
-        s32 Iout = __shfl_sync(FULL, inc.A, 31);
+        if (lane == 31) sh->wagg[warp] = inc;
+        xf exl; exl.A = __shfl_up_sync(FULL, inc.A, 1); exl.S = __shfl_up_sync(FULL, inc.S, 1); exl.r = __shfl_up_sync(FULL, inc.r, 1);
+        if (lane == 0) { exl.A = LZB_NEG_INF; exl.S = 0; exl.r = 0; }
+        __syncthreads();
+        xf pre; pre.A = LZB_NEG_INF; pre.S = 0; pre.r = 0;
+        xf tot = pre;
+#pragma unroll
+        for (int w = 0; w < DP_WARPS; w++) { xf a = sh->wagg[w]; if (w < (int)warp) pre = xf_then(pre, a); tot = xf_then(tot, a); }
+        const s32 Iin = xf_then(pre, exl).A;
+        const s32 Iout = tot.A;                                    /* I leaving the row's last cell */
         /* pass 2: cell values, links, next row's D; candidates for bestScore */
         s32 candMax = LZB_NEG_INF;
         {
@@ -313,16 +338,21 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
                 I = In;
             }
         }
-        /* exclusive prefix max of the candidates, seeded with bestScore */
+        /* block-wide exclusive prefix max of the candidates, seeded with bestScore */
         s32 pm = candMax;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { s32 u = __shfl_up_sync(FULL, pm, o); if ((int)lane >= o) pm = max(pm, u); }
+        if (lane == 31) sh->wmax[warp] = pm;
         s32 B = __shfl_up_sync(FULL, pm, 1);
         if (lane == 0) B = LZB_NEG_INF;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < DP_WARPS; w++) if (w < (int)warp) B = max(B, sh->wmax[w]);
         B = max(B, best);
         /* pass 3: prune, band edges, best/end */
         u32 firstAlive = 0xFFFFFFFFu, lastAlive = 0; bool anyAlive = false;
-        s32 upVal = LZB_NEG_INF; u32 upCol = 0; bool upd = false;
+        s32 upVal = 0; u32 upCol = 0; bool upd = false;
+        s32 bVal = 0; u32 bCol = 0; bool bUpd = false;
         for (u32 j = j0; j < j1; j++) {
             s32 c = Ccur[j & msk]; u32 f = flg[j & msk];
             bool alive = !(f & F_MASK) && c >= B - yDrop;
@@ -330,40 +360,39 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
             tb[(u32)(tbBase + j)] = (u8)(f & 15);
             if (!anyAlive) { firstAlive = j; anyAlive = true; }
             lastAlive = j;
-            if ((f & F_CAND) && c >= B) { B = c; upVal = c; upCol = j; upd = true; }
+            if (f & F_CAND) {
+                if (c >= B) { B = c; upVal = c; upCol = j; upd = true; }
+                if (!trim && (row == M || j == N) && (!bUpd || c >= bVal)) { bVal = c; bCol = j; bUpd = true; }
+            }
         }
-        /* reduce across lanes */
-        u32 fa = firstAlive, la = anyAlive ? lastAlive + 1 : 0;       /* la = lastAlive+1, 0 = none */
-        s32 nb = upd ? upVal : LZB_NEG_INF;
+        /* block reductions: band edges; (value, column) keys so that ties go to the later cell.
+         * Values that matter are >= best >= 0 (bestScore) -- boundary scores may be negative, so
+         * they are biased into unsigned order. */
+        u32 fa = firstAlive, la = anyAlive ? lastAlive + 1 : 0;
+        unsigned long long key = upd ? (((unsigned long long)(u32)upVal << 32) | (upCol + 1)) : 0ull;
+        unsigned long long bkey = bUpd ? (((unsigned long long)((u32)bVal ^ 0x80000000u) << 32) | (bCol + 1)) : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             fa = min(fa, __shfl_xor_sync(FULL, fa, o)); la = max(la, __shfl_xor_sync(FULL, la, o));
-            nb = max(nb, __shfl_xor_sync(FULL, nb, o));
+            unsigned long long ok = __shfl_xor_sync(FULL, key, o); if (ok > key) key = ok;
+            if (!trim) { unsigned long long ob = __shfl_xor_sync(FULL, bkey, o); if (ob > bkey) bkey = ob; }
+        }
+        if (lane == 0) { sh->wfa[warp] = fa; sh->wla[warp] = la; sh->wkey[warp] = key; sh->wbkey[warp] = bkey; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < DP_WARPS; w++) {
+            fa = min(fa, sh->wfa[w]); la = max(la, sh->wla[w]);
+            unsigned long long ok = sh->wkey[w]; if (ok > key) key = ok;
+            unsigned long long ob = sh->wbkey[w]; if (ob > bkey) bkey = ob;
         }
         /* bestScore moves to the LAST cell (row-major) that equalled the row's final best (:3742) */
         u32 bestCol = 0; bool bestMoved = false;
-        if (nb > LZB_NEG_INF) {
-            u32 cnd = (upd && upVal == nb) ? upCol + 1 : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cnd = max(cnd, __shfl_xor_sync(FULL, cnd, o));
-            bestCol = cnd - 1; bestMoved = true; best = nb;
-        }
-        /* boundaryScore (:3747-3750, only without y-drop trimming) moves the same way over the
-         * surviving diagonal winners on the last row / last column */
+        if (key) { best = (s32)(u32)(key >> 32); bestCol = (u32)key - 1; bestMoved = true; }
+        /* boundaryScore (:3747-3750, only without y-drop trimming) */
         u32 bndCol = 0; bool bndMoved = false;
-        if (!trim) {
-            s32 lm = LZB_NEG_INF; u32 lc = 0; bool lu = false;
-            for (u32 j = j0; j < j1; j++) {
-                u32 f = flg[j & msk]; s32 c = Ccur[j & msk];
-                if ((f & F_CAND) && c > LZB_NEG_INF && (row == M || j == N) && c >= lm) { lm = c; lc = j; lu = true; }
-            }
-            s32 gm = lu ? lm : LZB_NEG_INF;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) gm = max(gm, __shfl_xor_sync(FULL, gm, o));
-            u32 gc = (lu && lm == gm) ? lc + 1 : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) gc = max(gc, __shfl_xor_sync(FULL, gc, o));
-            if (gm > LZB_NEG_INF && gm >= bnd) { bnd = gm; bndCol = gc - 1; bndMoved = true; }
+        if (!trim && bkey) {
+            s32 gm = (s32)((u32)(bkey >> 32) ^ 0x80000000u);
+            if (gm >= bnd) { bnd = gm; bndCol = (u32)bkey - 1; bndMoved = true; }
         }
         /* the later event in row-major order owns the end cell; in one cell the boundary test runs second */
         if (bestMoved && (!bndMoved || bestCol > bndCol)) { end1 = row; end2 = bestCol; endIsBnd = 0; }
@@ -372,7 +401,6 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
         used += colEnd - leftCol;
         u32 npCol;
         if (la) { LY = fa; npCol = la - 1; } else { LY = colEnd; npCol = leftCol; }
-        __syncwarp();
         s32* t = Cprev; Cprev = Ccur; Ccur = t;
         if (LY >= RY) break;
         /* ---- row end, gapped_extend.c:3789-3827 ---- */
@@ -387,7 +415,7 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
                 p = byScore < room ? byScore : room;
             }
             if ((s64)(RY + p + 2 - LY) + 8 >= (s64)cap) { status = DP_RING; break; }
-            for (u32 q = lane; q < p; q += 32) {
+            for (u32 q = tid; q < p; q += DP_THREADS) {
                 s32 v = Iout - (s32)q * gapE;
                 Cprev[(wcol + q) & msk] = v; Dv[(wcol + q) & msk] = v - gapOE;
                 tb[(u32)(tbBase + wcol + q)] = LINK_I;
@@ -395,14 +423,15 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
             wcol += p; RY += p; used += p;
         }
         if ((s32)RY <= NN) {
-            if (lane == 0) { Cprev[wcol & msk] = LZB_NEG_INF; Dv[wcol & msk] = LZB_NEG_INF; }
+            if (tid == 0) { Cprev[wcol & msk] = LZB_NEG_INF; Dv[wcol & msk] = LZB_NEG_INF; }
             RY++;
         }
-        __syncwarp();
+        __syncthreads();
     }
-    /* ---- traceback, gapped_extend.c:3847-3859: 32 diagonal steps per iteration ---- */
-    __syncwarp();
-    __threadfence_block();
+    /* ---- traceback, gapped_extend.c:3847-3859: warp 0, 32 diagonal steps per iteration ---- */
+    __threadfence();
+    __syncthreads();
+    if (warp != 0) return;
     u32 nops = 0;
     if (status == DP_OK || status == DP_TRUNCATED) {
         u32 r = end1, c = end2; u32 prevOp = 0;
@@ -417,8 +446,8 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
                 if (prevOp == LINK_I && (link & LINK_IEXT)) op = LINK_I;
                 if (prevOp == LINK_D && (link & LINK_DEXT)) op = LINK_D;
             }
-            /* lane t>0 assumes the step before it was a substitution, true iff all earlier lanes are subs.
-             * a diagonal step needs r-t >= 1 and c-t >= 1 */
+            /* lane t>0 assumes the step before it was a substitution, true iff all earlier lanes are
+             * substitutions; a diagonal step needs r-t >= 1 and c-t >= 1 */
             bool isSub = inb && op == 0 && (r - lane) >= 1 && (c - lane) >= 1;
             u32 notSub = __ballot_sync(FULL, !isSub);
             u32 run = notSub ? (u32)(__ffs(notSub) - 1) : 32;
@@ -428,7 +457,6 @@ k_ydrop(dp_job* jobs, const dalign* __restrict__ al, const dseg* __restrict__ se
                 r -= run; c -= run; prevOp = 0;
                 continue;
             }
-            /* lane 0's step is a gap step (or a substitution forced at the matrix edge) */
             u32 op0 = __shfl_sync(FULL, op, 0);
             u32 eop;
             if (op0 == LINK_I) { c--; eop = LZB_OP_INS; }
@@ -533,7 +561,6 @@ struct gx {                             /* state of one lzb_gapped_extend call *
     std::vector<int> committed;         /* host alignment indices in commit order = device table order */
     std::vector<dseg> hsegs;            /* device segment table (host mirror) */
     std::vector<dalign> haligns;
-    dseg* d_segs; size_t d_segsCap; dalign* d_aligns; size_t d_alignsCap;
     lzb_gapped_stats st;
 };
 
@@ -623,37 +650,51 @@ static s32 rescore(gx& G, u32 p1, u32 p2, lzb_editscript* s) {
 
 static segref dev_ref(gx& G, segref r) { segref o = NOSEG; if (r.al >= 0) { o.al = G.al[r.al].devIx; o.sg = r.sg; } return o; }
 
-/* push the committed alignments the device has not seen yet, and refresh the list links */
-static int sync_device_tables(gx& G) {
-    lzb_ctx* c = G.c;
-    size_t haveA = G.haligns.size();
-    for (size_t k = haveA; k < G.committed.size(); k++) {
-        galn& m = G.al[G.committed[k]];
-        dalign d; memset(&d, 0, sizeof d);
-        d.segBegin = (int)G.hsegs.size(); d.segCount = (int)m.segs.size();
-        for (auto& s : m.segs) { dseg x = { s.b1, s.b2, s.e1, s.e2, s.type }; G.hsegs.push_back(x); }
-        G.haligns.push_back(d);
-    }
-    for (size_t k = 0; k < G.committed.size(); k++) {
-        galn& m = G.al[G.committed[k]]; dalign& d = G.haligns[k];
-        d.pos1 = m.pos1; d.end1 = m.end1;
-        d.left1 = dev_ref(G, m.left1); d.right1 = dev_ref(G, m.right1); d.left2 = dev_ref(G, m.left2); d.right2 = dev_ref(G, m.right2);
-        d.next = m.next >= 0 ? G.al[m.next].devIx : -1; d.prev = m.prev >= 0 ? G.al[m.prev].devIx : -1;
-    }
-    if (G.hsegs.size() > G.d_segsCap) {
-        cudaFree(G.d_segs); G.d_segsCap = G.hsegs.size() * 2 + 1024;
-        CUDA_TRY(cudaMalloc(&G.d_segs, G.d_segsCap * sizeof(dseg)));
-    }
-    if (G.haligns.size() > G.d_alignsCap) {
-        cudaFree(G.d_aligns); G.d_alignsCap = G.haligns.size() * 2 + 256;
-        CUDA_TRY(cudaMalloc(&G.d_aligns, G.d_alignsCap * sizeof(dalign)));
-    }
-    if (!G.hsegs.empty()) CUDA_TRY(cudaMemcpyAsync(G.d_segs, G.hsegs.data(), G.hsegs.size() * sizeof(dseg), cudaMemcpyHostToDevice, c->stream));
-    if (!G.haligns.empty()) CUDA_TRY(cudaMemcpyAsync(G.d_aligns, G.haligns.data(), G.haligns.size() * sizeof(dalign), cudaMemcpyHostToDevice, c->stream));
-    return 0;
+/* one speculation lane: a stream, the two one-sided DPs of one anchor, their buffers */
+struct gx_lane {
+    cudaStream_t stream; cudaEvent_t evA, evB;
+    dp_job* h_jobs;                      /* pinned, 2 entries */
+    dp_job* d_jobs;
+    dalign* d_aligns; size_t alignsCap;  /* private snapshot of the alignment table */
+    u8* tb[2]; u32 tbBytes; u32* tbRow[2]; u32 tbRowCap[2]; u32* ops[2]; u32 opsCap[2]; int* act[2]; u32 actCap[2];
+    /* state */
+    bool busy; u64 anchor; size_t snapshot; segref left1, right1; u32 ring;
+};
+
+struct gx_cache {                        /* lives in the context: lanes are expensive to allocate */
+    std::vector<gx_lane> lanes; u32 tbBytes;
+    dseg* d_segs; size_t segsCap, segsUploaded;
+};
+
+static void free_lane(gx_lane& ln) {
+    cudaStreamDestroy(ln.stream); cudaEventDestroy(ln.evA); cudaEventDestroy(ln.evB);
+    cudaFreeHost(ln.h_jobs); cudaFree(ln.d_jobs); cudaFree(ln.d_aligns);
+    for (int s = 0; s < 2; s++) { cudaFree(ln.tb[s]); cudaFree(ln.tbRow[s]); cudaFree(ln.ops[s]); cudaFree(ln.act[s]); }
 }
 
-struct slot_bufs { u8* tb; u32* tbRow; u32 tbRowCap; u32* ops; u32 opsCap; int* act; u32 actCap; };
+void lzb_gapped_cache_free(lzb_ctx* c) {
+    gx_cache* gc = (gx_cache*)c->gappedCache;
+    if (!gc) return;
+    for (auto& ln : gc->lanes) free_lane(ln);
+    cudaFree(gc->d_segs);
+    delete gc; c->gappedCache = NULL;
+}
+
+static int make_lane(gx_lane& ln, u32 tbBytes, u32 tbLen) {
+    memset(&ln, 0, sizeof ln);
+    CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ln.evA)); CUDA_TRY(cudaEventCreate(&ln.evB));
+    CUDA_TRY(cudaHostAlloc(&ln.h_jobs, 2 * sizeof(dp_job), cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc(&ln.d_jobs, 2 * sizeof(dp_job)));
+    ln.tbBytes = tbBytes;
+    for (int s = 0; s < 2; s++) {
+        CUDA_TRY(cudaMalloc(&ln.tb[s], (size_t)tbBytes + 64));
+        ln.tbRowCap[s] = tbLen / 24 + 4096; CUDA_TRY(cudaMalloc(&ln.tbRow[s], (size_t)ln.tbRowCap[s] * 4));
+        ln.opsCap[s] = 1u << 20; CUDA_TRY(cudaMalloc(&ln.ops[s], (size_t)ln.opsCap[s] * 4));
+        ln.actCap[s] = 256; CUDA_TRY(cudaMalloc(&ln.act[s], (size_t)ln.actCap[s] * 5 * 4));
+    }
+    return 0;
+}
 
 struct spec_result {                    /* a finished (possibly speculative) two-sided extension */
     bool have; size_t snapshot;         /* committed.size() when it was launched */
@@ -671,7 +712,6 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     u64 launches0 = c->launches;
     *list = NULL;
     gx G; G.c = c; G.t = t; G.q = q; G.P = P; G.obi = G.oed = -1;
-    G.d_segs = NULL; G.d_segsCap = 0; G.d_aligns = NULL; G.d_alignsCap = 0;
     memset(&G.st, 0, sizeof G.st); G.st.anchors = n;
     const u32 tbLen = 1 + (P->tracebackBytes - 8);                    /* new_traceback :2272-2290 */
     const u32 len1 = t->len, len2 = q->len;
@@ -712,115 +752,161 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         }
     }
 
-    /* ---- device buffers: two slots (left, right) per speculative anchor ---- */
-    int W = P->speculation < 1 ? 1 : (P->speculation > 64 ? 64 : P->speculation);
-    const char* wenv = getenv("LZB_SPECULATION"); if (wenv) { W = atoi(wenv); if (W < 1) W = 1; if (W > 64) W = 64; }
+    /* ---- speculation lanes (cached in the context across calls) ---- */
+    int W = P->speculation < 1 ? 1 : (P->speculation > 128 ? 128 : P->speculation);
+    const char* wenv = getenv("LZB_SPECULATION"); if (wenv) { W = atoi(wenv); if (W < 1) W = 1; if (W > 128) W = 128; }
     if ((u64)W > n) W = n ? (int)n : 1;
-    u32 cap = 4096;                                         /* sweep-row ring, columns */
-    const char* cenv = getenv("LZB_RING"); if (cenv) cap = (u32)atoi(cenv);
-    u32 tbRowCap = tbLen / 24 + 4096, opsCap = 1u << 20, actCap = 256;
-    std::vector<slot_bufs> slots(2 * W);
-    std::vector<dp_job> hjobs(2 * W);
-    dp_job* d_jobs = NULL;
-    auto free_slots = [&]() { for (auto& s : slots) { cudaFree(s.tb); cudaFree(s.tbRow); cudaFree(s.ops); cudaFree(s.act); } cudaFree(d_jobs); cudaFree(G.d_segs); cudaFree(G.d_aligns); };
-    for (auto& s : slots) { memset(&s, 0, sizeof s); }
-    for (auto& s : slots) {
-        CUDA_TRY(cudaMalloc(&s.tb, (size_t)P->tracebackBytes + 64));
-        s.tbRowCap = tbRowCap; CUDA_TRY(cudaMalloc(&s.tbRow, (size_t)tbRowCap * 4));
-        s.opsCap = opsCap; CUDA_TRY(cudaMalloc(&s.ops, (size_t)opsCap * 4));
-        s.actCap = actCap; CUDA_TRY(cudaMalloc(&s.act, (size_t)actCap * 5 * 4));
+    u32 ring0 = 4096;                                       /* sweep-row ring, columns */
+    const char* cenv = getenv("LZB_RING"); if (cenv) ring0 = (u32)atoi(cenv);
+    gx_cache* gc = (gx_cache*)c->gappedCache;
+    if (gc && gc->tbBytes != P->tracebackBytes) { lzb_gapped_cache_free(c); gc = NULL; }
+    if (!gc) { gc = new gx_cache(); gc->tbBytes = P->tracebackBytes; gc->d_segs = NULL; gc->segsCap = 0; gc->segsUploaded = 0; c->gappedCache = gc; }
+    while ((int)gc->lanes.size() < W) {
+        gx_lane ln;
+        if (make_lane(ln, P->tracebackBytes, tbLen)) return -1;
+        gc->lanes.push_back(ln);
     }
-    CUDA_TRY(cudaMalloc(&d_jobs, (size_t)2 * W * sizeof(dp_job)));
-    cudaEvent_t evA, evB; CUDA_TRY(cudaEventCreate(&evA)); CUDA_TRY(cudaEventCreate(&evB));
+    for (auto& ln : gc->lanes) { ln.busy = false; }
+    gc->segsUploaded = 0;
     CUDA_TRY(cudaFuncSetAttribute(k_ydrop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
     std::vector<spec_result> spec(n);
     for (auto& s : spec) s.have = false;
-    u64 reach = tbLen / 300 + 1000;                          /* rows a DP is expected to cover, for batch selection */
+    std::vector<char> inflight(n, 0);
+    u64 reach = tbLen / 300 + 1000;                          /* rows a DP is expected to cover */
 
-    /* runs the DPs of the chosen anchors (left+right each) and stores their results */
-    auto run_batch = [&](const std::vector<u64>& pick) -> int {
-        if (sync_device_tables(G)) return -1;
-        size_t snap = G.committed.size();
-        std::vector<int> todo;                               /* job indices still to run */
-        for (size_t b = 0; b < pick.size(); b++) {
-            galn& m = G.al[pick[b]];
-            /* get_above_below :4043-4060 */
-            int below = G.oed; while (below >= 0 && !(G.al[below].end1 < m.pos1)) below = G.al[below].prev;
-            int above = G.obi; while (above >= 0 && !(G.al[above].pos1 > m.pos1)) above = G.al[above].next;
-            for (int side = 0; side < 2; side++) {
-                dp_job& J = hjobs[2 * b + side]; memset(&J, 0, sizeof J);
-                int rev = side == 0;
-                J.reversed = rev; J.a1 = m.pos1; J.a2 = m.pos2;
-                J.M = rev ? m.pos1 + 1 : len1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 : len2 - (m.pos2 + 1);
-                /* initial L/R, gapped_extend.c:3500-3543 */
-                s32 L = 0, R = (s32)(J.N + 1);
-                if (m.left1.al >= 0) { hseg& s = G.al[m.left1.al].segs[m.left1.sg]; L = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) L -= (s32)(s.b1 - m.pos1); }
-                if (m.right1.al >= 0) { hseg& s = G.al[m.right1.al].segs[m.right1.sg]; R = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) R -= (s32)(s.b1 - m.pos1); }
-                if (rev) {
-                    if (m.left1.al < 0 && m.right1.al >= 0) { L = -R + 1; R = (s32)(J.N + 1); }
-                    else if (m.left1.al >= 0 && m.right1.al < 0) { R = -L - 1; L = 0; }
-                    else if (m.left1.al >= 0 && m.right1.al >= 0) { s32 tt = -L - 1; L = -R + 1; R = tt; }
-                }
-                J.L0 = L; J.R0 = R;
-                J.leftSeg = dev_ref(G, m.left1); J.rightSeg = dev_ref(G, m.right1);
-                int lst = rev ? below : above;
-                J.alignList = lst >= 0 ? G.al[lst].devIx : -1;
-                todo.push_back((int)(2 * b + side));
-            }
+    /* append newly committed alignments to the device segment table (append-only, so running
+     * kernels are undisturbed); the alignment table itself is snapshotted per launch */
+    auto push_segments = [&]() -> int {
+        size_t haveA = G.haligns.size();
+        for (size_t k = haveA; k < G.committed.size(); k++) {
+            galn& m = G.al[G.committed[k]];
+            dalign d; memset(&d, 0, sizeof d);
+            d.segBegin = (int)G.hsegs.size(); d.segCount = (int)m.segs.size();
+            for (auto& s : m.segs) { dseg x = { s.b1, s.b2, s.e1, s.e2, s.type }; G.hsegs.push_back(x); }
+            G.haligns.push_back(d);
         }
-        u32 ring = cap;
-        while (!todo.empty()) {
-            /* compact the jobs to run into the front of the device array */
-            std::vector<dp_job> run(todo.size());
-            for (size_t k = 0; k < todo.size(); k++) {
-                dp_job J = hjobs[todo[k]]; slot_bufs& s = slots[todo[k]];
-                J.tb = s.tb; J.tbLen = tbLen; J.tbRow = s.tbRow; J.tbRowCap = s.tbRowCap; J.ops = s.ops; J.opsCap = s.opsCap; J.act = s.act; J.actCap = s.actCap;
-                run[k] = J;
-            }
-            CUDA_TRY(cudaMemcpyAsync(d_jobs, run.data(), run.size() * sizeof(dp_job), cudaMemcpyHostToDevice, c->stream));
-            size_t smem = (size_t)ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 64;
-            CUDA_TRY(cudaEventRecord(evA, c->stream));
-            k_ydrop<<<(int)run.size(), 32, smem, c->stream>>>(d_jobs, G.d_aligns, G.d_segs, t->d_cls, q->d_cls, len1, len2,
-                                                            c->d_sc, P->yDrop, P->trimToPeak, ring);
-            c->launches++;
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(evB, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(run.data(), d_jobs, run.size() * sizeof(dp_job), cudaMemcpyDeviceToHost, c->stream));
+        if (G.hsegs.size() > gc->segsCap) {
+            /* running kernels hold the old pointer: drain them first */
+            for (auto& ln : gc->lanes) if (ln.busy) CUDA_TRY(cudaStreamSynchronize(ln.stream));
+            cudaFree(gc->d_segs); gc->segsCap = G.hsegs.size() * 2 + (1u << 20);
+            CUDA_TRY(cudaMalloc(&gc->d_segs, gc->segsCap * sizeof(dseg)));
+            gc->segsUploaded = 0;
+        }
+        if (G.hsegs.size() > gc->segsUploaded) {
+            CUDA_TRY(cudaMemcpyAsync(gc->d_segs + gc->segsUploaded, G.hsegs.data() + gc->segsUploaded,
+                                     (G.hsegs.size() - gc->segsUploaded) * sizeof(dseg), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            float ms = 0; cudaEventElapsedTime(&ms, evA, evB); G.st.kernelSeconds[0] += ms / 1e3;
-            std::vector<int> again; bool growRing = false;
-            for (size_t k = 0; k < todo.size(); k++) {
-                dp_job& J = run[k]; int ji = todo[k]; slot_bufs& s = slots[ji];
-                if (J.status == DP_RING) { growRing = true; again.push_back(ji); continue; }
-                if (J.status == DP_TBROW) {
-                    cudaFree(s.tbRow); s.tbRowCap = s.tbRowCap * 4 < tbLen ? s.tbRowCap * 4 : tbLen + 8;
-                    CUDA_TRY(cudaMalloc(&s.tbRow, (size_t)s.tbRowCap * 4)); again.push_back(ji); continue;
-                }
-                if (J.status == DP_OPS) { cudaFree(s.ops); s.opsCap *= 4; CUDA_TRY(cudaMalloc(&s.ops, (size_t)s.opsCap * 4)); again.push_back(ji); continue; }
-                if (J.status == DP_ACT) { cudaFree(s.act); s.actCap *= 4; CUDA_TRY(cudaMalloc(&s.act, (size_t)s.actCap * 5 * 4)); again.push_back(ji); continue; }
-                spec_result& sr = spec[pick[ji / 2]];
-                dp_result& r = (ji & 1) ? sr.R : sr.L;
-                r.score = J.score; r.end1 = J.end1; r.end2 = J.end2; r.rows = J.rows; r.status = J.status; r.cells = J.cells;
-                r.ops.resize(J.nops);
-                if (J.nops) CUDA_TRY(cudaMemcpy(r.ops.data(), s.ops, (size_t)J.nops * 4, cudaMemcpyDeviceToHost));
-            }
-            if (growRing) {
-                if (ring >= 8192) { free_slots(); return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ring); }
-                ring *= 2;
-            }
-            todo.swap(again);
+            gc->segsUploaded = G.hsegs.size();
         }
-        for (size_t b = 0; b < pick.size(); b++) {
-            spec_result& sr = spec[pick[b]]; galn& m = G.al[pick[b]];
-            sr.have = true; sr.snapshot = snap; sr.left1 = m.left1; sr.right1 = m.right1;
-            G.st.dpCells += sr.L.cells + sr.R.cells; G.st.dpRows += sr.L.rows + sr.R.rows;
-            G.st.truncated += (sr.L.status == DP_TRUNCATED) + (sr.R.status == DP_TRUNCATED);
+        for (size_t k = 0; k < G.committed.size(); k++) {
+            galn& m = G.al[G.committed[k]]; dalign& d = G.haligns[k];
+            d.pos1 = m.pos1; d.end1 = m.end1;
+            d.left1 = dev_ref(G, m.left1); d.right1 = dev_ref(G, m.right1); d.left2 = dev_ref(G, m.left2); d.right2 = dev_ref(G, m.right2);
+            d.next = m.next >= 0 ? G.al[m.next].devIx : -1; d.prev = m.prev >= 0 ? G.al[m.prev].devIx : -1;
         }
         return 0;
     };
+    bool tablesDirty = true;
 
-    /* ---- the anchor loop, gapped_extend.c:1300-1470, committed strictly in score order ---- */
+    auto launch = [&](gx_lane& ln, int onlySide) -> int {
+        galn& m = G.al[ln.anchor];
+        const segref mLeft = ln.left1, mRight = ln.right1;   /* the neighbours this anchor was started with */
+        if (tablesDirty) { if (push_segments()) return -1; tablesDirty = false; }
+        if (G.haligns.size() > ln.alignsCap) {
+            cudaFree(ln.d_aligns); ln.alignsCap = G.haligns.size() * 2 + 256;
+            CUDA_TRY(cudaMalloc(&ln.d_aligns, ln.alignsCap * sizeof(dalign)));
+        }
+        if (!G.haligns.empty())
+            CUDA_TRY(cudaMemcpyAsync(ln.d_aligns, G.haligns.data(), G.haligns.size() * sizeof(dalign), cudaMemcpyHostToDevice, ln.stream));
+        /* get_above_below :4043-4060 */
+        int below = G.oed; while (below >= 0 && !(G.al[below].end1 < m.pos1)) below = G.al[below].prev;
+        int above = G.obi; while (above >= 0 && !(G.al[above].pos1 > m.pos1)) above = G.al[above].next;
+        for (int side = 0; side < 2; side++) {
+            dp_job& J = ln.h_jobs[side];
+            memset(&J, 0, sizeof J);
+            if (onlySide >= 0 && side != onlySide) { J.skip = 1; continue; }     /* kernel returns at once */
+            int rev = side == 0;
+            J.reversed = rev; J.a1 = m.pos1; J.a2 = m.pos2;
+            J.M = rev ? m.pos1 + 1 : len1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 : len2 - (m.pos2 + 1);
+            /* initial L/R, gapped_extend.c:3500-3543 */
+            s32 L = 0, R = (s32)(J.N + 1);
+            if (mLeft.al >= 0) { hseg& s = G.al[mLeft.al].segs[mLeft.sg]; L = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) L -= (s32)(s.b1 - m.pos1); }
+            if (mRight.al >= 0) { hseg& s = G.al[mRight.al].segs[mRight.sg]; R = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) R -= (s32)(s.b1 - m.pos1); }
+            if (rev) {
+                if (mLeft.al < 0 && mRight.al >= 0) { L = -R + 1; R = (s32)(J.N + 1); }
+                else if (mLeft.al >= 0 && mRight.al < 0) { R = -L - 1; L = 0; }
+                else if (mLeft.al >= 0 && mRight.al >= 0) { s32 tt = -L - 1; L = -R + 1; R = tt; }
+            }
+            J.L0 = L; J.R0 = R;
+            J.leftSeg = dev_ref(G, mLeft); J.rightSeg = dev_ref(G, mRight);
+            int lst = rev ? below : above;
+            J.alignList = lst >= 0 ? G.al[lst].devIx : -1;
+            J.al = ln.d_aligns;
+            J.tb = ln.tb[side]; J.tbLen = tbLen; J.tbRow = ln.tbRow[side]; J.tbRowCap = ln.tbRowCap[side];
+            J.ops = ln.ops[side]; J.opsCap = ln.opsCap[side]; J.act = ln.act[side]; J.actCap = ln.actCap[side];
+        }
+        CUDA_TRY(cudaMemcpyAsync(ln.d_jobs, ln.h_jobs, 2 * sizeof(dp_job), cudaMemcpyHostToDevice, ln.stream));
+        size_t smem = (size_t)ln.ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
+        CUDA_TRY(cudaEventRecord(ln.evA, ln.stream));
+        k_ydrop<<<2, DP_THREADS, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
+                                                   c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ln.evB, ln.stream));
+        CUDA_TRY(cudaMemcpyAsync(ln.h_jobs, ln.d_jobs, 2 * sizeof(dp_job), cudaMemcpyDeviceToHost, ln.stream));
+        return 0;
+    };
+
+    auto start_anchor = [&](gx_lane& ln, u64 ai) -> int {
+        galn& m = G.al[ai];
+        ln.busy = true; ln.anchor = ai; ln.snapshot = G.committed.size(); ln.left1 = m.left1; ln.right1 = m.right1; ln.ring = ring0;
+        inflight[ai] = 1;
+        return launch(ln, -1);
+    };
+
+    /* a lane's stream has drained: collect the result, or rerun a side that outgrew a buffer */
+    auto harvest = [&](gx_lane& ln) -> int {
+        float ms = 0; cudaEventElapsedTime(&ms, ln.evA, ln.evB); G.st.kernelSeconds[0] += ms / 1e3;
+        spec_result& sr = spec[ln.anchor];
+        int redo = -2;                                       /* -2 none, -1 both, 0/1 one side */
+        for (int side = 0; side < 2; side++) {
+            dp_job& J = ln.h_jobs[side];
+            if (J.skip) continue;                            /* side finished in an earlier pass */
+            bool again = false;
+            if (J.status == DP_RING) {
+                if (ln.ring >= 8192) return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ln.ring);
+                again = true;
+            } else if (J.status == DP_TBROW) {
+                cudaFree(ln.tbRow[side]); ln.tbRowCap[side] = ln.tbRowCap[side] * 4 < tbLen ? ln.tbRowCap[side] * 4 : tbLen + 8;
+                CUDA_TRY(cudaMalloc(&ln.tbRow[side], (size_t)ln.tbRowCap[side] * 4)); again = true;
+            } else if (J.status == DP_OPS) {
+                cudaFree(ln.ops[side]); ln.opsCap[side] *= 4; CUDA_TRY(cudaMalloc(&ln.ops[side], (size_t)ln.opsCap[side] * 4)); again = true;
+            } else if (J.status == DP_ACT) {
+                cudaFree(ln.act[side]); ln.actCap[side] *= 4; CUDA_TRY(cudaMalloc(&ln.act[side], (size_t)ln.actCap[side] * 5 * 4)); again = true;
+            }
+            if (again) { redo = (redo == -2) ? side : -1; continue; }
+            dp_result& r = side ? sr.R : sr.L;
+            r.score = J.score; r.end1 = J.end1; r.end2 = J.end2; r.rows = J.rows; r.status = J.status; r.cells = J.cells;
+            r.ops.resize(J.nops);
+            if (J.nops) CUDA_TRY(cudaMemcpyAsync(r.ops.data(), ln.ops[side], (size_t)J.nops * 4, cudaMemcpyDeviceToHost, ln.stream));
+            G.st.dpCells += J.cells; G.st.dpRows += J.rows; G.st.truncated += (J.status == DP_TRUNCATED);
+        }
+        CUDA_TRY(cudaStreamSynchronize(ln.stream));
+        if (redo != -2) {
+            bool ringGrow = false;
+            for (int side = 0; side < 2; side++) if (ln.h_jobs[side].status == DP_RING) ringGrow = true;
+            if (ringGrow) ln.ring *= 2;
+            /* rerun with the neighbours it was started with; the (possibly newer) alignment table is a
+             * superset, and validation still uses the ORIGINAL snapshot, so any difference is caught */
+            return launch(ln, redo);
+        }
+        sr.have = true; sr.snapshot = ln.snapshot; sr.left1 = ln.left1; sr.right1 = ln.right1;
+        ln.busy = false; inflight[ln.anchor] = 0;
+        return 0;
+    };
+
+    /* ---- the anchor loop, gapped_extend.c:1300-1470: commits strictly in score order ---- */
     u64 i = 0;
     while (i < n) {
         galn& m = G.al[i];
@@ -836,25 +922,52 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                 if (!((u64)x.end1 < lo || (u64)x.pos1 > hi)) usable = false;
             }
             if (usable && (sr.left1.al != m.left1.al || sr.left1.sg != m.left1.sg || sr.right1.al != m.right1.al || sr.right1.sg != m.right1.sg)) usable = false;
-            if (!usable) G.st.redone++;
+            if (!usable) { G.st.redone++; sr.have = false; }
         }
         if (!usable) {
-            /* launch a batch: this anchor plus later uncovered anchors that are unlikely to interact */
-            std::vector<u64> pick; pick.push_back(i);
-            for (u64 j = i + 1; j < n && (int)pick.size() < W; j++) {
-                if (spec[j].have) continue;                 /* validated (or redone) at its turn */
-                galn& y = G.al[j];
-                bool far = true;
-                for (u64 pj : pick) { u64 a = G.al[pj].pos1, b = y.pos1; if ((a > b ? a - b : b - a) < 2 * reach) { far = false; break; } }
-                if (!far) continue;
-                if (!anchor_neighbours(G, y)) continue;
-                pick.push_back(j);
-                if (j - i > 4096) break;
+            /* keep the lanes full: anchor i first, then later uncovered anchors that are unlikely to
+             * interact with anything still pending */
+            if (!inflight[i]) {
+                gx_lane* fl = NULL;
+                for (auto& ln : gc->lanes) if (!ln.busy && (&ln - &gc->lanes[0]) < W) { fl = &ln; break; }
+                if (fl) { if (start_anchor(*fl, i)) return -1; }
             }
-            G.st.speculated += pick.size() - 1;
-            if (run_batch(pick)) { free_slots(); return -1; }
-            { u64 r = std::max<u64>(spec[i].L.rows, spec[i].R.rows); reach = (reach * 3 + r) / 4 + 1; }
-            continue;                                      /* re-enter: now usable */
+            int freeLanes = 0;
+            for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
+            if (freeLanes > 0 && inflight[i]) {
+                std::vector<u64> pending;                    /* anchor rows of everything not yet committed */
+                for (int z = 0; z < W; z++) if (gc->lanes[z].busy) pending.push_back(G.al[gc->lanes[z].anchor].pos1);
+                u64 scanned = 0;
+                for (u64 j = i + 1; j < n && freeLanes > 0 && scanned < 20000; j++, scanned++) {
+                    if (inflight[j]) continue;
+                    if (spec[j].have) { pending.push_back(G.al[j].pos1); continue; }
+                    galn& y = G.al[j];
+                    bool far = true;
+                    for (u64 pr : pending) { u64 b = y.pos1; if ((pr > b ? pr - b : b - pr) < 2 * reach) { far = false; break; } }
+                    if (!far) continue;
+                    if (!anchor_neighbours(G, y)) continue;
+                    gx_lane* fl = NULL;
+                    for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
+                    if (!fl) break;
+                    if (start_anchor(*fl, j)) return -1;
+                    pending.push_back(y.pos1); freeLanes--; G.st.speculated++;
+                }
+            }
+            /* wait for any lane to finish, harvest every finished lane */
+            bool got = false;
+            while (!got) {
+                for (int z = 0; z < W; z++) {
+                    gx_lane& ln = gc->lanes[z];
+                    if (!ln.busy) continue;
+                    cudaError_t e = cudaStreamQuery(ln.stream);
+                    if (e == cudaSuccess) { if (harvest(ln)) return -1; if (!ln.busy) got = true; }
+                    else if (e != cudaErrorNotReady) return lzb_fail("Y-drop kernel failed: %s", cudaGetErrorString(e));
+                }
+                if (!got) std::this_thread::sleep_for(std::chrono::microseconds(20));
+            }
+            { u64 r = 0, cnt = 0; for (u64 j = i; j < n && cnt < 1; j++) if (spec[j].have) { r = std::max<u64>(spec[j].L.rows, spec[j].R.rows); cnt++; }
+              if (cnt) reach = (reach * 7 + r) / 8 + 1; }
+            continue;
         }
         /* ---- commit: ydrop_align's script assembly :2529-2580, format_alignment :5153 ---- */
         G.st.anchorsExtended++;
@@ -903,8 +1016,11 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         alignment_neighbours(G, m);
         list_insert(G, (int)i);
         m.devIx = (int)G.committed.size(); G.committed.push_back((int)i);
+        tablesDirty = true;
         i++;
     }
+    /* abandon speculative work that was never needed */
+    for (auto& ln : gc->lanes) if (ln.busy) { cudaStreamSynchronize(ln.stream); ln.busy = false; }
     lzb_alignel* head = NULL, *last = NULL;
     for (int o = G.obi; o >= 0; o = G.al[o].next) {
         galn& m = G.al[o];
@@ -912,8 +1028,6 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         if (drop) { free(m.align->script); free(m.align); }
         else { if (!head) head = last = m.align; else { last->next = m.align; last = m.align; } }
     }
-    cudaEventDestroy(evA); cudaEventDestroy(evB);
-    free_slots();
     *list = head;
     G.st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
     G.st.launches = c->launches - launches0;

@@ -52,7 +52,10 @@ struct lzb_ctx {
     lzb_scoring_dev sc;                      /* host mirror */
     lzb_scoring_dev* d_sc;                   /* device copy */
     u64 launches;                            /* kernels launched by this context */
+    void* gappedCache;                       /* gapped.cu: speculation lanes kept across calls */
 };
+
+void lzb_gapped_cache_free(lzb_ctx*);        /* gapped.cu */
 
 struct lzb_target {
     lzb_ctx* ctx;

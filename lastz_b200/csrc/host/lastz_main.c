@@ -169,6 +169,7 @@ int main(int argc, char** argv) {
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
     uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
+    double ks[8] = {0}, gk = 0; uint64_t gExt = 0, gSpec = 0, gRedo = 0, gLaunch = 0, gTrunc = 0;
     lzb_seqfile* qf = lzb_seqfile_open(o.querySpec);
     lzb_seq query;
     while (lzb_seqfile_next(qf, &query)) {
@@ -191,6 +192,7 @@ int main(int argc, char** argv) {
                 if (lzb_seed_hit_search(ctx, T, Q, &seed, lzb_upper_nuc_to_bits, &sp, &segs, &nsegs, &sst))
                     lzb_die("%s", lzb_last_error());
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
+                for (int z = 0; z < 8; z++) ks[z] += sst.kernelSeconds[z];
             }
             int headerDone = 0;
             if (!o.gapped) {
@@ -211,7 +213,8 @@ int main(int argc, char** argv) {
                 lzb_alignel* list = NULL;
                 if (lzb_gapped_extend(ctx, T, Q, target.v, query.v, segs, nsegs, &gp, &list, &gst))
                     lzb_die("%s", lzb_last_error());
-                totCells += gst.dpCells; gapSec += gst.seconds;
+                totCells += gst.dpCells; gapSec += gst.seconds; gk += gst.kernelSeconds[0];
+                gExt += gst.anchorsExtended; gSpec += gst.speculated; gRedo += gst.redone; gLaunch += gst.launches; gTrunc += gst.truncated;
                 for (lzb_alignel* a = list; a; a = a->next) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
@@ -230,6 +233,13 @@ int main(int argc, char** argv) {
         fprintf(stderr, "backend=%s raw_seed_hits=%llu hsps=%llu dp_cells=%llu seed_seconds=%.6f gapped_seconds=%.6f\n",
                 lzb_backend(), (unsigned long long)totHits, (unsigned long long)totHsps,
                 (unsigned long long)totCells, seedSec, gapSec);
+    if (o.showStats) {
+        fprintf(stderr, "seed kernels (s): words=%.4f count=%.4f slots=%.4f scan=%.4f expand=%.4f sort=%.4f bounds=%.4f extend=%.4f\n",
+                ks[0], ks[1], ks[2], ks[3], ks[4], ks[5], ks[6], ks[7]);
+        fprintf(stderr, "gapped: extended=%llu speculated=%llu redone=%llu truncated=%llu launches=%llu dp_kernel_seconds=%.4f\n",
+                (unsigned long long)gExt, (unsigned long long)gSpec, (unsigned long long)gRedo,
+                (unsigned long long)gTrunc, (unsigned long long)gLaunch, gk);
+    }
     lzb_seqfile_close(qf); lzb_seqfile_close(tf);
     lzb_target_free(T); lzb_close(ctx); lzb_seq_free(&target);
     if (out != stdout) fclose(out);
