@@ -167,6 +167,12 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     segref leftSeg = J->leftSeg, rightSeg = J->rightSeg;
     int alignList = J->alignList;
     int* act = J->act; int nact = 0;
+    const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
+    /* far edge (e1 forward, b1 reversed) and type of the two bounding segments */
+    u32 lLim = 0, rLim = 0; int lTyp = 0, rTyp = 0;
+#define LOAD_BOUND(ref_, lim_, typ_) \
+    do { if ((ref_).al >= 0) { const dseg s_ = segs[al[(ref_).al].segBegin + (ref_).sg]; lim_ = rev ? s_.b1 : s_.e1; typ_ = s_.type; } } while (0)
+    LOAD_BOUND(leftSeg, lLim, lTyp); LOAD_BOUND(rightSeg, rLim, rTyp);
     s64 used = 0;
     __syncthreads();
     /* ---- first row, gapped_extend.c:3576-3591 ---- */
@@ -187,38 +193,35 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
             used = (s64)last + 1;
         }
         RY = last + 1;
-        if (tid == 0 && J->tbRowCap > 0) tbRow[0] = 0;
+        if (tid == 0 && tbRowCap > 0) tbRow[0] = 0;
     }
     __syncthreads();
     s32* Cprev = C0; s32* Ccur = C1;
     if (status == DP_OK)
     for (row = 1; row <= M; row++) {
         u32 prevLY = LY;
-        /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every thread, same values) ---- */
+        /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every thread, same values).  The bounding
+         * segment's far edge and type sit in registers; HBM is touched only when the walk moves on ---- */
         if (!rev) {
             if (leftSeg.al >= 0) {
-                const dseg s = segs[al[leftSeg.al].segBegin + leftSeg.sg];
-                if (s.e1 >= row + a1) { if (s.type == SEG_DIAG) L++; }
-                else L = sweep_step(al, segs, 0, 0, &leftSeg, row, a1, a2) + 1;
+                if (lLim >= row + a1) { if (lTyp == SEG_DIAG) L++; }
+                else { L = sweep_step(al, segs, 0, 0, &leftSeg, row, a1, a2) + 1; LOAD_BOUND(leftSeg, lLim, lTyp); }
             }
             if (leftSeg.al >= 0) { if ((s32)LY < L) LY = (u32)L; }
             if (rightSeg.al >= 0) {
-                const dseg s = segs[al[rightSeg.al].segBegin + rightSeg.sg];
-                if (s.e1 >= row + a1) { if (s.type == SEG_DIAG) R++; }
-                else R = sweep_step(al, segs, 0, 1, &rightSeg, row, a1, a2) - 1;
+                if (rLim >= row + a1) { if (rTyp == SEG_DIAG) R++; }
+                else { R = sweep_step(al, segs, 0, 1, &rightSeg, row, a1, a2) - 1; LOAD_BOUND(rightSeg, rLim, rTyp); }
             }
             if (rightSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
         } else {
             if (rightSeg.al >= 0) {
-                const dseg s = segs[al[rightSeg.al].segBegin + rightSeg.sg];
-                if (s.b1 <= a1 - row) { if (s.type == SEG_DIAG) L++; }
-                else L = sweep_step(al, segs, 1, 1, &rightSeg, row, a1, a2) + 1;
+                if (rLim <= a1 - row) { if (rTyp == SEG_DIAG) L++; }
+                else { L = sweep_step(al, segs, 1, 1, &rightSeg, row, a1, a2) + 1; LOAD_BOUND(rightSeg, rLim, rTyp); }
             }
             if (rightSeg.al >= 0) { if ((s32)LY < L) LY = (u32)L; }
             if (leftSeg.al >= 0) {
-                const dseg s = segs[al[leftSeg.al].segBegin + leftSeg.sg];
-                if (s.b1 <= a1 - row) { if (s.type == SEG_DIAG) R++; }
-                else R = sweep_step(al, segs, 1, 0, &leftSeg, row, a1, a2) - 1;
+                if (lLim <= a1 - row) { if (lTyp == SEG_DIAG) R++; }
+                else { R = sweep_step(al, segs, 1, 0, &leftSeg, row, a1, a2) - 1; LOAD_BOUND(leftSeg, lLim, lTyp); }
             }
             if (leftSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
         }
@@ -245,7 +248,7 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
                 while (alignList >= 0) {
                     const dalign x = al[alignList];
                     if (!rev) { if (x.pos1 - a1 != row) break; } else { if (a1 - x.end1 != row) break; }
-                    if ((u32)nact >= J->actCap) { status = DP_ACT; break; }
+                    if ((u32)nact >= actCap) { status = DP_ACT; break; }
                     int* a = act + 5 * nact; nact++;
                     a[0] = alignList; a[1] = !rev ? 0 : x.segCount - 1;
                     act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
@@ -264,7 +267,7 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         if (RY < LY) RY = LY;
         s64 need = (s64)(RY - LY) + yTail;
         if (used + need >= tbLen) { status = DP_TRUNCATED; break; }
-        if (row >= J->tbRowCap) { status = DP_TBROW; break; }
+        if (row >= tbRowCap) { status = DP_TBROW; break; }
         const u32 tbBase = (u32)((u64)used - (u64)LY);            /* tbRow[row], modulo 2^32 like the walk */
         if (tid == 0) tbRow[row] = tbBase;
         /* ---- the sweep, gapped_extend.c:3669-3774 ---- */

@@ -459,7 +459,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             stats->wordsInQuery = hc.words; stats->rawSeedHits = totalHits; stats->extensions = hc.extensions;
             stats->bpExtended = hc.bpExtended; stats->hsps = m;
             float ms = 0; cudaEventElapsedTime(&ms, evBegin, evEnd); stats->seconds = ms / 1e3;
-            for (auto& e : evs) { float x = 0; cudaEventElapsedTime(&x, e.a, e.b); stats->kernelSeconds[e.which] += x / 1e3; }
+            for (auto& e : evs) { float x = 0; cudaEventElapsedTime(&x, e.a, e.b); stats->kernelSeconds[e.which] += x / 1e3; stats->kernelLaunches[e.which]++; }
         }
     }
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
