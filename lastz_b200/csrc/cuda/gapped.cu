@@ -126,11 +126,13 @@ __device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u
 #define DP_THREADS 256
 #define DP_WARPS (DP_THREADS / 32)
 
+#define DP_KC 5                       /* cells per thread whose inputs are kept in registers */
+
 struct dp_shared {                    /* small block-wide exchange area */
     xf  wagg[DP_WARPS];
-    s32 wmax[DP_WARPS];
-    u32 wfa[DP_WARPS], wla[DP_WARPS];
-    unsigned long long wkey[DP_WARPS], wbkey[DP_WARPS];
+    s32 wmaxI[DP_WARPS], wmax[DP_WARPS];
+    u32 wfa[DP_WARPS], wla[DP_WARPS], wuc[DP_WARPS], wbc[DP_WARPS];
+    s32 wuv[DP_WARPS], wbv[DP_WARPS];
     int nact, alignList, status;
 };
 
@@ -277,126 +279,181 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         const u32 k = ((width + DP_THREADS - 1) / DP_THREADS) | 1;
         const u32 j0 = LY + tid * k;
         const u32 j1 = (j0 + k < colEnd) ? j0 + k : colEnd;       /* may be <= j0: idle thread */
-        s64 ai = !rev ? (s64)a1 + row : (s64)a1 + 1 - (s64)row;
-        const u8 ac = (ai < 0 || ai >= (s64)len1) ? cls0 : cls1[ai];
+        const s32 ai = !rev ? (s32)(a1 + row) : (s32)(a1 + 1 - row);
+        const u8 ac = (ai < 0 || (u32)ai >= len1) ? cls0 : cls1[ai];
         const s32* subRow = subC + ac * LZB_MAX_CLASSES;
         const bool masking = nact > 0;
-        /* pass 1: this thread's insertion-chain map */
-        xf mine; mine.A = LZB_NEG_INF; mine.S = 0; mine.r = 0;
+        const bool cached = k <= DP_KC;                            /* cell inputs stay in registers between passes */
+        s32 dg0 = 0, dg1 = 0, dg2 = 0, dg3 = 0, dg4 = 0, dd0 = 0, dd1 = 0, dd2 = 0, dd3 = 0, dd4 = 0;   /* DP_KC of each */
+        /* pass 1: diagonal proposals and D inputs; this thread's piece of the insertion chain.
+         * Unmasked rows use the shifted form I'(j) = I(j) + e*(j-LY): I'(j+1) = max(a_j + e*(j-LY+1), I'(j)),
+         * a plain running max, so the chain is a prefix-max scan.  Rows with masked cells (earlier
+         * alignments inside the band) need resets and take the general affine-map scan. */
+        s32 Iin, Iout;
         {
             s32 pc = (j0 > LY && j0 < colEnd) ? Cprev[(j0 - 1) & msk] : LZB_NEG_INF;
-            for (u32 j = j0; j < j1; j++) {
-                s64 bi = !rev ? (s64)a2 + j : (s64)a2 + 1 - (s64)j;
-                u8 bc = (bi < 0) ? cls0 : cls2[bi];
-                s32 diag = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];
-                pc = Cprev[j & msk];
-                s32 d = Dv[j & msk];
-                xf g;
-                if (masking && stamp[j & msk] == row) { g.A = LZB_NEG_INF; g.S = 0; g.r = 1; }
-                else { g.A = diag >= d ? satadd(diag, -gapOE) : LZB_NEG_INF; g.S = -gapE; g.r = 0; }
-                mine = xf_then(mine, g);
+            s32 vmax = LZB_NEG_INF;
+            xf mine; mine.A = LZB_NEG_INF; mine.S = 0; mine.r = 0;
+            if (cached) {
+#define DP_P1(c_)                                                                                          \
+                { const u32 j = j0 + (c_);                                                                   \
+                  if (j < j1) {                                                                              \
+                    const s32 bi = !rev ? (s32)(a2 + j) : (s32)(a2 + 1 - j);                                 \
+                    const u8 bc = (bi < 0) ? cls0 : cls2[bi];                                                \
+                    const s32 diag = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];                              \
+                    pc = Cprev[j & msk];                                                                     \
+                    const s32 d = Dv[j & msk];                                                               \
+                    dg##c_ = diag; dd##c_ = d;                                                               \
+                    const s32 a = diag >= d ? satadd(diag, -gapOE) : LZB_NEG_INF;                            \
+                    if (!masking) vmax = max(vmax, a + gapE * (s32)(j - LY + 1));                            \
+                    else {                                                                                   \
+                        xf g;                                                                                \
+                        if (stamp[j & msk] == row) { g.A = LZB_NEG_INF; g.S = 0; g.r = 1; } else { g.A = a; g.S = -gapE; g.r = 0; } \
+                        mine = xf_then(mine, g);                                                             \
+                    } } }
+                DP_P1(0) DP_P1(1) DP_P1(2) DP_P1(3) DP_P1(4)
+#undef DP_P1
+            } else {
+                for (u32 j = j0; j < j1; j++) {
+                    const s32 bi = !rev ? (s32)(a2 + j) : (s32)(a2 + 1 - j);
+                    const u8 bc = (bi < 0) ? cls0 : cls2[bi];
+                    const s32 diag = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];
+                    pc = Cprev[j & msk];
+                    const s32 d = Dv[j & msk];
+                    const s32 a = diag >= d ? satadd(diag, -gapOE) : LZB_NEG_INF;
+                    if (!masking) vmax = max(vmax, a + gapE * (s32)(j - LY + 1));
+                    else {
+                        xf g;
+                        if (stamp[j & msk] == row) { g.A = LZB_NEG_INF; g.S = 0; g.r = 1; } else { g.A = a; g.S = -gapE; g.r = 0; }
+                        mine = xf_then(mine, g);
+                    }
+                }
+            }
+            if (!masking) {
+                /* block-wide exclusive prefix max of vmax */
+                s32 inc = vmax;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { s32 u = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc = max(inc, u); }
+                if (lane == 31) sh->wmaxI[warp] = inc;
+                s32 ex = __shfl_up_sync(FULL, inc, 1);
+                if (lane == 0) ex = LZB_NEG_INF;
+                __syncthreads();
+                s32 tot = LZB_NEG_INF;
+#pragma unroll
+                for (int w = 0; w < DP_WARPS; w++) { const s32 v = sh->wmaxI[w]; if (w < (int)warp) ex = max(ex, v); tot = max(tot, v); }
+                Iin = satadd(ex, -gapE * (s32)(j0 < colEnd ? j0 - LY : 0));
+                Iout = satadd(tot, -gapE * (s32)width);
+            } else {
+                xf inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    xf up; up.A = __shfl_up_sync(FULL, inc.A, o); up.S = __shfl_up_sync(FULL, inc.S, o); up.r = __shfl_up_sync(FULL, inc.r, o);
+                    if ((int)lane >= o) inc = xf_then(up, inc);
+                }
+                if (lane == 31) sh->wagg[warp] = inc;
+                xf exl; exl.A = __shfl_up_sync(FULL, inc.A, 1); exl.S = __shfl_up_sync(FULL, inc.S, 1); exl.r = __shfl_up_sync(FULL, inc.r, 1);
+                if (lane == 0) { exl.A = LZB_NEG_INF; exl.S = 0; exl.r = 0; }
+                __syncthreads();
+                xf pre; pre.A = LZB_NEG_INF; pre.S = 0; pre.r = 0;
+                xf tot = pre;
+#pragma unroll
+                for (int w = 0; w < DP_WARPS; w++) { xf a = sh->wagg[w]; if (w < (int)warp) pre = xf_then(pre, a); tot = xf_then(tot, a); }
+                Iin = xf_then(pre, exl).A;
+                Iout = tot.A;
             }
         }
-        /* block-wide exclusive scan of the maps; I enters the row as -inf */
-        xf inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            xf up; up.A = __shfl_up_sync(FULL, inc.A, o); up.S = __shfl_up_sync(FULL, inc.S, o); up.r = __shfl_up_sync(FULL, inc.r, o);
-            if ((int)lane >= o) inc = xf_then(up, inc);
-        }
-        if (lane == 31) sh->wagg[warp] = inc;
-        xf exl; exl.A = __shfl_up_sync(FULL, inc.A, 1); exl.S = __shfl_up_sync(FULL, inc.S, 1); exl.r = __shfl_up_sync(FULL, inc.r, 1);
-        if (lane == 0) { exl.A = LZB_NEG_INF; exl.S = 0; exl.r = 0; }
-        __syncthreads();
-        xf pre; pre.A = LZB_NEG_INF; pre.S = 0; pre.r = 0;
-        xf tot = pre;
-#pragma unroll
-        for (int w = 0; w < DP_WARPS; w++) { xf a = sh->wagg[w]; if (w < (int)warp) pre = xf_then(pre, a); tot = xf_then(tot, a); }
-        const s32 Iin = xf_then(pre, exl).A;
-        const s32 Iout = tot.A;                                    /* I leaving the row's last cell */
         /* pass 2: cell values, links, next row's D; candidates for bestScore */
         s32 candMax = LZB_NEG_INF;
         {
             s32 I = Iin;
-            s32 pc = (j0 > LY && j0 < colEnd) ? Cprev[(j0 - 1) & msk] : LZB_NEG_INF;
-            for (u32 j = j0; j < j1; j++) {
-                s64 bi = !rev ? (s64)a2 + j : (s64)a2 + 1 - (s64)j;
-                u8 bc = (bi < 0) ? cls0 : cls2[bi];
-                s32 c = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];
-                pc = Cprev[j & msk];
-                s32 d = Dv[j & msk];
-                u32 f; s32 Dn, In;
-                if (masking && stamp[j & msk] == row) { f = F_MASK; c = LZB_NEG_INF; Dn = LZB_NEG_INF; In = LZB_NEG_INF; }
-                else if (d > c || I > c) {
-                    if (d >= I) { c = d; f = LINK_D | LINK_IEXT | LINK_DEXT; } else { c = I; f = LINK_I | LINK_IEXT | LINK_DEXT; }
-                    In = satadd(I, -gapE); Dn = satadd(d, -gapE);
-                } else {
-                    s32 open = satadd(c, -gapOE), dd = satadd(d, -gapE), ii = satadd(I, -gapE);
-                    if (open > dd) { Dn = open; f = 0; } else { Dn = dd; f = LINK_DEXT; }
-                    if (open > ii) In = open; else { In = ii; f |= LINK_IEXT; }
-                    f |= F_CAND;
-                    candMax = max(candMax, c);
+#define DP_CELL(j_, c_, d_)                                                                              \
+            {   s32 c = (c_); const s32 d = (d_); u32 f; s32 Dn, In;                                       \
+                if (masking && stamp[(j_) & msk] == row) { f = F_MASK; c = LZB_NEG_INF; Dn = LZB_NEG_INF; In = LZB_NEG_INF; } \
+                else if (d > c || I > c) {                                                                 \
+                    if (d >= I) { c = d; f = LINK_D | LINK_IEXT | LINK_DEXT; } else { c = I; f = LINK_I | LINK_IEXT | LINK_DEXT; } \
+                    In = satadd(I, -gapE); Dn = satadd(d, -gapE);                                          \
+                } else {                                                                                   \
+                    const s32 open = satadd(c, -gapOE), dx = satadd(d, -gapE), ii = satadd(I, -gapE);      \
+                    if (open > dx) { Dn = open; f = 0; } else { Dn = dx; f = LINK_DEXT; }                  \
+                    if (open > ii) In = open; else { In = ii; f |= LINK_IEXT; }                            \
+                    f |= F_CAND; candMax = max(candMax, c);                                                \
+                }                                                                                          \
+                Ccur[(j_) & msk] = c; Dv[(j_) & msk] = Dn; flg[(j_) & msk] = (u8)f; I = In; }
+            if (cached) {
+                if (j0 + 0 < j1) DP_CELL(j0 + 0, dg0, dd0)
+                if (j0 + 1 < j1) DP_CELL(j0 + 1, dg1, dd1)
+                if (j0 + 2 < j1) DP_CELL(j0 + 2, dg2, dd2)
+                if (j0 + 3 < j1) DP_CELL(j0 + 3, dg3, dd3)
+                if (j0 + 4 < j1) DP_CELL(j0 + 4, dg4, dd4)
+            } else {
+                s32 pc = (j0 > LY && j0 < colEnd) ? Cprev[(j0 - 1) & msk] : LZB_NEG_INF;
+                for (u32 j = j0; j < j1; j++) {
+                    const s32 bi = !rev ? (s32)(a2 + j) : (s32)(a2 + 1 - j);
+                    const u8 bc = (bi < 0) ? cls0 : cls2[bi];
+                    const s32 diag = (j == LY) ? LZB_NEG_INF : pc + subRow[bc];
+                    pc = Cprev[j & msk];
+                    DP_CELL(j, diag, Dv[j & msk])
                 }
-                Ccur[j & msk] = c; Dv[j & msk] = Dn; flg[j & msk] = (u8)f;
-                I = In;
             }
+#undef DP_CELL
         }
         /* block-wide exclusive prefix max of the candidates, seeded with bestScore */
-        s32 pm = candMax;
+        s32 B;
+        {
+            s32 pm = candMax;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { s32 u = __shfl_up_sync(FULL, pm, o); if ((int)lane >= o) pm = max(pm, u); }
-        if (lane == 31) sh->wmax[warp] = pm;
-        s32 B = __shfl_up_sync(FULL, pm, 1);
-        if (lane == 0) B = LZB_NEG_INF;
-        __syncthreads();
+            for (int o = 1; o < 32; o <<= 1) { s32 u = __shfl_up_sync(FULL, pm, o); if ((int)lane >= o) pm = max(pm, u); }
+            if (lane == 31) sh->wmax[warp] = pm;
+            B = __shfl_up_sync(FULL, pm, 1);
+            if (lane == 0) B = LZB_NEG_INF;
+            __syncthreads();
 #pragma unroll
-        for (int w = 0; w < DP_WARPS; w++) if (w < (int)warp) B = max(B, sh->wmax[w]);
-        B = max(B, best);
+            for (int w = 0; w < DP_WARPS; w++) if (w < (int)warp) B = max(B, sh->wmax[w]);
+            B = max(B, best);
+        }
         /* pass 3: prune, band edges, best/end */
-        u32 firstAlive = 0xFFFFFFFFu, lastAlive = 0; bool anyAlive = false;
-        s32 upVal = 0; u32 upCol = 0; bool upd = false;
-        s32 bVal = 0; u32 bCol = 0; bool bUpd = false;
+        u32 firstAlive = 0xFFFFFFFFu, lastAlive1 = 0;               /* lastAlive1 = last alive column + 1 */
+        s32 upVal = -1; u32 upCol1 = 0;                             /* bestScore updates are >= best >= 0 */
+        s32 bVal = LZB_NEG_INF; u32 bCol1 = 0;
         for (u32 j = j0; j < j1; j++) {
-            s32 c = Ccur[j & msk]; u32 f = flg[j & msk];
-            bool alive = !(f & F_MASK) && c >= B - yDrop;
+            const s32 c = Ccur[j & msk]; const u32 f = flg[j & msk];
+            const bool alive = !(f & F_MASK) && c >= B - yDrop;
             if (!alive) { Ccur[j & msk] = LZB_NEG_INF; Dv[j & msk] = LZB_NEG_INF; tb[(u32)(tbBase + j)] = 0; continue; }
             tb[(u32)(tbBase + j)] = (u8)(f & 15);
-            if (!anyAlive) { firstAlive = j; anyAlive = true; }
-            lastAlive = j;
+            if (firstAlive == 0xFFFFFFFFu) firstAlive = j;
+            lastAlive1 = j + 1;
             if (f & F_CAND) {
-                if (c >= B) { B = c; upVal = c; upCol = j; upd = true; }
-                if (!trim && (row == M || j == N) && (!bUpd || c >= bVal)) { bVal = c; bCol = j; bUpd = true; }
+                if (c >= B) { B = c; upVal = c; upCol1 = j + 1; }
+                if (!trim && (row == M || j == N) && c >= bVal) { bVal = c; bCol1 = j + 1; }
             }
         }
-        /* block reductions: band edges; (value, column) keys so that ties go to the later cell.
-         * Values that matter are >= best >= 0 (bestScore) -- boundary scores may be negative, so
-         * they are biased into unsigned order. */
-        u32 fa = firstAlive, la = anyAlive ? lastAlive + 1 : 0;
-        unsigned long long key = upd ? (((unsigned long long)(u32)upVal << 32) | (upCol + 1)) : 0ull;
-        unsigned long long bkey = bUpd ? (((unsigned long long)((u32)bVal ^ 0x80000000u) << 32) | (bCol + 1)) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            fa = min(fa, __shfl_xor_sync(FULL, fa, o)); la = max(la, __shfl_xor_sync(FULL, la, o));
-            unsigned long long ok = __shfl_xor_sync(FULL, key, o); if (ok > key) key = ok;
-            if (!trim) { unsigned long long ob = __shfl_xor_sync(FULL, bkey, o); if (ob > bkey) bkey = ob; }
+        /* block reductions with the warp-reduce unit; ties go to the later cell (:3742, :3749) */
+        {
+            const u32 fa = __reduce_min_sync(FULL, firstAlive), la = __reduce_max_sync(FULL, lastAlive1);
+            const s32 uv = __reduce_max_sync(FULL, upVal);
+            const u32 uc = __reduce_max_sync(FULL, (upVal == uv && upCol1) ? upCol1 : 0u);
+            if (lane == 0) { sh->wfa[warp] = fa; sh->wla[warp] = la; sh->wuv[warp] = uv; sh->wuc[warp] = uc; }
+            if (!trim) {
+                const s32 bv = __reduce_max_sync(FULL, bVal);
+                const u32 bc = __reduce_max_sync(FULL, (bVal == bv && bCol1) ? bCol1 : 0u);
+                if (lane == 0) { sh->wbv[warp] = bv; sh->wbc[warp] = bc; }
+            }
         }
-        if (lane == 0) { sh->wfa[warp] = fa; sh->wla[warp] = la; sh->wkey[warp] = key; sh->wbkey[warp] = bkey; }
         __syncthreads();
+        u32 fa = 0xFFFFFFFFu, la = 0; s32 uv = -1; u32 uc = 0; s32 bv = LZB_NEG_INF; u32 bc = 0;
 #pragma unroll
         for (int w = 0; w < DP_WARPS; w++) {
             fa = min(fa, sh->wfa[w]); la = max(la, sh->wla[w]);
-            unsigned long long ok = sh->wkey[w]; if (ok > key) key = ok;
-            unsigned long long ob = sh->wbkey[w]; if (ob > bkey) bkey = ob;
+            const s32 v = sh->wuv[w]; const u32 cc = sh->wuc[w];
+            if (v > uv || (v == uv && cc > uc)) { uv = v; uc = cc; }
+            if (!trim) { const s32 v2 = sh->wbv[w]; const u32 c2 = sh->wbc[w]; if (v2 > bv || (v2 == bv && c2 > bc)) { bv = v2; bc = c2; } }
         }
         /* bestScore moves to the LAST cell (row-major) that equalled the row's final best (:3742) */
         u32 bestCol = 0; bool bestMoved = false;
-        if (key) { best = (s32)(u32)(key >> 32); bestCol = (u32)key - 1; bestMoved = true; }
+        if (uc) { best = uv; bestCol = uc - 1; bestMoved = true; }
         /* boundaryScore (:3747-3750, only without y-drop trimming) */
         u32 bndCol = 0; bool bndMoved = false;
-        if (!trim && bkey) {
-            s32 gm = (s32)((u32)(bkey >> 32) ^ 0x80000000u);
-            if (gm >= bnd) { bnd = gm; bndCol = (u32)bkey - 1; bndMoved = true; }
-        }
+        if (!trim && bc && bv >= bnd) { bnd = bv; bndCol = bc - 1; bndMoved = true; }
         /* the later event in row-major order owns the end cell; in one cell the boundary test runs second */
         if (bestMoved && (!bndMoved || bestCol > bndCol)) { end1 = row; end2 = bestCol; endIsBnd = 0; }
         else if (bndMoved) { end1 = row; end2 = bndCol; endIsBnd = 1; }
@@ -711,6 +768,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     cudaSetDevice(c->device);
     if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
     if (P->tracebackBytes < 8) return lzb_fail("in new_traceback(), size can't be %u", P->tracebackBytes);
+    if (c->sc.gapOpen < 0) return lzb_fail("lastz_b200's Y-drop kernel requires a non-negative gap open penalty (got %d)", c->sc.gapOpen);
     auto wall0 = std::chrono::steady_clock::now();
     u64 launches0 = c->launches;
     *list = NULL;

@@ -185,18 +185,41 @@ __global__ void k_bucket_bounds(const u32* __restrict__ keys, u32 nhits, u32 nbu
     }
 }
 
-/* ---- K3b: replay each bucket in discovery order; x-drop extension ---- */
-__global__ void __launch_bounds__(256)
+/* ---- K3b: replay each bucket in discovery order; x-drop extension ----
+ *
+ * The scans read the class-coded sequences eight bases at a time (two aligned 64-bit loads and a
+ * funnel shift per sequence) instead of one byte per column: a warp's 32 lanes sit on 32
+ * unrelated diagonals, so every load instruction costs up to 32 L1 wavefronts whatever its width,
+ * and the wavefront pipe -- not HBM -- was the first limit (profiles/r01_k_extend_before.txt).
+ * With at most 16 byte classes (any DNA scoring set) the eight (row, column) class pairs of a
+ * chunk are formed by one shift+or and looked up in a 256-entry table. */
+__device__ __forceinline__ u64 ld8(const u8* __restrict__ p, u32 idx) {
+    const u64* w = (const u64*)(p + (idx & ~7u));
+    u32 sh = (idx & 7u) * 8u;
+    u64 lo = w[0], hi = w[1];
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+}
+
+template <bool SMALL>
+__device__ __forceinline__ s32 pair_score(const s32* __restrict__ lut, u64 x1, u64 x2, u64 pr, int i) {
+    if (SMALL) return lut[(u32)(pr >> (8 * i)) & 255u];
+    return lut[((u32)(x1 >> (8 * i)) & 255u) * LZB_MAX_CLASSES + ((u32)(x2 >> (8 * i)) & 255u)];
+}
+
+template <bool SMALL>
+__global__ void __launch_bounds__(256, 3)
 k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuckets,
          const u8* __restrict__ cls1, const u8* __restrict__ cls2,
          const u8* __restrict__ asc1, const u8* __restrict__ asc2,
          const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32* __restrict__ diagEnd,
          cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt) {
-    __shared__ s32 msub[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
-    for (int i = threadIdx.x; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += blockDim.x) msub[i] = sc->msubC[i];
+    __shared__ s32 lut[SMALL ? 256 : LZB_MAX_CLASSES * LZB_MAX_CLASSES];
+    if (SMALL) { for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = sc->msubC[(i >> 4) * LZB_MAX_CLASSES + (i & 15)]; }
+    else { for (int i = threadIdx.x; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += blockDim.x) lut[i] = sc->msubC[i]; }
     __syncthreads();
     const u32 lane = threadIdx.x & 31;
     const u32 L = (u32)P.L;
+    const s32 xDrop = P.xDrop;
     u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long nExt = 0, nBp = 0;
     for (u32 h = warp; h < nbuckets; h += nwarps) {
@@ -219,18 +242,29 @@ k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuck
             /* right scan (seed_search.c:2663-2693): independent of the bucket state.  Hits the
              * bucket has already passed (diagEnd only grows) are skipped outright. */
             bool maybe = have && !(E > pos2 - L);
-            u32 rightStop = pos1, rightBlock = pos1; s32 rightScore = 0;
+            u32 rightLen = 0, rightCols = 0; s32 rightScore = 0;        /* best prefix length, columns examined */
             if (maybe && P.gfExtend == LZB_GFEX_XDROP) {
                 s64 lim = (s64)P.len2 + diag;
                 u32 rstop = ((s64)P.len1 <= lim) ? P.len1 : (u32)lim;
-                u32 a = pos1, b = pos2; s32 run = 0;
-                while (a < rstop && run >= rightScore - P.xDrop) {
-                    run += msub[cls1[a] * LZB_MAX_CLASSES + cls2[b]];
-                    a++; b++;
-                    if (run > rightScore) { rightStop = a; rightScore = run; }
+                u32 avail = rstop > pos1 ? rstop - pos1 : 0;
+                s32 run = 0; bool going = true;
+                while (going && rightCols < avail) {
+                    u64 x1 = ld8(cls1, pos1 + rightCols), x2 = ld8(cls2, pos2 + rightCols);
+                    u64 pr = (x1 << 4) | x2;
+                    u32 n = avail - rightCols; if (n > 8) n = 8;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (going && (u32)i < n) {
+                            if (run >= rightScore - xDrop) {
+                                run += pair_score<SMALL>(lut, x1, x2, pr, i);
+                                rightCols++;
+                                if (run > rightScore) { rightScore = run; rightLen = rightCols; }
+                            } else going = false;
+                        }
+                    }
                 }
-                rightBlock = a;
             }
+            u32 rightBlock = pos1 + rightCols;
             u32 ext = (P.gfExtend == LZB_GFEX_XDROP) ? (u32)((s64)rightBlock - diag) : pos2;
             /* replay process_for_simple_hit's test/update (seed_search.c:1113, :2785-2789) in
              * discovery order: lane k sees the bucket exactly as hit k would have */
@@ -253,18 +287,44 @@ k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuck
             /* left scan (seed_search.c:2598-2632), blocked by the bucket's previous extent */
             s64 blk = (s64)myStop + diag;
             u32 stop = blk > 0 ? (u32)blk : 0;
-            u32 a = pos1, b = pos2, leftStart = pos1; s32 run = 0, leftScore = 0;
-            while (a > stop && run >= leftScore - P.xDrop) {
-                a--; b--;
-                run += msub[cls1[a] * LZB_MAX_CLASSES + cls2[b]];
-                if (run > leftScore) { leftStart = a; leftScore = run; }
+            u32 leftCols = 0, leftLen = 0; s32 leftScore = 0;
+            {
+                u32 avail = pos1 > stop ? pos1 - stop : 0;
+                s32 run = 0; bool going = true;
+                while (going && leftCols < avail) {
+                    u32 a = pos1 - leftCols, b = pos2 - leftCols;       /* columns a-1, a-2, ... */
+                    u32 n = avail - leftCols; if (n > 8) n = 8;
+                    if (a >= 8 && b >= 8) {
+                        u64 x1 = ld8(cls1, a - 8), x2 = ld8(cls2, b - 8);
+                        u64 pr = (x1 << 4) | x2;
+#pragma unroll
+                        for (int i = 7; i >= 0; i--) {
+                            if (going && (u32)(7 - i) < n) {
+                                if (run >= leftScore - xDrop) {
+                                    run += pair_score<SMALL>(lut, x1, x2, pr, i);
+                                    leftCols++;
+                                    if (run > leftScore) { leftScore = run; leftLen = leftCols; }
+                                } else going = false;
+                            }
+                        }
+                    } else {                                              /* within 8 bases of a sequence start */
+                        for (u32 i = 0; i < n && going; i++) {
+                            if (run >= leftScore - xDrop) {
+                                u32 c1 = cls1[a - 1 - i], c2 = cls2[b - 1 - i];
+                                run += SMALL ? lut[(c1 << 4) | c2] : lut[c1 * LZB_MAX_CLASSES + c2];
+                                leftCols++;
+                                if (run > leftScore) { leftScore = run; leftLen = leftCols; }
+                            } else going = false;
+                        }
+                    }
+                }
             }
-            nExt++; nBp += rightBlock - a;
+            nExt++; nBp += rightCols + leftCols;
             s32 sim = leftScore + rightScore;
             if (sim < P.K) continue;                /* entropy can only lower the score */
             cand_rec r;
-            r.hit1 = pos1; r.hit2 = pos2; r.pos1 = leftStart; r.pos2 = (u32)((s64)leftStart - diag);
-            r.length = rightStop - leftStart; r.score = sim; r.cA = r.cC = r.cG = r.cT = 0;
+            r.hit1 = pos1; r.hit2 = pos2; r.pos1 = pos1 - leftLen; r.pos2 = pos2 - leftLen;
+            r.length = leftLen + rightLen; r.score = sim; r.cA = r.cC = r.cG = r.cT = 0;
             if (P.entropy && sim <= 3 * P.K) {      /* match counts for entropy(), dna_utilities.c:2905-2915 */
                 for (u32 i = 0; i < r.length; i++) {
                     u8 x = asc1[r.pos1 + i];
@@ -336,8 +396,9 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     u32 *d_qword = NULL, *d_flips = NULL, *d_E = NULL, *d_bstart = NULL;
     unsigned long long* d_blkcnt = NULL; search_counters* d_cnt = NULL;
     std::vector<ev_pair> evs;
-    cudaEvent_t evBegin, evEnd;
+    cudaEvent_t evBegin, evMid, evMid2, evEnd;       /* device time = [begin,mid] + [mid2,end]; planning + cudaMalloc sit between */
     CUDA_TRY(cudaEventCreate(&evBegin)); CUDA_TRY(cudaEventCreate(&evEnd));
+    CUDA_TRY(cudaEventCreate(&evMid)); CUDA_TRY(cudaEventCreate(&evMid2));
     CUDA_TRY(cudaMalloc(&d_qword, (size_t)n * 4 + 16));
     CUDA_TRY(cudaMalloc(&d_flips, flips.size() * 4));
     CUDA_TRY(cudaMalloc(&d_blkcnt, (size_t)nblk * 8));
@@ -358,6 +419,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cudaGetLastError());
     std::vector<unsigned long long> blkcnt(nblk);
     CUDA_TRY(cudaMemcpyAsync(blkcnt.data(), d_blkcnt, (size_t)nblk * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(evMid, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     u64 totalHits = 0, maxBlk = 0;
     for (u32 b = 0; b < nblk; b++) { totalHits += blkcnt[b]; if (blkcnt[b] > maxBlk) maxBlk = blkcnt[b]; }
@@ -385,6 +447,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cudaMalloc(&d_tmp, tmpBytes));
 
     /* chunk loop */
+    CUDA_TRY(cudaEventRecord(evMid2, st));
     u64 chunks = 0;
     for (u32 b0 = 0; b0 < nblk;) {
         u64 h = 0; u32 b1 = b0;
@@ -400,8 +463,12 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             tb = tmpBytes;
             TIMED(5, cub::DeviceRadixSort::SortPairs(d_tmp, tb, keysA, keysB, valsA, valsB, nh, 0, hashBits, st));
             TIMED(6, (k_bucket_bounds<<<(nbuckets + 256) / 256, 256, 0, st>>>(keysB, nh, nbuckets, d_bstart)));
-            TIMED(7, (k_extend<<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
-                                                     c->d_sc, P, d_E, d_cand, candCap, d_cnt)));
+            if (c->sc.numClasses <= 16)
+                TIMED(7, (k_extend<true><<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
+                                                               c->d_sc, P, d_E, d_cand, candCap, d_cnt)));
+            else
+                TIMED(7, (k_extend<false><<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
+                                                                c->d_sc, P, d_E, d_cand, candCap, d_cnt)));
             CUDA_TRY(cudaGetLastError());
             chunks++;
         }
@@ -458,12 +525,13 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
         if (stats) {
             stats->wordsInQuery = hc.words; stats->rawSeedHits = totalHits; stats->extensions = hc.extensions;
             stats->bpExtended = hc.bpExtended; stats->hsps = m;
-            float ms = 0; cudaEventElapsedTime(&ms, evBegin, evEnd); stats->seconds = ms / 1e3;
+            float ms = 0, ms2 = 0; cudaEventElapsedTime(&ms, evBegin, evMid); cudaEventElapsedTime(&ms2, evMid2, evEnd);
+            stats->seconds = (ms + ms2) / 1e3;
             for (auto& e : evs) { float x = 0; cudaEventElapsedTime(&x, e.a, e.b); stats->kernelSeconds[e.which] += x / 1e3; stats->kernelLaunches[e.which]++; }
         }
     }
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    cudaEventDestroy(evBegin); cudaEventDestroy(evEnd);
+    cudaEventDestroy(evBegin); cudaEventDestroy(evEnd); cudaEventDestroy(evMid); cudaEventDestroy(evMid2);
     cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
     cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
     cudaFree(d_cand); cudaFree(d_tmp);
