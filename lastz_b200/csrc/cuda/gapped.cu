@@ -123,19 +123,19 @@ __device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u
     }
 }
 
-#define DP_THREADS 256
-#define DP_WARPS (DP_THREADS / 32)
+#define DP_MAX_WARPS 8
 
 #define DP_KC 5                       /* cells per thread whose inputs are kept in registers */
 
 struct dp_shared {                    /* small block-wide exchange area */
-    xf  wagg[DP_WARPS];
-    s32 wmaxI[DP_WARPS], wmax[DP_WARPS];
-    u32 wfa[DP_WARPS], wla[DP_WARPS], wuc[DP_WARPS], wbc[DP_WARPS];
-    s32 wuv[DP_WARPS], wbv[DP_WARPS];
+    xf  wagg[DP_MAX_WARPS];
+    s32 wmaxI[DP_MAX_WARPS], wmax[DP_MAX_WARPS];
+    u32 wfa[DP_MAX_WARPS], wla[DP_MAX_WARPS], wuc[DP_MAX_WARPS], wbc[DP_MAX_WARPS];
+    s32 wuv[DP_MAX_WARPS], wbv[DP_MAX_WARPS];
     int nact, alignList, status;
 };
 
+template <int DP_THREADS>
 __global__ void __launch_bounds__(DP_THREADS)
 k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
@@ -145,6 +145,7 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     u32* stamp = (u32*)(Dv + cap); s32* subC = (s32*)(stamp + cap);
     dp_shared* sh = (dp_shared*)(subC + LZB_MAX_CLASSES * LZB_MAX_CLASSES);
     u8* flg = (u8*)(sh + 1);
+    constexpr int DP_WARPS = DP_THREADS / 32;
     const u32 msk = cap - 1;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 FULL = 0xFFFFFFFFu;
@@ -719,6 +720,7 @@ struct gx_lane {
     u8* tb[2]; u32 tbBytes; u32* tbRow[2]; u32 tbRowCap[2]; u32* ops[2]; u32 opsCap[2]; int* act[2]; u32 actCap[2];
     /* state */
     bool busy; u64 anchor; size_t snapshot; segref left1, right1; u32 ring;
+    u64 estLo, estHi;                    /* seq1 rows this extension is expected to examine */
 };
 
 struct gx_cache {                        /* lives in the context: lanes are expensive to allocate */
@@ -829,7 +831,10 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     }
     for (auto& ln : gc->lanes) { ln.busy = false; }
     gc->segsUploaded = 0;
-    CUDA_TRY(cudaFuncSetAttribute(k_ydrop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_ydrop<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_ydrop<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    int dpThreads = 256;
+    { const char* e = getenv("LZB_DP_THREADS"); if (e && atoi(e) == 128) dpThreads = 128; }
 
     std::vector<spec_result> spec(n);
     for (auto& s : spec) s.have = false;
@@ -910,8 +915,12 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         CUDA_TRY(cudaMemcpyAsync(ln.d_jobs, ln.h_jobs, 2 * sizeof(dp_job), cudaMemcpyHostToDevice, ln.stream));
         size_t smem = (size_t)ln.ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
         CUDA_TRY(cudaEventRecord(ln.evA, ln.stream));
-        k_ydrop<<<2, DP_THREADS, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
-                                                   c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
+        if (dpThreads == 128)
+            k_ydrop<128><<<2, 128, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
+                                                     c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
+        else
+            k_ydrop<256><<<2, 256, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
+                                                     c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ln.evB, ln.stream));
@@ -919,8 +928,24 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         return 0;
     };
 
+    /* rows an extension from anchor y will probably examine: +-reach, cut short by committed
+     * alignments that end/start on a nearby diagonal (its DP stops at their masked cells).  Only a
+     * scheduling hint: correctness rests on the validation at commit time. */
+    auto est_region = [&](galn& y) -> std::pair<u64, u64> {
+        s64 dy = (s64)y.pos1 - (s64)y.pos2;
+        u64 lo = y.pos1 > reach ? y.pos1 - reach : 0, hi = (u64)y.pos1 + reach;
+        for (int ci : G.committed) {
+            galn& x = G.al[ci];
+            s64 dEnd = (s64)x.end1 - (s64)x.end2, dBeg = (s64)x.pos1 - (s64)x.pos2;
+            if (x.end1 < y.pos1 && llabs(dEnd - dy) < 3000) { u64 b = x.end1 > 600 ? x.end1 - 600 : 0; if (b > lo) lo = b; }
+            if (x.pos1 > y.pos1 && llabs(dBeg - dy) < 3000) { u64 b = (u64)x.pos1 + 600; if (b < hi) hi = b; }
+        }
+        return std::make_pair(lo, hi);
+    };
+
     auto start_anchor = [&](gx_lane& ln, u64 ai) -> int {
         galn& m = G.al[ai];
+        { std::pair<u64, u64> rg = est_region(m); ln.estLo = rg.first; ln.estHi = rg.second; }
         ln.busy = true; ln.anchor = ai; ln.snapshot = G.committed.size(); ln.left1 = m.left1; ln.right1 = m.right1; ln.ring = ring0;
         inflight[ai] = 1;
         return launch(ln, -1);
@@ -996,22 +1021,29 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             int freeLanes = 0;
             for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
             if (freeLanes > 0 && inflight[i]) {
-                std::vector<u64> pending;                    /* anchor rows of everything not yet committed */
-                for (int z = 0; z < W; z++) if (gc->lanes[z].busy) pending.push_back(G.al[gc->lanes[z].anchor].pos1);
+                /* rows every uncommitted extension covers (exact once finished, estimated while in flight) */
+                std::vector<std::pair<u64, u64>> pending;
+                for (int z = 0; z < W; z++) if (gc->lanes[z].busy) pending.push_back(std::make_pair(gc->lanes[z].estLo, gc->lanes[z].estHi));
                 u64 scanned = 0;
-                for (u64 j = i + 1; j < n && freeLanes > 0 && scanned < 20000; j++, scanned++) {
+                for (u64 j = i + 1; j < n && freeLanes > 0 && scanned < 6000; j++, scanned++) {
                     if (inflight[j]) continue;
-                    if (spec[j].have) { pending.push_back(G.al[j].pos1); continue; }
                     galn& y = G.al[j];
-                    bool far = true;
-                    for (u64 pr : pending) { u64 b = y.pos1; if ((pr > b ? pr - b : b - pr) < 2 * reach) { far = false; break; } }
-                    if (!far) continue;
+                    if (spec[j].have) {
+                        u64 lo = (u64)y.pos1 + 1 >= (u64)spec[j].L.rows + 2 ? (u64)y.pos1 + 1 - spec[j].L.rows - 2 : 0;
+                        pending.push_back(std::make_pair(lo, (u64)y.pos1 + spec[j].R.rows + 2));
+                        continue;
+                    }
+                    std::pair<u64, u64> rg = est_region(y);
+                    bool clash = false;
+                    for (auto& pr : pending) if (!(rg.second < pr.first || rg.first > pr.second)) { clash = true; break; }
+                    if (clash) continue;
                     if (!anchor_neighbours(G, y)) continue;
                     gx_lane* fl = NULL;
                     for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
                     if (!fl) break;
                     if (start_anchor(*fl, j)) return -1;
-                    pending.push_back(y.pos1); freeLanes--; G.st.speculated++;
+                    fl->estLo = rg.first; fl->estHi = rg.second;
+                    pending.push_back(rg); freeLanes--; G.st.speculated++;
                 }
             }
             /* wait for any lane to finish, harvest every finished lane */
