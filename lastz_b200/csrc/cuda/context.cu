@@ -20,6 +20,10 @@ extern "C" void lzb_free(void* p) { free(p); }
 extern "C" uint64_t lzb_launch_count(lzb_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" lzb_ctx* lzb_open(int device) {
+    /* The gapped stage keeps up to 32 streams busy; with the default 8 hardware queues unrelated
+     * streams share a queue and a kernel waits behind another stream's pending D2H copy.  Must be
+     * set before the CUDA context exists (a host process that created it earlier sets it itself). */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {

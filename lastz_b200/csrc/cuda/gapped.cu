@@ -836,6 +836,9 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     int dpThreads = 256;
     { const char* e = getenv("LZB_DP_THREADS"); if (e && atoi(e) == 128) dpThreads = 128; }
 
+    const bool trace = getenv("LZB_GAP_TRACE") != NULL;
+    u64 headAnchor = 0;
+    auto now = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count(); };
     std::vector<spec_result> spec(n);
     for (auto& s : spec) s.have = false;
     std::vector<char> inflight(n, 0);
@@ -948,6 +951,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         { std::pair<u64, u64> rg = est_region(m); ln.estLo = rg.first; ln.estHi = rg.second; }
         ln.busy = true; ln.anchor = ai; ln.snapshot = G.committed.size(); ln.left1 = m.left1; ln.right1 = m.right1; ln.ring = ring0;
         inflight[ai] = 1;
+        if (trace) fprintf(stderr, "[gx %.4f] launch a=%llu pos1=%u est=[%llu,%llu] head=%llu committed=%zu\n", now(), (unsigned long long)ai, m.pos1, (unsigned long long)ln.estLo, (unsigned long long)ln.estHi, (unsigned long long)headAnchor, G.committed.size());
         return launch(ln, -1);
     };
 
@@ -988,6 +992,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             return launch(ln, redo);
         }
         sr.have = true; sr.snapshot = ln.snapshot; sr.left1 = ln.left1; sr.right1 = ln.right1;
+        if (trace) fprintf(stderr, "[gx %.4f] done a=%llu rowsL=%u rowsR=%u kernel_ms=%.1f\n", now(), (unsigned long long)ln.anchor, sr.L.rows, sr.R.rows, ms);
         ln.busy = false; inflight[ln.anchor] = 0;
         return 0;
     };
@@ -996,6 +1001,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     u64 i = 0;
     while (i < n) {
         galn& m = G.al[i];
+        headAnchor = i;
         if (!anchor_neighbours(G, m)) { spec[i].have = false; spec[i].L.ops.clear(); spec[i].R.ops.clear(); i++; continue; }
         spec_result& sr = spec[i];
         bool usable = sr.have;
@@ -1008,7 +1014,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                 if (!((u64)x.end1 < lo || (u64)x.pos1 > hi)) usable = false;
             }
             if (usable && (sr.left1.al != m.left1.al || sr.left1.sg != m.left1.sg || sr.right1.al != m.right1.al || sr.right1.sg != m.right1.sg)) usable = false;
-            if (!usable) { G.st.redone++; sr.have = false; }
+            if (!usable) { G.st.redone++; sr.have = false; if (trace) fprintf(stderr, "[gx %.4f] invalid a=%llu\n", now(), (unsigned long long)i); }
         }
         if (!usable) {
             /* keep the lanes full: anchor i first, then later uncovered anchors that are unlikely to
@@ -1064,6 +1070,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         }
         /* ---- commit: ydrop_align's script assembly :2529-2580, format_alignment :5153 ---- */
         G.st.anchorsExtended++;
+        if (trace) fprintf(stderr, "[gx %.4f] commit a=%llu pos1=%u\n", now(), (unsigned long long)i, m.pos1);
         u32 a1 = m.pos1, a2 = m.pos2;
         u32 start1 = a1 + 1 - sr.L.end1, start2 = a2 + 1 - sr.L.end2, stop1 = a1 + sr.R.end1, stop2 = a2 + sr.R.end2;
         lzb_editscript* sl = es_new((u32)(sr.L.ops.size() + sr.R.ops.size() + 4));
