@@ -249,18 +249,9 @@ def main():
 
     def gather_segments(tables):
         """the one exchange step: every rank's HSP table to all ranks over NCCL"""
-        if world == 1:
-            return sum(len(t) for t in tables)
-        raw = np.concatenate([t.view(np.uint8).reshape(-1) for t in tables]) if tables else np.zeros(0, np.uint8)
-        n = torch.tensor([raw.size], device="cuda", dtype=torch.int64)
-        counts = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(counts, n)
-        mx = int(max(c.item() for c in counts))
-        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-        buf[:raw.size] = torch.from_numpy(raw).cuda()
-        out = torch.empty(world * mx, dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(out, buf)
-        return sum(int(c.item()) for c in counts) // 48
+        from lastz_b200.sharding import gather_segment_tables
+        parts = gather_segment_tables(np.concatenate(tables), torch.device("cuda", local))
+        return sum(len(p) for p in parts)
 
     def step(resident, handles=None):
         acc = dict(hits=0, cells=0, seed_s=0.0, gap_s=0.0, ext_s=0.0, ext_launch=0, bp=0, hsps=0, h2d=0, d2h=0,
