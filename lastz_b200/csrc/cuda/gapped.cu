@@ -1014,7 +1014,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                 if (!((u64)x.end1 < lo || (u64)x.pos1 > hi)) usable = false;
             }
             if (usable && (sr.left1.al != m.left1.al || sr.left1.sg != m.left1.sg || sr.right1.al != m.right1.al || sr.right1.sg != m.right1.sg)) usable = false;
-            if (!usable) { G.st.redone++; sr.have = false; if (trace) fprintf(stderr, "[gx %.4f] invalid a=%llu\n", now(), (unsigned long long)i); }
+            if (!usable) { G.st.redone++; sr.have = false; if (trace) fprintf(stderr, "[gx %.4f] invalid a=%llu rows=[%llu,%llu] snapshot=%zu\n", now(), (unsigned long long)i, (unsigned long long)lo, (unsigned long long)hi, sr.snapshot); }
         }
         if (!usable) {
             /* keep the lanes full: anchor i first, then later uncovered anchors that are unlikely to
@@ -1027,29 +1027,45 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             int freeLanes = 0;
             for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
             if (freeLanes > 0 && inflight[i]) {
-                /* rows every uncommitted extension covers (exact once finished, estimated while in flight) */
-                std::vector<std::pair<u64, u64>> pending;
-                for (int z = 0; z < W; z++) if (gc->lanes[z].busy) pending.push_back(std::make_pair(gc->lanes[z].estLo, gc->lanes[z].estHi));
-                u64 scanned = 0;
-                for (u64 j = i + 1; j < n && freeLanes > 0 && scanned < 6000; j++, scanned++) {
+                /* rows every uncommitted extension covers (exact once finished, estimated while in
+                 * flight), plus RESERVATIONS: an earlier-ordered anchor that cannot start yet (it
+                 * would run into a pending extension) but will probably need its own DP later; later
+                 * anchors must stay out of its way or they would be invalidated when it commits */
+                struct pend { u64 lo, hi; s64 diag; };
+                std::vector<pend> pending;
+                for (int z = 0; z < W; z++) if (gc->lanes[z].busy) {
+                    galn& p = G.al[gc->lanes[z].anchor];
+                    pending.push_back(pend{ gc->lanes[z].estLo, gc->lanes[z].estHi, (s64)p.pos1 - (s64)p.pos2 });
+                }
+                u64 scanned = 0; int reserved = 0;
+                for (u64 j = i + 1; j < n && freeLanes > 0 && scanned < 6000 && reserved < 4096; j++, scanned++) {
                     if (inflight[j]) continue;
                     galn& y = G.al[j];
+                    const s64 dy = (s64)y.pos1 - (s64)y.pos2;
                     if (spec[j].have) {
                         u64 lo = (u64)y.pos1 + 1 >= (u64)spec[j].L.rows + 2 ? (u64)y.pos1 + 1 - spec[j].L.rows - 2 : 0;
-                        pending.push_back(std::make_pair(lo, (u64)y.pos1 + spec[j].R.rows + 2));
+                        pending.push_back(pend{ lo, (u64)y.pos1 + spec[j].R.rows + 2, dy });
                         continue;
                     }
                     std::pair<u64, u64> rg = est_region(y);
-                    bool clash = false;
-                    for (auto& pr : pending) if (!(rg.second < pr.first || rg.first > pr.second)) { clash = true; break; }
-                    if (clash) continue;
+                    bool clash = false, inside = false;
+                    for (auto& pr : pending) {
+                        if (rg.second < pr.lo || rg.first > pr.hi) continue;
+                        clash = true;
+                        if (y.pos1 >= pr.lo && y.pos1 <= pr.hi && llabs(dy - pr.diag) < 5000) { inside = true; break; }
+                    }
+                    if (clash) {
+                        /* inside a pending extension on its diagonal: it will almost surely be covered; else reserve */
+                        if (!inside && anchor_neighbours(G, y)) { pending.push_back(pend{ rg.first, rg.second, dy }); reserved++; }
+                        continue;
+                    }
                     if (!anchor_neighbours(G, y)) continue;
                     gx_lane* fl = NULL;
                     for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
                     if (!fl) break;
                     if (start_anchor(*fl, j)) return -1;
                     fl->estLo = rg.first; fl->estHi = rg.second;
-                    pending.push_back(rg); freeLanes--; G.st.speculated++;
+                    pending.push_back(pend{ rg.first, rg.second, dy }); freeLanes--; G.st.speculated++;
                 }
             }
             /* wait for any lane to finish, harvest every finished lane */
