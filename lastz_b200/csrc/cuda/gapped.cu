@@ -123,6 +123,49 @@ __device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u
     }
 }
 
+/* traceback, gapped_extend.c:3847-3859, by one warp: lane t speculates that the path continues
+ * diagonally and looks at (r-t, c-t); a ballot finds the first non-substitution, so a run of up to
+ * 32 substitutions costs one dependent load.  Emits run-length ops (op | count<<2) in walk order. */
+__device__ u32 traceback_walk(const u8* tb, const u32* tbRow, u32 end1, u32 end2, u32* ops, u32 opsCap,
+                              u32 lane, bool* overflow) {
+    const u32 FULL = 0xFFFFFFFFu;
+    u32 nops = 0;
+    u32 r = end1, c = end2; u32 prevOp = 0;
+    u32 curOp = 0, curCnt = 0; bool ovf = false;
+    while (r >= 1 || c > 0) {
+        bool inb = (r >= lane) && (c >= lane) && ((r - lane) >= 1 || (c - lane) > 0);
+        u32 link = 0;
+        if (inb) link = tb[(u32)(tbRow[r - lane] + (c - lane))];
+        u32 op = link & 3;
+        if (lane == 0) {
+            if (prevOp == LINK_I && (link & LINK_IEXT)) op = LINK_I;
+            if (prevOp == LINK_D && (link & LINK_DEXT)) op = LINK_D;
+        }
+        /* lane t>0 assumes the step before it was a substitution, true iff all earlier lanes are
+         * substitutions; a diagonal step needs r-t >= 1 and c-t >= 1 */
+        bool isSub = inb && op == 0 && (r - lane) >= 1 && (c - lane) >= 1;
+        u32 notSub = __ballot_sync(FULL, !isSub);
+        u32 run = notSub ? (u32)(__ffs(notSub) - 1) : 32;
+        if (run > 0) {
+            if (curOp == LZB_OP_SUB) curCnt += run;
+            else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = LZB_OP_SUB; curCnt = run; }
+            r -= run; c -= run; prevOp = 0;
+            continue;
+        }
+        u32 op0 = __shfl_sync(FULL, op, 0);
+        u32 eop;
+        if (op0 == LINK_I) { c--; eop = LZB_OP_INS; }
+        else if (op0 == LINK_D) { r--; eop = LZB_OP_DEL; }
+        else { r--; c--; eop = LZB_OP_SUB; }
+        if (curOp == eop) curCnt++;
+        else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = eop; curCnt = 1; }
+        prevOp = op0;
+    }
+    if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; }
+    *overflow = ovf;
+    return nops;
+}
+
 #define DP_MAX_WARPS 8
 
 #define DP_KC 5                       /* cells per thread whose inputs are kept in registers */
@@ -495,39 +538,8 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     if (warp != 0) return;
     u32 nops = 0;
     if (status == DP_OK || status == DP_TRUNCATED) {
-        u32 r = end1, c = end2; u32 prevOp = 0;
-        u32 curOp = 0, curCnt = 0; u32* ops = J->ops; const u32 opsCap = J->opsCap; bool ovf = false;
-        while (r >= 1 || c > 0) {
-            /* speculate a diagonal run: lane t looks at (r-t, c-t) */
-            bool inb = (r >= lane) && (c >= lane) && ((r - lane) >= 1 || (c - lane) > 0);
-            u32 link = 0;
-            if (inb) link = tb[(u32)(tbRow[r - lane] + (c - lane))];
-            u32 op = link & 3;
-            if (lane == 0) {
-                if (prevOp == LINK_I && (link & LINK_IEXT)) op = LINK_I;
-                if (prevOp == LINK_D && (link & LINK_DEXT)) op = LINK_D;
-            }
-            /* lane t>0 assumes the step before it was a substitution, true iff all earlier lanes are
-             * substitutions; a diagonal step needs r-t >= 1 and c-t >= 1 */
-            bool isSub = inb && op == 0 && (r - lane) >= 1 && (c - lane) >= 1;
-            u32 notSub = __ballot_sync(FULL, !isSub);
-            u32 run = notSub ? (u32)(__ffs(notSub) - 1) : 32;
-            if (run > 0) {
-                if (curOp == LZB_OP_SUB) curCnt += run;
-                else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = LZB_OP_SUB; curCnt = run; }
-                r -= run; c -= run; prevOp = 0;
-                continue;
-            }
-            u32 op0 = __shfl_sync(FULL, op, 0);
-            u32 eop;
-            if (op0 == LINK_I) { c--; eop = LZB_OP_INS; }
-            else if (op0 == LINK_D) { r--; eop = LZB_OP_DEL; }
-            else { r--; c--; eop = LZB_OP_SUB; }
-            if (curOp == eop) curCnt++;
-            else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = eop; curCnt = 1; }
-            prevOp = op0;
-        }
-        if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; }
+        bool ovf = false;
+        nops = traceback_walk(tb, tbRow, end1, end2, J->ops, J->opsCap, lane, &ovf);
         if (ovf) status = DP_OPS;
     }
     if (lane == 0) {
@@ -535,6 +547,8 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         J->rows = row; J->cells = cells; J->status = status;
     }
 }
+
+#include "ydrop_reg.cuh"
 
 /* ---- K4: segment_peak gapped_extend.c:515-559, one thread per HSP ---- */
 __global__ void k_peaks(lzb_segment* __restrict__ seg, u64 n, const u8* __restrict__ cls1,
@@ -720,6 +734,7 @@ struct gx_lane {
     u8* tb[2]; u32 tbBytes; u32* tbRow[2]; u32 tbRowCap[2]; u32* ops[2]; u32 opsCap[2]; int* act[2]; u32 actCap[2];
     /* state */
     bool busy; u64 anchor; size_t snapshot; segref left1, right1; u32 ring;
+    int mode;                            /* 0/1 register kernel K=4/8, 2/3 shared-memory kernel ring 4096/8192 */
     u64 estLo, estHi;                    /* seq1 rows this extension is expected to examine */
 };
 
@@ -834,6 +849,10 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     CUDA_TRY(cudaFuncSetAttribute(k_ydrop<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_ydrop<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int dpThreads = 256;
+    /* narrow bands (the common case) run on the register-resident kernel; LZB_DP_MODE forces a start mode */
+    int firstMode = c->sc.gapExtend > 0 ? 0 : 2;
+    { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3 && (mdv >= 2 || c->sc.gapExtend > 0)) firstMode = mdv; } }
+    if (cenv) firstMode = 2;                                   /* an explicit ring size means the shared-memory kernel */
     { const char* e = getenv("LZB_DP_THREADS"); if (e && atoi(e) == 128) dpThreads = 128; }
 
     const bool trace = getenv("LZB_GAP_TRACE") != NULL;
@@ -916,14 +935,21 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             J.ops = ln.ops[side]; J.opsCap = ln.opsCap[side]; J.act = ln.act[side]; J.actCap = ln.actCap[side];
         }
         CUDA_TRY(cudaMemcpyAsync(ln.d_jobs, ln.h_jobs, 2 * sizeof(dp_job), cudaMemcpyHostToDevice, ln.stream));
-        size_t smem = (size_t)ln.ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
         CUDA_TRY(cudaEventRecord(ln.evA, ln.stream));
-        if (dpThreads == 128)
-            k_ydrop<128><<<2, 128, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
-                                                     c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
-        else
-            k_ydrop<256><<<2, 256, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
-                                                     c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
+        if (ln.mode == 0)
+            k_ydrop_reg<4><<<2, RG_THREADS, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
+        else if (ln.mode == 1)
+            k_ydrop_reg<8><<<2, RG_THREADS, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
+        else {
+            ln.ring = ln.mode == 2 ? ring0 : ring0 * 2;
+            size_t smem = (size_t)ln.ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
+            if (dpThreads == 128)
+                k_ydrop<128><<<2, 128, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
+                                                         c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
+            else
+                k_ydrop<256><<<2, 256, smem, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2,
+                                                         c->d_sc, P->yDrop, P->trimToPeak, ln.ring);
+        }
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ln.evB, ln.stream));
@@ -949,7 +975,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     auto start_anchor = [&](gx_lane& ln, u64 ai) -> int {
         galn& m = G.al[ai];
         { std::pair<u64, u64> rg = est_region(m); ln.estLo = rg.first; ln.estHi = rg.second; }
-        ln.busy = true; ln.anchor = ai; ln.snapshot = G.committed.size(); ln.left1 = m.left1; ln.right1 = m.right1; ln.ring = ring0;
+        ln.busy = true; ln.anchor = ai; ln.snapshot = G.committed.size(); ln.left1 = m.left1; ln.right1 = m.right1; ln.ring = ring0; ln.mode = firstMode;
         inflight[ai] = 1;
         if (trace) fprintf(stderr, "[gx %.4f] launch a=%llu pos1=%u est=[%llu,%llu] head=%llu committed=%zu\n", now(), (unsigned long long)ai, m.pos1, (unsigned long long)ln.estLo, (unsigned long long)ln.estHi, (unsigned long long)headAnchor, G.committed.size());
         return launch(ln, -1);
@@ -965,7 +991,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             if (J.skip) continue;                            /* side finished in an earlier pass */
             bool again = false;
             if (J.status == DP_RING) {
-                if (ln.ring >= 8192) return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ln.ring);
+                if (ln.mode >= 3) return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ln.ring);
                 again = true;
             } else if (J.status == DP_TBROW) {
                 cudaFree(ln.tbRow[side]); ln.tbRowCap[side] = ln.tbRowCap[side] * 4 < tbLen ? ln.tbRowCap[side] * 4 : tbLen + 8;
@@ -986,7 +1012,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         if (redo != -2) {
             bool ringGrow = false;
             for (int side = 0; side < 2; side++) if (ln.h_jobs[side].status == DP_RING) ringGrow = true;
-            if (ringGrow) ln.ring *= 2;
+            if (ringGrow) ln.mode++;
             /* rerun with the neighbours it was started with; the (possibly newer) alignment table is a
              * superset, and validation still uses the ORIGINAL snapshot, so any difference is caught */
             return launch(ln, redo);
