@@ -640,18 +640,19 @@ struct gx {                             /* state of one lzb_gapped_extend call *
 };
 
 /* msp_left_right gapped_extend.c:3953-4040 */
-static bool anchor_neighbours(gx& G, galn& m) {
+static bool anchor_neighbours(gx& G, galn& m, int* coverer = NULL) {
     u32 pos1 = m.pos1, pos2 = m.pos2, right = 0xFFFFFFFFu, left = 0xFFFFFFFFu;
     segref R = NOSEG, Lf = NOSEG;
     for (int o = G.obi; o >= 0 && G.al[o].pos1 <= pos1; o = G.al[o].next) {
         galn& x = G.al[o];
         if (x.end1 < pos1) continue;
-        int k = 0, ns = (int)x.segs.size();
-        while (k < ns && x.segs[k].e1 < pos1) k++;
+        /* first segment whose e1 >= pos1 (e1 never decreases along an alignment) */
+        int ns = (int)x.segs.size(), k = 0, hi2 = ns;
+        while (k < hi2) { int mid = (k + hi2) >> 1; if (x.segs[mid].e1 < pos1) k = mid + 1; else hi2 = mid; }
         if (k == ns) continue;
         hseg& bp = x.segs[k]; s32 d;
         if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - pos2) + (s32)(pos1 - bp.b1); else d = (s32)(bp.b2 - pos2);
-        if (d == 0) return false;
+        if (d == 0) { if (coverer) *coverer = o; return false; }
         if (d > 0 && (u32)d < right) { right = (u32)d; R.al = o; R.sg = k; }
         else if (d < 0 && (u32)-d < left) { left = (u32)-d; Lf.al = o; Lf.sg = k; }
     }
@@ -831,7 +832,8 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     }
 
     /* ---- speculation lanes (cached in the context across calls) ---- */
-    int W = P->speculation < 1 ? 1 : (P->speculation > 128 ? 128 : P->speculation);
+    const bool strict = P->speculation < 0;                    /* internal: exact-order rerun after a scheduling violation */
+    int W = abs(P->speculation); if (W < 1) W = 1; if (W > 128) W = 128;
     const char* wenv = getenv("LZB_SPECULATION"); if (wenv) { W = atoi(wenv); if (W < 1) W = 1; if (W > 128) W = 128; }
     if ((u64)W > n) W = n ? (int)n : 1;
     u32 ring0 = 4096;                                       /* sweep-row ring, columns */
@@ -850,7 +852,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     CUDA_TRY(cudaFuncSetAttribute(k_ydrop<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int dpThreads = 256;
     /* narrow bands (the common case) run on the register-resident kernel; LZB_DP_MODE forces a start mode */
-    int firstMode = c->sc.gapExtend > 0 ? 0 : 2;
+    int firstMode = 2;    /* measured: the register kernel is ~1.5x SLOWER per row than the shared-memory one */
     { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3 && (mdv >= 2 || c->sc.gapExtend > 0)) firstMode = mdv; } }
     if (cenv) firstMode = 2;                                   /* an explicit ring size means the shared-memory kernel */
     { const char* e = getenv("LZB_DP_THREADS"); if (e && atoi(e) == 128) dpThreads = 128; }
@@ -861,7 +863,8 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     std::vector<spec_result> spec(n);
     for (auto& s : spec) s.have = false;
     std::vector<char> inflight(n, 0);
-    u64 reach = tbLen / 300 + 1000;                          /* rows a DP is expected to cover */
+    const u64 reach = tbLen / 300 + 1000;                    /* rows a DP is expected to cover, before any has finished */
+    bool tablesDirtyInit = true; (void)tablesDirtyInit;
 
     /* append newly committed alignments to the device segment table (append-only, so running
      * kernels are undisturbed); the alignment table itself is snapshotted per launch */
@@ -960,9 +963,9 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     /* rows an extension from anchor y will probably examine: +-reach, cut short by committed
      * alignments that end/start on a nearby diagonal (its DP stops at their masked cells).  Only a
      * scheduling hint: correctness rests on the validation at commit time. */
-    auto est_region = [&](galn& y) -> std::pair<u64, u64> {
+    auto est_region = [&](galn& y, u64 rch) -> std::pair<u64, u64> {
         s64 dy = (s64)y.pos1 - (s64)y.pos2;
-        u64 lo = y.pos1 > reach ? y.pos1 - reach : 0, hi = (u64)y.pos1 + reach;
+        u64 lo = y.pos1 > rch ? y.pos1 - rch : 0, hi = (u64)y.pos1 + rch;
         for (int ci : G.committed) {
             galn& x = G.al[ci];
             s64 dEnd = (s64)x.end1 - (s64)x.end2, dBeg = (s64)x.pos1 - (s64)x.pos2;
@@ -974,7 +977,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
 
     auto start_anchor = [&](gx_lane& ln, u64 ai) -> int {
         galn& m = G.al[ai];
-        { std::pair<u64, u64> rg = est_region(m); ln.estLo = rg.first; ln.estHi = rg.second; }
+        ln.estLo = 0; ln.estHi = ~0ull;                          /* the caller fills in its estimate */
         ln.busy = true; ln.anchor = ai; ln.snapshot = G.committed.size(); ln.left1 = m.left1; ln.right1 = m.right1; ln.ring = ring0; ln.mode = firstMode;
         inflight[ai] = 1;
         if (trace) fprintf(stderr, "[gx %.4f] launch a=%llu pos1=%u est=[%llu,%llu] head=%llu committed=%zu\n", now(), (unsigned long long)ai, m.pos1, (unsigned long long)ln.estLo, (unsigned long long)ln.estHi, (unsigned long long)headAnchor, G.committed.size());
@@ -1010,6 +1013,8 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         }
         CUDA_TRY(cudaStreamSynchronize(ln.stream));
         if (redo != -2) {
+            if (trace) fprintf(stderr, "[gx %.4f] rerun a=%llu side=%d statusL=%d statusR=%d rowsL=%u rowsR=%u kernel_ms=%.1f mode=%d\n", now(), (unsigned long long)ln.anchor, redo,
+                               ln.h_jobs[0].status, ln.h_jobs[1].status, ln.h_jobs[0].rows, ln.h_jobs[1].rows, ms, ln.mode);
             bool ringGrow = false;
             for (int side = 0; side < 2; side++) if (ln.h_jobs[side].status == DP_RING) ringGrow = true;
             if (ringGrow) ln.mode++;
@@ -1018,108 +1023,40 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             return launch(ln, redo);
         }
         sr.have = true; sr.snapshot = ln.snapshot; sr.left1 = ln.left1; sr.right1 = ln.right1;
-        if (trace) fprintf(stderr, "[gx %.4f] done a=%llu rowsL=%u rowsR=%u kernel_ms=%.1f\n", now(), (unsigned long long)ln.anchor, sr.L.rows, sr.R.rows, ms);
+        if (trace) fprintf(stderr, "[gx %.4f] done a=%llu rowsL=%u rowsR=%u kernel_ms=%.1f mode=%d\n", now(), (unsigned long long)ln.anchor, sr.L.rows, sr.R.rows, ms, ln.mode);
         ln.busy = false; inflight[ln.anchor] = 0;
         return 0;
     };
 
-    /* ---- the anchor loop, gapped_extend.c:1300-1470: commits strictly in score order ---- */
-    u64 i = 0;
-    while (i < n) {
-        galn& m = G.al[i];
-        headAnchor = i;
-        if (!anchor_neighbours(G, m)) { spec[i].have = false; spec[i].L.ops.clear(); spec[i].R.ops.clear(); i++; continue; }
-        spec_result& sr = spec[i];
-        bool usable = sr.have;
-        if (usable && sr.snapshot != G.committed.size()) {
-            /* valid only if nothing committed since its launch touches the rows its DPs examined */
-            u64 lo = (u64)m.pos1 + 1 >= (u64)sr.L.rows + 2 ? (u64)m.pos1 + 1 - sr.L.rows - 2 : 0;
-            u64 hi = (u64)m.pos1 + sr.R.rows + 2;
-            for (size_t k = sr.snapshot; k < G.committed.size() && usable; k++) {
-                galn& x = G.al[G.committed[k]];
-                if (!((u64)x.end1 < lo || (u64)x.pos1 > hi)) usable = false;
-            }
-            if (usable && (sr.left1.al != m.left1.al || sr.left1.sg != m.left1.sg || sr.right1.al != m.right1.al || sr.right1.sg != m.right1.sg)) usable = false;
-            if (!usable) { G.st.redone++; sr.have = false; if (trace) fprintf(stderr, "[gx %.4f] invalid a=%llu rows=[%llu,%llu] snapshot=%zu\n", now(), (unsigned long long)i, (unsigned long long)lo, (unsigned long long)hi, sr.snapshot); }
-        }
-        if (!usable) {
-            /* keep the lanes full: anchor i first, then later uncovered anchors that are unlikely to
-             * interact with anything still pending */
-            if (!inflight[i]) {
-                gx_lane* fl = NULL;
-                for (auto& ln : gc->lanes) if (!ln.busy && (&ln - &gc->lanes[0]) < W) { fl = &ln; break; }
-                if (fl) { if (start_anchor(*fl, i)) return -1; }
-            }
-            int freeLanes = 0;
-            for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
-            if (freeLanes > 0 && inflight[i]) {
-                /* rows every uncommitted extension covers (exact once finished, estimated while in
-                 * flight), plus RESERVATIONS: an earlier-ordered anchor that cannot start yet (it
-                 * would run into a pending extension) but will probably need its own DP later; later
-                 * anchors must stay out of its way or they would be invalidated when it commits */
-                struct pend { u64 lo, hi; s64 diag; };
-                std::vector<pend> pending;
-                for (int z = 0; z < W; z++) if (gc->lanes[z].busy) {
-                    galn& p = G.al[gc->lanes[z].anchor];
-                    pending.push_back(pend{ gc->lanes[z].estLo, gc->lanes[z].estHi, (s64)p.pos1 - (s64)p.pos2 });
-                }
-                u64 scanned = 0; int reserved = 0;
-                for (u64 j = i + 1; j < n && freeLanes > 0 && scanned < 6000 && reserved < 4096; j++, scanned++) {
-                    if (inflight[j]) continue;
-                    galn& y = G.al[j];
-                    const s64 dy = (s64)y.pos1 - (s64)y.pos2;
-                    if (spec[j].have) {
-                        u64 lo = (u64)y.pos1 + 1 >= (u64)spec[j].L.rows + 2 ? (u64)y.pos1 + 1 - spec[j].L.rows - 2 : 0;
-                        pending.push_back(pend{ lo, (u64)y.pos1 + spec[j].R.rows + 2, dy });
-                        continue;
-                    }
-                    std::pair<u64, u64> rg = est_region(y);
-                    bool clash = false, inside = false;
-                    for (auto& pr : pending) {
-                        if (rg.second < pr.lo || rg.first > pr.hi) continue;
-                        clash = true;
-                        if (y.pos1 >= pr.lo && y.pos1 <= pr.hi && llabs(dy - pr.diag) < 5000) { inside = true; break; }
-                    }
-                    if (clash) {
-                        /* inside a pending extension on its diagonal: it will almost surely be covered; else reserve */
-                        if (!inside && anchor_neighbours(G, y)) { pending.push_back(pend{ rg.first, rg.second, dy }); reserved++; }
-                        continue;
-                    }
-                    if (!anchor_neighbours(G, y)) continue;
-                    gx_lane* fl = NULL;
-                    for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
-                    if (!fl) break;
-                    if (start_anchor(*fl, j)) return -1;
-                    fl->estLo = rg.first; fl->estHi = rg.second;
-                    pending.push_back(pend{ rg.first, rg.second, dy }); freeLanes--; G.st.speculated++;
-                }
-            }
-            /* wait for any lane to finish, harvest every finished lane */
-            bool got = false;
-            while (!got) {
-                for (int z = 0; z < W; z++) {
-                    gx_lane& ln = gc->lanes[z];
-                    if (!ln.busy) continue;
-                    cudaError_t e = cudaStreamQuery(ln.stream);
-                    if (e == cudaSuccess) { if (harvest(ln)) return -1; if (!ln.busy) got = true; }
-                    else if (e != cudaErrorNotReady) return lzb_fail("Y-drop kernel failed: %s", cudaGetErrorString(e));
-                }
-                if (!got) std::this_thread::sleep_for(std::chrono::microseconds(20));
-            }
-            { u64 r = 0, cnt = 0; for (u64 j = i; j < n && cnt < 1; j++) if (spec[j].have) { r = std::max<u64>(spec[j].L.rows, spec[j].R.rows); cnt++; }
-              if (cnt) reach = (reach * 7 + r) / 8 + 1; }
-            continue;
-        }
-        /* ---- commit: ydrop_align's script assembly :2529-2580, format_alignment :5153 ---- */
+    /* ---- the anchor loop, gapped_extend.c:1300-1470 ----
+     * Sequential semantics: anchors are extended best score first and every kept alignment
+     * constrains the later ones.  Two alignments whose DPs examined disjoint seq-1 row ranges cannot
+     * see each other (bounds, masks and the skip rule are all row-local), so they may be committed in
+     * either order.  The loop therefore sweeps the not-yet-final anchors in score order carrying the
+     * row ranges of everything EARLIER that is still unresolved (in flight, waiting, or finished but
+     * itself waiting): a finished extension commits as soon as its exact rows clear all of them; an
+     * anchor may start as soon as its estimated rows do.  Estimates only schedule.  At every commit
+     * the exact ranges are checked against alignments that were committed ahead of their turn; if
+     * an estimate was too small and two such ranges do overlap, the whole call is redone in strict
+     * order (`strict`), so the result always equals the sequential algorithm's. */
+    std::vector<u8> fin(n, 0);                               /* 1 = skipped / committed / dropped */
+    std::vector<u64> dpLo(n + 1, 0), dpHi(n + 1, 0);        /* rows examined by a committed anchor's DPs */
+    u64 hd = 0; bool violation = false;
+    u64 maxRows = 0;
+
+    /* commit anchor i from its finished, validated result */
+    auto commit_anchor = [&](u64 i) {
+        galn& m = G.al[i]; spec_result& sr = spec[i];
         G.st.anchorsExtended++;
-        if (trace) fprintf(stderr, "[gx %.4f] commit a=%llu pos1=%u\n", now(), (unsigned long long)i, m.pos1);
+        if (trace) fprintf(stderr, "[gx %.4f] commit a=%llu pos1=%u hd=%llu\n", now(), (unsigned long long)i, m.pos1, (unsigned long long)hd);
         u32 a1 = m.pos1, a2 = m.pos2;
+        dpLo[i] = (u64)a1 + 1 >= (u64)sr.L.rows + 2 ? (u64)a1 + 1 - sr.L.rows - 2 : 0; dpHi[i] = (u64)a1 + sr.R.rows + 2;
         u32 start1 = a1 + 1 - sr.L.end1, start2 = a2 + 1 - sr.L.end2, stop1 = a1 + sr.R.end1, stop2 = a2 + sr.R.end2;
         lzb_editscript* sl = es_new((u32)(sr.L.ops.size() + sr.R.ops.size() + 4));
-        /* left script: ops in emission order; right script: emitted far-end first, so reversed */
+        /* left script: ops in emission order; right script: emitted far-end first, so reversed (:2529-2551) */
         for (size_t k = 0; k < sr.L.ops.size(); k++) es_add(&sl, sr.L.ops[k] & 3, sr.L.ops[k] >> 2);
         for (size_t k = sr.R.ops.size(); k-- > 0;) es_add(&sl, sr.R.ops[k] & 3, sr.R.ops[k] >> 2);
-        if (sl->len > 0 && sr.R.ops.size() > 0) sl->tailOp = sr.R.ops.back() & 3;    /* edit_script_append keeps src->tailOp (unreversed) */
+        if (sl->len > 0 && sr.R.ops.size() > 0) sl->tailOp = sr.R.ops.back() & 3;
         s32 score = sr.L.score + sr.R.score;
         if (sl->len != 0) {
             if ((sl->op[0] & 3) != LZB_OP_SUB) {             /* lop_initial_indels :2589 */
@@ -1135,6 +1072,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                 else { stop1 = p1; stop2 = p2; sl->len = k; score = rescore(G, start1, start2, sl); }
             }
         }
+        /* format_alignment :5153 */
         u32 beg1 = start1 + 1, end1 = stop1 + 1, beg2 = start2 + 1, end2 = stop2 + 1;
         u32 height = end1 - beg1 + 1, width = end2 - beg2 + 1, k = 0;
         m.segs.clear();
@@ -1153,16 +1091,130 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         a->seq1 = h1; a->seq2 = h2; a->s = score; a->hspId = m.hspId;
         m.align = a; m.pos1 = start1; m.pos2 = start2; m.end1 = stop1; m.end2 = stop2;
         sr.have = false; sr.L.ops.clear(); sr.L.ops.shrink_to_fit(); sr.R.ops.clear(); sr.R.ops.shrink_to_fit();
-        if (m.segs.empty()) { i++; continue; }
-        if (!P->allBounds && a->s < P->scoreThreshold) { free(a->script); free(a); m.align = NULL; m.segs.clear(); i++; continue; }
+        fin[i] = 1;
+        if (m.segs.empty()) return;
+        if (!P->allBounds && a->s < P->scoreThreshold) { free(a->script); free(a); m.align = NULL; m.segs.clear(); return; }
         alignment_neighbours(G, m);
         list_insert(G, (int)i);
         m.devIx = (int)G.committed.size(); G.committed.push_back((int)i);
         tablesDirty = true;
-        i++;
+    };
+
+    struct pend { u64 lo, hi; s64 diag; };
+    while (hd < n && !violation) {
+        while (hd < n && fin[hd]) hd++;
+        if (hd >= n) break;
+        headAnchor = hd;
+        /* ---- one sweep in score order over the not-yet-final anchors ---- */
+        std::vector<pend> unresolved;                        /* earlier anchors whose outcome is still open */
+        int freeLanes = 0;
+        for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
+        const u64 est = std::max<u64>(reach, maxRows + maxRows / 4);
+        bool progressed = false; u64 examined = 0;
+        for (u64 j = hd; j < n && examined < 8192; j++) {
+            if (fin[j]) continue;
+            examined++;
+            galn& y = G.al[j];
+            const s64 dy = (s64)y.pos1 - (s64)y.pos2;
+            int coverer = -1;
+            if (!inflight[j] || spec[j].have) {
+                if (!anchor_neighbours(G, y, &coverer)) {
+                    /* on an alignment committed EARLIER in the order: skipped for good (:1335) */
+                    if (coverer >= 0 && (u64)coverer > j && coverer != (int)n) { violation = true; break; }
+                    fin[j] = 1; spec[j].have = false; spec[j].L.ops.clear(); spec[j].R.ops.clear(); progressed = true;
+                    continue;
+                }
+            }
+            if (spec[j].have) {
+                spec_result& sr = spec[j];
+                const u64 lo = (u64)y.pos1 + 1 >= (u64)sr.L.rows + 2 ? (u64)y.pos1 + 1 - sr.L.rows - 2 : 0;
+                const u64 hi = (u64)y.pos1 + sr.R.rows + 2;
+                bool usable = true;
+                /* nothing committed since its launch may touch the rows its DPs examined (:1335-1389 inputs) */
+                for (size_t k = sr.snapshot; k < G.committed.size() && usable; k++) {
+                    galn& x = G.al[G.committed[k]];
+                    if (!((u64)x.end1 < lo || (u64)x.pos1 > hi)) usable = false;
+                }
+                if (usable && (sr.left1.al != y.left1.al || sr.left1.sg != y.left1.sg || sr.right1.al != y.right1.al || sr.right1.sg != y.right1.sg)) usable = false;
+                if (!usable) {
+                    G.st.redone++; sr.have = false;
+                    if (trace) fprintf(stderr, "[gx %.4f] invalid a=%llu rows=[%llu,%llu]\n", now(), (unsigned long long)j, (unsigned long long)lo, (unsigned long long)hi);
+                } else {
+                    bool clear = true;
+                    for (auto& u : unresolved) if (!(hi < u.lo || lo > u.hi)) { clear = false; break; }
+                    if (strict && !unresolved.empty()) clear = false;
+                    if (clear) {
+                        /* alignments committed ahead of their turn must be out of reach of this one, and vice versa */
+                        for (int ci : G.committed) if ((u64)ci > j && ci != (int)n && !(dpHi[ci] < lo || dpLo[ci] > hi)) { violation = true; break; }
+                        if (violation) break;
+                        commit_anchor(j); progressed = true;
+                        continue;
+                    }
+                    unresolved.push_back(pend{ lo, hi, dy });
+                    continue;
+                }
+            }
+            if (inflight[j]) {
+                gx_lane* ln = NULL;
+                for (int z = 0; z < W; z++) if (gc->lanes[z].busy && gc->lanes[z].anchor == j) ln = &gc->lanes[z];
+                unresolved.push_back(pend{ ln ? ln->estLo : 0, ln ? ln->estHi : ~0ull, dy });
+                continue;
+            }
+            /* not started: may start if its estimated rows clear every unresolved earlier anchor */
+            std::pair<u64, u64> rg = est_region(y, est);
+            bool clash = false, inside = false;
+            for (auto& u : unresolved) {
+                if (rg.second < u.lo || rg.first > u.hi) continue;
+                clash = true;
+                if (y.pos1 >= u.lo && y.pos1 <= u.hi && llabs(dy - u.diag) < 5000) { inside = true; break; }
+            }
+            if (strict && !unresolved.empty()) clash = true;
+            if (!clash && freeLanes > 0) {
+                gx_lane* fl = NULL;
+                for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
+                if (start_anchor(*fl, j)) return -1;
+                fl->estLo = rg.first; fl->estHi = rg.second;
+                freeLanes--; if (j != hd) G.st.speculated++;
+                unresolved.push_back(pend{ rg.first, rg.second, dy });
+                continue;
+            }
+            /* blocked (or no lane): an anchor inside an unresolved extension on its own diagonal will
+             * almost surely be covered by it and needs no reservation; anything else keeps later
+             * anchors out of its way */
+            if (!inside || !clash) unresolved.push_back(pend{ rg.first, rg.second, dy });
+            if (unresolved.size() > 4096) break;
+        }
+        if (violation) break;
+        if (progressed) continue;                            /* commits/skips may have unblocked more */
+        /* ---- nothing more to decide: wait for a lane ---- */
+        bool any = false;
+        for (int z = 0; z < W; z++) if (gc->lanes[z].busy) any = true;
+        if (!any) return lzb_fail("internal error: gapped scheduler stalled at anchor %llu", (unsigned long long)hd);
+        bool got = false;
+        while (!got) {
+            for (int z = 0; z < W; z++) {
+                gx_lane& ln = gc->lanes[z];
+                if (!ln.busy) continue;
+                cudaError_t e = cudaStreamQuery(ln.stream);
+                if (e == cudaSuccess) { const u64 a = ln.anchor; if (harvest(ln)) return -1; if (!ln.busy) { got = true; maxRows = std::max<u64>(maxRows, std::max<u64>(spec[a].L.rows, spec[a].R.rows)); } }
+                else if (e != cudaErrorNotReady) return lzb_fail("Y-drop kernel failed: %s", cudaGetErrorString(e));
+            }
+            if (!got) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
     }
     /* abandon speculative work that was never needed */
     for (auto& ln : gc->lanes) if (ln.busy) { cudaStreamSynchronize(ln.stream); ln.busy = false; }
+    if (violation) {
+        /* an estimate was too small: redo everything in strict order (exact by construction) */
+        for (int o = G.obi; o >= 0; o = G.al[o].next) { galn& m = G.al[o]; if (m.align) { free(m.align->script); free(m.align); } }
+        if (trace) fprintf(stderr, "[gx %.4f] out-of-order commit violated an estimate; strict rerun\n", now());
+        if (strict) return lzb_fail("internal error: ordering violation in strict mode");
+        lzb_gapped_params P2 = *P; P2.speculation = -W;      /* negative => strict */
+        lzb_gapped_stats st2;
+        int rc = lzb_gapped_extend(c, t, q, h1, h2, anchors, n, &P2, list, &st2);
+        if (stats) { *stats = st2; stats->redone += G.st.redone + 1000000; }
+        return rc;
+    }
     lzb_alignel* head = NULL, *last = NULL;
     for (int o = G.obi; o >= 0; o = G.al[o].next) {
         galn& m = G.al[o];
