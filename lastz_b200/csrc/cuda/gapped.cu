@@ -731,7 +731,6 @@ struct gx_lane {
     cudaStream_t stream; cudaEvent_t evA, evB;
     dp_job* h_jobs;                      /* pinned, 2 entries */
     dp_job* d_jobs;
-    dalign* d_aligns; size_t alignsCap;  /* private snapshot of the alignment table */
     u8* tb[2]; u32 tbBytes; u32* tbRow[2]; u32 tbRowCap[2]; u32* ops[2]; u32 opsCap[2]; int* act[2]; u32 actCap[2];
     /* state */
     bool busy; u64 anchor; size_t snapshot; segref left1, right1; u32 ring;
@@ -746,7 +745,7 @@ struct gx_cache {                        /* lives in the context: lanes are expe
 
 static void free_lane(gx_lane& ln) {
     cudaStreamDestroy(ln.stream); cudaEventDestroy(ln.evA); cudaEventDestroy(ln.evB);
-    cudaFreeHost(ln.h_jobs); cudaFree(ln.d_jobs); cudaFree(ln.d_aligns);
+    cudaFreeHost(ln.h_jobs);
     for (int s = 0; s < 2; s++) { cudaFree(ln.tb[s]); cudaFree(ln.tbRow[s]); cudaFree(ln.ops[s]); cudaFree(ln.act[s]); }
 }
 
@@ -762,8 +761,11 @@ static int make_lane(gx_lane& ln, u32 tbBytes, u32 tbLen) {
     memset(&ln, 0, sizeof ln);
     CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&ln.evA)); CUDA_TRY(cudaEventCreate(&ln.evB));
-    CUDA_TRY(cudaHostAlloc(&ln.h_jobs, 2 * sizeof(dp_job), cudaHostAllocDefault));
-    CUDA_TRY(cudaMalloc(&ln.d_jobs, 2 * sizeof(dp_job)));
+    /* job descriptors live in mapped pinned memory: the kernel reads its job and writes its result
+     * there, so a lane's stream carries nothing but kernels (no copy that another stream sharing the
+     * hardware queue could get stuck behind) */
+    CUDA_TRY(cudaHostAlloc(&ln.h_jobs, 2 * sizeof(dp_job), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&ln.d_jobs, ln.h_jobs, 0));
     ln.tbBytes = tbBytes;
     for (int s = 0; s < 2; s++) {
         CUDA_TRY(cudaMalloc(&ln.tb[s], (size_t)tbBytes + 64));
@@ -833,8 +835,8 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
 
     /* ---- speculation lanes (cached in the context across calls) ---- */
     const bool strict = P->speculation < 0;                    /* internal: exact-order rerun after a scheduling violation */
-    int W = abs(P->speculation); if (W < 1) W = 1; if (W > 128) W = 128;
-    const char* wenv = getenv("LZB_SPECULATION"); if (wenv) { W = atoi(wenv); if (W < 1) W = 1; if (W > 128) W = 128; }
+    int W = abs(P->speculation); if (W < 1) W = 1; if (W > 192) W = 192;
+    const char* wenv = getenv("LZB_SPECULATION"); if (wenv) { W = atoi(wenv); if (W < 1) W = 1; if (W > 192) W = 192; }
     if ((u64)W > n) W = n ? (int)n : 1;
     u32 ring0 = 4096;                                       /* sweep-row ring, columns */
     const char* cenv = getenv("LZB_RING"); if (cenv) ring0 = (u32)atoi(cenv);
@@ -868,6 +870,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
 
     /* append newly committed alignments to the device segment table (append-only, so running
      * kernels are undisturbed); the alignment table itself is snapshotted per launch */
+    dalign* curAligns = NULL; std::vector<dalign*> alignEpochs;
     auto push_segments = [&]() -> int {
         size_t haveA = G.haligns.size();
         for (size_t k = haveA; k < G.committed.size(); k++) {
@@ -896,6 +899,15 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             d.left1 = dev_ref(G, m.left1); d.right1 = dev_ref(G, m.right1); d.left2 = dev_ref(G, m.left2); d.right2 = dev_ref(G, m.right2);
             d.next = m.next >= 0 ? G.al[m.next].devIx : -1; d.prev = m.prev >= 0 ? G.al[m.prev].devIx : -1;
         }
+        /* a fresh, immutable copy of the alignment table per commit epoch: kernels already running
+         * keep reading the copy they were launched with; the copies are tiny and freed at the end */
+        curAligns = NULL;
+        if (!G.haligns.empty()) {
+            CUDA_TRY(cudaMalloc(&curAligns, G.haligns.size() * sizeof(dalign)));
+            alignEpochs.push_back(curAligns);
+            CUDA_TRY(cudaMemcpyAsync(curAligns, G.haligns.data(), G.haligns.size() * sizeof(dalign), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
         return 0;
     };
     bool tablesDirty = true;
@@ -904,12 +916,6 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         galn& m = G.al[ln.anchor];
         const segref mLeft = ln.left1, mRight = ln.right1;   /* the neighbours this anchor was started with */
         if (tablesDirty) { if (push_segments()) return -1; tablesDirty = false; }
-        if (G.haligns.size() > ln.alignsCap) {
-            cudaFree(ln.d_aligns); ln.alignsCap = G.haligns.size() * 2 + 256;
-            CUDA_TRY(cudaMalloc(&ln.d_aligns, ln.alignsCap * sizeof(dalign)));
-        }
-        if (!G.haligns.empty())
-            CUDA_TRY(cudaMemcpyAsync(ln.d_aligns, G.haligns.data(), G.haligns.size() * sizeof(dalign), cudaMemcpyHostToDevice, ln.stream));
         /* get_above_below :4043-4060 */
         int below = G.oed; while (below >= 0 && !(G.al[below].end1 < m.pos1)) below = G.al[below].prev;
         int above = G.obi; while (above >= 0 && !(G.al[above].pos1 > m.pos1)) above = G.al[above].next;
@@ -933,11 +939,10 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             J.leftSeg = dev_ref(G, mLeft); J.rightSeg = dev_ref(G, mRight);
             int lst = rev ? below : above;
             J.alignList = lst >= 0 ? G.al[lst].devIx : -1;
-            J.al = ln.d_aligns;
+            J.al = curAligns;
             J.tb = ln.tb[side]; J.tbLen = tbLen; J.tbRow = ln.tbRow[side]; J.tbRowCap = ln.tbRowCap[side];
             J.ops = ln.ops[side]; J.opsCap = ln.opsCap[side]; J.act = ln.act[side]; J.actCap = ln.actCap[side];
         }
-        CUDA_TRY(cudaMemcpyAsync(ln.d_jobs, ln.h_jobs, 2 * sizeof(dp_job), cudaMemcpyHostToDevice, ln.stream));
         CUDA_TRY(cudaEventRecord(ln.evA, ln.stream));
         if (ln.mode == 0)
             k_ydrop_reg<4><<<2, RG_THREADS, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
@@ -956,7 +961,6 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ln.evB, ln.stream));
-        CUDA_TRY(cudaMemcpyAsync(ln.h_jobs, ln.d_jobs, 2 * sizeof(dp_job), cudaMemcpyDeviceToHost, ln.stream));
         return 0;
     };
 
@@ -1204,6 +1208,8 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     }
     /* abandon speculative work that was never needed */
     for (auto& ln : gc->lanes) if (ln.busy) { cudaStreamSynchronize(ln.stream); ln.busy = false; }
+    for (dalign* d : alignEpochs) cudaFree(d);
+    alignEpochs.clear();
     if (violation) {
         /* an estimate was too small: redo everything in strict order (exact by construction) */
         for (int o = G.obi; o >= 0; o = G.al[o].next) { galn& m = G.al[o]; if (m.align) { free(m.align->script); free(m.align); } }
