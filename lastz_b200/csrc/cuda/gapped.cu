@@ -1104,7 +1104,11 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         tablesDirty = true;
     };
 
-    struct pend { u64 lo, hi; s64 diag; };
+    /* an earlier, still unresolved anchor: [lo,hi] = rows its extension covers (estimated while in
+     * flight, exact once finished) -- nothing that overlaps it may START; [clo,chi] = rows that it, or an
+     * anchor waiting on it, could still come to cover -- nothing that overlaps it may COMMIT */
+    struct pend { u64 lo, hi, clo, chi; };
+    auto widen = [](u64 v, u64 by, bool down) -> u64 { return down ? (v > by ? v - by : 0) : v + by; };
     while (hd < n && !violation) {
         while (hd < n && fin[hd]) hd++;
         if (hd >= n) break;
@@ -1114,7 +1118,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         int freeLanes = 0;
         for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
         const u64 est = std::max<u64>(reach, maxRows + maxRows / 4);
-        bool progressed = false; u64 examined = 0;
+        bool progressed = false; u64 examined = 0; int starved = 0;
         for (u64 j = hd; j < n && examined < 8192; j++) {
             if (fin[j]) continue;
             examined++;
@@ -1145,7 +1149,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                     if (trace) fprintf(stderr, "[gx %.4f] invalid a=%llu rows=[%llu,%llu]\n", now(), (unsigned long long)j, (unsigned long long)lo, (unsigned long long)hi);
                 } else {
                     bool clear = true;
-                    for (auto& u : unresolved) if (!(hi < u.lo || lo > u.hi)) { clear = false; break; }
+                    for (auto& u : unresolved) if (!(hi < u.clo || lo > u.chi)) { clear = false; break; }
                     if (strict && !unresolved.empty()) clear = false;
                     if (clear) {
                         /* alignments committed ahead of their turn must be out of reach of this one, and vice versa */
@@ -1154,39 +1158,35 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                         commit_anchor(j); progressed = true;
                         continue;
                     }
-                    unresolved.push_back(pend{ lo, hi, dy });
+                    unresolved.push_back(pend{ lo, hi, widen(lo, 2 * est, true), widen(hi, 2 * est, false) });
                     continue;
                 }
             }
             if (inflight[j]) {
                 gx_lane* ln = NULL;
                 for (int z = 0; z < W; z++) if (gc->lanes[z].busy && gc->lanes[z].anchor == j) ln = &gc->lanes[z];
-                unresolved.push_back(pend{ ln ? ln->estLo : 0, ln ? ln->estHi : ~0ull, dy });
+                const u64 lo = ln ? ln->estLo : 0, hi = ln ? ln->estHi : ~0ull;
+                unresolved.push_back(pend{ lo, hi, widen(lo, 2 * est, true), widen(hi, 2 * est, false) });
                 continue;
             }
-            /* not started: may start if its estimated rows clear every unresolved earlier anchor */
+            /* not started: may start if its estimated rows clear every earlier extension */
             std::pair<u64, u64> rg = est_region(y, est);
-            bool clash = false, inside = false;
-            for (auto& u : unresolved) {
-                if (rg.second < u.lo || rg.first > u.hi) continue;
-                clash = true;
-                if (y.pos1 >= u.lo && y.pos1 <= u.hi && llabs(dy - u.diag) < 5000) { inside = true; break; }
-            }
+            bool clash = false;
+            for (auto& u : unresolved) if (!(rg.second < u.lo || rg.first > u.hi)) { clash = true; break; }
             if (strict && !unresolved.empty()) clash = true;
-            if (!clash && freeLanes > 0) {
-                gx_lane* fl = NULL;
-                for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
-                if (start_anchor(*fl, j)) return -1;
-                fl->estLo = rg.first; fl->estHi = rg.second;
-                freeLanes--; if (j != hd) G.st.speculated++;
-                unresolved.push_back(pend{ rg.first, rg.second, dy });
+            if (clash) continue;                             /* waits on that extension; its commit window already covers this anchor */
+            if (freeLanes == 0) {
+                /* could start but no lane is free: hold later commits off its rows, and stop looking */
+                unresolved.push_back(pend{ 1, 0, rg.first, rg.second });
+                if (++starved >= 8) break;
                 continue;
             }
-            /* blocked (or no lane): an anchor inside an unresolved extension on its own diagonal will
-             * almost surely be covered by it and needs no reservation; anything else keeps later
-             * anchors out of its way */
-            if (!inside || !clash) unresolved.push_back(pend{ rg.first, rg.second, dy });
-            if (unresolved.size() > 4096) break;
+            gx_lane* fl = NULL;
+            for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) { fl = &gc->lanes[z]; break; }
+            if (start_anchor(*fl, j)) return -1;
+            fl->estLo = rg.first; fl->estHi = rg.second;
+            freeLanes--; if (j != hd) G.st.speculated++;
+            unresolved.push_back(pend{ rg.first, rg.second, widen(rg.first, 2 * est, true), widen(rg.second, 2 * est, false) });
         }
         if (violation) break;
         if (progressed) continue;                            /* commits/skips may have unblocked more */
