@@ -327,7 +327,11 @@ def main():
     bytes_per_hit = 12.0 + 0.5 * my_bp / max(1, my_hits)      # 4 B position + 8 B diagEnd + 0.5 B/column
     peak, peak_src = measured_peak()
     achieved = bytes_per_hit * my_hits / max(ext_s, 1e-12) / 1e9
-    e2e_hits = total("hits", accs_e2e)
+    # every cross-rank aggregate is computed HERE, on all ranks (collectives must not sit under `if rank == 0`)
+    agg = {"e2e_hits": total("hits", accs_e2e), "e2e_cells": total("cells", accs_e2e),
+           "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_wall", accs_e2e),
+           "hsps": total("hsps", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e)}
+    e2e_hits = agg["e2e_hits"]
 
     if rank == 0:
         line = {"metric": "seed-hits/s (seed stage); Gcells/s in gcells_per_s", "value": hits / seed_s, "unit": "hits/s",
@@ -337,16 +341,16 @@ def main():
                 "stage_ms_per_step": {"seed": 1e3 * seed_s / args.steps, "gapped": 1e3 * gap_s / args.steps,
                                       "index_build_once": 1e3 * index_s},
                 "counts_per_step": {"raw_seed_hits": hits / args.steps, "dp_cells": cells / args.steps,
-                                    "hsps": total("hsps", accs) / args.steps, "segments_gathered": accs[-1]["gathered"]},
+                                    "hsps": agg["hsps"] / args.steps, "segments_gathered": accs[-1]["gathered"]},
                 "timing": "host clock around blocking C-ABI calls, barrier+sync both sides, max over ranks; "
                           "kernels timed by CUDA events on the library's stream",
                 "clocks": clocks, "gpu_launches": int(total_l.item()),
-                "e2e": {"value": e2e_hits / worst("seed_wall", accs_e2e),
+                "e2e": {"value": e2e_hits / agg["e2e_seed_wall"],
                         "unit": "hits/s (host clock: H2D copy of the query from host memory + lzb_seed_hit_search incl. D2H of the HSP table)",
-                        "gcells_per_s": total("cells", accs_e2e) / worst("gap_wall", accs_e2e) / 1e9,
+                        "gcells_per_s": agg["e2e_cells"] / agg["e2e_gap_wall"] / 1e9,
                         "ms_per_step": 1e3 * dt_e2e / args.steps,
-                        "h2d_bytes_per_step": int(total("h2d", accs_e2e) / args.steps),
-                        "d2h_bytes_per_step": int(total("d2h", accs_e2e) / args.steps)},
+                        "h2d_bytes_per_step": int(agg["h2d"] / args.steps),
+                        "d2h_bytes_per_step": int(agg["d2h"] / args.steps)},
                 "roofline": {"kernel": "k_extend (bucket replay + x-drop)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n}}
