@@ -117,9 +117,9 @@ typedef struct lzb_seed_stats {
     uint64_t bpExtended;       /* seedSearchStats.bpExtended (seed_search.c:2839) */
     uint64_t hsps;             /* HSPs reported */
     double   seconds;          /* device time of the call (CUDA events), 0 for the oracle */
-    double   kernelSeconds[8]; /* CUDA-event time per kernel: 0 words 1 count 2 slots 3 scan 4 expand
-                                  5 sort 6 bounds 7 extend */
-    uint64_t kernelLaunches[8];/* launches behind each kernelSeconds entry */
+    double   kernelSeconds[12];/* CUDA-event time per kernel: 0 words 1 count 2 slots 3 scan 4 expand 5 sort
+                                  6 bounds 7 extend (fused) 8 right 9 replay 10 left */
+    uint64_t kernelLaunches[12];/* launches behind each kernelSeconds entry */
 } lzb_seed_stats;
 
 /* gapped_extend (gapped_extend.h:153-159) arguments */

@@ -59,7 +59,7 @@ class SeedParams(C.Structure):
 class SeedStats(C.Structure):
     _fields_ = [("wordsInQuery", C.c_uint64), ("rawSeedHits", C.c_uint64), ("extensions", C.c_uint64),
                 ("bpExtended", C.c_uint64), ("hsps", C.c_uint64), ("seconds", C.c_double),
-                ("kernelSeconds", C.c_double * 8), ("kernelLaunches", C.c_uint64 * 8)]
+                ("kernelSeconds", C.c_double * 12), ("kernelLaunches", C.c_uint64 * 12)]
 
 
 class GappedParams(C.Structure):

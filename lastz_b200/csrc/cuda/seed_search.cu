@@ -344,6 +344,8 @@ k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuck
 
 /* ------------------------------------------------------------------------------------------ */
 
+#include "xdrop_split.cuh"
+
 static inline u32 host_pack(const lzb_seed* sd, u64 w) {
     u32 p = 0;
     for (int i = 0; i < sd->numParts; i++) p |= (u32)(w >> sd->shift[i]) & sd->mask[i];
@@ -441,6 +443,15 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cudaMalloc(&keysA, hitCap * 4)); CUDA_TRY(cudaMalloc(&keysB, hitCap * 4));
     CUDA_TRY(cudaMalloc(&valsA, hitCap * 8)); CUDA_TRY(cudaMalloc(&valsB, hitCap * 8));
     CUDA_TRY(cudaMalloc(&d_cand, (size_t)candCap * sizeof(cand_rec)));
+    /* three-kernel extension (xdrop_split.cuh) needs per-hit scratch; LZB_FUSED_EXTEND=1 keeps the fused kernel */
+    const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= 16 &&
+                             !(getenv("LZB_FUSED_EXTEND") && atoi(getenv("LZB_FUSED_EXTEND")));
+    right_rec* d_right = NULL; live_rec* d_live = NULL; unsigned long long* d_nlive = NULL;
+    if (splitExtend) {
+        CUDA_TRY(cudaMalloc(&d_right, hitCap * sizeof(right_rec)));
+        CUDA_TRY(cudaMalloc(&d_live, hitCap * sizeof(live_rec)));
+        CUDA_TRY(cudaMalloc(&d_nlive, 8));
+    }
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(NULL, tmpBytes, keysA, keysB, valsA, valsB, hitCap, 0, hashBits, st));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmpScan, d_slotcnt, d_slotoff, slotCap + 1, st));
     if (tmpScan > tmpBytes) tmpBytes = tmpScan;
@@ -463,7 +474,12 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             tb = tmpBytes;
             TIMED(5, cub::DeviceRadixSort::SortPairs(d_tmp, tb, keysA, keysB, valsA, valsB, nh, 0, hashBits, st));
             TIMED(6, (k_bucket_bounds<<<(nbuckets + 256) / 256, 256, 0, st>>>(keysB, nh, nbuckets, d_bstart)));
-            if (c->sc.numClasses <= 16)
+            if (splitExtend) {
+                CUDA_TRY(cudaMemsetAsync(d_nlive, 0, 8, st));
+                TIMED(8, (k_right<<<c->smCount * 8, 256, 0, st>>>(valsB, nh, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_right)));
+                TIMED(9, (k_replay<<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, d_right, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_live, d_nlive)));
+                TIMED(10, (k_left<<<c->smCount * 8, 256, 0, st>>>(d_live, d_nlive, t->d_cls, q->d_cls, t->d_seq, q->d_seq, c->d_sc, P, d_cand, candCap, d_cnt)));
+            } else if (c->sc.numClasses <= 16)
                 TIMED(7, (k_extend<true><<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
                                                                c->d_sc, P, d_E, d_cand, candCap, d_cnt)));
             else
@@ -534,12 +550,12 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     cudaEventDestroy(evBegin); cudaEventDestroy(evEnd); cudaEventDestroy(evMid); cudaEventDestroy(evMid2);
     cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
     cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
-    cudaFree(d_cand); cudaFree(d_tmp);
+    cudaFree(d_cand); cudaFree(d_tmp); cudaFree(d_right); cudaFree(d_live); cudaFree(d_nlive);
     return 0;
 cleanup_fail:
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
     cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
-    cudaFree(d_cand); cudaFree(d_tmp);
+    cudaFree(d_cand); cudaFree(d_tmp); cudaFree(d_right); cudaFree(d_live); cudaFree(d_nlive);
     return -1;
 }

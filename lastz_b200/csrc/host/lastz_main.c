@@ -169,7 +169,7 @@ int main(int argc, char** argv) {
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
     uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
-    double ks[8] = {0}, gk = 0; uint64_t gExt = 0, gSpec = 0, gRedo = 0, gLaunch = 0, gTrunc = 0;
+    double ks[12] = {0}, gk = 0; uint64_t gExt = 0, gSpec = 0, gRedo = 0, gLaunch = 0, gTrunc = 0;
     lzb_seqfile* qf = lzb_seqfile_open(o.querySpec);
     lzb_seq query;
     while (lzb_seqfile_next(qf, &query)) {
@@ -192,7 +192,7 @@ int main(int argc, char** argv) {
                 if (lzb_seed_hit_search(ctx, T, Q, &seed, lzb_upper_nuc_to_bits, &sp, &segs, &nsegs, &sst))
                     lzb_die("%s", lzb_last_error());
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
-                for (int z = 0; z < 8; z++) ks[z] += sst.kernelSeconds[z];
+                for (int z = 0; z < 12; z++) ks[z] += sst.kernelSeconds[z];
             }
             int headerDone = 0;
             if (!o.gapped) {
@@ -234,8 +234,8 @@ int main(int argc, char** argv) {
                 lzb_backend(), (unsigned long long)totHits, (unsigned long long)totHsps,
                 (unsigned long long)totCells, seedSec, gapSec);
     if (o.showStats) {
-        fprintf(stderr, "seed kernels (s): words=%.4f count=%.4f slots=%.4f scan=%.4f expand=%.4f sort=%.4f bounds=%.4f extend=%.4f\n",
-                ks[0], ks[1], ks[2], ks[3], ks[4], ks[5], ks[6], ks[7]);
+        fprintf(stderr, "seed kernels (s): words=%.4f count=%.4f slots=%.4f scan=%.4f expand=%.4f sort=%.4f bounds=%.4f extend=%.4f right=%.4f replay=%.4f left=%.4f\n",
+                ks[0], ks[1], ks[2], ks[3], ks[4], ks[5], ks[6], ks[7], ks[8], ks[9], ks[10]);
         fprintf(stderr, "gapped: extended=%llu speculated=%llu redone=%llu truncated=%llu launches=%llu dp_kernel_seconds=%.4f\n",
                 (unsigned long long)gExt, (unsigned long long)gSpec, (unsigned long long)gRedo,
                 (unsigned long long)gTrunc, (unsigned long long)gLaunch, gk);
