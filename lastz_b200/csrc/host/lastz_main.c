@@ -23,6 +23,7 @@ typedef struct {
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments */
     int device, showStats, speculation;
+    int chainDiag, chainAnti;
     char args[4096];
 } options;
 
@@ -82,6 +83,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "C=2")) { o->chain = 1; o->gapped = 1; }
         else if (!strcmp(a, "C=3")) { o->chain = 0; o->gapped = 0; }
         else if (!strcmp(a, "--chain")) o->chain = 1;
+        else if (starts(a, "--chain=")) { o->chain = 1; if (sscanf(v, "%d,%d", &o->chainDiag, &o->chainAnti) != 2) lzb_die("can't understand %s", a); }
         else if (!strcmp(a, "--nochain")) o->chain = 0;
         else if (!strcmp(a, "--noentropy")) o->entropy = 0;
         else if (!strcmp(a, "--entropy")) o->entropy = 1;
@@ -147,7 +149,6 @@ int main(int argc, char** argv) {
     if (!o.haveY) o.Y = ss.yDropSet ? ss.yDrop : ss.gapOpen + 300 * ss.gapExtend;
     if (!o.haveL) o.L = ss.gappedThresholdSet ? ss.gappedThreshold : (o.gfExtend == LZB_GFEX_XDROP ? o.K : 3000);
     if (!o.haveStep && ss.stepSet) o.step = ss.step;
-    if (o.chain) lzb_die("--chain is not implemented yet in lastz_b200");
     lzb_seed seed; lzb_seed_parse(&seed, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, o.withTrans);
 
     FILE* out = stdout;
@@ -194,6 +195,8 @@ int main(int argc, char** argv) {
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
                 for (int z = 0; z < 12; z++) ks[z] += sst.kernelSeconds[z];
             }
+            if (o.chain)                                         /* try_reduce_to_chain lastz.c:3349, chainScale = 100 (:511) */
+                lzb_reduce_to_chain(segs, &nsegs, o.chainDiag, o.chainAnti, 100, ss.sub['A' * 256 + 'A']);
             int headerDone = 0;
             if (!o.gapped) {
                 for (uint64_t k = 0; k < nsegs; k++) {

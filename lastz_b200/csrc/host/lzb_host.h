@@ -61,6 +61,9 @@ void lzb_seed_parse(lzb_seed* out, const char* pattern, int withTrans);
 extern const int8_t lzb_upper_nuc_to_bits[256];                /* dna_utilities.c:76-94 */
 extern const int8_t lzb_nuc_to_bits[256];                      /* dna_utilities.c:56-74 */
 
+/* best-chain reduction (chain.c:497, penalties lastz.c:3687); rewrites segs[0..*n) to the chain, sorted by pos1 */
+int32_t lzb_reduce_to_chain(lzb_segment* segs, uint64_t* n, int32_t diagPen, int32_t antiPen, int32_t scale, int32_t subAA);
+
 /* output writers */
 void lzb_lav_job_header(FILE*, const char* prog, const char* name1, const char* name2,
                         const char* args, const lzb_scoreset*, int32_t K, int32_t L);  /* lav.c:40 */

@@ -21,6 +21,8 @@ def norm(t):
     ("base_test.hits.lav", ["W=8", "T=0", "--plus", "--nogfextend", "--nogapped"]),
     ("base_test.hsp.lav", ["C=3", "W=8", "T=0"]),
     ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),
+    ("base_test.chained.lav", ["C=1", "W=8", "T=0"]),
+    ("base_test.extended.lav", ["C=2", "W=8", "T=0"]),
 ])
 def test_cli_reproduces_golden_lav(golden, opts):
     out, _ = run_cli(PRODUCT_CLI, [CAT, PIG] + opts)
@@ -40,6 +42,8 @@ def test_cli_segments_round_trip(tmp_path):
     (1000000, ["--nogapped", "--format=segments"]),
     (1000000, ["--allocate:traceback=8M"]),
     (500000, ["--seed=14of22", "--notransition", "--step=2", "--hspthresh=2200"]),
+    (1000000, ["--chain"]),
+    (1000000, ["--chain=40,30", "--nogapped"]),
 ])
 def test_cli_matches_reference_on_synthetic(synth, size, opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI

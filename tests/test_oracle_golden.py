@@ -17,6 +17,8 @@ CASES = [
     ("base_test.hits.lav", ["W=8", "T=0", "--plus", "--nogfextend", "--nogapped"]),  # Makefile:295
     ("base_test.hsp.lav", ["C=3", "W=8", "T=0"]),                                    # Makefile:306
     ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),                        # Makefile:465
+    ("base_test.chained.lav", ["C=1", "W=8", "T=0"]),                                # Makefile:351 (chain only)
+    ("base_test.extended.lav", ["C=2", "W=8", "T=0"]),                               # Makefile:362 (chain + gapped)
 ]
 
 
@@ -48,6 +50,9 @@ def test_oracle_segments_round_trip(tmp_path):
     (200000, ["--seed=14of22", "--notransition", "--step=3"]),
     (200000, ["--transition=2", "--hspthresh=2500", "--noentropy"]),
     (200000, ["--ydrop=4000", "--gappedthresh=5000", "--xdrop=400"]),
+    (300000, ["--chain", "--nogapped"]),                     # chain.c: K-d tree order decides ties
+    (300000, ["--chain=40,30", "--nogapped"]),               # diagonal / anti-diagonal penalties (lastz.c:3687)
+    (300000, ["--chain"]),                                   # config 4: chained + gapped
 ])
 def test_oracle_matches_reference_on_synthetic(synth, size, opts):
     t, q = synth(size)
