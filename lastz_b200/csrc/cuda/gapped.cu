@@ -58,6 +58,7 @@ struct dp_job {
     int* act; u32 actCap;             /* 5 ints per active segment */
     const dalign* al;                 /* alignment table snapshot this job runs against */
     int skip;                         /* nonzero: nothing to do (the other side of a rerun) */
+    u32* dbg; u32 dbgCap;             /* LZB_DP_DEBUG: per-row {LY, colEnd, best, used} for kernel-vs-kernel diffs */
     /* results */
     s32 score; u32 end1, end2, nops, rows; int status; unsigned long long cells;
 };
@@ -214,6 +215,7 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     int alignList = J->alignList;
     int* act = J->act; int nact = 0;
     const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
+    u32* const dbg = J->dbg; const u32 dbgCap = J->dbgCap;
     /* far edge (e1 forward, b1 reversed) and type of the two bounding segments */
     u32 lLim = 0, rLim = 0; int lTyp = 0, rTyp = 0;
 #define LOAD_BOUND(ref_, lim_, typ_) \
@@ -503,6 +505,7 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         else if (bndMoved) { end1 = row; end2 = bndCol; endIsBnd = 1; }
         cells += colEnd - leftCol;
         used += colEnd - leftCol;
+        if (dbg && tid == 0 && row < dbgCap) { u32* g = dbg + 4 * (size_t)row; g[0] = leftCol; g[1] = colEnd; g[2] = (u32)best; g[3] = (u32)used; }
         u32 npCol;
         if (la) { LY = fa; npCol = la - 1; } else { LY = colEnd; npCol = leftCol; }
         s32* t = Cprev; Cprev = Ccur; Ccur = t;
@@ -548,7 +551,8 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     }
 }
 
-#include "ydrop_reg.cuh"
+#include "ydrop_warp.cuh"
+#include "ydrop_mw.cuh"
 
 /* ---- K4: segment_peak gapped_extend.c:515-559, one thread per HSP ---- */
 __global__ void k_peaks(lzb_segment* __restrict__ seg, u64 n, const u8* __restrict__ cls1,
@@ -731,10 +735,11 @@ struct gx_lane {
     cudaStream_t stream; cudaEvent_t evA, evB;
     dp_job* h_jobs;                      /* pinned, 2 entries */
     dp_job* d_jobs;
+    u32* dbg[2];
     u8* tb[2]; u32 tbBytes; u32* tbRow[2]; u32 tbRowCap[2]; u32* ops[2]; u32 opsCap[2]; int* act[2]; u32 actCap[2];
     /* state */
     bool busy; u64 anchor; size_t snapshot; segref left1, right1; u32 ring;
-    int mode;                            /* 0/1 register kernel K=4/8, 2/3 shared-memory kernel ring 4096/8192 */
+    int mode;                            /* 0 four-warp register kernel (1024-column window), 1 one-warp kernel (512); 2/3 shared-memory kernel, ring 4096/8192 */
     u64 estLo, estHi;                    /* seq1 rows this extension is expected to examine */
 };
 
@@ -746,7 +751,7 @@ struct gx_cache {                        /* lives in the context: lanes are expe
 static void free_lane(gx_lane& ln) {
     cudaStreamDestroy(ln.stream); cudaEventDestroy(ln.evA); cudaEventDestroy(ln.evB);
     cudaFreeHost(ln.h_jobs);
-    for (int s = 0; s < 2; s++) { cudaFree(ln.tb[s]); cudaFree(ln.tbRow[s]); cudaFree(ln.ops[s]); cudaFree(ln.act[s]); }
+    for (int s = 0; s < 2; s++) { cudaFree(ln.dbg[s]); cudaFree(ln.tb[s]); cudaFree(ln.tbRow[s]); cudaFree(ln.ops[s]); cudaFree(ln.act[s]); }
 }
 
 void lzb_gapped_cache_free(lzb_ctx* c) {
@@ -853,13 +858,18 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     CUDA_TRY(cudaFuncSetAttribute(k_ydrop<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(k_ydrop<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     int dpThreads = 256;
-    /* narrow bands (the common case) run on the register-resident kernel; LZB_DP_MODE forces a start mode */
-    int firstMode = 2;    /* measured: the register kernel is ~1.5x SLOWER per row than the shared-memory one */
-    { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3 && (mdv >= 2 || c->sc.gapExtend > 0)) firstMode = mdv; } }
+    /* start with the register-resident kernel (1024-column window), fall back to the shared-memory kernel (4096, 8192);
+     * LZB_DP_MODE forces the starting mode */
+    int firstMode = 0;
+    { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3) firstMode = mdv; } }
     if (cenv) firstMode = 2;                                   /* an explicit ring size means the shared-memory kernel */
     { const char* e = getenv("LZB_DP_THREADS"); if (e && atoi(e) == 128) dpThreads = 128; }
 
     const bool trace = getenv("LZB_GAP_TRACE") != NULL;
+    const char* dbgPath = getenv("LZB_DP_DEBUG");           /* file that receives every finished DP's per-row record */
+    const u32 DBG_ROWS = 1u << 20;
+    const bool prof = getenv("LZB_GAP_PROFILE") != NULL;     /* host-side breakdown of the scheduler on stderr */
+    double pfSweep = 0, pfWait = 0, pfHarvest = 0, pfPush = 0, pfLaneBusy = 0, pfNbr = 0; u64 pfSweeps = 0, pfExamined = 0, pfNbrCalls = 0;
     u64 headAnchor = 0;
     auto now = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count(); };
     std::vector<spec_result> spec(n);
@@ -915,7 +925,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     auto launch = [&](gx_lane& ln, int onlySide) -> int {
         galn& m = G.al[ln.anchor];
         const segref mLeft = ln.left1, mRight = ln.right1;   /* the neighbours this anchor was started with */
-        if (tablesDirty) { if (push_segments()) return -1; tablesDirty = false; }
+        if (tablesDirty) { const double p0 = prof ? now() : 0; if (push_segments()) return -1; tablesDirty = false; if (prof) pfPush += now() - p0; }
         /* get_above_below :4043-4060 */
         int below = G.oed; while (below >= 0 && !(G.al[below].end1 < m.pos1)) below = G.al[below].prev;
         int above = G.obi; while (above >= 0 && !(G.al[above].pos1 > m.pos1)) above = G.al[above].next;
@@ -942,12 +952,16 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             J.al = curAligns;
             J.tb = ln.tb[side]; J.tbLen = tbLen; J.tbRow = ln.tbRow[side]; J.tbRowCap = ln.tbRowCap[side];
             J.ops = ln.ops[side]; J.opsCap = ln.opsCap[side]; J.act = ln.act[side]; J.actCap = ln.actCap[side];
+            if (dbgPath) {
+                if (!ln.dbg[side]) CUDA_TRY(cudaMalloc(&ln.dbg[side], (size_t)DBG_ROWS * 16));
+                J.dbg = ln.dbg[side]; J.dbgCap = DBG_ROWS;
+            }
         }
         CUDA_TRY(cudaEventRecord(ln.evA, ln.stream));
         if (ln.mode == 0)
-            k_ydrop_reg<4><<<2, RG_THREADS, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
+            k_ydrop_mw<8, 4><<<2, 128, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
         else if (ln.mode == 1)
-            k_ydrop_reg<8><<<2, RG_THREADS, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
+            k_ydrop_warp<16><<<2, 32, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
         else {
             ln.ring = ln.mode == 2 ? ring0 : ring0 * 2;
             size_t smem = (size_t)ln.ring * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
@@ -1014,6 +1028,16 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             r.ops.resize(J.nops);
             if (J.nops) CUDA_TRY(cudaMemcpyAsync(r.ops.data(), ln.ops[side], (size_t)J.nops * 4, cudaMemcpyDeviceToHost, ln.stream));
             G.st.dpCells += J.cells; G.st.dpRows += J.rows; G.st.truncated += (J.status == DP_TRUNCATED);
+            if (dbgPath && J.dbg) {
+                u32 nr = J.rows < DBG_ROWS ? J.rows : DBG_ROWS;
+                std::vector<u32> rows((size_t)nr * 4);
+                CUDA_TRY(cudaMemcpy(rows.data(), J.dbg, (size_t)nr * 16, cudaMemcpyDeviceToHost));
+                FILE* df = fopen(dbgPath, "ab");
+                if (df) {
+                    u32 hdr[8] = { 0x44504447u, (u32)ln.anchor, (u32)side, J.rows, (u32)J.status, (u32)J.cells, (u32)ln.mode, nr };
+                    fwrite(hdr, 4, 8, df); fwrite(rows.data(), 16, nr, df); fclose(df);
+                }
+            }
         }
         CUDA_TRY(cudaStreamSynchronize(ln.stream));
         if (redo != -2) {
@@ -1021,7 +1045,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                                ln.h_jobs[0].status, ln.h_jobs[1].status, ln.h_jobs[0].rows, ln.h_jobs[1].rows, ms, ln.mode);
             bool ringGrow = false;
             for (int side = 0; side < 2; side++) if (ln.h_jobs[side].status == DP_RING) ringGrow = true;
-            if (ringGrow) ln.mode++;
+            if (ringGrow) ln.mode = ln.mode < 2 ? 2 : ln.mode + 1;
             /* rerun with the neighbours it was started with; the (possibly newer) alignment table is a
              * superset, and validation still uses the ORIGINAL snapshot, so any difference is caught */
             return launch(ln, redo);
@@ -1119,14 +1143,18 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         for (int z = 0; z < W; z++) if (!gc->lanes[z].busy) freeLanes++;
         const u64 est = std::max<u64>(reach, maxRows + maxRows / 4);
         bool progressed = false; u64 examined = 0; int starved = 0;
+        const double sw0 = prof ? now() : 0; pfSweeps++;
         for (u64 j = hd; j < n && examined < 8192; j++) {
             if (fin[j]) continue;
-            examined++;
+            examined++; pfExamined++;
             galn& y = G.al[j];
             const s64 dy = (s64)y.pos1 - (s64)y.pos2;
             int coverer = -1;
             if (!inflight[j] || spec[j].have) {
-                if (!anchor_neighbours(G, y, &coverer)) {
+                const double n0 = prof ? now() : 0;
+                const bool open = anchor_neighbours(G, y, &coverer);
+                if (prof) { pfNbr += now() - n0; pfNbrCalls++; }
+                if (!open) {
                     /* on an alignment committed EARLIER in the order: skipped for good (:1335) */
                     if (coverer >= 0 && (u64)coverer > j && coverer != (int)n) { violation = true; break; }
                     fin[j] = 1; spec[j].have = false; spec[j].L.ops.clear(); spec[j].R.ops.clear(); progressed = true;
@@ -1188,24 +1216,38 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             freeLanes--; if (j != hd) G.st.speculated++;
             unresolved.push_back(pend{ rg.first, rg.second, widen(rg.first, 2 * est, true), widen(rg.second, 2 * est, false) });
         }
+        if (prof) pfSweep += now() - sw0;
         if (violation) break;
         if (progressed) continue;                            /* commits/skips may have unblocked more */
         /* ---- nothing more to decide: wait for a lane ---- */
-        bool any = false;
-        for (int z = 0; z < W; z++) if (gc->lanes[z].busy) any = true;
+        bool any = false; int nbusy = 0;
+        for (int z = 0; z < W; z++) if (gc->lanes[z].busy) { any = true; nbusy++; }
         if (!any) return lzb_fail("internal error: gapped scheduler stalled at anchor %llu", (unsigned long long)hd);
         bool got = false;
+        const double w0 = prof ? now() : 0; double hv = 0;
         while (!got) {
             for (int z = 0; z < W; z++) {
                 gx_lane& ln = gc->lanes[z];
                 if (!ln.busy) continue;
                 cudaError_t e = cudaStreamQuery(ln.stream);
-                if (e == cudaSuccess) { const u64 a = ln.anchor; if (harvest(ln)) return -1; if (!ln.busy) { got = true; maxRows = std::max<u64>(maxRows, std::max<u64>(spec[a].L.rows, spec[a].R.rows)); } }
+                if (e == cudaSuccess) {
+                    const u64 a = ln.anchor; const double h0 = prof ? now() : 0;
+                    if (harvest(ln)) return -1;
+                    if (prof) hv += now() - h0;
+                    if (!ln.busy) { got = true; maxRows = std::max<u64>(maxRows, std::max<u64>(spec[a].L.rows, spec[a].R.rows)); }
+                }
                 else if (e != cudaErrorNotReady) return lzb_fail("Y-drop kernel failed: %s", cudaGetErrorString(e));
             }
             if (!got) std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
+        if (prof) { const double dtw = now() - w0; pfWait += dtw - hv; pfHarvest += hv; pfLaneBusy += dtw * nbusy; }
     }
+    if (prof)
+        fprintf(stderr, "[gx profile] W=%d wall=%.3f sweeps=%llu examined=%llu sweep_s=%.3f (neighbour calls %llu, %.3f s) push_s=%.3f wait_s=%.3f harvest_s=%.3f "
+                        "avg_busy_lanes_while_waiting=%.1f kernel_lane_s=%.3f extended=%llu redone=%llu rows=%llu committed=%zu\n",
+                W, now(), (unsigned long long)pfSweeps, (unsigned long long)pfExamined, pfSweep, (unsigned long long)pfNbrCalls, pfNbr, pfPush, pfWait, pfHarvest,
+                pfWait + pfHarvest > 0 ? pfLaneBusy / (pfWait + pfHarvest) : 0.0, G.st.kernelSeconds[0], (unsigned long long)G.st.anchorsExtended,
+                (unsigned long long)G.st.redone, (unsigned long long)G.st.dpRows, G.committed.size());
     /* abandon speculative work that was never needed */
     for (auto& ln : gc->lanes) if (ln.busy) { cudaStreamSynchronize(ln.stream); ln.busy = false; }
     for (dalign* d : alignEpochs) cudaFree(d);
