@@ -261,12 +261,14 @@ def main():
         return sum(len(p) for p in parts)
 
     def step(resident, handles=None):
-        acc = dict(hits=0, cells=0, seed_s=0.0, gap_s=0.0, ext_s=0.0, ext_launch=0, bp=0, hsps=0, h2d=0, d2h=0,
-                   ext=0, dp_kernel_s=0.0, seed_wall=0.0, gap_wall=0.0)
+        acc = dict(hits=0, cells=0, cells_computed=0, seed_s=0.0, gap_s=0.0, ext_s=0.0, ext_launch=0, bp=0, hsps=0, h2d=0, d2h=0,
+                   ext=0, dp_kernel_s=0.0, dp_launches=0, seed_wall=0.0, gap_wall=0.0, load_wall=0.0, free_wall=0.0, gather_wall=0.0,
+                   words=0, kern=[0.0] * 12, kern_n=[0] * 12)
         tables = []
         for k, (sid, s) in enumerate(strands):
             w0 = time.perf_counter()
             Q = handles[k] if resident else eng.load_query(s)
+            wl = time.perf_counter()
             if not resident:
                 acc["h2d"] += len(s)
             segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid)
@@ -274,18 +276,25 @@ def main():
             tables.append(segs.copy())
             anchors = eng.reduce_to_points(T, Q, segs)
             al, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, identity_check=False, speculation=args.speculation)
-            acc["seed_wall"] += w1 - w0; acc["gap_wall"] += time.perf_counter() - w1
-            acc["hits"] += st.rawSeedHits; acc["seed_s"] += st.seconds
-            # the x-drop extension stage: fused k_extend [7] or k_right + k_replay + k_left [8..10], one of each per chunk
+            w2 = time.perf_counter()
+            acc["seed_wall"] += w1 - w0; acc["gap_wall"] += w2 - w1; acc["load_wall"] += wl - w0
+            acc["hits"] += st.rawSeedHits; acc["seed_s"] += st.seconds; acc["words"] += st.wordsInQuery
+            for i in range(12):
+                acc["kern"][i] += st.kernelSeconds[i]; acc["kern_n"][i] += st.kernelLaunches[i]
+            # the x-drop extension stage: k_extend2 / k_extend [7] or k_right + k_replay + k_left [8..10], one of each per chunk
             acc["ext_s"] += sum(st.kernelSeconds[i] for i in (7, 8, 9, 10))
             acc["ext_launch"] += st.kernelLaunches[7] + st.kernelLaunches[8]
             acc["bp"] += st.bpExtended; acc["ext"] += st.extensions
-            acc["hsps"] += len(segs); acc["cells"] += gst.dpCells; acc["gap_s"] += gst.seconds
-            acc["dp_kernel_s"] += gst.kernelSeconds[0]
+            acc["hsps"] += len(segs); acc["cells"] += gst.dpCells; acc["cells_computed"] += gst.dpCellsComputed
+            acc["gap_s"] += gst.seconds
+            acc["dp_kernel_s"] += gst.kernelSeconds[0]; acc["dp_launches"] += gst.launches
             acc["h2d"] += 48 * len(segs); acc["d2h"] += 2 * 48 * len(segs) + 4 * sum(len(a["ops"]) for a in al)
             if not resident:
                 eng.free_query(Q)
+            acc["free_wall"] += time.perf_counter() - w2
+        w3 = time.perf_counter()
         acc["gathered"] = gather_segments(tables)
+        acc["gather_wall"] = time.perf_counter() - w3
         return acc
 
     def timed(resident):
@@ -343,6 +352,26 @@ def main():
            "hsps": total("hsps", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e)}
     e2e_hits = agg["e2e_hits"]
 
+    def per_step(key, accs_):
+        return 1e3 * sum(a[key] for a in accs_) / args.steps
+
+    def wall_breakdown(accs_):
+        """rank 0's host clock, ms per step: where the time outside the kernels goes"""
+        return {"load_query": per_step("load_wall", accs_), "seed_call": per_step("seed_wall", accs_) - per_step("load_wall", accs_),
+                "seed_device": per_step("seed_s", accs_), "peaks_and_gapped_call": per_step("gap_wall", accs_),
+                "free_query": per_step("free_wall", accs_), "gather_segments": per_step("gather_wall", accs_)}
+
+    # per-kernel view of the seed stage + the DP kernel, this rank (CUDA events on the library's streams)
+    KNAMES = ["k_query_words", "k_count_hits", "k_slot_count", "cub scan", "k_expand", "cub radix sort", "k_bucket_bounds",
+              "k_extend2", "k_right", "k_replay", "k_left", "bucket order (k_bucket_sizes + cub sort)"]
+    kern = [sum(a["kern"][i] for a in accs) for i in range(12)]
+    kern_n = [sum(a["kern_n"][i] for a in accs) for i in range(12)]
+    my_words = sum(a["words"] for a in accs)
+    traffic_per_hit = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp):
+        traffic_per_hit = json.load(open(tp)).get("k_extend_dram_bytes_per_hit")
+
     if rank == 0:
         line = {"metric": "seed-hits/s (seed stage); Gcells/s in gcells_per_s", "value": hits / seed_s, "unit": "hits/s",
                 "gcells_per_s": cells / gap_s / 1e9, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -351,6 +380,7 @@ def main():
                 "stage_ms_per_step": {"seed": 1e3 * seed_s / args.steps, "gapped": 1e3 * gap_s / args.steps,
                                       "index_build_once": 1e3 * index_s},
                 "counts_per_step": {"raw_seed_hits": hits / args.steps, "dp_cells": cells / args.steps,
+                                    "dp_cells_incl_discarded_speculation": total("cells_computed", accs) / args.steps,
                                     "hsps": agg["hsps"] / args.steps, "segments_gathered": accs[-1]["gathered"]},
                 "timing": "host clock around blocking C-ABI calls, barrier+sync both sides, max over ranks; "
                           "kernels timed by CUDA events on the library's stream",
@@ -361,9 +391,39 @@ def main():
                         "ms_per_step": 1e3 * dt_e2e / args.steps,
                         "h2d_bytes_per_step": int(agg["h2d"] / args.steps),
                         "d2h_bytes_per_step": int(agg["d2h"] / args.steps)},
-                "roofline": {"kernel": "x-drop extension stage: k_right + k_replay + k_left per chunk (DESIGN.md K3)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                             "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n}}
+                "roofline": {"kernel": "k_extend2 (bucket replay + x-drop extension, DESIGN.md K3): the dominant kernel of the seed stage, "
+                                       "i.e. of the time `value` is measured on; the step as a whole is dominated by k_ydrop_mw, see roofline_kernels",
+                             "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None if traffic_per_hit is None else traffic_per_hit * my_hits / ext_n,
+                             "traffic_source": None if traffic_per_hit is None else
+                             "dram__bytes_read+write per hit from the ncu --set full capture in profiles/ (5 Mbp pair) x hits per launch here",
+                             "peak_source": peak_src,
+                             "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n},
+                "wall_ms_per_step": {"resident": wall_breakdown(accs), "e2e": wall_breakdown(accs_e2e)}}
+        # the other kernels against the same HBM peak (algorithmic bytes as in DESIGN.md section 4)
+        V = seed.numFlips + 1 if seed.withTrans == 1 else 1
+        alg = {4: 4.0 * V * my_words + 16.0 * my_hits,            # k_expand: index probes + 4 B position read + 12 B record written
+               5: 2 * 2 * 12.0 * my_hits,                         # radix sort: 2 passes x (read + write) x 12 B (16 hash bits)
+               2: 4.0 * V * my_words + 4.0 * V * my_words}        # k_slot_count: probes + one count per slot
+        rk = []
+        for i in range(12):
+            if kern_n[i] == 0:
+                continue
+            ent = {"kernel": KNAMES[i], "launches": kern_n[i], "ms_per_step": 1e3 * kern[i] / args.steps,
+                   "share_of_seed_stage": kern[i] / max(sum(kern), 1e-12)}
+            if i in alg:
+                ent["achieved_gbs"] = alg[i] / max(kern[i], 1e-12) / 1e9
+                ent["frac_of_hbm_peak"] = ent["achieved_gbs"] / peak
+            rk.append(ent)
+        dp_s = sum(a["dp_kernel_s"] for a in accs); my_cells = sum(a["cells_computed"] for a in accs)
+        rk.append({"kernel": "k_ydrop_mw (Y-drop DP + traceback; one launch = the two one-sided DPs of an anchor, up to "
+                             f"{args.speculation} launches in flight)", "launches": sum(a["dp_launches"] for a in accs),
+                   "lane_ms_per_step": 1e3 * dp_s / args.steps, "bound": "latency (integer max-plus recurrence per row), not HBM",
+                   "achieved_gbs": 1.0 * my_cells / max(dp_s, 1e-12) / 1e9, "frac_of_hbm_peak": 1.0 * my_cells / max(dp_s, 1e-12) / 1e9 / peak,
+                   "note": "1 traceback byte per cell is the only algorithmic HBM traffic; lane time is summed over concurrent launches",
+                   "cells_computed_per_step": my_cells / args.steps})
+        line["roofline_kernels"] = rk
         if world == 1 and not args.no_cpu_baseline:
             def hc(ranges):
                 h = c = 0

@@ -118,7 +118,7 @@ typedef struct lzb_seed_stats {
     uint64_t hsps;             /* HSPs reported */
     double   seconds;          /* device time of the call (CUDA events), 0 for the oracle */
     double   kernelSeconds[12];/* CUDA-event time per kernel: 0 words 1 count 2 slots 3 scan 4 expand 5 sort
-                                  6 bounds 7 extend (fused) 8 right 9 replay 10 left */
+                                  6 bounds 7 extend 8 right 9 replay 10 left 11 bucket order */
     uint64_t kernelLaunches[12];/* launches behind each kernelSeconds entry */
 } lzb_seed_stats;
 
@@ -138,7 +138,7 @@ typedef struct lzb_gapped_params {
 typedef struct lzb_gapped_stats {
     uint64_t anchors;          /* anchors given */
     uint64_t anchorsExtended;  /* anchors for which ydrop_align ran */
-    uint64_t dpCells;          /* gappedExtendStats.dpCellsVisited (gapped_extend.c:3593,3776) */
+    uint64_t dpCells;          /* gappedExtendStats.dpCellsVisited (gapped_extend.c:3593,3776): DPs whose result was used */
     uint64_t dpRows;
     uint64_t truncated;        /* one-sided DPs stopped by traceback capacity */
     uint64_t speculated;       /* product: DPs launched speculatively */
@@ -146,6 +146,7 @@ typedef struct lzb_gapped_stats {
     double   seconds;          /* wall time of the call (host clock around the device work) */
     double   kernelSeconds[4]; /* [0] Y-drop DP kernel, [1] traceback kernel (CUDA events), see DESIGN.md */
     uint64_t launches;         /* kernels launched by this call */
+    uint64_t dpCellsComputed;  /* product: every cell the device computed, discarded speculation included (>= dpCells) */
 } lzb_gapped_stats;
 
 typedef struct lzb_ctx    lzb_ctx;     /* one device + stream + scratch */

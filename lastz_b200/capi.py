@@ -72,7 +72,7 @@ class GappedStats(C.Structure):
     _fields_ = [("anchors", C.c_uint64), ("anchorsExtended", C.c_uint64), ("dpCells", C.c_uint64),
                 ("dpRows", C.c_uint64), ("truncated", C.c_uint64), ("speculated", C.c_uint64),
                 ("redone", C.c_uint64), ("seconds", C.c_double), ("kernelSeconds", C.c_double * 4),
-                ("launches", C.c_uint64)]
+                ("launches", C.c_uint64), ("dpCellsComputed", C.c_uint64)]
 
 
 assert C.sizeof(Segment) == 48 and C.sizeof(Alignel) == 64

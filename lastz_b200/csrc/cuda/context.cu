@@ -2,6 +2,7 @@
  * context.cu -- device context, scoring classes, sequence residency.
  * Part of liblastz_b200.so (sm_100a only; there is no CPU path: lzb_open fails without a GPU).
  */
+#include <chrono>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -128,10 +129,15 @@ int lzb_upload_classes(lzb_ctx* c, const u8* h_seq, u32 len, u8** d_seq, u8** d_
 
 extern "C" lzb_query* lzb_query_load(lzb_ctx* c, const uint8_t* seq2, uint32_t len2) {
     cudaSetDevice(c->device);
+    const bool wtrace = getenv("LZB_SEED_TRACE") != NULL;
+    const auto w0 = std::chrono::steady_clock::now();
     lzb_query* q = (lzb_query*)calloc(1, sizeof *q);
     q->ctx = c; q->len = len2;
     q->h_seq = (u8*)malloc((size_t)len2 + 1); memcpy(q->h_seq, seq2, len2); q->h_seq[len2] = 0;
+    const double w1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
     if (lzb_upload_classes(c, q->h_seq, len2, &q->d_seq, &q->d_cls)) { free(q->h_seq); free(q); return NULL; }
+    if (wtrace) fprintf(stderr, "[query load] host copy=%.4f upload+classify enqueue=%.4f s (%u bp)\n", w1,
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count() - w1, len2);
     return q;
 }
 

@@ -1027,7 +1027,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             r.score = J.score; r.end1 = J.end1; r.end2 = J.end2; r.rows = J.rows; r.status = J.status; r.cells = J.cells;
             r.ops.resize(J.nops);
             if (J.nops) CUDA_TRY(cudaMemcpyAsync(r.ops.data(), ln.ops[side], (size_t)J.nops * 4, cudaMemcpyDeviceToHost, ln.stream));
-            G.st.dpCells += J.cells; G.st.dpRows += J.rows; G.st.truncated += (J.status == DP_TRUNCATED);
+            G.st.dpCellsComputed += J.cells;
             if (dbgPath && J.dbg) {
                 u32 nr = J.rows < DBG_ROWS ? J.rows : DBG_ROWS;
                 std::vector<u32> rows((size_t)nr * 4);
@@ -1076,6 +1076,9 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     auto commit_anchor = [&](u64 i) {
         galn& m = G.al[i]; spec_result& sr = spec[i];
         G.st.anchorsExtended++;
+        /* the reference's counters see exactly the DPs whose results are used (gapped_extend.c:3593,3776) */
+        G.st.dpCells += sr.L.cells + sr.R.cells; G.st.dpRows += (u64)sr.L.rows + sr.R.rows;
+        G.st.truncated += (sr.L.status == DP_TRUNCATED) + (sr.R.status == DP_TRUNCATED);
         if (trace) fprintf(stderr, "[gx %.4f] commit a=%llu pos1=%u hd=%llu\n", now(), (unsigned long long)i, m.pos1, (unsigned long long)hd);
         u32 a1 = m.pos1, a2 = m.pos2;
         dpLo[i] = (u64)a1 + 1 >= (u64)sr.L.rows + 2 ? (u64)a1 + 1 - sr.L.rows - 2 : 0; dpHi[i] = (u64)a1 + sr.R.rows + 2;

@@ -30,6 +30,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <vector>
 #include "lzb_cuda.h"
 
@@ -46,12 +47,7 @@ struct sp_dev {
     int gfExtend, plain, entropy;
 };
 
-struct cand_rec {                      /* one HSP candidate, 40 bytes */
-    u32 hit1, hit2;                    /* the seed hit (one past its end) that produced it */
-    u32 pos1, pos2, length;            /* HSP start + length */
-    s32 score;
-    u32 cA, cC, cG, cT;                /* exact-match counts by base (entropy) */
-};
+#include "xdrop_warp.cuh"             /* cand_rec + the warp-cooperative bucket replay */
 
 struct search_counters {
     unsigned long long words, extensions, bpExtended, ncand, overflow;
@@ -342,6 +338,44 @@ k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuck
     if (lane == 0) { if (nExt) atomicAdd(&cnt->extensions, nExt); if (bpw) atomicAdd(&cnt->bpExtended, bpw); }
 }
 
+/* ---- K3c: the default extension kernel (x-drop, <= 16 byte classes): xdrop_warp.cuh ----
+ * Buckets are handed out largest first from a global counter (longest-processing-time order): the
+ * few buckets that hold a homologous diagonal take far longer than the rest, and with a static
+ * assignment they finished long after every other warp had run dry. */
+__global__ void k_bucket_sizes(const u32* __restrict__ bstart, u32 nbuckets, u32* __restrict__ cnt, u32* __restrict__ ids) {
+    for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nbuckets; h += gridDim.x * blockDim.x) { cnt[h] = bstart[h + 1] - bstart[h]; ids[h] = h; }
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_extend2(const u64* __restrict__ hits, const u32* __restrict__ bstart, const u32* __restrict__ order, u32 nbuckets,
+          const u8* __restrict__ cls1, const u8* __restrict__ cls2, const u8* __restrict__ asc1, const u8* __restrict__ asc2,
+          const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32* __restrict__ diagEnd,
+          cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt, u32* __restrict__ nextBucket) {
+    __shared__ s32 lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = sc->msubC[(i >> 4) * LZB_MAX_CLASSES + (i & 15)];
+    __syncthreads();
+    xd_env e;
+    e.cls1 = cls1; e.cls2 = cls2; e.asc1 = asc1; e.asc2 = asc2; e.lut = lut;
+    e.len1 = P.len1; e.len2 = P.len2; e.L = (u32)P.L; e.xDrop = P.xDrop; e.K = P.K; e.entropy = P.entropy;
+    e.cand = cand; e.candCap = candCap; e.ncand = &cnt->ncand;
+    const u32 lane = threadIdx.x & 31;
+    unsigned long long nExt = 0, nBp = 0;
+    for (;;) {
+        u32 slot = 0;
+        if (lane == 0) slot = atomicAdd(nextBucket, 1u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+        if (slot >= nbuckets) break;
+        const u32 h = order[slot];
+        const u32 b0 = bstart[h], b1 = bstart[h + 1];
+        if (b0 == b1) break;                            /* sorted by size: everything after is empty too */
+        u32 E = diagEnd[h];
+        xd_bucket(e, lane, hits, b0, b1, E, nExt, nBp);
+        if (lane == 0) diagEnd[h] = E;
+    }
+    for (int o = 16; o > 0; o >>= 1) { nExt += __shfl_down_sync(0xFFFFFFFFu, nExt, o); nBp += __shfl_down_sync(0xFFFFFFFFu, nBp, o); }
+    if (lane == 0) { if (nExt) atomicAdd(&cnt->extensions, nExt); if (nBp) atomicAdd(&cnt->bpExtended, nBp); }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 
 #include "xdrop_split.cuh"
@@ -375,6 +409,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     *segs = NULL; *nsegs = 0;
     if (stats) memset(stats, 0, sizeof *stats);
     cudaStream_t st = c->stream;
+    /* LZB_SEED_TRACE=1: host wall clock of the call's phases on stderr (what the CUDA-event time does not see) */
+    const bool wtrace = getenv("LZB_SEED_TRACE") != NULL;
+    const auto w0 = std::chrono::steady_clock::now(); double wt[8] = {0}; int wk = 0;
+#define WMARK() do { if (wtrace && wk < 8) wt[wk++] = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count(); } while (0)
 
     /* seed variants in probing order (seed_search.c:522-549) */
     std::vector<u32> flips; flips.push_back(0);
@@ -423,6 +461,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cudaMemcpyAsync(blkcnt.data(), d_blkcnt, (size_t)nblk * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(evMid, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    WMARK();                                            /* [0] small allocations + words + hit counts + sync */
     u64 totalHits = 0, maxBlk = 0;
     for (u32 b = 0; b < nblk; b++) { totalHits += blkcnt[b]; if (blkcnt[b] > maxBlk) maxBlk = blkcnt[b]; }
 
@@ -448,6 +487,16 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
      * remove), so it is opt-in: LZB_SPLIT_EXTEND=1.  Kept because it bounds the work on long repeats. */
     const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= 16 &&
                              getenv("LZB_SPLIT_EXTEND") && atoi(getenv("LZB_SPLIT_EXTEND"));
+    /* the warp-cooperative kernel (xdrop_warp.cuh) is the default x-drop path; LZB_EXTEND_V1=1 keeps the first one */
+    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= 16 && !splitExtend &&
+                            !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
+    u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
+    if (coopExtend) {
+        CUDA_TRY(cudaMalloc(&d_bcnt, (size_t)nbuckets * 4)); CUDA_TRY(cudaMalloc(&d_bcnt2, (size_t)nbuckets * 4));
+        CUDA_TRY(cudaMalloc(&d_bid, (size_t)nbuckets * 4)); CUDA_TRY(cudaMalloc(&d_border, (size_t)nbuckets * 4));
+        CUDA_TRY(cudaMalloc(&d_next, 4));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(NULL, tmpOrder, d_bcnt, d_bcnt2, d_bid, d_border, nbuckets, 0, 32, st));
+    }
     right_rec* d_right = NULL; live_rec* d_live = NULL; unsigned long long* d_nlive = NULL;
     if (splitExtend) {
         CUDA_TRY(cudaMalloc(&d_right, hitCap * sizeof(right_rec)));
@@ -457,9 +506,11 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(NULL, tmpBytes, keysA, keysB, valsA, valsB, hitCap, 0, hashBits, st));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmpScan, d_slotcnt, d_slotoff, slotCap + 1, st));
     if (tmpScan > tmpBytes) tmpBytes = tmpScan;
+    if (tmpOrder > tmpBytes) tmpBytes = tmpOrder;
     CUDA_TRY(cudaMalloc(&d_tmp, tmpBytes));
 
     /* chunk loop */
+    WMARK();                                            /* [1] hit/slot/candidate buffers allocated */
     CUDA_TRY(cudaEventRecord(evMid2, st));
     u64 chunks = 0;
     for (u32 b0 = 0; b0 < nblk;) {
@@ -481,6 +532,14 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
                 TIMED(8, (k_right<<<c->smCount * 8, 256, 0, st>>>(valsB, nh, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_right)));
                 TIMED(9, (k_replay<<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, d_right, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_live, d_nlive)));
                 TIMED(10, (k_left<<<c->smCount * 8, 256, 0, st>>>(d_live, d_nlive, t->d_cls, q->d_cls, t->d_seq, q->d_seq, c->d_sc, P, d_cand, candCap, d_cnt)));
+            } else if (coopExtend) {
+                int bits = 1; while (bits < 32 && (nh >> bits)) bits++;          /* bucket sizes are <= nh */
+                size_t tbo = tmpBytes;
+                CUDA_TRY(cudaMemsetAsync(d_next, 0, 4, st));
+                TIMED(11, (k_bucket_sizes<<<(nbuckets + 255) / 256, 256, 0, st>>>(d_bstart, nbuckets, d_bcnt, d_bid)));
+                TIMED(11, cub::DeviceRadixSort::SortPairsDescending(d_tmp, tbo, d_bcnt, d_bcnt2, d_bid, d_border, nbuckets, 0, bits, st));
+                TIMED(7, (k_extend2<<<c->smCount * 4, 256, 0, st>>>(valsB, d_bstart, d_border, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
+                                                                     c->d_sc, P, d_E, d_cand, candCap, d_cnt, d_next)));
             } else if (c->sc.numClasses <= 16)
                 TIMED(7, (k_extend<true><<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
                                                                c->d_sc, P, d_E, d_cand, candCap, d_cnt)));
@@ -493,9 +552,11 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
         b0 = b1;
     }
     CUDA_TRY(cudaEventRecord(evEnd, st));
+    WMARK();                                            /* [2] chunk loop enqueued */
     search_counters hc;
     CUDA_TRY(cudaMemcpyAsync(&hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    WMARK();                                            /* [3] device work finished */
     if (hc.ncand > candCap) {
         lzb_fail("%llu HSP candidates exceed the %u-entry result buffer; raise the threshold (--hspthresh)", hc.ncand, candCap);
         goto cleanup_fail;
@@ -540,6 +601,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             g->pos1 = r.pos1; g->pos2 = r.pos2; g->length = r.length; g->s = sim; g->id = prm->strandId; g->scoreCov = r.length;
         }
         *segs = out; *nsegs = m;
+        WMARK();                                        /* [4] candidates copied back, entropy, ordering */
         if (stats) {
             stats->wordsInQuery = hc.words; stats->rawSeedHits = totalHits; stats->extensions = hc.extensions;
             stats->bpExtended = hc.bpExtended; stats->hsps = m;
@@ -553,11 +615,17 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
     cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
     cudaFree(d_cand); cudaFree(d_tmp); cudaFree(d_right); cudaFree(d_live); cudaFree(d_nlive);
+    cudaFree(d_bcnt); cudaFree(d_bcnt2); cudaFree(d_bid); cudaFree(d_border); cudaFree(d_next);
+    WMARK();                                            /* [5] buffers freed */
+    if (wtrace) fprintf(stderr, "[seed trace] plan=%.4f alloc=%.4f enqueue=%.4f device_wait=%.4f post=%.4f free=%.4f total=%.4f s (chunks=%llu hits=%llu cand=%llu)\n",
+                        wt[0], wt[1] - wt[0], wt[2] - wt[1], wt[3] - wt[2], wt[4] - wt[3], wt[5] - wt[4], wt[5],
+                        (unsigned long long)chunks, (unsigned long long)totalHits, (unsigned long long)hc.ncand);
     return 0;
 cleanup_fail:
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
     cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
     cudaFree(d_cand); cudaFree(d_tmp); cudaFree(d_right); cudaFree(d_live); cudaFree(d_nlive);
+    cudaFree(d_bcnt); cudaFree(d_bcnt2); cudaFree(d_bid); cudaFree(d_border); cudaFree(d_next);
     return -1;
 }

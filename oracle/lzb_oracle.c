@@ -720,7 +720,7 @@ static s32 one_sided(genv* G, int rev, u32 a1, u32 a2, u32 M, u32 N,
             Rw.D[wcol & Rw.msk] = Rw.C[wcol & Rw.msk] = NEG_INF; RY++;
         }
     }
-    G->st.dpCells += cells; G->st.dpRows += row;
+    G->st.dpCells += cells; G->st.dpCellsComputed += cells; G->st.dpRows += row;
     /* traceback :3847-3859 */
     u32 r = end1, cc = end2; u8 prevOp = 0, op;
     *oend1 = end1; *oend2 = end2;
