@@ -51,6 +51,8 @@ extern "C" void lzb_close(lzb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     lzb_gapped_cache_free(c);
+    lzb_seed_scratch_free(c);
+    for (int i = 0; i < 4; i++) { cudaFree(c->qpool[i].seq); cudaFree(c->qpool[i].cls); }
     cudaStreamDestroy(c->stream);
     cudaFree(c->d_sc);
     free(c->hostSub); free(c->hostMsub);
@@ -112,11 +114,17 @@ __global__ void k_classify(const uint4* __restrict__ in, uint4* __restrict__ out
 }
 
 /* copies len bytes (+ NUL + zero pad to 16) to the device and derives the class-code copy */
-int lzb_upload_classes(lzb_ctx* c, const u8* h_seq, u32 len, u8** d_seq, u8** d_cls) {
+int lzb_upload_classes(lzb_ctx* c, const u8* h_seq, u32 len, u8** d_seq, u8** d_cls, size_t* cap) {
     if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
     size_t padded = (((size_t)len + 1 + 15) / 16) * 16 + 16;
-    CUDA_TRY(cudaMalloc(d_seq, padded));
-    CUDA_TRY(cudaMalloc(d_cls, padded));
+    int best = -1;                                       /* smallest pooled pair that is large enough */
+    for (int i = 0; i < 4; i++) if (c->qpool[i].seq && c->qpool[i].cap >= padded && (best < 0 || c->qpool[i].cap < c->qpool[best].cap)) best = i;
+    if (best >= 0) { *d_seq = c->qpool[best].seq; *d_cls = c->qpool[best].cls; *cap = c->qpool[best].cap; c->qpool[best].seq = c->qpool[best].cls = NULL; c->qpool[best].cap = 0; }
+    else {
+        CUDA_TRY(cudaMalloc(d_seq, padded));
+        CUDA_TRY(cudaMalloc(d_cls, padded));
+        *cap = padded;
+    }
     CUDA_TRY(cudaMemsetAsync(*d_seq, 0, padded, c->stream));
     CUDA_TRY(cudaMemcpyAsync(*d_seq, h_seq, len, cudaMemcpyHostToDevice, c->stream));
     size_t n16 = padded / 16;
@@ -135,7 +143,7 @@ extern "C" lzb_query* lzb_query_load(lzb_ctx* c, const uint8_t* seq2, uint32_t l
     q->ctx = c; q->len = len2;
     q->h_seq = (u8*)malloc((size_t)len2 + 1); memcpy(q->h_seq, seq2, len2); q->h_seq[len2] = 0;
     const double w1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
-    if (lzb_upload_classes(c, q->h_seq, len2, &q->d_seq, &q->d_cls)) { free(q->h_seq); free(q); return NULL; }
+    if (lzb_upload_classes(c, q->h_seq, len2, &q->d_seq, &q->d_cls, &q->cap)) { free(q->h_seq); free(q); return NULL; }
     if (wtrace) fprintf(stderr, "[query load] host copy=%.4f upload+classify enqueue=%.4f s (%u bp)\n", w1,
                         std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count() - w1, len2);
     return q;
@@ -144,6 +152,15 @@ extern "C" lzb_query* lzb_query_load(lzb_ctx* c, const uint8_t* seq2, uint32_t l
 extern "C" void lzb_query_free(lzb_query* q) {
     if (!q) return;
     cudaSetDevice(q->ctx->device);
-    cudaStreamSynchronize(q->ctx->stream);
-    cudaFree(q->d_seq); cudaFree(q->d_cls); free(q->h_seq); free(q);
+    lzb_ctx* c = q->ctx;
+    cudaStreamSynchronize(c->stream);
+    int slot = -1;
+    for (int i = 0; i < 4 && slot < 0; i++) if (!c->qpool[i].seq) slot = i;
+    if (slot < 0) {                                      /* pool full: evict the smallest if this pair is larger */
+        int sm = 0; for (int i = 1; i < 4; i++) if (c->qpool[i].cap < c->qpool[sm].cap) sm = i;
+        if (c->qpool[sm].cap < q->cap) { cudaFree(c->qpool[sm].seq); cudaFree(c->qpool[sm].cls); slot = sm; }
+    }
+    if (slot >= 0) { c->qpool[slot].seq = q->d_seq; c->qpool[slot].cls = q->d_cls; c->qpool[slot].cap = q->cap; }
+    else { cudaFree(q->d_seq); cudaFree(q->d_cls); }
+    free(q->h_seq); free(q);
 }

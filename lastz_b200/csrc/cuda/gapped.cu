@@ -732,7 +732,7 @@ static segref dev_ref(gx& G, segref r) { segref o = NOSEG; if (r.al >= 0) { o.al
 
 /* one speculation lane: a stream, the two one-sided DPs of one anchor, their buffers */
 struct gx_lane {
-    cudaStream_t stream; cudaEvent_t evA, evB;
+    cudaStream_t stream; cudaEvent_t evA, evB; double launchedAt;
     dp_job* h_jobs;                      /* pinned, 2 entries */
     dp_job* d_jobs;
     u32* dbg[2];
@@ -746,7 +746,33 @@ struct gx_lane {
 struct gx_cache {                        /* lives in the context: lanes are expensive to allocate */
     std::vector<gx_lane> lanes; u32 tbBytes;
     dseg* d_segs; size_t segsCap, segsUploaded;
+    /* uploads go through mapped pinned staging + a copy KERNEL: an H2D copy on a stream that shares a
+     * hardware queue with a running DP kernel waits for that kernel (engine switch inside one channel) */
+    u32* h_stage; u32* d_stage; size_t stageWords; cudaStream_t upStream;
+    std::vector<char*> epochChunks; size_t epochUsed;        /* bump pool for the per-epoch alignment tables */
 };
+#define GX_STAGE_WORDS (16u << 20)                          /* 64 MB */
+#define GX_EPOCH_CHUNK ((size_t)16 << 20)
+
+__global__ void k_upload_words(u32* __restrict__ dst, const u32* __restrict__ src, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+/* host words -> device through the staging buffer; returns with the data in place */
+static int gx_upload(lzb_ctx* c, gx_cache* gc, void* dst, const void* src, size_t bytes) {
+    const u32* w = (const u32*)src; u32* d = (u32*)dst; size_t n = (bytes + 3) / 4;
+    while (n) {
+        size_t k = n < gc->stageWords ? n : gc->stageWords;
+        memcpy(gc->h_stage, w, k * 4);
+        int blocks = (int)((k + 255) / 256); if (blocks > 64) blocks = 64;
+        k_upload_words<<<blocks, 256, 0, gc->upStream>>>(d, gc->d_stage, k);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(gc->upStream));
+        w += k; d += k; n -= k;
+    }
+    return 0;
+}
 
 static void free_lane(gx_lane& ln) {
     cudaStreamDestroy(ln.stream); cudaEventDestroy(ln.evA); cudaEventDestroy(ln.evB);
@@ -758,7 +784,9 @@ void lzb_gapped_cache_free(lzb_ctx* c) {
     gx_cache* gc = (gx_cache*)c->gappedCache;
     if (!gc) return;
     for (auto& ln : gc->lanes) free_lane(ln);
-    cudaFree(gc->d_segs);
+    cudaFree(gc->d_segs); cudaFreeHost(gc->h_stage);
+    if (gc->upStream != c->stream) cudaStreamDestroy(gc->upStream);
+    for (char* ch : gc->epochChunks) cudaFree(ch);
     delete gc; c->gappedCache = NULL;
 }
 
@@ -847,7 +875,21 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     const char* cenv = getenv("LZB_RING"); if (cenv) ring0 = (u32)atoi(cenv);
     gx_cache* gc = (gx_cache*)c->gappedCache;
     if (gc && gc->tbBytes != P->tracebackBytes) { lzb_gapped_cache_free(c); gc = NULL; }
-    if (!gc) { gc = new gx_cache(); gc->tbBytes = P->tracebackBytes; gc->d_segs = NULL; gc->segsCap = 0; gc->segsUploaded = 0; c->gappedCache = gc; }
+    if (!gc) {
+        gc = new gx_cache(); gc->tbBytes = P->tracebackBytes; gc->d_segs = NULL; gc->segsCap = 0; gc->segsUploaded = 0;
+        gc->h_stage = gc->d_stage = NULL; gc->stageWords = GX_STAGE_WORDS; gc->epochUsed = 0;
+        c->gappedCache = gc;
+        gc->upStream = c->stream;
+        if (getenv("LZB_UPLOAD_PRIO") && atoi(getenv("LZB_UPLOAD_PRIO"))) {   /* experiment: a high-priority stream of its own for the table uploads */
+            int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CUDA_TRY(cudaStreamCreateWithPriority(&gc->upStream, cudaStreamNonBlocking, hi));
+        }
+        CUDA_TRY(cudaHostAlloc(&gc->h_stage, (size_t)gc->stageWords * 4, cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&gc->d_stage, gc->h_stage, 0));
+        gc->segsCap = 16u << 20;                            /* 320 MB up front: regrowing has to drain every lane */
+        CUDA_TRY(cudaMalloc(&gc->d_segs, gc->segsCap * sizeof(dseg)));
+    }
+    gc->epochUsed = 0;
     while ((int)gc->lanes.size() < W) {
         gx_lane ln;
         if (make_lane(ln, P->tracebackBytes, tbLen)) return -1;
@@ -872,6 +914,9 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     double pfSweep = 0, pfWait = 0, pfHarvest = 0, pfPush = 0, pfLaneBusy = 0, pfNbr = 0; u64 pfSweeps = 0, pfExamined = 0, pfNbrCalls = 0;
     u64 headAnchor = 0;
     auto now = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count(); };
+    /* an event recorded behind a DP kernel blocks whatever else shares that hardware queue until the kernel ends;
+     * LZB_LANE_EVENTS=0 times the DP launches by the host clock instead */
+    const bool laneEvents = !(getenv("LZB_LANE_EVENTS") && !atoi(getenv("LZB_LANE_EVENTS")));
     std::vector<spec_result> spec(n);
     for (auto& s : spec) s.have = false;
     std::vector<char> inflight(n, 0);
@@ -893,14 +938,13 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         if (G.hsegs.size() > gc->segsCap) {
             /* running kernels hold the old pointer: drain them first */
             for (auto& ln : gc->lanes) if (ln.busy) CUDA_TRY(cudaStreamSynchronize(ln.stream));
-            cudaFree(gc->d_segs); gc->segsCap = G.hsegs.size() * 2 + (1u << 20);
+            cudaFree(gc->d_segs); gc->segsCap = G.hsegs.size() * 2 + (16u << 20);
             CUDA_TRY(cudaMalloc(&gc->d_segs, gc->segsCap * sizeof(dseg)));
             gc->segsUploaded = 0;
         }
         if (G.hsegs.size() > gc->segsUploaded) {
-            CUDA_TRY(cudaMemcpyAsync(gc->d_segs + gc->segsUploaded, G.hsegs.data() + gc->segsUploaded,
-                                     (G.hsegs.size() - gc->segsUploaded) * sizeof(dseg), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (gx_upload(c, gc, gc->d_segs + gc->segsUploaded, G.hsegs.data() + gc->segsUploaded,
+                          (G.hsegs.size() - gc->segsUploaded) * sizeof(dseg))) return -1;
             gc->segsUploaded = G.hsegs.size();
         }
         for (size_t k = 0; k < G.committed.size(); k++) {
@@ -913,10 +957,18 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
          * keep reading the copy they were launched with; the copies are tiny and freed at the end */
         curAligns = NULL;
         if (!G.haligns.empty()) {
-            CUDA_TRY(cudaMalloc(&curAligns, G.haligns.size() * sizeof(dalign)));
-            alignEpochs.push_back(curAligns);
-            CUDA_TRY(cudaMemcpyAsync(curAligns, G.haligns.data(), G.haligns.size() * sizeof(dalign), cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            const size_t need = ((G.haligns.size() * sizeof(dalign) + 255) / 256) * 256;
+            if (need > GX_EPOCH_CHUNK) {                       /* enormous table: its own allocation, freed at the end of the call */
+                CUDA_TRY(cudaMalloc(&curAligns, need)); alignEpochs.push_back(curAligns);
+            } else {
+                const size_t chunk = gc->epochUsed / GX_EPOCH_CHUNK, off = gc->epochUsed % GX_EPOCH_CHUNK;
+                size_t at = gc->epochUsed;
+                if (off + need > GX_EPOCH_CHUNK) at = (chunk + 1) * GX_EPOCH_CHUNK;   /* does not fit the rest of this chunk */
+                while (gc->epochChunks.size() <= at / GX_EPOCH_CHUNK) { char* ch = NULL; CUDA_TRY(cudaMalloc(&ch, GX_EPOCH_CHUNK)); gc->epochChunks.push_back(ch); }
+                curAligns = (dalign*)(gc->epochChunks[at / GX_EPOCH_CHUNK] + at % GX_EPOCH_CHUNK);
+                gc->epochUsed = at + need;
+            }
+            if (gx_upload(c, gc, curAligns, G.haligns.data(), G.haligns.size() * sizeof(dalign))) return -1;
         }
         return 0;
     };
@@ -957,7 +1009,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                 J.dbg = ln.dbg[side]; J.dbgCap = DBG_ROWS;
             }
         }
-        CUDA_TRY(cudaEventRecord(ln.evA, ln.stream));
+        if (laneEvents) CUDA_TRY(cudaEventRecord(ln.evA, ln.stream)); else ln.launchedAt = now();
         if (ln.mode == 0)
             k_ydrop_mw<8, 4><<<2, 128, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
         else if (ln.mode == 1)
@@ -974,7 +1026,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         }
         c->launches++;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(ln.evB, ln.stream));
+        if (laneEvents) CUDA_TRY(cudaEventRecord(ln.evB, ln.stream));
         return 0;
     };
 
@@ -1004,7 +1056,9 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
 
     /* a lane's stream has drained: collect the result, or rerun a side that outgrew a buffer */
     auto harvest = [&](gx_lane& ln) -> int {
-        float ms = 0; cudaEventElapsedTime(&ms, ln.evA, ln.evB); G.st.kernelSeconds[0] += ms / 1e3;
+        float ms = 0;
+        if (laneEvents) cudaEventElapsedTime(&ms, ln.evA, ln.evB); else ms = (float)((now() - ln.launchedAt) * 1e3);   /* host clock: launch to harvest */
+        G.st.kernelSeconds[0] += ms / 1e3;
         spec_result& sr = spec[ln.anchor];
         int redo = -2;                                       /* -2 none, -1 both, 0/1 one side */
         for (int side = 0; side < 2; side++) {
@@ -1068,9 +1122,43 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
      * an estimate was too small and two such ranges do overlap, the whole call is redone in strict
      * order (`strict`), so the result always equals the sequential algorithm's. */
     std::vector<u8> fin(n, 0);                               /* 1 = skipped / committed / dropped */
+    /* the anchor POINTS (commit overwrites al[i].pos1/pos2 with the alignment's start) and the anchors by
+     * seq-1 position: when an alignment is committed the anchors lying on it are retired there and then
+     * (msp_left_right's d == 0 test, gapped_extend.c:4008), instead of re-testing thousands of anchors
+     * against every alignment on every sweep -- that was 1.2-2.2 s of host time per 50 Mbp strand */
+    std::vector<u32> apos1(n), apos2(n);
+    for (u64 i = 0; i < n; i++) { apos1[i] = G.al[i].pos1; apos2[i] = G.al[i].pos2; }
+    std::vector<u32> byPos(n);
+    for (u64 i = 0; i < n; i++) byPos[i] = (u32)i;
+    std::sort(byPos.begin(), byPos.end(), [&](u32 a, u32 b) { return apos1[a] != apos1[b] ? apos1[a] < apos1[b] : a < b; });
+    std::vector<int> blockedBy(n, -1);                      /* the running earlier extension a waiting anchor clashed with ... */
+    std::vector<u32> blockedAt(n, 0);                       /* ... and the number of commits at that time */
     std::vector<u64> dpLo(n + 1, 0), dpHi(n + 1, 0);        /* rows examined by a committed anchor's DPs */
     u64 hd = 0; bool violation = false;
     u64 maxRows = 0;
+    /* retire the anchors that lie on alignment `ai` (index into G.al; n = the trivial self alignment) */
+    auto retire_covered = [&](int ai) {
+        galn& x = G.al[ai];
+        const int ns = (int)x.segs.size();
+        if (ns == 0) return;
+        size_t lo = std::lower_bound(byPos.begin(), byPos.end(), x.pos1, [&](u32 a, u32 v) { return apos1[a] < v; }) - byPos.begin();
+        for (size_t z = lo; z < byPos.size() && apos1[byPos[z]] <= x.end1; z++) {
+            const u32 j = byPos[z];
+            if (fin[j] || (int)j == ai) continue;
+            const u32 pos1 = apos1[j], pos2 = apos2[j];
+            int k = 0, hi2 = ns;                             /* first segment whose e1 >= pos1 */
+            while (k < hi2) { int mid = (k + hi2) >> 1; if (x.segs[mid].e1 < pos1) k = mid + 1; else hi2 = mid; }
+            if (k == ns) continue;
+            const hseg& bp = x.segs[k]; s32 d;
+            if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - pos2) + (s32)(pos1 - bp.b1); else d = (s32)(bp.b2 - pos2);
+            if (d != 0) continue;
+            /* on an alignment committed EARLIER in the order: skipped for good (:1335); on one committed
+             * ahead of its turn: the estimates were wrong */
+            if (ai != (int)n && (u64)ai > j) { violation = true; return; }
+            fin[j] = 1; spec[j].have = false; spec[j].L.ops.clear(); spec[j].R.ops.clear();
+        }
+    };
+    if (G.obi == (int)n) retire_covered((int)n);
 
     /* commit anchor i from its finished, validated result */
     auto commit_anchor = [&](u64 i) {
@@ -1129,12 +1217,13 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         list_insert(G, (int)i);
         m.devIx = (int)G.committed.size(); G.committed.push_back((int)i);
         tablesDirty = true;
+        retire_covered((int)i);
     };
 
     /* an earlier, still unresolved anchor: [lo,hi] = rows its extension covers (estimated while in
      * flight, exact once finished) -- nothing that overlaps it may START; [clo,chi] = rows that it, or an
      * anchor waiting on it, could still come to cover -- nothing that overlaps it may COMMIT */
-    struct pend { u64 lo, hi, clo, chi; };
+    struct pend { u64 lo, hi, clo, chi; int owner; };
     auto widen = [](u64 v, u64 by, bool down) -> u64 { return down ? (v > by ? v - by : 0) : v + by; };
     while (hd < n && !violation) {
         while (hd < n && fin[hd]) hd++;
@@ -1153,17 +1242,19 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             galn& y = G.al[j];
             const s64 dy = (s64)y.pos1 - (s64)y.pos2;
             int coverer = -1;
-            if (!inflight[j] || spec[j].have) {
+            /* neighbours (msp_left_right) are needed only to validate a finished extension or to start one */
+            auto fresh_neighbours = [&]() -> bool {
                 const double n0 = prof ? now() : 0;
                 const bool open = anchor_neighbours(G, y, &coverer);
                 if (prof) { pfNbr += now() - n0; pfNbrCalls++; }
                 if (!open) {
-                    /* on an alignment committed EARLIER in the order: skipped for good (:1335) */
-                    if (coverer >= 0 && (u64)coverer > j && coverer != (int)n) { violation = true; break; }
+                    if (coverer >= 0 && (u64)coverer > j && coverer != (int)n) { violation = true; return false; }
                     fin[j] = 1; spec[j].have = false; spec[j].L.ops.clear(); spec[j].R.ops.clear(); progressed = true;
-                    continue;
+                    return false;
                 }
-            }
+                return true;
+            };
+            if (spec[j].have && !fresh_neighbours()) { if (violation) break; continue; }
             if (spec[j].have) {
                 spec_result& sr = spec[j];
                 const u64 lo = (u64)y.pos1 + 1 >= (u64)sr.L.rows + 2 ? (u64)y.pos1 + 1 - sr.L.rows - 2 : 0;
@@ -1187,9 +1278,10 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                         for (int ci : G.committed) if ((u64)ci > j && ci != (int)n && !(dpHi[ci] < lo || dpLo[ci] > hi)) { violation = true; break; }
                         if (violation) break;
                         commit_anchor(j); progressed = true;
+                        if (violation) break;
                         continue;
                     }
-                    unresolved.push_back(pend{ lo, hi, widen(lo, 2 * est, true), widen(hi, 2 * est, false) });
+                    unresolved.push_back(pend{ lo, hi, widen(lo, 2 * est, true), widen(hi, 2 * est, false), (int)j });
                     continue;
                 }
             }
@@ -1197,18 +1289,25 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                 gx_lane* ln = NULL;
                 for (int z = 0; z < W; z++) if (gc->lanes[z].busy && gc->lanes[z].anchor == j) ln = &gc->lanes[z];
                 const u64 lo = ln ? ln->estLo : 0, hi = ln ? ln->estHi : ~0ull;
-                unresolved.push_back(pend{ lo, hi, widen(lo, 2 * est, true), widen(hi, 2 * est, false) });
+                unresolved.push_back(pend{ lo, hi, widen(lo, 2 * est, true), widen(hi, 2 * est, false), (int)j });
                 continue;
             }
             /* not started: may start if its estimated rows clear every earlier extension */
+            if (blockedBy[j] >= 0 && inflight[blockedBy[j]] && !spec[blockedBy[j]].have && blockedAt[j] == (u32)G.committed.size()) {
+                /* same running extension (its estimated rows are fixed at launch), same committed set
+                 * (so this anchor's estimate cannot have shrunk): still clashing */
+                continue;
+            }
             std::pair<u64, u64> rg = est_region(y, est);
             bool clash = false;
-            for (auto& u : unresolved) if (!(rg.second < u.lo || rg.first > u.hi)) { clash = true; break; }
+            for (auto& u : unresolved) if (!(rg.second < u.lo || rg.first > u.hi)) { clash = true; blockedBy[j] = u.owner; blockedAt[j] = (u32)G.committed.size(); break; }
             if (strict && !unresolved.empty()) clash = true;
             if (clash) continue;                             /* waits on that extension; its commit window already covers this anchor */
+            blockedBy[j] = -1;
+            if (!fresh_neighbours()) { if (violation) break; continue; }
             if (freeLanes == 0) {
                 /* could start but no lane is free: hold later commits off its rows, and stop looking */
-                unresolved.push_back(pend{ 1, 0, rg.first, rg.second });
+                unresolved.push_back(pend{ 1, 0, rg.first, rg.second, (int)j });
                 if (++starved >= 8) break;
                 continue;
             }
@@ -1217,7 +1316,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             if (start_anchor(*fl, j)) return -1;
             fl->estLo = rg.first; fl->estHi = rg.second;
             freeLanes--; if (j != hd) G.st.speculated++;
-            unresolved.push_back(pend{ rg.first, rg.second, widen(rg.first, 2 * est, true), widen(rg.second, 2 * est, false) });
+            unresolved.push_back(pend{ rg.first, rg.second, widen(rg.first, 2 * est, true), widen(rg.second, 2 * est, false), (int)j });
         }
         if (prof) pfSweep += now() - sw0;
         if (violation) break;

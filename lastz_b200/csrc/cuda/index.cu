@@ -53,7 +53,8 @@ extern "C" lzb_target* lzb_target_build(lzb_ctx* c, const uint8_t* seq1, uint32_
     t->ctx = c; t->len = len1; t->start = start; t->end = end; t->step = step;
     t->wordBits = seed->weight; t->seedLength = seed->length;
     t->h_seq = (u8*)malloc((size_t)len1 + 1); memcpy(t->h_seq, seq1, len1); t->h_seq[len1] = 0;
-    if (lzb_upload_classes(c, t->h_seq, len1, &t->d_seq, &t->d_cls)) return NULL;
+    size_t capUnused = 0;
+    if (lzb_upload_classes(c, t->h_seq, len1, &t->d_seq, &t->d_cls, &capUnused)) return NULL;
 
     u64 nw = 1ull << seed->weight;
     CUDA_TRYP(cudaMalloc(&t->d_off, (nw + 2) * 4));

@@ -53,9 +53,13 @@ struct lzb_ctx {
     lzb_scoring_dev* d_sc;                   /* device copy */
     u64 launches;                            /* kernels launched by this context */
     void* gappedCache;                       /* gapped.cu: speculation lanes kept across calls */
+    void* seedScratch;                       /* seed_search.cu: device scratch kept across calls */
+    struct { u8* seq; u8* cls; size_t cap; } qpool[4];   /* device buffers of freed queries, reused by the next load
+                                                (cudaFree is a device-wide synchronisation: 0.1 s with 32 lanes' buffers live) */
 };
 
 void lzb_gapped_cache_free(lzb_ctx*);        /* gapped.cu */
+void lzb_seed_scratch_free(lzb_ctx*);        /* seed_search.cu */
 
 struct lzb_target {
     lzb_ctx* ctx;
@@ -72,7 +76,7 @@ struct lzb_target {
 struct lzb_query {
     lzb_ctx* ctx;
     u8* h_seq;  u32 len;
-    u8* d_seq;  u8* d_cls;
+    u8* d_seq;  u8* d_cls;  size_t cap;
 };
 
 /* device helpers */
@@ -86,6 +90,6 @@ static inline void seed_to_dev(seed_dev* d, const lzb_seed* s) {
     for (int i = 0; i < s->numParts; i++) { d->shift[i] = s->shift[i]; d->mask[i] = s->mask[i]; }
 }
 
-int  lzb_upload_classes(lzb_ctx*, const u8* h_seq, u32 len, u8** d_seq, u8** d_cls);
+int  lzb_upload_classes(lzb_ctx*, const u8* h_seq, u32 len, u8** d_seq, u8** d_cls, size_t* cap);
 
 #endif

@@ -393,6 +393,31 @@ static u32 host_word_at(const u8* v, u32 endPos, const lzb_seed* sd, const int8_
 
 struct ev_pair { cudaEvent_t a, b; int which; };
 
+/* Device scratch of the seed stage, kept in the context across calls: at 50 Mbp x 50 Mbp the hit buffers are
+ * 3.5 GB and cudaMalloc + cudaFree of them cost 0.1-0.7 s of host time per call (LZB_SEED_TRACE) against
+ * 0.34 s of device work.  A buffer only ever grows. */
+#define SEED_SCRATCH_SLOTS 24
+struct seed_scratch { void* p[SEED_SCRATCH_SLOTS]; size_t cap[SEED_SCRATCH_SLOTS]; };
+static int scratch_get(lzb_ctx* c, int slot, size_t bytes, void** out) {
+    if (!c->seedScratch) c->seedScratch = calloc(1, sizeof(seed_scratch));
+    seed_scratch* sc = (seed_scratch*)c->seedScratch;
+    if (bytes == 0) bytes = 16;
+    if (sc->cap[slot] < bytes) {
+        if (sc->p[slot]) { cudaStreamSynchronize(c->stream); cudaFree(sc->p[slot]); sc->p[slot] = NULL; sc->cap[slot] = 0; }
+        CUDA_TRY(cudaMalloc(&sc->p[slot], bytes));
+        sc->cap[slot] = bytes;
+    }
+    *out = sc->p[slot];
+    return 0;
+}
+#define SCRATCH(slot_, var_, size_) do { if (scratch_get(c, (slot_), (size_), (void**)&var_)) return -1; } while (0)
+void lzb_seed_scratch_free(lzb_ctx* c) {
+    seed_scratch* sc = (seed_scratch*)c->seedScratch;
+    if (!sc) return;
+    for (int i = 0; i < SEED_SCRATCH_SLOTS; i++) cudaFree(sc->p[i]);
+    free(sc); c->seedScratch = NULL;
+}
+
 extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed* seed,
                                    const int8_t ctb[256], const lzb_seed_params* prm,
                                    lzb_segment** segs, uint64_t* nsegs, lzb_seed_stats* stats) {
@@ -439,12 +464,12 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     cudaEvent_t evBegin, evMid, evMid2, evEnd;       /* device time = [begin,mid] + [mid2,end]; planning + cudaMalloc sit between */
     CUDA_TRY(cudaEventCreate(&evBegin)); CUDA_TRY(cudaEventCreate(&evEnd));
     CUDA_TRY(cudaEventCreate(&evMid)); CUDA_TRY(cudaEventCreate(&evMid2));
-    CUDA_TRY(cudaMalloc(&d_qword, (size_t)n * 4 + 16));
-    CUDA_TRY(cudaMalloc(&d_flips, flips.size() * 4));
-    CUDA_TRY(cudaMalloc(&d_blkcnt, (size_t)nblk * 8));
-    CUDA_TRY(cudaMalloc(&d_cnt, sizeof(search_counters)));
-    CUDA_TRY(cudaMalloc(&d_E, (size_t)nbuckets * 4));
-    CUDA_TRY(cudaMalloc(&d_bstart, ((size_t)nbuckets + 2) * 4));
+    SCRATCH(0, d_qword, (size_t)n * 4 + 16);
+    SCRATCH(1, d_flips, flips.size() * 4);
+    SCRATCH(2, d_blkcnt, (size_t)nblk * 8);
+    SCRATCH(3, d_cnt, sizeof(search_counters));
+    SCRATCH(4, d_E, (size_t)nbuckets * 4);
+    SCRATCH(5, d_bstart, ((size_t)nbuckets + 2) * 4);
     CUDA_TRY(cudaMemcpyAsync(d_flips, flips.data(), flips.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(search_counters), st));
     CUDA_TRY(cudaMemsetAsync(d_E, 0, (size_t)nbuckets * 4, st));        /* empty_diag_hash diag_hash.c:125 */
@@ -478,10 +503,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
 
     u32 *d_slotcnt = NULL, *d_slotoff = NULL, *keysA = NULL, *keysB = NULL; u64 *valsA = NULL, *valsB = NULL;
     cand_rec* d_cand = NULL; void* d_tmp = NULL; size_t tmpBytes = 0, tmpScan = 0;
-    CUDA_TRY(cudaMalloc(&d_slotcnt, (slotCap + 2) * 4)); CUDA_TRY(cudaMalloc(&d_slotoff, (slotCap + 2) * 4));
-    CUDA_TRY(cudaMalloc(&keysA, hitCap * 4)); CUDA_TRY(cudaMalloc(&keysB, hitCap * 4));
-    CUDA_TRY(cudaMalloc(&valsA, hitCap * 8)); CUDA_TRY(cudaMalloc(&valsB, hitCap * 8));
-    CUDA_TRY(cudaMalloc(&d_cand, (size_t)candCap * sizeof(cand_rec)));
+    SCRATCH(6, d_slotcnt, (slotCap + 2) * 4); SCRATCH(7, d_slotoff, (slotCap + 2) * 4);
+    SCRATCH(8, keysA, hitCap * 4); SCRATCH(9, keysB, hitCap * 4);
+    SCRATCH(10, valsA, hitCap * 8); SCRATCH(11, valsB, hitCap * 8);
+    SCRATCH(12, d_cand, (size_t)candCap * sizeof(cand_rec));
     /* the three-kernel extension (xdrop_split.cuh) measured SLOWER than the fused kernel (0.70 s vs 0.62 s
      * at 50 Mbp x 50 Mbp: the extra passes over the hit records cost more than the lockstep idling they
      * remove), so it is opt-in: LZB_SPLIT_EXTEND=1.  Kept because it bounds the work on long repeats. */
@@ -492,22 +517,22 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
                             !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
     u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
     if (coopExtend) {
-        CUDA_TRY(cudaMalloc(&d_bcnt, (size_t)nbuckets * 4)); CUDA_TRY(cudaMalloc(&d_bcnt2, (size_t)nbuckets * 4));
-        CUDA_TRY(cudaMalloc(&d_bid, (size_t)nbuckets * 4)); CUDA_TRY(cudaMalloc(&d_border, (size_t)nbuckets * 4));
-        CUDA_TRY(cudaMalloc(&d_next, 4));
+        SCRATCH(13, d_bcnt, (size_t)nbuckets * 4); SCRATCH(14, d_bcnt2, (size_t)nbuckets * 4);
+        SCRATCH(15, d_bid, (size_t)nbuckets * 4); SCRATCH(16, d_border, (size_t)nbuckets * 4);
+        SCRATCH(17, d_next, 4);
         CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(NULL, tmpOrder, d_bcnt, d_bcnt2, d_bid, d_border, nbuckets, 0, 32, st));
     }
     right_rec* d_right = NULL; live_rec* d_live = NULL; unsigned long long* d_nlive = NULL;
     if (splitExtend) {
-        CUDA_TRY(cudaMalloc(&d_right, hitCap * sizeof(right_rec)));
-        CUDA_TRY(cudaMalloc(&d_live, hitCap * sizeof(live_rec)));
-        CUDA_TRY(cudaMalloc(&d_nlive, 8));
+        SCRATCH(18, d_right, hitCap * sizeof(right_rec));
+        SCRATCH(19, d_live, hitCap * sizeof(live_rec));
+        SCRATCH(20, d_nlive, 8);
     }
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(NULL, tmpBytes, keysA, keysB, valsA, valsB, hitCap, 0, hashBits, st));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmpScan, d_slotcnt, d_slotoff, slotCap + 1, st));
     if (tmpScan > tmpBytes) tmpBytes = tmpScan;
     if (tmpOrder > tmpBytes) tmpBytes = tmpOrder;
-    CUDA_TRY(cudaMalloc(&d_tmp, tmpBytes));
+    SCRATCH(21, d_tmp, tmpBytes);
 
     /* chunk loop */
     WMARK();                                            /* [1] hit/slot/candidate buffers allocated */
@@ -564,24 +589,36 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     {
         std::vector<cand_rec> cand(hc.ncand);
         if (hc.ncand) CUDA_TRY(cudaMemcpy(cand.data(), d_cand, (size_t)hc.ncand * sizeof(cand_rec), cudaMemcpyDeviceToHost));
-        /* discovery order = (query position, variant index, target position descending) */
-        struct keyed { u32 hit2; u32 variant; u32 hit1; u32 ix; };
-        std::vector<keyed> order(cand.size());
-        for (size_t i = 0; i < cand.size(); i++) {
-            u32 qw = host_word_at(q->h_seq, cand[i].hit2, seed, ctb), tw = host_word_at(t->h_seq, cand[i].hit1, seed, ctb);
-            u32 x = qw ^ tw, v = 0;
-            for (; v < flips.size(); v++) if (flips[v] == x) break;
-            order[i] = { cand[i].hit2, v, cand[i].hit1, (u32)i };
+        /* discovery order = (query position, variant index, target position descending).  Candidates
+         * that share a query position are rare, so: sort (hit2, index) as plain 64-bit keys, then order
+         * each run of equal hit2 by the seed variant that produced the hit (recomputed from the bytes) */
+        struct keyed { u32 variant; u32 hit1; u32 ix; };
+        std::vector<u64> order(cand.size());
+        for (size_t i = 0; i < cand.size(); i++) order[i] = ((u64)cand[i].hit2 << 32) | (u32)i;
+        std::sort(order.begin(), order.end());
+        for (size_t i = 0; i < order.size();) {
+            size_t j = i + 1;
+            while (j < order.size() && (order[j] >> 32) == (order[i] >> 32)) j++;
+            if (j - i > 1) {
+                std::vector<keyed> run(j - i);
+                for (size_t k = i; k < j; k++) {
+                    const cand_rec& r = cand[(u32)order[k]];
+                    u32 x = host_word_at(q->h_seq, r.hit2, seed, ctb) ^ host_word_at(t->h_seq, r.hit1, seed, ctb), v = 0;
+                    for (; v < flips.size(); v++) if (flips[v] == x) break;
+                    run[k - i] = { v, r.hit1, (u32)order[k] };
+                }
+                std::sort(run.begin(), run.end(), [](const keyed& a, const keyed& b) {
+                    if (a.variant != b.variant) return a.variant < b.variant;
+                    return a.hit1 > b.hit1;
+                });
+                for (size_t k = i; k < j; k++) order[k] = (order[k] & 0xFFFFFFFF00000000ull) | run[k - i].ix;
+            }
+            i = j;
         }
-        std::sort(order.begin(), order.end(), [](const keyed& a, const keyed& b) {
-            if (a.hit2 != b.hit2) return a.hit2 < b.hit2;
-            if (a.variant != b.variant) return a.variant < b.variant;
-            return a.hit1 > b.hit1;
-        });
         lzb_segment* out = (lzb_segment*)malloc((cand.size() + 1) * sizeof(lzb_segment));
         u64 m = 0;
         for (size_t i = 0; i < order.size(); i++) {
-            const cand_rec& r = cand[order[i].ix];
+            const cand_rec& r = cand[(u32)order[i]];
             s32 sim = r.score;
             if (!prm->plainHits && prm->gfExtend == LZB_GFEX_XDROP && prm->entropy &&
                 sim >= prm->hspThreshold && sim <= 3 * prm->hspThreshold) {
@@ -612,10 +649,6 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     }
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaEventDestroy(evBegin); cudaEventDestroy(evEnd); cudaEventDestroy(evMid); cudaEventDestroy(evMid2);
-    cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
-    cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
-    cudaFree(d_cand); cudaFree(d_tmp); cudaFree(d_right); cudaFree(d_live); cudaFree(d_nlive);
-    cudaFree(d_bcnt); cudaFree(d_bcnt2); cudaFree(d_bid); cudaFree(d_border); cudaFree(d_next);
     WMARK();                                            /* [5] buffers freed */
     if (wtrace) fprintf(stderr, "[seed trace] plan=%.4f alloc=%.4f enqueue=%.4f device_wait=%.4f post=%.4f free=%.4f total=%.4f s (chunks=%llu hits=%llu cand=%llu)\n",
                         wt[0], wt[1] - wt[0], wt[2] - wt[1], wt[3] - wt[2], wt[4] - wt[3], wt[5] - wt[4], wt[5],
@@ -623,9 +656,5 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     return 0;
 cleanup_fail:
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    cudaFree(d_qword); cudaFree(d_flips); cudaFree(d_blkcnt); cudaFree(d_cnt); cudaFree(d_E); cudaFree(d_bstart);
-    cudaFree(d_slotcnt); cudaFree(d_slotoff); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB);
-    cudaFree(d_cand); cudaFree(d_tmp); cudaFree(d_right); cudaFree(d_live); cudaFree(d_nlive);
-    cudaFree(d_bcnt); cudaFree(d_bcnt2); cudaFree(d_bid); cudaFree(d_border); cudaFree(d_next);
     return -1;
 }

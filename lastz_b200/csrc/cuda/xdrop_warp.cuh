@@ -80,31 +80,47 @@ W_DEV void xd_fetch8(const xd_env& e, u32 p1, u32 p2, u32 o, u32 n, s32 (&s)[8])
 }
 
 /* one lane's own scan state; the reference loop is
- *     while (cols < avail && run >= best - xDrop) { run += score(col); cols++; if (run > best) { best = run; bestLen = cols; } } */
-struct xd_scan { u32 avail, cols, bestLen; s32 run, best; bool going; };
+ *     while (cols < avail && run >= best - xDrop) { run += score(col); cols++; if (run > best) { best = run; bestLen = cols; } }
+ * A scan is CLOSED when cols == avail: a failed loop test closes it by setting avail = cols. */
+struct xd_scan { u32 avail, cols, bestLen; s32 run, best; };
 
-W_DEV void xd_scan_init(xd_scan& z, u32 avail) { z.avail = avail; z.cols = 0; z.bestLen = 0; z.run = 0; z.best = 0; z.going = true; }
-W_DEV bool xd_scan_open(const xd_scan& z) { return z.going && z.cols < z.avail; }
+W_DEV void xd_scan_init(xd_scan& z, u32 avail) { z.avail = avail; z.cols = 0; z.bestLen = 0; z.run = 0; z.best = 0; }
+W_DEV bool xd_scan_open(const xd_scan& z) { return z.cols < z.avail; }
 
-/* advance my scan by up to 8 columns */
-template <int DIR>
-W_DEV void xd_scan_step8(const xd_env& e, u32 p1, u32 p2, xd_scan& z) {
-    u32 n = z.avail - z.cols; if (n > 8) n = 8;
-    s32 s[8]; xd_fetch8<DIR>(e, p1, p2, z.cols, n, s);
+/* advance my (open) scan by up to 8 columns; written as straight-line selects so that the column
+ * step compiles to predicated instructions (the first version's nested ifs became a BSSY/BRA/BSYNC
+ * block per column: 16 instructions a column, profiles/r01_k_extend2_sass.txt) */
+template <int DIR, bool FULL>
+W_DEV void xd_scan_cols(const s32 (&s)[8], u32 n, s32 xDrop, xd_scan& z) {
+    /* d = best - run >= 0 is the whole recurrence: the loop test is d <= xDrop, a new best is d - score < 0.
+     * If column i is consumed so were all before it, hence cols = cols0 + i + 1 with a literal offset. */
+    s32 d = z.best - z.run, best = z.best; const u32 cols0 = z.cols; u32 cols = cols0, bestLen = z.bestLen;
+    bool alive = true;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        if (z.going && (u32)i < n) {
-            if (z.run >= z.best - e.xDrop) { z.run += s[i]; z.cols++; if (z.run > z.best) { z.best = z.run; z.bestLen = z.cols; } }
-            else z.going = false;
-        }
+        const bool p = alive && (FULL || (u32)i < n) && d <= xDrop;
+        d = p ? d - s[i] : d;
+        const bool q = p && d < 0;
+        best = q ? best - d : best;
+        d = w_max(d, 0);
+        cols = p ? cols0 + (u32)(i + 1) : cols;
+        bestLen = q ? cols0 + (u32)(i + 1) : bestLen;
+        alive = p;
     }
+    z.run = best - d; z.best = best; z.cols = cols; z.bestLen = bestLen;
+    if (!alive) z.avail = cols;                         /* the loop test failed (or the columns ran out): closed */
+}
+template <int DIR>
+W_DEV void xd_scan_step8(const xd_env& e, u32 p1, u32 p2, s32 xDrop, xd_scan& z) {
+    u32 n = z.avail - z.cols; if (n > 8) n = 8;
+    s32 s[8]; xd_fetch8<DIR>(e, p1, p2, z.cols, n, s);
+    if (n == 8) xd_scan_cols<DIR, true>(s, n, xDrop, z); else xd_scan_cols<DIR, false>(s, n, xDrop, z);
 }
 
 /* The warp finishes ONE scan; every lane passes the same state and receives the same result. */
 template <int DIR>
 W_DEV void xd_coop_finish(const xd_env& e, u32 lane, u32 p1, u32 p2, xd_scan& z) {
-    bool done = !z.going;
-    while (!done && z.cols < z.avail) {
+    while (z.cols < z.avail) {
         const u32 o = z.cols + lane * 8u;
         const u32 n = o < z.avail ? w_min(z.avail - o, 8u) : 0u;
         s32 ps[8]; xd_fetch8<DIR>(e, p1, p2, o, n, ps);
@@ -133,7 +149,7 @@ W_DEV void xd_coop_finish(const xd_env& e, u32 lane, u32 p1, u32 p2, xd_scan& z)
         }
         const u32 term = W_BALLOT(t < 8);
         u32 consumed = w_min(z.avail - z.cols, 256u);
-        if (term) { const u32 f = (u32)W_FFS(term) - 1u; consumed = f * 8u + W_SHFL(t, f); done = true; }
+        if (term) { const u32 f = (u32)W_FFS(term) - 1u; consumed = f * 8u + W_SHFL(t, f); }
         /* best run over the consumed columns: the first column that reaches the maximum */
         s32 bv = XD_NEG; u32 bi = 0xFFFFFFFFu;
 #pragma unroll
@@ -155,8 +171,8 @@ W_DEV void xd_coop_finish(const xd_env& e, u32 lane, u32 p1, u32 p2, xd_scan& z)
             z.run = W_SHFL(mine, gl >> 3);
         }
         z.cols += consumed;
+        if (term) z.avail = z.cols;                      /* closed by the loop test */
     }
-    if (done) z.going = false;
 }
 
 /* broadcast lane k's scan, finish it with the whole warp, hand it back */
@@ -165,15 +181,15 @@ W_DEV void xd_finish_lane(const xd_env& e, u32 lane, int k, u32 pos1, u32 pos2, 
     xd_scan z;
     const u32 p1 = W_SHFL(pos1, k), p2 = W_SHFL(pos2, k);
     z.avail = W_SHFL(mine.avail, k); z.cols = W_SHFL(mine.cols, k); z.bestLen = W_SHFL(mine.bestLen, k);
-    z.run = W_SHFL(mine.run, k); z.best = W_SHFL(mine.best, k); z.going = true;
+    z.run = W_SHFL(mine.run, k); z.best = W_SHFL(mine.best, k);
     xd_coop_finish<DIR>(e, lane, p1, p2, z);
-    if ((int)lane == k) { mine = z; mine.going = false; }
+    if ((int)lane == k) { mine = z; mine.avail = z.cols; }
 }
 
 /* all hits [b0,b1) of one bucket, in discovery order; E = diagEnd[bucket] in and out */
 W_DEV void xd_bucket(const xd_env& e, u32 lane, const u64* hits, u32 b0, u32 b1, u32& E,
                      unsigned long long& nExt, unsigned long long& nBp) {
-    const u32 L = e.L;
+    const u32 L = e.L; const s32 xDrop = e.xDrop;
     for (u32 base = b0; base < b1; base += 32) {
         const u32 idx = base + lane;
         const bool have = idx < b1;
@@ -190,26 +206,47 @@ W_DEV void xd_bucket(const xd_env& e, u32 lane, const u64* hits, u32 b0, u32 b1,
             const s64 lim = (s64)e.len2 + diag;
             const u32 rstop = ((s64)e.len1 <= lim) ? e.len1 : (u32)lim;
             xd_scan_init(rs, rstop > pos1 ? rstop - pos1 : 0);
-            while (xd_scan_open(rs) && rs.cols < XD_CAP) xd_scan_step8<1>(e, pos1, pos2, rs);
+            while (xd_scan_open(rs) && rs.cols < XD_CAP) xd_scan_step8<1>(e, pos1, pos2, xDrop, rs);
         }
         /* replay the test/update of process_for_simple_hit (:1113, :2785-2789) in discovery order */
         bool live = false; u32 myStop = 0;
-        while (active) {
-            const int k = W_FFS(active) - 1; active &= active - 1;
-            const u32 p2k = W_SHFL(pos2, k);
-            if (E > p2k - L) continue;                                 /* dead by now; its scan is never finished */
-            if (W_SHFL(xd_scan_open(rs) ? 1 : 0, k)) xd_finish_lane<1>(e, lane, k, pos1, pos2, rs);
-            const u32 ex = W_SHFL(pos2 + rs.cols, k);                  /* where the right scan stopped, in seq 2 */
-            if ((int)lane == k) { live = true; myStop = E; }
-            if (ex > E) E = ex;
+        if (!W_BALLOT(maybe && xd_scan_open(rs))) {
+            /* every extent is known.  Suppose all remaining candidates contribute their extent: the
+             * bucket as hit k meets it is E0 max'ed with the extents in front of k (a prefix maximum).
+             * Lanes in front of the first hit that comes out dead saw exactly the true bucket, so that
+             * hit IS dead; drop its extent and look again.  One trip per dead hit (usually none or one). */
+            const u32 ext = pos2 + rs.cols;                           /* where the right scan stopped, in seq 2 */
+            bool contrib = maybe;
+            for (;;) {
+                u32 pm = contrib ? ext : 0u;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const u32 t = W_SHFL_UP(pm, d); if (lane >= (u32)d) pm = w_max(pm, t); }
+                u32 before = W_SHFL_UP(pm, 1); if (lane == 0) before = 0u;
+                before = w_max(before, E);
+                const u32 dm = W_BALLOT(contrib && before > pos2 - L);
+                if (!dm) { live = contrib; myStop = before; E = w_max(E, W_SHFL(pm, 31)); break; }
+                if ((int)lane == W_FFS(dm) - 1) contrib = false;
+            }
+        } else {
+            /* some scan outlived XD_CAP columns: walk the hits one by one and let the warp finish a
+             * long scan only when its hit turns out to be live */
+            while (active) {
+                const int k = W_FFS(active) - 1; active &= active - 1;
+                const u32 p2k = W_SHFL(pos2, k);
+                if (E > p2k - L) continue;                             /* dead by now; its scan is never finished */
+                if (W_SHFL(xd_scan_open(rs) ? 1 : 0, k)) xd_finish_lane<1>(e, lane, k, pos1, pos2, rs);
+                const u32 ex = W_SHFL(pos2 + rs.cols, k);
+                if ((int)lane == k) { live = true; myStop = E; }
+                if (ex > E) E = ex;
+            }
         }
         /* left scan (:2598-2632), blocked by the bucket's previous extent on this diagonal */
-        xd_scan ls; xd_scan_init(ls, 0); ls.going = false;
+        xd_scan ls; xd_scan_init(ls, 0);
         if (live) {
             const s64 blk = (s64)myStop + diag;
             const u32 stop = blk > 0 ? (u32)blk : 0;
             xd_scan_init(ls, pos1 > stop ? pos1 - stop : 0);
-            while (xd_scan_open(ls) && ls.cols < XD_CAP) xd_scan_step8<-1>(e, pos1, pos2, ls);
+            while (xd_scan_open(ls) && ls.cols < XD_CAP) xd_scan_step8<-1>(e, pos1, pos2, xDrop, ls);
         }
         u32 longLeft = W_BALLOT(live && xd_scan_open(ls));
         while (longLeft) {
