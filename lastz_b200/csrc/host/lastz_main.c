@@ -40,7 +40,7 @@ static void parse_options(options* o, int argc, char** argv) {
     memset(o, 0, sizeof *o);
     o->withTrans = 1; o->step = 1; o->whichStrand = 1; o->gfExtend = LZB_GFEX_XDROP; o->gapped = 1;
     o->entropy = 1; o->trimToPeak = 1; o->tracebackBytes = 80u * 1024 * 1024; o->hashBits = 16;
-    o->speculation = 128;
+    o->speculation = 32;
     char* wordSeed = NULL;
     for (int i = 1; i < argc; i++) {
         const char* a = argv[i]; const char* v = strchr(a, '='); v = v ? v + 1 : "";
