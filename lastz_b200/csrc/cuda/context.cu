@@ -68,7 +68,11 @@ extern "C" int lzb_set_scoring(lzb_ctx* c, const int32_t* sub, const int32_t* ms
     lzb_scoring_dev* sc = &c->sc;
     memset(sc, 0, sizeof *sc);
     int rep[LZB_MAX_CLASSES]; int nc = 0;
-    for (int b = 0; b < 256; b++) {
+    /* A, C, G, T are numbered first (classes 0..3 for any DNA score set): k_extend2's pair table relies
+     * on it for conflict-free shared-memory banks, nothing relies on it for correctness */
+    for (int bi = 0; bi < 256 + 4; bi++) {
+        const int b = bi < 4 ? "ACGT"[bi] : bi - 4;
+        if (bi >= 4 && (b == 'A' || b == 'C' || b == 'G' || b == 'T')) continue;
         int found = -1;
         for (int k = 0; k < nc && found < 0; k++) {
             int r = rep[k]; bool same = true;

@@ -352,7 +352,10 @@ k_extend2(const u64* __restrict__ hits, const u32* __restrict__ bstart, const u3
           const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32* __restrict__ diagEnd,
           cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt, u32* __restrict__ nextBucket) {
     __shared__ s32 lut[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = sc->msubC[(i >> 4) * LZB_MAX_CLASSES + (i & 15)];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int c1 = i / (int)XD_LUT_STRIDE, c2 = i % (int)XD_LUT_STRIDE;
+        lut[i] = (c1 < XD_LUT_MAX_CLASSES && c2 < XD_LUT_MAX_CLASSES) ? sc->msubC[c1 * LZB_MAX_CLASSES + c2] : 0;
+    }
     __syncthreads();
     xd_env e;
     e.cls1 = cls1; e.cls2 = cls2; e.asc1 = asc1; e.asc2 = asc2; e.lut = lut;
@@ -513,7 +516,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= 16 &&
                              getenv("LZB_SPLIT_EXTEND") && atoi(getenv("LZB_SPLIT_EXTEND"));
     /* the warp-cooperative kernel (xdrop_warp.cuh) is the default x-drop path; LZB_EXTEND_V1=1 keeps the first one */
-    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= 16 && !splitExtend &&
+    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= XD_LUT_MAX_CLASSES && !splitExtend &&
                             !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
     u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
     if (coopExtend) {

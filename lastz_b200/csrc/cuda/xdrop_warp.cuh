@@ -28,6 +28,12 @@
 #define XD_CAP 128u                    /* columns a lane scans alone before the warp takes over */
 #endif
 #define XD_NEG ((s32)-0x3FFFFFFF)
+/* pair table index = class1 * 20 + class2 (<= 13 classes, so < 256).  With A,C,G,T as classes 0..3
+ * (context.cu numbers them first) the 16 common pairs fall into 16 different shared-memory banks;
+ * at stride 16 they shared 8 and every lookup of a warp on 32 unrelated diagonals conflicted
+ * (ncu: L1/shared pipe 77 % busy, 590 M bank conflicts per launch). */
+#define XD_LUT_STRIDE 20u
+#define XD_LUT_MAX_CLASSES 13
 
 struct cand_rec {                      /* one HSP candidate, 40 bytes */
     u32 hit1, hit2;                    /* the seed hit (one past its end) that produced it */
@@ -39,7 +45,7 @@ struct cand_rec {                      /* one HSP candidate, 40 bytes */
 struct xd_env {
     const u8* cls1; const u8* cls2;    /* class-coded sequences (<= 16 classes) */
     const u8* asc1; const u8* asc2;    /* the bytes themselves (entropy counts) */
-    const s32* lut;                    /* 256 entries: maskedScoring by (class1 << 4 | class2) */
+    const s32* lut;                    /* 256 entries: maskedScoring by class1 * XD_LUT_STRIDE + class2 */
     u32 len1, len2, L;                 /* L = seed length */
     s32 xDrop, K; int entropy;
     cand_rec* cand; u32 candCap; unsigned long long* ncand;
@@ -62,19 +68,19 @@ W_DEV void xd_fetch8(const xd_env& e, u32 p1, u32 p2, u32 o, u32 n, s32 (&s)[8])
     if (n == 0) return;
     if (DIR > 0) {
         const u64 x1 = xd_ld8(e.cls1, p1 + o), x2 = xd_ld8(e.cls2, p2 + o);
-        const u64 pr = (x1 << 4) | x2;
+        const u64 pr = (x1 << 4) + (x1 << 2) + x2;              /* bytewise class1 * 20 + class2; no byte overflows */
 #pragma unroll
         for (int i = 0; i < 8; i++) if ((u32)i < n) s[i] = e.lut[(u32)(pr >> (8 * i)) & 255u];
     } else {
         const u32 a = p1 - o, b = p2 - o;                       /* columns a-1, a-2, ... */
         if (n == 8 && a >= 8 && b >= 8) {
             const u64 x1 = xd_ld8(e.cls1, a - 8), x2 = xd_ld8(e.cls2, b - 8);
-            const u64 pr = (x1 << 4) | x2;
+            const u64 pr = (x1 << 4) + (x1 << 2) + x2;
 #pragma unroll
             for (int i = 0; i < 8; i++) s[i] = e.lut[(u32)(pr >> (8 * (7 - i))) & 255u];
         } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) if ((u32)i < n) s[i] = e.lut[((u32)e.cls1[a - 1 - i] << 4) | e.cls2[b - 1 - i]];
+            for (int i = 0; i < 8; i++) if ((u32)i < n) s[i] = e.lut[(u32)e.cls1[a - 1 - i] * XD_LUT_STRIDE + e.cls2[b - 1 - i]];
         }
     }
 }

@@ -195,6 +195,22 @@ int main(int argc, char** argv) {
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
                 for (int z = 0; z < 12; z++) ks[z] += sst.kernelSeconds[z];
             }
+            /* --self mirrors every HSP across the main diagonal when the run stops at HSPs (report_hsps /
+             * collect_hsps lastz.c:3858-3880, :4050-4075; with gapped extension the mirroring moves to the
+             * alignments, lastz.c:9055-9061) */
+            if (o.selfCompare && !o.gapped && !o.segmentsFile && nsegs) {
+                lzb_segment* both = malloc(2 * nsegs * sizeof *both); uint64_t m = 0;
+                int same = query.revCompFlags == target.revCompFlags;
+                for (uint64_t k = 0; k < nsegs; k++) {
+                    lzb_segment g = segs[k]; both[m++] = g;
+                    uint32_t len = g.length, e1 = g.pos1 + len, e2 = g.pos2 + len, s1, s2;
+                    if (same) { s1 = e1; s2 = e2; }
+                    else { s1 = target.len - e1 + len; s2 = query.len - e2 + len; if (s2 == e1 && s1 == e2) continue; }
+                    g.pos1 = s2 - len; g.pos2 = s1 - len; g.hspId = 0;
+                    both[m++] = g;
+                }
+                lzb_free(segs); segs = both; nsegs = m;
+            }
             if (o.chain)                                         /* try_reduce_to_chain lastz.c:3349, chainScale = 100 (:511) */
                 lzb_reduce_to_chain(segs, &nsegs, o.chainDiag, o.chainAnti, 100, ss.sub['A' * 256 + 'A']);
             int headerDone = 0;
@@ -218,6 +234,8 @@ int main(int argc, char** argv) {
                     lzb_die("%s", lzb_last_error());
                 totCells += gst.dpCells; gapSec += gst.seconds; gk += gst.kernelSeconds[0];
                 gExt += gst.anchorsExtended; gSpec += gst.speculated; gRedo += gst.redone; gLaunch += gst.launches; gTrunc += gst.truncated;
+                if (o.selfCompare && list)                        /* mirrorGapped, lastz.c:3494-3498 */
+                    list = lzb_mirror_alignments(list, &target, &query, &ss);
                 for (lzb_alignel* a = list; a; a = a->next) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }

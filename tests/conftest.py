@@ -65,3 +65,46 @@ def synth(tmp_path_factory):
             made[key] = (t, q)
         return made[key]
     return get
+
+
+def write_inverted_repeat_fasta(path, seed=7):
+    """A 60 kb sequence with a reverse-complement copy, a hairpin, a direct repeat and an exact palindrome:
+    --self alignments that lie below, touch and cross the main diagonal on the minus strand
+    (mirror_alignments lastz.c:4229, edit_script_upper_truncate edit_script.c:573)."""
+    import random
+    rnd = random.Random(seed)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+
+    def rc(s):
+        return "".join(comp[c] for c in reversed(s))
+
+    def mut(s, r):
+        return "".join(rnd.choice("ACGT") if rnd.random() < r else c for c in s)
+    s = "".join(rnd.choice("ACGT") for _ in range(60000))
+    s = s[:30000] + mut(rc(s[5000:9000]), 0.05) + s[34000:]
+    s = s[:45500] + "ACGTTGCA" + mut(rc(s[44000:45500]), 0.03) + s[45500 + 8 + 1500:]
+    s = s[:52000] + mut(s[12000:14000], 0.04) + s[54000:]
+    s = s[:20600] + rc(s[20000:20600]) + s[21200:]
+    with open(path, "w") as f:
+        f.write(">selfy\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n")
+
+
+# --self runs (BASELINE.json configs[1] is the first): target spec, options
+SELF_CASES = [
+    ("aglobin", ["--self", "--seed=12of19", "--nogapped"]),
+    ("aglobin", ["--self", "--seed=12of19", "--nogapped", "--format=segments"]),
+    ("aglobin", ["--self", "--nogapped", "--chain"]),
+    ("aglobin", ["--self"]),
+    ("inverted", ["--self"]),
+    ("inverted", ["--self", "--nogapped"]),
+    ("inverted", ["--self", "--chain"]),
+    ("inverted", ["--self", "--hspthresh=2000", "--ydrop=5000"]),
+]
+
+
+def self_case_target(which, tmp_path):
+    if which == "aglobin":
+        return os.path.join(GOLDEN, "aglobin.2bit") + "/human"
+    p = str(tmp_path / "selfy.fa")
+    write_inverted_repeat_fasta(p)
+    return p

@@ -4,7 +4,7 @@ import os
 
 import pytest
 
-from conftest import GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, lav_body, run_cli
+from conftest import GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, SELF_CASES, lav_body, run_cli, self_case_target
 
 pytestmark = pytest.mark.gpu
 
@@ -54,3 +54,13 @@ def test_cli_matches_reference_on_synthetic(synth, size, opts):
         assert got == want
     else:
         assert lav_body(got) == lav_body(want)
+
+
+@pytest.mark.parametrize("which,opts", SELF_CASES)
+def test_cli_self_alignment_matches_reference(tmp_path, which, opts):
+    """BASELINE.json configs[1] (aglobin.2bit/human --self --seed=12of19 --nogapped) and the other --self shapes."""
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    target = self_case_target(which, tmp_path)
+    got, _ = run_cli(PRODUCT_CLI, [target] + opts)
+    want, _ = run_cli(ref, [target] + opts)
+    assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]

@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import GOLDEN, ORACLE_CLI, REF_CLI, lav_body, run_cli
+from conftest import GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body, run_cli, self_case_target
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
 PIG = os.path.join(GOLDEN, "pseudopig.fa")
@@ -62,3 +62,14 @@ def test_oracle_matches_reference_on_synthetic(synth, size, opts):
         assert got == want
     else:
         assert lav_body(got) == lav_body(want)
+
+
+@pytest.mark.parametrize("which,opts", SELF_CASES)
+def test_oracle_self_alignment_matches_reference(tmp_path, which, opts):
+    """--self: below-diagonal hits dropped (seed_search.c:2182), HSPs / alignments mirrored (lastz.c:3858, :4229)."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    target = self_case_target(which, tmp_path)
+    got, _ = run_cli(ORACLE_CLI, [target] + opts)
+    want, _ = run_cli(REF_CLI, [target] + opts)
+    assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]

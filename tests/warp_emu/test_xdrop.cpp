@@ -123,7 +123,7 @@ static int one_case(int caseNo, u32 len1, u32 len2, u32 nhits, double homolog, d
 }
 
 int main(int argc, char** argv) {
-    for (int i = 0; i < 256; i++) g_lut[i] = pair_score((u32)i >> 4, (u32)i & 15);
+    for (u32 a = 0; a < 6; a++) for (u32 b = 0; b < 6; b++) g_lut[a * XD_LUT_STRIDE + b] = pair_score(a, b);
     int reps = argc > 1 ? atoi(argv[1]) : 1, bad = 0, n = 0;
     for (int r = 0; r < reps; r++) {
         bad += one_case(n++, 3000, 3000, 400, 1.0, 0.05, 0.0, 910, 3000, 1, 0);       // the default channel: HSPs of a few hundred columns
