@@ -95,6 +95,9 @@ typedef struct lzb_seed {
  * hitprocinfo fields (seed_search.h:112-156) process_for_simple_hit / xdrop_extend_seed_hit use */
 #define LZB_GFEX_NONE  0                      /* --nogfextend: raw hits */
 #define LZB_GFEX_XDROP 1                      /* default x-drop extension */
+#define LZB_GFEX_EXACT 2                      /* --exact=N: match_extend_seed_hit seed_search.c:3018; hspThreshold = N (a length) */
+#define LZB_GFEX_MISMATCH 3                   /* --mismatch=M,N / --<M>mismatch=N: mismatch_extend_seed_hit :3450; gfMismatches = M */
+#define LZB_GFEX_MISMATCH_MAX 50              /* gfexMismatch_max seed_search.h:168 */
 typedef struct lzb_seed_params {
     uint32_t start, end;       /* query interval to scan; end==0 => whole query */
     int32_t  gfExtend;         /* LZB_GFEX_* */
@@ -108,6 +111,7 @@ typedef struct lzb_seed_params {
     int32_t  plainHits;        /* process_for_plain_hit (seed_search.c:995): report every raw hit,
                                   no diag-hash filter; chosen by the reference when neither gap-free
                                   nor gapped extension is requested (lastz.c:2789) */
+    int32_t  gfMismatches;     /* LZB_GFEX_MISMATCH: mismatches allowed, 1..50 */
 } lzb_seed_params;
 
 typedef struct lzb_seed_stats {

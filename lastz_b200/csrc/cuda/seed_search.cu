@@ -379,6 +379,99 @@ k_extend2(const u64* __restrict__ hits, const u32* __restrict__ bstart, const u3
     if (lane == 0) { if (nExt) atomicAdd(&cnt->extensions, nExt); if (nBp) atomicAdd(&cnt->bpExtended, nBp); }
 }
 
+/* ---- K3d: --exact=N and --mismatch=M,N extension (match_extend_seed_hit seed_search.c:3018-3254,
+ * mismatch_extend_seed_hit :3450-3778).  In the mismatch mode the extent a hit leaves in its bucket
+ * depends on the left scan (:3740), which depends on the bucket -- right scans cannot run ahead of the
+ * replay -- so these non-default modes take the plain route: ONE THREAD PER BUCKET walks its hits in
+ * discovery order (2^hashBits independent threads).  Bases are compared with the case-insensitive
+ * nuc_to_bits table (dna_utilities.c:56; params->charToBits lastz.c:353), not with the score matrix. */
+__device__ __forceinline__ int alt_bits(u8 c) {
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return -1; }
+}
+__device__ __forceinline__ bool alt_mism(u8 a, u8 b) { const int x = alt_bits(a), y = alt_bits(b); return x != y || x < 0 || y < 0; }
+
+__global__ void __launch_bounds__(128)
+k_extend_alt(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuckets,
+             const u8* __restrict__ v1, const u8* __restrict__ v2, sp_dev P, int mismatches, u32* __restrict__ diagEnd,
+             cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt) {
+    const u32 L = (u32)P.L, K = (u32)P.K, INACTIVE = 0xFFFFFFFFu;
+    unsigned long long nExt = 0;
+    for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nbuckets; h += gridDim.x * blockDim.x) {
+        const u32 b0 = bstart[h], b1 = bstart[h + 1];
+        if (b0 == b1) continue;
+        u32 E = diagEnd[h];
+        for (u32 idx = b0; idx < b1; idx++) {
+            const u64 rec = hits[idx];
+            const u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
+            if (E > pos2 - L) continue;                              /* process_for_simple_hit :1113 */
+            const s64 diag = (s64)pos1 - (s64)pos2;
+            const s64 blk = (s64)E + diag, stop = blk > 0 ? blk : 0;
+            const s64 lim = (s64)P.len2 + diag, rstop = ((s64)P.len1 <= lim) ? (s64)P.len1 : lim;
+            u32 extent = INACTIVE; int inHit = 0; bool reject = false;
+            for (u32 k = 1; k <= L; k++)                             /* mismatches inside the hit, right to left */
+                if (alt_mism(v1[pos1 - k], v2[pos2 - k])) { extent = pos2 - k; if (++inHit > mismatches) { reject = true; break; } }
+            if (reject) { if (extent > E) E = extent; continue; }   /* hit_isnt_a_match :3232, :3760 */
+            s64 s1 = (s64)pos1 - L, s2 = (s64)pos2 - L, left, right;
+            if (mismatches == 0) {                                   /* ---- exact ---- */
+                if (s1 < stop) { s1--; s2--; }
+                else while (s1 >= stop) {
+                    if (s1 == stop) { s1--; s2--; break; }
+                    const u8 n1 = v1[--s1], n2 = v2[--s2];
+                    if (n1 == 0 || n2 == 0 || alt_mism(n1, n2)) break;
+                }
+                left = s1;
+                s1 = (s64)pos1 - 1; s2 = (s64)pos2 - 1;
+                while (s1 < rstop) {
+                    const u8 n1 = v1[++s1], n2 = v2[++s2];
+                    if (n1 == 0 || n2 == 0 || alt_mism(n1, n2)) break;
+                }
+                right = s1;
+                extent = (u32)(right - diag);
+            } else {                                                 /* ---- up to `mismatches` mismatches ---- */
+                s64 mmLoc[LZB_GFEX_MISMATCH_MAX + 1];
+                int mmScan = mismatches + 1 - inHit; const int mmStop = mmScan;
+                if (s1 < stop) { s1--; s2--; }
+                else while (s1 >= stop) {
+                    if (s1 == stop) { s1--; s2--; break; }
+                    const u8 n1 = v1[--s1], n2 = v2[--s2];
+                    if (n1 == 0 || n2 == 0) break;
+                    if (alt_mism(n1, n2)) { mmLoc[--mmScan] = s1; if (mmScan == 0) break; }
+                }
+                if (mmScan > 0) mmLoc[--mmScan] = s1;
+                int shortfall = mmScan;
+                s1 = (s64)pos1 - 1; s2 = (s64)pos2 - 1;
+                s64 bestLength = 0; left = right = -2; bool have = false;
+                while (s1 < rstop) {
+                    const u8 n1 = v1[++s1], n2 = v2[++s2];
+                    if (n1 == 0 || n2 == 0) break;
+                    if (alt_mism(n1, n2)) {
+                        if (extent == INACTIVE) extent = (u32)s2;
+                        if (shortfall > 0) { shortfall--; continue; }
+                        const s64 thisLength = s1 - mmLoc[mmScan];
+                        if (thisLength > bestLength) { bestLength = thisLength; left = mmLoc[mmScan]; right = s1; have = true; }
+                        if (++mmScan == mmStop) break;
+                    }
+                }
+                if (mmScan < mmStop) {
+                    if (extent == INACTIVE) extent = (u32)s2;
+                    const s64 thisLength = s1 - mmLoc[mmScan];
+                    if (thisLength > bestLength) { left = mmLoc[mmScan]; right = s1; have = true; }
+                }
+                if (!have) continue;
+                if ((u32)(right - (left + 1)) >= K) extent = (u32)(right + 1 - diag);
+            }
+            nExt++;
+            if (extent > E) E = extent;
+            const u32 length = (u32)(right - (left + 1));
+            if (length < K) continue;
+            const u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+            if (slot < candCap) { cand_rec r = { pos1, pos2, (u32)(left + 1), (u32)(left + 1 - diag), length, (s32)length, 0, 0, 0, 0 }; cand[slot] = r; }
+        }
+        diagEnd[h] = E;
+    }
+    if (nExt) atomicAdd(&cnt->extensions, nExt);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 
 #include "xdrop_split.cuh"
@@ -430,6 +523,8 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     if (qend <= qstart) return lzb_fail("in seed_hit_search(), interval is void (%u-%u)", qstart, qend);
     if (qend > q->len) return lzb_fail("in seed_hit_search(), interval end is bad (%u>%u)", qend, q->len);
     if (seed->length < 2) return lzb_fail("seed length must be at least two (yours is %d)", seed->length);
+    if (prm->gfExtend == LZB_GFEX_MISMATCH && (prm->gfMismatches < 1 || prm->gfMismatches > LZB_GFEX_MISMATCH_MAX))
+        return lzb_fail("%d is out of range for N-mismatch (valid range is 1..%d)", prm->gfMismatches, LZB_GFEX_MISMATCH_MAX);
     if (seed->weight != t->wordBits || seed->length != t->seedLength)
         return lzb_fail("the seed does not match the one the target index was built with");
     int hashBits = prm->hashBits ? prm->hashBits : 16;
@@ -560,6 +655,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
                 TIMED(8, (k_right<<<c->smCount * 8, 256, 0, st>>>(valsB, nh, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_right)));
                 TIMED(9, (k_replay<<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, d_right, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_live, d_nlive)));
                 TIMED(10, (k_left<<<c->smCount * 8, 256, 0, st>>>(d_live, d_nlive, t->d_cls, q->d_cls, t->d_seq, q->d_seq, c->d_sc, P, d_cand, candCap, d_cnt)));
+            } else if (prm->gfExtend == LZB_GFEX_EXACT || prm->gfExtend == LZB_GFEX_MISMATCH) {
+                TIMED(7, (k_extend_alt<<<(nbuckets + 127) / 128, 128, 0, st>>>(valsB, d_bstart, nbuckets, t->d_seq, q->d_seq, P,
+                                                                                 prm->gfExtend == LZB_GFEX_EXACT ? 0 : prm->gfMismatches,
+                                                                                 d_E, d_cand, candCap, d_cnt)));
             } else if (coopExtend) {
                 int bits = 1; while (bits < 32 && (nh >> bits)) bits++;          /* bucket sizes are <= nh */
                 size_t tbo = tmpBytes;

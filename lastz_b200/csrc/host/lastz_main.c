@@ -16,7 +16,7 @@ typedef struct {
     const char* seedPattern; int withTrans, haveTrans;
     uint32_t step; int haveStep;
     int whichStrand;               /* 0 plus, 1 both, -1 minus */
-    int gfExtend, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
+    int gfExtend, gfMismatches, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
     uint32_t tracebackBytes;
     int hashBits;
@@ -74,6 +74,19 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--strand=minus")) o->whichStrand = -1;
         else if (!strcmp(a, "--self")) { o->selfCompare = 1; o->inhibitTrivial = 1; }
         else if (!strcmp(a, "--notrivial")) o->inhibitTrivial = 1;
+        else if (starts(a, "--exact=")) { o->gfExtend = LZB_GFEX_EXACT; o->K = atoi(v); o->haveK = 1; }      /* lastz.c:6330-6350 */
+        else if (starts(a, "--mismatch=") || (a[0] == '-' && a[1] == '-' && a[2] >= '0' && a[2] <= '9' && strstr(a, "mismatch="))) {
+            int M = 0, N = 0;                                    /* --mismatch=M,N or --<M>mismatch=N, lastz.c:6355-6390 */
+            if (starts(a, "--mismatch=")) { if (sscanf(v, "%d,%d", &M, &N) != 2) lzb_die("--mismatch requires two values (count and length)"); }
+            else { M = atoi(a + 2); N = atoi(v); }
+            if (M == 0) o->gfExtend = LZB_GFEX_EXACT;
+            else {
+                if (M < 1 || M > LZB_GFEX_MISMATCH_MAX) lzb_die("%d is out of range for N-mismatch (valid range is 1..%d)", M, LZB_GFEX_MISMATCH_MAX);
+                if (N < M) lzb_die("%d is not a valid exact %dmismatch threshold", N, M);
+                o->gfExtend = LZB_GFEX_MISMATCH; o->gfMismatches = M;
+            }
+            o->K = N; o->haveK = 1;
+        }
         else if (!strcmp(a, "--nogfextend")) o->gfExtend = LZB_GFEX_NONE;
         else if (!strcmp(a, "--gfextend")) o->gfExtend = LZB_GFEX_XDROP;
         else if (!strcmp(a, "--nogapped") || !strcmp(a, "--ungapped")) o->gapped = 0;
@@ -185,7 +198,7 @@ int main(int argc, char** argv) {
             if (o.segmentsFile) nsegs = read_segments(o.segmentsFile, &target, &query, &segs);
             else {
                 lzb_seed_params sp; memset(&sp, 0, sizeof sp);
-                sp.gfExtend = o.gfExtend; sp.xDrop = o.X; sp.hspThreshold = o.K; sp.entropy = o.entropy;
+                sp.gfExtend = o.gfExtend; sp.gfMismatches = o.gfMismatches; sp.xDrop = o.X; sp.hspThreshold = o.K; sp.entropy = o.entropy;
                 sp.hashBits = o.hashBits; sp.selfCompare = o.selfCompare;
                 sp.sameStrand = o.selfCompare && query.revCompFlags == target.revCompFlags;
                 sp.strandId = query.revCompFlags;
@@ -211,6 +224,14 @@ int main(int argc, char** argv) {
                 }
                 lzb_free(segs); segs = both; nsegs = m;
             }
+            /* only the x-drop extension leaves real scores in the table (seed_search.c:2953); the other modes
+             * are scored here when chaining or the gapped stage needs them (lastz.c:3336-3340, score_segments segment.c:1262) */
+            if (!o.segmentsFile && o.gfExtend != LZB_GFEX_XDROP && (o.chain || o.gapped))
+                for (uint64_t k = 0; k < nsegs; k++) {
+                    int32_t sc = 0;
+                    for (uint32_t j = 0; j < segs[k].length; j++) sc += ss.masked[(uint32_t)target.v[segs[k].pos1 + j] * 256 + query.v[segs[k].pos2 + j]];
+                    segs[k].s = sc;
+                }
             if (o.chain)                                         /* try_reduce_to_chain lastz.c:3349, chainScale = 100 (:511) */
                 lzb_reduce_to_chain(segs, &nsegs, o.chainDiag, o.chainAnti, 100, ss.sub['A' * 256 + 'A']);
             int headerDone = 0;

@@ -187,6 +187,105 @@ static void emit_hsp(search* S, u32 end1, u32 end2, u32 len, s32 score) {
     S->st.hsps++;
 }
 
+/* nuc_to_bits dna_utilities.c:56-74: the case-insensitive table the exact/mismatch extensions compare with
+ * (params->charToBits, lastz.c:353, :2902) */
+static inline int n2b(u8 c) {
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return -1; }
+}
+static inline int mism(u8 a, u8 b) { int x = n2b(a), y = n2b(b); return x != y || x < 0 || y < 0; }
+
+/* match_extend_seed_hit seed_search.c:3018-3254 (--exact=N); positions are indices, s64 where the
+ * reference steps a pointer one below the sequence start */
+static void exact_hit(search* S, u32 pos1, u32 pos2, u32 h) {
+    const u8* v1 = S->t->v; const u8* v2 = S->q->v;
+    u32 len = (u32)S->sd->length; s64 diag = (s64)pos1 - (s64)pos2;
+    u32 extent;
+    for (u32 k = 1; k <= len; k++)                                  /* :3076-3090 the hit itself must match */
+        if (mism(v1[pos1 - k], v2[pos2 - k])) { extent = pos2 - k; goto not_a_match; }
+    {
+        s64 s1 = (s64)pos1 - len, s2 = (s64)pos2 - len;             /* :3096-3140 left */
+        s64 blk = (s64)S->E[h] + diag, stop = blk > 0 ? blk : 0;
+        if (s1 < stop) { s1--; s2--; }
+        else while (s1 >= stop) {
+            if (s1 == stop) { s1--; s2--; break; }
+            u8 n1 = v1[--s1], n2 = v2[--s2];
+            if (n1 == 0 || n2 == 0 || mism(n1, n2)) break;
+        }
+        s64 left = s1;
+        s1 = (s64)pos1 - 1; s2 = (s64)pos2 - 1;                     /* :3146-3176 right */
+        s64 lim = (s64)S->q->len + diag, rstop = ((s64)S->t->len <= lim) ? (s64)S->t->len : lim;
+        while (s1 < rstop) {
+            u8 n1 = v1[++s1], n2 = v2[++s2];
+            if (n1 == 0 || n2 == 0 || mism(n1, n2)) break;
+        }
+        s64 right = s1;
+        S->st.extensions++;
+        extent = (u32)(right - diag);                               /* :3182-3200 */
+        if (extent > S->E[h]) S->E[h] = extent;
+        u32 length = (u32)(right - (left + 1));
+        if (length < (u32)S->p->hspThreshold) return;
+        emit_hsp(S, (u32)right, (u32)(right - diag), length, (s32)length);
+        return;
+    }
+not_a_match:
+    if (extent > S->E[h]) S->E[h] = extent;                         /* :3232-3250 */
+}
+
+/* mismatch_extend_seed_hit seed_search.c:3450-3778 (--mismatch=M,N) */
+static void mismatch_hit(search* S, u32 pos1, u32 pos2, u32 h) {
+    const u8* v1 = S->t->v; const u8* v2 = S->q->v;
+    u32 len = (u32)S->sd->length; s64 diag = (s64)pos1 - (s64)pos2;
+    int M = S->p->gfMismatches, Ecnt = 0;
+    const u32 INACTIVE = 0xFFFFFFFFu;                               /* hashInactiveEnd diag_hash.h:101 */
+    u32 extent = INACTIVE;
+    s64 mmLoc[LZB_GFEX_MISMATCH_MAX + 1];
+    for (u32 k = 1; k <= len; k++)                                  /* :3520-3538 mismatches inside the hit */
+        if (mism(v1[pos1 - k], v2[pos2 - k])) { extent = pos2 - k; if (++Ecnt > M) goto not_a_match; }
+    {
+        s64 s1 = (s64)pos1 - len, s2 = (s64)pos2 - len;             /* :3548-3612 left, collecting mismatch positions */
+        s64 blk = (s64)S->E[h] + diag, stop = blk > 0 ? blk : 0;
+        int mmScan = M + 1 - Ecnt; const int mmStop = mmScan;
+        if (s1 < stop) { s1--; s2--; }
+        else while (s1 >= stop) {
+            if (s1 == stop) { s1--; s2--; break; }
+            u8 n1 = v1[--s1], n2 = v2[--s2];
+            if (n1 == 0 || n2 == 0) break;
+            if (mism(n1, n2)) { mmLoc[--mmScan] = s1; if (mmScan == 0) break; }
+        }
+        if (mmScan > 0) mmLoc[--mmScan] = s1;                       /* :3618-3621 */
+        int mmShortfall = mmScan;
+        s1 = (s64)pos1 - 1; s2 = (s64)pos2 - 1;                     /* :3630-3700 right */
+        s64 lim = (s64)S->q->len + diag, rstop = ((s64)S->t->len <= lim) ? (s64)S->t->len : lim;
+        s64 bestLength = 0, left = -2, right = -2; int have = 0;
+        while (s1 < rstop) {
+            u8 n1 = v1[++s1], n2 = v2[++s2];
+            if (n1 == 0 || n2 == 0) break;
+            if (mism(n1, n2)) {
+                if (extent == INACTIVE) extent = (u32)s2;
+                if (mmShortfall > 0) { mmShortfall--; continue; }
+                s64 thisLength = s1 - mmLoc[mmScan];
+                if (thisLength > bestLength) { bestLength = thisLength; left = mmLoc[mmScan]; right = s1; have = 1; }
+                if (++mmScan == mmStop) break;
+            }
+        }
+        if (mmScan < mmStop) {                                      /* :3706-3720 the stopping point is an endpoint too */
+            if (extent == INACTIVE) extent = (u32)s2;
+            s64 thisLength = s1 - mmLoc[mmScan];
+            if (thisLength > bestLength) { left = mmLoc[mmScan]; right = s1; have = 1; }
+        }
+        if (!have) return;                                          /* the reference dies here (":3723 found no interval") */
+        S->st.extensions++;
+        u32 length = (u32)(right - (left + 1));                     /* :3730-3745 */
+        if (length >= (u32)S->p->hspThreshold) extent = (u32)(right + 1 - diag);
+        if (extent > S->E[h]) S->E[h] = extent;
+        if (length < (u32)S->p->hspThreshold) return;
+        emit_hsp(S, (u32)right, (u32)(right - diag), length, (s32)length);
+        return;
+    }
+not_a_match:
+    if (extent > S->E[h]) S->E[h] = extent;
+}
+
 /*
  * One seed hit: process_for_simple_hit seed_search.c:1056-1192 followed by
  * xdrop_extend_seed_hit :2528-2959.  pos1/pos2 = one past the hit end.
@@ -206,6 +305,8 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
         emit_hsp(S, pos1, pos2, len, 0);
         return;
     }
+    if (P->gfExtend == LZB_GFEX_EXACT) { exact_hit(S, pos1, pos2, h); return; }          /* :1146-1151 */
+    if (P->gfExtend == LZB_GFEX_MISMATCH) { mismatch_hit(S, pos1, pos2, h); return; }    /* :1158-1164 */
     S->st.extensions++;
     const u8* v1 = S->t->v; const u8* v2 = S->q->v;
     const s32* sub = S->c->msub;
@@ -276,6 +377,8 @@ int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed*
     if (end <= start) return fail("in seed_hit_search(), interval is void (%u-%u)", start, end);
     if (end > q->len) return fail("in seed_hit_search(), interval end is bad (%u>%u)", end, q->len);
     if (sd->length < 2) return fail("seed length must be at least two (yours is %d)", sd->length);
+    if (P->gfExtend == LZB_GFEX_MISMATCH && (P->gfMismatches < 1 || P->gfMismatches > LZB_GFEX_MISMATCH_MAX))
+        return fail("%d is out of range for N-mismatch (valid range is 1..%d)", P->gfMismatches, LZB_GFEX_MISMATCH_MAX);
     search S; memset(&S, 0, sizeof S);
     S.c = c; S.t = t; S.q = q; S.sd = sd; S.p = P;
     int hb = P->hashBits ? P->hashBits : 16;

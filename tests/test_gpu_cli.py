@@ -4,7 +4,8 @@ import os
 
 import pytest
 
-from conftest import GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, SELF_CASES, lav_body, run_cli, self_case_target
+from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, SELF_CASES,
+                      lav_body, masked_query, run_cli, same_output, self_case_target)
 
 pytestmark = pytest.mark.gpu
 
@@ -64,3 +65,16 @@ def test_cli_self_alignment_matches_reference(tmp_path, which, opts):
     got, _ = run_cli(PRODUCT_CLI, [target] + opts)
     want, _ = run_cli(ref, [target] + opts)
     assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]
+
+
+@pytest.mark.parametrize("opts", ALT_EXTEND_FIXTURE_CASES)
+def test_cli_exact_and_mismatch_extension_on_fixtures(opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    same_output(run_cli(PRODUCT_CLI, [CAT, PIG] + opts)[0], run_cli(ref, [CAT, PIG] + opts)[0])
+
+
+@pytest.mark.parametrize("opts", ALT_EXTEND_SYNTH_CASES)
+def test_cli_exact_and_mismatch_extension_on_synthetic(synth, tmp_path, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    t, qm = masked_query(synth, tmp_path)
+    same_output(run_cli(PRODUCT_CLI, [t, qm] + opts)[0], run_cli(ref, [t, qm] + opts)[0])

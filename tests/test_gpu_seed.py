@@ -73,6 +73,9 @@ CONFIGS = [
     dict(gf_extend=0, plain_hits=True, seed=("11111111", 0)),  # base_test.hits
     dict(hash_bits=10),                                       # tiny hash: collisions everywhere (diag_hash.h:43-48)
     dict(hash_bits=22),                                       # lastz_32's 4M-entry hash
+    dict(gf_extend=2, hsp_threshold=14, seed=("11111111", 0)),  # --exact=14 (match_extend_seed_hit)
+    dict(gf_extend=3, gf_mismatches=2, hsp_threshold=20),       # --mismatch=2,20 (mismatch_extend_seed_hit)
+    dict(gf_extend=3, gf_mismatches=1, hsp_threshold=12, seed=("111111", 0), hash_bits=9),   # collisions + mismatch mode
 ]
 
 

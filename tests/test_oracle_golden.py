@@ -7,7 +7,8 @@ import os
 
 import pytest
 
-from conftest import GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body, run_cli, self_case_target
+from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+                      masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
 PIG = os.path.join(GOLDEN, "pseudopig.fa")
@@ -73,3 +74,19 @@ def test_oracle_self_alignment_matches_reference(tmp_path, which, opts):
     got, _ = run_cli(ORACLE_CLI, [target] + opts)
     want, _ = run_cli(REF_CLI, [target] + opts)
     assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]
+
+
+@pytest.mark.parametrize("opts", ALT_EXTEND_FIXTURE_CASES)
+def test_oracle_exact_and_mismatch_extension_on_fixtures(opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    files = [os.path.join(GOLDEN, "pseudocat.fa"), os.path.join(GOLDEN, "pseudopig.fa")]
+    same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])
+
+
+@pytest.mark.parametrize("opts", ALT_EXTEND_SYNTH_CASES)
+def test_oracle_exact_and_mismatch_extension_on_synthetic(synth, tmp_path, opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    t, qm = masked_query(synth, tmp_path)
+    same_output(run_cli(ORACLE_CLI, [t, qm] + opts)[0], run_cli(REF_CLI, [t, qm] + opts)[0])
