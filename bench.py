@@ -355,7 +355,8 @@ def main():
     # every cross-rank aggregate is computed HERE, on all ranks (collectives must not sit under `if rank == 0`)
     agg = {"e2e_hits": total("hits", accs_e2e), "e2e_cells": total("cells", accs_e2e),
            "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_wall", accs_e2e),
-           "hsps": total("hsps", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e)}
+           "hsps": total("hsps", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e),
+           "cells_computed": total("cells_computed", accs)}
     e2e_hits = agg["e2e_hits"]
 
     def per_step(key, accs_):
@@ -386,7 +387,7 @@ def main():
                 "stage_ms_per_step": {"seed": 1e3 * seed_s / args.steps, "gapped": 1e3 * gap_s / args.steps,
                                       "index_build_once": 1e3 * index_s},
                 "counts_per_step": {"raw_seed_hits": hits / args.steps, "dp_cells": cells / args.steps,
-                                    "dp_cells_incl_discarded_speculation": total("cells_computed", accs) / args.steps,
+                                    "dp_cells_incl_discarded_speculation": agg["cells_computed"] / args.steps,
                                     "hsps": agg["hsps"] / args.steps, "segments_gathered": accs[-1]["gathered"]},
                 "timing": "host clock around blocking C-ABI calls, barrier+sync both sides, max over ranks; "
                           "kernels timed by CUDA events on the library's stream",
