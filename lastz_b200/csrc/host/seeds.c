@@ -25,17 +25,21 @@ void lzb_seed_parse(lzb_seed* out, const char* pattern, int withTrans) {
     while (s < e && (*s == '0' || *s == 'X' || *s == 'x')) s++;
     if (s == e) lzb_die("seed string is empty!");
     while (e[-1] == '0' || e[-1] == 'X' || e[-1] == 'x') e--;
-    uint64_t bits = 0, flips = 0; int length = 0, weight = 0;
+    uint64_t bits = 0, flips = 0; int length = 0, weight = 0, allStrict = 1, anyMatch = 0;
     for (const char* p = s; p < e; p++) {
         switch (*p) {
-            case '1': bits = (bits << 2) + 3; flips = (flips << 2) + 2; weight += 2; length++; break;
+            case '1': bits = (bits << 2) + 3; flips = (flips << 2) + 2; weight += 2; length++; anyMatch = 1; break;
             case '0': case 'X': case 'x': bits <<= 2; flips <<= 2; length++; break;
-            case 'T': case 't':
-                lzb_die("lastz_b200 supports strict seeds only (1s and 0s); \"%s\" has a transition position", pattern);
-                break;
+            /* a transition position matches on the purine/pyrimidine bit alone (seeds.c:471-481).  The
+             * reference packs all-T ("half-weight") seeds from a 1-bit-per-base word (seeds.c:404, pos_table.c:479);
+             * here they go through the same 2-bit word with 1-bit masks: another index layout, the same hits
+             * in the same order (half-weight seeds have no transition variants, seeds.c:540) */
+            case 'T': case 't': bits = (bits << 2) + 1; flips <<= 2; weight += 1; length++; allStrict = 0; break;
             default: lzb_die("seed string %s contains illegal character %c", pattern, *p);
         }
     }
+    if (!allStrict && !anyMatch) flips = 0;             /* type 'H' */
+    if (weight == 0) lzb_die("seed string (%s) cannot have zero weight.", pattern);
     if (length > 31) lzb_die("seed string (%s) cannot have length exceeding 31 (it's %d).", pattern, length);
     if (weight > 28) lzb_die("seed (%s) needs %d index bits; lastz_b200 does not implement overweight seeds (max 28)", pattern, weight);
     memset(out, 0, sizeof *out);

@@ -22,6 +22,7 @@ def norm(t):
     ("base_test.hits.lav", ["W=8", "T=0", "--plus", "--nogfextend", "--nogapped"]),
     ("base_test.hsp.lav", ["C=3", "W=8", "T=0"]),
     ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),
+    ("base_test.hwseeded.lav", ["C=3", "--seed=TTT0T0T0TTT00T0T"]),
     ("base_test.chained.lav", ["C=1", "W=8", "T=0"]),
     ("base_test.extended.lav", ["C=2", "W=8", "T=0"]),
 ])

@@ -17,7 +17,8 @@ CASES = [
     ("base_test.default.lav", []),                                                  # Makefile:208
     ("base_test.hits.lav", ["W=8", "T=0", "--plus", "--nogfextend", "--nogapped"]),  # Makefile:295
     ("base_test.hsp.lav", ["C=3", "W=8", "T=0"]),                                    # Makefile:306
-    ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),                        # Makefile:465
+    ("base_test.seeded.lav", ["C=3", "--seed=111010011101"]),
+    ("base_test.hwseeded.lav", ["C=3", "--seed=TTT0T0T0TTT00T0T"]),                        # Makefile:465
     ("base_test.chained.lav", ["C=1", "W=8", "T=0"]),                                # Makefile:351 (chain only)
     ("base_test.extended.lav", ["C=2", "W=8", "T=0"]),                               # Makefile:362 (chain + gapped)
 ]
