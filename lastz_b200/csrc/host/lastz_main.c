@@ -21,7 +21,7 @@ typedef struct {
     uint32_t tracebackBytes;
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
-    int format;                    /* 0 lav, 1 segments */
+    int format;                    /* 0 lav, 1 segments, 2 general, 3 general- */
     int device, showStats, speculation;
     int chainDiag, chainAnti;
     char args[4096];
@@ -115,6 +115,8 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--output=")) o->outputFile = v;
         else if (!strcmp(a, "--format=lav")) o->format = 0;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
+        else if (!strcmp(a, "--format=general")) o->format = 2;          /* default fields, genpaf.h:117 */
+        else if (!strcmp(a, "--format=general-")) o->format = 3;         /* ... without the header line */
         /* lastz_b200 additions */
         else if (starts(a, "--device=")) o->device = atoi(v);
         else if (starts(a, "--diaghash=")) o->hashBits = atoi(v);
@@ -179,7 +181,8 @@ int main(int argc, char** argv) {
     if (!T) lzb_die("%s", lzb_last_error());
 
     if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, o.K, o.L);
-    else fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
+    else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
+    else if (o.format == 2) lzb_general_header(out);
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
     uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
@@ -240,7 +243,7 @@ int main(int argc, char** argv) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_match(out, &target, &query, &segs[k]);
-                    }
+                    } else if (o.format >= 2) lzb_general_match(out, &target, &query, &segs[k]);
                 }
                 if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
             } else {
@@ -261,7 +264,8 @@ int main(int argc, char** argv) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_align(out, &target, &query, a);
-                    } else lzb_die("--format=segments needs --nogapped");
+                    } else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
+                    else lzb_die("--format=segments needs --nogapped");
                 }
                 lzb_free_align_list(list);
             }

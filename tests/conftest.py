@@ -145,3 +145,13 @@ def masked_query(synth, tmp_path, size=300000):
 
 def same_output(got, want):
     assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]
+
+
+# --format=general (default fields, genpaf.c:595-690 / genpaf.h:117): target spec suffix, query spec suffix, options
+GENERAL_CASES = [
+    ("", "", ["--format=general"]),
+    ("", "", ["--format=general", "--nogapped"]),
+    ("", "", ["--format=general-", "--chain"]),
+    ("", "", ["--format=general", "--strand=minus", "K=2200"]),
+    ("[2000..15000]", "[500..20000]", ["--format=general"]),
+]

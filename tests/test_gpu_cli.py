@@ -4,7 +4,7 @@ import os
 
 import pytest
 
-from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, SELF_CASES,
+from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, GENERAL_CASES, GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, SELF_CASES,
                       lav_body, masked_query, run_cli, same_output, self_case_target)
 
 pytestmark = pytest.mark.gpu
@@ -79,3 +79,9 @@ def test_cli_exact_and_mismatch_extension_on_synthetic(synth, tmp_path, opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
     t, qm = masked_query(synth, tmp_path)
     same_output(run_cli(PRODUCT_CLI, [t, qm] + opts)[0], run_cli(ref, [t, qm] + opts)[0])
+
+
+@pytest.mark.parametrize("a1,a2,opts", GENERAL_CASES)
+def test_cli_general_format(a1, a2, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    assert run_cli(PRODUCT_CLI, [CAT + a1, PIG + a2] + opts)[0] == run_cli(ref, [CAT + a1, PIG + a2] + opts)[0]
