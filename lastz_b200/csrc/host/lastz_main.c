@@ -21,7 +21,7 @@ typedef struct {
     uint32_t tracebackBytes;
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
-    int format;                    /* 0 lav, 1 segments, 2 general, 3 general- */
+    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf- */
     int device, showStats, speculation;
     int chainDiag, chainAnti;
     char args[4096];
@@ -117,6 +117,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--format=segments")) o->format = 1;
         else if (!strcmp(a, "--format=general")) o->format = 2;          /* default fields, genpaf.h:117 */
         else if (!strcmp(a, "--format=general-")) o->format = 3;         /* ... without the header line */
+        else if (!strcmp(a, "--format=maf-")) o->format = 4;             /* MAF blocks, no parameter header */
         /* lastz_b200 additions */
         else if (starts(a, "--device=")) o->device = atoi(v);
         else if (starts(a, "--diaghash=")) o->hashBits = atoi(v);
@@ -243,6 +244,12 @@ int main(int argc, char** argv) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_match(out, &target, &query, &segs[k]);
+                    } else if (o.format == 4) {                  /* an HSP is an alignment with one run of substitutions */
+                        lzb_editscript es = { 1, 1, LZB_OP_SUB, { LZB_OP_SUB | (segs[k].length << 2) } };
+                        lzb_alignel al; memset(&al, 0, sizeof al);
+                        al.beg1 = segs[k].pos1 + 1; al.end1 = segs[k].pos1 + segs[k].length; al.beg2 = segs[k].pos2 + 1; al.end2 = segs[k].pos2 + segs[k].length;
+                        al.s = segs[k].s; al.script = &es;
+                        lzb_maf_align(out, &target, &query, &al);
                     } else if (o.format >= 2) lzb_general_match(out, &target, &query, &segs[k]);
                 }
                 if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
@@ -264,7 +271,8 @@ int main(int argc, char** argv) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_align(out, &target, &query, a);
-                    } else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
+                    } else if (o.format == 4) lzb_maf_align(out, &target, &query, a);
+                    else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
                     else lzb_die("--format=segments needs --nogapped");
                 }
                 lzb_free_align_list(list);

@@ -76,6 +76,7 @@ void lzb_segments_write(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_s
 void lzb_general_header(FILE*);
 void lzb_general_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
 void lzb_general_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
+void lzb_maf_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);    /* maf.c:271, --format=maf- */
 
 /* mirror.c -- mirror_alignments lastz.c:4229 (--self with gapped extension) */
 lzb_alignel* lzb_mirror_alignments(lzb_alignel* list, const lzb_seq* seq1, const lzb_seq* seq2, const lzb_scoreset* ss);

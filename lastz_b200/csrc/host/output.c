@@ -151,3 +151,46 @@ void lzb_general_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_
     if (d == 0) m = 0;
     general_row(f, s1, s2, g->pos1, g->length, g->pos2, g->length, g->s, m, d);
 }
+
+/* ---- --format=maf- (MAF blocks without the parameter header), print_maf_align maf.c:271-470,
+ * unpartitioned sequences ---- */
+static int digits_of(uint32_t a, uint32_t b) { uint32_t m = a > b ? a : b; int d = 1; while (m >= 10) { m /= 10; d++; } return d; }
+static char toprint(uint8_t c) { return (c >= 0x20 && c < 0x7F) ? (char)c : '*'; }      /* dna_toprint dna_utilities.h:305 */
+
+void lzb_maf_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a) {
+    const char* name1 = (s1->shortHeader && s1->shortHeader[0]) ? s1->shortHeader : "seq1";
+    const char* name2 = (s2->shortHeader && s2->shortHeader[0]) ? s2->shortHeader : "seq2";
+    static const char* rcfSuffix[4] = { "", "~", "~", "" };                             /* maf.c / cigar.c:191 */
+    const char* suff1 = rcfSuffix[s1->revCompFlags & 3]; const char* suff2 = rcfSuffix[s2->revCompFlags & 3];
+    uint32_t beg1 = a->beg1, beg2 = a->beg2, height = a->end1 - beg1 + 1, width = a->end2 - beg2 + 1;
+    uint32_t start1, start2; char strand1, strand2;
+    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = beg1 - 1 + s1->startLoc; strand1 = '+'; }
+    else { start1 = beg1 - 1 + s1->trueLen + 2 - (s1->startLoc + s1->len); strand1 = '-'; }
+    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = beg2 - 1 + s2->startLoc; strand2 = '+'; }
+    else { start2 = beg2 - 1 + s2->trueLen + 2 - (s2->startLoc + s2->len); strand2 = '-'; }
+    int len1 = (int)(strlen(name1) + strlen(suff1)), len2 = (int)(strlen(name2) + strlen(suff2));
+    int nameW = len1 >= len2 ? len1 : len2;
+    int startW = digits_of(start1, start2), endW = digits_of(height, width), lenW = digits_of(s1->trueLen, s2->trueLen);
+    const lzb_editscript* sc = a->script;
+    fprintf(f, "a score=%d\n", a->s);
+    for (int row = 0; row < 2; row++) {
+        if (row == 0) fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name1, suff1, nameW + 1 - len1, " ", startW, start1 - 1, endW, height, strand1, lenW, s1->trueLen);
+        else fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name2, suff2, nameW + 1 - len2, " ", startW, start2 - 1, endW, width, strand2, lenW, s2->trueLen);
+        uint32_t k = 0;
+        for (uint32_t i = 0, j = 0; i < height || j < width;) {
+            uint32_t run = 0;
+            while (k < sc->len && (sc->op[k] & 3) == LZB_OP_SUB) { run += sc->op[k] >> 2; k++; }
+            const uint8_t* p = (row == 0 ? s1->v + beg1 - 1 + i : s2->v + beg2 - 1 + j);
+            for (uint32_t x = 0; x < run; x++) fputc(toprint(p[x]), f);
+            i += run; j += run;
+            if (i < height || j < width) {
+                if (k >= sc->len) break;
+                uint32_t op = sc->op[k] & 3, rpt = sc->op[k] >> 2; k++;
+                if (op == LZB_OP_DEL) { for (uint32_t x = 0; x < rpt; x++) fputc(row == 0 ? toprint(s1->v[beg1 - 1 + i + x]) : '-', f); i += rpt; }
+                else if (op == LZB_OP_INS) { for (uint32_t x = 0; x < rpt; x++) fputc(row == 0 ? '-' : toprint(s2->v[beg2 - 1 + j + x]), f); j += rpt; }
+            }
+        }
+        fputc('\n', f);
+    }
+    fputc('\n', f);
+}

@@ -154,4 +154,7 @@ GENERAL_CASES = [
     ("", "", ["--format=general-", "--chain"]),
     ("", "", ["--format=general", "--strand=minus", "K=2200"]),
     ("[2000..15000]", "[500..20000]", ["--format=general"]),
+    ("", "", ["--format=maf-"]),                                  # print_maf_align maf.c:271
+    ("", "", ["--format=maf-", "--nogapped"]),
+    ("[2000..15000]", "[500..20000]", ["--format=maf-", "--chain"]),
 ]
