@@ -404,7 +404,7 @@ def main():
                              "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None if traffic_per_hit is None else traffic_per_hit * my_hits / ext_n,
                              "traffic_source": None if traffic_per_hit is None else
-                             "dram__bytes_read+write per hit from the ncu --set full capture in profiles/ (5 Mbp pair) x hits per launch here",
+                             "dram__bytes_read+write per hit from the ncu --set full capture in profiles/ (r01_traffic.json) x hits per launch here",
                              "peak_source": peak_src,
                              "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n},
                 "wall_ms_per_step": {"resident": wall_breakdown(accs), "e2e": wall_breakdown(accs_e2e)}}
