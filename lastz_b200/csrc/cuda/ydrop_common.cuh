@@ -1,0 +1,149 @@
+/*
+ * ydrop_common.cuh -- device-side vocabulary shared by the Y-drop kernels (k_ydrop in gapped.cu,
+ * k_ydrop_warp, k_ydrop_mw): job descriptors, the device view of committed alignments, the affine
+ * max-plus map of the masked insertion chain, the bound walks over neighbouring alignments
+ * (next/prev_sweep_seg gapped_extend.c:4754-4853), active-segment stamps (build_active_seg :4989) and
+ * the warp traceback (:3847-3859).  Kept free of host/runtime code so that the kernels can also be
+ * compiled for the host block emulator (tests/warp_emu/cuda_emu.h).
+ */
+#ifndef LZB_YDROP_COMMON_CUH
+#define LZB_YDROP_COMMON_CUH
+
+enum { SEG_DIAG = 0, SEG_HORZ = 1, SEG_VERT = 2 };
+
+struct dseg { u32 b1, b2, e1, e2; int type; };
+struct segref { int al, sg; };
+struct dalign {                       /* device view of a committed alignment (galign :214-245) */
+    u32 pos1, end1;
+    int segBegin, segCount;
+    segref left1, right1, left2, right2;
+    int next, prev;                   /* obi / oed links */
+};
+
+enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_ACT = 5 };
+
+struct dp_job {
+    int reversed; u32 a1, a2, M, N;
+    s32 L0, R0;
+    segref leftSeg, rightSeg;
+    int alignList;
+    u8* tb; u32 tbLen; u32* tbRow; u32 tbRowCap; u32* ops; u32 opsCap;
+    int* act; u32 actCap;             /* 5 ints per active segment */
+    const dalign* al;                 /* alignment table snapshot this job runs against */
+    int skip;                         /* nonzero: nothing to do (the other side of a rerun) */
+    u32* dbg; u32 dbgCap;             /* LZB_DP_DEBUG: per-row {LY, colEnd, best, used} for kernel-vs-kernel diffs */
+    /* results */
+    s32 score; u32 end1, end2, nops, rows; int status; unsigned long long cells;
+};
+
+struct xf { s32 A; s32 S; int r; };   /* x -> r ? A : max(A, x + S) */
+
+__device__ __forceinline__ s32 satadd(s32 a, s32 s) { s32 v = a + s; return v < LZB_NEG_INF ? LZB_NEG_INF : v; }
+__device__ __forceinline__ xf xf_then(xf f, xf g) {      /* apply f, then g */
+    xf o;
+    if (g.r) return g;
+    o.A = max(g.A, satadd(f.A, g.S)); o.S = f.S + g.S; o.r = f.r;
+    return o;
+}
+
+#define LINK_I 1
+#define LINK_D 2
+#define LINK_IEXT 4
+#define LINK_DEXT 8
+#define F_CAND 16
+#define F_MASK 32
+
+/* next_sweep_seg / prev_sweep_seg gapped_extend.c:4754-4853 */
+__device__ s32 sweep_step(const dalign* al, const dseg* segs, int rev, int lookRight, segref* bp,
+                          u32 row, u32 a1, u32 a2) {
+    const dalign m = al[bp->al];
+    if (!rev) {
+        if (bp->sg + 1 < m.segCount) {
+            bp->sg++;
+            if (segs[m.segBegin + bp->sg].type == SEG_HORZ) bp->sg++;
+            return (s32)(segs[m.segBegin + bp->sg].b2 - a2);
+        }
+        *bp = lookRight ? m.right2 : m.left2;
+        if (bp->al < 0) return 0;
+        const dseg s = segs[al[bp->al].segBegin + bp->sg];
+        if (s.type == SEG_DIAG) return (s32)row + (s32)(s.b2 - a2) - (s32)(s.b1 - a1);
+        return (s32)(s.b2 - a2);
+    }
+    if (bp->sg - 1 >= 0) {
+        bp->sg--;
+        if (segs[m.segBegin + bp->sg].type == SEG_HORZ) bp->sg--;
+        return (s32)(a2 - segs[m.segBegin + bp->sg].e2);
+    }
+    *bp = lookRight ? m.right1 : m.left1;
+    if (bp->al < 0) return 0;
+    const dseg s = segs[al[bp->al].segBegin + bp->sg];
+    if (s.type == SEG_DIAG) return (s32)row + (s32)(a2 - s.e2) - (s32)(a1 - s.e1);
+    return (s32)(a2 - s.e2);
+}
+
+/* build_active_seg gapped_extend.c:4989-5040; act record = {al, sg, x, lastRow, type} */
+__device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u32* stamp, u32 msk,
+                          u32 row, u32 a1, u32 a2, u32 LY, u32 RY) {
+    const dseg s = segs[al[a[0]].segBegin + a[1]];
+    a[4] = s.type;
+    u32 x, lastRow;
+    if (!rev) { x = s.b2 - a2; lastRow = s.e1 - a1; } else { x = a2 - s.e2; lastRow = a1 - s.b1; }
+    a[2] = (int)x; a[3] = (int)lastRow;
+    if (s.type != SEG_HORZ) { if (x >= LY && x <= RY) stamp[x & msk] = row; }
+    else {
+        u32 hend = !rev ? s.e2 - a2 : a2 - s.b2;
+        u32 lo = x > LY ? x : LY, hi = hend < RY ? hend : RY;
+        for (u32 i = lo; i <= hi && i >= lo; i++) stamp[i & msk] = row;
+    }
+}
+
+/* traceback, gapped_extend.c:3847-3859, by one warp: lane t speculates that the path continues
+ * diagonally and looks at (r-t, c-t); a ballot finds the first non-substitution, so a run of up to
+ * 32 substitutions costs one dependent load.  Emits run-length ops (op | count<<2) in walk order. */
+__device__ u32 traceback_walk(const u8* tb, const u32* tbRow, u32 end1, u32 end2, u32* ops, u32 opsCap,
+                              u32 lane, bool* overflow) {
+    const u32 FULL = 0xFFFFFFFFu;
+    u32 nops = 0;
+    u32 r = end1, c = end2; u32 prevOp = 0;
+    u32 curOp = 0, curCnt = 0; bool ovf = false;
+    while (r >= 1 || c > 0) {
+        bool inb = (r >= lane) && (c >= lane) && ((r - lane) >= 1 || (c - lane) > 0);
+        u32 link = 0;
+        if (inb) link = tb[(u32)(tbRow[r - lane] + (c - lane))];
+        u32 op = link & 3;
+        if (lane == 0) {
+            if (prevOp == LINK_I && (link & LINK_IEXT)) op = LINK_I;
+            if (prevOp == LINK_D && (link & LINK_DEXT)) op = LINK_D;
+        }
+        /* lane t>0 assumes the step before it was a substitution, true iff all earlier lanes are
+         * substitutions; a diagonal step needs r-t >= 1 and c-t >= 1 */
+        bool isSub = inb && op == 0 && (r - lane) >= 1 && (c - lane) >= 1;
+        u32 notSub = __ballot_sync(FULL, !isSub);
+        u32 run = notSub ? (u32)(__ffs(notSub) - 1) : 32;
+        if (run > 0) {
+            if (curOp == LZB_OP_SUB) curCnt += run;
+            else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = LZB_OP_SUB; curCnt = run; }
+            r -= run; c -= run; prevOp = 0;
+            continue;
+        }
+        u32 op0 = __shfl_sync(FULL, op, 0);
+        u32 eop;
+        if (op0 == LINK_I) { c--; eop = LZB_OP_INS; }
+        else if (op0 == LINK_D) { r--; eop = LZB_OP_DEL; }
+        else { r--; c--; eop = LZB_OP_SUB; }
+        if (curOp == eop) curCnt++;
+        else { if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; } curOp = eop; curCnt = 1; }
+        prevOp = op0;
+    }
+    if (curCnt) { if (nops < opsCap) { if (lane == 0) ops[nops] = curOp | (curCnt << 2); } else ovf = true; nops++; }
+    *overflow = ovf;
+    return nops;
+}
+
+/* far edge (e1 forward, b1 reversed) and type of a bounding segment; expects al, segs, rev in scope */
+#define LOAD_BOUND(ref_, lim_, typ_) \
+    do { if ((ref_).al >= 0) { const dseg s_ = segs[al[(ref_).al].segBegin + (ref_).sg]; lim_ = rev ? s_.b1 : s_.e1; typ_ = s_.type; } } while (0)
+
+__device__ __forceinline__ u32 wg_lowmask(u32 n) { return n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u; }
+
+#endif

@@ -38,7 +38,6 @@ struct wg_out { u32 fa, la, uc, bc; s32 uv, bv, Iout; };
 
 #define WG_SCAP 1024u                  /* stamp ring (columns), >= the widest window */
 
-__device__ __forceinline__ u32 wg_lowmask(u32 n) { return n >= 32u ? 0xFFFFFFFFu : (1u << n) - 1u; }
 
 /* one row of the sweep, gapped_extend.c:3669-3774 */
 template <int K, bool MASKING>
