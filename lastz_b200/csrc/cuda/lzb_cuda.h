@@ -10,15 +10,7 @@
 #include <stdio.h>
 #include "../../../include/lastz_b200.h"
 
-typedef uint8_t  u8;
-typedef uint16_t u16;
-typedef uint32_t u32;
-typedef int32_t  s32;
-typedef uint64_t u64;
-typedef int64_t  s64;
-
-#define LZB_NEG_INF ((s32)-1932735283)      /* dna_utilities.h:138 negInfinity */
-#define LZB_MAX_CLASSES 32                  /* byte equivalence classes of the two score matrices */
+#include "lzb_types.h"
 
 int lzb_fail(const char* fmt, ...);         /* sets lzb_last_error(), returns -1 */
 
@@ -32,16 +24,6 @@ int lzb_fail(const char* fmt, ...);         /* sets lzb_last_error(), returns -1
          if (e_ != cudaSuccess) { lzb_fail("%s failed: %s (%s:%d)", #expr,                \
                                            cudaGetErrorString(e_), __FILE__, __LINE__);   \
                                   return NULL; } } while (0)
-
-/* score matrices reduced to byte classes: two bytes share a class iff their rows and columns
- * agree in BOTH scoring->sub and maskedScoring->sub, so sub[a][b] == subC[cls[a]][cls[b]] exactly */
-struct lzb_scoring_dev {
-    int  numClasses;
-    u8   cls[256];
-    s32  subC[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
-    s32  msubC[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
-    s32  gapOpen, gapExtend;
-};
 
 struct lzb_ctx {
     int device;
