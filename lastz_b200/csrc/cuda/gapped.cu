@@ -749,10 +749,6 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         gc->h_stage = gc->d_stage = NULL; gc->stageWords = GX_STAGE_WORDS; gc->epochUsed = 0;
         c->gappedCache = gc;
         gc->upStream = c->stream;
-        if (getenv("LZB_UPLOAD_PRIO") && atoi(getenv("LZB_UPLOAD_PRIO"))) {   /* experiment: a high-priority stream of its own for the table uploads */
-            int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            CUDA_TRY(cudaStreamCreateWithPriority(&gc->upStream, cudaStreamNonBlocking, hi));
-        }
         CUDA_TRY(cudaHostAlloc(&gc->h_stage, (size_t)gc->stageWords * 4, cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&gc->d_stage, gc->h_stage, 0));
         gc->segsCap = 16u << 20;                            /* 320 MB up front: regrowing has to drain every lane */
@@ -774,8 +770,6 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     int firstMode = 0;
     { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3) firstMode = mdv; } }
     if (cenv) firstMode = 2;                                   /* an explicit ring size means the shared-memory kernel */
-    int dpShape = 84;                                          /* columns per thread, warps per DP of the register kernel */
-    { const char* e = getenv("LZB_DP_SHAPE"); if (e && (atoi(e) == 48 || atoi(e) == 64)) dpShape = atoi(e); }
     { const char* e = getenv("LZB_DP_THREADS"); if (e && atoi(e) == 128) dpThreads = 128; }
 
     const bool trace = getenv("LZB_GAP_TRACE") != NULL;
@@ -881,11 +875,9 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             }
         }
         if (laneEvents) CUDA_TRY(cudaEventRecord(ln.evA, ln.stream)); else ln.launchedAt = now();
-        if (ln.mode == 0 && dpShape == 48)                   /* experiment: 8 warps x 4 columns, same 1024-column window */
-            k_ydrop_mw<4, 8><<<2, 256, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
-        else if (ln.mode == 0 && dpShape == 64)              /* experiment: 4 warps x 6 columns, 768-column window; DP_RING escalates to mode 4 */
-            k_ydrop_mw<6, 4><<<2, 128, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
-        else if (ln.mode == 0 || ln.mode == 4)
+        /* other shapes of the register kernel were measured and lost on the 50 Mbp pair (DP-kernel wait 1.81 s):
+         * 8 warps x 4 columns 2.13 s, 4 warps x 6 columns with escalation 3.05 s (gpurun round 12) */
+        if (ln.mode == 0)
             k_ydrop_mw<8, 4><<<2, 128, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
         else if (ln.mode == 1)
             k_ydrop_warp<16><<<2, 32, 0, ln.stream>>>(ln.d_jobs, gc->d_segs, t->d_cls, q->d_cls, len1, len2, c->d_sc, P->yDrop, P->trimToPeak);
@@ -941,7 +933,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             if (J.skip) continue;                            /* side finished in an earlier pass */
             bool again = false;
             if (J.status == DP_RING) {
-                if (ln.mode == 3) return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ln.ring);
+                if (ln.mode >= 3) return lzb_fail("Y-drop band wider than %u columns; lower --ydrop", ln.ring);
                 again = true;
             } else if (J.status == DP_TBROW) {
                 cudaFree(ln.tbRow[side]); ln.tbRowCap[side] = ln.tbRowCap[side] * 4 < tbLen ? ln.tbRowCap[side] * 4 : tbLen + 8;
@@ -974,7 +966,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
                                ln.h_jobs[0].status, ln.h_jobs[1].status, ln.h_jobs[0].rows, ln.h_jobs[1].rows, ms, ln.mode);
             bool ringGrow = false;
             for (int side = 0; side < 2; side++) if (ln.h_jobs[side].status == DP_RING) ringGrow = true;
-            if (ringGrow) ln.mode = (ln.mode == 0 && dpShape == 64) ? 4 : (ln.mode < 2 || ln.mode == 4) ? 2 : ln.mode + 1;
+            if (ringGrow) ln.mode = ln.mode < 2 ? 2 : ln.mode + 1;
             /* rerun with the neighbours it was started with; the (possibly newer) alignment table is a
              * superset, and validation still uses the ORIGINAL snapshot, so any difference is caught */
             return launch(ln, redo);
