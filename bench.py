@@ -240,9 +240,18 @@ def main():
     import torch.distributed as dist
     from lastz_b200 import Engine, default_scoring, parse_seed, revcomp
 
+    # LZB_BENCH_DEVICE=cpu exists for tests/test_bench_dryrun.py only: it runs this very control flow (sharding,
+    # collectives, aggregation, the JSON line) with world_size 2 over gloo, the test substituting its own engine.
+    # The product engine needs a GPU; nothing here falls back to anything.
+    on_gpu = os.environ.get("LZB_BENCH_DEVICE", "cuda") != "cpu"
+    dev = torch.device("cuda", local) if on_gpu else torch.device("cpu")
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+        if on_gpu:
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group("gloo")
+    if on_gpu:
+        torch.cuda.set_device(local)
     target, query = synth_pair(L)
     lo, hi = rank * len(query) // world, (rank + 1) * len(query) // world
     shard = query[lo:hi]
@@ -256,14 +265,15 @@ def main():
     index_s = time.perf_counter() - t0
 
     def sync():
-        torch.cuda.synchronize()
+        if on_gpu:
+            torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
     def gather_segments(tables):
         """the one exchange step: every rank's HSP table to all ranks over NCCL"""
         from lastz_b200.sharding import gather_segment_tables
-        parts = gather_segment_tables(np.concatenate(tables), torch.device("cuda", local))
+        parts = gather_segment_tables(np.concatenate(tables), dev)
         return sum(len(p) for p in parts)
 
     def step(resident, handles=None):
@@ -317,7 +327,7 @@ def main():
         if handles:
             for h in handles:
                 eng.free_query(h)
-        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item()), accs, launches
@@ -330,20 +340,20 @@ def main():
     dt_e2e, accs_e2e, _ = timed(False)
 
     def total(key, accs_):
-        v = torch.tensor([float(sum(a[key] for a in accs_))], device="cuda", dtype=torch.float64)
+        v = torch.tensor([float(sum(a[key] for a in accs_))], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(v, op=dist.ReduceOp.SUM)
         return float(v.item())
 
     def worst(key, accs_):
-        v = torch.tensor([float(sum(a[key] for a in accs_))], device="cuda", dtype=torch.float64)
+        v = torch.tensor([float(sum(a[key] for a in accs_))], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(v, op=dist.ReduceOp.MAX)
         return float(v.item())
 
     hits, cells = total("hits", accs), total("cells", accs)
     seed_s, gap_s = worst("seed_s", accs), worst("gap_s", accs)
-    total_l = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+    total_l = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_l, op=dist.ReduceOp.SUM)
     # roofline of the dominant seed-stage kernel (k_extend), this rank
