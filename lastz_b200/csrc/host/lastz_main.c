@@ -110,7 +110,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "E=")) { o->E = atoi(v); o->haveE = 1; }
         else if (starts(a, "--gap=")) { if (sscanf(v, "%d,%d", &o->O, &o->E) != 2) lzb_die("can't understand %s", a); o->haveO = o->haveE = 1; }
         else if (starts(a, "--scores=") || starts(a, "Q=")) o->scoresFile = v;
-        else if (starts(a, "--segments=")) o->segmentsFile = v;
+        else if (starts(a, "--segments=") || starts(a, "--anchors=")) o->segmentsFile = v;   /* --anchors: the older spelling, lastz.c:5855 */
         else if (starts(a, "--allocate:traceback=") || starts(a, "--traceback=")) o->tracebackBytes = (uint32_t)unitized(v);
         else if (starts(a, "--output=")) o->outputFile = v;
         else if (!strcmp(a, "--format=lav")) o->format = 0;

@@ -25,6 +25,7 @@ struct lzb_seqfile {
     uint32_t start, end;        /* 1-based inclusive limits, 0 = none */
     int unmask;
     uint32_t contig;            /* sequences delivered so far */
+    uint32_t lastIx;            /* 2bit: index of the sequence delivered last */
     /* 2bit index */
     uint32_t n2; char** names; uint32_t* offsets;
     int pendingCh;
@@ -165,6 +166,7 @@ static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
         ix = sf->contig;
         if (ix >= sf->n2) return 0;
     }
+    sf->lastIx = ix;
     fseek(sf->f, (long)sf->offsets[ix], SEEK_SET);
     uint32_t dna = rd4(sf);
     uint32_t nb = rd4(sf);
@@ -195,7 +197,7 @@ int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
     int ok = sf->is2bit ? next_2bit(sf, out) : next_fasta(sf, out);
     if (!ok) return 0;
     sf->contig++;
-    out->contig = sf->is2bit && sf->contigName ? 1 : sf->contig;
+    out->contig = sf->is2bit && sf->contigName ? sf->lastIx + 1 : sf->contig;   /* ordinal within the file (sequences.c:3677ff) */
     out->filename = dupstr(sf->filename);
     out->revCompFlags = LZB_RCF_FORWARD;
     return 1;

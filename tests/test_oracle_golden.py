@@ -33,6 +33,23 @@ def test_oracle_reproduces_golden_lav(golden, opts):
     assert norm(out) == norm(want)
 
 
+AGLOBIN = os.path.join(GOLDEN, "aglobin.2bit")
+
+
+def test_oracle_subrange_golden():
+    """base_test_subrange (Makefile:534): 2bit contigs with [a,b] and [a#len] subranges; contig ordinals in the s stanza."""
+    out, _ = run_cli(ORACLE_CLI, [AGLOBIN + "/human[10000,60000]", AGLOBIN + "/cow[15000#40000]"])
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.subrange.lav")).read())
+
+
+def test_oracle_anchors_golden():
+    """base_test_anchors (Makefile:510): gapped stage from an external anchors file, MAF blocks out."""
+    out, _ = run_cli(ORACLE_CLI, [AGLOBIN + "/human", AGLOBIN + "/cow", "C=0", "--format=maf-",
+                                  "--anchors=" + os.path.join(GOLDEN, "base_test.anchors.anchors")])
+    assert out == open(os.path.join(GOLDEN, "base_test.anchors.maf")).read()
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
