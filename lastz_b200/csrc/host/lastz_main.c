@@ -127,7 +127,7 @@ static void parse_options(options* o, int argc, char** argv) {
     }
     if (!o->targetSpec) lzb_die("You must specify a target file");
     if (o->selfCompare && !o->querySpec) o->querySpec = o->targetSpec;
-    if (!o->querySpec) lzb_die("You must specify a query file (reading from stdin is not supported)");
+    if (!o->querySpec) o->querySpec = "(stdin)";                    /* lastz.c:8762: no query file => read it from stdin */
 }
 
 /* read_segment_table segment.c:456: rows name1 start1 end1 name2 start2 end2 strand [score] */

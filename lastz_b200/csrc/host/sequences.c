@@ -73,6 +73,7 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
     char* tb = strstr(s, ".2bit/");
     if (tb) { sf->contigName = dupstr(tb + 6); tb[5] = 0; }
     sf->filename = s;
+    if (!strcmp(s, "(stdin)")) { sf->f = stdin; return sf; }    /* the query may come from stdin, as FASTA (lastz.c:8762ff) */
     sf->f = fopen(s, "rb");
     if (!sf->f) lzb_die("fopen_or_die failed to open \"%s\" for \"rb\"", s);
     unsigned char magic[4];

@@ -50,6 +50,24 @@ def test_oracle_anchors_golden():
     assert out == open(os.path.join(GOLDEN, "base_test.anchors.maf")).read()
 
 
+def test_oracle_2bit_query_golden():
+    """base_test_2bit2 (Makefile:441): a 2bit file as the query, same alignments as the FASTA run."""
+    out, _ = run_cli(ORACLE_CLI, [CAT, os.path.join(GOLDEN, "pseudopig.2bit"), "C=2", "W=8", "T=0"])
+    out = out.replace("pig", "> pig").replace("do> pig.2bit", "dopig.fa")          # the Makefile's two seds
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.extended.lav")).read())
+
+
+def test_oracle_query_from_stdin_golden():
+    """base_test_stdin2 (Makefile:402): no query file => the query is read from stdin."""
+    import subprocess
+    p = subprocess.run([ORACLE_CLI, CAT, "C=3", "W=8", "T=0"], stdin=open(PIG, "rb"), capture_output=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = p.stdout.decode().replace("(stdin)", "../test_data/pseudopig.fa")
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.hsp.lav")).read())
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
