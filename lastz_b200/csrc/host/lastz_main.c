@@ -113,7 +113,10 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--segments=") || starts(a, "--anchors=")) o->segmentsFile = v;   /* --anchors: the older spelling, lastz.c:5855 */
         else if (starts(a, "--allocate:traceback=") || starts(a, "--traceback=")) o->tracebackBytes = (uint32_t)unitized(v);
         else if (starts(a, "--output=")) o->outputFile = v;
-        else if (!strcmp(a, "--format=lav")) o->format = 0;
+        else if (!strcmp(a, "--format=lav") || !strcmp(a, "--lav")) o->format = 0;
+        else if (!strcmp(a, "--maf-")) o->format = 4;
+        else if (!strcmp(a, "--general")) o->format = 2;
+        else if (!strcmp(a, "--general-")) o->format = 3;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
         else if (!strcmp(a, "--format=general")) o->format = 2;          /* default fields, genpaf.h:117 */
         else if (!strcmp(a, "--format=general-")) o->format = 3;         /* ... without the header line */

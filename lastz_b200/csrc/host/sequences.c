@@ -29,6 +29,8 @@ struct lzb_seqfile {
     /* 2bit index */
     uint32_t n2; char** names; uint32_t* offsets;
     int pendingCh;
+    /* [subset=<file>]: the names of the sequences to deliver (sequences.c "contigs of interest") */
+    char** subset; uint32_t nsubset, subsetNext;
 };
 
 static char* dupstr(const char* s) { char* d = malloc(strlen(s) + 1); strcpy(d, s); return d; }
@@ -53,6 +55,20 @@ static void parse_actions(lzb_seqfile* sf, char* act) {
         else {
             for (char* p = strtok(tok, ","); p; p = strtok(NULL, ",")) {
                 if (!strcmp(p, "unmask")) sf->unmask = 1;
+                else if (!strncmp(p, "subset=", 7)) {
+                    FILE* nf = fopen(p + 7, "rt");
+                    if (!nf) lzb_die("fopen_or_die failed to open \"%s\" for \"rt\"", p + 7);
+                    char line[1024];
+                    while (fgets(line, sizeof line, nf)) {
+                        char* w = line; while (*w == ' ' || *w == '\t') w++;
+                        size_t n = strcspn(w, " \t\r\n");
+                        if (n == 0 || *w == '#') continue;
+                        w[n] = 0;
+                        sf->subset = realloc(sf->subset, (sf->nsubset + 1) * sizeof(char*));
+                        sf->subset[sf->nsubset++] = dupstr(w);
+                    }
+                    fclose(nf);
+                }
                 else if (sscanf(p, "%u..%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = b; }
                 else if (sscanf(p, "%u#%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = a + b - 1; }
                 else lzb_die("sequence action \"%s\" is not supported by lastz_b200 (file %s)", p, sf->filename);
@@ -163,6 +179,11 @@ static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
         if (sf->contig > 0) return 0;
         for (ix = 0; ix < sf->n2; ix++) if (!strcmp(sf->names[ix], sf->contigName)) break;
         if (ix == sf->n2) lzb_die("2bit file %s doesn't contain %s", sf->filename, sf->contigName);
+    } else if (sf->subset) {
+        if (sf->subsetNext >= sf->nsubset) return 0;
+        const char* want = sf->subset[sf->subsetNext++];
+        for (ix = 0; ix < sf->n2; ix++) if (!strcmp(sf->names[ix], want)) break;
+        if (ix == sf->n2) lzb_die("2bit file %s doesn't contain %s", sf->filename, want);
     } else {
         ix = sf->contig;
         if (ix >= sf->n2) return 0;
@@ -195,10 +216,17 @@ static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
 
 int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
     memset(out, 0, sizeof *out);
-    int ok = sf->is2bit ? next_2bit(sf, out) : next_fasta(sf, out);
-    if (!ok) return 0;
-    sf->contig++;
-    out->contig = sf->is2bit && sf->contigName ? sf->lastIx + 1 : sf->contig;   /* ordinal within the file (sequences.c:3677ff) */
+    for (;;) {
+        int ok = sf->is2bit ? next_2bit(sf, out) : next_fasta(sf, out);
+        if (!ok) return 0;
+        sf->contig++;
+        if (sf->is2bit || !sf->subset) break;
+        int wanted = 0;                                  /* FASTA: deliver the named sequences, skip the others */
+        for (uint32_t k = 0; k < sf->nsubset && !wanted; k++) wanted = !strcmp(sf->subset[k], out->shortHeader);
+        if (wanted) break;
+        lzb_seq_free(out); memset(out, 0, sizeof *out);
+    }
+    out->contig = sf->is2bit && (sf->contigName || sf->subset) ? sf->lastIx + 1 : sf->contig;   /* ordinal within the file (sequences.c:3677ff) */
     out->filename = dupstr(sf->filename);
     out->revCompFlags = LZB_RCF_FORWARD;
     return 1;

@@ -68,6 +68,24 @@ def test_oracle_query_from_stdin_golden():
     assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.hsp.lav")).read())
 
 
+def test_oracle_2bit_target_golden():
+    """base_test_2bit1 (Makefile:427): one contig of a 2bit file as the TARGET."""
+    out, _ = run_cli(ORACLE_CLI, [os.path.join(GOLDEN, "pseudopig.2bit") + "/pig2", CAT, "C=2", "W=8", "T=0"])
+    import re
+    out = out.replace("pig", "> pig").replace("do> pig.2bit", "dopig2.fa")
+    out = re.sub(r"(dopig2.*) 0 2", r"\1 0 1", out)                                # the Makefile's three seds
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.pig_cat.lav")).read())
+
+
+@pytest.mark.parametrize("query", ["shorties.fa", "shorties.2bit"])
+def test_oracle_contigs_of_interest_golden(query):
+    """base_test_coi (Makefile:553): [subset=<names file>] on a multi-sequence FASTA / 2bit query, --maf- out."""
+    names = os.path.join(GOLDEN, "shorties.names")
+    out, _ = run_cli(ORACLE_CLI, [AGLOBIN + "/human", os.path.join(GOLDEN, query) + f"[subset={names}]", "K=3000", "--maf-"])
+    assert out == open(os.path.join(GOLDEN, "base_test.coi.maf")).read()
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
