@@ -21,7 +21,7 @@ typedef struct {
     uint32_t tracebackBytes;
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
-    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf- */
+    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt */
     int device, showStats, speculation;
     int chainDiag, chainAnti;
     char args[4096];
@@ -115,6 +115,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--output=")) o->outputFile = v;
         else if (!strcmp(a, "--format=lav") || !strcmp(a, "--lav")) o->format = 0;
         else if (!strcmp(a, "--maf-")) o->format = 4;
+        else if (!strcmp(a, "--format=axt") || !strcmp(a, "--axt")) o->format = 5;
         else if (!strcmp(a, "--general")) o->format = 2;
         else if (!strcmp(a, "--general-")) o->format = 3;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
@@ -187,6 +188,8 @@ int main(int argc, char** argv) {
     if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, o.K, o.L);
     else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
     else if (o.format == 2) lzb_general_header(out);
+    else if (o.format == 5) lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, o.K, o.L, o.X, o.Y);
+    uint64_t axtNumber = 0;
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
     uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
@@ -247,12 +250,12 @@ int main(int argc, char** argv) {
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_match(out, &target, &query, &segs[k]);
-                    } else if (o.format == 4) {                  /* an HSP is an alignment with one run of substitutions */
+                    } else if (o.format == 4 || o.format == 5) { /* an HSP is an alignment with one run of substitutions */
                         lzb_editscript es = { 1, 1, LZB_OP_SUB, { LZB_OP_SUB | (segs[k].length << 2) } };
                         lzb_alignel al; memset(&al, 0, sizeof al);
                         al.beg1 = segs[k].pos1 + 1; al.end1 = segs[k].pos1 + segs[k].length; al.beg2 = segs[k].pos2 + 1; al.end2 = segs[k].pos2 + segs[k].length;
                         al.s = segs[k].s; al.script = &es;
-                        lzb_maf_align(out, &target, &query, &al);
+                        if (o.format == 4) lzb_maf_align(out, &target, &query, &al); else lzb_axt_align(out, &target, &query, &al, &axtNumber);
                     } else if (o.format >= 2) lzb_general_match(out, &target, &query, &segs[k]);
                 }
                 if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
@@ -275,6 +278,7 @@ int main(int argc, char** argv) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_align(out, &target, &query, a);
                     } else if (o.format == 4) lzb_maf_align(out, &target, &query, a);
+                    else if (o.format == 5) lzb_axt_align(out, &target, &query, a, &axtNumber);
                     else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
                     else lzb_die("--format=segments needs --nogapped");
                 }

@@ -77,6 +77,8 @@ void lzb_general_header(FILE*);
 void lzb_general_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
 void lzb_general_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
 void lzb_maf_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);    /* maf.c:271, --format=maf- */
+void lzb_axt_header(FILE*, const char* prog, const char* args, const lzb_scoreset*, int32_t K, int32_t L, int32_t X, int32_t Y);
+void lzb_axt_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, uint64_t* number);   /* axt.c:96, --format=axt */
 
 /* mirror.c -- mirror_alignments lastz.c:4229 (--self with gapped extension) */
 lzb_alignel* lzb_mirror_alignments(lzb_alignel* list, const lzb_seq* seq1, const lzb_seq* seq2, const lzb_scoreset* ss);

@@ -157,6 +157,26 @@ void lzb_general_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_
 static int digits_of(uint32_t a, uint32_t b) { uint32_t m = a > b ? a : b; int d = 1; while (m >= 10) { m /= 10; d++; } return d; }
 static char toprint(uint8_t c) { return (c >= 0x20 && c < 0x7F) ? (char)c : '*'; }      /* dna_toprint dna_utilities.h:305 */
 
+/* one text row of an alignment (row 0: sequence 1, row 1: sequence 2), gaps as '-' (maf.c:392-470, axt.c:196-253) */
+static void align_text_row(FILE* f, int row, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a) {
+    const lzb_editscript* sc = a->script;
+    uint32_t beg1 = a->beg1, beg2 = a->beg2, height = a->end1 - beg1 + 1, width = a->end2 - beg2 + 1, k = 0;
+    for (uint32_t i = 0, j = 0; i < height || j < width;) {
+        uint32_t run = 0;
+        while (k < sc->len && (sc->op[k] & 3) == LZB_OP_SUB) { run += sc->op[k] >> 2; k++; }
+        const uint8_t* p = (row == 0 ? s1->v + beg1 - 1 + i : s2->v + beg2 - 1 + j);
+        for (uint32_t x = 0; x < run; x++) fputc(toprint(p[x]), f);
+        i += run; j += run;
+        if (i < height || j < width) {
+            if (k >= sc->len) break;
+            uint32_t op = sc->op[k] & 3, rpt = sc->op[k] >> 2; k++;
+            if (op == LZB_OP_DEL) { for (uint32_t x = 0; x < rpt; x++) fputc(row == 0 ? toprint(s1->v[beg1 - 1 + i + x]) : '-', f); i += rpt; }
+            else if (op == LZB_OP_INS) { for (uint32_t x = 0; x < rpt; x++) fputc(row == 0 ? '-' : toprint(s2->v[beg2 - 1 + j + x]), f); j += rpt; }
+        }
+    }
+    fputc('\n', f);
+}
+
 void lzb_maf_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a) {
     const char* name1 = (s1->shortHeader && s1->shortHeader[0]) ? s1->shortHeader : "seq1";
     const char* name2 = (s2->shortHeader && s2->shortHeader[0]) ? s2->shortHeader : "seq2";
@@ -171,26 +191,39 @@ void lzb_maf_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alig
     int len1 = (int)(strlen(name1) + strlen(suff1)), len2 = (int)(strlen(name2) + strlen(suff2));
     int nameW = len1 >= len2 ? len1 : len2;
     int startW = digits_of(start1, start2), endW = digits_of(height, width), lenW = digits_of(s1->trueLen, s2->trueLen);
-    const lzb_editscript* sc = a->script;
     fprintf(f, "a score=%d\n", a->s);
     for (int row = 0; row < 2; row++) {
         if (row == 0) fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name1, suff1, nameW + 1 - len1, " ", startW, start1 - 1, endW, height, strand1, lenW, s1->trueLen);
         else fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name2, suff2, nameW + 1 - len2, " ", startW, start2 - 1, endW, width, strand2, lenW, s2->trueLen);
-        uint32_t k = 0;
-        for (uint32_t i = 0, j = 0; i < height || j < width;) {
-            uint32_t run = 0;
-            while (k < sc->len && (sc->op[k] & 3) == LZB_OP_SUB) { run += sc->op[k] >> 2; k++; }
-            const uint8_t* p = (row == 0 ? s1->v + beg1 - 1 + i : s2->v + beg2 - 1 + j);
-            for (uint32_t x = 0; x < run; x++) fputc(toprint(p[x]), f);
-            i += run; j += run;
-            if (i < height || j < width) {
-                if (k >= sc->len) break;
-                uint32_t op = sc->op[k] & 3, rpt = sc->op[k] >> 2; k++;
-                if (op == LZB_OP_DEL) { for (uint32_t x = 0; x < rpt; x++) fputc(row == 0 ? toprint(s1->v[beg1 - 1 + i + x]) : '-', f); i += rpt; }
-                else if (op == LZB_OP_INS) { for (uint32_t x = 0; x < rpt; x++) fputc(row == 0 ? '-' : toprint(s2->v[beg2 - 1 + j + x]), f); j += rpt; }
-            }
-        }
-        fputc('\n', f);
+        align_text_row(f, row, s1, s2, a);
     }
+    fputc('\n', f);
+}
+
+/* ---- --format=axt, print_axt_align axt.c:96-255 (unpartitioned sequences).  The block number runs over the
+ * whole output (axtAlignmentNumber).  The comment header carries the same parameters as the reference's. ---- */
+void lzb_axt_header(FILE* f, const char* prog, const char* args, const lzb_scoreset* ss, int32_t K, int32_t L, int32_t X, int32_t Y) {
+    static const char acgt[4] = { 'A', 'C', 'G', 'T' };
+    fprintf(f, "# %s %s\n#\n# hsp_threshold      = %d\n# gapped_threshold   = %d\n# x_drop             = %d\n# y_drop             = %d\n"
+               "# gap_open_penalty   = %d\n# gap_extend_penalty = %d\n", prog, args, K, L, X, Y, ss->gapOpen, ss->gapExtend);
+    fprintf(f, "#        A    C    G    T\n");
+    for (int r = 0; r < 4; r++) {
+        fprintf(f, "#   %c", acgt[r]);
+        for (int c = 0; c < 4; c++) fprintf(f, " %4d", ss->sub[(uint32_t)acgt[r] * 256 + acgt[c]]);
+        fprintf(f, "\n");
+    }
+}
+
+void lzb_axt_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, uint64_t* number) {
+    const char* name1 = (s1->shortHeader && s1->shortHeader[0]) ? s1->shortHeader : "seq1";
+    const char* name2 = (s2->shortHeader && s2->shortHeader[0]) ? s2->shortHeader : "seq2";
+    uint32_t height = a->end1 - a->beg1 + 1, width = a->end2 - a->beg2 + 1;
+    uint32_t start1 = a->beg1 - 1 + s1->startLoc, start2; char strand2;
+    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = a->beg2 - 1 + s2->startLoc; strand2 = '+'; }
+    else { start2 = a->beg2 - 1 + s2->trueLen + 2 - (s2->startLoc + s2->len); strand2 = '-'; }
+    fprintf(f, "%llu %s %u %u %s %u %u %c %d\n", (unsigned long long)(*number)++, name1, start1, start1 + height - 1,
+            name2, start2, start2 + width - 1, strand2, a->s);
+    align_text_row(f, 0, s1, s2, a);
+    align_text_row(f, 1, s1, s2, a);
     fputc('\n', f);
 }

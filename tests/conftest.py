@@ -157,4 +157,6 @@ GENERAL_CASES = [
     ("", "", ["--format=maf-"]),                                  # print_maf_align maf.c:271
     ("", "", ["--format=maf-", "--nogapped"]),
     ("[2000..15000]", "[500..20000]", ["--format=maf-", "--chain"]),
+    ("", "", ["--format=axt"]),                                   # print_axt_align axt.c:96, header included
+    ("", "[500..20000]", ["--format=axt", "--nogapped"]),
 ]

@@ -86,6 +86,13 @@ def test_oracle_contigs_of_interest_golden(query):
     assert out == open(os.path.join(GOLDEN, "base_test.coi.maf")).read()
 
 
+def test_oracle_axt_golden():
+    """base_test_axt (Makefile:340); comment lines are not compared (tools/axt_compare.py:132)."""
+    out, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--format=axt"])
+    body = lambda t: [l for l in t.splitlines() if not l.startswith("#")]
+    assert body(out) == body(open(os.path.join(GOLDEN, "base_test.default.axt")).read())
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
