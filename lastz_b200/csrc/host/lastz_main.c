@@ -22,7 +22,7 @@ typedef struct {
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt */
-    int device, showStats, speculation;
+    int device, showStats, speculation, mafHeader;
     int chainDiag, chainAnti;
     char args[4096];
 } options;
@@ -116,6 +116,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--format=lav") || !strcmp(a, "--lav")) o->format = 0;
         else if (!strcmp(a, "--maf-")) o->format = 4;
         else if (!strcmp(a, "--format=axt") || !strcmp(a, "--axt")) o->format = 5;
+        else if (!strcmp(a, "--format=maf") || !strcmp(a, "--maf")) { o->format = 4; o->mafHeader = 1; }
         else if (!strcmp(a, "--general")) o->format = 2;
         else if (!strcmp(a, "--general-")) o->format = 3;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
@@ -189,6 +190,10 @@ int main(int argc, char** argv) {
     else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
     else if (o.format == 2) lzb_general_header(out);
     else if (o.format == 5) lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, o.K, o.L, o.X, o.Y);
+    else if (o.format == 4 && o.mafHeader) {                     /* maf.c:96-130: version line + the same parameter comments */
+        fprintf(out, "##maf version=1 scoring=lastz.v1.04.58\n");
+        lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, o.K, o.L, o.X, o.Y);
+    }
     uint64_t axtNumber = 0;
 
     lzb_seed_stats sst; lzb_gapped_stats gst;

@@ -159,4 +159,5 @@ GENERAL_CASES = [
     ("[2000..15000]", "[500..20000]", ["--format=maf-", "--chain"]),
     ("", "", ["--format=axt"]),                                   # print_axt_align axt.c:96, header included
     ("", "[500..20000]", ["--format=axt", "--nogapped"]),
+    ("", "", ["--format=maf", "--chain", "Y=5000"]),              # MAF with the parameter header (maf.c:96)
 ]
