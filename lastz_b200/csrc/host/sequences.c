@@ -21,7 +21,7 @@ void lzb_die(const char* fmt, ...) {
 struct lzb_seqfile {
     char* filename; char* contigName;
     FILE* f;
-    int is2bit, bigEndian;
+    int is2bit, bigEndian, isNib;
     uint32_t start, end;        /* 1-based inclusive limits, 0 = none */
     int unmask;
     uint32_t contig;            /* sequences delivered so far */
@@ -107,6 +107,8 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
             if (fread(sf->names[i], 1, (size_t)nl, sf->f) != (size_t)nl) lzb_die("bad 2bit index in %s", s);
             sf->offsets[i] = rd4(sf);
         }
+    } else if (be == 0x6BE93D3Au || le == 0x6BE93D3Au) {   /* nib: nibMagicBig / nibMagicLittle sequences.c:635 */
+        sf->isNib = 1; sf->bigEndian = (be == 0x6BE93D3Au);
     } else {
         rewind(sf->f);
     }
@@ -214,10 +216,30 @@ static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
     return 1;
 }
 
+/* load_nib_sequence sequences.c:3418-3560: length, then two bases per byte, high nybble first;
+ * nybbles 0..4 = T C A G N, bit 3 = soft mask (lower case), everything else X */
+static int next_nib(lzb_seqfile* sf, lzb_seq* out) {
+    if (sf->contig > 0) return 0;
+    uint32_t length = rd4(sf);
+    if (length == 0 || length == 0xFFFFFFFFu) lzb_die("bad nib length in %s (%08X)", sf->filename, length);
+    size_t nb = ((size_t)length + 1) / 2;
+    uint8_t* packed = malloc(nb + 1);
+    if (fread(packed, 1, nb, sf->f) != nb) lzb_die("premature end of file in %s", sf->filename);
+    static const char code[17] = "TCAGNXXXtcagnxxx";
+    uint8_t* v = malloc((size_t)length + 1);
+    for (uint32_t i = 0; i < length; i++) v[i] = (uint8_t)code[(i & 1) ? (packed[i >> 1] & 15) : (packed[i >> 1] >> 4)];
+    free(packed);
+    apply_limits(sf, out, v, length);
+    char hdr[1200];
+    snprintf(hdr, sizeof hdr, "%s:%u-%u", sf->filename, out->startLoc, out->startLoc + out->len - 1);
+    out->header = dupstr(hdr); out->shortHeader = short_header(hdr);
+    return 1;
+}
+
 int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
     memset(out, 0, sizeof *out);
     for (;;) {
-        int ok = sf->is2bit ? next_2bit(sf, out) : next_fasta(sf, out);
+        int ok = sf->is2bit ? next_2bit(sf, out) : sf->isNib ? next_nib(sf, out) : next_fasta(sf, out);
         if (!ok) return 0;
         sf->contig++;
         if (sf->is2bit || !sf->subset) break;

@@ -93,6 +93,15 @@ def test_oracle_axt_golden():
     assert body(out) == body(open(os.path.join(GOLDEN, "base_test.default.axt")).read())
 
 
+def test_oracle_nib_target_golden():
+    """base_test_nib1 (Makefile:414): a .nib file as the target (header = file:start-end)."""
+    import re
+    out, _ = run_cli(ORACLE_CLI, [os.path.join(GOLDEN, "pseudopig2.nib"), CAT, "C=2", "W=8", "T=0"])
+    out = re.sub(r'"[^"]*\.nib:[^"]*"', '"> pig2"', out).replace(".nib", ".fa")          # the Makefile's two seds
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.pig_cat.lav")).read())
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
