@@ -23,6 +23,7 @@ typedef struct {
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt */
     int device, showStats, speculation, mafHeader;
+    int nIsAmbiguous; int32_t ambiMatch, ambiMismatch;     /* --ambiguous=n[,[<match>,]<penalty>] lastz.c:5767-5852 */
     int chainDiag, chainAnti;
     char args[4096];
 } options;
@@ -98,6 +99,13 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--chain")) o->chain = 1;
         else if (starts(a, "--chain=")) { o->chain = 1; if (sscanf(v, "%d,%d", &o->chainDiag, &o->chainAnti) != 2) lzb_die("can't understand %s", a); }
         else if (!strcmp(a, "--nochain")) o->chain = 0;
+        else if (!strcmp(a, "--ambiguous=n") || !strcmp(a, "--ambiguousn") || !strcmp(a, "--ambig=n")) o->nIsAmbiguous = 1;
+        else if (starts(a, "--ambiguous=n,") || starts(a, "--ambig=n,")) {
+            const char* p1 = strchr(a, ',') + 1; const char* p2 = strchr(p1, ',');
+            o->nIsAmbiguous = 1;
+            if (p2) { o->ambiMatch = atoi(p1); o->ambiMismatch = atoi(p2 + 1); } else { o->ambiMatch = 0; o->ambiMismatch = atoi(p1); }
+            if (o->ambiMismatch < 0) lzb_die("penalty for --ambiguous=n must be non-negative");
+        }
         else if (!strcmp(a, "--noentropy")) o->entropy = 0;
         else if (!strcmp(a, "--entropy")) o->entropy = 1;
         else if (!strcmp(a, "--allgappedbounds")) o->allBounds = 1;
@@ -164,6 +172,18 @@ int main(int argc, char** argv) {
     if (o.scoresFile) lzb_scores_read_file(&ss, o.scoresFile); else lzb_scores_default(&ss);
     if (o.haveO) ss.gapOpen = o.O;
     if (o.haveE) ss.gapExtend = o.E;
+    if (o.nIsAmbiguous) {                                        /* ambiguate_n dna_utilities.c:1544 on both matrices (lastz.c:9424-9429) */
+        int32_t* mats[2] = { ss.sub, ss.masked };
+        for (int m = 0; m < 2; m++) {
+            int32_t* sub = mats[m];
+            const char* ns = "Nn";
+            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) sub[(uint32_t)ns[i] * 256 + ns[j]] = o.ambiMatch;
+            for (const char* c = "ACGT"; *c; c++) for (int lc = 0; lc < 2; lc++) {
+                int ch = lc ? *c + 32 : *c;
+                for (int i = 0; i < 2; i++) { sub[(uint32_t)ch * 256 + ns[i]] = -o.ambiMismatch; sub[(uint32_t)ns[i] * 256 + ch] = -o.ambiMismatch; }
+            }
+        }
+    }
     if (!o.haveK) o.K = ss.hspThresholdSet ? ss.hspThreshold : 3000;
     if (o.gfExtend == LZB_GFEX_NONE && !o.haveK) o.K = 0;          /* lastz.c:8984-9010 */
     if (!o.haveX) o.X = ss.xDropSet ? ss.xDrop : 10 * ss.sub['A' * 256 + 'A'];

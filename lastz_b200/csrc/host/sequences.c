@@ -31,6 +31,8 @@ struct lzb_seqfile {
     int pendingCh;
     /* [subset=<file>]: the names of the sequences to deliver (sequences.c "contigs of interest") */
     char** subset; uint32_t nsubset, subsetNext;
+    /* [nmask=<file>] / [xmask=<file>] / [softmask=<file>]: intervals to overwrite (mask_sequence sequences.c:6973) */
+    char* maskFile[4]; int maskChar[4]; int nmasks;
 };
 
 static char* dupstr(const char* s) { char* d = malloc(strlen(s) + 1); strcpy(d, s); return d; }
@@ -55,6 +57,11 @@ static void parse_actions(lzb_seqfile* sf, char* act) {
         else {
             for (char* p = strtok(tok, ","); p; p = strtok(NULL, ",")) {
                 if (!strcmp(p, "unmask")) sf->unmask = 1;
+                else if (!strncmp(p, "nmask=", 6) || !strncmp(p, "xmask=", 6) || !strncmp(p, "softmask=", 9)) {
+                    if (sf->nmasks == 4) lzb_die("too many masking actions for %s", sf->filename);
+                    sf->maskChar[sf->nmasks] = p[0] == 'n' ? 'N' : p[0] == 'x' ? 'X' : -1;
+                    sf->maskFile[sf->nmasks++] = dupstr(strchr(p, '=') + 1);
+                }
                 else if (!strncmp(p, "subset=", 7)) {
                     FILE* nf = fopen(p + 7, "rt");
                     if (!nf) lzb_die("fopen_or_die failed to open \"%s\" for \"rt\"", p + 7);
@@ -144,6 +151,30 @@ static void apply_limits(lzb_seqfile* sf, lzb_seq* out, uint8_t* all, uint32_t t
     memcpy(out->v, all + a - 1, out->len); out->v[out->len] = 0;
     if (sf->unmask) for (uint32_t i = 0; i < out->len; i++) out->v[i] = (uint8_t)toupper(out->v[i]);
     free(all);
+    for (int m = 0; m < sf->nmasks; m++) {              /* mask_sequence: "begin end" lines, 1-based inclusive, full-sequence coordinates */
+        FILE* mf = fopen(sf->maskFile[m], "rt");
+        if (!mf) lzb_die("fopen_or_die failed to open \"%s\" for \"rt\"", sf->maskFile[m]);
+        char line[512]; int lineNum = 0;
+        while (fgets(line, sizeof line, mf)) {
+            lineNum++;
+            char* w = strchr(line, '#'); if (w) *w = 0;
+            unsigned long long b, e; char extra;
+            int items = sscanf(line, "%llu %llu%c", &b, &e, &extra);
+            if (items <= 0) continue;
+            if (items == 3 && isspace((unsigned char)extra)) items = 2;
+            if (items != 2) lzb_die("bad interval (in %s, line %d): \"%s\"", sf->maskFile[m], lineNum, line);
+            if (e < out->startLoc) continue;
+            if (b < out->startLoc) b = out->startLoc;
+            b -= out->startLoc; e -= out->startLoc - 1;      /* zero-based, half open */
+            if (b >= out->len) continue;
+            if (e >= out->len) e = out->len;
+            for (; b < e; b++) {
+                if (sf->maskChar[m] >= 0) out->v[b] = (uint8_t)sf->maskChar[m];
+                else if (out->v[b] >= 'A' && out->v[b] <= 'Z') out->v[b] = (uint8_t)(out->v[b] + 'a' - 'A');
+            }
+        }
+        fclose(mf);
+    }
 }
 
 static int next_fasta(lzb_seqfile* sf, lzb_seq* out) {

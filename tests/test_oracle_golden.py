@@ -102,6 +102,14 @@ def test_oracle_nib_target_golden():
     assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.pig_cat.lav")).read())
 
 
+def test_oracle_mask_golden():
+    """base_test_mask (Makefile:543): [nmask=<file>] intervals become N, N scored as ambiguous (--ambiguous=n,60)."""
+    mask = os.path.join(GOLDEN, "pseudopig.n.mask")
+    out, _ = run_cli(ORACLE_CLI, [CAT, PIG + f"[nmask={mask}]", "--ambiguous=n,60"])
+    norm = lambda t: [l.replace("../test_data/", "").replace(GOLDEN + "/", "") for l in lav_body(t)]
+    assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.mask.lav")).read())
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
