@@ -61,12 +61,6 @@ struct lzb_query {
     u8* d_seq;  u8* d_cls;  size_t cap;
 };
 
-/* device helpers */
-struct seed_dev {                            /* lzb_seed, flattened for kernels */
-    int length, numParts;
-    int shift[LZB_MAX_SEED_PARTS];
-    u32 mask[LZB_MAX_SEED_PARTS];
-};
 static inline void seed_to_dev(seed_dev* d, const lzb_seed* s) {
     d->length = s->length; d->numParts = s->numParts;
     for (int i = 0; i < s->numParts; i++) { d->shift[i] = s->shift[i]; d->mask[i] = s->mask[i]; }

@@ -5,6 +5,7 @@
 #ifndef LZB_TYPES_H
 #define LZB_TYPES_H
 #include <stdint.h>
+#include "../../../include/lastz_b200.h"
 
 typedef uint8_t  u8;
 typedef uint16_t u16;
@@ -24,6 +25,13 @@ struct lzb_scoring_dev {
     s32  subC[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
     s32  msubC[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
     s32  gapOpen, gapExtend;
+};
+
+/* device helpers */
+struct seed_dev {                            /* lzb_seed, flattened for kernels */
+    int length, numParts;
+    int shift[LZB_MAX_SEED_PARTS];
+    u32 mask[LZB_MAX_SEED_PARTS];
 };
 
 #endif
