@@ -17,30 +17,7 @@
 #include <string.h>
 #include "lzb_cuda.h"
 
-struct ctb_dev { int8_t v[256]; };
-
-/* entry j (0-based) is the window ending at pos = pmax - j*step; key = packed word, or the
- * sentinel 1<<wordBits when the window holds an invalid character */
-__global__ void k_index_words(const u8* __restrict__ seq, u32 start, u32 pmax, u32 step, u64 nent,
-                              seed_dev sd, ctb_dev ctb, int wordBits,
-                              u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ hist) {
-    for (u64 j = blockIdx.x * (u64)blockDim.x + threadIdx.x; j < nent; j += (u64)gridDim.x * blockDim.x) {
-        u32 pos = pmax - (u32)(j * step);
-        u64 w = 0; bool ok = true;
-        u32 first = pos - (u32)sd.length;
-        (void)start;
-        for (int k = 0; k < sd.length; k++) {
-            int b = ctb.v[seq[first + k]];
-            ok = ok && (b >= 0);
-            w = (w << 2) | (u64)(b & 3);
-        }
-        u32 word = 0;
-        for (int p = 0; p < sd.numParts; p++) word |= (u32)(w >> sd.shift[p]) & sd.mask[p];
-        u32 key = ok ? word : (1u << wordBits);
-        keys[j] = key; vals[j] = pos;
-        if (ok) atomicAdd(&hist[word], 1u);
-    }
-}
+#include "index_kernels.cuh"
 
 extern "C" lzb_target* lzb_target_build(lzb_ctx* c, const uint8_t* seq1, uint32_t len1, uint32_t start,
                                         uint32_t end, const int8_t ctb[256], const lzb_seed* seed, uint32_t step) {
