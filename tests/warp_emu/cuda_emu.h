@@ -68,4 +68,8 @@ static inline unsigned long long min(unsigned long long a, unsigned long long b)
 static inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+
+// vector types the kernels use
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = { x, y, z, w }; return v; }
 #endif
