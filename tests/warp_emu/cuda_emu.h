@@ -38,6 +38,7 @@ template <class T> static inline T emu_shfl(T v, int src, int line) {
 }
 #define __syncthreads()               emu_syncthreads(__LINE__)
 #define __threadfence()               ((void)0)
+#define __syncwarp()                  ((void)emu_warp_ballot(1, __LINE__))     /* a warp rendezvous */
 #define __shfl_sync(m, v, src)        emu_shfl((v), (int)(src), __LINE__)
 #define __shfl_up_sync(m, v, d)       emu_shfl((v), emu_lane() >= (int)(d) ? emu_lane() - (int)(d) : emu_lane(), __LINE__)
 #define __shfl_down_sync(m, v, d)     emu_shfl((v), emu_lane() + (int)(d) < 32 ? emu_lane() + (int)(d) : emu_lane(), __LINE__)

@@ -13,6 +13,7 @@
 #include "../../lastz_b200/csrc/cuda/lzb_types.h"
 #include "cuda_emu.h"
 #include "../../lastz_b200/csrc/cuda/ydrop_common.cuh"
+#include "../../lastz_b200/csrc/cuda/ydrop_warp.cuh"
 #include "../../lastz_b200/csrc/cuda/ydrop_mw.cuh"
 
 static u64 rng_state = 0x2545F4914F6CDD1Dull;
@@ -53,7 +54,7 @@ static void expand(std::string& out, const u32* ops, u32 n, bool reversedOrder) 
     else for (u32 k = n; k-- > 0;) out.append(ops[k] >> 2, "?IDS"[ops[k] & 3]);
 }
 
-static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim) {
+static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int oneWarp = 0) {
     // query = target through a substitution/indel channel, so that one long alignment exists
     std::string t, q; const char* acgt = "ACGT";
     for (u32 i = 0; i < len; i++) t.push_back(acgt[rnd() & 3]);
@@ -99,7 +100,8 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
         J.tb = tb[side].data(); J.tbLen = tbLen; J.tbRow = tbRow[side].data(); J.tbRowCap = (u32)tbRow[side].size();
         J.ops = ops[side].data(); J.opsCap = (u32)ops[side].size(); J.act = act[side].data(); J.actCap = 16;
     }
-    emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
+    if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });   // the one-warp kernel (512-column window)
+    else emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
     int bad = 0;
     for (int side = 0; side < 2; side++) if (jobs[side].status != DP_OK && jobs[side].status != DP_TRUNCATED) { fprintf(stderr, "  side %d: kernel status %d\n", side, jobs[side].status); bad++; }
     // assemble like ydrop_align (gapped_extend.c:2529-2560): left script in emission order, right script reversed
@@ -116,7 +118,7 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
             bad++;
         }
     }
-    printf("case %2d: %u x %u bp, sub=%.2f indel=%.3f traceback=%u yDrop=%d trim=%d: score %d, %zu columns, rows %u+%u, cells %llu, status %d/%d%s  %s\n", caseNo, len1, len2, sub, indel,
+    printf("case %2d%s: %u x %u bp, sub=%.2f indel=%.3f traceback=%u yDrop=%d trim=%d: score %d, %zu columns, rows %u+%u, cells %llu, status %d/%d%s  %s\n", caseNo, oneWarp ? " (one-warp kernel)" : "", len1, len2, sub, indel,
            tbBytes, yDrop, trim, score, gotCols.size(), jobs[0].rows, jobs[1].rows, jobs[0].cells + jobs[1].cells, jobs[0].status, jobs[1].status, lopped ? " (lopped, not compared)" : "", bad ? "MISMATCH" : "ok");
     lzb_free_align_list(want); lzb_free(segs); lzb_query_free(Q); lzb_target_free(T); lzb_close(oc);
     return bad;
@@ -132,6 +134,8 @@ int main() {
     bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 3000, 1);         // narrow band
     bad += one_case(n++, 3000, 0.05, 0.010, 80u << 20, 9400, 0);         // --noytrim: boundary scores
     bad += one_case(n++, 1500, 0.30, 0.050, 80u << 20, 9400, 1);         // mostly noise
+    bad += one_case(n++, 2500, 0.04, 0.010, 80u << 20, 6000, 1, 1);      // k_ydrop_warp<16>
+    bad += one_case(n++, 2500, 0.06, 0.015, 200000, 6000, 0, 1);         // ... truncated, --noytrim
     printf("%d cases, %d mismatching, %llu collectives emulated\n", n, bad, emu_collectives);
     return bad ? 1 : 0;
 }
