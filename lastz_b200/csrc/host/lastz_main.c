@@ -45,7 +45,7 @@ static void parse_options(options* o, int argc, char** argv) {
     char* wordSeed = NULL;
     for (int i = 1; i < argc; i++) {
         const char* a = argv[i]; const char* v = strchr(a, '='); v = v ? v + 1 : "";
-        if (a[0] != '-' && !(strlen(a) > 1 && a[1] == '=' && strchr("CTWKLXYOEZ", a[0]))) {
+        if (a[0] != '-' && !(strlen(a) > 1 && a[1] == '=' && strchr("CTWKLXYOEZQ", a[0]))) {
             if (!o->targetSpec) o->targetSpec = a; else if (!o->querySpec) o->querySpec = a;
             else lzb_die("Can't understand \"%s\"", a);
             continue;

@@ -176,3 +176,40 @@ def test_oracle_general_format(a1, a2, opts):
         pytest.skip("oracle/_ref not built")
     files = [os.path.join(GOLDEN, "pseudocat.fa") + a1, os.path.join(GOLDEN, "pseudopig.fa") + a2]
     assert run_cli(ORACLE_CLI, files + opts)[0] == run_cli(REF_CLI, files + opts)[0]
+
+
+SCORES = """# a scoring file in the reference's grammar (dna_utilities.c:581-628)
+gap_open_penalty   = 300
+gap_extend_penalty = 25
+hsp_threshold      = 2200
+x_drop             = 600
+y_drop             = 7000
+     A     C     G     T
+A   91   -90   -25  -100
+C  -90   100  -100   -25
+G  -25  -100   100   -90
+T -100   -25   -90    91
+"""
+
+
+@pytest.mark.parametrize("opts", [["--scores={f}"], ["--scores={f}", "--nogapped"], ["Q={f}", "K=2600", "--chain"]])
+def test_oracle_scoring_file(synth, tmp_path, opts):
+    """--scores=<file>: substitution matrix, gap penalties and the thresholds embedded in the file."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    f = tmp_path / "my.scores"
+    f.write_text(SCORES)
+    t, qm = masked_query(synth, tmp_path)
+    opts = [o.format(f=f) for o in opts]
+    same_output(run_cli(ORACLE_CLI, [t, qm] + opts)[0], run_cli(REF_CLI, [t, qm] + opts)[0])
+
+
+@pytest.mark.parametrize("opts", [[], ["--nogapped"]])
+def test_oracle_matches_lastz_32_with_its_diag_hash(synth, tmp_path, opts):
+    """lastz_32 (src/Makefile:59: 4M-entry diagonal hash) gives other HSPs than lastz; --diaghash=22 reproduces them."""
+    ref32 = os.path.join(os.path.dirname(REF_CLI), "lastz_32")
+    if not os.path.exists(ref32):
+        pytest.skip("oracle/_ref/lastz_32 not built")
+    t, qm = masked_query(synth, tmp_path)
+    strip = lambda x: [l for l in x.splitlines() if "lastz" not in l]
+    assert strip(run_cli(ORACLE_CLI, [t, qm, "--diaghash=22"] + opts)[0]) == strip(run_cli(ref32, [t, qm] + opts)[0])
