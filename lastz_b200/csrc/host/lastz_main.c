@@ -21,7 +21,7 @@ typedef struct {
     uint32_t tracebackBytes;
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
-    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt */
+    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa */
     int device, showStats, speculation, mafHeader;
     int nIsAmbiguous; int32_t ambiMatch, ambiMismatch;     /* --ambiguous=n[,[<match>,]<penalty>] lastz.c:5767-5852 */
     int chainDiag, chainAnti;
@@ -56,7 +56,10 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "T=2")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 0; }
         else if (!strcmp(a, "T=3")) { o->seedPattern = LZB_SEED_14OF22; o->withTrans = 1; }
         else if (!strcmp(a, "T=4")) { o->seedPattern = LZB_SEED_14OF22; o->withTrans = 0; }
-        else if (starts(a, "W=") || starts(a, "--word=") || starts(a, "--seed=match")) {
+        else if (starts(a, "--word=")) ;                         /* lastz.c:5665: max index bits; only a table-layout matter (overweight
+                                                                    seeds are "resolved", seed_search.c:878) -- this index holds 28 bits anyway */
+        else if (!strcmp(a, "--justhits") || !strcmp(a, "--hitsonly")) { o->gfExtend = LZB_GFEX_NONE; o->gapped = 0; }   /* lastz.c:5875 */
+        else if (starts(a, "W=") || starts(a, "--seed=match")) {
             int w = atoi(starts(a, "--seed=match") ? a + 12 : v);
             if (w < 1 || w > 15) lzb_die("%d is not a valid word length", w);
             wordSeed = malloc((size_t)w + 1); memset(wordSeed, '1', (size_t)w); wordSeed[w] = 0;
@@ -125,6 +128,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--maf-")) o->format = 4;
         else if (!strcmp(a, "--format=axt") || !strcmp(a, "--axt")) o->format = 5;
         else if (!strcmp(a, "--format=maf") || !strcmp(a, "--maf")) { o->format = 4; o->mafHeader = 1; }
+        else if (!strcmp(a, "--format=gfa") || !strcmp(a, "--gfa")) o->format = 6;
         else if (!strcmp(a, "--general")) o->format = 2;
         else if (!strcmp(a, "--general-")) o->format = 3;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
@@ -209,6 +213,15 @@ int main(int argc, char** argv) {
     if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, o.K, o.L);
     else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
     else if (o.format == 2) lzb_general_header(out);
+    else if (o.format == 6) {                                    /* file names without actions or 2bit contig (seq->filename) */
+        char n1[1024], n2[1024]; char* cut;
+        snprintf(n1, sizeof n1, "%s", o.targetSpec); snprintf(n2, sizeof n2, "%s", o.querySpec);
+        if ((cut = strchr(n1, '['))) *cut = 0;
+        if ((cut = strchr(n2, '['))) *cut = 0;
+        if ((cut = strstr(n1, ".2bit/"))) cut[5] = 0;
+        if ((cut = strstr(n2, ".2bit/"))) cut[5] = 0;
+        lzb_gfa_job_header(out, "lastz.v1.04.58", n1, n2, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, seed.withTrans, o.step);
+    }
     else if (o.format == 5) lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, o.K, o.L, o.X, o.Y);
     else if (o.format == 4 && o.mafHeader) {                     /* maf.c:96-130: version line + the same parameter comments */
         fprintf(out, "##maf version=1 scoring=lastz.v1.04.58\n");
@@ -281,7 +294,11 @@ int main(int argc, char** argv) {
                         al.beg1 = segs[k].pos1 + 1; al.end1 = segs[k].pos1 + segs[k].length; al.beg2 = segs[k].pos2 + 1; al.end2 = segs[k].pos2 + segs[k].length;
                         al.s = segs[k].s; al.script = &es;
                         if (o.format == 4) lzb_maf_align(out, &target, &query, &al); else lzb_axt_align(out, &target, &query, &al, &axtNumber);
-                    } else if (o.format >= 2) lzb_general_match(out, &target, &query, &segs[k]);
+                    } else if (o.format == 6) {
+                        if (!headerDone) { lzb_gfa_strand_header(out, &target, &query); headerDone = 1; }
+                        lzb_gfa_match(out, &target, &query, &segs[k]);
+                    }
+                    else if (o.format >= 2) lzb_general_match(out, &target, &query, &segs[k]);
                 }
                 if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
             } else {
@@ -304,6 +321,10 @@ int main(int argc, char** argv) {
                         lzb_lav_align(out, &target, &query, a);
                     } else if (o.format == 4) lzb_maf_align(out, &target, &query, a);
                     else if (o.format == 5) lzb_axt_align(out, &target, &query, a, &axtNumber);
+                    else if (o.format == 6) {
+                        if (!headerDone) { lzb_gfa_strand_header(out, &target, &query); headerDone = 1; }
+                        lzb_gfa_align(out, &target, &query, a, &ss);
+                    }
                     else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
                     else lzb_die("--format=segments needs --nogapped");
                 }

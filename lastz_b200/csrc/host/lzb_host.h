@@ -77,6 +77,11 @@ void lzb_general_header(FILE*);
 void lzb_general_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
 void lzb_general_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
 void lzb_maf_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);    /* maf.c:271, --format=maf- */
+/* gfa.c:95-330, --format=gfa */
+void lzb_gfa_job_header(FILE*, const char* prog, const char* name1, const char* name2, const char* seedPattern, int withTrans, uint32_t step);
+void lzb_gfa_strand_header(FILE*, const lzb_seq* s1, const lzb_seq* s2);
+void lzb_gfa_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
+void lzb_gfa_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, const lzb_scoreset*);
 void lzb_axt_header(FILE*, const char* prog, const char* args, const lzb_scoreset*, int32_t K, int32_t L, int32_t X, int32_t Y);
 void lzb_axt_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, uint64_t* number);   /* axt.c:96, --format=axt */
 

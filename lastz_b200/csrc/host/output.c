@@ -227,3 +227,55 @@ void lzb_axt_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alig
     align_text_row(f, 1, s1, s2, a);
     fputc('\n', f);
 }
+
+/* ---- --format=gfa (gfa.c:95-330, unpartitioned sequences): d/z job lines, s/h per strand pair, one `a` line per
+ * gap-free block (an `A` line in front of a gapped alignment's blocks) ---- */
+void lzb_gfa_job_header(FILE* f, const char* prog, const char* name1, const char* name2, const char* seedPattern, int withTrans, uint32_t step) {
+    fprintf(f, "d %s %s %s\n", prog, name1, name2);
+    fprintf(f, "z seed=%s%s\n", seedPattern, withTrans == 0 ? "" : withTrans == 1 ? " w/transition" : " w/2 transitions");   /* print_options lastz.c:10441 */
+    fprintf(f, "z step=%u\n", step);
+}
+
+void lzb_gfa_strand_header(FILE* f, const lzb_seq* s1, const lzb_seq* s2) {
+    static const char* shortSuffix[4] = { "", "~", "~-", "-" };
+    static const char* longSuffix[4] = { "", "~", "~ (reverse complement)", " (reverse complement)" };
+    fprintf(f, "s \"%s%s\" %u %u %d %u \"%s%s\" %u %u %d %u\n",
+            s1->filename, shortSuffix[s1->revCompFlags & 3], s1->startLoc, s1->startLoc + s1->len - 1, (s1->revCompFlags & LZB_RCF_REV) ? 1 : 0, s1->contig,
+            s2->filename, shortSuffix[s2->revCompFlags & 3], s2->startLoc, s2->startLoc + s2->len - 1, (s2->revCompFlags & LZB_RCF_REV) ? 1 : 0, s2->contig);
+    fprintf(f, "h \"%s%s\" \"%s%s\"\n", s1->header ? s1->header : "(no header)", longSuffix[s1->revCompFlags & 3],
+            s2->header ? s2->header : "(no header)", longSuffix[s2->revCompFlags & 3]);
+}
+
+static void gfa_block(FILE* f, const lzb_seq* s1, uint32_t pos1, const lzb_seq* s2, uint32_t pos2, uint32_t length, int32_t s) {
+    int pct = length ? pct_identical(s1->v + pos1, s2->v + pos2, length) : 0;
+    fprintf(f, "a %u%s/%u%s %u %d %d ; diag %lld\n", pos1 + 1, (s1->revCompFlags & LZB_RCF_REV) ? "-" : "+",
+            pos2 + 1, (s2->revCompFlags & LZB_RCF_REV) ? "-" : "+", length, s, pct, (long long)pos1 - (long long)pos2);
+}
+
+void lzb_gfa_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g) {
+    gfa_block(f, s1, g->pos1, s2, g->pos2, g->length, g->s);
+}
+
+void lzb_gfa_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, const lzb_scoreset* ss) {
+    uint32_t beg1 = a->beg1, beg2 = a->beg2, height = a->end1 - beg1 + 1, width = a->end2 - beg2 + 1;
+    const lzb_editscript* sc = a->script;
+    for (int pass = 0; pass < 2; pass++) {              /* pass 0: the alignment's score from its blocks and gaps; pass 1: the blocks */
+        int32_t total = 0; uint32_t k = 0;
+        for (uint32_t i = 0, j = 0; i < height || j < width;) {
+            uint32_t run = 0, pi = i, pj = j;
+            while (k < sc->len && (sc->op[k] & 3) == LZB_OP_SUB) { run += sc->op[k] >> 2; k++; }
+            int32_t bs = 0;
+            for (uint32_t x = 0; x < run; x++) bs += ss->sub[(uint32_t)s1->v[beg1 - 1 + pi + x] * 256 + s2->v[beg2 - 1 + pj + x]];
+            i += run; j += run; total += bs;
+            if (pass == 1) gfa_block(f, s1, beg1 - 1 + pi, s2, beg2 - 1 + pj, run, bs);
+            if (i < height || j < width) {
+                if (k >= sc->len) break;
+                uint32_t op = sc->op[k] & 3, rpt = sc->op[k] >> 2; k++;
+                if (op == LZB_OP_INS) j += rpt; else if (op == LZB_OP_DEL) i += rpt;
+                if (rpt > 0) total -= ss->gapOpen + (int32_t)rpt * ss->gapExtend;
+            }
+        }
+        if (pass == 0) fprintf(f, "A %u%s/%u%s %u/%u %d\n", beg1, (s1->revCompFlags & LZB_RCF_REV) ? "-" : "+",
+                               beg2, (s2->revCompFlags & LZB_RCF_REV) ? "-" : "+", height, width, total);
+    }
+}

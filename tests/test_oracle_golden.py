@@ -110,6 +110,15 @@ def test_oracle_mask_golden():
     assert norm(out) == norm(open(os.path.join(GOLDEN, "base_test.mask.lav")).read())
 
 
+def test_oracle_overweight_seed_hits_golden():
+    """base_test_ow_seeded (Makefile:487): --justhits with a 16-bit seed and --word=12.  The reference resolves
+    the overweight seed through a 12-bit table (seed_search.c:878), which changes the ORDER hits are found in, not
+    the set; its own test compares order-insensitively (gfa_compare.py --sort) and so does this one."""
+    out, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--justhits", "--seed=111010011101", "--word=12", "--gfa"])
+    hits = lambda t: sorted(l for l in t.splitlines() if l.startswith("a "))
+    assert hits(out) == hits(open(os.path.join(GOLDEN, "base_test.owseeded.gfa")).read())
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
