@@ -119,6 +119,14 @@ def test_oracle_overweight_seed_hits_golden():
     assert hits(out) == hits(open(os.path.join(GOLDEN, "base_test.owseeded.gfa")).read())
 
 
+def test_oracle_anchors_multi_golden():
+    """base_test_anchors_multi (Makefile:522): one anchors file for several query sequences (matched by name)."""
+    names = os.path.join(GOLDEN, "shorties.names")
+    out, _ = run_cli(ORACLE_CLI, [AGLOBIN + "/human", os.path.join(GOLDEN, "shorties.fa") + f"[subset={names}]", "C=0", "--format=maf-",
+                                  "--anchors=" + os.path.join(GOLDEN, "base_test.anchors_multi.anchors")])
+    assert out == open(os.path.join(GOLDEN, "base_test.anchors_multi.maf")).read()
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
