@@ -2,7 +2,7 @@
 // seed_kernels,peaks_kernel}.cuh) compiled for the host block emulator and driven by a host loop that
 // mirrors lzb_seed_hit_search (seed_search.cu), checked against the ORACLE library through the C-ABI:
 // index contents, raw hit counts, HSP tables (x-drop through k_extend2 and the first k_extend, --exact and
-// --mismatch through k_extend_alt, raw hits) and anchor peaks.  TEST INFRASTRUCTURE (links liblzb_oracle.so).
+// --mismatch through k_extend_alt, the three-kernel split, raw hits) and anchor peaks.  TEST INFRASTRUCTURE (links liblzb_oracle.so).
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -31,6 +31,7 @@ template <class T, int N> struct BlockReduce {
 #include "../../lastz_b200/csrc/cuda/classify_kernel.cuh"
 #include "../../lastz_b200/csrc/cuda/index_kernels.cuh"
 #include "../../lastz_b200/csrc/cuda/seed_kernels.cuh"
+#include "../../lastz_b200/csrc/cuda/xdrop_split.cuh"
 #include "../../lastz_b200/csrc/cuda/peaks_kernel.cuh"
 
 static u64 rng_state = 0x9E3779B97F4A7C15ull;
@@ -192,6 +193,11 @@ static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u3
             emu_launch(1, 256, [&]() { k_bucket_sizes(bstart.data(), nbuckets, bcnt.data(), bid.data()); });
             std::stable_sort(bid.begin(), bid.end(), [&](u32 a, u32 b) { return bcnt[a] > bcnt[b]; });   // largest bucket first
             emu_launch(2, 256, [&]() { k_extend2(valsB.data(), bstart.data(), bid.data(), nbuckets, P1.cls.data(), P2.cls.data(), P1.asc.data(), P2.asc.data(), &g_sc, P, diagEnd.data(), cand.data(), candCap, &cnt, &next); });
+        } else if (M.useFirstKernel == 2) {                      /* the three-kernel extension (xdrop_split.cuh, LZB_SPLIT_EXTEND=1) */
+            std::vector<right_rec> right(nh + 1); std::vector<live_rec> live(nh + 1); unsigned long long nlive = 0;
+            emu_launch(2, 256, [&]() { k_right(valsB.data(), nh, P1.cls.data(), P2.cls.data(), &g_sc, P, diagEnd.data(), right.data()); });
+            emu_launch(2, 256, [&]() { k_replay(valsB.data(), bstart.data(), nbuckets, right.data(), P1.cls.data(), P2.cls.data(), &g_sc, P, diagEnd.data(), live.data(), &nlive); });
+            emu_launch(2, 256, [&]() { k_left(live.data(), &nlive, P1.cls.data(), P2.cls.data(), P1.asc.data(), P2.asc.data(), &g_sc, P, cand.data(), candCap, &cnt); });
         } else
             emu_launch(2, 256, [&]() { k_extend<true>(valsB.data(), bstart.data(), nbuckets, P1.cls.data(), P2.cls.data(), P1.asc.data(), P2.asc.data(), &g_sc, P, diagEnd.data(), cand.data(), candCap, &cnt); });
         // ---- candidates -> HSP table (the host tail of lzb_seed_hit_search) ----
@@ -245,6 +251,7 @@ int main() {
         { "x-drop (k_extend2)",          LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 0 },
         { "x-drop, 2^6 buckets",         LZB_GFEX_XDROP, 0, 2000, 0, 0, 6, 0 },
         { "x-drop (first k_extend)",     LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 1 },
+        { "x-drop (right/replay/left)",  LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 2 },
         { "--nogfextend (diag filter)",  LZB_GFEX_NONE, 0, 0, 0, 0, 16, 1 },
         { "--mismatch=2,40",             LZB_GFEX_MISMATCH, 2, 40, 0, 0, 16, 0 },
     };

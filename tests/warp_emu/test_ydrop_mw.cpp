@@ -1,5 +1,5 @@
-// test_ydrop_mw.cpp -- the register-resident Y-drop kernel (lastz_b200/csrc/cuda/ydrop_mw.cuh, k_ydrop_mw<8,4>,
-// the kernel that is 99 % of the bench step) compiled for the host block emulator and checked against the
+// test_ydrop_mw.cpp -- the Y-drop kernels (k_ydrop_mw<8,4> of ydrop_mw.cuh, the kernel that is 99 % of the bench
+// step; its fallbacks k_ydrop_warp<16> and the shared-memory k_ydrop<256>) compiled for the host block emulator and checked against the
 // ORACLE library through the C-ABI: for one anchor without neighbours, the two one-sided DPs of the kernel
 // must give the oracle's alignment -- score, end points and edit script, column by column.
 // TEST INFRASTRUCTURE: this is the one place outside tests/*.py that links liblzb_oracle.so.
@@ -12,7 +12,9 @@
 #include "../../include/lastz_b200.h"
 #include "../../lastz_b200/csrc/cuda/lzb_types.h"
 #include "cuda_emu.h"
+#define LZB_DYNAMIC_SHARED(name_) static unsigned char name_[200 * 1024] __attribute__((aligned(16)))   /* k_ydrop's ring: one block runs at a time */
 #include "../../lastz_b200/csrc/cuda/ydrop_common.cuh"
+#include "../../lastz_b200/csrc/cuda/ydrop_smem.cuh"
 #include "../../lastz_b200/csrc/cuda/ydrop_warp.cuh"
 #include "../../lastz_b200/csrc/cuda/ydrop_mw.cuh"
 
@@ -100,7 +102,8 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
         J.tb = tb[side].data(); J.tbLen = tbLen; J.tbRow = tbRow[side].data(); J.tbRowCap = (u32)tbRow[side].size();
         J.ops = ops[side].data(); J.opsCap = (u32)ops[side].size(); J.act = act[side].data(); J.actCap = 16;
     }
-    if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });   // the one-warp kernel (512-column window)
+    if (oneWarp == 2) emu_launch(2, 256, [&]() { k_ydrop<256>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim, 4096u); });   // the shared-memory fallback, 4096-column ring
+    else if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });   // the one-warp kernel (512-column window)
     else emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
     int bad = 0;
     for (int side = 0; side < 2; side++) if (jobs[side].status != DP_OK && jobs[side].status != DP_TRUNCATED) { fprintf(stderr, "  side %d: kernel status %d\n", side, jobs[side].status); bad++; }
@@ -118,7 +121,7 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
             bad++;
         }
     }
-    printf("case %2d%s: %u x %u bp, sub=%.2f indel=%.3f traceback=%u yDrop=%d trim=%d: score %d, %zu columns, rows %u+%u, cells %llu, status %d/%d%s  %s\n", caseNo, oneWarp ? " (one-warp kernel)" : "", len1, len2, sub, indel,
+    printf("case %2d%s: %u x %u bp, sub=%.2f indel=%.3f traceback=%u yDrop=%d trim=%d: score %d, %zu columns, rows %u+%u, cells %llu, status %d/%d%s  %s\n", caseNo, oneWarp == 2 ? " (shared-memory kernel)" : oneWarp ? " (one-warp kernel)" : "", len1, len2, sub, indel,
            tbBytes, yDrop, trim, score, gotCols.size(), jobs[0].rows, jobs[1].rows, jobs[0].cells + jobs[1].cells, jobs[0].status, jobs[1].status, lopped ? " (lopped, not compared)" : "", bad ? "MISMATCH" : "ok");
     lzb_free_align_list(want); lzb_free(segs); lzb_query_free(Q); lzb_target_free(T); lzb_close(oc);
     return bad;
@@ -136,6 +139,8 @@ int main() {
     bad += one_case(n++, 1500, 0.30, 0.050, 80u << 20, 9400, 1);         // mostly noise
     bad += one_case(n++, 2500, 0.04, 0.010, 80u << 20, 6000, 1, 1);      // k_ydrop_warp<16>
     bad += one_case(n++, 2500, 0.06, 0.015, 200000, 6000, 0, 1);         // ... truncated, --noytrim
+    bad += one_case(n++, 2000, 0.04, 0.010, 80u << 20, 9400, 1, 2);      // k_ydrop<256> (shared-memory ring)
+    bad += one_case(n++, 2000, 0.07, 0.020, 150000, 9400, 0, 2);         // ... truncated, --noytrim
     printf("%d cases, %d mismatching, %llu collectives emulated\n", n, bad, emu_collectives);
     return bad ? 1 : 0;
 }
