@@ -23,6 +23,7 @@ typedef struct {
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa */
     int device, showStats, speculation, mafHeader;
+    int anyOrNone;                                           /* --anyornone: hspImmediate + searchLimit 1 (lastz.c:5962) */
     int nIsAmbiguous; int32_t ambiMatch, ambiMismatch;     /* --ambiguous=n[,[<match>,]<penalty>] lastz.c:5767-5852 */
     int chainDiag, chainAnti;
     char args[4096];
@@ -58,6 +59,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "T=4")) { o->seedPattern = LZB_SEED_14OF22; o->withTrans = 0; }
         else if (starts(a, "--word=")) ;                         /* lastz.c:5665: max index bits; only a table-layout matter (overweight
                                                                     seeds are "resolved", seed_search.c:878) -- this index holds 28 bits anyway */
+        else if (!strcmp(a, "--anyornone") || !strcmp(a, "--stopafterone")) o->anyOrNone = 1;
         else if (!strcmp(a, "--justhits") || !strcmp(a, "--hitsonly")) { o->gfExtend = LZB_GFEX_NONE; o->gapped = 0; }   /* lastz.c:5875 */
         else if (starts(a, "W=") || starts(a, "--seed=match")) {
             int w = atoi(starts(a, "--seed=match") ? a + 12 : v);
@@ -236,7 +238,9 @@ int main(int argc, char** argv) {
     lzb_seq query;
     while (lzb_seqfile_next(qf, &query)) {
         if (query.len == 0) { lzb_seq_free(&query); continue; }
+        int reported = 0;                                        /* --anyornone: alignments reported for this query */
         for (int pass = 0; pass < 2; pass++) {
+            if (o.anyOrNone && reported) continue;               /* the search limit of 1 is per query, both strands */
             if (pass == 0 && o.whichStrand < 0) continue;
             if (pass == 1 && o.whichStrand == 0) continue;
             if (pass == 1) lzb_seq_revcomp(&query);
@@ -282,6 +286,42 @@ int main(int argc, char** argv) {
                 }
             if (o.chain)                                         /* try_reduce_to_chain lastz.c:3349, chainScale = 100 (:511) */
                 lzb_reduce_to_chain(segs, &nsegs, o.chainDiag, o.chainAnti, 100, ss.sub['A' * 256 + 'A']);
+            if (o.anyOrNone && nsegs) {
+                /* gappily_extend_hsps (gapped_extend.c:5279; a17): every HSP, in discovery order, is reduced to its
+                 * peak and extended on its own, unconstrained by other alignments; the first one that reaches the
+                 * gapped threshold is reported and the search stops (searchLimit 1).  Without gapped extension
+                 * the first HSP is reported (report_filtered_hsps lastz.c:3905).  The anchors handed over are
+                 * single-element tables, so the library's anchor loop has nothing to bound or to skip. */
+                lzb_segment first; int have = 0; lzb_alignel* one = NULL;
+                for (uint64_t k = 0; k < nsegs && !have; k++) {
+                    first = segs[k];
+                    if (!o.gapped) { have = 1; break; }
+                    lzb_gapped_params gp; memset(&gp, 0, sizeof gp);
+                    gp.yDrop = o.Y; gp.trimToPeak = o.trimToPeak; gp.scoreThreshold = o.L; gp.tracebackBytes = o.tracebackBytes; gp.speculation = 1;
+                    lzb_segment anchor = first;
+                    if (lzb_reduce_to_points(ctx, T, Q, &anchor, 1)) lzb_die("%s", lzb_last_error());
+                    if (lzb_gapped_extend(ctx, T, Q, target.v, query.v, &anchor, 1, &gp, &one, &gst)) lzb_die("%s", lzb_last_error());
+                    totCells += gst.dpCells; gapSec += gst.seconds;
+                    if (one) have = 1;
+                }
+                lzb_free(segs);
+                if (!have) { segs = NULL; nsegs = 0; }
+                else if (!o.gapped) { segs = malloc(sizeof *segs); segs[0] = first; nsegs = 1; reported = 1; }
+                else {                                            /* print through the normal path below: one alignment, no anchors */
+                    reported = 1; segs = NULL; nsegs = 0;
+                    int hd = 0;
+                    for (lzb_alignel* a = one; a; a = a->next) {
+                        if (o.format == 0) { if (!hd) { lzb_lav_strand_header(out, &target, &query); hd = 1; } lzb_lav_align(out, &target, &query, a); }
+                        else if (o.format == 4) lzb_maf_align(out, &target, &query, a);
+                        else if (o.format == 5) lzb_axt_align(out, &target, &query, a, &axtNumber);
+                        else if (o.format == 6) { if (!hd) { lzb_gfa_strand_header(out, &target, &query); hd = 1; } lzb_gfa_align(out, &target, &query, a, &ss); }
+                        else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
+                    }
+                    lzb_free_align_list(one);
+                    lzb_query_free(Q);
+                    continue;
+                }
+            }
             int headerDone = 0;
             if (!o.gapped) {
                 for (uint64_t k = 0; k < nsegs; k++) {

@@ -164,3 +164,15 @@ GENERAL_CASES = [
     ("", "[500..20000]", ["--gfa", "--nogapped", "--transition=2", "--hspthresh=2200"]),
     ("", "", ["--gfa", "--chain", "--seed=14of22", "--notransition", "--step=4"]),
 ]
+
+
+# --anyornone (gappily_extend_hsps gapped_extend.c:5279): first HSP, in discovery order, whose
+# unconstrained gapped extension reaches the threshold; one alignment per query, both strands
+ANYORNONE_CASES = [
+    ["--anyornone", "--format=general-"],
+    ["--anyornone"],
+    ["--anyornone", "--nogapped", "--format=general-"],
+    ["--anyornone", "--strand=minus", "--format=maf-"],
+    ["--anyornone", "--gappedthresh=60000", "--format=general-"],
+    ["--anyornone", "W=8", "T=0", "--hspthresh=2500", "--gfa"],
+]

@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, GENERAL_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, GENERAL_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -230,3 +230,12 @@ def test_oracle_matches_lastz_32_with_its_diag_hash(synth, tmp_path, opts):
     t, qm = masked_query(synth, tmp_path)
     strip = lambda x: [l for l in x.splitlines() if "lastz" not in l]
     assert strip(run_cli(ORACLE_CLI, [t, qm, "--diaghash=22"] + opts)[0]) == strip(run_cli(ref32, [t, qm] + opts)[0])
+
+
+@pytest.mark.parametrize("opts", ANYORNONE_CASES)
+def test_oracle_anyornone(opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    same_output(run_cli(ORACLE_CLI, [CAT, PIG] + opts)[0], run_cli(REF_CLI, [CAT, PIG] + opts)[0])
+    multi = [AGLOBIN + "/human", os.path.join(GOLDEN, "shorties.fa")] + opts      # 20 query sequences
+    same_output(run_cli(ORACLE_CLI, multi)[0], run_cli(REF_CLI, multi)[0])
