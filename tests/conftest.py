@@ -160,7 +160,11 @@ GENERAL_CASES = [
     ("", "", ["--format=axt"]),                                   # print_axt_align axt.c:96, header included
     ("", "[500..20000]", ["--format=axt", "--nogapped"]),
     ("", "", ["--format=maf", "--chain", "Y=5000"]),              # MAF with the parameter header (maf.c:96)
-    ("", "", ["--format=gfa"]),                                   # gfa.c:95-330: A lines + one a line per gap-free block
+]
+
+# --format=gfa (gfa.c:95-330): A lines + one a line per gap-free block
+GFA_CASES = [
+    ("", "", ["--format=gfa"]),
     ("", "[500..20000]", ["--gfa", "--nogapped", "--transition=2", "--hspthresh=2200"]),
     ("", "", ["--gfa", "--chain", "--seed=14of22", "--notransition", "--step=4"]),
 ]

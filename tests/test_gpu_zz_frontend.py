@@ -1,0 +1,26 @@
+"""Front-end features added after the last full GPU run of round 1, through the product command line on the GPU:
+GFA output and --anyornone (single-anchor gapped_extend calls per HSP).  The file sorts last on purpose: pytest
+-x stops at the first failure, and these are the cases that had CPU verification only (same host C code through
+the oracle library, tests/test_oracle_golden.py) when they were written."""
+import os
+
+import pytest
+
+from conftest import ANYORNONE_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
+
+pytestmark = pytest.mark.gpu
+
+CAT = os.path.join(GOLDEN, "pseudocat.fa")
+PIG = os.path.join(GOLDEN, "pseudopig.fa")
+
+
+@pytest.mark.parametrize("a1,a2,opts", GFA_CASES)
+def test_cli_gfa_format(a1, a2, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    assert run_cli(PRODUCT_CLI, [CAT + a1, PIG + a2] + opts)[0] == run_cli(ref, [CAT + a1, PIG + a2] + opts)[0]
+
+
+@pytest.mark.parametrize("opts", ANYORNONE_CASES)
+def test_cli_anyornone(opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    same_output(run_cli(PRODUCT_CLI, [CAT, PIG] + opts)[0], run_cli(ref, [CAT, PIG] + opts)[0])
