@@ -131,8 +131,6 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--format=axt") || !strcmp(a, "--axt")) o->format = 5;
         else if (!strcmp(a, "--format=maf") || !strcmp(a, "--maf")) { o->format = 4; o->mafHeader = 1; }
         else if (!strcmp(a, "--format=gfa") || !strcmp(a, "--gfa")) o->format = 6;
-        else if (!strcmp(a, "--general")) o->format = 2;
-        else if (!strcmp(a, "--general-")) o->format = 3;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
         else if (!strcmp(a, "--format=general")) o->format = 2;          /* default fields, genpaf.h:117 */
         else if (!strcmp(a, "--format=general-")) o->format = 3;         /* ... without the header line */
