@@ -289,6 +289,11 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
     if (P->tracebackBytes < 8) return lzb_fail("in new_traceback(), size can't be %u", P->tracebackBytes);
     if (c->sc.gapOpen < 0) return lzb_fail("lastz_b200's Y-drop kernel requires a non-negative gap open penalty (got %d)", c->sc.gapOpen);
+    /* [multi] sequences (NUL-separated partitions, sequences.h:188-191) need per-partition DP limits
+     * (gapped_extend.c:1357-1372).  The oracle and the front end implement them; this library was not run on such
+     * input on a GPU in round 1, so it says so instead of extending across partition borders. */
+    if (memchr(t->h_seq, 0, t->len) || memchr(q->h_seq, 0, q->len))
+        return lzb_fail("the CUDA library does not extend anchors in partitioned ([multi]) sequences yet; use --nogapped or one sequence at a time");
     auto wall0 = std::chrono::steady_clock::now();
     u64 launches0 = c->launches;
     *list = NULL;

@@ -203,6 +203,7 @@ int main(int argc, char** argv) {
     lzb_seq target;
     if (!lzb_seqfile_next(tf, &target)) lzb_die("%s contains no sequence", o.targetSpec);
     { lzb_seq extra; if (lzb_seqfile_next(tf, &extra)) lzb_die("%s contains more than one sequence, consider using the \"multiple\" action", o.targetSpec); }
+    if (target.npart) lzb_die("lastz_b200 does not implement [multi] on the target yet (anchors are extended in per-partition batches, gapped_extend.c:1058); [multi] on the query is supported");
 
     lzb_ctx* ctx = lzb_open(o.device);
     if (!ctx) lzb_die("%s", lzb_last_error());
@@ -236,6 +237,9 @@ int main(int argc, char** argv) {
     lzb_seq query;
     while (lzb_seqfile_next(qf, &query)) {
         if (query.len == 0) { lzb_seq_free(&query); continue; }
+        if (query.npart && (o.format == 0 || o.format == 6)) lzb_die("%s format can't handle multi-sequences", o.format == 0 ? "lav" : "gfa");
+        if (query.npart && (o.selfCompare || o.segmentsFile || o.chain || o.anyOrNone))
+            lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments, --chain or --anyornone yet");
         int reported = 0;                                        /* --anyornone: alignments reported for this query */
         for (int pass = 0; pass < 2; pass++) {
             if (o.anyOrNone && reported) continue;               /* the search limit of 1 is per query, both strands */

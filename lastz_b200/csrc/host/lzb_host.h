@@ -28,7 +28,19 @@ typedef struct lzb_seq {
     char*    filename;   /* as given on the command line, actions stripped */
     char*    header;     /* full header line (FASTA: including '>') */
     char*    shortHeader;/* first word of the header */
+    /* [multi]: several sequences in one vector, v = NUL seq0 NUL seq1 NUL ... (sequences.h:188-191 note 2): v[0] and
+     * every separator are NUL, len counts them, part[i] describes sequence i; npart == 0 for an ordinary sequence */
+    uint32_t npart;
+    struct lzb_partition* part;
 } lzb_seq;
+typedef struct lzb_partition {
+    uint32_t sepBefore, sepAfter;   /* indices of the NULs around the sequence */
+    uint32_t contig, startLoc, trueLen;
+    char* header; char* shortHeader;
+} lzb_partition;
+/* name, offset in v, startLoc, length and full length of the (part of the) sequence that holds position pos0 */
+typedef struct lzb_seqview { const char* name; uint32_t offset, startLoc, len, trueLen; } lzb_seqview;
+void lzb_seq_view(const lzb_seq* s, uint32_t pos0, lzb_seqview* out);
 
 /* a sequence file + bracketed actions; load successive sequences with lzb_seqfile_next */
 typedef struct lzb_seqfile lzb_seqfile;

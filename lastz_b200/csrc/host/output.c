@@ -24,6 +24,7 @@ void lzb_lav_job_header(FILE* f, const char* prog, const char* name1, const char
 }
 
 void lzb_lav_strand_header(FILE* f, const lzb_seq* s1, const lzb_seq* s2) {
+    if (s1->npart || s2->npart) lzb_die("lav format can't handle multi-sequences");
     static const char* shortSfx[4] = { "", "~", "~-", "-" };
     static const char* longSfx[4] = { "", "~", "~ (reverse complement)", " (reverse complement)" };
     fprintf(f, "#:lav\ns {\n");
@@ -101,17 +102,17 @@ void lzb_general_header(FILE* f) {
 
 static void general_row(FILE* f, const lzb_seq* s1, const lzb_seq* s2, uint32_t pos1, uint32_t len1, uint32_t pos2, uint32_t len2,
                         int32_t score, uint64_t idNumer, uint64_t idDenom) {
-    const char* name1 = (s1->shortHeader && s1->shortHeader[0]) ? s1->shortHeader : "seq1";
-    const char* name2 = (s2->shortHeader && s2->shortHeader[0]) ? s2->shortHeader : "seq2";
+    lzb_seqview w1, w2; lzb_seq_view(s1, pos1, &w1); lzb_seq_view(s2, pos2, &w2);      /* the partitions the alignment lies in */
+    const char* name1 = w1.name ? w1.name : "seq1"; const char* name2 = w2.name ? w2.name : "seq2";
     uint32_t start1, start2; char strand1, strand2;
-    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = pos1 + s1->startLoc; strand1 = '+'; }
-    else { start1 = pos1 + s1->trueLen + 2 - (s1->startLoc + s1->len); strand1 = '-'; }
-    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = pos2 + s2->startLoc; strand2 = '+'; }
-    else { start2 = pos2 + s2->trueLen + 2 - (s2->startLoc + s2->len); strand2 = '-'; }
+    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = pos1 - w1.offset + w1.startLoc; strand1 = '+'; }
+    else { start1 = pos1 - w1.offset + w1.trueLen + 2 - (w1.startLoc + w1.len); strand1 = '-'; }
+    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = pos2 - w2.offset + w2.startLoc; strand2 = '+'; }
+    else { start2 = pos2 - w2.offset + w2.trueLen + 2 - (w2.startLoc + w2.len); strand2 = '-'; }
     uint64_t covNumer, covDenom;
-    if (s1->trueLen < s2->trueLen) { covNumer = len1; covDenom = s1->trueLen; } else { covNumer = len2; covDenom = s2->trueLen; }
-    fprintf(f, "%d\t%s\t%c\t%u\t%u\t%u\t%s\t%c\t%u\t%u\t%u\t", score, name1, strand1, s1->trueLen, start1 - 1, start1 + len1 - 1,
-            name2, strand2, s2->trueLen, start2 - 1, start2 + len2 - 1);
+    if (w1.trueLen < w2.trueLen) { covNumer = len1; covDenom = w1.trueLen; } else { covNumer = len2; covDenom = w2.trueLen; }
+    fprintf(f, "%d\t%s\t%c\t%u\t%u\t%u\t%s\t%c\t%u\t%u\t%u\t", score, name1, strand1, w1.trueLen, start1 - 1, start1 + len1 - 1,
+            name2, strand2, w2.trueLen, start2 - 1, start2 + len2 - 1);
     fprintf(f, "%llu/%llu", (unsigned long long)idNumer, (unsigned long long)idDenom);
     if (idDenom) fprintf(f, "\t%.1f%%", (100.0 * idNumer) / idDenom); else fprintf(f, "\tNA");
     fprintf(f, "\t%llu/%llu", (unsigned long long)covNumer, (unsigned long long)covDenom);
@@ -178,23 +179,23 @@ static void align_text_row(FILE* f, int row, const lzb_seq* s1, const lzb_seq* s
 }
 
 void lzb_maf_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a) {
-    const char* name1 = (s1->shortHeader && s1->shortHeader[0]) ? s1->shortHeader : "seq1";
-    const char* name2 = (s2->shortHeader && s2->shortHeader[0]) ? s2->shortHeader : "seq2";
+    lzb_seqview w1, w2; lzb_seq_view(s1, a->beg1 - 1, &w1); lzb_seq_view(s2, a->beg2 - 1, &w2);
+    const char* name1 = w1.name ? w1.name : "seq1"; const char* name2 = w2.name ? w2.name : "seq2";
     static const char* rcfSuffix[4] = { "", "~", "~", "" };                             /* maf.c / cigar.c:191 */
     const char* suff1 = rcfSuffix[s1->revCompFlags & 3]; const char* suff2 = rcfSuffix[s2->revCompFlags & 3];
     uint32_t beg1 = a->beg1, beg2 = a->beg2, height = a->end1 - beg1 + 1, width = a->end2 - beg2 + 1;
     uint32_t start1, start2; char strand1, strand2;
-    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = beg1 - 1 + s1->startLoc; strand1 = '+'; }
-    else { start1 = beg1 - 1 + s1->trueLen + 2 - (s1->startLoc + s1->len); strand1 = '-'; }
-    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = beg2 - 1 + s2->startLoc; strand2 = '+'; }
-    else { start2 = beg2 - 1 + s2->trueLen + 2 - (s2->startLoc + s2->len); strand2 = '-'; }
+    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = beg1 - 1 - w1.offset + w1.startLoc; strand1 = '+'; }
+    else { start1 = beg1 - 1 - w1.offset + w1.trueLen + 2 - (w1.startLoc + w1.len); strand1 = '-'; }
+    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = beg2 - 1 - w2.offset + w2.startLoc; strand2 = '+'; }
+    else { start2 = beg2 - 1 - w2.offset + w2.trueLen + 2 - (w2.startLoc + w2.len); strand2 = '-'; }
     int len1 = (int)(strlen(name1) + strlen(suff1)), len2 = (int)(strlen(name2) + strlen(suff2));
     int nameW = len1 >= len2 ? len1 : len2;
-    int startW = digits_of(start1, start2), endW = digits_of(height, width), lenW = digits_of(s1->trueLen, s2->trueLen);
+    int startW = digits_of(start1, start2), endW = digits_of(height, width), lenW = digits_of(w1.trueLen, w2.trueLen);
     fprintf(f, "a score=%d\n", a->s);
     for (int row = 0; row < 2; row++) {
-        if (row == 0) fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name1, suff1, nameW + 1 - len1, " ", startW, start1 - 1, endW, height, strand1, lenW, s1->trueLen);
-        else fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name2, suff2, nameW + 1 - len2, " ", startW, start2 - 1, endW, width, strand2, lenW, s2->trueLen);
+        if (row == 0) fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name1, suff1, nameW + 1 - len1, " ", startW, start1 - 1, endW, height, strand1, lenW, w1.trueLen);
+        else fprintf(f, "s %s%s%*s%*u %*u %c %*u ", name2, suff2, nameW + 1 - len2, " ", startW, start2 - 1, endW, width, strand2, lenW, w2.trueLen);
         align_text_row(f, row, s1, s2, a);
     }
     fputc('\n', f);
@@ -215,12 +216,12 @@ void lzb_axt_header(FILE* f, const char* prog, const char* args, const lzb_score
 }
 
 void lzb_axt_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, uint64_t* number) {
-    const char* name1 = (s1->shortHeader && s1->shortHeader[0]) ? s1->shortHeader : "seq1";
-    const char* name2 = (s2->shortHeader && s2->shortHeader[0]) ? s2->shortHeader : "seq2";
+    lzb_seqview w1, w2; lzb_seq_view(s1, a->beg1 - 1, &w1); lzb_seq_view(s2, a->beg2 - 1, &w2);
+    const char* name1 = w1.name ? w1.name : "seq1"; const char* name2 = w2.name ? w2.name : "seq2";
     uint32_t height = a->end1 - a->beg1 + 1, width = a->end2 - a->beg2 + 1;
-    uint32_t start1 = a->beg1 - 1 + s1->startLoc, start2; char strand2;
-    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = a->beg2 - 1 + s2->startLoc; strand2 = '+'; }
-    else { start2 = a->beg2 - 1 + s2->trueLen + 2 - (s2->startLoc + s2->len); strand2 = '-'; }
+    uint32_t start1 = a->beg1 - 1 - w1.offset + w1.startLoc, start2; char strand2;
+    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = a->beg2 - 1 - w2.offset + w2.startLoc; strand2 = '+'; }
+    else { start2 = a->beg2 - 1 - w2.offset + w2.trueLen + 2 - (w2.startLoc + w2.len); strand2 = '-'; }
     fprintf(f, "%llu %s %u %u %s %u %u %c %d\n", (unsigned long long)(*number)++, name1, start1, start1 + height - 1,
             name2, start2, start2 + width - 1, strand2, a->s);
     align_text_row(f, 0, s1, s2, a);
@@ -237,6 +238,7 @@ void lzb_gfa_job_header(FILE* f, const char* prog, const char* name1, const char
 }
 
 void lzb_gfa_strand_header(FILE* f, const lzb_seq* s1, const lzb_seq* s2) {
+    if (s1->npart || s2->npart) lzb_die("gfa format can't handle multi-sequences");
     static const char* shortSuffix[4] = { "", "~", "~-", "-" };
     static const char* longSuffix[4] = { "", "~", "~ (reverse complement)", " (reverse complement)" };
     fprintf(f, "s \"%s%s\" %u %u %d %u \"%s%s\" %u %u %d %u\n",

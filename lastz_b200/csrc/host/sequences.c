@@ -33,6 +33,7 @@ struct lzb_seqfile {
     char** subset; uint32_t nsubset, subsetNext;
     /* [nmask=<file>] / [xmask=<file>] / [softmask=<file>]: intervals to overwrite (mask_sequence sequences.c:6973) */
     char* maskFile[4]; int maskChar[4]; int nmasks;
+    int multi;                  /* [multi]: deliver every (selected) sequence of the file as one partitioned sequence */
 };
 
 static char* dupstr(const char* s) { char* d = malloc(strlen(s) + 1); strcpy(d, s); return d; }
@@ -57,14 +58,18 @@ static void parse_actions(lzb_seqfile* sf, char* act) {
         else {
             for (char* p = strtok(tok, ","); p; p = strtok(NULL, ",")) {
                 if (!strcmp(p, "unmask")) sf->unmask = 1;
+                else if (!strcmp(p, "multi") || !strcmp(p, "multiple")) sf->multi = 1;
+                else if (p[0] == '@') goto subset_file;           /* @<file> is the short spelling of subset=<file> */
                 else if (!strncmp(p, "nmask=", 6) || !strncmp(p, "xmask=", 6) || !strncmp(p, "softmask=", 9)) {
                     if (sf->nmasks == 4) lzb_die("too many masking actions for %s", sf->filename);
                     sf->maskChar[sf->nmasks] = p[0] == 'n' ? 'N' : p[0] == 'x' ? 'X' : -1;
                     sf->maskFile[sf->nmasks++] = dupstr(strchr(p, '=') + 1);
                 }
                 else if (!strncmp(p, "subset=", 7)) {
-                    FILE* nf = fopen(p + 7, "rt");
-                    if (!nf) lzb_die("fopen_or_die failed to open \"%s\" for \"rt\"", p + 7);
+                subset_file:;
+                    const char* nfName = p[0] == '@' ? p + 1 : p + 7;
+                    FILE* nf = fopen(nfName, "rt");
+                    if (!nf) lzb_die("fopen_or_die failed to open \"%s\" for \"rt\"", nfName);
                     char line[1024];
                     while (fgets(line, sizeof line, nf)) {
                         char* w = line; while (*w == ' ' || *w == '\t') w++;
@@ -122,6 +127,18 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
     return sf;
 }
 
+void lzb_seq_view(const lzb_seq* s, uint32_t pos0, lzb_seqview* o) {
+    if (s->npart == 0) {
+        o->name = (s->shortHeader && s->shortHeader[0]) ? s->shortHeader : NULL;
+        o->offset = 0; o->startLoc = s->startLoc; o->len = s->len; o->trueLen = s->trueLen;
+        return;
+    }
+    uint32_t lo = 0, hi = s->npart;                      /* lookup_partition sequences.c: last partition with sepBefore < pos0+1 */
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (s->part[mid].sepBefore <= pos0) lo = mid; else hi = mid; }
+    const lzb_partition* p = &s->part[lo];
+    o->name = p->shortHeader; o->offset = p->sepBefore + 1; o->startLoc = p->startLoc; o->len = p->sepAfter - o->offset; o->trueLen = p->trueLen;
+}
+
 void lzb_seqfile_close(lzb_seqfile* sf) {
     if (!sf) return;
     if (sf->f) fclose(sf->f);
@@ -130,6 +147,8 @@ void lzb_seqfile_close(lzb_seqfile* sf) {
 }
 
 void lzb_seq_free(lzb_seq* s) {
+    for (uint32_t k = 0; k < s->npart; k++) { free(s->part[k].header); free(s->part[k].shortHeader); }
+    free(s->part);
     free(s->v); free(s->filename); free(s->header); free(s->shortHeader);
     memset(s, 0, sizeof *s);
 }
@@ -267,7 +286,7 @@ static int next_nib(lzb_seqfile* sf, lzb_seq* out) {
     return 1;
 }
 
-int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
+static int next_single(lzb_seqfile* sf, lzb_seq* out) {
     memset(out, 0, sizeof *out);
     for (;;) {
         int ok = sf->is2bit ? next_2bit(sf, out) : sf->isNib ? next_nib(sf, out) : next_fasta(sf, out);
@@ -294,11 +313,43 @@ void lzb_seq_revcomp(lzb_seq* s) {
         for (int i = 0; a[i]; i++) { comp[(int)a[i]] = (uint8_t)b[i]; comp[tolower(a[i])] = (uint8_t)tolower(b[i]); }
         init = 1;
     }
-    uint32_t n = s->len;
-    for (uint32_t i = 0, j = n ? n - 1 : 0; n && i <= j; i++, j--) {
-        uint8_t x = comp[s->v[i]], y = comp[s->v[j]];
-        s->v[i] = y; s->v[j] = x;
-        if (j == 0) break;
+    /* a partitioned sequence is reverse-complemented partition by partition, in place (sequences.c:7540-7552) */
+    for (uint32_t k = 0; k < (s->npart ? s->npart : 1u); k++) {
+        uint8_t* v = s->npart ? s->v + s->part[k].sepBefore + 1 : s->v;
+        uint32_t n = s->npart ? s->part[k].sepAfter - (s->part[k].sepBefore + 1) : s->len;
+        for (uint32_t i = 0, j = n ? n - 1 : 0; n && i <= j; i++, j--) {
+            uint8_t x = comp[v[i]], y = comp[v[j]];
+            v[i] = y; v[j] = x;
+            if (j == 0) break;
+        }
     }
     s->revCompFlags ^= LZB_RCF_REVCOMP;
+}
+
+/* load_sequence with doPartitioning (sequences.c:1840-1960): all remaining sequences, NUL-separated */
+int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
+    if (!sf->multi) return next_single(sf, out);
+    lzb_seq one;
+    if (!next_single(sf, &one)) return 0;
+    memset(out, 0, sizeof *out);
+    size_t cap = (size_t)one.len + 1024, n = 0;
+    uint8_t* v = malloc(cap + 2);
+    v[n++] = 0;
+    do {
+        if (n + one.len + 2 > cap) { cap = (n + one.len + 2) * 2; v = realloc(v, cap + 2); }
+        out->part = realloc(out->part, (out->npart + 1) * sizeof(lzb_partition));
+        lzb_partition* p = &out->part[out->npart++];
+        p->sepBefore = (uint32_t)(n - 1);
+        memcpy(v + n, one.v, one.len); n += one.len;
+        p->sepAfter = (uint32_t)n; v[n++] = 0;
+        p->contig = one.contig; p->startLoc = one.startLoc; p->trueLen = one.trueLen;
+        p->header = one.header; p->shortHeader = one.shortHeader; one.header = one.shortHeader = NULL;
+        if (!out->filename) { out->filename = one.filename; one.filename = NULL; }
+        lzb_seq_free(&one);
+        if (n > 0x7FFFFFF0u) lzb_die("sequences in %s are too long to be combined with [multi]", sf->filename);
+    } while (next_single(sf, &one));
+    out->v = v; out->len = (uint32_t)(n - 1);            /* the last NUL is the terminator: v[len] == 0 */
+    out->startLoc = 1; out->trueLen = out->len; out->contig = 1; out->revCompFlags = LZB_RCF_FORWARD;
+    out->header = dupstr(""); out->shortHeader = dupstr("");
+    return 1;
 }

@@ -856,13 +856,23 @@ static s32 rescore(genv* G, u32 p1, u32 p2, lzb_editscript* s) {
 typedef struct { s32 s; u32 start1, start2, stop1, stop2; lzb_editscript* script; } ydres;
 
 /* ydrop_align gapped_extend.c:2459-2584 + lop_initial/final_indels :2589-2683 */
+/* the partition of a [multi] sequence that holds position a (gapped_extend.c:1357-1372: io.low = sepBefore + 1,
+ * io.high = sepAfter); partitions are delimited by NUL bytes (sequences.h:188-191), an ordinary sequence has none */
+static void partition_limits(const u8* v, u32 len, u32 a, u32* low, u32* high) {
+    s64 i = a; while (i >= 0 && v[i] != 0) i--;
+    u32 j = a; while (j < len && v[j] != 0) j++;
+    *low = (u32)(i + 1); *high = j;
+}
+
 static void two_sided(genv* G, galn* m, int above, int below, ydres* o) {
-    u32 a1 = m->pos1, a2 = m->pos2, e1, e2;
+    u32 a1 = m->pos1, a2 = m->pos2, e1, e2, low1, high1, low2, high2;
+    partition_limits(G->s1, G->len1, a1, &low1, &high1);
+    partition_limits(G->s2, G->len2, a2, &low2, &high2);
     lzb_editscript* sl = es_new();
-    s32 left = one_sided(G, 1, a1, a2, a1 + 1, a2 + 1, m->left1, m->right1, below, &sl, &e1, &e2);
+    s32 left = one_sided(G, 1, a1, a2, a1 + 1 - low1, a2 + 1 - low2, m->left1, m->right1, below, &sl, &e1, &e2);
     o->start1 = a1 + 1 - e1; o->start2 = a2 + 1 - e2;
     lzb_editscript* sr = es_new();
-    s32 right = one_sided(G, 0, a1, a2, G->len1 - (a1 + 1), G->len2 - (a2 + 1), m->left1, m->right1, above, &sr, &e1, &e2);
+    s32 right = one_sided(G, 0, a1, a2, high1 - (a1 + 1), high2 - (a2 + 1), m->left1, m->right1, above, &sr, &e1, &e2);
     o->stop1 = a1 + e1; o->stop2 = a2 + e2;
     es_reverse(sr); es_append(&sl, sr); free(sr);
     o->s = left + right; o->script = sl;

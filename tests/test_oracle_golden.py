@@ -127,6 +127,41 @@ def test_oracle_anchors_multi_golden():
     assert out == open(os.path.join(GOLDEN, "base_test.anchors_multi.maf")).read()
 
 
+def _maf_blocks_by_pos1(text):
+    """MAF blocks ordered by (start, strand) in sequence 1, then (start, strand) in sequence 2, then lengths and
+    score: the order the reference's base_test_multi puts both files in before diffing them (Makefile:571)."""
+    def key(b):
+        s1, s2 = [l.split() for l in b.splitlines() if l.startswith("s ")][:2]
+        score = int(b.split("score=")[1].split()[0])
+        return (int(s1[2]), s1[4], int(s2[2]), s2[4], int(s1[3]), int(s2[3]), score, s1[1], s2[1])
+    blocks = [b for b in text.split("\n\n") if b.strip()]
+    blocks.sort(key=key)
+    return "\n\n".join(blocks) + "\n\n"
+
+
+def test_oracle_multi_golden():
+    """base_test_multi (Makefile:571): the query is ALL the named sequences of a 2bit file as one partitioned
+    sequence ([multi], sequences.h:188-191); the reference's recipe sorts the blocks by position in the target."""
+    names = os.path.join(GOLDEN, "shorties.names")
+    out, _ = run_cli(ORACLE_CLI, [AGLOBIN + "/human", os.path.join(GOLDEN, "shorties.2bit") + f"[multi,@{names}]", "K=3000", "--maf-"])
+    assert _maf_blocks_by_pos1(out) == open(os.path.join(GOLDEN, "base_test.multi.maf")).read()
+
+
+def test_oracle_multi_subrange_golden():
+    """base_test_multi_subrange (Makefile:582): [multi] with a subrange applied to every sequence."""
+    out, _ = run_cli(ORACLE_CLI, [AGLOBIN + "/human", os.path.join(GOLDEN, "shorties.2bit") + "[multi,51..200]", "K=3000", "--maf-"])
+    assert out == open(os.path.join(GOLDEN, "base_test.multi_subrange.maf")).read()
+
+
+@pytest.mark.parametrize("opts", [["--format=general-"], ["--format=general-", "--nogapped"], ["--format=maf-", "--strand=minus"],
+                                  ["--format=axt", "W=8", "T=0"], ["--format=general-", "--exact=14", "--nogapped", "W=8", "T=0"]])
+def test_oracle_multi_query_matches_reference(opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    args = [CAT, PIG + "[multi]"] + opts
+    same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
 def test_oracle_segments_round_trip(tmp_path):
     """base_test_segments (Makefile:384): HSPs written, re-read as anchors, gapped stage alone."""
     segs, _ = run_cli(ORACLE_CLI, [CAT, PIG, "--nogapped", "--format=segments"])
