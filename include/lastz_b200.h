@@ -77,8 +77,8 @@ typedef struct lzb_alignel {
 
 /* seeds.h:37-76, the fields apply_seed (seeds.c:1335) and private_hit_search
  * (seed_search.c:464) read.  Match ('1') positions contribute both bits of a base, transition ('T') positions
- * the purine/pyrimidine bit; transFlips[] holds single-bit masks in packed bit order, lowest first
- * (seeds.c:615-625). */
+ * the purine/pyrimidine bit; transFlips[] holds the packed single-bit masks in the reference's order, the
+ * rightmost seed position first (seeds.c:165,603-613: built with maintainFlippedBitOrder). */
 #define LZB_MAX_SEED_PARTS 32
 #define LZB_MAX_SEED_FLIPS 32
 typedef struct lzb_seed {

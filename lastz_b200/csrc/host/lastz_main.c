@@ -18,6 +18,7 @@ typedef struct {
     int whichStrand;               /* 0 plus, 1 both, -1 minus */
     int gfExtend, gfMismatches, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
+    int adaptive; double adaptFraction; uint32_t adaptBases;   /* K=top<N>% ('P') or K=top<bases> ('C'), string_to_score_thresh dna_utilities.c:2248 */
     uint32_t tracebackBytes;
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
@@ -115,7 +116,19 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--entropy")) o->entropy = 1;
         else if (!strcmp(a, "--allgappedbounds")) o->allBounds = 1;
         else if (!strcmp(a, "--noytrim")) o->trimToPeak = 0;
-        else if (starts(a, "--hspthresh=") || starts(a, "K=")) { o->K = atoi(v); o->haveK = 1; }
+        else if (starts(a, "--hspthresh=top") || starts(a, "K=top")) {
+            const char* n = v + 3; size_t ln = strlen(n); char* e;
+            if (ln > 0 && n[ln - 1] == '%') { o->adaptive = 'P'; o->adaptFraction = strtod(n, &e) / 100.0; if (e != n + ln - 1 || o->adaptFraction < 0) lzb_die("\"%s\" is not a valid percentage", n); }
+            else {                                               /* string_to_unitized_int by thousands, utilities.c */
+                double c = strtod(n, &e);
+                if (*e == 'K' || *e == 'k') { c *= 1000; e++; } else if (*e == 'M' || *e == 'm') { c *= 1000 * 1000; e++; } else if (*e == 'G' || *e == 'g') { c *= 1000.0 * 1000 * 1000; e++; }
+                if (e == n || *e || c < 0 || c > 4294967295.0) lzb_die("\"%s\" is not a valid base count", n);
+                o->adaptive = 'C'; o->adaptBases = (uint32_t)c;
+            }
+            o->haveK = 1;
+        }
+        else if (starts(a, "--hspthresh=") || starts(a, "K=")) { o->K = atoi(v); o->haveK = 1; o->adaptive = 0; }
+        else if (starts(a, "--gappedthresh=top") || starts(a, "L=top")) lzb_die("lastz_b200 does not implement an adaptive gapped threshold (%s)", a);
         else if (starts(a, "--gappedthresh=") || starts(a, "L=")) { o->L = atoi(v); o->haveL = 1; }
         else if (starts(a, "--xdrop=") || starts(a, "X=")) { o->X = atoi(v); o->haveX = 1; }
         else if (starts(a, "--ydrop=") || starts(a, "Y=")) { o->Y = atoi(v); o->haveY = 1; }
@@ -145,6 +158,12 @@ static void parse_options(options* o, int argc, char** argv) {
     if (!o->targetSpec) lzb_die("You must specify a target file");
     if (o->selfCompare && !o->querySpec) o->querySpec = o->targetSpec;
     if (!o->querySpec) o->querySpec = "(stdin)";                    /* lastz.c:8762: no query file => read it from stdin */
+    if (o->adaptive) {
+        if (o->gfExtend != LZB_GFEX_XDROP) lzb_die("an adaptive HSP threshold requires --gfextend");   /* the other extensions assume a score, seed_search.c:3003 */
+        if (o->anyOrNone) lzb_die("can't use --anyornone with adaptive hsp score threshold");         /* lastz.c:8898 */
+        if (o->segmentsFile) lzb_die("lastz_b200 does not combine --segments with an adaptive HSP threshold");
+        if (o->selfCompare) lzb_die("lastz_b200 does not combine --self with an adaptive HSP threshold (the reference stops with an internal error there)");
+    }
 }
 
 /* read_segment_table segment.c:456: rows name1 start1 end1 name2 start2 end2 strand [score] */
@@ -211,7 +230,13 @@ int main(int argc, char** argv) {
     lzb_target* T = lzb_target_build(ctx, target.v, target.len, 0, 0, lzb_upper_nuc_to_bits, &seed, o.step);
     if (!T) lzb_die("%s", lzb_last_error());
 
-    if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, o.K, o.L);
+    /* thresholds as the headers print them (score_thresh_to_string dna_utilities.c:2290): an adaptive one as top<bases>,
+     * the percentage already resolved against the target length; an unset L copies K */
+    char textK[32], textL[32];
+    const uint32_t adaptLimit = o.adaptive == 'P' ? (uint32_t)(o.adaptFraction * target.len + 0.5) : o.adaptBases;
+    if (o.adaptive) snprintf(textK, sizeof textK, "top%u", adaptLimit); else snprintf(textK, sizeof textK, "%d", o.K);
+    if (o.adaptive && !o.haveL) snprintf(textL, sizeof textL, "top%u", adaptLimit); else snprintf(textL, sizeof textL, "%d", o.L);
+    if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, textK, textL);
     else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
     else if (o.format == 2) lzb_general_header(out);
     else if (o.format == 6) {                                    /* file names without actions or 2bit contig (seq->filename) */
@@ -223,10 +248,10 @@ int main(int argc, char** argv) {
         if ((cut = strstr(n2, ".2bit/"))) cut[5] = 0;
         lzb_gfa_job_header(out, "lastz.v1.04.58", n1, n2, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, seed.withTrans, o.step);
     }
-    else if (o.format == 5) lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, o.K, o.L, o.X, o.Y);
+    else if (o.format == 5) lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, textK, textL, o.X, o.Y);
     else if (o.format == 4 && o.mafHeader) {                     /* maf.c:96-130: version line + the same parameter comments */
         fprintf(out, "##maf version=1 scoring=lastz.v1.04.58\n");
-        lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, o.K, o.L, o.X, o.Y);
+        lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, textK, textL, o.X, o.Y);
     }
     uint64_t axtNumber = 0;
 
@@ -240,19 +265,48 @@ int main(int argc, char** argv) {
         if (query.npart && (o.format == 0 || o.format == 6)) lzb_die("%s format can't handle multi-sequences", o.format == 0 ? "lav" : "gfa");
         if (query.npart && (o.selfCompare || o.segmentsFile || o.chain || o.anyOrNone))
             lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments, --chain or --anyornone yet");
+        if (query.npart && o.adaptive) lzb_die("lastz_b200 does not combine a [multi] query with an adaptive HSP threshold yet");
         int reported = 0;                                        /* --anyornone: alignments reported for this query */
-        for (int pass = 0; pass < 2; pass++) {
+        /* Order of work for one query (main, lastz.c:1566-1700): each strand is searched and finished in turn -- unless the
+         * HSP threshold is adaptive: then both strands are searched into ONE table (collectHspsFromBoth :1426), the table
+         * is split by strand (split_anchors :1678), and the - strand is finished BEFORE the + strand (:1680-1700). */
+        struct { int strand, search, finish; } steps[4]; int nsteps = 0;
+        const int doPlus = o.whichStrand >= 0, doMinus = o.whichStrand != 0;
+        if (!o.adaptive) {
+            if (doPlus)  { steps[nsteps].strand = 0; steps[nsteps].search = 1; steps[nsteps++].finish = 1; }
+            if (doMinus) { steps[nsteps].strand = 1; steps[nsteps].search = 1; steps[nsteps++].finish = 1; }
+        } else {
+            if (doPlus)  { steps[nsteps].strand = 0; steps[nsteps].search = 1; steps[nsteps++].finish = 0; }
+            if (doMinus) { steps[nsteps].strand = 1; steps[nsteps].search = 1; steps[nsteps++].finish = 0; }
+            if (doMinus) { steps[nsteps].strand = 1; steps[nsteps].search = 0; steps[nsteps++].finish = 1; }
+            if (doPlus)  { steps[nsteps].strand = 0; steps[nsteps].search = 0; steps[nsteps++].finish = 1; }
+        }
+        lzb_query* strandQ[2] = { NULL, NULL }; lzb_segment* strandSegs[2] = { NULL, NULL }; uint64_t strandN[2] = { 0, 0 };
+        int strandId[2] = { 0, 0 }, orientation = 0, tableSplit = 0; int32_t lowAnchorScore = 0;
+        lzb_hsptable table, others;                              /* anchors / secondaryAnchors of the adaptive flow */
+        if (o.adaptive) {                                        /* resolve_score_thresh dna_utilities.c:2220, limit_segment_table lastz.c:1399 */
+            lzb_hsptable_init(&table, adaptLimit);
+            lzb_hsptable_init(&others, 0);
+        }
+        for (int step = 0; step < nsteps; step++) {
+            const int pass = steps[step].strand;
             if (o.anyOrNone && reported) continue;               /* the search limit of 1 is per query, both strands */
-            if (pass == 0 && o.whichStrand < 0) continue;
-            if (pass == 1 && o.whichStrand == 0) continue;
-            if (pass == 1) lzb_seq_revcomp(&query);
-            lzb_query* Q = lzb_query_load(ctx, query.v, query.len);
-            if (!Q) lzb_die("%s", lzb_last_error());
+            if (pass != orientation) { lzb_seq_revcomp(&query); orientation = pass; }
+            if (steps[step].search) {
+                strandQ[pass] = lzb_query_load(ctx, query.v, query.len);
+                if (!strandQ[pass]) lzb_die("%s", lzb_last_error());
+                strandId[pass] = query.revCompFlags;
+            }
+            lzb_query* Q = strandQ[pass];
             lzb_segment* segs = NULL; uint64_t nsegs = 0;
-            if (o.segmentsFile) nsegs = read_segments(o.segmentsFile, &target, &query, &segs);
+            if (!steps[step].search) ;
+            else if (o.segmentsFile) nsegs = read_segments(o.segmentsFile, &target, &query, &segs);
             else {
                 lzb_seed_params sp; memset(&sp, 0, sizeof sp);
                 sp.gfExtend = o.gfExtend; sp.gfMismatches = o.gfMismatches; sp.xDrop = o.X; sp.hspThreshold = o.K; sp.entropy = o.entropy;
+                /* adaptive: every extension is an HSP candidate (seed_search.c:2907 rejects on score only for a fixed
+                 * threshold) and the entropy adjustment depends on the table as it stands (below) */
+                if (o.adaptive) { sp.hspThreshold = -600000000; sp.entropy = 0; }
                 sp.hashBits = o.hashBits; sp.selfCompare = o.selfCompare;
                 sp.sameStrand = o.selfCompare && query.revCompFlags == target.revCompFlags;
                 sp.strandId = query.revCompFlags;
@@ -265,7 +319,40 @@ int main(int argc, char** argv) {
             /* --self mirrors every HSP across the main diagonal when the run stops at HSPs (report_hsps /
              * collect_hsps lastz.c:3858-3880, :4050-4075; with gapped extension the mirroring moves to the
              * alignments, lastz.c:9055-9061) */
-            if (o.selfCompare && !o.gapped && !o.segmentsFile && nsegs) {
+            if (o.adaptive && steps[step].search) {
+                /* collect_hsps -> add_segment in discovery order.  An extension's score is entropy-adjusted only if it is
+                 * positive and could make the table as it stands (seed_search.c:2856-2863); its --self mirror follows it
+                 * with the same score (lastz.c:4050-4075). */
+                const int mirror = o.selfCompare && !o.gapped, same = query.revCompFlags == target.revCompFlags;
+                for (uint64_t k = 0; k < nsegs; k++) {
+                    lzb_segment g = segs[k];
+                    if (o.entropy && g.s > 0 && table.len > 0 && g.s >= table.lowScore)
+                        g.s = (int32_t)((double)g.s * lzb_hsp_entropy(target.v + g.pos1, query.v + g.pos2, g.length));
+                    lzb_hsptable_add(&table, &g);
+                    if (!mirror) continue;
+                    uint32_t len = g.length, e1 = g.pos1 + len, e2 = g.pos2 + len, s1, s2;
+                    if (same) { s1 = e1; s2 = e2; }
+                    else { s1 = target.len - e1 + len; s2 = query.len - e2 + len; if (s2 == e1 && s1 == e2) continue; }
+                    g.pos1 = s2 - len; g.pos2 = s1 - len; g.hspId = 0;
+                    lzb_hsptable_add(&table, &g);
+                }
+                lzb_free(segs); segs = NULL; nsegs = 0;
+            }
+            if (!steps[step].finish) continue;
+            if (o.adaptive) {
+                if (!tableSplit) {
+                    tableSplit = 1;
+                    if (doPlus && doMinus) {                     /* - strand stays in the table, + strand moves to the second one */
+                        lzb_hsptable_split(&table, strandId[1], &others);
+                        strandSegs[1] = table.seg; strandN[1] = table.len; strandSegs[0] = others.seg; strandN[0] = others.len;
+                    } else { strandSegs[pass] = table.seg; strandN[pass] = table.len; free(others.seg); }
+                    /* the gapped threshold follows the lowest HSP score kept, over both tables; an EMPTY table counts as
+                     * the worst possible score (finish_one_strand lastz.c:3278-3285, segment.c:127,209,1372) */
+                    lowAnchorScore = table.lowScore < others.lowScore ? table.lowScore : others.lowScore;
+                }
+                segs = strandSegs[pass]; nsegs = strandN[pass]; strandSegs[pass] = NULL;
+            }
+            if (!o.adaptive && o.selfCompare && !o.gapped && !o.segmentsFile && nsegs) {
                 lzb_segment* both = malloc(2 * nsegs * sizeof *both); uint64_t m = 0;
                 int same = query.revCompFlags == target.revCompFlags;
                 for (uint64_t k = 0; k < nsegs; k++) {
@@ -280,7 +367,11 @@ int main(int argc, char** argv) {
             }
             /* only the x-drop extension leaves real scores in the table (seed_search.c:2953); the other modes
              * are scored here when chaining or the gapped stage needs them (lastz.c:3336-3340, score_segments segment.c:1262) */
-            if (!o.segmentsFile && o.gfExtend != LZB_GFEX_XDROP && (o.chain || o.gapped))
+            /* adaptive, both strands: the + strand's HSPs were MOVED to the second table, which never saw an extension and
+             * so does not count as scored (haveScores: seed_search.c:2953 marks the table being searched into, segment.c:207
+             * clears it on the emptied one) -- they are scored again here, which undoes their entropy adjustment */
+            const int movedTable = o.adaptive && doPlus && doMinus && pass == 0;
+            if (!o.segmentsFile && (o.gfExtend != LZB_GFEX_XDROP || movedTable) && (o.chain || o.gapped))
                 for (uint64_t k = 0; k < nsegs; k++) {
                     int32_t sc = 0;
                     for (uint32_t j = 0; j < segs[k].length; j++) sc += ss.masked[(uint32_t)target.v[segs[k].pos1 + j] * 256 + query.v[segs[k].pos2 + j]];
@@ -346,6 +437,7 @@ int main(int argc, char** argv) {
             } else {
                 lzb_gapped_params gp; memset(&gp, 0, sizeof gp);
                 gp.yDrop = o.Y; gp.trimToPeak = o.trimToPeak; gp.scoreThreshold = o.L; gp.allBounds = o.allBounds;
+                if (o.adaptive && !o.haveL) gp.scoreThreshold = lowAnchorScore;   /* lastz.c:3405-3410 */
                 gp.inhibitTrivial = o.inhibitTrivial; gp.tracebackBytes = o.tracebackBytes;
                 gp.identityCheck = query.revCompFlags == target.revCompFlags;
                 gp.speculation = o.speculation;

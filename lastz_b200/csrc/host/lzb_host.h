@@ -76,9 +76,18 @@ extern const int8_t lzb_nuc_to_bits[256];                      /* dna_utilities.
 /* best-chain reduction (chain.c:497, penalties lastz.c:3687); rewrites segs[0..*n) to the chain, sorted by pos1 */
 int32_t lzb_reduce_to_chain(lzb_segment* segs, uint64_t* n, int32_t diagPen, int32_t antiPen, int32_t scale, int32_t subAA);
 
+/* adaptive.c -- HSP table of an adaptive threshold (add_segment segment.c:981): a list until the covered bases
+ * reach the limit, then a min-heap on score that drops whole groups of tied lowest scores */
+typedef struct lzb_hsptable { lzb_segment* seg; uint32_t len, cap; uint64_t coverage, limit; int32_t lowScore; } lzb_hsptable;
+void   lzb_hsptable_init(lzb_hsptable*, uint64_t coverageLimit);     /* limit 0 = keep everything, in arrival order */
+void   lzb_hsptable_add(lzb_hsptable*, const lzb_segment*);
+void   lzb_hsptable_split(lzb_hsptable*, int id, lzb_hsptable* rest); /* split_segment_table segment.c:1352 */
+void   lzb_hsptable_free(lzb_hsptable*);
+double lzb_hsp_entropy(const uint8_t* s, const uint8_t* t, uint32_t len);   /* entropy dna_utilities.c:2883 */
+
 /* output writers */
 void lzb_lav_job_header(FILE*, const char* prog, const char* name1, const char* name2,
-                        const char* args, const lzb_scoreset*, int32_t K, int32_t L);  /* lav.c:40 */
+                        const char* args, const lzb_scoreset*, const char* K, const char* L);  /* lav.c:40; thresholds as text (score_thresh_to_string) */
 void lzb_lav_strand_header(FILE*, const lzb_seq* s1, const lzb_seq* s2);               /* lav.c:101 */
 void lzb_lav_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);   /* lav.c:187 */
 void lzb_lav_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);   /* lav.c:327 */
@@ -94,7 +103,7 @@ void lzb_gfa_job_header(FILE*, const char* prog, const char* name1, const char* 
 void lzb_gfa_strand_header(FILE*, const lzb_seq* s1, const lzb_seq* s2);
 void lzb_gfa_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
 void lzb_gfa_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, const lzb_scoreset*);
-void lzb_axt_header(FILE*, const char* prog, const char* args, const lzb_scoreset*, int32_t K, int32_t L, int32_t X, int32_t Y);
+void lzb_axt_header(FILE*, const char* prog, const char* args, const lzb_scoreset*, const char* K, const char* L, int32_t X, int32_t Y);
 void lzb_axt_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, uint64_t* number);   /* axt.c:96, --format=axt */
 
 /* mirror.c -- mirror_alignments lastz.c:4229 (--self with gapped extension) */

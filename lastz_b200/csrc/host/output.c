@@ -8,7 +8,7 @@
 #include "lzb_host.h"
 
 void lzb_lav_job_header(FILE* f, const char* prog, const char* name1, const char* name2,
-                        const char* args, const lzb_scoreset* ss, int32_t K, int32_t L) {
+                        const char* args, const lzb_scoreset* ss, const char* K, const char* L) {
     const char* nuc = "ACGT";
     fprintf(f, "#:lav\nd {\n  \"%s %s %s %s\n", prog, name1, name2, args);
     /* print_score_matrix dna_utilities.c: column header, then one row per nucleotide */
@@ -20,7 +20,7 @@ void lzb_lav_job_header(FILE* f, const char* prog, const char* name1, const char
         for (int c = 0; c < 4; c++) fprintf(f, "%s%4d", c ? " " : "", ss->sub[nuc[r] * 256 + nuc[c]]);
         fprintf(f, "\n");
     }
-    fprintf(f, "  O = %d, E = %d, K = %d, L = %d, M = %d\"\n}\n", ss->gapOpen, ss->gapExtend, K, L, 0);
+    fprintf(f, "  O = %d, E = %d, K = %s, L = %s, M = %d\"\n}\n", ss->gapOpen, ss->gapExtend, K, L, 0);
 }
 
 void lzb_lav_strand_header(FILE* f, const lzb_seq* s1, const lzb_seq* s2) {
@@ -203,9 +203,9 @@ void lzb_maf_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alig
 
 /* ---- --format=axt, print_axt_align axt.c:96-255 (unpartitioned sequences).  The block number runs over the
  * whole output (axtAlignmentNumber).  The comment header carries the same parameters as the reference's. ---- */
-void lzb_axt_header(FILE* f, const char* prog, const char* args, const lzb_scoreset* ss, int32_t K, int32_t L, int32_t X, int32_t Y) {
+void lzb_axt_header(FILE* f, const char* prog, const char* args, const lzb_scoreset* ss, const char* K, const char* L, int32_t X, int32_t Y) {
     static const char acgt[4] = { 'A', 'C', 'G', 'T' };
-    fprintf(f, "# %s %s\n#\n# hsp_threshold      = %d\n# gapped_threshold   = %d\n# x_drop             = %d\n# y_drop             = %d\n"
+    fprintf(f, "# %s %s\n#\n# hsp_threshold      = %s\n# gapped_threshold   = %s\n# x_drop             = %d\n# y_drop             = %d\n"
                "# gap_open_penalty   = %d\n# gap_extend_penalty = %d\n", prog, args, K, L, X, Y, ss->gapOpen, ss->gapExtend);
     fprintf(f, "#        A    C    G    T\n");
     for (int r = 0; r < 4; r++) {

@@ -1,9 +1,9 @@
 /*
  * seeds.c -- spaced-seed parsing and packing recipe.  Reference: seeds.c:321-632
  * (parse_one_seed), :1399-1418 (best_shift).  The packing (which unpacked bit lands on which index
- * bit) must be the reference's own greedy recipe: transition variants are probed in ascending
- * PACKED bit order (seeds.c:615-625, seed_search.c:528-533), so the recipe decides the order in
- * which seed hits are discovered.
+ * bit) must be the reference's own greedy recipe: transition variants are probed in the order of
+ * transFlips[] (seed_search.c:528-533) -- rightmost seed position first (seeds.c:165,603-613) -- which decides the
+ * order in which seed hits are discovered.
  */
 #include <string.h>
 #include "lzb_host.h"
@@ -55,12 +55,13 @@ void lzb_seed_parse(lzb_seed* out, const char* pattern, int withTrans) {
         if (out->numParts >= LZB_MAX_SEED_PARTS) lzb_die("seed (%s) needs too many shift/mask parts", pattern);
         out->shift[out->numParts] = sh; out->mask[out->numParts] = m; out->numParts++;
     }
-    /* single-bit transition flips, lowest packed bit first */
-    uint32_t packed = 0;
-    for (int i = 0; i < out->numParts; i++) packed |= (uint32_t)(flips >> out->shift[i]) & out->mask[i];
-    while (packed) {
-        uint32_t low = packed & (~packed + 1);
-        packed -= low;
-        out->transFlips[out->numFlips++] = low;
+    /* single-bit transition flips in UNPACKED bit order, rightmost seed position first, each one carried through the
+     * packing (seeds.c:603-613: the reference builds with maintainFlippedBitOrder defined, seeds.c:165) */
+    while (flips) {
+        uint64_t low = flips & (~flips + 1);
+        flips -= low;
+        uint32_t packedBit = 0;
+        for (int i = 0; i < out->numParts; i++) packedBit |= (uint32_t)(low >> out->shift[i]) & out->mask[i];
+        out->transFlips[out->numFlips++] = packedBit;
     }
 }

@@ -170,6 +170,28 @@ GFA_CASES = [
 ]
 
 
+# adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
+# strands collected into one table and the - strand finished first, lastz.c:1426,1678-1700): target suffix, query, options
+ADAPTIVE_CASES = [
+    ("aglobin", ["K=top50%", "C=3", "W=8", "T=0", "--noentropy", "--gfa"]),          # base_test_adaptive_k, Makefile:317
+    ("aglobin", ["K=top50%", "--nogapped", "--format=general-"]),                      # entropy decided against the table as it stands
+    ("aglobin", ["K=top5K", "--format=maf-"]),                                         # gapped threshold = lowest HSP kept
+    ("aglobin", ["K=top5K", "--strand=minus", "--format=maf-"]),                       # one strand: the second table is empty
+    ("aglobin", ["K=top30%", "--chain", "--format=general-"]),
+    ("catpig", ["--hspthresh=top2.5%", "--nogapped", "--chain"]),                      # + strand HSPs rescored after the split
+    ("catpig", ["K=top20%", "--format=lav"]),                                          # header prints top<bases>
+    ("catpig", ["K=top20%", "L=2500", "--format=axt"]),
+    ("catpig", ["K=top1500", "--format=general-"]),
+    ("catpig", ["K=top100%", "--nogapped", "--format=general-"]),                      # the limit is never met: a plain list
+]
+
+
+def adaptive_case_files(which):
+    if which == "aglobin":
+        return [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, "aglobin.2bit") + "/cow"]
+    return [os.path.join(GOLDEN, "pseudocat.fa"), os.path.join(GOLDEN, "pseudopig.fa")]
+
+
 # --anyornone (gappily_extend_hsps gapped_extend.c:5279): first HSP, in discovery order, whose
 # unconstrained gapped extension reaches the threshold; one alignment per query, both strands
 ANYORNONE_CASES = [

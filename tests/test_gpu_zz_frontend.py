@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import ANYORNONE_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
+from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, GFA_CASES, GOLDEN, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
 
 pytestmark = pytest.mark.gpu
 
@@ -24,3 +24,19 @@ def test_cli_gfa_format(a1, a2, opts):
 def test_cli_anyornone(opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
     same_output(run_cli(PRODUCT_CLI, [CAT, PIG] + opts)[0], run_cli(ref, [CAT, PIG] + opts)[0])
+
+
+@pytest.mark.parametrize("which,opts", ADAPTIVE_CASES)
+def test_cli_adaptive_threshold(which, opts):
+    """K=top<N>%: the library returns every extension (threshold far below any score, entropy off) and the front end
+    replays the reference's coverage-limited heap over them in discovery order"""
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    files = adaptive_case_files(which)
+    same_output(run_cli(PRODUCT_CLI, files + opts)[0], run_cli(ref, files + opts)[0])
+
+
+def test_cli_variant_order_fixture():
+    files = [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, "aglobin.2bit") + "/cow[20000..32000]"]
+    out, _ = run_cli(PRODUCT_CLI, files + ["--nogfextend", "--nogapped", "--strand=plus", "--format=general-"])
+    got = ["\t".join((l.split("\t")[4], l.split("\t")[9])) for l in out.splitlines()]
+    assert got == open(os.path.join(GOLDEN, "aglobin_cow_20k_32k.plus_hits.order.tsv")).read().splitlines()

@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -274,3 +274,31 @@ def test_oracle_anyornone(opts):
     same_output(run_cli(ORACLE_CLI, [CAT, PIG] + opts)[0], run_cli(REF_CLI, [CAT, PIG] + opts)[0])
     multi = [AGLOBIN + "/human", os.path.join(GOLDEN, "shorties.fa")] + opts      # 20 query sequences
     same_output(run_cli(ORACLE_CLI, multi)[0], run_cli(REF_CLI, multi)[0])
+
+
+def test_oracle_adaptive_k_golden():
+    """base_test_adaptive_k (Makefile:317-327): K=top50% HSPs in GFA, compared like the reference's own test: the 'a'
+    lines, sorted."""
+    out, _ = run_cli(ORACLE_CLI, adaptive_case_files("aglobin") + ["C=3", "W=8", "T=0", "--noentropy", "K=top50%", "--gfa"])
+    got = sorted(l for l in out.splitlines() if l.startswith("a"))
+    want = sorted(open(os.path.join(GOLDEN, "base_test.adaptive_k.gfa")).read().splitlines())
+    assert got == want
+
+
+@pytest.mark.parametrize("which,opts", ADAPTIVE_CASES)
+def test_oracle_adaptive_threshold_matches_reference(which, opts):
+    """byte for byte, so the table's heap order (what --nogapped prints) is the reference's too"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    files = adaptive_case_files(which)
+    same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])
+
+
+def test_oracle_variant_order_fixture():
+    """Seed hits at one query position are discovered exact word first, then the transition variants in the order of
+    seed->transFlips: rightmost seed position first (seeds.c:165,603-613).  pseudocat/pseudopig never has two variants
+    hitting at one position; this stretch of aglobin does (fixture: tests/golden/make_ref_fixtures.sh)."""
+    files = [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, "aglobin.2bit") + "/cow[20000..32000]"]
+    out, _ = run_cli(ORACLE_CLI, files + ["--nogfextend", "--nogapped", "--strand=plus", "--format=general-"])
+    got = ["\t".join((l.split("\t")[4], l.split("\t")[9])) for l in out.splitlines()]
+    assert got == open(os.path.join(GOLDEN, "aglobin_cow_20k_32k.plus_hits.order.tsv")).read().splitlines()

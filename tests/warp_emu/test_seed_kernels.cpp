@@ -87,8 +87,11 @@ static void parse_seed(lzb_seed* out, const char* pattern, int withTrans) {
         covered += m; rem -= (u64)m << bestShift;
         out->shift[out->numParts] = bestShift; out->mask[out->numParts] = m; out->numParts++;
     }
-    u32 packed = 0; for (int i = 0; i < out->numParts; i++) packed |= (u32)(flips >> out->shift[i]) & out->mask[i];
-    while (packed) { u32 low = packed & (~packed + 1); packed -= low; out->transFlips[out->numFlips++] = low; }
+    while (flips) {                                                    // rightmost seed position first, seeds.c:603-613
+        u64 low = flips & (~flips + 1); flips -= low; u32 bit = 0;
+        for (int i = 0; i < out->numParts; i++) bit |= (u32)(low >> out->shift[i]) & out->mask[i];
+        out->transFlips[out->numFlips++] = bit;
+    }
 }
 static u32 host_word_at(const u8* v, u32 endPos, const lzb_seed* sd, const int8_t* ctb) {
     u64 w = 0; for (int j = 0; j < sd->length; j++) w = (w << 2) | (u64)(ctb[v[endPos - sd->length + j]] & 3);
@@ -108,12 +111,13 @@ static int g_bad = 0;
 
 struct mode { const char* name; int gfExtend, mismatches, K, plain, entropy, hashBits, useFirstKernel; };
 
-static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u32 step, const std::vector<mode>& modes) {
+static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u32 step, const std::vector<mode>& modes, u32 partitionEvery = 0) {
     std::string t, q; const char* acgt = "ACGT";
     for (u32 i = 0; i < len; i++) t.push_back(acgt[rnd() & 3]);
     for (u32 i = 0; i < len; i++) { u64 r = rnd() % 1000; if (r < 50) q.push_back(acgt[rnd() & 3]); else if (r < 55) continue; else if (r < 60) { q.push_back(t[i]); q.push_back(acgt[rnd() & 3]); } else q.push_back(t[i]); }
     for (u32 i = len / 3; i < len / 3 + 400 && i < q.size(); i++) q[i] = (char)tolower(q[i]);        // a soft-masked stretch
     for (u32 i = len / 2; i < len / 2 + 60 && i < t.size(); i++) t[i] = 'N';                          // and a run of N
+    if (partitionEvery) for (u32 i = partitionEvery; i + 1 < q.size(); i += partitionEvery + (u32)(rnd() % 97)) q[i] = 0;   // a [multi] query: NUL between partitions (sequences.h:188)
     const u32 len1 = (u32)t.size(), len2 = (u32)q.size();
     lzb_seed seed; parse_seed(&seed, pattern, withTrans);
     int8_t ctb[256]; memset(ctb, -1, 256); ctb['A'] = 0; ctb['C'] = 1; ctb['G'] = 2; ctb['T'] = 3;
@@ -263,6 +267,13 @@ int main() {
         { "--mismatch=1,25, 2^8 buckets", LZB_GFEX_MISMATCH, 1, 25, 0, 0, 8, 0 },
     };
     one_pair(1, 15000, "111111111111", 0, 3, b);
+    std::vector<mode> c = {
+        { "[multi] query, x-drop",       LZB_GFEX_XDROP, 0, 2200, 0, 1, 16, 0 },
+        { "every extension kept (K=top%)", LZB_GFEX_XDROP, 0, -600000000, 0, 0, 16, 0 },   // what an adaptive threshold asks of the library
+        { "[multi] query, --exact=25",   LZB_GFEX_EXACT, 0, 25, 0, 0, 16, 0 },
+        { "[multi] query, raw hits",     LZB_GFEX_NONE, 0, 0, 1, 0, 16, 1 },
+    };
+    one_pair(2, 12000, "1110100110010101111", 1, 1, c, 311);
     printf("%d checks failed, %llu collectives emulated\n", g_bad, emu_collectives);
     return g_bad ? 1 : 0;
 }
