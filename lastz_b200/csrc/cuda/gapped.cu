@@ -289,11 +289,14 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     if (!c->haveScoring) return lzb_fail("lzb_set_scoring has not been called");
     if (P->tracebackBytes < 8) return lzb_fail("in new_traceback(), size can't be %u", P->tracebackBytes);
     if (c->sc.gapOpen < 0) return lzb_fail("lastz_b200's Y-drop kernel requires a non-negative gap open penalty (got %d)", c->sc.gapOpen);
-    /* [multi] sequences (NUL-separated partitions, sequences.h:188-191) need per-partition DP limits
-     * (gapped_extend.c:1357-1372).  The oracle and the front end implement them; this library was not run on such
-     * input on a GPU in round 1, so it says so instead of extending across partition borders. */
-    if (memchr(t->h_seq, 0, t->len) || memchr(q->h_seq, 0, q->len))
-        return lzb_fail("the CUDA library does not extend anchors in partitioned ([multi]) sequences yet; use --nogapped or one sequence at a time");
+    /* [multi] sequences (NUL-separated partitions, sequences.h:188-191): a sweep ends at the NULs around its anchor
+     * (gapped_extend.c:1357-1372).  Query partitions are handled below (the limits go into the job's N); a partitioned
+     * TARGET also needs the anchors extended in per-partition batches (gapped_extend.c:1058), which is not built. */
+    if (memchr(t->h_seq, 0, t->len))
+        return lzb_fail("the CUDA library does not extend anchors in a partitioned ([multi]) target yet; use --nogapped or one sequence at a time");
+    std::vector<u32> qSeparators;                                /* positions of the NULs inside the query, ascending */
+    for (const u8* z = (const u8*)memchr(q->h_seq, 0, q->len); z; z = (const u8*)memchr(z + 1, 0, q->len - (size_t)(z + 1 - q->h_seq)))
+        qSeparators.push_back((u32)(z - q->h_seq));
     auto wall0 = std::chrono::steady_clock::now();
     u64 launches0 = c->launches;
     *list = NULL;
@@ -455,7 +458,13 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             if (onlySide >= 0 && side != onlySide) { J.skip = 1; continue; }     /* kernel returns at once */
             int rev = side == 0;
             J.reversed = rev; J.a1 = m.pos1; J.a2 = m.pos2;
-            J.M = rev ? m.pos1 + 1 : len1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 : len2 - (m.pos2 + 1);
+            u32 low2 = 0, high2 = len2;                          /* the anchor's partition: first base, one past the last */
+            if (!qSeparators.empty()) {
+                auto after = std::upper_bound(qSeparators.begin(), qSeparators.end(), m.pos2);
+                if (after != qSeparators.end()) high2 = *after;
+                if (after != qSeparators.begin()) low2 = *(after - 1) + 1;
+            }
+            J.M = rev ? m.pos1 + 1 : len1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 - low2 : high2 - (m.pos2 + 1);
             /* initial L/R, gapped_extend.c:3500-3543 */
             s32 L = 0, R = (s32)(J.N + 1);
             if (mLeft.al >= 0) { hseg& s = G.al[mLeft.al].segs[mLeft.sg]; L = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) L -= (s32)(s.b1 - m.pos1); }

@@ -170,6 +170,10 @@ GFA_CASES = [
 ]
 
 
+# [multi] queries (sequences.h:188-191: the sequences of a file joined by NULs; hits, extensions and DP sweeps stop at them)
+MULTI_QUERY_CASES = [["--format=general-"], ["--format=general-", "--nogapped"], ["--format=maf-", "--strand=minus"],
+                     ["--format=axt", "W=8", "T=0"], ["--format=general-", "--exact=14", "--nogapped", "W=8", "T=0"]]
+
 # adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
 # strands collected into one table and the - strand finished first, lastz.c:1426,1678-1700): target suffix, query, options
 ADAPTIVE_CASES = [

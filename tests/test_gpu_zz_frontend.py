@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, GFA_CASES, GOLDEN, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
+from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
 
 pytestmark = pytest.mark.gpu
 
@@ -40,3 +40,18 @@ def test_cli_variant_order_fixture():
     out, _ = run_cli(PRODUCT_CLI, files + ["--nogfextend", "--nogapped", "--strand=plus", "--format=general-"])
     got = ["\t".join((l.split("\t")[4], l.split("\t")[9])) for l in out.splitlines()]
     assert got == open(os.path.join(GOLDEN, "aglobin_cow_20k_32k.plus_hits.order.tsv")).read().splitlines()
+
+
+@pytest.mark.parametrize("opts", MULTI_QUERY_CASES)
+def test_cli_multi_query(opts):
+    """[multi] query: seeds and x-drop scans stop at the NUL separators by themselves (no seed word spans one, their
+    substitution score ends any scan); the gapped stage cuts each sweep at the separators around its anchor"""
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    args = [CAT, PIG + "[multi]"] + opts
+    same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])
+
+
+def test_cli_multi_subrange_golden():
+    """base_test_multi_subrange (Makefile:582) through the product"""
+    out, _ = run_cli(PRODUCT_CLI, [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, "shorties.2bit") + "[multi,51..200]", "K=3000", "--maf-"])
+    assert out == open(os.path.join(GOLDEN, "base_test.multi_subrange.maf")).read()

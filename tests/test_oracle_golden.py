@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, MULTI_QUERY_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -153,8 +153,7 @@ def test_oracle_multi_subrange_golden():
     assert out == open(os.path.join(GOLDEN, "base_test.multi_subrange.maf")).read()
 
 
-@pytest.mark.parametrize("opts", [["--format=general-"], ["--format=general-", "--nogapped"], ["--format=maf-", "--strand=minus"],
-                                  ["--format=axt", "W=8", "T=0"], ["--format=general-", "--exact=14", "--nogapped", "W=8", "T=0"]])
+@pytest.mark.parametrize("opts", MULTI_QUERY_CASES)
 def test_oracle_multi_query_matches_reference(opts):
     if not os.path.exists(REF_CLI):
         pytest.skip("oracle/_ref not built")
