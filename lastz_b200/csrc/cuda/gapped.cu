@@ -290,11 +290,12 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     if (P->tracebackBytes < 8) return lzb_fail("in new_traceback(), size can't be %u", P->tracebackBytes);
     if (c->sc.gapOpen < 0) return lzb_fail("lastz_b200's Y-drop kernel requires a non-negative gap open penalty (got %d)", c->sc.gapOpen);
     /* [multi] sequences (NUL-separated partitions, sequences.h:188-191): a sweep ends at the NULs around its anchor
-     * (gapped_extend.c:1357-1372).  Query partitions are handled below (the limits go into the job's N); a partitioned
-     * TARGET also needs the anchors extended in per-partition batches (gapped_extend.c:1058), which is not built. */
-    if (memchr(t->h_seq, 0, t->len))
-        return lzb_fail("the CUDA library does not extend anchors in a partitioned ([multi]) target yet; use --nogapped or one sequence at a time");
-    std::vector<u32> qSeparators;                                /* positions of the NULs inside the query, ascending */
+     * (gapped_extend.c:1357-1372); the limits go into the job's M and N.  Alignments of different partitions cannot
+     * meet, so one pass over all anchors gives what the reference's per-partition batches give (gapped_extend.c:1058).
+     * The trivial self-alignment of identical PARTITIONS (:1185-1290) is not built: callers keep such pairs away. */
+    std::vector<u32> tSeparators, qSeparators;                   /* positions of the NULs inside each sequence, ascending */
+    for (const u8* z = (const u8*)memchr(t->h_seq, 0, t->len); z; z = (const u8*)memchr(z + 1, 0, t->len - (size_t)(z + 1 - t->h_seq)))
+        tSeparators.push_back((u32)(z - t->h_seq));
     for (const u8* z = (const u8*)memchr(q->h_seq, 0, q->len); z; z = (const u8*)memchr(z + 1, 0, q->len - (size_t)(z + 1 - q->h_seq)))
         qSeparators.push_back((u32)(z - q->h_seq));
     auto wall0 = std::chrono::steady_clock::now();
@@ -458,13 +459,18 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             if (onlySide >= 0 && side != onlySide) { J.skip = 1; continue; }     /* kernel returns at once */
             int rev = side == 0;
             J.reversed = rev; J.a1 = m.pos1; J.a2 = m.pos2;
-            u32 low2 = 0, high2 = len2;                          /* the anchor's partition: first base, one past the last */
+            u32 low1 = 0, high1 = len1, low2 = 0, high2 = len2;  /* the anchor's partition in each sequence: first base, one past the last */
+            if (!tSeparators.empty()) {
+                auto after = std::upper_bound(tSeparators.begin(), tSeparators.end(), m.pos1);
+                if (after != tSeparators.end()) high1 = *after;
+                if (after != tSeparators.begin()) low1 = *(after - 1) + 1;
+            }
             if (!qSeparators.empty()) {
                 auto after = std::upper_bound(qSeparators.begin(), qSeparators.end(), m.pos2);
                 if (after != qSeparators.end()) high2 = *after;
                 if (after != qSeparators.begin()) low2 = *(after - 1) + 1;
             }
-            J.M = rev ? m.pos1 + 1 : len1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 - low2 : high2 - (m.pos2 + 1);
+            J.M = rev ? m.pos1 + 1 - low1 : high1 - (m.pos1 + 1); J.N = rev ? m.pos2 + 1 - low2 : high2 - (m.pos2 + 1);
             /* initial L/R, gapped_extend.c:3500-3543 */
             s32 L = 0, R = (s32)(J.N + 1);
             if (mLeft.al >= 0) { hseg& s = G.al[mLeft.al].segs[mLeft.sg]; L = (s32)(s.b2 - m.pos2); if (s.type == SEG_DIAG) L -= (s32)(s.b1 - m.pos1); }

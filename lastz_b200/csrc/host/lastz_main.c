@@ -9,6 +9,7 @@
  */
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include "lzb_host.h"
 
 typedef struct {
@@ -222,7 +223,6 @@ int main(int argc, char** argv) {
     lzb_seq target;
     if (!lzb_seqfile_next(tf, &target)) lzb_die("%s contains no sequence", o.targetSpec);
     { lzb_seq extra; if (lzb_seqfile_next(tf, &extra)) lzb_die("%s contains more than one sequence, consider using the \"multiple\" action", o.targetSpec); }
-    if (target.npart) lzb_die("lastz_b200 does not implement [multi] on the target yet (anchors are extended in per-partition batches, gapped_extend.c:1058); [multi] on the query is supported");
 
     lzb_ctx* ctx = lzb_open(o.device);
     if (!ctx) lzb_die("%s", lzb_last_error());
@@ -262,7 +262,24 @@ int main(int argc, char** argv) {
     lzb_seq query;
     while (lzb_seqfile_next(qf, &query)) {
         if (query.len == 0) { lzb_seq_free(&query); continue; }
-        if (query.npart && (o.format == 0 || o.format == 6)) lzb_die("%s format can't handle multi-sequences", o.format == 0 ? "lav" : "gfa");
+        if ((query.npart || target.npart) && (o.format == 0 || o.format == 6)) lzb_die("%s format can't handle multi-sequences", o.format == 0 ? "lav" : "gfa");
+        if (target.npart) {
+            /* a partitioned target: hits, extensions and DP sweeps stop at its NULs like they do in a partitioned query.
+             * Not built: what the reference does PER PARTITION -- chaining (chain.c:278-340), the segments writer's rows,
+             * and the trivial self-alignment of a query that equals one target partition, which bounds every other
+             * alignment (identical_partition_of_sequence gapped_extend.c:2034, :1185-1230).  Such runs stop here. */
+            if (o.selfCompare || o.segmentsFile || o.chain || o.anyOrNone || o.adaptive || o.inhibitTrivial || o.format == 1)
+                lzb_die("lastz_b200 does not combine a [multi] target with --self, --notrivial, --segments, --format=segments, --chain, --anyornone or an adaptive threshold yet");
+            if (o.gapped && o.whichStrand >= 0 && query.revCompFlags == target.revCompFlags) {     /* only the + strand pass can be trivial */
+                int twin = 0;
+                if (query.npart) twin = query.len == target.len && !strncasecmp((const char*)query.v + 1, (const char*)target.v + 1, query.len - 1);
+                else for (uint32_t p = 0; p < target.npart && !twin; p++) {
+                    const lzb_partition* tp = &target.part[p];
+                    twin = tp->sepAfter - (tp->sepBefore + 1) == query.len && !strncasecmp((const char*)query.v, (const char*)target.v + tp->sepBefore + 1, query.len);
+                }
+                if (twin) lzb_die("%s is identical to (part of) the [multi] target; lastz_b200 does not build the trivial self-alignment of partitions yet", query.shortHeader ? query.shortHeader : "the query");
+            }
+        }
         if (query.npart && (o.selfCompare || o.segmentsFile || o.chain || o.anyOrNone))
             lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments, --chain or --anyornone yet");
         if (query.npart && o.adaptive) lzb_die("lastz_b200 does not combine a [multi] query with an adaptive HSP threshold yet");
@@ -439,7 +456,7 @@ int main(int argc, char** argv) {
                 gp.yDrop = o.Y; gp.trimToPeak = o.trimToPeak; gp.scoreThreshold = o.L; gp.allBounds = o.allBounds;
                 if (o.adaptive && !o.haveL) gp.scoreThreshold = lowAnchorScore;   /* lastz.c:3405-3410 */
                 gp.inhibitTrivial = o.inhibitTrivial; gp.tracebackBytes = o.tracebackBytes;
-                gp.identityCheck = query.revCompFlags == target.revCompFlags;
+                gp.identityCheck = query.revCompFlags == target.revCompFlags && !query.npart && !target.npart;   /* identical_sequences: unpartitioned only, gapped_extend.c:1147 */
                 gp.speculation = o.speculation;
                 if (lzb_reduce_to_points(ctx, T, Q, segs, nsegs)) lzb_die("%s", lzb_last_error());
                 lzb_alignel* list = NULL;

@@ -174,6 +174,16 @@ GFA_CASES = [
 MULTI_QUERY_CASES = [["--format=general-"], ["--format=general-", "--nogapped"], ["--format=maf-", "--strand=minus"],
                      ["--format=axt", "W=8", "T=0"], ["--format=general-", "--exact=14", "--nogapped", "W=8", "T=0"]]
 
+# [multi] TARGETS (and both sides partitioned): (target, query, options), files relative to tests/golden
+MULTI_TARGET_CASES = [
+    ("pseudopig.fa[multi]", "pseudocat.fa", ["--format=general-"]),
+    ("pseudopig.fa[multi]", "pseudocat.fa", ["--format=maf", "--nogapped"]),
+    ("aglobin.2bit[multi]", "shorties.fa", ["--format=general-", "K=2500"]),
+    ("aglobin.2bit[multi]", "shorties.fa[multi]", ["--format=axt", "K=2500"]),
+    ("shorties.fa[multi]", "aglobin.2bit/human", ["--format=axt", "K=2500", "--noytrim"]),
+    ("shorties.2bit[multi,51..200]", "aglobin.2bit/human", ["--format=maf-", "K=3000", "--strand=minus"]),
+]
+
 # adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
 # strands collected into one table and the - strand finished first, lastz.c:1426,1678-1700): target suffix, query, options
 ADAPTIVE_CASES = [

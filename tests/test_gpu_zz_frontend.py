@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
+from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
 
 pytestmark = pytest.mark.gpu
 
@@ -55,3 +55,10 @@ def test_cli_multi_subrange_golden():
     """base_test_multi_subrange (Makefile:582) through the product"""
     out, _ = run_cli(PRODUCT_CLI, [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, "shorties.2bit") + "[multi,51..200]", "K=3000", "--maf-"])
     assert out == open(os.path.join(GOLDEN, "base_test.multi_subrange.maf")).read()
+
+
+@pytest.mark.parametrize("target,query,opts", MULTI_TARGET_CASES)
+def test_cli_multi_target(target, query, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    args = [os.path.join(GOLDEN, target), os.path.join(GOLDEN, query)] + opts
+    same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])

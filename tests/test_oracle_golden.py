@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, MULTI_QUERY_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -159,6 +159,24 @@ def test_oracle_multi_query_matches_reference(opts):
         pytest.skip("oracle/_ref not built")
     args = [CAT, PIG + "[multi]"] + opts
     same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
+@pytest.mark.parametrize("target,query,opts", MULTI_TARGET_CASES)
+def test_oracle_multi_target_matches_reference(target, query, opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    args = [os.path.join(GOLDEN, target), os.path.join(GOLDEN, query)] + opts
+    same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
+def test_multi_target_refusals():
+    """what a partitioned target does not do yet stops with a FAILURE instead of giving other results than the reference"""
+    import subprocess
+    t = os.path.join(GOLDEN, "aglobin.2bit[multi]")
+    for q, opts in [("aglobin.2bit/cow", []), ("shorties.fa", ["--chain"]), ("shorties.fa", ["--notrivial"]), ("shorties.fa", ["--format=lav"]),
+                    ("shorties.fa", ["K=top20%"]), ("shorties.fa", ["--nogapped", "--format=segments"])]:
+        p = subprocess.run([ORACLE_CLI, t, os.path.join(GOLDEN, q)] + opts, capture_output=True, text=True)
+        assert p.returncode != 0 and "FAILURE" in p.stderr, (q, opts)
 
 
 def test_oracle_segments_round_trip(tmp_path):

@@ -67,7 +67,8 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
         else if (r < sub + indel) { q.push_back(t[i]); q.push_back(acgt[rnd() & 3]); }
         else q.push_back(t[i]);
     }
-    if (partitioned) { q[q.size() / 3] = 0; q[2 * q.size() / 3] = 0; }   // a [multi] query: the sweeps must stop at the NULs around the anchor (gapped_extend.c:1357-1372)
+    if (partitioned) { q[q.size() / 3] = 0; q[2 * q.size() / 3] = 0; }
+    if (partitioned == 2) { t[t.size() / 3 + 40] = 0; t[2 * t.size() / 3 - 55] = 0; }   // ... and a [multi] target, cut elsewhere   // a [multi] query: the sweeps must stop at the NULs around the anchor (gapped_extend.c:1357-1372)
     const u32 len1 = (u32)t.size(), len2 = (u32)q.size();
     // anchor somewhere in the middle, on the homologous diagonal as far as we can tell: use the oracle's own seed stage
     lzb_ctx* oc = lzb_open(0);
@@ -95,12 +96,15 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
     u32 lo2 = a2, hi2 = a2;                                            // the anchor's partition, as gapped.cu's launch() cuts it
     while (lo2 > 0 && q[lo2 - 1] != 0) lo2--;
     while (hi2 < len2 && q[hi2] != 0) hi2++;
+    u32 lo1 = a1, hi1 = a1;
+    while (lo1 > 0 && t[lo1 - 1] != 0) lo1--;
+    while (hi1 < len1 && t[hi1] != 0) hi1++;
     dp_job jobs[2]; memset(jobs, 0, sizeof jobs);
     std::vector<u8> tb[2]; std::vector<u32> tbRow[2], ops[2]; std::vector<int> act[2];
     for (int side = 0; side < 2; side++) {
         dp_job& J = jobs[side]; const int rev = side == 0;
         J.reversed = rev; J.a1 = a1; J.a2 = a2;
-        J.M = rev ? a1 + 1 : len1 - (a1 + 1); J.N = rev ? a2 + 1 - lo2 : hi2 - (a2 + 1);
+        J.M = rev ? a1 + 1 - lo1 : hi1 - (a1 + 1); J.N = rev ? a2 + 1 - lo2 : hi2 - (a2 + 1);
         J.L0 = 0; J.R0 = (s32)(J.N + 1); J.leftSeg = { -1, -1 }; J.rightSeg = { -1, -1 }; J.alignList = -1; J.al = NULL;
         tb[side].resize((size_t)tbBytes + 64); tbRow[side].resize(len1 + len2 + 16); ops[side].resize(2 * (len1 + len2) + 16); act[side].resize(5 * 16);
         J.tb = tb[side].data(); J.tbLen = tbLen; J.tbRow = tbRow[side].data(); J.tbRowCap = (u32)tbRow[side].size();
@@ -146,6 +150,8 @@ int main() {
     bad += one_case(n++, 2000, 0.04, 0.010, 80u << 20, 9400, 1, 2);      // k_ydrop<256> (shared-memory ring)
     bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 1, 0, 1);   // partitioned query: both sweeps end at a NUL
     bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 0, 0, 1);   // ... --noytrim: the partition edge is a sequence edge
+    bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 1, 0, 2);   // target and query both partitioned
+    bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 0, 0, 2);
     bad += one_case(n++, 2000, 0.07, 0.020, 150000, 9400, 0, 2);         // ... truncated, --noytrim
     printf("%d cases, %d mismatching, %llu collectives emulated\n", n, bad, emu_collectives);
     return bad ? 1 : 0;
