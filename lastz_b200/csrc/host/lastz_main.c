@@ -23,7 +23,9 @@ typedef struct {
     uint32_t tracebackBytes;
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
-    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa */
+    int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa, 7 cigar, 8 sam */
+    int samSoft, samEqx, samHeader;
+    lzb_fieldlist* fields;         /* columns of --format=general[-][:<names>] / mapping[-] */
     int device, showStats, speculation, mafHeader;
     int anyOrNone;                                           /* --anyornone: hspImmediate + searchLimit 1 (lastz.c:5962) */
     int nIsAmbiguous; int32_t ambiMatch, ambiMismatch;     /* --ambiguous=n[,[<match>,]<penalty>] lastz.c:5767-5852 */
@@ -146,8 +148,21 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--format=maf") || !strcmp(a, "--maf")) { o->format = 4; o->mafHeader = 1; }
         else if (!strcmp(a, "--format=gfa") || !strcmp(a, "--gfa")) o->format = 6;
         else if (!strcmp(a, "--format=segments")) o->format = 1;
-        else if (!strcmp(a, "--format=general")) o->format = 2;          /* default fields, genpaf.h:117 */
-        else if (!strcmp(a, "--format=general-")) o->format = 3;         /* ... without the header line */
+        else if (!strcmp(a, "--format=general") || !strcmp(a, "--format=gen")) { o->format = 2; o->fields = lzb_fieldlist_standard(); }   /* default fields, genpaf.h:117 */
+        else if (!strcmp(a, "--format=general-") || !strcmp(a, "--format=gen-")) { o->format = 3; o->fields = lzb_fieldlist_standard(); } /* ... without the header line */
+        else if (starts(a, "--format=general:") || starts(a, "--format=gen:")) { o->format = 2; o->fields = lzb_fieldlist_parse(strchr(a, ':') + 1); }   /* lastz.c:7319 */
+        else if (starts(a, "--format=general-:") || starts(a, "--format=gen-:")) { o->format = 3; o->fields = lzb_fieldlist_parse(strchr(a, ':') + 1); }
+        else if (!strcmp(a, "--format=mapping")) { o->format = 2; o->fields = lzb_fieldlist_mapping(); }                                 /* lastz.c:7347 */
+        else if (!strcmp(a, "--format=mapping-")) { o->format = 3; o->fields = lzb_fieldlist_mapping(); }
+        else if (!strcmp(a, "--format=cigar") || !strcmp(a, "--cigar")) o->format = 7;
+        else if (starts(a, "--format=sam") || starts(a, "--format=softsam") || starts(a, "--sam") || starts(a, "--softsam")) {           /* lastz.c:7170-7248 */
+            const char* n = starts(a, "--format=") ? a + 9 : a + 2;
+            o->samSoft = starts(n, "soft"); n += o->samSoft ? 7 : 3;
+            o->samEqx = starts(n, "+eqx"); if (o->samEqx) n += 4;
+            o->samHeader = n[0] != '-';
+            if (strcmp(n, "") && strcmp(n, "-")) lzb_die("lastz_b200 does not implement option \"%s\" (seed-and-extend hot path only)", a);
+            o->format = 8;
+        }                                                  /* lastz.c:7250 */
         else if (!strcmp(a, "--format=maf-")) o->format = 4;             /* MAF blocks, no parameter header */
         /* lastz_b200 additions */
         else if (starts(a, "--device=")) o->device = atoi(v);
@@ -238,7 +253,8 @@ int main(int argc, char** argv) {
     if (o.adaptive && !o.haveL) snprintf(textL, sizeof textL, "top%u", adaptLimit); else snprintf(textL, sizeof textL, "%d", o.L);
     if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, textK, textL);
     else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
-    else if (o.format == 2) lzb_general_header(out);
+    else if (o.format == 2) lzb_fieldlist_header(out, o.fields);
+    else if (o.format == 8 && o.samHeader) lzb_sam_header(out, &target);
     else if (o.format == 6) {                                    /* file names without actions or 2bit contig (seq->filename) */
         char n1[1024], n2[1024]; char* cut;
         snprintf(n1, sizeof n1, "%s", o.targetSpec); snprintf(n2, sizeof n2, "%s", o.querySpec);
@@ -253,7 +269,7 @@ int main(int argc, char** argv) {
         fprintf(out, "##maf version=1 scoring=lastz.v1.04.58\n");
         lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, textK, textL, o.X, o.Y);
     }
-    uint64_t axtNumber = 0;
+    uint64_t axtNumber = 0, rowNumber = 0;
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
     uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
@@ -425,7 +441,9 @@ int main(int argc, char** argv) {
                         else if (o.format == 4) lzb_maf_align(out, &target, &query, a);
                         else if (o.format == 5) lzb_axt_align(out, &target, &query, a, &axtNumber);
                         else if (o.format == 6) { if (!hd) { lzb_gfa_strand_header(out, &target, &query); hd = 1; } lzb_gfa_align(out, &target, &query, a, &ss); }
-                        else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
+                        else if (o.format == 7) lzb_cigar_align(out, &target, &query, a);
+                    else if (o.format == 8) lzb_sam_align(out, &target, &query, a, o.samEqx, o.samSoft);
+                        else if (o.format >= 2) lzb_fieldlist_align(out, o.fields, &target, &query, a, &rowNumber);
                     }
                     lzb_free_align_list(one);
                     lzb_query_free(Q);
@@ -448,7 +466,9 @@ int main(int argc, char** argv) {
                         if (!headerDone) { lzb_gfa_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_gfa_match(out, &target, &query, &segs[k]);
                     }
-                    else if (o.format >= 2) lzb_general_match(out, &target, &query, &segs[k]);
+                    else if (o.format == 7) lzb_cigar_match(out, &target, &query, &segs[k]);
+                    else if (o.format == 8) lzb_sam_match(out, &target, &query, &segs[k], o.samEqx, o.samSoft);
+                    else if (o.format >= 2) lzb_fieldlist_match(out, o.fields, &target, &query, &segs[k], &rowNumber);
                 }
                 if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
             } else {
@@ -476,7 +496,9 @@ int main(int argc, char** argv) {
                         if (!headerDone) { lzb_gfa_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_gfa_align(out, &target, &query, a, &ss);
                     }
-                    else if (o.format >= 2) lzb_general_align(out, &target, &query, a);
+                    else if (o.format == 7) lzb_cigar_align(out, &target, &query, a);
+                    else if (o.format == 8) lzb_sam_align(out, &target, &query, a, o.samEqx, o.samSoft);
+                    else if (o.format >= 2) lzb_fieldlist_align(out, o.fields, &target, &query, a, &rowNumber);
                     else lzb_die("--format=segments needs --nogapped");
                 }
                 lzb_free_align_list(list);

@@ -39,7 +39,7 @@ typedef struct lzb_partition {
     char* header; char* shortHeader;
 } lzb_partition;
 /* name, offset in v, startLoc, length and full length of the (part of the) sequence that holds position pos0 */
-typedef struct lzb_seqview { const char* name; uint32_t offset, startLoc, len, trueLen; } lzb_seqview;
+typedef struct lzb_seqview { const char* name; uint32_t offset, startLoc, len, trueLen, contig; } lzb_seqview;
 void lzb_seq_view(const lzb_seq* s, uint32_t pos0, lzb_seqview* out);
 
 /* a sequence file + bracketed actions; load successive sequences with lzb_seqfile_next */
@@ -94,9 +94,19 @@ void lzb_lav_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segmen
 void lzb_lav_footer(FILE*);                                                            /* m stanza + #:eof */
 void lzb_segments_write(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, uint64_t n);
                                                                                        /* write_segments segment.c:1930 */
-void lzb_general_header(FILE*);
-void lzb_general_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
-void lzb_general_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
+/* general.c -- --format=general[-][:fields] / mapping[-] / cigar (genpaf.c, cigar.c): rows with named columns */
+typedef struct lzb_fieldlist lzb_fieldlist;
+lzb_fieldlist* lzb_fieldlist_parse(const char* commaSeparatedNames);      /* parse_genpaf_keys genpaf.c:1945 */
+lzb_fieldlist* lzb_fieldlist_standard(void);                              /* --format=general */
+lzb_fieldlist* lzb_fieldlist_mapping(void);                               /* --format=mapping */
+void lzb_fieldlist_header(FILE*, const lzb_fieldlist*);
+void lzb_fieldlist_align(FILE*, const lzb_fieldlist*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, uint64_t* number);
+void lzb_fieldlist_match(FILE*, const lzb_fieldlist*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, uint64_t* number);
+void lzb_cigar_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
+void lzb_cigar_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
+void lzb_sam_header(FILE*, const lzb_seq* s1);                             /* sam.c:196-232 */
+void lzb_sam_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, int markMismatches, int softClip);
+void lzb_sam_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, int markMismatches, int softClip);
 void lzb_maf_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);    /* maf.c:271, --format=maf- */
 /* gfa.c:95-330, --format=gfa */
 void lzb_gfa_job_header(FILE*, const char* prog, const char* name1, const char* name2, const char* seedPattern, int withTrans, uint32_t step);

@@ -91,67 +91,7 @@ void lzb_segments_write(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb
                 g[i].pos2 + g[i].length + s2->startLoc - 1, strand, g[i].s);
 }
 
-/* ---- --format=general with the default fields (genpafStandardKeys "#NDSZEndszeIC", genpaf.h:117):
- * score name1 strand1 size1 zstart1 end1 name2 strand2 size2 zstart2 end2 identity idPct coverage covPct.
- * Coordinates as in print_genpaf_align genpaf.c:595-690 (unpartitioned sequences), identity as in
- * alignment_identity identity_dist.c:184-234 / count_substitutions :383, coverage as in
- * alignment_coverage coverage_dist.c (shorter sequence is the denominator). ---- */
-void lzb_general_header(FILE* f) {
-    fprintf(f, "#score\tname1\tstrand1\tsize1\tzstart1\tend1\tname2\tstrand2\tsize2\tzstart2\tend2\tidentity\tidPct\tcoverage\tcovPct\n");
-}
-
-static void general_row(FILE* f, const lzb_seq* s1, const lzb_seq* s2, uint32_t pos1, uint32_t len1, uint32_t pos2, uint32_t len2,
-                        int32_t score, uint64_t idNumer, uint64_t idDenom) {
-    lzb_seqview w1, w2; lzb_seq_view(s1, pos1, &w1); lzb_seq_view(s2, pos2, &w2);      /* the partitions the alignment lies in */
-    const char* name1 = w1.name ? w1.name : "seq1"; const char* name2 = w2.name ? w2.name : "seq2";
-    uint32_t start1, start2; char strand1, strand2;
-    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = pos1 - w1.offset + w1.startLoc; strand1 = '+'; }
-    else { start1 = pos1 - w1.offset + w1.trueLen + 2 - (w1.startLoc + w1.len); strand1 = '-'; }
-    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = pos2 - w2.offset + w2.startLoc; strand2 = '+'; }
-    else { start2 = pos2 - w2.offset + w2.trueLen + 2 - (w2.startLoc + w2.len); strand2 = '-'; }
-    uint64_t covNumer, covDenom;
-    if (w1.trueLen < w2.trueLen) { covNumer = len1; covDenom = w1.trueLen; } else { covNumer = len2; covDenom = w2.trueLen; }
-    fprintf(f, "%d\t%s\t%c\t%u\t%u\t%u\t%s\t%c\t%u\t%u\t%u\t", score, name1, strand1, w1.trueLen, start1 - 1, start1 + len1 - 1,
-            name2, strand2, w2.trueLen, start2 - 1, start2 + len2 - 1);
-    fprintf(f, "%llu/%llu", (unsigned long long)idNumer, (unsigned long long)idDenom);
-    if (idDenom) fprintf(f, "\t%.1f%%", (100.0 * idNumer) / idDenom); else fprintf(f, "\tNA");
-    fprintf(f, "\t%llu/%llu", (unsigned long long)covNumer, (unsigned long long)covDenom);
-    if (covDenom) fprintf(f, "\t%.1f%%\n", (100.0 * covNumer) / covDenom); else fprintf(f, "\tNA\n");
-}
-
-static void count_pairs(const uint8_t* a, const uint8_t* b, uint32_t len, uint64_t* matches, uint64_t* denom) {
-    for (uint32_t i = 0; i < len; i++) {
-        int x = lzb_nuc_to_bits[a[i]], y = lzb_nuc_to_bits[b[i]];
-        if (x >= 0 && y >= 0) { if (x == y) (*matches)++; (*denom)++; }
-    }
-}
-
-void lzb_general_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a) {
-    uint32_t height = a->end1 - a->beg1 + 1, width = a->end2 - a->beg2 + 1, k = 0;
-    const lzb_editscript* sc = a->script;
-    uint64_t m = 0, d = 0;
-    for (uint32_t i = 0, j = 0; i < height || j < width;) {
-        uint32_t run = 0;
-        while (k < sc->len && (sc->op[k] & 3) == LZB_OP_SUB) { run += sc->op[k] >> 2; k++; }
-        count_pairs(s1->v + a->beg1 - 1 + i, s2->v + a->beg2 - 1 + j, run, &m, &d);
-        i += run; j += run;
-        if (i < height || j < width) {
-            if (k >= sc->len) break;
-            uint32_t op = sc->op[k] & 3, rpt = sc->op[k] >> 2;
-            if (op == LZB_OP_INS) j += rpt; else if (op == LZB_OP_DEL) i += rpt;
-            k++;
-        }
-    }
-    if (d == 0) m = 0;
-    general_row(f, s1, s2, a->beg1 - 1, height, a->beg2 - 1, width, a->s, m, d);
-}
-
-void lzb_general_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g) {
-    uint64_t m = 0, d = 0;
-    count_pairs(s1->v + g->pos1, s2->v + g->pos2, g->length, &m, &d);
-    if (d == 0) m = 0;
-    general_row(f, s1, s2, g->pos1, g->length, g->pos2, g->length, g->s, m, d);
-}
+/* (--format=general / mapping / cigar: general.c) */
 
 /* ---- --format=maf- (MAF blocks without the parameter header), print_maf_align maf.c:271-470,
  * unpartitioned sequences ---- */

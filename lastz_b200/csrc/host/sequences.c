@@ -130,13 +130,13 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
 void lzb_seq_view(const lzb_seq* s, uint32_t pos0, lzb_seqview* o) {
     if (s->npart == 0) {
         o->name = (s->shortHeader && s->shortHeader[0]) ? s->shortHeader : NULL;
-        o->offset = 0; o->startLoc = s->startLoc; o->len = s->len; o->trueLen = s->trueLen;
+        o->offset = 0; o->startLoc = s->startLoc; o->len = s->len; o->trueLen = s->trueLen; o->contig = s->contig;
         return;
     }
     uint32_t lo = 0, hi = s->npart;                      /* lookup_partition sequences.c: last partition with sepBefore < pos0+1 */
     while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (s->part[mid].sepBefore <= pos0) lo = mid; else hi = mid; }
     const lzb_partition* p = &s->part[lo];
-    o->name = p->shortHeader; o->offset = p->sepBefore + 1; o->startLoc = p->startLoc; o->len = p->sepAfter - o->offset; o->trueLen = p->trueLen;
+    o->name = p->shortHeader; o->offset = p->sepBefore + 1; o->startLoc = p->startLoc; o->len = p->sepAfter - o->offset; o->trueLen = p->trueLen; o->contig = p->contig;
 }
 
 void lzb_seqfile_close(lzb_seqfile* sf) {

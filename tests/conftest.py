@@ -162,6 +162,26 @@ GENERAL_CASES = [
     ("", "", ["--format=maf", "--chain", "Y=5000"]),              # MAF with the parameter header (maf.c:96)
 ]
 
+# --format=general:<fields>, mapping, cigar (genpaf.c:545-1490, cigar.c:135): every field this front end carries
+FIELD_CASES = [
+    ("", "", ["--format=general:name1,number1,strand1,size1,start1,zstart1,end1,length1,name2,number2,strand2,size2,start2,zstart2,start2+,zstart2+,end2,end2+,length2"]),
+    ("", "", ["--format=general:score,nmatch,nmismatch,npair,ncolumn,ngap,cgap,diagonal,shingle,number,znumber,NA"]),
+    ("", "", ["--format=general-:identity,idfrac,id%,blastid%,coverage,covfrac,cov%,continuity,confrac,con%,gaprate"]),
+    ("", "", ["--format=general-:text1,text2,diff", "--strand=minus", "K=2200"]),
+    ("", "", ["--format=general-:cigar,cigar-,cigarx,cigarx-,cigarx1,cigarx1-"]),
+    ("", "", ["--format=general-:n1,s1,z1,e1,l1,n2,s2,z2,s2+,z2+,e2,e2+,l2,d,diag,s,id,ident,cov,con,gap", "--nogapped"]),
+    ("[100..9000]", "[2000..18000]", ["--format=general:name1,size1,start1,end1,name2,strand2,size2,start2,end2,start2+,end2+,shingle,coverage"]),
+    ("", "", ["--format=mapping"]),
+    ("", "[multi]", ["--format=mapping-", "--nogapped"]),
+    ("", "", ["--format=cigar"]),
+    ("[100..9000]", "[2000..18000]", ["--format=cigar", "--nogapped"]),
+    ("", "", ["--format=sam"]),                                   # sam.c:196-560: hard clipping, header
+    ("", "", ["--format=softsam-", "--strand=minus"]),            # soft clipping: the whole read, clipped parts in lower case
+    ("", "", ["--format=sam+eqx"]),                               # =/X runs instead of M
+    ("", "[multi]", ["--format=softsam+eqx-", "--nogapped"]),
+    ("", "[2000..18000]", ["--format=sam-"]),
+]
+
 # --format=gfa (gfa.c:95-330): A lines + one a line per gap-free block
 GFA_CASES = [
     ("", "", ["--format=gfa"]),

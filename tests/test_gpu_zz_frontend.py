@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
+from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, FIELD_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
 
 pytestmark = pytest.mark.gpu
 
@@ -14,7 +14,7 @@ CAT = os.path.join(GOLDEN, "pseudocat.fa")
 PIG = os.path.join(GOLDEN, "pseudopig.fa")
 
 
-@pytest.mark.parametrize("a1,a2,opts", GFA_CASES)
+@pytest.mark.parametrize("a1,a2,opts", GFA_CASES + FIELD_CASES)
 def test_cli_gfa_format(a1, a2, opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
     assert run_cli(PRODUCT_CLI, [CAT + a1, PIG + a2] + opts)[0] == run_cli(ref, [CAT + a1, PIG + a2] + opts)[0]

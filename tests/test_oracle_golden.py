@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FIELD_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -239,7 +239,7 @@ def test_oracle_exact_and_mismatch_extension_on_synthetic(synth, tmp_path, opts)
     same_output(run_cli(ORACLE_CLI, [t, qm] + opts)[0], run_cli(REF_CLI, [t, qm] + opts)[0])
 
 
-@pytest.mark.parametrize("a1,a2,opts", GENERAL_CASES + GFA_CASES)
+@pytest.mark.parametrize("a1,a2,opts", GENERAL_CASES + GFA_CASES + FIELD_CASES)
 def test_oracle_general_format(a1, a2, opts):
     if not os.path.exists(REF_CLI):
         pytest.skip("oracle/_ref not built")
