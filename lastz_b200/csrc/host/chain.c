@@ -169,3 +169,41 @@ int32_t lzb_reduce_to_chain(lzb_segment* segs, uint64_t* pn, int32_t diagPen, in
     free(k.perm); free(k.chainScore); free(k.nodes); free(inv); free(link);
     return best > 2147483647.0 ? 0x7FFFFFFF : (int32_t)best;
 }
+
+/* try_reduce_to_chain chain.c:224-392: with [multi] sequences the segments are chained separately for every pair of
+ * partitions (a segment never spans two), batches in partition order; the caller's sort by pos1 (lastz.c:3352) follows */
+static uint32_t partition_index(const lzb_seq* s, uint32_t pos0) {
+    if (s->npart == 0) return 0;
+    uint32_t lo = 0, hi = s->npart;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (s->part[mid].sepBefore <= pos0) lo = mid; else hi = mid; }
+    return lo;
+}
+typedef struct { uint32_t p1, p2; lzb_segment g; } batched;
+static int by_batch(const void* pa, const void* pb) {
+    const batched* a = pa; const batched* b = pb;
+    if (a->p1 != b->p1) return a->p1 < b->p1 ? -1 : 1;
+    if (a->p2 != b->p2) return a->p2 < b->p2 ? -1 : 1;
+    return by_pos1(&a->g, &b->g);
+}
+int32_t lzb_reduce_to_chains(const lzb_seq* s1, const lzb_seq* s2, lzb_segment* segs, uint64_t* pn,
+                             int32_t diagPen, int32_t antiPen, int32_t scale, int32_t subAA) {
+    int32_t best = 0;
+    if (s1->npart == 0 && s2->npart == 0) best = lzb_reduce_to_chain(segs, pn, diagPen, antiPen, scale, subAA);
+    else if (*pn) {
+        uint64_t n = *pn, kept = 0;
+        batched* b = malloc(n * sizeof *b);
+        for (uint64_t i = 0; i < n; i++) { b[i].p1 = partition_index(s1, segs[i].pos1); b[i].p2 = partition_index(s2, segs[i].pos2); b[i].g = segs[i]; }
+        qsort(b, n, sizeof *b, by_batch);
+        for (uint64_t lo = 0; lo < n;) {
+            uint64_t hi = lo; while (hi < n && b[hi].p1 == b[lo].p1 && b[hi].p2 == b[lo].p2) hi++;
+            uint64_t m = hi - lo;
+            for (uint64_t i = 0; i < m; i++) segs[kept + i] = b[lo + i].g;
+            int32_t sc = lzb_reduce_to_chain(segs + kept, &m, diagPen, antiPen, scale, subAA);
+            if (sc > best) best = sc;
+            kept += m; lo = hi;
+        }
+        free(b); *pn = kept;
+    }
+    qsort(segs, *pn, sizeof *segs, by_pos1);
+    return best;
+}

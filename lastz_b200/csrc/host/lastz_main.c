@@ -281,11 +281,11 @@ int main(int argc, char** argv) {
         if ((query.npart || target.npart) && (o.format == 0 || o.format == 6)) lzb_die("%s format can't handle multi-sequences", o.format == 0 ? "lav" : "gfa");
         if (target.npart) {
             /* a partitioned target: hits, extensions and DP sweeps stop at its NULs like they do in a partitioned query.
-             * Not built: what the reference does PER PARTITION -- chaining (chain.c:278-340), the segments writer's rows,
+             * Not built: what the reference does PER PARTITION beyond chaining -- the segments writer's rows
              * and the trivial self-alignment of a query that equals one target partition, which bounds every other
              * alignment (identical_partition_of_sequence gapped_extend.c:2034, :1185-1230).  Such runs stop here. */
-            if (o.selfCompare || o.segmentsFile || o.chain || o.anyOrNone || o.adaptive || o.inhibitTrivial || o.format == 1)
-                lzb_die("lastz_b200 does not combine a [multi] target with --self, --notrivial, --segments, --format=segments, --chain, --anyornone or an adaptive threshold yet");
+            if (o.selfCompare || o.segmentsFile || o.anyOrNone || o.adaptive || o.inhibitTrivial || o.format == 1)
+                lzb_die("lastz_b200 does not combine a [multi] target with --self, --notrivial, --segments, --format=segments, --anyornone or an adaptive threshold yet");
             if (o.gapped && o.whichStrand >= 0 && query.revCompFlags == target.revCompFlags) {     /* only the + strand pass can be trivial */
                 int twin = 0;
                 if (query.npart) twin = query.len == target.len && !strncasecmp((const char*)query.v + 1, (const char*)target.v + 1, query.len - 1);
@@ -296,8 +296,8 @@ int main(int argc, char** argv) {
                 if (twin) lzb_die("%s is identical to (part of) the [multi] target; lastz_b200 does not build the trivial self-alignment of partitions yet", query.shortHeader ? query.shortHeader : "the query");
             }
         }
-        if (query.npart && (o.selfCompare || o.segmentsFile || o.chain || o.anyOrNone))
-            lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments, --chain or --anyornone yet");
+        if (query.npart && (o.selfCompare || o.segmentsFile || o.anyOrNone))
+            lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments or --anyornone yet");
         if (query.npart && o.adaptive) lzb_die("lastz_b200 does not combine a [multi] query with an adaptive HSP threshold yet");
         int reported = 0;                                        /* --anyornone: alignments reported for this query */
         /* Order of work for one query (main, lastz.c:1566-1700): each strand is searched and finished in turn -- unless the
@@ -411,7 +411,7 @@ int main(int argc, char** argv) {
                     segs[k].s = sc;
                 }
             if (o.chain)                                         /* try_reduce_to_chain lastz.c:3349, chainScale = 100 (:511) */
-                lzb_reduce_to_chain(segs, &nsegs, o.chainDiag, o.chainAnti, 100, ss.sub['A' * 256 + 'A']);
+                lzb_reduce_to_chains(&target, &query, segs, &nsegs, o.chainDiag, o.chainAnti, 100, ss.sub['A' * 256 + 'A']);
             if (o.anyOrNone && nsegs) {
                 /* gappily_extend_hsps (gapped_extend.c:5279; a17): every HSP, in discovery order, is reduced to its
                  * peak and extended on its own, unconstrained by other alignments; the first one that reaches the

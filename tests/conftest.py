@@ -202,6 +202,8 @@ MULTI_TARGET_CASES = [
     ("aglobin.2bit[multi]", "shorties.fa[multi]", ["--format=axt", "K=2500"]),
     ("shorties.fa[multi]", "aglobin.2bit/human", ["--format=axt", "K=2500", "--noytrim"]),
     ("shorties.2bit[multi,51..200]", "aglobin.2bit/human", ["--format=maf-", "K=3000", "--strand=minus"]),
+    ("aglobin.2bit[multi]", "shorties.fa[multi]", ["--format=general-", "K=2500", "--chain"]),          # chained per pair of partitions, chain.c:224
+    ("aglobin.2bit/human", "shorties.fa[multi]", ["--format=maf-", "K=2000", "--chain=20,30", "--nogapped"]),
 ]
 
 # adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
