@@ -146,18 +146,11 @@ static char diff_char(uint8_t p, uint8_t q) {
     return ((a ^ b) == 2) ? ':' : 'x';                              /* A<->G, C<->T differ in bit 1 only */
 }
 
-static const char* const RCF_SUFFIX[4] = { "", "~", "~", "" };      /* genpaf.c / cigar.c:191 */
-
-void lzb_fieldlist_align(FILE* f, const lzb_fieldlist* fl, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, uint64_t* number) {
+/* matches / aligned pairs (alignment_identity identity_dist.c:184), shorter sequence covered (alignment_coverage
+ * coverage_dist.c:132), gap-free columns / columns and gapped bases / gap-free columns (continuity_dist.c:282-349) */
+void lzb_align_stats(const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, lzb_alignstats* st) {
     lzb_seqview w1, w2; lzb_seq_view(s1, a->beg1 - 1, &w1); lzb_seq_view(s2, a->beg2 - 1, &w2);
-    const char* name1 = w1.name && w1.name[0] ? w1.name : "seq1"; const char* name2 = w2.name && w2.name[0] ? w2.name : "seq2";
     const uint32_t beg1 = a->beg1, beg2 = a->beg2, height = a->end1 - beg1 + 1, width = a->end2 - beg2 + 1;
-    uint32_t start1, start2; char strand1, strand2;
-    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = beg1 - 1 - w1.offset + w1.startLoc; strand1 = '+'; }
-    else { start1 = beg1 - 1 - w1.offset + w1.trueLen + 2 - (w1.startLoc + w1.len); strand1 = '-'; }
-    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = beg2 - 1 - w2.offset + w2.startLoc; strand2 = '+'; }
-    else { start2 = beg2 - 1 - w2.offset + w2.trueLen + 2 - (w2.startLoc + w2.len); strand2 = '-'; }
-    /* statistics: matches / aligned pairs (identity), gap-free columns / columns (continuity), gapped bases / gap-free columns */
     uint64_t idNumer = 0, idDenom = 0, subs = 0, ngap = 0;
     walker w; walk_start(&w, a);
     while (walk_more(&w)) {
@@ -169,11 +162,59 @@ void lzb_fieldlist_align(FILE* f, const lzb_fieldlist* fl, const lzb_seq* s1, co
         uint32_t di, dj; walk_gap(&w, &di, &dj); ngap++;
     }
     if (idDenom == 0) idNumer = 0;
-    uint64_t gapNumer = 0, gapDenom = 0, conNumer = 0, conDenom = 0;
-    if (subs) { gapNumer = (height - subs) + (width - subs); gapDenom = subs; }
-    conNumer = gapDenom; conDenom = gapDenom + gapNumer;
-    uint64_t covNumer, covDenom;
-    if (w1.trueLen < w2.trueLen) { covNumer = height; covDenom = w1.trueLen; } else { covNumer = width; covDenom = w2.trueLen; }
+    memset(st, 0, sizeof *st);
+    st->idNumer = idNumer; st->idDenom = idDenom; st->ngap = ngap;
+    if (subs) { st->gapNumer = (height - subs) + (width - subs); st->gapDenom = subs; }
+    st->conNumer = st->gapDenom; st->conDenom = st->gapDenom + st->gapNumer;
+    if (w1.trueLen < w2.trueLen) { st->covNumer = height; st->covDenom = w1.trueLen; } else { st->covNumer = width; st->covDenom = w2.trueLen; }
+}
+
+/* the --filter= family (lastz.c:3430-3462 for alignments, :3312-3332 for HSPs); single-precision products as in the
+ * reference (identity_dist.c:102-104, coverage_dist.c:86-89, continuity_dist.c:92-95) */
+void lzb_filters_init(lzb_filters* f) {
+    memset(f, 0, sizeof *f);
+    f->maxIdentity = f->maxCoverage = f->maxContinuity = 1; f->maxMismatchCount = f->maxSeparateGaps = f->maxGapColumns = -1;
+}
+int lzb_filters_active(const lzb_filters* f) {
+    return f->minIdentity > 0 || f->maxIdentity < 1 || f->minCoverage > 0 || f->maxCoverage < 1 || f->minContinuity > 0 || f->maxContinuity < 1 ||
+           f->minMatchCount > 0 || f->maxMismatchCount >= 0 || f->maxSeparateGaps >= 0 || f->maxGapColumns >= 0;
+}
+int lzb_filters_reject(const lzb_filters* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, int isSegment) {
+    lzb_alignstats st; lzb_align_stats(s1, s2, a, &st);
+    const uint32_t idN = (uint32_t)st.idNumer, idD = (uint32_t)st.idDenom, covN = (uint32_t)st.covNumer, covD = (uint32_t)st.covDenom,
+                   conN = (uint32_t)st.conNumer, conD = (uint32_t)st.conDenom;
+    if (f->minIdentity > 0 || f->maxIdentity < 1)
+        if (idD == 0 || idN < idD * f->minIdentity || idN > idD * f->maxIdentity) return 1;
+    if (f->minCoverage > 0 || f->maxCoverage < 1) {
+        float lo = covD * f->minCoverage, hi = covD * f->maxCoverage;
+        if (covN < lo || covN > hi) return 1;
+    }
+    if (!isSegment && (f->minContinuity > 0 || f->maxContinuity < 1)) {
+        float lo = conD * f->minContinuity, hi = conD * f->maxContinuity;
+        if (conN < lo || conN > hi) return 1;
+    }
+    if (f->minMatchCount > 0 && (idD == 0 || idN < f->minMatchCount)) return 1;
+    if (f->maxMismatchCount >= 0 && (idD == 0 || idD - idN > (uint32_t)f->maxMismatchCount)) return 1;
+    if (!isSegment && f->maxSeparateGaps >= 0 && (int64_t)st.ngap > f->maxSeparateGaps) return 1;
+    if (!isSegment && f->maxGapColumns >= 0 && (conD == 0 || conD - conN > (uint32_t)f->maxGapColumns)) return 1;
+    return 0;
+}
+
+static const char* const RCF_SUFFIX[4] = { "", "~", "~", "" };      /* genpaf.c / cigar.c:191 */
+
+void lzb_fieldlist_align(FILE* f, const lzb_fieldlist* fl, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, uint64_t* number) {
+    lzb_seqview w1, w2; lzb_seq_view(s1, a->beg1 - 1, &w1); lzb_seq_view(s2, a->beg2 - 1, &w2);
+    const char* name1 = w1.name && w1.name[0] ? w1.name : "seq1"; const char* name2 = w2.name && w2.name[0] ? w2.name : "seq2";
+    const uint32_t beg1 = a->beg1, beg2 = a->beg2, height = a->end1 - beg1 + 1, width = a->end2 - beg2 + 1;
+    uint32_t start1, start2; char strand1, strand2;
+    if (!(s1->revCompFlags & LZB_RCF_REV)) { start1 = beg1 - 1 - w1.offset + w1.startLoc; strand1 = '+'; }
+    else { start1 = beg1 - 1 - w1.offset + w1.trueLen + 2 - (w1.startLoc + w1.len); strand1 = '-'; }
+    if (!(s2->revCompFlags & LZB_RCF_REV)) { start2 = beg2 - 1 - w2.offset + w2.startLoc; strand2 = '+'; }
+    else { start2 = beg2 - 1 - w2.offset + w2.trueLen + 2 - (w2.startLoc + w2.len); strand2 = '-'; }
+    lzb_alignstats st; lzb_align_stats(s1, s2, a, &st);
+    const uint64_t idNumer = st.idNumer, idDenom = st.idDenom, covNumer = st.covNumer, covDenom = st.covDenom, conNumer = st.conNumer,
+                   conDenom = st.conDenom, gapNumer = st.gapNumer, gapDenom = st.gapDenom, ngap = st.ngap;
+    walker w;
     const uint64_t ordinal = (*number)++;
 
     for (int k = 0; k < fl->n; k++) {

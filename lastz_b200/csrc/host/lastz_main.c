@@ -25,6 +25,7 @@ typedef struct {
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa, 7 cigar, 8 sam */
     int samSoft, samEqx, samHeader;
+    lzb_filters filters;           /* --filter=identity:.. and friends */
     lzb_fieldlist* fields;         /* columns of --format=general[-][:<names>] / mapping[-] */
     int device, showStats, speculation, mafHeader;
     int anyOrNone;                                           /* --anyornone: hspImmediate + searchLimit 1 (lastz.c:5962) */
@@ -35,6 +36,13 @@ typedef struct {
 
 static int starts(const char* a, const char* p) { return strncmp(a, p, strlen(p)) == 0; }
 
+static long unitized_thousands(const char* s) {   /* string_to_unitized_int, units of 1000 */
+    char* e; double v = strtod(s, &e);
+    if (*e == 'K' || *e == 'k') { v *= 1000; e++; } else if (*e == 'M' || *e == 'm') { v *= 1000 * 1000; e++; } else if (*e == 'G' || *e == 'g') { v *= 1000.0 * 1000 * 1000; e++; }
+    if (e == s || *e) lzb_die("\"%s\" is not an integer", s);
+    return (long)v;
+}
+
 static long unitized(const char* s) {       /* string_to_unitized_int, units of 1024 */
     char* e; double v = strtod(s, &e);
     if (*e == 'K' || *e == 'k') v *= 1024; else if (*e == 'M' || *e == 'm') v *= 1024 * 1024;
@@ -42,8 +50,22 @@ static long unitized(const char* s) {       /* string_to_unitized_int, units of 
     return (long)v;
 }
 
+/* <min>[..<max>] in percent, each with an optional % sign (lastz.c:6680-6725); ..<max> and <min>.. are allowed */
+static void percent_range(const char* a, const char* v, float* lo, float* hi) {
+    float mn = 0.0f, mx = 100.0f; char text[64]; char* e;
+    if (!strcmp(v, "..") || strlen(v) >= sizeof text) lzb_die("Can't understand \"%s\"", a);
+    strcpy(text, v);
+    char* dots = strstr(text, ".."); char* upper = NULL;
+    if (dots) { *dots = 0; upper = dots + 2; }
+    if (text[0]) { mn = strtof(text, &e); if (e == text) lzb_die("Can't understand \"%s\"", a); if (*e == '%') e++; if (*e && !(!dots && !strcmp(e, "."))) lzb_die("Can't understand \"%s\"", a); }
+    if (upper && upper[0]) { mx = strtof(upper, &e); if (e == upper) lzb_die("Can't understand \"%s\"", a); if (*e == '%') e++; if (*e) lzb_die("Can't understand \"%s\"", a); }
+    if (mn < 0 || mx > 100 || mn > mx) lzb_die("Can't understand \"%s\"", a);
+    *lo = mn / 100.0; *hi = mx / 100.0;
+}
+
 static void parse_options(options* o, int argc, char** argv) {
     memset(o, 0, sizeof *o);
+    lzb_filters_init(&o->filters);
     o->withTrans = 1; o->step = 1; o->whichStrand = 1; o->gfExtend = LZB_GFEX_XDROP; o->gapped = 1;
     o->entropy = 1; o->trimToPeak = 1; o->tracebackBytes = 80u * 1024 * 1024; o->hashBits = 16;
     o->speculation = 32;
@@ -115,6 +137,22 @@ static void parse_options(options* o, int argc, char** argv) {
             if (p2) { o->ambiMatch = atoi(p1); o->ambiMismatch = atoi(p2 + 1); } else { o->ambiMatch = 0; o->ambiMismatch = atoi(p1); }
             if (o->ambiMismatch < 0) lzb_die("penalty for --ambiguous=n must be non-negative");
         }
+        else if (starts(a, "--identity=") || starts(a, "--filter=identity:")) percent_range(a, starts(a, "--filter=") ? strchr(a, ':') + 1 : v, &o->filters.minIdentity, &o->filters.maxIdentity);
+        else if (starts(a, "--coverage=") || starts(a, "--filter=coverage:")) percent_range(a, starts(a, "--filter=") ? strchr(a, ':') + 1 : v, &o->filters.minCoverage, &o->filters.maxCoverage);
+        else if (starts(a, "--continuity=") || starts(a, "--filter=continuity:")) percent_range(a, starts(a, "--filter=") ? strchr(a, ':') + 1 : v, &o->filters.minContinuity, &o->filters.maxContinuity);
+        else if (starts(a, "--matchcount=") || starts(a, "--filter=nmatch:")) {                       /* lastz.c:6850-6872 */
+            const char* n = starts(a, "--filter=") ? strchr(a, ':') + 1 : v;
+            if (n[0] && n[strlen(n) - 1] == '%') lzb_die("lastz_b200 does not implement a match count relative to the sequence length (%s)", a);
+            long c = unitized_thousands(n);
+            if (c <= 0) lzb_die("--filter=nmatch must be positive");
+            o->filters.minMatchCount = (uint32_t)c;
+        }
+        else if (starts(a, "--filter=nmismatch:..") || starts(a, "--filter=nmismatch:0..")) {
+            long c = unitized_thousands(strstr(a, "..") + 2); if (c < 0) lzb_die("--filter=nmismatch can't be negative");
+            o->filters.maxMismatchCount = (int32_t)c;
+        }
+        else if (starts(a, "--filter=ngap:..") || starts(a, "--filter=ngap:0..")) { o->filters.maxSeparateGaps = atoi(strstr(a, "..") + 2); if (o->filters.maxSeparateGaps < 0) lzb_die("--filter=ngap can't be negative"); }
+        else if (starts(a, "--filter=cgap:..") || starts(a, "--filter=cgap:0..")) { o->filters.maxGapColumns = atoi(strstr(a, "..") + 2); if (o->filters.maxGapColumns < 0) lzb_die("--filter=cgap can't be negative"); }
         else if (!strcmp(a, "--noentropy")) o->entropy = 0;
         else if (!strcmp(a, "--entropy")) o->entropy = 1;
         else if (!strcmp(a, "--allgappedbounds")) o->allBounds = 1;
@@ -174,6 +212,7 @@ static void parse_options(options* o, int argc, char** argv) {
     if (!o->targetSpec) lzb_die("You must specify a target file");
     if (o->selfCompare && !o->querySpec) o->querySpec = o->targetSpec;
     if (!o->querySpec) o->querySpec = "(stdin)";                    /* lastz.c:8762: no query file => read it from stdin */
+    if (o->anyOrNone && lzb_filters_active(&o->filters)) lzb_die("lastz_b200 does not combine --anyornone with --filter options yet");
     if (o->adaptive) {
         if (o->gfExtend != LZB_GFEX_XDROP) lzb_die("an adaptive HSP threshold requires --gfextend");   /* the other extensions assume a score, seed_search.c:3003 */
         if (o->anyOrNone) lzb_die("can't use --anyornone with adaptive hsp score threshold");         /* lastz.c:8898 */
@@ -400,6 +439,16 @@ int main(int argc, char** argv) {
             }
             /* only the x-drop extension leaves real scores in the table (seed_search.c:2953); the other modes
              * are scored here when chaining or the gapped stage needs them (lastz.c:3336-3340, score_segments segment.c:1262) */
+            if (!o.gapped && lzb_filters_active(&o.filters)) {   /* filter_segments_by_* lastz.c:3312-3332: identity, coverage, match counts */
+                uint64_t kept = 0;
+                for (uint64_t k = 0; k < nsegs; k++) {
+                    lzb_editscript es = { 1, 1, LZB_OP_SUB, { LZB_OP_SUB | (segs[k].length << 2) } };
+                    lzb_alignel al; memset(&al, 0, sizeof al);
+                    al.beg1 = segs[k].pos1 + 1; al.end1 = segs[k].pos1 + segs[k].length; al.beg2 = segs[k].pos2 + 1; al.end2 = segs[k].pos2 + segs[k].length; al.script = &es;
+                    if (!lzb_filters_reject(&o.filters, &target, &query, &al, 1)) segs[kept++] = segs[k];
+                }
+                nsegs = kept;
+            }
             /* adaptive, both strands: the + strand's HSPs were MOVED to the second table, which never saw an extension and
              * so does not count as scored (haveScores: seed_search.c:2953 marks the table being searched into, segment.c:207
              * clears it on the emptied one) -- they are scored again here, which undoes their entropy adjustment */
@@ -484,6 +533,16 @@ int main(int argc, char** argv) {
                     lzb_die("%s", lzb_last_error());
                 totCells += gst.dpCells; gapSec += gst.seconds; gk += gst.kernelSeconds[0];
                 gExt += gst.anchorsExtended; gSpec += gst.speculated; gRedo += gst.redone; gLaunch += gst.launches; gTrunc += gst.truncated;
+                if (lzb_filters_active(&o.filters)) {             /* filter_aligns_by_* lastz.c:3430-3462 */
+                    lzb_alignel* head = NULL; lzb_alignel** tail = &head;
+                    for (lzb_alignel* a = list; a;) {
+                        lzb_alignel* next = a->next; a->next = NULL;
+                        if (lzb_filters_reject(&o.filters, &target, &query, a, 0)) lzb_free_align_list(a);
+                        else { *tail = a; tail = &a->next; }
+                        a = next;
+                    }
+                    list = head;
+                }
                 if (o.selfCompare && list)                        /* mirrorGapped, lastz.c:3494-3498 */
                     list = lzb_mirror_alignments(list, &target, &query, &ss);
                 for (lzb_alignel* a = list; a; a = a->next) {

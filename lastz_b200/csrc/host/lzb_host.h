@@ -105,6 +105,14 @@ lzb_fieldlist* lzb_fieldlist_mapping(void);                               /* --f
 void lzb_fieldlist_header(FILE*, const lzb_fieldlist*);
 void lzb_fieldlist_align(FILE*, const lzb_fieldlist*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, uint64_t* number);
 void lzb_fieldlist_match(FILE*, const lzb_fieldlist*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, uint64_t* number);
+typedef struct lzb_alignstats { uint64_t idNumer, idDenom, covNumer, covDenom, conNumer, conDenom, gapNumer, gapDenom, ngap; } lzb_alignstats;
+void lzb_align_stats(const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, lzb_alignstats*);
+/* --filter=identity|coverage|continuity|nmatch|nmismatch|ngap|cgap (lastz.c:6672-6950); fractions, not percentages */
+typedef struct lzb_filters { float minIdentity, maxIdentity, minCoverage, maxCoverage, minContinuity, maxContinuity;
+                             uint32_t minMatchCount; int32_t maxMismatchCount, maxSeparateGaps, maxGapColumns; } lzb_filters;
+void lzb_filters_init(lzb_filters*);
+int  lzb_filters_active(const lzb_filters*);
+int  lzb_filters_reject(const lzb_filters*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, int isSegment);
 void lzb_cigar_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
 void lzb_cigar_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
 void lzb_sam_header(FILE*, const lzb_seq* s1);                             /* sam.c:196-232 */

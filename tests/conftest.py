@@ -206,6 +206,20 @@ MULTI_TARGET_CASES = [
     ("aglobin.2bit/human", "shorties.fa[multi]", ["--format=maf-", "K=2000", "--chain=20,30", "--nogapped"]),
 ]
 
+# --filter= family (lastz.c:6672-6950; filter_aligns_by_* after the gapped stage, filter_segments_by_* on HSPs): aglobin human x cow
+FILTER_CASES = [
+    ["--format=general-", "--identity=60..75"],
+    ["--format=general-", "--filter=identity:..72.5%"],
+    ["--format=general-", "--filter=coverage:0.5..3"],
+    ["--format=general-", "--filter=continuity:90..97%"],
+    ["--format=general-", "--filter=nmatch:1K"],
+    ["--format=general-", "--filter=nmismatch:0..200", "--filter=ngap:0..5"],
+    ["--format=general-", "--filter=cgap:..30"],
+    ["--format=general-", "--nogapped", "--coverage=0.1", "--matchcount=60", "K=2000"],
+    ["--format=general-", "--nogapped", "--filter=nmismatch:0..20", "K=2000", "--chain"],
+    ["--format=maf-", "--identity=65", "--continuity=90", "--coverage=0.8"],
+]
+
 # adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
 # strands collected into one table and the - strand finished first, lastz.c:1426,1678-1700): target suffix, query, options
 ADAPTIVE_CASES = [

@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FIELD_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FIELD_CASES, FILTER_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -167,6 +167,14 @@ def test_oracle_multi_target_matches_reference(target, query, opts):
         pytest.skip("oracle/_ref not built")
     args = [os.path.join(GOLDEN, target), os.path.join(GOLDEN, query)] + opts
     same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
+@pytest.mark.parametrize("opts", FILTER_CASES)
+def test_oracle_filters_match_reference(opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    files = adaptive_case_files("aglobin")
+    same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])
 
 
 def test_multi_target_refusals():
