@@ -7,6 +7,7 @@
  * implementing include/lastz_b200.h this binary is linked with: liblastz_b200.so (CUDA, the
  * product, `lastz_b200`) or oracle/liblzb_oracle.so (CPU restatement, test tool `lastz_oracle`).
  */
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
@@ -26,6 +27,7 @@ typedef struct {
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa, 7 cigar, 8 sam */
     int samSoft, samEqx, samHeader;
     lzb_filters filters;           /* --filter=identity:.. and friends */
+    int unitScores; int32_t unitMatch, unitMismatch;   /* --match=<reward>[,<penalty>] lastz.c:6138 */
     lzb_fieldlist* fields;         /* columns of --format=general[-][:<names>] / mapping[-] */
     int device, showStats, speculation, mafHeader;
     int anyOrNone;                                           /* --anyornone: hspImmediate + searchLimit 1 (lastz.c:5962) */
@@ -177,6 +179,12 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "E=")) { o->E = atoi(v); o->haveE = 1; }
         else if (starts(a, "--gap=")) { if (sscanf(v, "%d,%d", &o->O, &o->E) != 2) lzb_die("can't understand %s", a); o->haveO = o->haveE = 1; }
         else if (starts(a, "--scores=") || starts(a, "Q=")) o->scoresFile = v;
+        else if (starts(a, "--match=")) {
+            const char* comma = strchr(v, ',');
+            o->unitScores = 1; o->unitMatch = atoi(v); o->unitMismatch = comma ? -atoi(comma + 1) : -o->unitMatch;
+            if (o->unitMatch <= 0) lzb_die("%s is not a valid match score", v);
+            if (o->unitMismatch >= 0) lzb_die("%s is not a valid mismatch penalty", comma + 1);
+        }
         else if (starts(a, "--segments=") || starts(a, "--anchors=")) o->segmentsFile = v;   /* --anchors: the older spelling, lastz.c:5855 */
         else if (starts(a, "--allocate:traceback=") || starts(a, "--traceback=")) o->tracebackBytes = (uint32_t)unitized(v);
         else if (starts(a, "--output=")) o->outputFile = v;
@@ -247,7 +255,21 @@ int main(int argc, char** argv) {
     options o; parse_options(&o, argc, argv);
     /* scoring + derived defaults, lastz.c:9127-9339 */
     static lzb_scoreset ss;
-    if (o.scoresFile) lzb_scores_read_file(&ss, o.scoresFile); else lzb_scores_default(&ss);
+    if (o.scoresFile && o.unitScores) lzb_die("can't use --scores and --match together");
+    if (o.scoresFile) lzb_scores_read_file(&ss, o.scoresFile);
+    else if (o.unitScores) {                                     /* unit scores and what is derived from them, lastz.c:9168-9236, dna_utilities.c:158-162 */
+        const int32_t R = o.unitMatch, P = -o.unitMismatch;
+        int32_t unit[4][4];
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) unit[r][c] = r == c ? R : -P;
+        if (!o.haveO) { o.O = (int32_t)ceil(3.25 * P); o.haveO = 1; }
+        if (!o.haveE) { o.E = (int32_t)ceil(0.24375 * P); o.haveE = 1; }
+        if (!o.haveK) { o.K = (int32_t)ceil(30.0 * R); o.haveK = 1; }
+        if (!o.haveL && o.gfExtend == LZB_GFEX_EXACT) { o.L = (int32_t)ceil(30.0 * R); o.haveL = 1; }
+        if (!o.haveX) { o.X = (int32_t)ceil(10.0 * sqrt((double)P)); o.haveX = 1; }
+        if (!o.haveY) { o.Y = 2 * o.X; o.haveY = 1; }
+        lzb_scores_from_template(&ss, unit, (int32_t)(-10.0 * P), (int32_t)(-1.0 * P), o.O, o.E);
+    }
+    else lzb_scores_default(&ss);
     if (o.haveO) ss.gapOpen = o.O;
     if (o.haveE) ss.gapExtend = o.E;
     if (o.nIsAmbiguous) {                                        /* ambiguate_n dna_utilities.c:1544 on both matrices (lastz.c:9424-9429) */
@@ -290,19 +312,19 @@ int main(int argc, char** argv) {
     const uint32_t adaptLimit = o.adaptive == 'P' ? (uint32_t)(o.adaptFraction * target.len + 0.5) : o.adaptBases;
     if (o.adaptive) snprintf(textK, sizeof textK, "top%u", adaptLimit); else snprintf(textK, sizeof textK, "%d", o.K);
     if (o.adaptive && !o.haveL) snprintf(textL, sizeof textL, "top%u", adaptLimit); else snprintf(textL, sizeof textL, "%d", o.L);
-    if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", o.targetSpec, o.querySpec, o.args, &ss, textK, textL);
+    /* job headers name the FILES: no actions, no 2bit contig (seq->filename, lav.c:62, gfa.c:108) */
+    char n1[1024], n2[1024];
+    { char* cut;
+      snprintf(n1, sizeof n1, "%s", o.targetSpec); snprintf(n2, sizeof n2, "%s", o.querySpec);
+      if ((cut = strchr(n1, '['))) *cut = 0;
+      if ((cut = strchr(n2, '['))) *cut = 0;
+      if ((cut = strstr(n1, ".2bit/"))) cut[5] = 0;
+      if ((cut = strstr(n2, ".2bit/"))) cut[5] = 0; }
+    if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", n1, n2, o.args, &ss, textK, textL);
     else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
     else if (o.format == 2) lzb_fieldlist_header(out, o.fields);
     else if (o.format == 8 && o.samHeader) lzb_sam_header(out, &target);
-    else if (o.format == 6) {                                    /* file names without actions or 2bit contig (seq->filename) */
-        char n1[1024], n2[1024]; char* cut;
-        snprintf(n1, sizeof n1, "%s", o.targetSpec); snprintf(n2, sizeof n2, "%s", o.querySpec);
-        if ((cut = strchr(n1, '['))) *cut = 0;
-        if ((cut = strchr(n2, '['))) *cut = 0;
-        if ((cut = strstr(n1, ".2bit/"))) cut[5] = 0;
-        if ((cut = strstr(n2, ".2bit/"))) cut[5] = 0;
-        lzb_gfa_job_header(out, "lastz.v1.04.58", n1, n2, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, seed.withTrans, o.step);
-    }
+    else if (o.format == 6) lzb_gfa_job_header(out, "lastz.v1.04.58", n1, n2, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, seed.withTrans, o.step);
     else if (o.format == 5) lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, textK, textL, o.X, o.Y);
     else if (o.format == 4 && o.mafHeader) {                     /* maf.c:96-130: version line + the same parameter comments */
         fprintf(out, "##maf version=1 scoring=lastz.v1.04.58\n");
