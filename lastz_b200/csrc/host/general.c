@@ -8,6 +8,7 @@
  * run of substitutions, so both kinds of record go through the same code.  Fields that need data this front end does
  * not carry (base qualities, chore ids, hashes, BLAST statistics) are refused by name.
  */
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include "lzb_host.h"
@@ -17,7 +18,9 @@ enum {
     F_NAME2, F_NUMBER2, F_STRAND2, F_SIZE2, F_START2, F_ZSTART2, F_START2P, F_ZSTART2P, F_END2, F_END2P, F_LENGTH2, F_TEXT2,
     F_NMATCH, F_NMISMATCH, F_NPAIR, F_NCOLUMN, F_NGAP, F_CGAP, F_DIFF, F_CIGAR, F_CIGARL, F_CIGARX, F_CIGARXL, F_CIGARX1, F_CIGARX1L,
     F_DIAGONAL, F_SHINGLE, F_SCORE, F_IDENTITY, F_IDFRAC, F_IDPCT, F_BLASTIDPCT, F_COVERAGE, F_COVFRAC, F_COVPCT,
-    F_CONTINUITY, F_CONFRAC, F_CONPCT, F_GAPRATE, F_NUMBER, F_ZNUMBER
+    F_CONTINUITY, F_CONFRAC, F_CONPCT, F_GAPRATE, F_NUMBER, F_ZNUMBER,
+    /* only inside the canned lists of --format=paf / blastn (genpaf.h:119-125) */
+    F_MAPQUAL, F_ASTAG, F_CGTAG_X, F_CGTAG_M, F_BSTART1, F_BEND1, F_EVALUE, F_BITSCORE
 };
 static const struct { const char* name; int code; const char* heading; } FIELDS[] = {
     { "name1", F_NAME1, "name1" }, { "number1", F_NUMBER1, "number1" }, { "strand1", F_STRAND1, "strand1" }, { "size1", F_SIZE1, "size1" },
@@ -73,6 +76,27 @@ lzb_fieldlist* lzb_fieldlist_standard(void) {      /* genpafStandardKeys genpaf.
 }
 lzb_fieldlist* lzb_fieldlist_mapping(void) {       /* genpafMappingKeys genpaf.h:118 */
     return lzb_fieldlist_parse("name1,zstart1,end1,name2,strand2,zstart2+,end2+,identity,coverage,cigarx-");
+}
+static lzb_fieldlist* canned(const int* codes, int n) {
+    lzb_fieldlist* fl = calloc(1, sizeof *fl);
+    for (int k = 0; k < n; k++) { fl->code[k] = codes[k]; fl->heading[k] = ""; }
+    fl->n = n;
+    return fl;
+}
+lzb_fieldlist* lzb_fieldlist_paf(int wfmash) {     /* genpafPafMinimap2Keys "ns>,dNSZEuW{|." / genpafPafWfMashKeys "...}" */
+    const int codes[14] = { F_NAME2, F_SIZE2, F_ZSTART2P, F_END2P, F_STRAND2, F_NAME1, F_SIZE1, F_ZSTART1, F_END1, F_NMATCH, F_NCOLUMN, F_MAPQUAL, F_ASTAG,
+                            wfmash ? F_CGTAG_X : F_CGTAG_M };
+    return canned(codes, 14);
+}
+lzb_fieldlist* lzb_fieldlist_blastn(void) {        /* genpafBlastKeys "nNmWvy<,QR%$" */
+    const int codes[12] = { F_NAME2, F_NAME1, F_BLASTIDPCT, F_NCOLUMN, F_NMISMATCH, F_NGAP, F_START2P, F_END2P, F_BSTART1, F_BEND1, F_EVALUE, F_BITSCORE };
+    return canned(codes, 12);
+}
+/* print_blast_header genpaf.c:228: one comment block per query */
+void lzb_blastn_header(FILE* f, const char* prog, const char* args, const char* databaseFile, const lzb_seq* query) {
+    const char* name = query->shortHeader && query->shortHeader[0] ? query->shortHeader : "query";
+    fprintf(f, "# %s %s\n# Query: %s\n# Database: %s\n", prog, args, name, databaseFile);
+    fprintf(f, "# Fields: query id, subject id, %% identity, alignment length, mismatches, gap opens, q. start, q. end, s. start, s. end, evalue, bit score\n");
 }
 void lzb_fieldlist_header(FILE* f, const lzb_fieldlist* fl) {
     for (int k = 0; k < fl->n; k++) fprintf(f, "%s%s", k ? "\t" : "#", fl->heading[k]);
@@ -278,6 +302,14 @@ void lzb_fieldlist_align(FILE* f, const lzb_fieldlist* fl, const lzb_seq* s1, co
             }
             case F_SCORE: fprintf(f, "%d", a->s); break;
             case F_ZNUMBER: fprintf(f, "%llu", (unsigned long long)ordinal); break;
+            case F_MAPQUAL: fprintf(f, "255"); break;
+            case F_ASTAG: fprintf(f, "AS:i:%d", a->s); break;
+            case F_CGTAG_X: fprintf(f, "cg:Z:"); cigar_ops(f, s1, s2, a, 1, 1, 1, 0, 0); break;
+            case F_CGTAG_M: fprintf(f, "cg:Z:"); cigar_ops(f, s1, s2, a, 0, 1, 1, 0, 0); break;
+            case F_BSTART1: fprintf(f, "%u", strand2 == strand1 ? start1 : start1 + height - 1); break;      /* genpafStart1Blast genpaf.c:748 */
+            case F_BEND1: fprintf(f, "%u", strand2 == strand1 ? start1 + height - 1 : start1); break;
+            case F_EVALUE: fprintf(f, "%.2g", 3.0e9 * exp(-(a->s * 0.0205) * log(2))); break;                 /* blastz_score_to_ncbi_expectation dna_utilities.c:2346 */
+            case F_BITSCORE: fprintf(f, "%.1f", a->s * 0.0205); break;
             case F_NUMBER: fprintf(f, "%llu", (unsigned long long)ordinal + 1); break;
 #define FRACTION(n, d) fprintf(f, "%llu/%llu", (unsigned long long)(n), (unsigned long long)(d))
 #define PERCENT(n, d) do { if (d) fprintf(f, "%.1f%%", (100.0 * (n)) / (d)); else fprintf(f, "NA"); } while (0)
@@ -380,4 +412,46 @@ void lzb_sam_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segm
     lzb_alignel al; memset(&al, 0, sizeof al);
     al.beg1 = g->pos1 + 1; al.end1 = g->pos1 + g->length; al.beg2 = g->pos2 + 1; al.end2 = g->pos2 + g->length; al.s = g->s; al.script = &es;
     lzb_sam_align(f, s1, s2, &al, markMismatches, softMasked);
+}
+
+/* ---- --format=rdotplot[+score] and --rdotplot[+score]=<file>: every gap-free block of an alignment as a line segment
+ * for R's plot(): "start1 start2 / end1 end2 / NA NA" (genpafRDotplotKeys "02!13!XX" genpaf.h:121, blocks from
+ * print_genpaf_align_list_segments genpaf.c:433, coordinates from print_genpaf_match :1458-1490), preceded by the
+ * two sequence names whenever they change (print_header output.c:459-478) ---- */
+static void rdotplot_rows(FILE* f, lzb_rdotplot* st, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, const lzb_scoreset* ss, int withScore, int ownScore) {
+    const char* name1 = s1->npart == 0 && s1->shortHeader && s1->shortHeader[0] ? s1->shortHeader : "seq1";
+    const char* name2 = s2->npart == 0 && s2->shortHeader && s2->shortHeader[0] ? s2->shortHeader : "seq2";
+    if (strcmp(name1, st->prev1) || strcmp(name2, st->prev2)) {
+        fprintf(f, withScore ? "%s\t%s\tscore\n" : "%s\t%s\n", name1, name2);
+        snprintf(st->prev1, sizeof st->prev1, "%s", name1); snprintf(st->prev2, sizeof st->prev2, "%s", name2);
+    }
+    walker w; walk_start(&w, a);
+    while (walk_more(&w)) {
+        const uint32_t pos1 = a->beg1 - 1 + w.i, pos2 = a->beg2 - 1 + w.j;
+        uint32_t run = walk_subs(&w);
+        w.i += run; w.j += run;
+        if (walk_more(&w) && w.k < w.sc->len) { uint32_t di, dj; walk_gap(&w, &di, &dj); }
+        else if (walk_more(&w)) { w.i = w.height; w.j = w.width; }
+        lzb_seqview w1, w2; lzb_seq_view(s1, pos1, &w1); lzb_seq_view(s2, pos2, &w2);
+        uint32_t d1, e1, d2, e2;
+        if (!(s1->revCompFlags & LZB_RCF_REV)) { d1 = s1->npart == 0 ? pos1 - w1.offset + w1.startLoc : pos1 + 1; e1 = d1 + run - 1; }
+        else { d1 = s1->npart == 0 ? (w1.startLoc + w1.len + w1.offset - pos1) - 1 : (w1.offset - 1) + (w1.offset + w1.len) + 1 - pos1; e1 = d1 - run + 1; }
+        if (!(s2->revCompFlags & LZB_RCF_REV)) { d2 = s2->npart == 0 ? pos2 - w2.offset + w2.startLoc : pos2 + 1; e2 = d2 + run - 1; }
+        else { d2 = s2->npart == 0 ? (w2.startLoc + w2.len + w2.offset - pos2) - 1 : (w2.offset - 1) + (w2.offset + w2.len) + 1 - pos2; e2 = d2 - run + 1; }
+        if (!withScore) fprintf(f, "%u\t%u\n%u\t%u\nNA\tNA\n", d1, d2, e1, e2);
+        else {
+            int32_t sc = ownScore ? a->s : 0;                    /* an HSP keeps its score (output.c:930); a block of an alignment is scored, score_match sequences.c:9682 */
+            for (uint32_t x = 0; x < run && !ownScore; x++) sc += ss->sub[(uint32_t)s1->v[pos1 + x] * 256 + s2->v[pos2 + x]];
+            fprintf(f, "%u\t%u\t%d\n%u\t%u\t%d\nNA\tNA\tNA\n", d1, d2, sc, e1, e2, sc);
+        }
+    }
+}
+void lzb_rdotplot_match(FILE* f, lzb_rdotplot* st, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g, const lzb_scoreset* ss, int withScore) {
+    lzb_editscript es = { 1, 1, LZB_OP_SUB, { LZB_OP_SUB | (g->length << 2) } };
+    lzb_alignel al; memset(&al, 0, sizeof al);
+    al.beg1 = g->pos1 + 1; al.end1 = g->pos1 + g->length; al.beg2 = g->pos2 + 1; al.end2 = g->pos2 + g->length; al.s = g->s; al.script = &es;
+    rdotplot_rows(f, st, s1, s2, &al, ss, withScore, 1);
+}
+void lzb_rdotplot_align(FILE* f, lzb_rdotplot* st, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, const lzb_scoreset* ss, int withScore) {
+    rdotplot_rows(f, st, s1, s2, a, ss, withScore, 0);
 }

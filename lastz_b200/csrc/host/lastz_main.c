@@ -25,7 +25,8 @@ typedef struct {
     int hashBits;
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa, 7 cigar, 8 sam */
-    int samSoft, samEqx, samHeader;
+    int samSoft, samEqx, samHeader, blastHeader;
+    int dotScore; const char* dotplotFile; int dotplotFileScore;   /* --format=rdotplot[+score] (format 9), --rdotplot[+score]=<file> */
     lzb_filters filters;           /* --filter=identity:.. and friends */
     int unitScores; int32_t unitMatch, unitMismatch;   /* --match=<reward>[,<penalty>] lastz.c:6138 */
     lzb_fieldlist* fields;         /* columns of --format=general[-][:<names>] / mapping[-] */
@@ -200,6 +201,14 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--format=general-:") || starts(a, "--format=gen-:")) { o->format = 3; o->fields = lzb_fieldlist_parse(strchr(a, ':') + 1); }
         else if (!strcmp(a, "--format=mapping")) { o->format = 2; o->fields = lzb_fieldlist_mapping(); }                                 /* lastz.c:7347 */
         else if (!strcmp(a, "--format=mapping-")) { o->format = 3; o->fields = lzb_fieldlist_mapping(); }
+        else if (!strcmp(a, "--format=paf") || !strcmp(a, "--format=paf:minimap2")) { o->format = 3; o->fields = lzb_fieldlist_paf(0); }    /* lastz.c:7384 */
+        else if (!strcmp(a, "--format=paf:wfmash")) { o->format = 3; o->fields = lzb_fieldlist_paf(1); }
+        else if (!strcmp(a, "--format=blastn")) { o->format = 3; o->fields = lzb_fieldlist_blastn(); o->blastHeader = 1; }              /* lastz.c:7365 */
+        else if (!strcmp(a, "--format=blastn-")) { o->format = 3; o->fields = lzb_fieldlist_blastn(); }
+        else if (!strcmp(a, "--format=rdotplot")) { o->format = 9; o->dotScore = 0; }                                                   /* lastz.c:7405 */
+        else if (!strcmp(a, "--format=rdotplot+score")) { o->format = 9; o->dotScore = 1; }
+        else if (starts(a, "--rdotplot=")) { if (o->dotplotFile) lzb_die("duplicated or conflicting option \"%s\"", a); o->dotplotFile = v; o->dotplotFileScore = 0; }   /* lastz.c:7489 */
+        else if (starts(a, "--rdotplot+score=")) { if (o->dotplotFile) lzb_die("duplicated or conflicting option \"%s\"", a); o->dotplotFile = v; o->dotplotFileScore = 1; }
         else if (!strcmp(a, "--format=cigar") || !strcmp(a, "--cigar")) o->format = 7;
         else if (starts(a, "--format=sam") || starts(a, "--format=softsam") || starts(a, "--sam") || starts(a, "--softsam")) {           /* lastz.c:7170-7248 */
             const char* n = starts(a, "--format=") ? a + 9 : a + 2;
@@ -331,6 +340,9 @@ int main(int argc, char** argv) {
         lzb_axt_header(out, "lastz.v1.04.58", o.args, &ss, textK, textL, o.X, o.Y);
     }
     uint64_t axtNumber = 0, rowNumber = 0;
+    lzb_rdotplot dotMain, dotSide; memset(&dotMain, 0, sizeof dotMain); memset(&dotSide, 0, sizeof dotSide);
+    FILE* dotOut = NULL;
+    if (o.dotplotFile) { dotOut = fopen(o.dotplotFile, "wt"); if (!dotOut) lzb_die("fopen_or_die failed to open \"%s\" for \"wt\"", o.dotplotFile); }
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
     uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
@@ -508,11 +520,13 @@ int main(int argc, char** argv) {
                     reported = 1; segs = NULL; nsegs = 0;
                     int hd = 0;
                     for (lzb_alignel* a = one; a; a = a->next) {
+                        if (o.blastHeader && !hd) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); hd = 1; }
                         if (o.format == 0) { if (!hd) { lzb_lav_strand_header(out, &target, &query); hd = 1; } lzb_lav_align(out, &target, &query, a); }
                         else if (o.format == 4) lzb_maf_align(out, &target, &query, a);
                         else if (o.format == 5) lzb_axt_align(out, &target, &query, a, &axtNumber);
                         else if (o.format == 6) { if (!hd) { lzb_gfa_strand_header(out, &target, &query); hd = 1; } lzb_gfa_align(out, &target, &query, a, &ss); }
                         else if (o.format == 7) lzb_cigar_align(out, &target, &query, a);
+                    else if (o.format == 9) lzb_rdotplot_align(out, &dotMain, &target, &query, a, &ss, o.dotScore);
                     else if (o.format == 8) lzb_sam_align(out, &target, &query, a, o.samEqx, o.samSoft);
                         else if (o.format >= 2) lzb_fieldlist_align(out, o.fields, &target, &query, a, &rowNumber);
                     }
@@ -524,6 +538,8 @@ int main(int argc, char** argv) {
             int headerDone = 0;
             if (!o.gapped) {
                 for (uint64_t k = 0; k < nsegs; k++) {
+                    if (dotOut) lzb_rdotplot_match(dotOut, &dotSide, &target, &query, &segs[k], &ss, o.dotplotFileScore);
+                    if (o.blastHeader && !headerDone) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); headerDone = 1; }   /* per query and strand, before its first row */
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_match(out, &target, &query, &segs[k]);
@@ -538,6 +554,7 @@ int main(int argc, char** argv) {
                         lzb_gfa_match(out, &target, &query, &segs[k]);
                     }
                     else if (o.format == 7) lzb_cigar_match(out, &target, &query, &segs[k]);
+                    else if (o.format == 9) lzb_rdotplot_match(out, &dotMain, &target, &query, &segs[k], &ss, o.dotScore);
                     else if (o.format == 8) lzb_sam_match(out, &target, &query, &segs[k], o.samEqx, o.samSoft);
                     else if (o.format >= 2) lzb_fieldlist_match(out, o.fields, &target, &query, &segs[k], &rowNumber);
                 }
@@ -568,6 +585,8 @@ int main(int argc, char** argv) {
                 if (o.selfCompare && list)                        /* mirrorGapped, lastz.c:3494-3498 */
                     list = lzb_mirror_alignments(list, &target, &query, &ss);
                 for (lzb_alignel* a = list; a; a = a->next) {
+                    if (dotOut) lzb_rdotplot_align(dotOut, &dotSide, &target, &query, a, &ss, o.dotplotFileScore);
+                    if (o.blastHeader && !headerDone) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); headerDone = 1; }
                     if (o.format == 0) {
                         if (!headerDone) { lzb_lav_strand_header(out, &target, &query); headerDone = 1; }
                         lzb_lav_align(out, &target, &query, a);
@@ -578,6 +597,7 @@ int main(int argc, char** argv) {
                         lzb_gfa_align(out, &target, &query, a, &ss);
                     }
                     else if (o.format == 7) lzb_cigar_align(out, &target, &query, a);
+                    else if (o.format == 9) lzb_rdotplot_align(out, &dotMain, &target, &query, a, &ss, o.dotScore);
                     else if (o.format == 8) lzb_sam_align(out, &target, &query, a, o.samEqx, o.samSoft);
                     else if (o.format >= 2) lzb_fieldlist_align(out, o.fields, &target, &query, a, &rowNumber);
                     else lzb_die("--format=segments needs --nogapped");
@@ -604,5 +624,6 @@ int main(int argc, char** argv) {
     lzb_seqfile_close(qf); lzb_seqfile_close(tf);
     lzb_target_free(T); lzb_close(ctx); lzb_seq_free(&target);
     if (out != stdout) fclose(out);
+    if (dotOut) fclose(dotOut);
     return 0;
 }

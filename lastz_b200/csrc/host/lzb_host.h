@@ -102,6 +102,9 @@ typedef struct lzb_fieldlist lzb_fieldlist;
 lzb_fieldlist* lzb_fieldlist_parse(const char* commaSeparatedNames);      /* parse_genpaf_keys genpaf.c:1945 */
 lzb_fieldlist* lzb_fieldlist_standard(void);                              /* --format=general */
 lzb_fieldlist* lzb_fieldlist_mapping(void);                               /* --format=mapping */
+lzb_fieldlist* lzb_fieldlist_paf(int wfmash);                             /* --format=paf[:minimap2|:wfmash] */
+lzb_fieldlist* lzb_fieldlist_blastn(void);                                /* --format=blastn[-] */
+void lzb_blastn_header(FILE*, const char* prog, const char* args, const char* databaseFile, const lzb_seq* query);
 void lzb_fieldlist_header(FILE*, const lzb_fieldlist*);
 void lzb_fieldlist_align(FILE*, const lzb_fieldlist*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, uint64_t* number);
 void lzb_fieldlist_match(FILE*, const lzb_fieldlist*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, uint64_t* number);
@@ -115,6 +118,9 @@ int  lzb_filters_active(const lzb_filters*);
 int  lzb_filters_reject(const lzb_filters*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, int isSegment);
 void lzb_cigar_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
 void lzb_cigar_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
+typedef struct lzb_rdotplot { char prev1[256], prev2[256]; } lzb_rdotplot;     /* the name pair last announced */
+void lzb_rdotplot_align(FILE*, lzb_rdotplot*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, const lzb_scoreset*, int withScore);
+void lzb_rdotplot_match(FILE*, lzb_rdotplot*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, const lzb_scoreset*, int withScore);
 void lzb_sam_header(FILE*, const lzb_seq* s1);                             /* sam.c:196-232 */
 void lzb_sam_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, int markMismatches, int softClip);
 void lzb_sam_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, int markMismatches, int softClip);

@@ -181,6 +181,13 @@ FIELD_CASES = [
     ("", "", ["--format=sam+eqx"]),                               # =/X runs instead of M
     ("", "[multi]", ["--format=softsam+eqx-", "--nogapped"]),
     ("", "[2000..18000]", ["--format=sam-"]),
+    ("", "", ["--format=paf"]),                                   # genpafPafMinimap2Keys: cg:Z: with M runs
+    ("", "[multi]", ["--format=paf:wfmash", "--strand=minus"]),   # ... with =/X runs
+    ("", "", ["--format=blastn"]),                                # comment block per query and strand, e-value and bit score
+    ("", "", ["--format=blastn-", "--nogapped"]),
+    ("", "", ["--format=rdotplot"]),                              # one line segment per gap-free block, names announced once
+    ("[100..9000]", "[2000..18000]", ["--format=rdotplot+score"]),
+    ("", "[multi]", ["--format=rdotplot+score", "--nogapped", "--strand=minus"]),
 ]
 
 # --format=gfa (gfa.c:95-330): A lines + one a line per gap-free block

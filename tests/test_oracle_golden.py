@@ -177,6 +177,18 @@ def test_oracle_filters_match_reference(opts):
     same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])
 
 
+@pytest.mark.parametrize("opts,score", [(["--format=axt"], 0), (["--format=maf-", "--nogapped"], 1)])
+def test_oracle_rdotplot_side_file(tmp_path, opts, score):
+    """--rdotplot[+score]=<file>: the dot plot written next to the main output (output.c:713, :928)"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    flag = "--rdotplot+score=" if score else "--rdotplot="
+    got = run_cli(ORACLE_CLI, [CAT, PIG] + opts + [flag + str(tmp_path / "o.dots")])[0]
+    want = run_cli(REF_CLI, [CAT, PIG] + opts + [flag + str(tmp_path / "r.dots")])[0]
+    assert open(tmp_path / "o.dots").read() == open(tmp_path / "r.dots").read()
+    assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]
+
+
 def test_multi_target_refusals():
     """what a partitioned target does not do yet stops with a FAILURE instead of giving other results than the reference"""
     import subprocess
