@@ -405,7 +405,14 @@ void lzb_sam_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alig
         if (w2.trueLen - (qstart - 1) > w2.len - (pos2 - w2.offset)) lzb_die("softsam needs the whole read: %s was loaded as a subrange", name2);
         for (uint32_t x = width; x < w2.trueLen - (qstart - 1); x++) { uint8_t c = s2->v[pos2 + x]; fputc(c >= 'A' && c <= 'Z' ? c + 32 : c, f); }
     }
-    fprintf(f, "\t*\n");
+    if (!s2->vq) fprintf(f, "\t*\n");
+    else {                                                       /* print_query_quals sam.c:764: the same stretch of the quality string, as is */
+        fputc('\t', f);
+        if (softMasked && qstart > 1) for (uint32_t x = 0; x < qstart - 1; x++) fputc(s2->vq[pos2 - (qstart - 1) + x], f);
+        for (uint32_t x = 0; x < width; x++) fputc(s2->vq[pos2 + x], f);
+        if (softMasked && qend < w2.trueLen) for (uint32_t x = width; x < w2.trueLen - (qstart - 1); x++) fputc(s2->vq[pos2 + x], f);
+        fputc('\n', f);
+    }
 }
 void lzb_sam_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g, int markMismatches, int softMasked) {
     lzb_editscript es = { 1, 1, LZB_OP_SUB, { LZB_OP_SUB | (g->length << 2) } };

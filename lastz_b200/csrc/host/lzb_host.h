@@ -20,6 +20,7 @@
 /* the subset of `seq` (sequences.h:381-588) the path and the writers need */
 typedef struct lzb_seq {
     uint8_t* v;          /* bases, NUL terminated (v[len] == 0) */
+    uint8_t* vq;         /* base qualities parallel to v (FASTQ input), or NULL; only the SAM writer reads them */
     uint32_t len;        /* bases held in v */
     uint32_t startLoc;   /* 1-based position of v[0] in the full sequence */
     uint32_t trueLen;    /* length of the full sequence */

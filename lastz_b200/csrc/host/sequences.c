@@ -21,7 +21,7 @@ void lzb_die(const char* fmt, ...) {
 struct lzb_seqfile {
     char* filename; char* contigName;
     FILE* f;
-    int is2bit, bigEndian, isNib;
+    int is2bit, bigEndian, isNib, isFastq;
     uint32_t start, end;        /* 1-based inclusive limits, 0 = none */
     int unmask;
     uint32_t contig;            /* sequences delivered so far */
@@ -101,7 +101,7 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
     char* tb = strstr(s, ".2bit/");
     if (tb) { sf->contigName = dupstr(tb + 6); tb[5] = 0; }
     sf->filename = s;
-    if (!strcmp(s, "(stdin)")) { sf->f = stdin; return sf; }    /* the query may come from stdin, as FASTA (lastz.c:8762ff) */
+    if (!strcmp(s, "(stdin)")) { sf->f = stdin; int c = fgetc(stdin); if (c != EOF) ungetc(c, stdin); sf->isFastq = c == '@'; return sf; }    /* the query may come from stdin, as FASTA (lastz.c:8762ff) */
     sf->f = fopen(s, "rb");
     if (!sf->f) lzb_die("fopen_or_die failed to open \"%s\" for \"rb\"", s);
     unsigned char magic[4];
@@ -123,6 +123,7 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
         sf->isNib = 1; sf->bigEndian = (be == 0x6BE93D3Au);
     } else {
         rewind(sf->f);
+        sf->isFastq = got > 0 && magic[0] == '@';           /* the first character decides (sequences.c:9106) */
     }
     return sf;
 }
@@ -149,7 +150,7 @@ void lzb_seqfile_close(lzb_seqfile* sf) {
 void lzb_seq_free(lzb_seq* s) {
     for (uint32_t k = 0; k < s->npart; k++) { free(s->part[k].header); free(s->part[k].shortHeader); }
     free(s->part);
-    free(s->v); free(s->filename); free(s->header); free(s->shortHeader);
+    free(s->v); free(s->vq); free(s->filename); free(s->header); free(s->shortHeader);
     memset(s, 0, sizeof *s);
 }
 
@@ -168,6 +169,7 @@ static void apply_limits(lzb_seqfile* sf, lzb_seq* out, uint8_t* all, uint32_t t
     out->len = b - a + 1; out->startLoc = a; out->trueLen = total;
     out->v = malloc((size_t)out->len + 1);
     memcpy(out->v, all + a - 1, out->len); out->v[out->len] = 0;
+    if (out->vq) { uint8_t* allq = out->vq; out->vq = malloc((size_t)out->len + 1); memcpy(out->vq, allq + a - 1, out->len); out->vq[out->len] = 0; free(allq); }
     if (sf->unmask) for (uint32_t i = 0; i < out->len; i++) out->v[i] = (uint8_t)toupper(out->v[i]);
     free(all);
     for (int m = 0; m < sf->nmasks; m++) {              /* mask_sequence: "begin end" lines, 1-based inclusive, full-sequence coordinates */
@@ -220,6 +222,47 @@ static int next_fasta(lzb_seqfile* sf, lzb_seq* out) {
         v[n++] = (uint8_t)ch; prev = ch;
     }
     if (n > 0x7FFFFFFFu) lzb_die("sequence length %zu exceeds maximum", n);
+    apply_limits(sf, out, v, (uint32_t)n);
+    out->header = hdr; out->shortHeader = short_header(hdr);
+    return 1;
+}
+
+/* load_fastq_sequence / parse_fastq sequences.c:2540-2900: four-line records -- @header, bases, +[header], qualities.
+ * The qualities ride along in seq->vq for the SAM writer. */
+static int next_fastq(lzb_seqfile* sf, lzb_seq* out) {
+    int ch;
+    do ch = fgetc(sf->f); while (ch != EOF && isspace(ch));
+    if (ch == EOF) return 0;
+    if (ch != '@') lzb_die("bad fastq header character in %s (expected \"@\" but read \"%c\")", sf->filename, ch);
+    size_t hcap = 256, hl = 0; char* hdr = malloc(hcap);
+    while ((ch = fgetc(sf->f)) != EOF && ch != '\n' && ch != '\r') {
+        if (hl + 2 > hcap) { hcap *= 2; hdr = realloc(hdr, hcap); }
+        hdr[hl++] = (char)ch;
+    }
+    hdr[hl] = 0;
+    if (ch == '\r') { ch = fgetc(sf->f); if (ch != '\n') ungetc(ch, sf->f); }
+    size_t cap = 1 << 12, n = 0; uint8_t* v = malloc(cap);
+    while ((ch = fgetc(sf->f)) != EOF && ch != '\n' && ch != '\r') {
+        if (!isalpha(ch)) lzb_die("bad fastq nucleotide character in %s, %s (ascii %02X)", sf->filename, hdr, ch);
+        if (n + 1 > cap) { cap *= 2; v = realloc(v, cap); }
+        v[n++] = (uint8_t)ch;
+    }
+    if (ch == '\r') { ch = fgetc(sf->f); if (ch != '\n') ungetc(ch, sf->f); }
+    ch = fgetc(sf->f);
+    if (ch == EOF) lzb_die("premature end of fastq file %s", sf->filename);
+    if (ch != '+') lzb_die("bad fastq separator character in %s, %s (expected \"+\" but read \"%c\")", sf->filename, hdr, ch);
+    size_t k = 0; int same = 1;
+    while ((ch = fgetc(sf->f)) != EOF && ch != '\n' && ch != '\r') { if (k >= hl || hdr[k] != ch) same = 0; k++; }
+    if (k != 0 && !(same && k == hl)) lzb_die("fastq mismatch between sequence and quality headers in %s (%s)", sf->filename, hdr);
+    if (ch == '\r') { ch = fgetc(sf->f); if (ch != '\n') ungetc(ch, sf->f); }
+    size_t q = 0; uint8_t* quals = malloc(n + 1);
+    while ((ch = fgetc(sf->f)) != EOF && ch != '\n' && ch != '\r') {
+        if (ch < '!' || ch > '~') lzb_die("bad fastq quality character in %s, %s (ascii %02X)", sf->filename, hdr, ch);
+        if (q < n) quals[q] = (uint8_t)ch;
+        q++;
+    }
+    if (q != n) lzb_die("fastq quality length (%zu) differs from sequence length (%zu) in %s, %s", q, n, sf->filename, hdr);
+    out->vq = quals;
     apply_limits(sf, out, v, (uint32_t)n);
     out->header = hdr; out->shortHeader = short_header(hdr);
     return 1;
@@ -289,7 +332,7 @@ static int next_nib(lzb_seqfile* sf, lzb_seq* out) {
 static int next_single(lzb_seqfile* sf, lzb_seq* out) {
     memset(out, 0, sizeof *out);
     for (;;) {
-        int ok = sf->is2bit ? next_2bit(sf, out) : sf->isNib ? next_nib(sf, out) : next_fasta(sf, out);
+        int ok = sf->is2bit ? next_2bit(sf, out) : sf->isNib ? next_nib(sf, out) : sf->isFastq ? next_fastq(sf, out) : next_fasta(sf, out);
         if (!ok) return 0;
         sf->contig++;
         if (sf->is2bit || !sf->subset) break;
@@ -322,6 +365,10 @@ void lzb_seq_revcomp(lzb_seq* s) {
             v[i] = y; v[j] = x;
             if (j == 0) break;
         }
+        if (s->vq) {                                         /* qualities are reversed, not complemented (sequences.c:7538) */
+            uint8_t* q = s->npart ? s->vq + s->part[k].sepBefore + 1 : s->vq;
+            for (uint32_t i = 0, j = n; i + 1 < j; i++) { j--; uint8_t x = q[i]; q[i] = q[j]; q[j] = x; }
+        }
     }
     s->revCompFlags ^= LZB_RCF_REVCOMP;
 }
@@ -334,13 +381,17 @@ int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
     memset(out, 0, sizeof *out);
     size_t cap = (size_t)one.len + 1024, n = 0;
     uint8_t* v = malloc(cap + 2);
+    uint8_t* vq = one.vq ? malloc(cap + 2) : NULL;
+    if (vq) vq[n] = 0;
     v[n++] = 0;
     do {
-        if (n + one.len + 2 > cap) { cap = (n + one.len + 2) * 2; v = realloc(v, cap + 2); }
+        if (n + one.len + 2 > cap) { cap = (n + one.len + 2) * 2; v = realloc(v, cap + 2); if (vq) vq = realloc(vq, cap + 2); }
         out->part = realloc(out->part, (out->npart + 1) * sizeof(lzb_partition));
         lzb_partition* p = &out->part[out->npart++];
         p->sepBefore = (uint32_t)(n - 1);
-        memcpy(v + n, one.v, one.len); n += one.len;
+        memcpy(v + n, one.v, one.len);
+        if (vq) { if (!one.vq) lzb_die("%s mixes sequences with and without qualities", sf->filename); memcpy(vq + n, one.vq, one.len); vq[n + one.len] = 0; }
+        n += one.len;
         p->sepAfter = (uint32_t)n; v[n++] = 0;
         p->contig = one.contig; p->startLoc = one.startLoc; p->trueLen = one.trueLen;
         p->header = one.header; p->shortHeader = one.shortHeader; one.header = one.shortHeader = NULL;
@@ -348,7 +399,7 @@ int lzb_seqfile_next(lzb_seqfile* sf, lzb_seq* out) {
         lzb_seq_free(&one);
         if (n > 0x7FFFFFF0u) lzb_die("sequences in %s are too long to be combined with [multi]", sf->filename);
     } while (next_single(sf, &one));
-    out->v = v; out->len = (uint32_t)(n - 1);            /* the last NUL is the terminator: v[len] == 0 */
+    out->v = v; out->vq = vq; out->len = (uint32_t)(n - 1);            /* the last NUL is the terminator: v[len] == 0 */
     out->startLoc = 1; out->trueLen = out->len; out->contig = 1; out->revCompFlags = LZB_RCF_FORWARD;
     out->header = dupstr(""); out->shortHeader = dupstr("");
     return 1;

@@ -233,6 +233,15 @@ FILTER_CASES = [
     ["--match=10,30", "--format=general-", "--nogapped"],
 ]
 
+# FASTQ queries (load_fastq_sequence sequences.c:2540): four-line records, qualities carried to the SAM writer
+FASTQ_CASES = [
+    ("shorties.fq", ["--format=general-", "K=2500"]),
+    ("shorties.fq", ["--format=sam", "K=2500"]),                    # QUAL column from the file, reversed on the - strand
+    ("shorties.fq", ["--format=softsam+eqx-", "K=2500", "--nogapped"]),
+    ("shorties.fq[multi]", ["--format=softsam", "K=2500", "--strand=minus"]),
+    ("shorties.fq[20..150]", ["--format=maf-", "K=2000"]),
+]
+
 # adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
 # strands collected into one table and the - strand finished first, lastz.c:1426,1678-1700): target suffix, query, options
 ADAPTIVE_CASES = [

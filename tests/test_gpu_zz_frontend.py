@@ -6,7 +6,7 @@ import os
 
 import pytest
 
-from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, FIELD_CASES, FILTER_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
+from conftest import ADAPTIVE_CASES, ANYORNONE_CASES, FASTQ_CASES, FIELD_CASES, FILTER_CASES, GFA_CASES, GOLDEN, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, ORACLE_CLI, PRODUCT_CLI, REF_CLI, run_cli, same_output
 
 pytestmark = pytest.mark.gpu
 
@@ -69,3 +69,10 @@ def test_cli_filters(opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
     files = adaptive_case_files("aglobin")
     same_output(run_cli(PRODUCT_CLI, files + opts)[0], run_cli(ref, files + opts)[0])
+
+
+@pytest.mark.parametrize("query,opts", FASTQ_CASES)
+def test_cli_fastq_query(query, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    args = [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, query)] + opts
+    same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])

@@ -7,7 +7,7 @@ import os
 
 import pytest
 
-from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FIELD_CASES, FILTER_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FASTQ_CASES, FIELD_CASES, FILTER_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -187,6 +187,14 @@ def test_oracle_rdotplot_side_file(tmp_path, opts, score):
     want = run_cli(REF_CLI, [CAT, PIG] + opts + [flag + str(tmp_path / "r.dots")])[0]
     assert open(tmp_path / "o.dots").read() == open(tmp_path / "r.dots").read()
     assert [l for l in got.splitlines() if "lastz.v" not in l] == [l for l in want.splitlines() if "lastz.v" not in l]
+
+
+@pytest.mark.parametrize("query,opts", FASTQ_CASES)
+def test_oracle_fastq_query_matches_reference(query, opts):
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    args = [AGLOBIN + "/human", os.path.join(GOLDEN, query)] + opts
+    same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
 
 
 def test_multi_target_refusals():
