@@ -73,14 +73,34 @@ static void parse_options(options* o, int argc, char** argv) {
     o->entropy = 1; o->trimToPeak = 1; o->tracebackBytes = 80u * 1024 * 1024; o->hashBits = 16;
     o->speculation = 32;
     char* wordSeed = NULL;
+    /* shortcuts that stand for a string of options (expanders[] lastz.c:559-577, current versions); the command line
+     * recorded for the headers keeps the shortcut itself */
+    static const struct { const char* name; const char* expansion; } shortcuts[] = {
+        { "--yasra98", "T=2 Z=20 --match=1,6 O=8 E=1 Y=20 K=22 L=30 --identity=98..100 --ambiguous=n --noytrim" },
+        { "--yasra95", "T=2 Z=20 --match=1,5 O=8 E=1 Y=20 K=22 L=30 --identity=95..100 --ambiguous=n --noytrim" },
+        { "--yasra90", "T=2 Z=20 --match=1,5 O=6 E=1 Y=20 K=22 L=30 --identity=90..100 --ambiguous=n --noytrim" },
+        { "--yasra85", "T=2 --match=1,2 O=4 E=1 Y=20 K=22 L=30 --identity=85..100 --ambiguous=n --noytrim" },
+        { "--yasra75", "T=2 --match=1,1 O=3 E=1 Y=20 K=22 L=30 --identity=75..100 --ambiguous=n --noytrim" },
+        { "--yasra95short", "T=2 --match=1,7 O=6 E=1 Y=14 K=10 L=14 --identity=95..100 --ambiguous=n --noytrim" },
+        { "--yasra85short", "T=2 --match=1,3 O=4 E=1 Y=14 K=11 L=14 --identity=85..100 --ambiguous=n --noytrim" },
+    };
+    const char** words = malloc(((size_t)argc + 1) * 16 * sizeof *words); char* silent = calloc(((size_t)argc + 1) * 16, 1); int nwords = 0;
     for (int i = 1; i < argc; i++) {
-        const char* a = argv[i]; const char* v = strchr(a, '='); v = v ? v + 1 : "";
+        int sc = -1;
+        for (size_t k = 0; k < sizeof shortcuts / sizeof shortcuts[0]; k++) if (!strcmp(argv[i], shortcuts[k].name)) sc = (int)k;
+        if (sc < 0) { words[nwords++] = argv[i]; continue; }
+        if (strlen(o->args) + strlen(argv[i]) + 2 < sizeof o->args) { strcat(o->args, argv[i]); strcat(o->args, " "); }
+        char* copy = strdup(shortcuts[sc].expansion);
+        for (char* tok = strtok(copy, " "); tok; tok = strtok(NULL, " ")) { silent[nwords] = 1; words[nwords++] = tok; }
+    }
+    for (int i = 0; i < nwords; i++) {
+        const char* a = words[i]; const char* v = strchr(a, '='); v = v ? v + 1 : "";
         if (a[0] != '-' && !(strlen(a) > 1 && a[1] == '=' && strchr("CTWKLXYOEZQ", a[0]))) {
             if (!o->targetSpec) o->targetSpec = a; else if (!o->querySpec) o->querySpec = a;
             else lzb_die("Can't understand \"%s\"", a);
             continue;
         }
-        if (strlen(o->args) + strlen(a) + 2 < sizeof o->args) { strcat(o->args, a); strcat(o->args, " "); }
+        if (!silent[i] && strlen(o->args) + strlen(a) + 2 < sizeof o->args) { strcat(o->args, a); strcat(o->args, " "); }
         if (!strcmp(a, "T=0")) { o->withTrans = 0; o->haveTrans = 1; }
         else if (!strcmp(a, "T=1")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 1; }
         else if (!strcmp(a, "T=2")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 0; }

@@ -240,6 +240,10 @@ FASTQ_CASES = [
     ("shorties.fq", ["--format=softsam+eqx-", "K=2500", "--nogapped"]),
     ("shorties.fq[multi]", ["--format=softsam", "K=2500", "--strand=minus"]),
     ("shorties.fq[20..150]", ["--format=maf-", "K=2000"]),
+    # read-mapping shortcuts (expanders[] lastz.c:559-577): seeds with two transitions, unit scores, identity filter, N ambiguous
+    ("shorties.fq", ["--yasra85", "--format=general-"]),
+    ("shorties.fq", ["--yasra95short", "--format=softsam-"]),
+    ("shorties.fa", ["--yasra90", "--format=lav"]),
 ]
 
 # adaptive HSP threshold K=top<N>% / K=top<bases> (add_segment's coverage-limited min-heap segment.c:981-1180, both
