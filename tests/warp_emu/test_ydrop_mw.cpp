@@ -148,6 +148,9 @@ int main() {
     bad += one_case(n++, 2500, 0.04, 0.010, 80u << 20, 6000, 1, 1);      // k_ydrop_warp<16>
     bad += one_case(n++, 2500, 0.06, 0.015, 200000, 6000, 0, 1);         // ... truncated, --noytrim
     bad += one_case(n++, 2000, 0.04, 0.010, 80u << 20, 9400, 1, 2);      // k_ydrop<256> (shared-memory ring)
+    bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 400, 1);          // a Y-drop of a few mismatches (read-mapping settings): bands of a handful of columns
+    bad += one_case(n++, 3000, 0.02, 0.004, 80u << 20, 14, 0);           // ... smaller than one mismatch, --noytrim
+    bad += one_case(n++, 2000, 0.04, 0.010, 80u << 20, 60, 1, 1);        // ... on the one-warp kernel
     bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 1, 0, 1);   // partitioned query: both sweeps end at a NUL
     bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 0, 0, 1);   // ... --noytrim: the partition edge is a sequence edge
     bad += one_case(n++, 3000, 0.04, 0.010, 80u << 20, 9400, 1, 0, 2);   // target and query both partitioned
