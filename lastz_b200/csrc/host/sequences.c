@@ -22,6 +22,7 @@ struct lzb_seqfile {
     char* filename; char* contigName;
     FILE* f;
     int is2bit, bigEndian, isNib, isFastq;
+    int nameParse; char* nickname;     /* [nameparse=...], [nickname=...] */
     uint32_t start, end;        /* 1-based inclusive limits, 0 = none */
     int unmask;
     uint32_t contig;            /* sequences delivered so far */
@@ -36,6 +37,7 @@ struct lzb_seqfile {
     int multi;                  /* [multi]: deliver every (selected) sequence of the file as one partitioned sequence */
 };
 
+enum { NAME_CORE = 0, NAME_DARKSPACE, NAME_ALNUM, NAME_FULL };      /* how a header becomes a name, see short_header_as */
 static char* dupstr(const char* s) { char* d = malloc(strlen(s) + 1); strcpy(d, s); return d; }
 
 static uint32_t rd4(lzb_seqfile* sf) {
@@ -58,6 +60,10 @@ static void parse_actions(lzb_seqfile* sf, char* act) {
         else {
             for (char* p = strtok(tok, ","); p; p = strtok(NULL, ",")) {
                 if (!strcmp(p, "unmask")) sf->unmask = 1;
+                else if (!strcmp(p, "nameparse=full") || !strcmp(p, "fullname") || !strcmp(p, "fullnames")) sf->nameParse = NAME_FULL;   /* sequences.c:8273 */
+                else if (!strcmp(p, "nameparse=alphanum") || !strcmp(p, "nameparse=alnum")) sf->nameParse = NAME_ALNUM;
+                else if (!strcmp(p, "nameparse=darkspace")) sf->nameParse = NAME_DARKSPACE;
+                else if (!strncmp(p, "nickname=", 9)) sf->nickname = dupstr(p + 9);
                 else if (!strcmp(p, "multi") || !strcmp(p, "multiple")) sf->multi = 1;
                 else if (p[0] == '@') goto subset_file;           /* @<file> is the short spelling of subset=<file> */
                 else if (!strncmp(p, "nmask=", 6) || !strncmp(p, "xmask=", 6) || !strncmp(p, "softmask=", 9)) {
@@ -154,12 +160,32 @@ void lzb_seq_free(lzb_seq* s) {
     memset(s, 0, sizeof *s);
 }
 
-/* create_short_header sequences.c: first word of the header, '>' and leading blanks skipped */
-static char* short_header(const char* h) {
-    while (*h == '>' || *h == ' ' || *h == '\t') h++;
-    size_t n = 0; while (h[n] && !isspace((unsigned char)h[n])) n++;
+/* shorten_header sequences.c:5913-6020: the name a sequence goes by in the output.  '>' and blanks are skipped, then
+ * "reverse complement of " and "positions <x> of "; the name runs to the first blank, '|' or ':' (default), to the first
+ * blank ([nameparse=darkspace]) or over letters, digits and '_' ([nameparse=alphanum]); the file suffixes .nib .2bit
+ * .hsx .fasta .fa are dropped except in the alphanumeric mode.  [nameparse=full] keeps the whole header line. */
+static char* short_header_as(const char* h, int how) {
+    if (how == NAME_FULL) return dupstr(h);              /* the header as it stands (seq->header, '>' included for FASTA) */
+    if (*h == '>') h++;
+    while (*h == ' ' || *h == '\t') h++;
+    if (!strncmp(h, "reverse complement of ", 22)) { h += 22; while (*h == ' ' || *h == '\t') h++; }
+    if (!strncmp(h, "positions ", 10)) {
+        const char* g = h + 10;
+        while (*g == ' ' || *g == '\t') g++;
+        while (*g && *g != ' ' && *g != '\t') g++;
+        while (*g == ' ' || *g == '\t') g++;
+        if (!strncmp(g, "of ", 3)) { h = g + 3; while (*h == ' ' || *h == '\t') h++; }
+    }
+    size_t n;
+    if (how == NAME_ALNUM) n = strspn(h, "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789_");
+    else {
+        n = strcspn(h, how == NAME_DARKSPACE ? " \t" : " \t|:");
+        static const char* const suffix[5] = { ".nib", ".2bit", ".hsx", ".fasta", ".fa" };
+        for (int k = 0; k < 5; k++) { size_t sl = strlen(suffix[k]); if (n > sl && !strncmp(h + n - sl, suffix[k], sl)) n -= sl; }
+    }
     char* d = malloc(n + 1); memcpy(d, h, n); d[n] = 0; return d;
 }
+static char* name_for(const lzb_seqfile* sf, const char* h) { return sf->nickname ? dupstr(sf->nickname) : short_header_as(h, sf->nameParse); }
 
 static void apply_limits(lzb_seqfile* sf, lzb_seq* out, uint8_t* all, uint32_t total) {
     uint32_t a = sf->start ? sf->start : 1, b = sf->end ? sf->end : total;
@@ -223,7 +249,7 @@ static int next_fasta(lzb_seqfile* sf, lzb_seq* out) {
     }
     if (n > 0x7FFFFFFFu) lzb_die("sequence length %zu exceeds maximum", n);
     apply_limits(sf, out, v, (uint32_t)n);
-    out->header = hdr; out->shortHeader = short_header(hdr);
+    out->header = hdr; out->shortHeader = name_for(sf, hdr);
     return 1;
 }
 
@@ -264,7 +290,7 @@ static int next_fastq(lzb_seqfile* sf, lzb_seq* out) {
     if (q != n) lzb_die("fastq quality length (%zu) differs from sequence length (%zu) in %s, %s", q, n, sf->filename, hdr);
     out->vq = quals;
     apply_limits(sf, out, v, (uint32_t)n);
-    out->header = hdr; out->shortHeader = short_header(hdr);
+    out->header = hdr; out->shortHeader = name_for(sf, hdr);
     return 1;
 }
 
@@ -305,7 +331,7 @@ static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
     for (uint32_t k = 0; k < mb; k++) for (uint32_t i = 0; i < ms[mb + k]; i++) v[ms[k] + i] = (uint8_t)tolower(v[ms[k] + i]);
     free(packed); free(ns); free(ms);
     apply_limits(sf, out, v, dna);
-    out->header = dupstr(sf->names[ix]); out->shortHeader = short_header(sf->names[ix]);
+    out->header = dupstr(sf->names[ix]); out->shortHeader = name_for(sf, sf->names[ix]);
     return 1;
 }
 
@@ -325,7 +351,7 @@ static int next_nib(lzb_seqfile* sf, lzb_seq* out) {
     apply_limits(sf, out, v, length);
     char hdr[1200];
     snprintf(hdr, sizeof hdr, "%s:%u-%u", sf->filename, out->startLoc, out->startLoc + out->len - 1);
-    out->header = dupstr(hdr); out->shortHeader = short_header(hdr);
+    out->header = dupstr(hdr); out->shortHeader = name_for(sf, hdr);
     return 1;
 }
 

@@ -197,6 +197,19 @@ def test_oracle_fastq_query_matches_reference(query, opts):
     same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
 
 
+@pytest.mark.parametrize("tact,qact", [("", ""), (",nameparse=darkspace", "[nameparse=darkspace]"), (",nameparse=alphanum", "[nameparse=alphanum]"),
+                                       (",nameparse=full", "[fullname]"), ("", "[nickname=bob]")])
+def test_oracle_sequence_names(tact, qact):
+    """shorten_header (sequences.c:5913): names cut at blanks, '|' and ':' by default, file suffixes dropped, the
+    "reverse complement of" / "positions x of" prefixes skipped; [nameparse=...] and [nickname=...] (tests/golden/names.fa
+    is a hand-made file with such headers)"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    f = os.path.join(GOLDEN, "names.fa")
+    args = [f + "[multi" + tact + "]", f + qact, "--format=general-:name1,name2,start1,end1", "K=2000", "--nogapped"]
+    same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
 def test_multi_target_refusals():
     """what a partitioned target does not do yet stops with a FAILURE instead of giving other results than the reference"""
     import subprocess
