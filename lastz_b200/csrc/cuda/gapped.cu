@@ -341,6 +341,34 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
             a->s = s < P->scoreThreshold ? P->scoreThreshold : s; a->isTrivial = 1; m.align = a;
         }
     }
+    /* identical_partition_of_sequence gapped_extend.c:2034-2120 -> :1185-1230: an unpartitioned query that equals
+     * one partition of a [multi] target (the first such partition) gets the trivial alignment of that partition */
+    if (P->identityCheck && !G.al[n].align && !tSeparators.empty() && qSeparators.empty()) {
+        for (size_t k = 0; k < tSeparators.size(); k++) {        /* partition k lies between separator k and the next one (or the end) */
+            const u32 before = tSeparators[k], after = k + 1 < tSeparators.size() ? tSeparators[k + 1] : len1;
+            if (after - (before + 1) != len2) continue;
+            bool same = true; s32 s = 0; const s32* sub = c->hostSub;
+            for (u32 i = 0; i < len2; i++) {
+                u8 a = t->h_seq[before + 1 + i], b = q->h_seq[i];
+                if (a >= 'a' && a <= 'z') a -= 32;
+                if (b >= 'a' && b <= 'z') b -= 32;
+                if (a != b) { same = false; break; }
+                s32 v = sub[(u32)a * 256 + b];
+                if (s == 0x7FFFFFFF) ; else if (v <= 0 || s < 0x7FFFFFFF - v) s += v; else s = 0x7FFFFFFF;
+            }
+            if (!same) continue;
+            galn& m = G.al[n];
+            m.pos1 = before + 1; m.pos2 = 0; m.end1 = after - 1; m.end2 = len2 - 1;
+            add_diag(m, m.pos1, m.pos2, m.end1, m.end2);
+            list_insert(G, (int)n);
+            m.devIx = (int)G.committed.size(); G.committed.push_back((int)n);
+            lzb_alignel* a = (lzb_alignel*)calloc(1, sizeof *a);
+            a->script = es_new(4); es_add(&a->script, LZB_OP_SUB, len2);
+            a->beg1 = before + 2; a->beg2 = 1; a->end1 = after; a->end2 = len2; a->seq1 = h1; a->seq2 = h2;
+            a->s = s < P->scoreThreshold ? P->scoreThreshold : s; a->isTrivial = 1; m.align = a;
+            break;
+        }
+    }
 
     /* ---- speculation lanes (cached in the context across calls) ---- */
     const bool strict = P->speculation < 0;                    /* internal: exact-order rerun after a scheduling violation */

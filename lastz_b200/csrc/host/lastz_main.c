@@ -374,20 +374,14 @@ int main(int argc, char** argv) {
         if ((query.npart || target.npart) && (o.format == 0 || o.format == 6)) lzb_die("%s format can't handle multi-sequences", o.format == 0 ? "lav" : "gfa");
         if (target.npart) {
             /* a partitioned target: hits, extensions and DP sweeps stop at its NULs like they do in a partitioned query.
-             * Not built: what the reference does PER PARTITION beyond chaining -- the segments writer's rows
-             * and the trivial self-alignment of a query that equals one target partition, which bounds every other
-             * alignment (identical_partition_of_sequence gapped_extend.c:2034, :1185-1230).  Such runs stop here. */
+             * A query that equals one target partition gets its trivial self-alignment from the library
+             * (identical_partition_of_sequence gapped_extend.c:2034, :1185-1230).  Not built: the segments writer's rows
+             * per partition, and what --notrivial does with partitions (:1131-1141).  Such runs stop here. */
             if (o.selfCompare || o.segmentsFile || o.anyOrNone || o.adaptive || o.inhibitTrivial || o.format == 1)
                 lzb_die("lastz_b200 does not combine a [multi] target with --self, --notrivial, --segments, --format=segments, --anyornone or an adaptive threshold yet");
-            if (o.gapped && o.whichStrand >= 0 && query.revCompFlags == target.revCompFlags) {     /* only the + strand pass can be trivial */
-                int twin = 0;
-                if (query.npart) twin = query.len == target.len && !strncasecmp((const char*)query.v + 1, (const char*)target.v + 1, query.len - 1);
-                else for (uint32_t p = 0; p < target.npart && !twin; p++) {
-                    const lzb_partition* tp = &target.part[p];
-                    twin = tp->sepAfter - (tp->sepBefore + 1) == query.len && !strncasecmp((const char*)query.v, (const char*)target.v + tp->sepBefore + 1, query.len);
-                }
-                if (twin) lzb_die("%s is identical to (part of) the [multi] target; lastz_b200 does not build the trivial self-alignment of partitions yet", query.shortHeader ? query.shortHeader : "the query");
-            }
+            /* both partitioned and identical: one trivial self-alignment per partition (gapped_extend.c:1232-1290), not built */
+            if (o.gapped && o.whichStrand >= 0 && query.npart && query.len == target.len && !strncasecmp((const char*)query.v + 1, (const char*)target.v + 1, query.len - 1))
+                lzb_die("the [multi] query is identical to the [multi] target; lastz_b200 does not build the trivial self-alignments of partitions yet");
         }
         if (query.npart && (o.selfCompare || o.segmentsFile || o.anyOrNone))
             lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments or --anyornone yet");
@@ -584,7 +578,7 @@ int main(int argc, char** argv) {
                 gp.yDrop = o.Y; gp.trimToPeak = o.trimToPeak; gp.scoreThreshold = o.L; gp.allBounds = o.allBounds;
                 if (o.adaptive && !o.haveL) gp.scoreThreshold = lowAnchorScore;   /* lastz.c:3405-3410 */
                 gp.inhibitTrivial = o.inhibitTrivial; gp.tracebackBytes = o.tracebackBytes;
-                gp.identityCheck = query.revCompFlags == target.revCompFlags && !query.npart && !target.npart;   /* identical_sequences: unpartitioned only, gapped_extend.c:1147 */
+                gp.identityCheck = query.revCompFlags == target.revCompFlags && !query.npart;   /* identical_sequences :1147, identical_partition_of_sequence :1131 */
                 gp.speculation = o.speculation;
                 if (lzb_reduce_to_points(ctx, T, Q, segs, nsegs)) lzb_die("%s", lzb_last_error());
                 lzb_alignel* list = NULL;

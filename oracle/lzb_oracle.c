@@ -932,7 +932,33 @@ static int same_sequences(genv* G, s32* score) {
     *score = s; return 1;
 }
 
-/* gapped_extend gapped_extend.c:1012-1604 (unpartitioned sequences) */
+/* identical_partition_of_sequence gapped_extend.c:2034-2120 + score_identical_partition_of :2217: the first partition of
+ * a [multi] target that equals the (unpartitioned) query, case-insensitively; its NUL-to-NUL bounds and score */
+static int same_as_partition(genv* G, u32* sepBefore, u32* sepAfter, s32* score) {
+    if (memchr(G->s2, 0, G->len2) || !memchr(G->s1, 0, G->len1)) return 0;
+    for (u32 before = 0; before < G->len1;) {
+        if (G->s1[before] != 0) return 0;                    /* a partitioned sequence starts with a separator */
+        u32 after = before + 1; while (after < G->len1 && G->s1[after] != 0) after++;
+        if (after - (before + 1) == G->len2) {
+            s32 s = 0; u32 i = 0;
+            for (; i < G->len2; i++) {
+                u8 a = G->s1[before + 1 + i], b = G->s2[i];
+                if (a >= 'a' && a <= 'z') a -= 32;
+                if (b >= 'a' && b <= 'z') b -= 32;
+                if (a != b) break;
+                s32 v = G->c->sub[(u32)a * 256 + b];
+                if (s == 0x7FFFFFFF) ;
+                else if (v <= 0 || s < 0x7FFFFFFF - v) s += v;
+                else s = 0x7FFFFFFF;
+            }
+            if (i == G->len2) { *sepBefore = before; *sepAfter = after; *score = s; return 1; }
+        }
+        before = after;
+    }
+    return 0;
+}
+
+/* gapped_extend gapped_extend.c:1012-1604 */
 int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const uint8_t* h1, const uint8_t* h2,
                       lzb_segment* anchors, uint64_t n, const lzb_gapped_params* P,
                       lzb_alignel** list, lzb_gapped_stats* stats) {
@@ -959,6 +985,20 @@ int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const uint8_t* h1
         lzb_alignel* a = calloc(1, sizeof *a);
         a->script = es_new(); es_add(&a->script, LZB_OP_SUB, G.len1);
         a->beg1 = a->beg2 = 1; a->end1 = a->end2 = G.len1;
+        a->seq1 = h1; a->seq2 = h2;
+        a->s = ts < P->scoreThreshold ? P->scoreThreshold : ts;
+        a->isTrivial = 1; m->align = a;
+    }
+    u32 sepB = 0, sepA = 0;
+    if (P->identityCheck && !G.al[n].align && same_as_partition(&G, &sepB, &sepA, &ts)) {
+        galn* m = &G.al[n];                              /* :1185-1230 the query is one partition of the target */
+        m->pos1 = sepB + 1; m->pos2 = 0; m->end1 = sepA - 1; m->end2 = G.len2 - 1;
+        m->left1 = m->left2 = m->right1 = m->right2 = NOSEG;
+        add_diag(m, m->pos1, m->pos2, m->end1, m->end2);
+        list_insert(&G, (int)n);
+        lzb_alignel* a = calloc(1, sizeof *a);
+        a->script = es_new(); es_add(&a->script, LZB_OP_SUB, G.len2);
+        a->beg1 = sepB + 2; a->beg2 = 1; a->end1 = sepA; a->end2 = G.len2;
         a->seq1 = h1; a->seq2 = h2;
         a->s = ts < P->scoreThreshold ? P->scoreThreshold : ts;
         a->isTrivial = 1; m->align = a;

@@ -212,6 +212,10 @@ MULTI_TARGET_CASES = [
     ("shorties.2bit[multi,51..200]", "aglobin.2bit/human", ["--format=maf-", "K=3000", "--strand=minus"]),
     ("aglobin.2bit[multi]", "shorties.fa[multi]", ["--format=general-", "K=2500", "--chain"]),          # chained per pair of partitions, chain.c:224
     ("aglobin.2bit/human", "shorties.fa[multi]", ["--format=maf-", "K=2000", "--chain=20,30", "--nogapped"]),
+    # a query that IS one partition of the target: trivial self-alignment of that partition (gapped_extend.c:1185-1230)
+    ("aglobin.2bit[multi]", "aglobin.2bit/cow", ["--format=general-"]),
+    ("shorties.fa[multi]", "shorties.fa", ["--format=general-", "K=2000"]),        # all against all, 20 x 20
+    ("names.fa[multi]", "names.fa", ["--format=axt", "K=2000"]),
 ]
 
 # --filter= family (lastz.c:6672-6950; filter_aligns_by_* after the gapped stage, filter_segments_by_* on HSPs): aglobin human x cow

@@ -214,7 +214,7 @@ def test_multi_target_refusals():
     """what a partitioned target does not do yet stops with a FAILURE instead of giving other results than the reference"""
     import subprocess
     t = os.path.join(GOLDEN, "aglobin.2bit[multi]")
-    for q, opts in [("aglobin.2bit/cow", []), ("shorties.fa", ["--notrivial"]), ("shorties.fa", ["--format=lav"]),
+    for q, opts in [("aglobin.2bit[multi]", []), ("shorties.fa", ["--notrivial"]), ("shorties.fa", ["--format=lav"]),
                     ("shorties.fa", ["K=top20%"]), ("shorties.fa", ["--nogapped", "--format=segments"])]:
         p = subprocess.run([ORACLE_CLI, t, os.path.join(GOLDEN, q)] + opts, capture_output=True, text=True)
         assert p.returncode != 0 and "FAILURE" in p.stderr, (q, opts)
