@@ -26,6 +26,7 @@ typedef struct {
     const char* scoresFile; const char* segmentsFile; const char* outputFile;
     int format;                    /* 0 lav, 1 segments, 2 general, 3 general-, 4 maf-, 5 axt, 6 gfa, 7 cigar, 8 sam */
     int samSoft, samEqx, samHeader, blastHeader;
+    int formatIsSegments, haveGappedOption;   /* --format=segments stops at HSPs unless a gapped option says otherwise (lastz.c:8940, :9053) */
     int dotScore; const char* dotplotFile; int dotplotFileScore;   /* --format=rdotplot[+score] (format 9), --rdotplot[+score]=<file> */
     lzb_filters filters;           /* --filter=identity:.. and friends */
     int unitScores; int32_t unitMatch, unitMismatch;   /* --match=<reward>[,<penalty>] lastz.c:6138 */
@@ -144,12 +145,12 @@ static void parse_options(options* o, int argc, char** argv) {
         }
         else if (!strcmp(a, "--nogfextend")) o->gfExtend = LZB_GFEX_NONE;
         else if (!strcmp(a, "--gfextend")) o->gfExtend = LZB_GFEX_XDROP;
-        else if (!strcmp(a, "--nogapped") || !strcmp(a, "--ungapped")) o->gapped = 0;
-        else if (!strcmp(a, "--gapped")) o->gapped = 1;
-        else if (!strcmp(a, "C=0")) { o->chain = 0; o->gapped = 1; }
-        else if (!strcmp(a, "C=1")) { o->chain = 1; o->gapped = 0; }
-        else if (!strcmp(a, "C=2")) { o->chain = 1; o->gapped = 1; }
-        else if (!strcmp(a, "C=3")) { o->chain = 0; o->gapped = 0; }
+        else if (!strcmp(a, "--nogapped") || !strcmp(a, "--ungapped")) { o->gapped = 0; o->haveGappedOption = 1; }
+        else if (!strcmp(a, "--gapped")) { o->gapped = 1; o->haveGappedOption = 1; }
+        else if (!strcmp(a, "C=0")) { o->chain = 0; o->gapped = 1; o->haveGappedOption = 1; }
+        else if (!strcmp(a, "C=1")) { o->chain = 1; o->gapped = 0; o->haveGappedOption = 1; }
+        else if (!strcmp(a, "C=2")) { o->chain = 1; o->gapped = 1; o->haveGappedOption = 1; }
+        else if (!strcmp(a, "C=3")) { o->chain = 0; o->gapped = 0; o->haveGappedOption = 1; }
         else if (!strcmp(a, "--chain")) o->chain = 1;
         else if (starts(a, "--chain=")) { o->chain = 1; if (sscanf(v, "%d,%d", &o->chainDiag, &o->chainAnti) != 2) lzb_die("can't understand %s", a); }
         else if (!strcmp(a, "--nochain")) o->chain = 0;
@@ -214,7 +215,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--format=axt") || !strcmp(a, "--axt")) o->format = 5;
         else if (!strcmp(a, "--format=maf") || !strcmp(a, "--maf")) { o->format = 4; o->mafHeader = 1; }
         else if (!strcmp(a, "--format=gfa") || !strcmp(a, "--gfa")) o->format = 6;
-        else if (!strcmp(a, "--format=segments")) o->format = 1;
+        else if (!strcmp(a, "--format=segments")) { o->format = 2; o->formatIsSegments = 1; o->fields = lzb_fieldlist_parse("name1,start1,end1,name2,start2,end2,strand2,score"); }   /* genpafSegmentKeys, lastz.c:7267 */
         else if (!strcmp(a, "--format=general") || !strcmp(a, "--format=gen")) { o->format = 2; o->fields = lzb_fieldlist_standard(); }   /* default fields, genpaf.h:117 */
         else if (!strcmp(a, "--format=general-") || !strcmp(a, "--format=gen-")) { o->format = 3; o->fields = lzb_fieldlist_standard(); } /* ... without the header line */
         else if (starts(a, "--format=general:") || starts(a, "--format=gen:")) { o->format = 2; o->fields = lzb_fieldlist_parse(strchr(a, ':') + 1); }   /* lastz.c:7319 */
@@ -249,6 +250,8 @@ static void parse_options(options* o, int argc, char** argv) {
     if (!o->targetSpec) lzb_die("You must specify a target file");
     if (o->selfCompare && !o->querySpec) o->querySpec = o->targetSpec;
     if (!o->querySpec) o->querySpec = "(stdin)";                    /* lastz.c:8762: no query file => read it from stdin */
+    if (o->formatIsSegments && !o->haveGappedOption) o->gapped = 0;
+    if (o->formatIsSegments && o->gapped) lzb_die("can't used --writesegments with --gapped");
     if (o->anyOrNone && lzb_filters_active(&o->filters)) lzb_die("lastz_b200 does not combine --anyornone with --filter options yet");
     if (o->adaptive) {
         if (o->gfExtend != LZB_GFEX_XDROP) lzb_die("an adaptive HSP threshold requires --gfextend");   /* the other extensions assume a score, seed_search.c:3003 */
@@ -350,7 +353,6 @@ int main(int argc, char** argv) {
       if ((cut = strstr(n1, ".2bit/"))) cut[5] = 0;
       if ((cut = strstr(n2, ".2bit/"))) cut[5] = 0; }
     if (o.format == 0) lzb_lav_job_header(out, "lastz.v1.04.58", n1, n2, o.args, &ss, textK, textL);
-    else if (o.format == 1) fprintf(out, "#name1\tstart1\tend1\tname2\tstart2\tend2\tstrand2\tscore\n");
     else if (o.format == 2) lzb_fieldlist_header(out, o.fields);
     else if (o.format == 8 && o.samHeader) lzb_sam_header(out, &target);
     else if (o.format == 6) lzb_gfa_job_header(out, "lastz.v1.04.58", n1, n2, o.seedPattern ? o.seedPattern : LZB_SEED_12OF19, seed.withTrans, o.step);
@@ -375,10 +377,10 @@ int main(int argc, char** argv) {
         if (target.npart) {
             /* a partitioned target: hits, extensions and DP sweeps stop at its NULs like they do in a partitioned query.
              * A query that equals one target partition gets its trivial self-alignment from the library
-             * (identical_partition_of_sequence gapped_extend.c:2034, :1185-1230).  Not built: the segments writer's rows
-             * per partition, and what --notrivial does with partitions (:1131-1141).  Such runs stop here. */
-            if (o.selfCompare || o.segmentsFile || o.anyOrNone || o.adaptive || o.inhibitTrivial || o.format == 1)
-                lzb_die("lastz_b200 does not combine a [multi] target with --self, --notrivial, --segments, --format=segments, --anyornone or an adaptive threshold yet");
+             * (identical_partition_of_sequence gapped_extend.c:2034, :1185-1230).  Not built: what --notrivial does with
+             * partitions (:1131-1141).  Such runs stop here. */
+            if (o.selfCompare || o.segmentsFile || o.anyOrNone || o.adaptive || o.inhibitTrivial)
+                lzb_die("lastz_b200 does not combine a [multi] target with --self, --notrivial, --segments, --anyornone or an adaptive threshold yet");
             /* both partitioned and identical: one trivial self-alignment per partition (gapped_extend.c:1232-1290), not built */
             if (o.gapped && o.whichStrand >= 0 && query.npart && query.len == target.len && !strncasecmp((const char*)query.v + 1, (const char*)target.v + 1, query.len - 1))
                 lzb_die("the [multi] query is identical to the [multi] target; lastz_b200 does not build the trivial self-alignments of partitions yet");
@@ -572,7 +574,6 @@ int main(int argc, char** argv) {
                     else if (o.format == 8) lzb_sam_match(out, &target, &query, &segs[k], o.samEqx, o.samSoft);
                     else if (o.format >= 2) lzb_fieldlist_match(out, o.fields, &target, &query, &segs[k], &rowNumber);
                 }
-                if (o.format == 1) lzb_segments_write(out, &target, &query, segs, nsegs);
             } else {
                 lzb_gapped_params gp; memset(&gp, 0, sizeof gp);
                 gp.yDrop = o.Y; gp.trimToPeak = o.trimToPeak; gp.scoreThreshold = o.L; gp.allBounds = o.allBounds;
@@ -614,7 +615,6 @@ int main(int argc, char** argv) {
                     else if (o.format == 9) lzb_rdotplot_align(out, &dotMain, &target, &query, a, &ss, o.dotScore);
                     else if (o.format == 8) lzb_sam_align(out, &target, &query, a, o.samEqx, o.samSoft);
                     else if (o.format >= 2) lzb_fieldlist_align(out, o.fields, &target, &query, a, &rowNumber);
-                    else lzb_die("--format=segments needs --nogapped");
                 }
                 lzb_free_align_list(list);
             }

@@ -96,8 +96,6 @@ void lzb_lav_strand_header(FILE*, const lzb_seq* s1, const lzb_seq* s2);        
 void lzb_lav_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);   /* lav.c:187 */
 void lzb_lav_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);   /* lav.c:327 */
 void lzb_lav_footer(FILE*);                                                            /* m stanza + #:eof */
-void lzb_segments_write(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, uint64_t n);
-                                                                                       /* write_segments segment.c:1930 */
 /* general.c -- --format=general[-][:fields] / mapping[-] / cigar (genpaf.c, cigar.c): rows with named columns */
 typedef struct lzb_fieldlist lzb_fieldlist;
 lzb_fieldlist* lzb_fieldlist_parse(const char* commaSeparatedNames);      /* parse_genpaf_keys genpaf.c:1945 */

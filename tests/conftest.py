@@ -216,6 +216,7 @@ MULTI_TARGET_CASES = [
     ("aglobin.2bit[multi]", "aglobin.2bit/cow", ["--format=general-"]),
     ("shorties.fa[multi]", "shorties.fa", ["--format=general-", "K=2000"]),        # all against all, 20 x 20
     ("names.fa[multi]", "names.fa", ["--format=axt", "K=2000"]),
+    ("aglobin.2bit[multi]", "shorties.fa[multi]", ["--format=segments", "K=2500", "--chain"]),     # genpafSegmentKeys rows, partition names
 ]
 
 # --filter= family (lastz.c:6672-6950; filter_aligns_by_* after the gapped stage, filter_segments_by_* on HSPs): aglobin human x cow

@@ -215,7 +215,7 @@ def test_multi_target_refusals():
     import subprocess
     t = os.path.join(GOLDEN, "aglobin.2bit[multi]")
     for q, opts in [("aglobin.2bit[multi]", []), ("shorties.fa", ["--notrivial"]), ("shorties.fa", ["--format=lav"]),
-                    ("shorties.fa", ["K=top20%"]), ("shorties.fa", ["--nogapped", "--format=segments"])]:
+                    ("shorties.fa", ["K=top20%"])]:
         p = subprocess.run([ORACLE_CLI, t, os.path.join(GOLDEN, q)] + opts, capture_output=True, text=True)
         assert p.returncode != 0 and "FAILURE" in p.stderr, (q, opts)
 
