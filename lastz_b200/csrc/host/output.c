@@ -64,7 +64,26 @@ void lzb_lav_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alig
     fprintf(f, "}\n");
 }
 
-/* (--format=general / mapping / cigar: general.c) */
+/* percent_identical sequences.c:9623-9659 */
+static int pct_identical(const uint8_t* a, const uint8_t* b, uint32_t len) {
+    uint32_t m = 0, d = 0;
+    for (uint32_t i = 0; i < len; i++) {
+        int x = lzb_nuc_to_bits[a[i]], y = lzb_nuc_to_bits[b[i]];
+        if (x >= 0 && y >= 0) { if (x == y) m++; d++; }
+    }
+    return d ? (int)((200ull * m + d) / (2ull * d)) : 0;
+}
+
+void lzb_lav_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment* g) {
+    uint32_t e1 = g->pos1 + g->length, e2 = g->pos2 + g->length;
+    int pct = g->length ? pct_identical(s1->v + g->pos1, s2->v + g->pos2, g->length) : 0;
+    fprintf(f, "a {\n  s %d\n  b %u %u\n  e %u %u\n  l %u %u %u %u %d\n}\n", g->s,
+            g->pos1 + 1, g->pos2 + 1, e1, e2, g->pos1 + 1, g->pos2 + 1, e1, e2, pct);
+}
+
+void lzb_lav_footer(FILE* f) { fprintf(f, "m {\n  n 0\n}\n#:eof\n"); }
+
+/* (--format=general / mapping / cigar / segments / sam / paf / blastn / rdotplot: general.c) */
 
 /* ---- --format=maf- (MAF blocks without the parameter header), print_maf_align maf.c:271-470,
  * unpartitioned sequences ---- */
