@@ -188,6 +188,13 @@ static char* short_header_as(const char* h, int how) {
 static char* name_for(const lzb_seqfile* sf, const char* h) { return sf->nickname ? dupstr(sf->nickname) : short_header_as(h, sf->nameParse); }
 
 static void apply_limits(lzb_seqfile* sf, lzb_seq* out, uint8_t* all, uint32_t total) {
+    if (total == 0 && !sf->start && !sf->end) {          /* an empty record is reported and carried as a sequence of length 0 (sequences.c:2398) */
+        out->len = 0; out->startLoc = 1; out->trueLen = 0;
+        out->v = malloc(1); out->v[0] = 0;
+        if (out->vq) { free(out->vq); out->vq = malloc(1); out->vq[0] = 0; }
+        free(all);
+        return;
+    }
     uint32_t a = sf->start ? sf->start : 1, b = sf->end ? sf->end : total;
     if (a > total) lzb_die("beyond end of sequence in %s (start limit %u, length %u)", sf->filename, a, total);
     if (b > total) lzb_die("beyond end of sequence in %s (end limit %u, length %u)", sf->filename, b, total);
@@ -248,6 +255,7 @@ static int next_fasta(lzb_seqfile* sf, lzb_seq* out) {
         v[n++] = (uint8_t)ch; prev = ch;
     }
     if (n > 0x7FFFFFFFu) lzb_die("sequence length %zu exceeds maximum", n);
+    if (n == 0) { if (hdr[0]) fprintf(stderr, "WARNING. %s contains an empty sequence:\n%s\n", sf->filename, hdr); else fprintf(stderr, "WARNING. %s contains an empty sequence\n", sf->filename); }
     apply_limits(sf, out, v, (uint32_t)n);
     out->header = hdr; out->shortHeader = name_for(sf, hdr);
     return 1;

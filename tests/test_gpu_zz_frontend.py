@@ -76,3 +76,11 @@ def test_cli_fastq_query(query, opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
     args = [os.path.join(GOLDEN, "aglobin.2bit") + "/human", os.path.join(GOLDEN, query)] + opts
     same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])
+
+
+@pytest.mark.parametrize("qact,opts", [("", ["--format=general-"]), ("[multi]", ["--format=maf-"])])
+def test_cli_ragged_query_file(qact, opts):
+    """a query shorter than the seed, an empty record, N only, lower case only, DOS line ends"""
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    args = [os.path.join(GOLDEN, "edge_target.fa"), os.path.join(GOLDEN, "edge_queries.fa") + qact] + opts
+    same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])

@@ -210,6 +210,18 @@ def test_oracle_sequence_names(tact, qact):
     same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
 
 
+@pytest.mark.parametrize("qact,opts", [("", ["--format=general-"]), ("", []), ("[multi]", ["--format=maf-"]), ("[unmask]", ["--format=sam"]),
+                                       ("", ["--format=blastn"])])
+def test_oracle_ragged_query_file(qact, opts):
+    """tests/golden/edge_queries.fa (hand-made): a normal record, one shorter than the seed, an EMPTY record (warned about
+    and skipped, sequences.c:2429), one of N only, one in lower case, one with DOS line ends; stdout and stderr"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    args = [os.path.join(GOLDEN, "edge_target.fa"), os.path.join(GOLDEN, "edge_queries.fa") + qact] + opts
+    got, want = run_cli(ORACLE_CLI, args), run_cli(REF_CLI, args)
+    assert got[0] == want[0] and got[1] == want[1]
+
+
 def test_multi_target_refusals():
     """what a partitioned target does not do yet stops with a FAILURE instead of giving other results than the reference"""
     import subprocess
