@@ -101,6 +101,24 @@ static void parse_options(options* o, int argc, char** argv) {
             else lzb_die("Can't understand \"%s\"", a);
             continue;
         }
+        if (!strcmp(a, "--version")) { printf("lastz_b200 (the seed-and-extend path of lastz 1.04.58 on sm_100a; back end: %s)\n", lzb_backend()); exit(0); }
+        if (!strcmp(a, "--help") || starts(a, "--help=")) {
+            printf("usage: lastz_b200 target[actions] [query[actions]] [options]\n"
+                   "  sequences  FASTA, FASTQ, 2bit (file.2bit/contig), nib; query from stdin when omitted\n"
+                   "  actions    [a..b] [a#len] [unmask] [multi] [subset=<file>] [@<file>] [nmask=|xmask=|softmask=<file>]\n"
+                   "             [nameparse=darkspace|alphanum|full] [fullname] [nickname=<name>]\n"
+                   "  seeding    --seed=<pattern>|12of19|14of22|match<N>  W=<N>  T=0..4  --[no]transition[=2]  --step=<N>  --strand=both|plus|minus  --self\n"
+                   "  extension  --[no]gfextend  --xdrop=  --hspthresh=<score>|top<N>%%|top<bases>  --exact=<N>  --mismatch=<M>,<N>  --[no]entropy\n"
+                   "             --[no]gapped  --ydrop=  --gappedthresh=  --gap=<open>,<extend>  --scores=<file>  --match=<reward>[,<penalty>]\n"
+                   "             --ambiguous=n[,..]  --noytrim  --allgappedbounds  --notrivial  --allocate:traceback=<bytes>  --[no]chain[=<diag>,<anti>]\n"
+                   "             --segments=<file>  --anyornone  --justhits  --yasra98|95|90|85|75|95short|85short\n"
+                   "  filters    --identity=  --coverage=  --continuity=  --matchcount=  --filter=nmismatch:0..<n>|ngap:0..<n>|cgap:0..<n>\n"
+                   "  output     --format=lav|axt|maf[-]|gfa|segments|cigar|general[-][:<fields>]|mapping[-]|sam[-]|softsam[-]|paf[:wfmash]|blastn[-]|rdotplot[+score]\n"
+                   "             --rdotplot[+score]=<file>  --output=<file>\n"
+                   "  additions  --device=<n>  --diaghash=<bits>  --speculation=<n>  --stats\n"
+                   "Option meanings are those of lastz 1.04.58 (INTEGRATION.md section 6 lists what is and is not built).\n");
+            exit(0);
+        }
         if (!silent[i] && strlen(o->args) + strlen(a) + 2 < sizeof o->args) { strcat(o->args, a); strcat(o->args, " "); }
         if (!strcmp(a, "T=0")) { o->withTrans = 0; o->haveTrans = 1; }
         else if (!strcmp(a, "T=1")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 1; }
