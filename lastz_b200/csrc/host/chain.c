@@ -204,6 +204,6 @@ int32_t lzb_reduce_to_chains(const lzb_seq* s1, const lzb_seq* s2, lzb_segment* 
         }
         free(b); *pn = kept;
     }
-    qsort(segs, *pn, sizeof *segs, by_pos1);
+    if (*pn) qsort(segs, *pn, sizeof *segs, by_pos1);
     return best;
 }

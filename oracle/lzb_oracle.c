@@ -970,7 +970,7 @@ int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const uint8_t* h1
     G.tbLen = 1 + (P->tracebackBytes - 8);           /* new_traceback :2272-2290 */
     G.tb = malloc(P->tracebackBytes);
     G.st.anchors = n;
-    qsort(anchors, n, sizeof(lzb_segment), cmp_anchor);   /* batched_segments :1675 */
+    if (n) qsort(anchors, n, sizeof(lzb_segment), cmp_anchor);   /* batched_segments :1675 */
     G.al = calloc(n + 1, sizeof(galn)); G.nal = (int)n + 1;
     for (u64 i = 0; i < n; i++) { G.al[i].pos1 = anchors[i].pos1; G.al[i].pos2 = anchors[i].pos2; G.al[i].hspId = anchors[i].hspId; }
     s32 ts;
