@@ -134,8 +134,9 @@ typedef struct lzb_gapped_params {
     int32_t  scoreThreshold;   /* L, default 3000 */
     int32_t  allBounds;        /* --allgappedbounds */
     int32_t  inhibitTrivial;   /* --notrivial */
-    int32_t  identityCheck;    /* nonzero => run identical_sequences (gapped_extend.c:1886); the caller
-                                  sets it when both sequences carry the same strand flags (:1905) */
+    int32_t  identityCheck;    /* nonzero => run identical_sequences (gapped_extend.c:1886) and, for a partitioned
+                                  target and a plain query, identical_partition_of_sequence (:2034); the caller
+                                  sets it when both sequences carry the same strand flags (:1905, :2058) */
     uint32_t tracebackBytes;   /* --allocate:traceback, default 80 MiB; changes results */
     int32_t  speculation;      /* product only: max anchors extended speculatively in parallel */
 } lzb_gapped_params;
@@ -201,7 +202,10 @@ int lzb_reduce_to_points(lzb_ctx*, lzb_target*, lzb_query*, lzb_segment* anchors
 /* gapped_extend (gapped_extend.h:153; gapped_extend.c:1012).  Reorders anchors in place exactly
  * as the reference does (sort by decreasing score).  Result list is ordered by start in seq1;
  * release with lzb_free_align_list.  seq1/seq2 in each alignel point at the host bytes given
- * here (may be NULL). */
+ * here (may be NULL).
+ * Partitioned ([multi]) sequences: bytes of value 0 INSIDE either sequence separate partitions (sequences.h:188-191);
+ * seeds and x-drop scans never cross them and every DP sweep ends at the separators around its anchor (:1357-1372).
+ */
 int lzb_gapped_extend(lzb_ctx*, lzb_target*, lzb_query*,
                       const uint8_t* hostSeq1, const uint8_t* hostSeq2,
                       lzb_segment* anchors, uint64_t n, const lzb_gapped_params*,
