@@ -263,6 +263,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--diaghash=")) o->hashBits = atoi(v);
         else if (starts(a, "--speculation=")) o->speculation = atoi(v);
         else if (!strcmp(a, "--stats")) o->showStats = 1;
+        else if (!strcmp(a, "--progress") || starts(a, "--progress=") || starts(a, "--progress+") || starts(a, "--verbosity=") || !strcmp(a, "--noruntime")) ;   /* diagnostics on stderr only (lastz.c:7700ff): accepted, nothing to report */
         else lzb_die("lastz_b200 does not implement option \"%s\" (seed-and-extend hot path only)", a);
     }
     if (!o->targetSpec) lzb_die("You must specify a target file");
