@@ -148,9 +148,18 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--strand=minus")) o->whichStrand = -1;
         else if (!strcmp(a, "--self")) { o->selfCompare = 1; o->inhibitTrivial = 1; }
         else if (!strcmp(a, "--notrivial")) o->inhibitTrivial = 1;
-        else if (starts(a, "--exact=")) { o->gfExtend = LZB_GFEX_EXACT; o->K = atoi(v); o->haveK = 1; }      /* lastz.c:6330-6350 */
+        else if (starts(a, "--exact=")) {
+            if (o->haveK && o->gfExtend == LZB_GFEX_XDROP) lzb_die("can't use %s with --hspthreshold", a);          /* lastz.c:6333-6341 */
+            if (o->haveX && o->gfExtend == LZB_GFEX_XDROP) lzb_die("can't use %s with --xdrop", a);
+            if (o->haveK && o->gfExtend == LZB_GFEX_MISMATCH) lzb_die("can't use %s with --%dmismatch", a, o->gfMismatches);
+            o->gfExtend = LZB_GFEX_EXACT; o->K = atoi(v); o->haveK = 1;
+            if (o->K <= 0) lzb_die("%s is not a valid exact match threshold", v);
+        }      /* lastz.c:6330-6350 */
         else if (starts(a, "--mismatch=") || (a[0] == '-' && a[1] == '-' && a[2] >= '0' && a[2] <= '9' && strstr(a, "mismatch="))) {
             int M = 0, N = 0;                                    /* --mismatch=M,N or --<M>mismatch=N, lastz.c:6355-6390 */
+            if (o->haveK && o->gfExtend == LZB_GFEX_XDROP) lzb_die("can't use %s with --hspthreshold", a);
+            if (o->haveX && o->gfExtend == LZB_GFEX_XDROP) lzb_die("can't use %s with --xdrop", a);
+            if (o->haveK && o->gfExtend == LZB_GFEX_EXACT) lzb_die("can't use %s with --exact", a);
             if (starts(a, "--mismatch=")) { if (sscanf(v, "%d,%d", &M, &N) != 2) lzb_die("--mismatch requires two values (count and length)"); }
             else { M = atoi(a + 2); N = atoi(v); }
             if (M == 0) o->gfExtend = LZB_GFEX_EXACT;
@@ -210,10 +219,18 @@ static void parse_options(options* o, int argc, char** argv) {
             }
             o->haveK = 1;
         }
-        else if (starts(a, "--hspthresh=") || starts(a, "K=")) { o->K = atoi(v); o->haveK = 1; o->adaptive = 0; }
+        else if (starts(a, "--hspthresh=") || starts(a, "K=")) {
+            if (o->haveK && o->gfExtend == LZB_GFEX_EXACT) lzb_die("can't use %s with --exact", a);               /* lastz.c:6312-6318 */
+            if (o->haveK && o->gfExtend == LZB_GFEX_MISMATCH) lzb_die("can't use %s with --%dmismatch", a, o->gfMismatches);
+            o->K = atoi(v); o->haveK = 1; o->adaptive = 0;
+        }
         else if (starts(a, "--gappedthresh=top") || starts(a, "L=top")) lzb_die("lastz_b200 does not implement an adaptive gapped threshold (%s)", a);
         else if (starts(a, "--gappedthresh=") || starts(a, "L=")) { o->L = atoi(v); o->haveL = 1; }
-        else if (starts(a, "--xdrop=") || starts(a, "X=")) { o->X = atoi(v); o->haveX = 1; }
+        else if (starts(a, "--xdrop=") || starts(a, "X=")) {
+            if (o->haveK && o->gfExtend == LZB_GFEX_EXACT) lzb_die("can't use %s with --exact", a);               /* lastz.c:6271-6277 */
+            if (o->haveK && o->gfExtend == LZB_GFEX_MISMATCH) lzb_die("can't use %s with --%dmismatch", a, o->gfMismatches);
+            o->X = atoi(v); o->haveX = 1; o->gfExtend = LZB_GFEX_XDROP;
+        }   /* an x-drop value selects x-drop extension, whatever came before (lastz.c:6278) */
         else if (starts(a, "--ydrop=") || starts(a, "Y=")) { o->Y = atoi(v); o->haveY = 1; }
         else if (starts(a, "O=")) { o->O = atoi(v); o->haveO = 1; }
         else if (starts(a, "E=")) { o->E = atoi(v); o->haveE = 1; }

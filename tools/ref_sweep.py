@@ -33,8 +33,12 @@ def main():
             opts += o
         opts.append(random.choice(FORMATS))
         argv = [os.path.join(G, t), os.path.join(G, q)] + opts
-        r = subprocess.run([REF] + argv, capture_output=True, text=True)
-        o = subprocess.run([OURS] + argv, capture_output=True, text=True)
+        try:                                             # low-weight seeds without extension make millions of anchors: skip what takes minutes
+            r = subprocess.run([REF] + argv, capture_output=True, text=True, timeout=60)
+            o = subprocess.run([OURS] + argv, capture_output=True, text=True, timeout=180)
+        except subprocess.TimeoutExpired:
+            print("TIMEOUT", " ".join(argv[2:]))
+            continue
         if r.returncode != 0 and o.returncode != 0:
             continue
         if r.returncode != 0 or o.returncode != 0:
