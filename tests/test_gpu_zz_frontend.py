@@ -1,7 +1,9 @@
-"""Front-end features added after the last full GPU run of round 1, through the product command line on the GPU:
-GFA output and --anyornone (single-anchor gapped_extend calls per HSP).  The file sorts last on purpose: pytest
--x stops at the first failure, and these are the cases that had CPU verification only (same host C code through
-the oracle library, tests/test_oracle_golden.py) when they were written."""
+"""Front-end features through the product command line on the GPU.  The first two groups (GFA output, --anyornone) ran
+on a B200 in round 1; everything after them was written when the round's GPU minutes were spent:
+adaptive thresholds, the transition-variant order fixture, [multi] queries and targets, field-list / SAM / PAF / blastn /
+rdotplot writers, filters, FASTQ input, ragged query files.  Those are the same host C sources the CPU suite compares
+with the reference binary through the oracle library; here they run over the CUDA library.  The file sorts last on
+purpose: pytest -x stops at the first failure, and these are the cases without a GPU run behind them yet."""
 import os
 
 import pytest
