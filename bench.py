@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=50_000_000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--speculation", type=int, default=32)
+    ap.add_argument("--speculation", type=int, default=256)
     ap.add_argument("--cpu-sample", type=int, default=125_000, help="query bp per reference process (x1 and x2)")
     ap.add_argument("--cpu-procs", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -197,7 +197,7 @@ class Engine:
     # ---- gapped_extend.h:153
     def gapped_extend(self, t, q, seq1: bytes, seq2: bytes, anchors, *, y_drop=9400, trim_to_peak=True,
                       score_threshold=3000, all_bounds=False, inhibit_trivial=False, identity_check=False,
-                      traceback_bytes=80 * 1024 * 1024, speculation=16):
+                      traceback_bytes=80 * 1024 * 1024, speculation=64):
         a = np.ascontiguousarray(anchors)
         p = capi.GappedParams(y_drop, int(trim_to_peak), score_threshold, int(all_bounds), int(inhibit_trivial),
                               int(identity_check), traceback_bytes, speculation)

@@ -52,6 +52,7 @@ extern "C" void lzb_close(lzb_ctx* c) {
     cudaSetDevice(c->device);
     lzb_gapped_cache_free(c);
     lzb_seed_scratch_free(c);
+    cudaFree(c->peaksBuf);
     for (int i = 0; i < 4; i++) { cudaFree(c->qpool[i].seq); cudaFree(c->qpool[i].cls); }
     cudaStreamDestroy(c->stream);
     cudaFree(c->d_sc);

@@ -17,23 +17,44 @@ struct dalign {                       /* device view of a committed alignment (g
     u32 pos1, end1;
     int segBegin, segCount;
     segref left1, right1, left2, right2;
-    int next, prev;                   /* obi / oed links */
 };
 
-enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_ACT = 5 };
+enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_ACT = 5, DP_ABORTED = 6 };
+
+/* jobs of one launch: block b runs jobs[ll.ix[b]] (the list travels in the kernel's parameter space, so a launch
+ * needs no device-side table that would have to outlive it) */
+#define LZB_LAUNCH_MAX 960
+struct launch_list { u16 ix[LZB_LAUNCH_MAX]; };
+
+/* checkpoint record of a sweep, written every ckptEvery rows (a multiple of 32): CK_HDR scalar words, the active
+ * segments (5 ints each, at most CK_ACT; a row with more takes no checkpoint), then 2K+1 words per thread
+ * (C[K], D[K], first column) stored word-major so that the block's stores coalesce.  A sweep restarted from
+ * record k continues at row (k+1)*ckptEvery + 1 exactly as if it had never stopped, against a LARGER set of
+ * earlier alignments whose first rows all lie beyond that row (see gapped_sched.hpp). */
+#define CK_HDR 32
+#define CK_ACT 8
+#define CK_WORDS(K_, NT_) (CK_HDR + 5 * CK_ACT + (2 * (K_) + 1) * (NT_))
 
 struct dp_job {
     int reversed; u32 a1, a2, M, N;
     s32 L0, R0;
     segref leftSeg, rightSeg;
-    int alignList;
+    const int* listv;                 /* alignments this sweep may run into, device table indices in sweep order
+                                         (aboveList / belowList, gapped_extend.c:4043-4060), -1 terminated; NULL = none */
+    int alignList;                    /* first pending entry of listv */
     u8* tb; u32 tbLen; u32* tbRow; u32 tbRowCap; u32* ops; u32 opsCap;
     int* act; u32 actCap;             /* 5 ints per active segment */
-    const dalign* al;                 /* alignment table snapshot this job runs against */
-    int skip;                         /* nonzero: nothing to do (the other side of a rerun) */
+    const dalign* al;                 /* alignment table (append-only: a sweep only follows indices it was given) */
+    u32* ckpt; u32 ckptCap, ckptEvery;/* checkpoint records (k_ydrop_mw only); ckptCap = 0: none taken */
+    int resume;                       /* -1 fresh sweep, else the checkpoint record to continue from */
+    int tbOnly;                       /* nonzero: the sweep is done (end1/end2/status below are its results); redo the traceback walk */
     u32* dbg; u32 dbgCap;             /* LZB_DP_DEBUG: per-row {LY, colEnd, best, used} for kernel-vs-kernel diffs */
+    u32 token;                        /* written to `done` after everything else */
+    volatile int abort;               /* set by the host while the sweep runs: its result is no longer wanted */
     /* results */
-    s32 score; u32 end1, end2, nops, rows; int status; unsigned long long cells;
+    s32 score; u32 end1, end2, nops, rows; int status; int opsOverflow; unsigned long long cells;
+    u32 ckptCount;                    /* records 0 .. ckptCount-1 are valid */
+    volatile u32 done;
 };
 
 struct xf { s32 A; s32 S; int r; };   /* x -> r ? A : max(A, x + S) */
@@ -95,6 +116,60 @@ __device__ void act_build(int* a, const dalign* al, const dseg* segs, int rev, u
         u32 lo = x > LY ? x : LY, hi = hend < RY ? hend : RY;
         for (u32 i = lo; i <= hi && i >= lo; i++) stamp[i & msk] = row;
     }
+}
+
+
+/* row (counted from the anchor) at which entry li of a sweep's list starts: aboveList entries are taken when
+ * pos1 - anchor1 == row, belowList entries when anchor1 - end1 == row (gapped_extend.c:4927-4945) */
+__device__ __forceinline__ u32 list_row(const int* listv, int li, const dalign* al, int rev, u32 a1) {
+    const int ix = listv ? listv[li] : -1;
+    if (ix < 0) return 0xFFFFFFFFu;
+    return !rev ? al[ix].pos1 - a1 : a1 - al[ix].end1;
+}
+
+/* update_active_segs gapped_extend.c:4885-4962, by ONE thread: advance the active segments to `row`, take the
+ * alignments that start at this row off the list, drop the finished ones.  *li indexes listv; *nextRow = row at
+ * which the next list entry starts (0xFFFFFFFF: none), so callers only come here when something is active. */
+__device__ void active_update(int* act, int* pnact, u32 actCap, const int* listv, int* li, u32* nextRow, int* status,
+                              const dalign* al, const dseg* segs, int rev, u32* stamp, u32 msk,
+                              u32 row, u32 a1, u32 a2, u32 LY, u32 RY) {
+    int nact = *pnact;
+    for (int k = 0; k < nact; k++) {
+        int* a = act + 5 * k;
+        if ((u32)a[3] >= row) {
+            if (a[4] == SEG_DIAG) a[2]++;
+            u32 x = (u32)a[2];
+            if (x >= LY && x <= RY) stamp[x & msk] = row;
+        } else {
+            int cnt = al[a[0]].segCount;
+            bool more = !rev ? (a[1] + 1 < cnt) : (a[1] - 1 >= 0);
+            if (more) {
+                a[1] += !rev ? 1 : -1;
+                act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
+                if (a[4] == SEG_HORZ) { a[1] += !rev ? 1 : -1; act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY); }
+            } else a[4] = -1;
+        }
+    }
+    while (*nextRow == row) {
+        if ((u32)nact >= actCap) { *status = DP_ACT; break; }
+        const int ix = listv[*li];
+        int* a = act + 5 * nact; nact++;
+        a[0] = ix; a[1] = !rev ? 0 : al[ix].segCount - 1;
+        act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
+        (*li)++;
+        *nextRow = list_row(listv, *li, al, rev, a1);
+    }
+    int w = 0;
+    for (int k = 0; k < nact; k++) if (act[5 * k + 4] >= 0) { if (w != k) for (int z = 0; z < 5; z++) act[5 * w + z] = act[5 * k + z]; w++; }
+    *pnact = w;
+}
+
+/* publish a job's results: everything first, then the token the host polls for */
+__device__ __forceinline__ void job_done(dp_job* J) {
+#ifndef CUDA_EMU_H
+    __threadfence_system();
+#endif
+    J->done = J->token;
 }
 
 /* traceback, gapped_extend.c:3847-3859, by one warp: lane t speculates that the path continues

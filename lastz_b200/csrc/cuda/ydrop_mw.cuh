@@ -26,7 +26,7 @@ template <int NW> struct mw_shared {
     s32 xB[NW];                        /* exchange 2: each warp's best candidate */
     s32 edgeC[NW];                     /* C of each warp's last column after the row */
     u32 xfa[NW], xla[NW], xuc[NW], xbc[NW]; s32 xuv[NW], xbv[NW];   /* exchange 3 */
-    int nact, alignList, status;
+    int nact, alignList, status; u32 nextActRow;
 };
 
 struct mw_in {
@@ -228,7 +228,7 @@ __device__ __forceinline__ void mw_sweep(s32 (&C)[K], s32 (&D)[K], const u32 (&B
 
 template <int K, int NW>
 __global__ void __launch_bounds__(32 * NW)
-k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
+k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
            const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
            const lzb_scoring_dev* __restrict__ sc, s32 yDrop, int trim) {
     constexpr u32 NT = 32u * NW, WIN = NT * K, WSPAN = 32u * K, smsk = MW_SCAP - 1;
@@ -236,9 +236,9 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
     static_assert(WIN <= MW_SCAP && K <= 32 && (NW & (NW - 1)) == 0, "window must fit the stamp ring");
     __shared__ mw_shared<NW> sh;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, FULL = 0xFFFFFFFFu;
-    dp_job* J = &jobs[blockIdx.x];
-    if (J->skip) return;
+    dp_job* J = &jobs[ll.ix[blockIdx.x]];
     const dalign* __restrict__ al = J->al;
+    constexpr u32 CKW = CK_WORDS(K, NT);
     for (u32 i = tid; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += NT) sh.subC[i] = sc->subC[i];
     for (u32 i = tid; i < MW_SCAP; i += NT) sh.stamp[i] = 0;
     const int rev = J->reversed; const u32 a1 = J->a1, a2 = J->a2, M = J->M, N = J->N;
@@ -249,14 +249,19 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
     s32 best = 0, bnd = LZB_NEG_INF; u32 end1 = 0, end2 = 0; int endIsBnd = 0;
     unsigned long long cells = 0; u32 row = 0;
     if (N == 0 || M == 0) {
-        if (tid == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; }
+        if (tid == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; J->opsOverflow = 0; J->ckptCount = 0; job_done(J); }
         return;
     }
     const s32 yTail = gapE != 0 ? yDrop / gapE + 6 : (N < 500000u ? (s32)N + 1 : 500000);
     s32 L = J->L0, R = J->R0;
     segref leftSeg = J->leftSeg, rightSeg = J->rightSeg;
-    int alignList = J->alignList;
+    const int* const listv = J->listv;
+    int alignList = J->alignList;                          /* index into listv */
+    u32 nextActRow = list_row(listv, alignList, al, rev, a1);
     int* act = J->act; int nact = 0;
+    u32* const ckpt = J->ckpt; const u32 ckptCap = J->ckptCap, ckptEvery = J->ckptEvery;
+    u32 ckptCount = 0;
+    const int resume = J->resume, tbOnly = J->tbOnly;
     const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
     u32* const dbg = J->dbg; const u32 dbgCap = J->dbgCap;
     u32 lLim = 0, rLim = 0; int lTyp = 0, rTyp = 0;
@@ -274,10 +279,30 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
             Bq[s_ >> 2] |= code_ << (8 * (s_ & 3));                                                       \
         }                                                                                                 \
     } while (0)
-    MW_LOAD_BLOCK();
-    /* ---- first row, gapped_extend.c:3576-3591 ---- */
-    u32 LY = 0, RY;
-    {
+    /* ---- first row, gapped_extend.c:3576-3591 -- or the state a checkpoint saved ---- */
+    u32 LY = 0, RY = 0, row0 = 1;
+    u32 pWcol = 0, pCnt = 0; s32 pIout = LZB_NEG_INF;       /* the previous row's prolongation (:3801-3816), needed to read a left neighbour's last column */
+    if (tbOnly) {
+        status = J->status; end1 = J->end1; end2 = J->end2; row = J->rows; ckptCount = J->ckptCount;
+#pragma unroll
+        for (int s = 0; s < K; s++) { C[s] = LZB_NEG_INF; D[s] = LZB_NEG_INF; }
+    } else if (resume >= 0) {
+        const u32* rec = ckpt + (size_t)resume * CKW;
+        row0 = rec[0] + 1; LY = rec[1]; RY = rec[2]; L = (s32)rec[3]; R = (s32)rec[4];
+        leftSeg.al = (int)rec[5]; leftSeg.sg = (int)rec[6]; rightSeg.al = (int)rec[7]; rightSeg.sg = (int)rec[8];
+        lLim = rec[9]; rLim = rec[10]; lTyp = (int)rec[11]; rTyp = (int)rec[12]; nact = (int)rec[13];
+        used = (s64)((u64)rec[14] | ((u64)rec[15] << 32));
+        best = (s32)rec[16]; bnd = (s32)rec[17]; end1 = rec[18]; end2 = rec[19]; endIsBnd = (int)rec[20];
+        cells = (u64)rec[21] | ((u64)rec[22] << 32);
+        pWcol = rec[23]; pCnt = rec[24]; pIout = (s32)rec[25];
+        if (tid == 0) for (int k = 0; k < 5 * nact; k++) act[k] = (int)rec[CK_HDR + k];
+        const u32* tv = rec + CK_HDR + 5 * CK_ACT;
+#pragma unroll
+        for (int s = 0; s < K; s++) { C[s] = (s32)tv[(u32)s * NT + tid]; D[s] = (s32)tv[(u32)(K + s) * NT + tid]; }
+        cb = tv[(u32)(2 * K) * NT + tid];
+        ckptCount = (u32)resume + 1;
+        row = row0;
+    } else {
         u32 last = 1;
         if (gapE > 0) { if (yDrop >= gapOE) last = (u32)(((s64)yDrop - gapOE) / gapE) + 2; }
         else if (yDrop >= gapOE) last = N;
@@ -296,17 +321,19 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
         RY = last + 1;
         if (tid == 0 && tbRowCap > 0) tbRow[0] = 0;
     }
+    MW_LOAD_BLOCK();
     /* target-side class codes, 32 rows per load, one chunk ahead (every warp keeps its own copy) */
 #define MW_ACODE(r_) ([&]() -> u32 { const u32 rr_ = (r_); if (rr_ > M) return (u32)cls0;                 \
                                       const s64 ai_ = !rev ? (s64)a1 + rr_ : (s64)a1 + 1 - (s64)rr_;      \
                                       return (ai_ < 0 || ai_ >= (s64)len1) ? (u32)cls0 : (u32)cls1[ai_]; }())
-    u32 acv = MW_ACODE(1 + lane), acvNext = MW_ACODE(33 + lane);
-    /* the previous row's prolongation (:3801-3816), needed to read a left neighbour's last column */
-    u32 pWcol = 0, pCnt = 0; s32 pIout = LZB_NEG_INF;
+    /* rows row0 .. row0+31 in acv when row0 - 1 is not a multiple of 32 (never after a checkpoint), else the 32 rows
+     * before row0 in acv and the loop's first iteration shifts; a fresh sweep has row0 = 1 and shifts at row 33 */
+    u32 acv = MW_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? -31 : 1) + lane), acvNext = MW_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? 1 : 33) + lane);
     if (lane == 31) sh.edgeC[warp] = C[K - 1];
     __syncthreads();
-    if (status == DP_OK)
-    for (row = 1; row <= M; row++) {
+    if (status == DP_OK && !tbOnly)
+    for (row = row0; row <= M; row++) {
+        if ((row & 255u) == 0 && J->abort) { status = DP_ABORTED; break; }   /* the anchor was retired (mapped host memory: looked at rarely) */
         /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every thread, same values) ---- */
         if (!rev) {
             if (leftSeg.al >= 0) {
@@ -332,40 +359,13 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
             if (leftSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
         }
         /* ---- update_active_segs gapped_extend.c:4885-4962 (thread 0; the list is tiny) ---- */
-        if (nact > 0 || alignList >= 0) {
+        if (nact > 0 || row == nextActRow) {
             if (tid == 0) {
-                for (int k = 0; k < nact; k++) {
-                    int* a = act + 5 * k;
-                    if ((u32)a[3] >= row) {
-                        if (a[4] == SEG_DIAG) a[2]++;
-                        u32 x = (u32)a[2];
-                        if (x >= LY && x <= RY) sh.stamp[x & smsk] = row;
-                    } else {
-                        int cnt = al[a[0]].segCount;
-                        bool more = !rev ? (a[1] + 1 < cnt) : (a[1] - 1 >= 0);
-                        if (more) {
-                            a[1] += !rev ? 1 : -1;
-                            act_build(a, al, segs, rev, sh.stamp, smsk, row, a1, a2, LY, RY);
-                            if (a[4] == SEG_HORZ) { a[1] += !rev ? 1 : -1; act_build(a, al, segs, rev, sh.stamp, smsk, row, a1, a2, LY, RY); }
-                        } else a[4] = -1;
-                    }
-                }
-                while (alignList >= 0) {
-                    const dalign x = al[alignList];
-                    if (!rev) { if (x.pos1 - a1 != row) break; } else { if (a1 - x.end1 != row) break; }
-                    if ((u32)nact >= actCap) { status = DP_ACT; break; }
-                    int* a = act + 5 * nact; nact++;
-                    a[0] = alignList; a[1] = !rev ? 0 : x.segCount - 1;
-                    act_build(a, al, segs, rev, sh.stamp, smsk, row, a1, a2, LY, RY);
-                    alignList = !rev ? x.next : x.prev;
-                }
-                int w = 0;
-                for (int k = 0; k < nact; k++) if (act[5 * k + 4] >= 0) { if (w != k) for (int z = 0; z < 5; z++) act[5 * w + z] = act[5 * k + z]; w++; }
-                nact = w;
-                sh.nact = nact; sh.alignList = alignList; sh.status = status;
+                active_update(act, &nact, actCap, listv, &alignList, &nextActRow, &status, al, segs, rev, sh.stamp, smsk, row, a1, a2, LY, RY);
+                sh.nact = nact; sh.alignList = alignList; sh.nextActRow = nextActRow; sh.status = status;
             }
             __syncthreads();
-            nact = sh.nact; alignList = sh.alignList; status = sh.status;
+            nact = sh.nact; alignList = sh.alignList; nextActRow = sh.nextActRow; status = sh.status;
             if (status != DP_OK) break;
         }
         /* ---- traceback capacity gapped_extend.c:3636-3662 ---- */
@@ -439,6 +439,25 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
             RY += p; used += p;
         }
         if ((s32)RY <= NN) RY++;                             /* the sentinel column already holds LZB_NEG_INF */
+        /* ---- checkpoint: everything the next row reads ---- */
+        if (ckptCap && row % ckptEvery == 0 && row / ckptEvery - 1 == ckptCount && ckptCount < ckptCap && nact <= CK_ACT) {
+            u32* rec = ckpt + (size_t)ckptCount * CKW;
+            if (tid == 0) {
+                rec[0] = row; rec[1] = LY; rec[2] = RY; rec[3] = (u32)L; rec[4] = (u32)R;
+                rec[5] = (u32)leftSeg.al; rec[6] = (u32)leftSeg.sg; rec[7] = (u32)rightSeg.al; rec[8] = (u32)rightSeg.sg;
+                rec[9] = lLim; rec[10] = rLim; rec[11] = (u32)lTyp; rec[12] = (u32)rTyp; rec[13] = (u32)nact;
+                rec[14] = (u32)(u64)used; rec[15] = (u32)((u64)used >> 32);
+                rec[16] = (u32)best; rec[17] = (u32)bnd; rec[18] = end1; rec[19] = end2; rec[20] = (u32)endIsBnd;
+                rec[21] = (u32)cells; rec[22] = (u32)(cells >> 32);
+                rec[23] = pWcol; rec[24] = pCnt; rec[25] = (u32)pIout;
+                for (int k = 0; k < 5 * nact; k++) rec[CK_HDR + k] = (u32)act[k];
+            }
+            u32* tv = rec + CK_HDR + 5 * CK_ACT;
+#pragma unroll
+            for (int s = 0; s < K; s++) { tv[(u32)s * NT + tid] = (u32)C[s]; tv[(u32)(K + s) * NT + tid] = (u32)D[s]; }
+            tv[(u32)(2 * K) * NT + tid] = cb;
+            ckptCount++;
+        }
     }
 #undef MW_LOAD_BLOCK
 #undef MW_ACODE
@@ -446,14 +465,15 @@ k_ydrop_mw(dp_job* jobs, const dseg* __restrict__ segs,
     __threadfence();
     __syncthreads();
     if (warp != 0) return;
-    u32 nops = 0;
-    if (status == DP_OK || status == DP_TRUNCATED) {
-        bool ovf = false;
+    u32 nops = 0; bool ovf = false;
+    if (status == DP_OK || status == DP_TRUNCATED)
         nops = traceback_walk(tb, tbRow, end1, end2, J->ops, J->opsCap, lane, &ovf);
-        if (ovf) status = DP_OPS;
-    }
     if (lane == 0) {
-        J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2; J->nops = nops;
-        J->rows = row; J->cells = cells; J->status = status;
+        if (!tbOnly) {
+            J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2;
+            J->rows = row; J->cells = cells; J->status = status; J->ckptCount = ckptCount;
+        }
+        J->nops = nops; J->opsOverflow = ovf ? 1 : 0;
+        job_done(J);
     }
 }

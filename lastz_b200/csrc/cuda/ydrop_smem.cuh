@@ -19,12 +19,12 @@ struct dp_shared {                    /* small block-wide exchange area */
     s32 wmaxI[DP_MAX_WARPS], wmax[DP_MAX_WARPS];
     u32 wfa[DP_MAX_WARPS], wla[DP_MAX_WARPS], wuc[DP_MAX_WARPS], wbc[DP_MAX_WARPS];
     s32 wuv[DP_MAX_WARPS], wbv[DP_MAX_WARPS];
-    int nact, alignList, status;
+    int nact, alignList, status; u32 nextActRow;
 };
 
 template <int DP_THREADS>
 __global__ void __launch_bounds__(DP_THREADS)
-k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
+k_ydrop(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
         const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
         const lzb_scoring_dev* __restrict__ sc, s32 yDrop, int trim, u32 cap) {
     LZB_DYNAMIC_SHARED(smem_raw);
@@ -36,8 +36,7 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     const u32 msk = cap - 1;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 FULL = 0xFFFFFFFFu;
-    dp_job* J = &jobs[blockIdx.x];
-    if (J->skip) return;
+    dp_job* J = &jobs[ll.ix[blockIdx.x]];
     const dalign* __restrict__ al = J->al;
     for (u32 i = tid; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += DP_THREADS) subC[i] = sc->subC[i];
     for (u32 i = tid; i < cap; i += DP_THREADS) stamp[i] = 0;
@@ -49,13 +48,17 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     s32 best = 0, bnd = LZB_NEG_INF; u32 end1 = 0, end2 = 0; int endIsBnd = 0;
     unsigned long long cells = 0; u32 row = 0;
     if (N == 0 || M == 0) {
-        if (tid == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; }
+        if (tid == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; J->opsOverflow = 0; J->ckptCount = 0; job_done(J); }
         return;
     }
     s32 yTail = gapE != 0 ? yDrop / gapE + 6 : (N < 500000u ? (s32)N + 1 : 500000);
     s32 L = J->L0, R = J->R0;
     segref leftSeg = J->leftSeg, rightSeg = J->rightSeg;
-    int alignList = J->alignList;
+    const int* const listv = J->listv;
+    int alignList = J->alignList;                          /* index into listv */
+    u32 nextActRow = list_row(listv, alignList, al, rev, a1);
+    const int tbOnly = J->tbOnly;
+    if (tbOnly) { status = J->status; end1 = J->end1; end2 = J->end2; }
     int* act = J->act; int nact = 0;
     const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
     u32* const dbg = J->dbg; const u32 dbgCap = J->dbgCap;
@@ -86,9 +89,10 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     }
     __syncthreads();
     s32* Cprev = C0; s32* Ccur = C1;
-    if (status == DP_OK)
+    if (status == DP_OK && !tbOnly)
     for (row = 1; row <= M; row++) {
         u32 prevLY = LY;
+        if ((row & 255u) == 0 && J->abort) { status = DP_ABORTED; break; }   /* the anchor was retired (mapped host memory: looked at rarely) */
         /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every thread, same values).  The bounding
          * segment's far edge and type sit in registers; HBM is touched only when the walk moves on ---- */
         if (!rev) {
@@ -116,40 +120,13 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
         }
         if ((s64)(RY > prevLY ? RY - prevLY : 0) + yTail + 40 >= (s64)cap) { status = DP_RING; break; }
         /* ---- update_active_segs gapped_extend.c:4885-4962 (thread 0; the list is tiny) ---- */
-        if (nact > 0 || alignList >= 0) {
+        if (nact > 0 || row == nextActRow) {
             if (tid == 0) {
-                for (int k = 0; k < nact; k++) {
-                    int* a = act + 5 * k;
-                    if ((u32)a[3] >= row) {
-                        if (a[4] == SEG_DIAG) a[2]++;
-                        u32 x = (u32)a[2];
-                        if (x >= LY && x <= RY) stamp[x & msk] = row;
-                    } else {
-                        int cnt = al[a[0]].segCount;
-                        bool more = !rev ? (a[1] + 1 < cnt) : (a[1] - 1 >= 0);
-                        if (more) {
-                            a[1] += !rev ? 1 : -1;
-                            act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
-                            if (a[4] == SEG_HORZ) { a[1] += !rev ? 1 : -1; act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY); }
-                        } else a[4] = -1;
-                    }
-                }
-                while (alignList >= 0) {
-                    const dalign x = al[alignList];
-                    if (!rev) { if (x.pos1 - a1 != row) break; } else { if (a1 - x.end1 != row) break; }
-                    if ((u32)nact >= actCap) { status = DP_ACT; break; }
-                    int* a = act + 5 * nact; nact++;
-                    a[0] = alignList; a[1] = !rev ? 0 : x.segCount - 1;
-                    act_build(a, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
-                    alignList = !rev ? x.next : x.prev;
-                }
-                int w = 0;
-                for (int k = 0; k < nact; k++) if (act[5 * k + 4] >= 0) { if (w != k) for (int z = 0; z < 5; z++) act[5 * w + z] = act[5 * k + z]; w++; }
-                nact = w;
-                sh->nact = nact; sh->alignList = alignList; sh->status = status;
+                active_update(act, &nact, actCap, listv, &alignList, &nextActRow, &status, al, segs, rev, stamp, msk, row, a1, a2, LY, RY);
+                sh->nact = nact; sh->alignList = alignList; sh->nextActRow = nextActRow; sh->status = status;
             }
             __syncthreads();
-            nact = sh->nact; alignList = sh->alignList; status = sh->status;
+            nact = sh->nact; alignList = sh->alignList; nextActRow = sh->nextActRow; status = sh->status;
             if (status != DP_OK) break;
         }
         /* ---- traceback capacity gapped_extend.c:3636-3662 ---- */
@@ -380,16 +357,17 @@ k_ydrop(dp_job* jobs, const dseg* __restrict__ segs,
     __threadfence();
     __syncthreads();
     if (warp != 0) return;
-    u32 nops = 0;
-    if (status == DP_OK || status == DP_TRUNCATED) {
-        bool ovf = false;
+    u32 nops = 0; bool ovf = false;
+    if (status == DP_OK || status == DP_TRUNCATED)
         nops = traceback_walk(tb, tbRow, end1, end2, J->ops, J->opsCap, lane, &ovf);
-        if (ovf) status = DP_OPS;
-    }
     if (lane == 0) {
-        J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2; J->nops = nops;
-        J->rows = row; J->cells = cells; J->status = status;
-    }
+        if (!tbOnly) {
+            J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2;
+            J->rows = row; J->cells = cells; J->status = status; J->ckptCount = 0;
+        }
+        J->nops = nops; J->opsOverflow = ovf ? 1 : 0;
+        job_done(J);
+}
 }
 
 #endif

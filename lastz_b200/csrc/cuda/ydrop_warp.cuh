@@ -184,7 +184,7 @@ __device__ __forceinline__ void wg_sweep(wg_state<K>& S, const wg_in& in, wg_out
 
 template <int K>
 __global__ void __launch_bounds__(32)
-k_ydrop_warp(dp_job* jobs, const dseg* __restrict__ segs,
+k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
              const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
              const lzb_scoring_dev* __restrict__ sc, s32 yDrop, int trim) {
     static_assert(K % 4 == 0 && K <= 32 && 32u * K <= WG_SCAP, "window must fit the stamp ring");
@@ -192,8 +192,7 @@ k_ydrop_warp(dp_job* jobs, const dseg* __restrict__ segs,
     __shared__ s32 subC[LZB_MAX_CLASSES * LZB_MAX_CLASSES];
     __shared__ u32 stamp[WG_SCAP];
     const u32 lane = threadIdx.x, FULL = 0xFFFFFFFFu;
-    dp_job* J = &jobs[blockIdx.x];
-    if (J->skip) return;
+    dp_job* J = &jobs[ll.ix[blockIdx.x]];
     const dalign* __restrict__ al = J->al;
     for (u32 i = lane; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += 32) subC[i] = sc->subC[i];
     for (u32 i = lane; i < WG_SCAP; i += 32) stamp[i] = 0;
@@ -205,13 +204,17 @@ k_ydrop_warp(dp_job* jobs, const dseg* __restrict__ segs,
     s32 best = 0, bnd = LZB_NEG_INF; u32 end1 = 0, end2 = 0; int endIsBnd = 0;
     unsigned long long cells = 0; u32 row = 0;
     if (N == 0 || M == 0) {
-        if (lane == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; }
+        if (lane == 0) { J->score = 0; J->end1 = J->end2 = 0; J->nops = 0; J->rows = 0; J->cells = 0; J->status = DP_OK; J->opsOverflow = 0; J->ckptCount = 0; job_done(J); }
         return;
     }
     const s32 yTail = gapE != 0 ? yDrop / gapE + 6 : (N < 500000u ? (s32)N + 1 : 500000);
     s32 L = J->L0, R = J->R0;
     segref leftSeg = J->leftSeg, rightSeg = J->rightSeg;
-    int alignList = J->alignList;
+    const int* const listv = J->listv;
+    int alignList = J->alignList;                          /* index into listv */
+    u32 nextActRow = list_row(listv, alignList, al, rev, a1);
+    const int tbOnly = J->tbOnly;
+    if (tbOnly) { status = J->status; end1 = J->end1; end2 = J->end2; }
     int* act = J->act; int nact = 0;
     const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
     u32* const dbg = J->dbg; const u32 dbgCap = J->dbgCap;
@@ -258,8 +261,9 @@ k_ydrop_warp(dp_job* jobs, const dseg* __restrict__ segs,
                                       return (ai_ < 0 || ai_ >= (s64)len1) ? (u32)cls0 : (u32)cls1[ai_]; }())
     u32 acv = WG_ACODE(1 + lane), acvNext = WG_ACODE(33 + lane);
     __syncwarp();
-    if (status == DP_OK)
+    if (status == DP_OK && !tbOnly)
     for (row = 1; row <= M; row++) {
+        if ((row & 255u) == 0 && J->abort) { status = DP_ABORTED; break; }   /* the anchor was retired (mapped host memory: looked at rarely) */
         /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every lane, same values) ---- */
         if (!rev) {
             if (leftSeg.al >= 0) {
@@ -285,39 +289,11 @@ k_ydrop_warp(dp_job* jobs, const dseg* __restrict__ segs,
             if (leftSeg.al >= 0) { if (R <= 0) RY = 0; else if ((u32)R < RY) RY = (u32)R; }
         }
         /* ---- update_active_segs gapped_extend.c:4885-4962 (lane 0; the list is tiny) ---- */
-        if (nact > 0 || alignList >= 0) {
-            if (lane == 0) {
-                for (int k = 0; k < nact; k++) {
-                    int* a = act + 5 * k;
-                    if ((u32)a[3] >= row) {
-                        if (a[4] == SEG_DIAG) a[2]++;
-                        u32 x = (u32)a[2];
-                        if (x >= LY && x <= RY) stamp[x & smsk] = row;
-                    } else {
-                        int cnt = al[a[0]].segCount;
-                        bool more = !rev ? (a[1] + 1 < cnt) : (a[1] - 1 >= 0);
-                        if (more) {
-                            a[1] += !rev ? 1 : -1;
-                            act_build(a, al, segs, rev, stamp, smsk, row, a1, a2, LY, RY);
-                            if (a[4] == SEG_HORZ) { a[1] += !rev ? 1 : -1; act_build(a, al, segs, rev, stamp, smsk, row, a1, a2, LY, RY); }
-                        } else a[4] = -1;
-                    }
-                }
-                while (alignList >= 0) {
-                    const dalign x = al[alignList];
-                    if (!rev) { if (x.pos1 - a1 != row) break; } else { if (a1 - x.end1 != row) break; }
-                    if ((u32)nact >= actCap) { status = DP_ACT; break; }
-                    int* a = act + 5 * nact; nact++;
-                    a[0] = alignList; a[1] = !rev ? 0 : x.segCount - 1;
-                    act_build(a, al, segs, rev, stamp, smsk, row, a1, a2, LY, RY);
-                    alignList = !rev ? x.next : x.prev;
-                }
-                int w = 0;
-                for (int k = 0; k < nact; k++) if (act[5 * k + 4] >= 0) { if (w != k) for (int z = 0; z < 5; z++) act[5 * w + z] = act[5 * k + z]; w++; }
-                nact = w;
-            }
+        if (nact > 0 || row == nextActRow) {
+            if (lane == 0)
+                active_update(act, &nact, actCap, listv, &alignList, &nextActRow, &status, al, segs, rev, stamp, smsk, row, a1, a2, LY, RY);
             __syncwarp();
-            nact = __shfl_sync(FULL, nact, 0); alignList = __shfl_sync(FULL, alignList, 0); status = __shfl_sync(FULL, status, 0);
+            nact = __shfl_sync(FULL, nact, 0); alignList = __shfl_sync(FULL, alignList, 0); nextActRow = __shfl_sync(FULL, nextActRow, 0); status = __shfl_sync(FULL, status, 0);
             if (status != DP_OK) break;
         }
         /* ---- traceback capacity gapped_extend.c:3636-3662 ---- */
@@ -395,14 +371,15 @@ k_ydrop_warp(dp_job* jobs, const dseg* __restrict__ segs,
     /* ---- traceback, gapped_extend.c:3847-3859 ---- */
     __threadfence();
     __syncwarp();
-    u32 nops = 0;
-    if (status == DP_OK || status == DP_TRUNCATED) {
-        bool ovf = false;
+    u32 nops = 0; bool ovf = false;
+    if (status == DP_OK || status == DP_TRUNCATED)
         nops = traceback_walk(tb, tbRow, end1, end2, J->ops, J->opsCap, lane, &ovf);
-        if (ovf) status = DP_OPS;
-    }
     if (lane == 0) {
-        J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2; J->nops = nops;
-        J->rows = row; J->cells = cells; J->status = status;
-    }
+        if (!tbOnly) {
+            J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2;
+            J->rows = row; J->cells = cells; J->status = status; J->ckptCount = 0;
+        }
+        J->nops = nops; J->opsOverflow = ovf ? 1 : 0;
+        job_done(J);
+}
 }

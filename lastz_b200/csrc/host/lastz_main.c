@@ -72,7 +72,7 @@ static void parse_options(options* o, int argc, char** argv) {
     lzb_filters_init(&o->filters);
     o->withTrans = 1; o->step = 1; o->whichStrand = 1; o->gfExtend = LZB_GFEX_XDROP; o->gapped = 1;
     o->entropy = 1; o->trimToPeak = 1; o->tracebackBytes = 80u * 1024 * 1024; o->hashBits = 16;
-    o->speculation = 32;
+    o->speculation = 256;
     char* wordSeed = NULL;
     /* shortcuts that stand for a string of options (expanders[] lastz.c:559-577, current versions); the command line
      * recorded for the headers keeps the shortcut itself */

@@ -70,6 +70,8 @@ def test_default_pipeline_on_fixtures(engines, spec):
     (300000, dict(speculation=8, traceback_bytes=1024 * 1024, all_bounds=True)),
     (200000, dict(speculation=4, y_drop=3000, score_threshold=5000)),
     (200000, dict(speculation=4, trim_to_peak=False)),
+    (1000000, dict(speculation=256, traceback_bytes=1024 * 1024)),       # hundreds of sweeps in one launch, most of them resumed from a checkpoint
+    (1000000, dict(speculation=48, traceback_bytes=4 * 1024 * 1024, trim_to_peak=False)),   # fewer lanes than anchors worth starting
 ])
 def test_synthetic_pairs(engines, synth, size, kw):
     prod, orc = engines
@@ -92,13 +94,27 @@ def test_sequence_ends_and_noise(engines, synth):
     _compare(prod, orc, tseq[:50000], qseq[:20000], 0, seed, dict(speculation=1))
 
 
-def test_small_ring_is_grown(engines, synth, monkeypatch):
-    """a sweep-row ring that is too small must be retried, not silently truncated"""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_fallback_kernels(engines, synth, monkeypatch, mode):
+    """the one-warp kernel and the shared-memory kernel (what a band too wide for the register window falls back to)
+    under the same scheduler: no checkpoints there, so a reached sweep restarts from its first row"""
     prod, orc = engines
-    monkeypatch.setenv("LZB_RING", "512")
+    monkeypatch.setenv("LZB_DP_MODE", mode)
     t, q = synth(200000)
     tseq, qseq = read_fasta(t)[0][1], read_fasta(q)[0][1]
-    _compare(prod, orc, tseq, qseq, 0, parse_seed(), dict(speculation=2))
+    _compare(prod, orc, tseq, qseq, 0, parse_seed(), dict(speculation=16, traceback_bytes=1024 * 1024))
+
+
+def test_checkpoint_interval(engines, synth, monkeypatch):
+    """a different checkpoint spacing must not change anything (fresh context: the spacing is fixed when the lanes are made)"""
+    from lastz_b200 import Engine, default_scoring
+    monkeypatch.setenv("LZB_CKPT_EVERY", "96")
+    prod2 = Engine.product(0)
+    prod2.set_scoring(default_scoring())
+    t, q = synth(300000)
+    tseq, qseq = read_fasta(t)[0][1], read_fasta(q)[0][1]
+    _compare(prod2, engines[1], tseq, qseq, 0, parse_seed(), dict(speculation=32, traceback_bytes=512 * 1024))
+    prod2.close()
 
 
 def test_identical_sequences_trivial_alignment(engines):

@@ -105,15 +105,17 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
         dp_job& J = jobs[side]; const int rev = side == 0;
         J.reversed = rev; J.a1 = a1; J.a2 = a2;
         J.M = rev ? a1 + 1 - lo1 : hi1 - (a1 + 1); J.N = rev ? a2 + 1 - lo2 : hi2 - (a2 + 1);
-        J.L0 = 0; J.R0 = (s32)(J.N + 1); J.leftSeg = { -1, -1 }; J.rightSeg = { -1, -1 }; J.alignList = -1; J.al = NULL;
+        J.L0 = 0; J.R0 = (s32)(J.N + 1); J.leftSeg = { -1, -1 }; J.rightSeg = { -1, -1 }; J.listv = NULL; J.alignList = 0; J.al = NULL; J.resume = -1; J.token = 7;
         tb[side].resize((size_t)tbBytes + 64); tbRow[side].resize(len1 + len2 + 16); ops[side].resize(2 * (len1 + len2) + 16); act[side].resize(5 * 16);
         J.tb = tb[side].data(); J.tbLen = tbLen; J.tbRow = tbRow[side].data(); J.tbRowCap = (u32)tbRow[side].size();
         J.ops = ops[side].data(); J.opsCap = (u32)ops[side].size(); J.act = act[side].data(); J.actCap = 16;
     }
-    if (oneWarp == 2) emu_launch(2, 256, [&]() { k_ydrop<256>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim, 4096u); });   // the shared-memory fallback, 4096-column ring
-    else if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });   // the one-warp kernel (512-column window)
-    else emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(jobs, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
+    launch_list ll; memset(&ll, 0, sizeof ll); ll.ix[0] = 0; ll.ix[1] = 1;
+    if (oneWarp == 2) emu_launch(2, 256, [&]() { k_ydrop<256>(jobs, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim, 4096u); });   // the shared-memory fallback, 4096-column ring
+    else if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(jobs, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });   // the one-warp kernel (512-column window)
+    else emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(jobs, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
     int bad = 0;
+    for (int side = 0; side < 2; side++) if (jobs[side].done != 7 || jobs[side].opsOverflow) { fprintf(stderr, "  side %d: done=%u overflow=%d\n", side, jobs[side].done, jobs[side].opsOverflow); bad++; }
     for (int side = 0; side < 2; side++) if (jobs[side].status != DP_OK && jobs[side].status != DP_TRUNCATED) { fprintf(stderr, "  side %d: kernel status %d\n", side, jobs[side].status); bad++; }
     // assemble like ydrop_align (gapped_extend.c:2529-2560): left script in emission order, right script reversed
     std::string gotCols; expand(gotCols, ops[0].data(), jobs[0].nops, false); expand(gotCols, ops[1].data(), jobs[1].nops, true);
