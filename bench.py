@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- LASTZ seed-and-extend hot path on B200: seed-hits/s and Y-drop Gcells/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--size L] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload auto|config3|config4] [--impl ours|reference]
 
-Workload (BASELINE.json configs[2]): synthetic L = 50 Mbp target x its ~5 %-divergent copy (the
-SURVEY.md 8d splitmix64 generator, seed 20260925), default options (12of19 + 1 transition,
-x-drop 910, K = L = 3000, entropy, Y-drop 9400, 80 MiB traceback), both strands.
-A "step" is one pass of the hot path over this rank's query interval: for each strand,
-seed_hit_search -> reduce_to_points -> gapped_extend through the C-ABI.  The target bytes and its
-position table stay resident in HBM (built once, outside the timed region, and reported).
-With N ranks the QUERY is cut into N equal intervals (strong scaling, reference-visible cuts
-`q.fa[a..b]`); after each step the ranks' HSP segment tables are gathered with one NCCL
-all_gather over NVLink.
+Workloads (BASELINE.json configs, SURVEY.md 8d generator: splitmix64 seed 20260925, ~5 % divergence):
+  config3  synthetic 50 Mbp x 50 Mbp, default lastz options, both strands, gapped          -- the 1-GPU line
+  config4  synthetic 250 Mbp x 250 Mbp, --chain, gapped, query cut into one interval per GPU -- the multi-GPU line
+`--workload auto` (the default) takes config3 on one GPU and config4 on several; the one-GPU line also carries one
+pass of config4 (`config4_one_gpu`) so that the multi-GPU numbers have their own single-GPU base.
 
-`value` = raw seed hits per second of seed-stage time (the metric's first half); `gcells_per_s` =
-DP cells per second of gapped-stage time (its second half).  `ms_per_step` covers the whole step.
-Timing is the host clock around blocking C-ABI calls bracketed by barrier + device sync (max over
-ranks); per-kernel numbers come from CUDA events recorded by the library on its own stream.
+A "step" is one pass of the hot path over this rank's query interval: for each strand seed_hit_search ->
+[reduce_to_chain] -> reduce_to_points -> gapped_extend through the C-ABI.  The target bytes and its position table stay
+resident in HBM (built once, outside the timed region, and reported).  The two strands run on two host threads with a
+context each: the minus strand's seed stage starts when the plus strand's has returned, so it overlaps the plus
+strand's gapped stage (which keeps only part of the SMs busy).  After each step the ranks' HSP tables and alignments
+are gathered to rank 0 over NCCL.
+
+`value` = raw seed hits of the step / WHOLE step time (both stages of both strands), device-resident query;
+`e2e.value` = the same with the query coming from host memory every step and the results read back.  The stage rates
+the metric names are in `seed_hits_per_s` (hits / seed-stage time) and `gcells_per_s` (DP cells / gapped-stage time).
+Timing is the host clock around blocking C-ABI calls bracketed by barrier + device sync (max over ranks); per-kernel
+numbers come from CUDA events recorded by the library on its own stream.
 """
 import argparse
 import json
@@ -31,41 +35,52 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# the gapped stage runs one stream per speculation lane; give each its own hardware queue.
 # Must be in the environment before torch creates the CUDA context (lzb_open sets it too).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SEED = 20260925
 GAMMA = np.uint64(0x9E3779B97F4A7C15)
+WORKLOADS = {
+    "config3": dict(L=50_000_000, chain=False,
+                    name="BASELINE configs[2]: synthetic 50 Mbp target x ~5%-divergent copy, default lastz options, both strands, gapped"),
+    "config4": dict(L=250_000_000, chain=True,
+                    name="BASELINE configs[3]: synthetic 250 Mbp target x ~5%-divergent copy, --chain, both strands, gapped, query cut into one interval per GPU"),
+}
+INT32_LANES_PER_SM = 128          # integer lanes per SM per clock (4 schedulers x 32)
 
 
-def _splitmix(seed, n):
-    """n outputs of splitmix64 started at `seed` (vectorised; wraps modulo 2^64)."""
+def _splitmix(seed, n, start=0):
+    """outputs start+1 .. start+n of splitmix64 started at `seed` (vectorised; wraps modulo 2^64)."""
     with np.errstate(over="ignore"):
-        z = np.uint64(seed) + GAMMA * np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + GAMMA * np.arange(start + 1, start + n + 1, dtype=np.uint64)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         return z ^ (z >> np.uint64(31))
 
 
-def synth_pair(L, seed=SEED):
-    """tools/gen_synth.c in numpy: (target bytes, query bytes)."""
+def synth_pair(L, seed=SEED, block=25_000_000):
+    """tools/gen_synth.c in numpy, in blocks so that 250 Mbp stays within a few GB: (target bytes, query bytes)."""
     acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
-    tcode = (_splitmix(seed, L) >> np.uint64(62)).astype(np.uint8)
-    r = _splitmix(seed + 1, L)
-    u = (r & np.uint64(0xFFFFFF)).astype(np.int64)
-    hi = (r >> np.uint64(24))
-    sub = u < 671089
-    dele = (u >= 671089) & (u < 754975)
-    ins = (u >= 754975) & (u < 838861)
-    first = np.where(sub, (tcode + 1 + (hi % np.uint64(3)).astype(np.uint8)) & 3, tcode).astype(np.uint8)
-    cnt = np.where(dele, 0, np.where(ins, 2, 1)).astype(np.int64)
-    off = np.cumsum(cnt) - cnt
-    q = np.empty(int(cnt.sum()), dtype=np.uint8)
-    keep = ~dele
-    q[off[keep]] = first[keep]
-    q[off[ins] + 1] = (hi[ins] & np.uint64(3)).astype(np.uint8)
-    return acgt[tcode].tobytes(), acgt[q].tobytes()
+    tparts, qparts = [], []
+    for b0 in range(0, L, block):
+        n = min(block, L - b0)
+        tcode = (_splitmix(seed, n, b0) >> np.uint64(62)).astype(np.uint8)
+        r = _splitmix(seed + 1, n, b0)
+        u = (r & np.uint64(0xFFFFFF)).astype(np.int64)
+        hi = (r >> np.uint64(24))
+        sub = u < 671089
+        dele = (u >= 671089) & (u < 754975)
+        ins = (u >= 754975) & (u < 838861)
+        first = np.where(sub, (tcode + 1 + (hi % np.uint64(3)).astype(np.uint8)) & 3, tcode).astype(np.uint8)
+        cnt = np.where(dele, 0, np.where(ins, 2, 1)).astype(np.int64)
+        off = np.cumsum(cnt) - cnt
+        q = np.empty(int(cnt.sum()), dtype=np.uint8)
+        keep = ~dele
+        q[off[keep]] = first[keep]
+        q[off[ins] + 1] = (hi[ins] & np.uint64(3)).astype(np.uint8)
+        tparts.append(acgt[tcode].tobytes())
+        qparts.append(acgt[q].tobytes())
+    return b"".join(tparts), b"".join(qparts)
 
 
 def write_fasta(path, name, seq):
@@ -118,28 +133,35 @@ def measured_peak():
 # the reference / CPU baseline arm: unmodified lastz (oracle/_ref) on the host cores
 # --------------------------------------------------------------------------------------------
 _REF_CACHE = {}
+REF_TARGET_BP = 50_000_000        # the reference's sample always runs against (a prefix of) 50 Mbp of target
 
 
-def cpu_reference(target, query, sample_bp, procs, hits_cells_fn):
-    """Time oracle/_ref/lastz on `procs` query subranges of `sample_bp` each against the full target.
+def cpu_reference(target, query, sample_bp, procs, chain, check_counts=None):
+    """Time oracle/_ref/lastz on `procs` query subranges against the first 50 Mbp of the target.
 
-    Stage times by difference: the same query prefix at two lengths, with and
-    without --nogapped, so index build and start-up cancel.  hits/cells for the sample come from
-    hits_cells_fn (the product, proven equal by the parity tests) or from the counter build."""
+    Stage times by difference: each process's subrange at two lengths (sample_bp and
+    2 x sample_bp), with --nogapped for the seed stage and re-run from those HSPs (--segments=) for the gapped stage, so
+    that start-up, file loading and the index build cancel.  The metric's numerators (raw seed hits, DP cells) come from
+    the reference's own counter build (oracle/_ref/lastz_stats, -Dcollect_stats) on the longer subranges.
+    check_counts(ranges) -> (hits, cells), when given, is the PRODUCT on the same subranges: a mismatch is fatal."""
     ref = os.path.join(ROOT, "oracle", "_ref", "lastz")
+    counter = os.path.join(ROOT, "oracle", "_ref", "lastz_stats")
     kind = "reference"
     if not os.path.exists(ref):
-        ref = os.path.join(ROOT, "oracle", "lastz_oracle")
+        ref = counter = os.path.join(ROOT, "oracle", "lastz_oracle")
         kind = "port"
+    tlen = min(len(target), REF_TARGET_BP)
     if "fasta" not in _REF_CACHE:                       # the inputs are written once per process
         d = tempfile.mkdtemp(prefix="lzb_bench_")
         _REF_CACHE["fasta"] = (os.path.join(d, "t.fa"), os.path.join(d, "q.fa"))
-        write_fasta(_REF_CACHE["fasta"][0], b"t", target)
-        write_fasta(_REF_CACHE["fasta"][1], b"q", query)
+        write_fasta(_REF_CACHE["fasta"][0], b"t", target[:tlen])
+        write_fasta(_REF_CACHE["fasta"][1], b"q", query[:tlen])
     tfa, qfa = _REF_CACHE["fasta"]
-    procs = max(1, min(procs, len(query) // (2 * sample_bp)))
-    short = [(k * 2 * sample_bp + 1, k * 2 * sample_bp + sample_bp) for k in range(procs)]
-    long_ = [(k * 2 * sample_bp + 1, (k + 1) * 2 * sample_bp) for k in range(procs)]
+    procs = max(1, min(procs, tlen // (2 * sample_bp)))
+    stride = tlen // procs                               # spread over the whole sample so that every piece of target is used
+    short = [(k * stride + 1, k * stride + sample_bp) for k in range(procs)]
+    long_ = [(k * stride + 1, k * stride + 2 * sample_bp) for k in range(procs)]
+    opts = ["--chain"] if chain else []
 
     def run(ranges, extra, tag=None):
         """one reference process per range, concurrently; tag: HSPs go to / anchors come from a segments file per range"""
@@ -157,35 +179,54 @@ def cpu_reference(target, query, sample_bp, procs, hits_cells_fn):
             p.wait()
         return time.perf_counter() - t0
 
-    # Seed stage: --nogapped runs (their HSPs are kept as segments files); gapped stage: the reference re-run from
-    # those files with --segments=, which skips index build and seed search (src/Makefile:384 base_test_segments),
-    # so the 6 s index build of a 50 Mbp target and its run-to-run noise never enter the gapped-stage time.
-    # Start-up, file loading and index build cancel in the differences between the two query lengths.  All four
-    # runs are timed afresh in every step (a cached first measurement would carry the cold file cache into every
-    # later step); only the hit/cell counts of the sample are taken once per process.
-    key = (sample_bp, procs)
-    if key not in _REF_CACHE:
-        run(short, ["--nogapped"], "short")             # untimed: pages the binary and the two FASTA files in
-        _REF_CACHE[key] = (hits_cells_fn(short), hits_cells_fn(long_))
+    def counts(ranges):
+        hits = cells = 0
+        ps = [subprocess.Popen([counter, tfa, f"{qfa}[{a}..{b}]", "--stats"] + opts, stdout=subprocess.DEVNULL,
+                               stderr=subprocess.PIPE, text=True) for a, b in ranges]   # --stats reports on stderr
+        for p in ps:
+            for line in p.communicate()[1].splitlines():
+                if "raw seed hits:" in line:
+                    hits += int(line.split(":")[1].replace(",", ""))
+                if "DP cells visited:" in line:
+                    cells += int(line.split(":")[1].replace(",", ""))
+        return hits, cells
+
+    key = (sample_bp, procs, chain)
+    if key not in _REF_CACHE:                            # once per process: warm the file cache, count, cross-check
+        run(short, ["--nogapped"] + opts, "short")
+        hs, cs = counts(short)
+        hl, cl = counts(long_)
+        if check_counts is not None and kind == "reference":
+            ph, pc = check_counts(long_)
+            if (ph, pc) != (hl, cl):
+                raise SystemExit(f"FAILURE: bench self-check: the product counts {ph} raw seed hits / {pc} DP cells on the "
+                                 f"sample subranges, the reference's counter build {hl} / {cl}")
+        _REF_CACHE[key] = ((hs, cs), (hl, cl))
     (hs, cs), (hl, cl) = _REF_CACHE[key]
-    t_ns, t_nl = run(short, ["--nogapped"], "short"), run(long_, ["--nogapped"], "long")
-    t_gs, t_gl = run(short, [], "short"), run(long_, [], "long")
+    t_ns, t_nl = run(short, ["--nogapped"] + opts, "short"), run(long_, ["--nogapped"] + opts, "long")
+    t_gs, t_gl = run(short, opts, "short"), run(long_, opts, "long")
     hits, cells = hl - hs, cl - cs
-    seed_s = t_nl - t_ns
-    gap_s = t_gl - t_gs
+    seed_s, gap_s = t_nl - t_ns, t_gl - t_gs
     note = ""
-    if seed_s < 0.05 * t_nl or gap_s < 0.05 * t_gl:
+    if seed_s < 0.05 * t_nl or gap_s < 0.05 * t_gl or cells <= 0:
         # sample too small for differences to rise above process start-up noise: charge whole runs
         # (index build / file loading included), which can only flatter the CPU less
-        hits, cells = hl, cl
+        hits, cells = hl, max(cl, 1)
         seed_s, gap_s = t_nl, max(t_gl, 1e-3)
         note = " [differences below noise: whole-run times used]"
-    return {"kind": kind, "cores": procs, "hits": hits, "cells": cells, "index_s": t_ns - seed_s, "seed_s": seed_s,
-            "gapped_s": gap_s, "hits_per_s": hits / seed_s, "gcells_per_s": cells / gap_s / 1e9,
-            "sample": f"{procs} processes, each query[{sample_bp} bp] and query[{2 * sample_bp} bp] vs the full "
-                      f"{len(target)} bp target, both strands; stage times are differences between the two lengths "
-                      f"(--nogapped for the seed stage; the gapped stage re-run from those HSPs with --segments=, "
-                      f"so no index build enters it)" + note}
+    return {"kind": kind, "cores": procs, "hits": hits, "cells": cells, "index_s": max(t_ns - seed_s, 0.0), "seed_s": seed_s,
+            "gapped_s": gap_s, "hits_per_s": hits / seed_s, "cells_per_s": cells / gap_s,
+            "self_check": "product hits and DP cells on the sample subranges equal oracle/_ref/lastz_stats" if check_counts and kind == "reference" else None,
+            "sample": f"{procs} processes, each query[{sample_bp} bp] and query[{2 * sample_bp} bp] (spread over the sequence) vs the first "
+                      f"{tlen} bp of the target, both strands{', --chain' if chain else ''}; stage times are differences between the two lengths "
+                      f"(--nogapped for the seed stage; the gapped stage re-run from those HSPs with --segments=, so no index build "
+                      f"enters it); numerators from the -Dcollect_stats build" + note}
+
+
+def whole_job_rate(hits_full, cells_full, hits_per_s, cells_per_s):
+    """seed hits per second of whole-job time for a workload with that many hits and cells, at the measured stage rates
+    (the linear extrapolation BASELINE.md section 3.5 prescribes)"""
+    return hits_full / (hits_full / hits_per_s + cells_full / cells_per_s)
 
 
 # --------------------------------------------------------------------------------------------
@@ -194,64 +235,65 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=50_000_000)
+    ap.add_argument("--workload", default=os.environ.get("LZB_BENCH_WORKLOAD", "auto"), choices=["auto", "config3", "config4"])
+    ap.add_argument("--size", type=int, default=0, help="override the workload's sequence length (tests)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--speculation", type=int, default=256)
-    ap.add_argument("--cpu-sample", type=int, default=125_000, help="query bp per reference process (x1 and x2)")
-    ap.add_argument("--cpu-procs", type=int, default=16)
+    ap.add_argument("--speculation", type=int, default=384)
+    ap.add_argument("--cpu-sample", type=int, default=500_000, help="query bp per reference process (x1 and x2)")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="reference processes (default: every host core, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the two strands one after the other")
+    ap.add_argument("--no-config4-base", action="store_true", help="skip the single pass of config4 on the one-GPU line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    L = args.size
-    config = {"workload": f"synthetic {L} bp target x ~5%-divergent copy, default lastz options, both strands, gapped",
-              "generator": "splitmix64 seed 20260925 (SURVEY.md 8d)", "seed": "12of19 + 1 transition",
-              "x_drop": 910, "y_drop": 9400, "hsp_threshold": 3000, "traceback_bytes": 80 * 1024 * 1024,
-              "query_shards": world, "l2": "inputs larger than L2 (index + hit buffers are GBs)"}
+    wname = args.workload if args.workload != "auto" else ("config3" if world == 1 else "config4")
+    wl = dict(WORKLOADS[wname])
+    if args.size:
+        wl["L"] = args.size
+    L = wl["L"]
+    ncores = os.cpu_count() or 1
+    procs = args.cpu_procs or min(ncores, 64)
+
+    def config_of(w, shards):
+        return {"workload": w["name"] if not args.size else f"{w['name']} [length overridden: {w['L']} bp]",
+                "generator": "splitmix64 seed 20260925 (SURVEY.md 8d)", "seed": "12of19 + 1 transition",
+                "x_drop": 910, "y_drop": 9400, "hsp_threshold": 3000, "traceback_bytes": 80 * 1024 * 1024,
+                "chain": bool(w["chain"]), "query_shards": shards,
+                "l2": "inputs larger than L2 (index, hit buffers and traceback are GBs)"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        target, query = synth_pair(L)
-        ncores = os.cpu_count() or 1
-        procs = min(ncores, 64)
-        counter = os.path.join(ROOT, "oracle", "_ref", "lastz_stats")
-
-        def count_with_stats(ranges):
-            # the counter build prints the metric numerators itself
-            tfa, qfa = _REF_CACHE["fasta"]               # written by cpu_reference before it asks for counts
-            hits = cells = 0
-            ps = [subprocess.Popen([counter, tfa, f"{qfa}[{a}..{b}]", "--stats"], stdout=subprocess.DEVNULL,
-                                   stderr=subprocess.PIPE, text=True) for a, b in ranges]   # --stats reports on stderr
-            for p in ps:
-                out = p.communicate()[1]
-                for line in out.splitlines():
-                    if "raw seed hits:" in line:
-                        hits += int(line.split(":")[1].replace(",", ""))
-                    if "DP cells visited:" in line:
-                        cells += int(line.split(":")[1].replace(",", ""))
-            return hits, cells
-        vals = []
-        for _ in range(args.warmup + args.steps):
-            r = cpu_reference(target, query, args.cpu_sample, procs, count_with_stats)
-            vals.append(r)
+        target, query = synth_pair(min(L, REF_TARGET_BP))
+        # the workload's own numerators, scaled from the sample: random hits grow with L1 x L2, DP cells with L2
+        vals = [cpu_reference(target, query, args.cpu_sample, procs, wl["chain"]) for _ in range(max(1, args.steps))]
+        hps = float(np.mean([v["hits_per_s"] for v in vals])); cps = float(np.mean([v["cells_per_s"] for v in vals]))
         r = vals[-1]
-        hps = float(np.mean([v["hits_per_s"] for v in vals[args.warmup:]]))
-        line = {"impl": "reference", "metric": "seed-hits/s (seed stage); Gcells/s in gcells_per_s", "value": hps,
-                "unit": "hits/s", "gcells_per_s": float(np.mean([v["gcells_per_s"] for v in vals[args.warmup:]])),
+        tl = min(L, REF_TARGET_BP)
+        sample_q = r["cores"] * args.cpu_sample
+        hits_full = r["hits"] * (L / tl) * (L / sample_q); cells_full = r["cells"] * (L / sample_q)
+        value = whole_job_rate(hits_full, cells_full, hps, cps)
+        line = {"impl": "reference", "metric": "seed-hits/s over the whole step (seed + gapped stages); stage rates in seed_hits_per_s and gcells_per_s",
+                "value": value, "unit": "hits/s", "seed_hits_per_s": hps, "gcells_per_s": cps / 1e9,
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * (r["index_s"] + r["seed_s"] + r["gapped_s"]), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": hps, "unit": "hits/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
-                "e2e": {"value": hps, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "ms_per_step": 1e3 * hits_full / value, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config_of(wl, args.gpus),
+                "extrapolation": f"stage rates measured on the sample; whole-job time = hits/rate + cells/rate with the workload's hits "
+                                 f"({hits_full:.3e}) and DP cells ({cells_full:.3e}) scaled from the sample (hits ~ L1 x L2, cells ~ L2; BASELINE.md 3.5); "
+                                 f"warm-up: one untimed pass that pages the binary and the inputs in",
+                "cpu_baseline": {"value": value, "unit": "hits/s", "seed_hits_per_s": hps, "gcells_per_s": cps / 1e9, "cores": r["cores"], "kind": r["kind"],
+                                 "sample": r["sample"], "host_cores_available": ncores},
+                "e2e": {"value": value, "unit": "hits/s", "gcells_per_s": cps / 1e9, "seed_hits_per_s": hps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
     import torch
     import torch.distributed as dist
-    from lastz_b200 import Engine, default_scoring, parse_seed, revcomp
+    from lastz_b200 import Engine, default_scoring, parse_seed, reduce_to_chain, revcomp
+    from lastz_b200.sharding import gather_to_rank0, pack_alignments, query_interval, to_global
 
     # LZB_BENCH_DEVICE=cpu exists for tests/test_bench_dryrun.py only: it runs this very control flow (sharding,
     # collectives, aggregation, the JSON line) with world_size 2 over gloo, the test substituting its own engine.
@@ -265,17 +307,15 @@ def main():
             dist.init_process_group("gloo")
     if on_gpu:
         torch.cuda.set_device(local)
-    target, query = synth_pair(L)
-    lo, hi = rank * len(query) // world, (rank + 1) * len(query) // world
-    shard = query[lo:hi]
-    strands = [(0, shard), (3, revcomp(shard))]
-
-    eng = Engine.product(local)
-    eng.set_scoring(default_scoring())
+    ss = default_scoring()
     seed = parse_seed()
-    t0 = time.perf_counter()
-    T = eng.build_seed_position_table(target, seed)
-    index_s = time.perf_counter() - t0
+    engA = Engine.product(local)
+    engA.set_scoring(ss)
+    overlap = not args.no_overlap
+    engB = engA
+    if overlap:
+        engB = Engine.product(local)                     # a second context (stream, scratch) for the other strand
+        engB.set_scoring(ss)
 
     def sync():
         if on_gpu:
@@ -283,93 +323,141 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def gather_segments(tables):
-        """the one exchange step: every rank's HSP table to all ranks over NCCL"""
-        from lastz_b200.sharding import gather_segment_tables
-        parts = gather_segment_tables(np.concatenate(tables), dev)
-        return sum(len(p) for p in parts)
+    def measure(w, steps, warmup, both_passes=True):
+        """the timed passes over one workload; returns (resident result, e2e result, static info)"""
+        target, query = synth_pair(w["L"])
+        lo, hi = query_interval(len(query), rank, world)
+        shard = query[lo:hi]
+        strands = [(0, shard), (3, revcomp(shard))]
+        t0 = time.perf_counter()
+        T = engA.build_seed_position_table(target, seed)
+        index_s = time.perf_counter() - t0
 
-    def step(resident, handles=None):
-        acc = dict(hits=0, cells=0, cells_computed=0, seed_s=0.0, gap_s=0.0, ext_s=0.0, ext_launch=0, bp=0, hsps=0, h2d=0, d2h=0,
-                   ext=0, dp_kernel_s=0.0, dp_launches=0, seed_wall=0.0, gap_wall=0.0, load_wall=0.0, free_wall=0.0, gather_wall=0.0,
-                   words=0, kern=[0.0] * 12, kern_n=[0] * 12)
-        tables = []
-        for k, (sid, s) in enumerate(strands):
+        def strand_pass(eng, sid, s, Q, resident, acc, seed_done=None):
             w0 = time.perf_counter()
-            Q = handles[k] if resident else eng.load_query(s)
-            wl = time.perf_counter()
             if not resident:
+                Q = eng.load_query(s)
                 acc["h2d"] += len(s)
+            wl_ = time.perf_counter()
             segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid)
             w1 = time.perf_counter()
-            tables.append(segs.copy())
+            if seed_done is not None:
+                seed_done.set()
+            table = segs.copy()
+            if w["chain"]:
+                segs = reduce_to_chain(segs, ss)
+            wc = time.perf_counter()
             anchors = eng.reduce_to_points(T, Q, segs)
             al, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, identity_check=False, speculation=args.speculation)
             w2 = time.perf_counter()
-            acc["seed_wall"] += w1 - w0; acc["gap_wall"] += w2 - w1; acc["load_wall"] += wl - w0
+            acc["seed_wall"] += w1 - w0; acc["chain_wall"] += wc - w1; acc["gap_wall"] += w2 - wc; acc["load_wall"] += wl_ - w0
             acc["hits"] += st.rawSeedHits; acc["seed_s"] += st.seconds; acc["words"] += st.wordsInQuery
             for i in range(12):
                 acc["kern"][i] += st.kernelSeconds[i]; acc["kern_n"][i] += st.kernelLaunches[i]
-            # the x-drop extension stage: k_extend2 / k_extend [7] or k_right + k_replay + k_left [8..10], one of each per chunk
+            # the x-drop extension stage: k_extend2 [7] or k_right + k_replay + k_left [8..10], one of each per chunk
             acc["ext_s"] += sum(st.kernelSeconds[i] for i in (7, 8, 9, 10))
             acc["ext_launch"] += st.kernelLaunches[7] + st.kernelLaunches[8]
             acc["bp"] += st.bpExtended; acc["ext"] += st.extensions
-            acc["hsps"] += len(segs); acc["cells"] += gst.dpCells; acc["cells_computed"] += gst.dpCellsComputed
-            acc["gap_s"] += gst.seconds
-            acc["dp_kernel_s"] += gst.kernelSeconds[0]; acc["dp_launches"] += gst.launches
-            acc["h2d"] += 48 * len(segs); acc["d2h"] += 2 * 48 * len(segs) + 4 * sum(len(a["ops"]) for a in al)
+            acc["hsps"] += len(table); acc["anchors"] += len(segs); acc["cells"] += gst.dpCells; acc["cells_computed"] += gst.dpCellsComputed
+            acc["gap_s"] += gst.seconds; acc["dp_launches"] += gst.launches; acc["alignments"] += len(al)
+            acc["dp_rows"] += gst.dpRows; acc["redone"] += gst.redone; acc["speculated"] += gst.speculated
+            acc["h2d"] += 48 * len(segs); acc["d2h"] += 2 * 48 * len(table) + 4 * sum(len(a["ops"]) for a in al)
             if not resident:
                 eng.free_query(Q)
             acc["free_wall"] += time.perf_counter() - w2
-        w3 = time.perf_counter()
-        acc["gathered"] = gather_segments(tables)
-        acc["gather_wall"] = time.perf_counter() - w3
-        return acc
+            acc["tables"].append(to_global(table, lo, hi, len(query), revcomp=(sid != 0)))
+            acc["aligns"].append(pack_alignments(al, sid))
 
-    def timed(resident):
-        handles = [eng.load_query(s) for _, s in strands] if resident else None
-        for _ in range(args.warmup):
-            step(resident, handles)
-        sync()
-        l0 = eng.launches()
-        t0 = time.perf_counter()
-        accs = [step(resident, handles) for _ in range(args.steps)]
-        sync()
-        dt = time.perf_counter() - t0
-        launches = eng.launches() - l0
-        if handles:
-            for h in handles:
-                eng.free_query(h)
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item()), accs, launches
+        def new_acc():
+            return dict(hits=0, cells=0, cells_computed=0, seed_s=0.0, gap_s=0.0, ext_s=0.0, ext_launch=0, bp=0, hsps=0, anchors=0, h2d=0, d2h=0,
+                        ext=0, dp_launches=0, seed_wall=0.0, chain_wall=0.0, gap_wall=0.0, load_wall=0.0, free_wall=0.0, gather_wall=0.0,
+                        words=0, kern=[0.0] * 12, kern_n=[0] * 12, alignments=0, dp_rows=0, redone=0, speculated=0, tables=[], aligns=[])
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    dt, accs, launches = timed(True)
-    clocks = sampler.stop() if rank == 0 else None
-    dt_e2e, accs_e2e, _ = timed(False)
+        def step(resident, handles):
+            accA, accB = new_acc(), new_acc()
+            (sidA, sA), (sidB, sB) = strands
+            if overlap:
+                ev = threading.Event()
+                err = []
 
-    def total(key, accs_):
+                def other():
+                    try:
+                        ev.wait()
+                        strand_pass(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+                    except BaseException as e:       # noqa: BLE001  (re-raised on the main thread)
+                        err.append(e)
+                th = threading.Thread(target=other)
+                th.start()
+                try:
+                    strand_pass(engA, sidA, sA, handles[0] if resident else None, resident, accA, seed_done=ev)
+                finally:
+                    ev.set()
+                    th.join()
+                if err:
+                    raise err[0]
+            else:
+                strand_pass(engA, sidA, sA, handles[0] if resident else None, resident, accA)
+                strand_pass(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+            acc = new_acc()
+            for k in acc:
+                if k in ("kern", "kern_n"):
+                    acc[k] = [a + b for a, b in zip(accA[k], accB[k])]
+                else:
+                    acc[k] = accA[k] + accB[k]
+            w3 = time.perf_counter()
+            segs_all = gather_to_rank0(np.concatenate(acc["tables"]).view(np.uint8).reshape(-1), dev)
+            al_all = gather_to_rank0(np.concatenate(acc["aligns"]).view(np.uint8).reshape(-1), dev)
+            acc["gathered_segments"] = sum(len(p) for p in segs_all) // 48 if segs_all is not None else 0
+            acc["gathered_alignment_bytes"] = sum(len(p) for p in al_all) if al_all is not None else 0
+            acc["gather_wall"] = time.perf_counter() - w3
+            acc["tables"], acc["aligns"] = [], []
+            return acc
+
+        def timed(resident, steps_, warmup_):
+            handles = [engA.load_query(strands[0][1]), engB.load_query(strands[1][1])] if resident else None
+            for _ in range(warmup_):
+                step(resident, handles)
+            sync()
+            l0 = engA.launches() + (engB.launches() if engB is not engA else 0)
+            t0_ = time.perf_counter()
+            accs = [step(resident, handles) for _ in range(steps_)]
+            sync()
+            dt = time.perf_counter() - t0_
+            launches = engA.launches() + (engB.launches() if engB is not engA else 0) - l0
+            if handles:
+                engA.free_query(handles[0]); engB.free_query(handles[1])
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), accs, launches
+
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        res = timed(True, steps, warmup)
+        clocks = sampler.stop() if rank == 0 else None
+        e2e = timed(False, steps, 1 if both_passes else 0) if both_passes else None
+        info = dict(target=target, query=query, T=T, index_s=index_s, clocks=clocks, lo=lo, hi=hi)
+        return res, e2e, info
+
+    def total(key, accs_, op=None):
         v = torch.tensor([float(sum(a[key] for a in accs_))], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            dist.all_reduce(v, op=op or dist.ReduceOp.SUM)
         return float(v.item())
 
     def worst(key, accs_):
-        v = torch.tensor([float(sum(a[key] for a in accs_))], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        return float(v.item())
+        return total(key, accs_, dist.ReduceOp.MAX)
 
+    (dt, accs, launches), (dt_e2e, accs_e2e, _), info = measure(wl, args.steps, args.warmup)
+    target, query, T = info["target"], info["query"], info["T"]
     hits, cells = total("hits", accs), total("cells", accs)
-    seed_s, gap_s = worst("seed_s", accs), worst("gap_s", accs)
+    seed_wall, gap_wall = worst("seed_wall", accs), worst("gap_wall", accs)
+    seed_dev = worst("seed_s", accs)
     total_l = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total_l, op=dist.ReduceOp.SUM)
-    # roofline of the dominant seed-stage kernel (k_extend), this rank
+    # roofline of the dominant seed-stage kernel (k_extend2), this rank
     ext_s = sum(a["ext_s"] for a in accs); ext_n = max(1, sum(a["ext_launch"] for a in accs))
     my_hits = sum(a["hits"] for a in accs); my_bp = sum(a["bp"] for a in accs)
     bytes_per_hit = 12.0 + 0.5 * my_bp / max(1, my_hits)      # SURVEY 8d: 4 B position + 8 B diagEnd + 0.5 B/column
@@ -378,56 +466,82 @@ def main():
     # every cross-rank aggregate is computed HERE, on all ranks (collectives must not sit under `if rank == 0`)
     agg = {"e2e_hits": total("hits", accs_e2e), "e2e_cells": total("cells", accs_e2e),
            "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_wall", accs_e2e),
-           "hsps": total("hsps", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e),
-           "cells_computed": total("cells_computed", accs)}
-    e2e_hits = agg["e2e_hits"]
+           "hsps": total("hsps", accs), "anchors": total("anchors", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e),
+           "cells_computed": total("cells_computed", accs), "alignments": total("alignments", accs),
+           "redone": total("redone", accs), "speculated": total("speculated", accs)}
 
     def per_step(key, accs_):
         return 1e3 * sum(a[key] for a in accs_) / args.steps
 
     def wall_breakdown(accs_):
-        """rank 0's host clock, ms per step: where the time outside the kernels goes"""
+        """rank 0's host clock, ms per step, summed over the two strands (which overlap in time when --no-overlap is not given)"""
         return {"load_query": per_step("load_wall", accs_), "seed_call": per_step("seed_wall", accs_) - per_step("load_wall", accs_),
-                "seed_device": per_step("seed_s", accs_), "peaks_and_gapped_call": per_step("gap_wall", accs_),
-                "free_query": per_step("free_wall", accs_), "gather_segments": per_step("gather_wall", accs_)}
+                "seed_device": per_step("seed_s", accs_), "chain": per_step("chain_wall", accs_), "peaks_and_gapped_call": per_step("gap_wall", accs_),
+                "free_query": per_step("free_wall", accs_), "gather_to_rank0": per_step("gather_wall", accs_)}
 
-    # per-kernel view of the seed stage + the DP kernel, this rank (CUDA events on the library's streams)
     KNAMES = ["k_query_words", "k_count_hits", "k_slot_count", "cub scan", "k_expand", "cub radix sort", "k_bucket_bounds",
               "k_extend2", "k_right", "k_replay", "k_left", "bucket order (k_bucket_sizes + cub sort)"]
     kern = [sum(a["kern"][i] for a in accs) for i in range(12)]
     kern_n = [sum(a["kern_n"][i] for a in accs) for i in range(12)]
     my_words = sum(a["words"] for a in accs)
     traffic_per_hit = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp):
-        traffic_per_hit = json.load(open(tp)).get("k_extend_dram_bytes_per_hit")
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            traffic_per_hit = json.load(open(tp)).get("k_extend_dram_bytes_per_hit")
+            traffic_src = name
+            break
+
+    base4 = None
+    if world == 1 and wname == "config3" and not args.no_config4_base and not args.size:
+        # the multi-GPU line's own single-GPU base: one timed pass of config4 (one warm-up pass before it)
+        engA.free_position_table(T)
+        T = None
+        (dt4, accs4, _), _, info4 = measure(WORKLOADS["config4"], 1, 1, both_passes=False)
+        h4 = sum(a["hits"] for a in accs4); c4 = sum(a["cells"] for a in accs4)
+        base4 = {"workload": WORKLOADS["config4"]["name"], "value": h4 / dt4, "unit": "hits/s", "ms_per_step": 1e3 * dt4, "steps": 1, "warmup": 1,
+                 "seed_hits_per_s": h4 / max(sum(a["seed_wall"] for a in accs4), 1e-12),
+                 "gcells_per_s": c4 / max(sum(a["gap_wall"] for a in accs4), 1e-12) / 1e9,
+                 "counts_per_step": {"raw_seed_hits": h4, "dp_cells": c4, "hsps": sum(a["hsps"] for a in accs4),
+                                     "anchors_after_chain": sum(a["anchors"] for a in accs4), "alignments": sum(a["alignments"] for a in accs4)},
+                 "index_build_once_ms": 1e3 * info4["index_s"]}
+        engA.free_position_table(info4["T"])
+        target, query = synth_pair(L)                    # back to this line's workload for the CPU leg
+        T = engA.build_seed_position_table(target, seed)
 
     if rank == 0:
-        line = {"metric": "seed-hits/s (seed stage); Gcells/s in gcells_per_s", "value": hits / seed_s, "unit": "hits/s",
-                "gcells_per_s": cells / gap_s / 1e9, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        sm_mhz = (info["clocks"] or {}).get("sm_mhz") or 1965
+        line = {"metric": "seed-hits/s over the whole step (seed + gapped stages); stage rates in seed_hits_per_s and gcells_per_s",
+                "value": hits / dt, "unit": "hits/s",
+                "seed_hits_per_s": hits / seed_wall, "gcells_per_s": cells / gap_wall / 1e9,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "int32", "data": "synthetic", "config": config,
-                "stage_ms_per_step": {"seed": 1e3 * seed_s / args.steps, "gapped": 1e3 * gap_s / args.steps,
-                                      "index_build_once": 1e3 * index_s},
+                "dtype": "int32", "data": "synthetic", "config": config_of(wl, world),
+                "stage_ms_per_step": {"seed": 1e3 * seed_wall / args.steps, "seed_device_events": 1e3 * seed_dev / args.steps,
+                                      "gapped": 1e3 * gap_wall / args.steps, "index_build_once": 1e3 * info["index_s"],
+                                      "note": "wall time of the blocking calls, summed over the two strands, max over ranks; with the strands "
+                                              "overlapped the stages add up to more than ms_per_step"},
                 "counts_per_step": {"raw_seed_hits": hits / args.steps, "dp_cells": cells / args.steps,
                                     "dp_cells_incl_discarded_speculation": agg["cells_computed"] / args.steps,
-                                    "hsps": agg["hsps"] / args.steps, "segments_gathered": accs[-1]["gathered"]},
+                                    "hsps": agg["hsps"] / args.steps, "anchors": agg["anchors"] / args.steps, "alignments": agg["alignments"] / args.steps,
+                                    "sweeps_started_speculatively": agg["speculated"] / args.steps, "sweeps_resumed_or_redone": agg["redone"] / args.steps,
+                                    "segments_gathered": accs[-1]["gathered_segments"], "alignment_bytes_gathered": accs[-1]["gathered_alignment_bytes"]},
                 "timing": "host clock around blocking C-ABI calls, barrier+sync both sides, max over ranks; "
-                          "kernels timed by CUDA events on the library's stream",
-                "clocks": clocks, "gpu_launches": int(total_l.item()),
-                "e2e": {"value": e2e_hits / agg["e2e_seed_wall"],
-                        "unit": "hits/s (host clock: H2D copy of the query from host memory + lzb_seed_hit_search incl. D2H of the HSP table)",
-                        "gcells_per_s": agg["e2e_cells"] / agg["e2e_gap_wall"] / 1e9,
+                          "kernels timed by CUDA events on the library's stream; strands overlapped: " + str(overlap),
+                "clocks": info["clocks"], "gpu_launches": int(total_l.item()),
+                "e2e": {"value": agg["e2e_hits"] / dt_e2e, "unit": "hits/s",
+                        "seed_hits_per_s": agg["e2e_hits"] / agg["e2e_seed_wall"], "gcells_per_s": agg["e2e_cells"] / agg["e2e_gap_wall"] / 1e9,
                         "ms_per_step": 1e3 * dt_e2e / args.steps,
+                        "what": "the same step with the query strands copied from host memory inside the timed region (lzb_query_load) and HSP tables + "
+                                "edit scripts read back",
                         "h2d_bytes_per_step": int(agg["h2d"] / args.steps),
                         "d2h_bytes_per_step": int(agg["d2h"] / args.steps)},
-                "roofline": {"kernel": "k_extend2 (bucket replay + x-drop extension, DESIGN.md K3): the dominant kernel of the seed stage, "
-                                       "i.e. of the time `value` is measured on; the step as a whole is dominated by k_ydrop_mw, see roofline_kernels",
+                "roofline": {"kernel": "k_extend2 (bucket replay + x-drop extension, DESIGN.md K3): the seed-hit kernel north_star's HBM target names",
                              "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None if traffic_per_hit is None else traffic_per_hit * my_hits / ext_n,
                              "traffic_source": None if traffic_per_hit is None else
-                             "dram__bytes_read+write per hit from the ncu --set full capture in profiles/ (r01_traffic.json) x hits per launch here",
+                             f"dram__bytes_read+write per hit from the ncu --set full capture in profiles/ ({traffic_src}) x hits per launch here",
                              "peak_source": peak_src,
                              "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n},
                 "wall_ms_per_step": {"resident": wall_breakdown(accs), "e2e": wall_breakdown(accs_e2e)}}
@@ -446,35 +560,55 @@ def main():
                 ent["achieved_gbs"] = alg[i] / max(kern[i], 1e-12) / 1e9
                 ent["frac_of_hbm_peak"] = ent["achieved_gbs"] / peak
             rk.append(ent)
-        dp_s = sum(a["dp_kernel_s"] for a in accs); my_cells = sum(a["cells_computed"] for a in accs)
-        rk.append({"kernel": "k_ydrop_mw (Y-drop DP + traceback; one launch = the two one-sided DPs of an anchor, up to "
-                             f"{args.speculation} launches in flight)", "launches": sum(a["dp_launches"] for a in accs),
-                   "lane_ms_per_step": 1e3 * dp_s / args.steps, "bound": "latency (integer max-plus recurrence per row), not HBM",
-                   "achieved_gbs": 1.0 * my_cells / max(dp_s, 1e-12) / 1e9, "frac_of_hbm_peak": 1.0 * my_cells / max(dp_s, 1e-12) / 1e9 / peak,
-                   "note": "1 traceback byte per cell is the only algorithmic HBM traffic; lane time is summed over concurrent launches",
-                   "cells_computed_per_step": my_cells / args.steps})
+        my_cells = sum(a["cells_computed"] for a in accs); gap_my = sum(a["gap_wall"] for a in accs)
+        int_peak = 148 * INT32_LANES_PER_SM * sm_mhz * 1e6
+        rk.append({"kernel": "k_ydrop_mw (Y-drop DP + traceback; one CTA per one-sided sweep, hundreds of sweeps per launch)",
+                   "launches": sum(a["dp_launches"] for a in accs), "gapped_stage_ms_per_step": 1e3 * gap_my / args.steps,
+                   "bound": "dependent integer issue per DP row (max-plus recurrence + two block-wide scans), not HBM",
+                   "achieved_gbs": 1.0 * my_cells / max(gap_my, 1e-12) / 1e9, "frac_of_hbm_peak": 1.0 * my_cells / max(gap_my, 1e-12) / 1e9 / peak,
+                   "int32_frac": 12.0 * my_cells / max(gap_my, 1e-12) / int_peak,
+                   "int32_note": f"12 integer ops per cell (BASELINE.md 4) x cells computed / gapped-stage time, against 148 SMs x {INT32_LANES_PER_SM} lanes x "
+                                 f"{sm_mhz} MHz = {int_peak / 1e12:.1f} Tops/s",
+                   "note": "1 traceback byte per cell is the only algorithmic HBM traffic",
+                   "cells_computed_per_step": my_cells / args.steps, "rows_per_step": sum(a["dp_rows"] for a in accs) / args.steps})
         line["roofline_kernels"] = rk
+        if base4 is not None:
+            line["config4_one_gpu"] = base4
         if world == 1 and not args.no_cpu_baseline:
-            def hc(ranges):
+            def product_counts(ranges):
                 h = c = 0
+                tl = min(len(target), REF_TARGET_BP)
+                Ts = T if tl == len(target) else engA.build_seed_position_table(target[:tl], seed)
                 for a, b in ranges:
                     sub = query[a - 1:b]
                     for sid, s in ((0, sub), (3, revcomp(sub))):
-                        Q = eng.load_query(s)
-                        segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid)
-                        anchors = eng.reduce_to_points(T, Q, segs)
-                        _, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, speculation=args.speculation)
+                        Q = engA.load_query(s)
+                        segs, st = engA.seed_hit_search(Ts, Q, seed, strand_id=sid)
+                        if wl["chain"]:
+                            segs = reduce_to_chain(segs, ss)
+                        anchors = engA.reduce_to_points(Ts, Q, segs)
+                        _, gst, _ = engA.gapped_extend(Ts, Q, target[:tl], s, anchors, speculation=args.speculation)
                         h += st.rawSeedHits; c += gst.dpCells
-                        eng.free_query(Q)
+                        engA.free_query(Q)
+                if Ts is not T:
+                    engA.free_position_table(Ts)
                 return h, c
-            ncores = os.cpu_count() or 1
-            r = cpu_reference(target, query, args.cpu_sample, min(args.cpu_procs, ncores), hc)
-            line["cpu_baseline"] = {"value": r["hits_per_s"], "unit": "hits/s", "gcells_per_s": r["gcells_per_s"],
-                                    "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-                                    "host_cores_available": ncores}
+            r = cpu_reference(target, query, args.cpu_sample, procs, wl["chain"], product_counts)
+            cpu_value = whole_job_rate(hits / args.steps, cells / args.steps, r["hits_per_s"], r["cells_per_s"])
+            line["cpu_baseline"] = {"value": cpu_value, "unit": "hits/s", "seed_hits_per_s": r["hits_per_s"], "gcells_per_s": r["cells_per_s"] / 1e9,
+                                    "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "self_check": r["self_check"],
+                                    "host_cores_available": ncores,
+                                    "whole_job": "stage rates measured on the sample, whole-job time = this step's hits / rate + this step's DP cells / rate"}
+            line["speedup_vs_cpu_baseline"] = {"whole_step_e2e": line["e2e"]["value"] / cpu_value,
+                                               "seed_stage_e2e": line["e2e"]["seed_hits_per_s"] / r["hits_per_s"],
+                                               "gapped_stage_e2e": line["e2e"]["gcells_per_s"] / (r["cells_per_s"] / 1e9),
+                                               "note": f"against {r['cores']} host cores running the unmodified reference; reported, not a target"}
         print(json.dumps(line))
-    eng.free_position_table(T)
-    eng.close()
+    if T is not None:
+        engA.free_position_table(T)
+    if engB is not engA:
+        engB.close()
+    engA.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

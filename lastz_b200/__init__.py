@@ -5,4 +5,4 @@ Python binding used by tests/, bench.py and __graft_entry__.py.
 """
 from . import capi  # noqa: F401
 from .api import (Engine, SEED_12OF19, SEED_14OF22, default_scoring, parse_seed, read_fasta,  # noqa: F401
-                  revcomp)
+                  reduce_to_chain, revcomp)

@@ -49,7 +49,20 @@ def host_lib():
         _host.lzb_seed_parse.argtypes = [C.POINTER(capi.Seed), C.c_char_p, C.c_int]
         _host.lzb_scores_default.argtypes = [C.POINTER(_ScoreSet)]
         _host.lzb_scores_read_file.argtypes = [C.POINTER(_ScoreSet), C.c_char_p]
+        _host.lzb_reduce_to_chain.restype = C.c_int32
+        _host.lzb_reduce_to_chain.argtypes = [C.POINTER(capi.Segment), C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     return _host
+
+
+def reduce_to_chain(segs, scoring, diag_penalty=0, anti_penalty=0):
+    """reduce_to_chain chain.c:497 with the penalties of lastz.c:3687 (chainScale 100, lastz.c:511): the HSP table
+    cut down to its best chain, ordered by pos1.  Host C (csrc/host/chain.c), as in the reference."""
+    a = np.ascontiguousarray(segs).copy()
+    n = C.c_uint64(len(a))
+    if len(a):
+        host_lib().lzb_reduce_to_chain(a.ctypes.data_as(C.POINTER(capi.Segment)), C.byref(n), diag_penalty, anti_penalty,
+                                       100, scoring.sub[ord("A") * 256 + ord("A")])
+    return a[:n.value]
 
 
 def parse_seed(pattern=SEED_12OF19, with_trans=1):

@@ -69,9 +69,9 @@ extern "C" int lzb_reduce_to_points(lzb_ctx* c, lzb_target* t, lzb_query* q, lzb
 #include "gapped_sched.hpp"
 
 #define GX_MAX_LANES (LZB_LAUNCH_MAX / 2)
-#define GX_STREAMS 16
+#define GX_STREAMS 120                                       /* a launch goes to a stream with nothing in flight; the device runs at most 128 grids at once */
 #define GX_STAGE_WORDS (4u << 20)                           /* 16 MB */
-#define GX_CKPT_CAP 512u
+#define GX_CKPT_CAP 1024u
 
 struct cuda_lane {
     u8* tb[2]; u32* tbRow[2]; u32 tbRowCap[2];
@@ -79,18 +79,22 @@ struct cuda_lane {
     int* act[2]; u32 actCap[2];
     u32* ckpt[2];
     int* list[2]; int* d_list[2]; size_t listCap[2];        /* mapped pinned */
+    bool ownTbRow[2], ownOps[2], ownAct[2];                  /* regrown on its own (else part of the chunk's slab) */
 };
+#define GX_CHUNK 16                                          /* lanes made at a time: a few big allocations instead of hundreds */
+struct lane_chunk { u8* tb; u32* tbRow; int* act; u32* ckpt; u32* ops; };
 
 struct gx_cache {                        /* lives in the context: lanes are expensive to allocate */
     lzb_ctx* c;
-    std::vector<cuda_lane> lanes; u32 tbBytes, tbLen, ckptEvery;
+    std::vector<cuda_lane> lanes; std::vector<lane_chunk> chunks; u32 tbBytes, tbLen, ckptEvery;
     dp_job* h_jobs; dp_job* d_jobs;      /* mapped pinned, 2 per lane: a kernel reads its job and writes its result there,
                                             so the launch streams carry nothing but kernels */
     dseg* d_segs; size_t segsCap; dalign* d_aligns; size_t alignsCap;
     /* uploads go through mapped pinned staging + a copy KERNEL: an H2D copy on a stream that shares a
      * hardware queue with a running DP kernel waits for that kernel (engine switch inside one channel) */
     u32* h_stage; u32* d_stage; cudaStream_t upStream;
-    cudaStream_t streams[GX_STREAMS]; int nextStream;
+    cudaStream_t streams[GX_STREAMS]; int nStreams;
+    std::vector<std::pair<u16, u32> > inflight[GX_STREAMS];   /* (job, token) of the last launch on each stream */
     const u8* cls1; const u8* cls2; u32 len1, len2; s32 yDrop; int trim;   /* of the current call */
     u32 launched[2 * GX_MAX_LANES];      /* token of the last launch of each job (0: never launched) */
     u64 polls; char err[256];
@@ -119,31 +123,50 @@ static int gx_upload(gx_cache* gc, void* dst, const void* src, size_t bytes) {
 
 static void free_lane(cuda_lane& ln) {
     for (int s = 0; s < 2; s++) {
-        cudaFree(ln.tb[s]); cudaFree(ln.tbRow[s]); cudaFreeHost(ln.ops[s]); cudaFree(ln.act[s]); cudaFree(ln.ckpt[s]);
+        if (ln.ownTbRow[s]) cudaFree(ln.tbRow[s]);
+        if (ln.ownOps[s]) cudaFreeHost(ln.ops[s]);
+        if (ln.ownAct[s]) cudaFree(ln.act[s]);
         if (ln.list[s]) cudaFreeHost(ln.list[s]);
     }
 }
+static void free_chunk(lane_chunk& ch) { cudaFree(ch.tb); cudaFree(ch.tbRow); cudaFree(ch.act); cudaFree(ch.ckpt); cudaFreeHost(ch.ops); }
 
 void lzb_gapped_cache_free(lzb_ctx* c) {
     gx_cache* gc = (gx_cache*)c->gappedCache;
     if (!gc) return;
     for (auto& ln : gc->lanes) free_lane(ln);
+    for (auto& ch : gc->chunks) free_chunk(ch);
     cudaFree(gc->d_segs); cudaFree(gc->d_aligns); cudaFreeHost(gc->h_stage); cudaFreeHost(gc->h_jobs);
-    for (int k = 0; k < GX_STREAMS; k++) cudaStreamDestroy(gc->streams[k]);
+    for (int k = 0; k < gc->nStreams; k++) cudaStreamDestroy(gc->streams[k]);
     cudaStreamDestroy(gc->upStream);
     delete gc; c->gappedCache = NULL;
 }
 
-static int make_lane(gx_cache* gc, cuda_lane& ln) {
-    memset(&ln, 0, sizeof ln);
-    for (int s = 0; s < 2; s++) {
-        CUDA_TRY(cudaMalloc(&ln.tb[s], (size_t)gc->tbBytes + 64));
-        ln.tbRowCap[s] = gc->tbLen / 128 + 4096; CUDA_TRY(cudaMalloc(&ln.tbRow[s], (size_t)ln.tbRowCap[s] * 4));
-        ln.opsCap[s] = 1u << 16;
-        CUDA_TRY(cudaHostAlloc(&ln.ops[s], (size_t)ln.opsCap[s] * 4, cudaHostAllocMapped));
-        CUDA_TRY(cudaHostGetDevicePointer((void**)&ln.d_ops[s], ln.ops[s], 0));
-        ln.actCap[s] = 256; CUDA_TRY(cudaMalloc(&ln.act[s], (size_t)ln.actCap[s] * 5 * 4));
-        CUDA_TRY(cudaMalloc(&ln.ckpt[s], (size_t)GX_CKPT_CAP * CK_WORDS(8, 128) * 4));
+#define GX_OPS_CAP (1u << 16)
+#define GX_ACT_CAP 256u
+/* GX_CHUNK more lanes out of five slabs */
+static int make_chunk(gx_cache* gc) {
+    lane_chunk ch; memset(&ch, 0, sizeof ch);
+    const size_t tbStride = (((size_t)gc->tbBytes + 64) + 255) & ~(size_t)255, nside = 2 * GX_CHUNK;
+    const u32 tbRowCap = gc->tbLen / 128 + 4096;
+    const size_t ckWords = (size_t)GX_CKPT_CAP * CK_WORDS(8, 128);
+    u32* d_ops = NULL;
+    if (cudaMalloc(&ch.tb, tbStride * nside) != cudaSuccess || cudaMalloc(&ch.tbRow, (size_t)tbRowCap * 4 * nside) != cudaSuccess ||
+        cudaMalloc(&ch.act, (size_t)GX_ACT_CAP * 5 * 4 * nside) != cudaSuccess || cudaMalloc(&ch.ckpt, ckWords * 4 * nside) != cudaSuccess ||
+        cudaHostAlloc(&ch.ops, (size_t)GX_OPS_CAP * 4 * nside, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&d_ops, ch.ops, 0) != cudaSuccess) { free_chunk(ch); cudaGetLastError(); return -1; }
+    gc->chunks.push_back(ch);
+    for (int k = 0; k < GX_CHUNK; k++) {
+        cuda_lane ln; memset(&ln, 0, sizeof ln);
+        for (int s = 0; s < 2; s++) {
+            const size_t e = (size_t)2 * k + s;
+            ln.tb[s] = ch.tb + tbStride * e;
+            ln.tbRow[s] = ch.tbRow + (size_t)tbRowCap * e; ln.tbRowCap[s] = tbRowCap;
+            ln.ops[s] = ch.ops + (size_t)GX_OPS_CAP * e; ln.d_ops[s] = d_ops + (size_t)GX_OPS_CAP * e; ln.opsCap[s] = GX_OPS_CAP;
+            ln.act[s] = ch.act + (size_t)GX_ACT_CAP * 5 * e; ln.actCap[s] = GX_ACT_CAP;
+            ln.ckpt[s] = ch.ckpt + ckWords * e;
+        }
+        gc->lanes.push_back(ln);
     }
     return 0;
 }
@@ -153,21 +176,19 @@ struct cuda_backend {
     const char* error() { return gc->err; }
     u32 ckpt_every() { return gc->ckptEvery; }
     u32 ring(int mode) { return mode == 2 ? 4096u : 8192u; }
-    int lanes(int want) {
+    int lanes(int want) {                                    /* called again when the scheduler wants more */
         if (want > GX_MAX_LANES) want = GX_MAX_LANES;
         const size_t laneBytes = 2 * ((size_t)gc->tbBytes + (size_t)(gc->tbLen / 128 + 4096) * 4 + (size_t)GX_CKPT_CAP * CK_WORDS(8, 128) * 4 + 8192);
         while ((int)gc->lanes.size() < want) {
             size_t freeB = 0, totalB = 0;
             if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) break;
-            /* keep a quarter of the device for the seed stage and the caller; one lane is always made */
-            if (!gc->lanes.empty() && freeB < totalB / 4 + laneBytes) break;
-            cuda_lane ln;
-            if (make_lane(gc, ln)) { free_lane(ln); cudaGetLastError(); if (gc->lanes.empty()) return -1; break; }
-            gc->lanes.push_back(ln);
+            /* keep a quarter of the device for the seed stage and the caller; one chunk is always made */
+            if (!gc->lanes.empty() && freeB < totalB / 4 + laneBytes * GX_CHUNK) break;
+            const int first = (int)gc->lanes.size();
+            if (make_chunk(gc)) { if (gc->lanes.empty()) { lzb_fail("no device memory for the traceback of one Y-drop lane"); return -1; } break; }
+            for (int z = first; z < (int)gc->lanes.size(); z++) { fill_job(z, 0); fill_job(z, 1); }
         }
-        const int have = (int)std::min<size_t>(gc->lanes.size(), (size_t)want);
-        for (int z = 0; z < have; z++) for (int s = 0; s < 2; s++) fill_job(z, s);
-        return have;
+        return (int)std::min<size_t>(gc->lanes.size(), (size_t)want);
     }
     void fill_job(int z, int s) {
         cuda_lane& ln = gc->lanes[z]; dp_job& J = gc->h_jobs[2 * z + s];
@@ -228,7 +249,25 @@ struct cuda_backend {
             gc->launched[ix[k]] = J.token;
         }
         std::atomic_thread_fence(std::memory_order_seq_cst);
-        cudaStream_t st = gc->streams[gc->nextStream]; gc->nextStream = (gc->nextStream + 1) % GX_STREAMS;
+        /* A stream runs its launches one after the other, and a launch lasts as long as its longest sweep: a short resume
+         * queued behind a batch of fresh sweeps would wait for all of them.  So every launch takes a stream whose last
+         * launch has finished (all its jobs have signalled), a new one if there is none. */
+        int pick = -1;
+        while (pick < 0) {
+            for (int k = 0; k < gc->nStreams && pick < 0; k++) {
+                bool idle = true;
+                for (auto& jt : gc->inflight[k]) if (gc->h_jobs[jt.first].done != jt.second && gc->launched[jt.first] == jt.second) { idle = false; break; }
+                if (idle) pick = k;
+            }
+            if (pick < 0 && gc->nStreams < GX_STREAMS) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&gc->streams[gc->nStreams], cudaStreamNonBlocking));
+                pick = gc->nStreams++;
+            }
+            if (pick < 0 && !poll()) return lzb_fail("Y-drop kernel failed: %s", gc->err);
+        }
+        cudaStream_t st = gc->streams[pick];
+        gc->inflight[pick].clear();
+        for (int k = 0; k < n; k++) gc->inflight[pick].push_back(std::make_pair(ix[k], gc->h_jobs[ix[k]].token));
         if (mode == 0)
             k_ydrop_mw<8, 4><<<n, 128, 0, st>>>(gc->d_jobs, ll, gc->d_segs, gc->cls1, gc->cls2, gc->len1, gc->len2, c->d_sc, gc->yDrop, gc->trim);
         else if (mode == 1)
@@ -245,7 +284,7 @@ struct cuda_backend {
     bool poll() {
         gc->polls++;
         if ((gc->polls & 1023) == 0) {
-            for (int k = 0; k < GX_STREAMS; k++) {
+            for (int k = 0; k < gc->nStreams; k++) {
                 cudaError_t e = cudaStreamQuery(gc->streams[k]);
                 if (e != cudaSuccess && e != cudaErrorNotReady) { snprintf(gc->err, sizeof gc->err, "%s", cudaGetErrorString(e)); return false; }
             }
@@ -256,12 +295,15 @@ struct cuda_backend {
     int grow(int z, int s, int what) {
         cuda_lane& ln = gc->lanes[z];
         if (what == DP_TBROW) {
-            cudaFree(ln.tbRow[s]); ln.tbRowCap[s] = ln.tbRowCap[s] < gc->tbLen / 4 ? ln.tbRowCap[s] * 4 : gc->tbLen + 8;
+            if (ln.ownTbRow[s]) cudaFree(ln.tbRow[s]);
+            ln.ownTbRow[s] = true; ln.tbRowCap[s] = ln.tbRowCap[s] < gc->tbLen / 4 ? ln.tbRowCap[s] * 4 : gc->tbLen + 8;
             CUDA_TRY(cudaMalloc(&ln.tbRow[s], (size_t)ln.tbRowCap[s] * 4));
         } else if (what == DP_ACT) {
-            cudaFree(ln.act[s]); ln.actCap[s] *= 4; CUDA_TRY(cudaMalloc(&ln.act[s], (size_t)ln.actCap[s] * 5 * 4));
+            if (ln.ownAct[s]) cudaFree(ln.act[s]);
+            ln.ownAct[s] = true; ln.actCap[s] *= 4; CUDA_TRY(cudaMalloc(&ln.act[s], (size_t)ln.actCap[s] * 5 * 4));
         } else if (what == DP_OPS) {
-            cudaFreeHost(ln.ops[s]); ln.opsCap[s] *= 4;
+            if (ln.ownOps[s]) cudaFreeHost(ln.ops[s]);
+            ln.ownOps[s] = true; ln.opsCap[s] *= 4;
             CUDA_TRY(cudaHostAlloc(&ln.ops[s], (size_t)ln.opsCap[s] * 4, cudaHostAllocMapped));
             CUDA_TRY(cudaHostGetDevicePointer((void**)&ln.d_ops[s], ln.ops[s], 0));
         }
@@ -282,13 +324,12 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
     gx_cache* gc = (gx_cache*)c->gappedCache;
     if (gc && gc->tbBytes != P->tracebackBytes) { lzb_gapped_cache_free(c); gc = NULL; }
     if (!gc) {
-        gc = new gx_cache(); memset((void*)&gc->tbBytes, 0, sizeof(gx_cache) - offsetof(gx_cache, tbBytes));
+        gc = new gx_cache();                               /* value-initialised: every scalar member starts at zero */
         gc->c = c; gc->tbBytes = P->tracebackBytes; gc->tbLen = 1 + (P->tracebackBytes - 8);
-        gc->ckptEvery = 1024;
+        gc->ckptEvery = 256;
         { const char* e = getenv("LZB_CKPT_EVERY"); if (e) { int v = atoi(e); if (v >= 32 && v % 32 == 0) gc->ckptEvery = (u32)v; } }
         c->gappedCache = gc;
         CUDA_TRY(cudaStreamCreateWithFlags(&gc->upStream, cudaStreamNonBlocking));
-        for (int k = 0; k < GX_STREAMS; k++) CUDA_TRY(cudaStreamCreateWithFlags(&gc->streams[k], cudaStreamNonBlocking));
         CUDA_TRY(cudaHostAlloc(&gc->h_stage, (size_t)GX_STAGE_WORDS * 4, cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&gc->d_stage, gc->h_stage, 0));
         CUDA_TRY(cudaHostAlloc(&gc->h_jobs, (size_t)2 * GX_MAX_LANES * sizeof(dp_job), cudaHostAllocMapped));

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -185,6 +186,7 @@ struct gx_side {
     bool tbOnly;                        /* the running launch only redoes the traceback */
     dp_result res;                      /* valid when DONE */
     u32 ckptCount, ckptEvery;           /* checkpoints the finished sweep left behind */
+    u32 prog0Rows, prog0Used;           /* first progress report seen from the running sweep */
 };
 struct gx_lane_state {
     bool busy; u64 anchor; segref left1, right1;   /* the anchor's neighbours the sweeps were started with */
@@ -281,8 +283,10 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     int W = P->speculation; if (W < 1) W = 1; if (W > LZB_LAUNCH_MAX / 2) W = LZB_LAUNCH_MAX / 2;
     { const char* e = getenv("LZB_SPECULATION"); if (e) { W = atoi(e); if (W < 1) W = 1; if (W > LZB_LAUNCH_MAX / 2) W = LZB_LAUNCH_MAX / 2; } }
     if ((u64)W > n) W = n ? (int)n : 1;
-    W = B.lanes(W);
-    if (W < 1) return -1;
+    /* lanes are made as they are needed (a lane is 2 x the traceback size of device memory) */
+    int have = B.lanes(std::min(W, 8));
+    if (have < 1) return -1;
+    if (have < std::min(W, 8)) W = have;
     int firstMode = 0;
     { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3) firstMode = mdv; } }
     std::vector<gx_lane_state> lanes(W);
@@ -383,6 +387,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             J.listv = lv; J.alignList = 0;
             J.tbLen = tbLen;
             J.resume = rec;
+            if (rec < 0) { J.progRows = 0; J.progUsed = 0; }
             sd.snapshot = G.committed.size();
         }
         (void)m;
@@ -486,8 +491,15 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     };
 
     /* expected length of a sweep in rows, for deciding what is worth starting: an average over finished sweeps */
-    double reach = (double)tbLen / 420.0 + 64;
-    u64 reachSamples = 0;
+    /* How far a sweep will go (scheduling only).  A sweep that is not stopped by anything ends where the traceback
+     * runs out (gapped_extend.c:3636-3662): rows ~ tbLen / (traceback bytes per row), and the bytes per row settle
+     * within the first thousand rows -- the kernel reports (rows, bytes) with every checkpoint, so the estimate is there
+     * a few milliseconds after the first launch and exact as soon as one truncated sweep has finished.  (Where the
+     * homology ends earlier the estimate is too long, which only makes a later anchor wait for an earlier one.) */
+    const double reachPrior = (double)tbLen / 250.0 + 64;    /* before anything is known: generous */
+    double reachTrunc = 0; bool reachExact = false;
+    auto reach = [&]() -> double { return reachTrunc > 0 ? reachTrunc : reachPrior; };
+    std::vector<u8> uncertain(n, 0);                         /* started although an earlier open anchor may come to cover it */
 
     /* validate a DONE side against the alignments committed since its snapshot; returns 0 valid, 1 relaunched, -1 error */
     auto validate_side = [&](int z, int side) -> int {
@@ -519,7 +531,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         gx_lane_state& ln = lanes[z]; galn& y = G.al[j];
         ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1;
         laneOf[j] = z;
-        for (int side = 0; side < 2; side++) { ln.s[side].mode = firstMode; ln.s[side].ckptCount = 0; ln.s[side].ckptEvery = 0; ln.s[side].res.ops.clear(); }
+        for (int side = 0; side < 2; side++) { ln.s[side].mode = firstMode; ln.s[side].ckptCount = 0; ln.s[side].ckptEvery = 0; ln.s[side].res.ops.clear(); ln.s[side].prog0Rows = ln.s[side].prog0Used = 0; }
         B.job(z, 0)->abort = 0; B.job(z, 1)->abort = 0;
         if (trace) fprintf(stderr, "[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size());
         if (queue_side(z, 0, -1, false) || queue_side(z, 1, -1, false)) return -1;
@@ -548,7 +560,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         r.ops.assign(ops, ops + J.nops);
         sd.ckptCount = J.ckptCount; sd.ckptEvery = sd.mode == 0 ? B.ckpt_every() : 0;
         sd.phase = SIDE_DONE;
-        if (r.status == DP_TRUNCATED || r.end1 > 0) { const double v = (double)std::max<u32>(r.end1, 1); reach = reachSamples ? reach * 0.9 + v * 0.1 : v; reachSamples++; }
+        if (r.status == DP_TRUNCATED) { reachTrunc = reachExact ? 0.8 * reachTrunc + 0.2 * r.rows : (double)r.rows; if (!reachExact) startDirty = true; reachExact = true; }
         if (trace) fprintf(stderr, "[gx %.4f] done a=%llu side=%d rows=%u end1=%u status=%d mode=%d ckpts=%u\n", now(), (unsigned long long)ln.anchor, side, r.rows, r.end1, r.status, sd.mode, sd.ckptCount);
         return 0;
     };
@@ -562,7 +574,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         bool progressed = false;
         /* 1. collect finished launches */
         double t0 = prof ? now() : 0;
-        for (int z = 0; z < W; z++) for (int side = 0; side < 2; side++) {
+        for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
             gx_side& sd = lanes[z].s[side];
             if (sd.phase != SIDE_RUNNING) continue;
             dp_job& J = *B.job(z, side);
@@ -572,7 +584,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             progressed = true;
         }
         /* 2. check finished sweeps against what has been committed since; resume the ones that were reached */
-        for (int z = 0; z < W; z++) {
+        for (int z = 0; z < have; z++) {
             gx_lane_state& ln = lanes[z];
             if (!ln.busy) continue;
             if (ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING) continue;
@@ -620,11 +632,20 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         if (startDirty) {
             startDirty = false;
             int freeLanes = 0;
-            for (int z = 0; z < W; z++) if (lane_free(z)) freeLanes++;
+            for (int z = 0; z < have; z++) if (lane_free(z)) freeLanes++;
+            auto more_lanes = [&]() -> int {                    /* made as they are needed */
+                if (have >= W) return 0;
+                const int got = B.lanes(std::min(W, have + 32));
+                if (got < 0) return -1;
+                if (got == have) W = have;                      /* the device has no room for more */
+                freeLanes += got - have; have = got;
+                return 0;
+            };
+            if (laneOf[hd] < 0 && freeLanes == 0 && more_lanes()) return -1;
             if (laneOf[hd] < 0 && freeLanes == 0) {
                 /* every lane is held by a later anchor: take back the latest one that is not running */
                 int victim = -1;
-                for (int z = 0; z < W; z++) {
+                for (int z = 0; z < have; z++) {
                     gx_lane_state& ln = lanes[z];
                     if (!ln.busy || ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING) continue;
                     if (victim < 0 || ln.anchor > lanes[victim].anchor) victim = z;
@@ -635,32 +656,67 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     freeLanes = 1;
                 } else startDirty = true;                     /* look again when a sweep has finished */
             }
+            /* no sweep has said yet how far sweeps go: the running ones report their progress.  Two reports of one sweep give
+             * the traceback bytes a row takes once the band has settled, hence the row where the traceback will run out. */
+            if (!reachExact) {
+                for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
+                    gx_side& sd = lanes[z].s[side];
+                    if (!lanes[z].busy || sd.phase != SIDE_RUNNING) continue;
+                    dp_job& J = *B.job(z, side);
+                    const u32 pr = J.progRows, pu = J.progUsed;
+                    if (J.resume >= 0 || pr < 2048 || pu == 0) continue;
+                    if (sd.prog0Rows == 0) { sd.prog0Rows = pr; sd.prog0Used = pu; continue; }
+                    if (pr < sd.prog0Rows + 4096 || pu <= sd.prog0Used) continue;
+                    const double perRow = (double)(pu - sd.prog0Used) / (double)(pr - sd.prog0Rows);
+                    const double est = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
+                    if (reachTrunc == 0 || est < reachTrunc) reachTrunc = est;
+                }
+                if (reachTrunc == 0) startDirty = true;        /* look again */
+            }
+            const bool calibrated = reachTrunc > 0;
+            int unsureRunning = 0;
+            for (int z = 0; z < have; z++) if (lanes[z].busy && uncertain[lanes[z].anchor]) unsureRunning++;
+            const double rr = reach();
             u64 examined = 0;
-            for (u64 j = hd; j < n && freeLanes > 0 && examined < 16384; j++) {
+            for (u64 j = hd; j < n && (freeLanes > 0 || have < W) && examined < 16384; j++) {
                 if (fin[j] || laneOf[j] >= 0) continue;
                 examined++;
+                bool unsure = false;
                 if (j != hd) {
-                    /* probably covered by an earlier anchor that is still open?  (scheduling only) */
+                    /* Will an earlier anchor that is still open cover this one?  (Scheduling only.)  Inside 0.96 of the
+                     * expected reach of an anchor that is itself safe: yes -- wait for it.  Near the edge of somebody's reach,
+                     * or inside the reach of an anchor that is itself unsure: start, but do not let it hold others back. */
                     if (blocker[j] >= 0 && !fin[blocker[j]] && laneOf[blocker[j]] >= 0) continue;
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
-                    for (int z = 0; z < W && blocker[j] < 0; z++) {
+                    bool tooEarly = false;
+                    for (int z = 0; z < have && blocker[j] < 0; z++) {
                         gx_lane_state& ln = lanes[z];
                         if (!ln.busy || ln.anchor >= j) continue;
                         const u64 i = ln.anchor;
                         const s64 di = (s64)apos1[i] - (s64)apos2[i];
                         if (llabs(di - dj) > 4000) continue;
-                        const double lo = ln.s[0].phase == SIDE_DONE ? (double)ln.s[0].res.end1 : 0.85 * reach;
-                        const double hi = ln.s[1].phase == SIDE_DONE ? (double)ln.s[1].res.end1 : 0.85 * reach;
-                        if ((double)apos1[j] >= (double)apos1[i] - lo && (double)apos1[j] <= (double)apos1[i] + hi) blocker[j] = (int)i;
+                        const int side = apos1[j] < apos1[i] ? 0 : 1;
+                        const double dist = fabs((double)apos1[j] - (double)apos1[i]);
+                        if (!calibrated) { if (dist < 2.5 * reachPrior) tooEarly = true; continue; }
+                        const double ext = ln.s[side].phase == SIDE_DONE ? (double)ln.s[side].res.end1 : rr;
+                        /* (an estimate from progress reports is good to a percent; a finished sweep gives the row itself) */
+                        const double slack = reachExact || ln.s[side].phase == SIDE_DONE ? 0.004 * ext + 300 : 0.02 * ext + 300;
+                        if (dist <= ext - slack) { if (uncertain[i]) unsure = true; else blocker[j] = (int)i; }
+                        else if (dist <= ext + slack) unsure = true;
                     }
                     if (blocker[j] >= 0) continue;
+                    if (tooEarly) { startDirty = true; continue; }
+                    if (unsure && unsureRunning >= std::max(2, W / 8)) continue;     /* keep most lanes for anchors that will be needed */
                 }
                 galn& y = G.al[j];
                 int coverer = -1;
                 if (!anchor_neighbours(G, y, &coverer)) { fin[j] = 1; progressed = true; continue; }     /* (retire_covered normally got there first) */
+                if (freeLanes == 0) { if (more_lanes()) return -1; if (freeLanes == 0) break; }
                 int fl = -1;
-                for (int z = 0; z < W; z++) if (lane_free(z)) { fl = z; break; }
+                for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
+                uncertain[j] = unsure ? 1 : 0;
+                if (unsure) unsureRunning++;
                 if (start_anchor(fl, j)) return -1;
                 freeLanes--; progressed = true;
                 if (j != hd) G.st.speculated++;
@@ -671,26 +727,26 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         if (progressed) continue;
         /* 5. nothing to decide: wait for the device */
         bool any = false;
-        for (int z = 0; z < W && !any; z++) if (lanes[z].s[0].phase == SIDE_RUNNING || lanes[z].s[1].phase == SIDE_RUNNING) any = true;
+        for (int z = 0; z < have && !any; z++) if (lanes[z].s[0].phase == SIDE_RUNNING || lanes[z].s[1].phase == SIDE_RUNNING) any = true;
         if (!any) return fail("internal error: gapped scheduler stalled at anchor %llu", (unsigned long long)hd);
         t0 = prof ? now() : 0;
         if (!B.poll()) return fail("Y-drop kernel failed: %s", B.error());
         if (prof) { pfPoll += now() - t0; pfPolls++; }
     }
     /* sweeps of retired anchors that are still running: ask them to stop and wait (their buffers are reused by the next call) */
-    for (int z = 0; z < W; z++) for (int side = 0; side < 2; side++) if (lanes[z].s[side].phase == SIDE_RUNNING) B.job(z, side)->abort = 1;
-    for (int z = 0; z < W; z++) for (int side = 0; side < 2; side++) {
+    for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) if (lanes[z].s[side].phase == SIDE_RUNNING) B.job(z, side)->abort = 1;
+    for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
         while (lanes[z].s[side].phase == SIDE_RUNNING) {
             if (B.job(z, side)->done == lanes[z].s[side].token) { lanes[z].s[side].phase = SIDE_IDLE; break; }
             if (!B.poll()) return fail("Y-drop kernel failed: %s", B.error());
         }
     }
     if (prof)
-        fprintf(stderr, "[gx profile] W=%d wall=%.3f validate_s=%.3f commit_s=%.3f start_s=%.3f poll_s=%.3f polls=%llu launches=%llu jobs=%llu resumes=%llu restarts=%llu "
+        fprintf(stderr, "[gx profile] lanes=%d wall=%.3f validate_s=%.3f commit_s=%.3f start_s=%.3f poll_s=%.3f polls=%llu launches=%llu jobs=%llu resumes=%llu restarts=%llu "
                         "retired_while_held=%llu extended=%llu redone=%llu rows=%llu committed=%zu reach=%.0f\n",
-                W, now(), pfValidate, pfCommit, pfStart, pfPoll, (unsigned long long)pfPolls, (unsigned long long)pfLaunches, (unsigned long long)pfJobs,
+                have, now(), pfValidate, pfCommit, pfStart, pfPoll, (unsigned long long)pfPolls, (unsigned long long)pfLaunches, (unsigned long long)pfJobs,
                 (unsigned long long)pfResumes, (unsigned long long)pfRestarts, (unsigned long long)pfWasted, (unsigned long long)G.st.anchorsExtended,
-                (unsigned long long)G.st.redone, (unsigned long long)G.st.dpRows, G.committed.size(), reach);
+                (unsigned long long)G.st.redone, (unsigned long long)G.st.dpRows, G.committed.size(), reach());
     lzb_alignel* head = NULL, *last = NULL;
     for (int o = G.obi; o >= 0; o = G.al[o].next) {
         galn& m = G.al[o];

@@ -54,6 +54,7 @@ struct dp_job {
     /* results */
     s32 score; u32 end1, end2, nops, rows; int status; int opsOverflow; unsigned long long cells;
     u32 ckptCount;                    /* records 0 .. ckptCount-1 are valid */
+    volatile u32 progRows, progUsed;  /* written with every checkpoint while the sweep runs: rows done, traceback bytes used */
     volatile u32 done;
 };
 

@@ -451,6 +451,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
                 rec[21] = (u32)cells; rec[22] = (u32)(cells >> 32);
                 rec[23] = pWcol; rec[24] = pCnt; rec[25] = (u32)pIout;
                 for (int k = 0; k < 5 * nact; k++) rec[CK_HDR + k] = (u32)act[k];
+                J->progUsed = (u32)(u64)used; J->progRows = row;      /* lets the host estimate where the traceback will run out */
             }
             u32* tv = rec + CK_HDR + 5 * CK_ACT;
 #pragma unroll

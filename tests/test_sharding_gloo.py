@@ -16,22 +16,26 @@ import os, sys, pickle
 sys.path.insert(0, %(root)r)
 import numpy as np, torch, torch.distributed as dist
 from lastz_b200 import Engine, default_scoring, parse_seed, read_fasta, revcomp
-from lastz_b200.sharding import query_interval, gather_segment_tables
+from lastz_b200.sharding import query_interval, gather_segment_tables, gather_to_rank0, pack_alignments
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 tseq = read_fasta(%(t)r)[0][1]; qseq = read_fasta(%(q)r)[0][1]
 lo, hi = query_interval(len(qseq), rank, world)
 eng = Engine.oracle(); eng.set_scoring(default_scoring()); seed = parse_seed()
 T = eng.build_seed_position_table(tseq, seed)
-tables = []
+tables, packed = [], []
 for sid, s in ((0, qseq[lo:hi]), (3, revcomp(qseq[lo:hi]))):
     Q = eng.load_query(s)
     segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid)
     tables.append(segs)
+    al, _, _ = eng.gapped_extend(T, Q, tseq, s, eng.reduce_to_points(T, Q, segs.copy()))
+    packed.append(pack_alignments(al, sid))
 mine = np.concatenate(tables)
 parts = gather_segment_tables(mine, torch.device("cpu"))
+als = gather_to_rank0(np.concatenate(packed).view(np.uint8), torch.device("cpu"))
+assert (parts is None) == (rank != 0) and (als is None) == (rank != 0)      # a gather to rank 0, not an all_gather
 if rank == 0:
-    pickle.dump([p.tolist() for p in parts], open(%(out)r, "wb"))
+    pickle.dump(([p.tolist() for p in parts], [a.tobytes() for a in als]), open(%(out)r, "wb"))
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -50,12 +54,12 @@ def test_two_rank_query_sharding(tmp_path):
     for p in procs:
         assert p.wait(timeout=300) == 0
     import pickle
-    parts = pickle.load(open(out, "rb"))
-    assert len(parts) == 2
+    parts, als = pickle.load(open(out, "rb"))
+    assert len(parts) == 2 and len(als) == 2
 
     # the same cuts in one process
     from lastz_b200 import Engine, default_scoring, parse_seed, read_fasta, revcomp
-    from lastz_b200.sharding import query_interval
+    from lastz_b200.sharding import query_interval, to_global, unpack_alignments
     tseq, qseq = read_fasta(t)[0][1], read_fasta(q)[0][1]
     eng = Engine.oracle()
     eng.set_scoring(default_scoring())
@@ -63,12 +67,23 @@ def test_two_rank_query_sharding(tmp_path):
     T = eng.build_seed_position_table(tseq, seed)
     for r in range(2):
         lo, hi = query_interval(len(qseq), r, 2)
-        want = []
+        want, want_al = [], []
         for sid, s in ((0, qseq[lo:hi]), (3, revcomp(qseq[lo:hi]))):
-            segs, _ = eng.seed_hit_search(T, eng.load_query(s), seed, strand_id=sid)
+            Q = eng.load_query(s)
+            segs, _ = eng.seed_hit_search(T, Q, seed, strand_id=sid)
             want += segs.tolist()
+            al, _, _ = eng.gapped_extend(T, Q, tseq, s, eng.reduce_to_points(T, Q, segs.copy()))
+            want_al += [(sid, a["beg1"], a["beg2"], a["end1"], a["end2"], a["s"], a["ops"].tolist()) for a in al]
+            # whole-query coordinates: the same bases on the whole strand as on the shard's strand
+            whole = qseq if sid == 0 else revcomp(qseq)
+            g = to_global(segs, lo, hi, len(qseq), revcomp=(sid != 0))
+            for a, b in zip(segs[:50], g[:50]):
+                assert whole[int(b["pos2"]):int(b["pos2"]) + int(b["length"])] == s[int(a["pos2"]):int(a["pos2"]) + int(a["length"])]
         assert parts[r] == want
         assert len(want) > 0
+        got_al = unpack_alignments(np.frombuffer(als[r], dtype=np.uint32))
+        assert [(a["strand"], a["beg1"], a["beg2"], a["end1"], a["end2"], a["s"], a["ops"].tolist()) for a in got_al] == want_al
+        assert len(want_al) > 0
 
     # and the unmodified reference with the same cuts (q.fa[a..b]), forward strand coordinates
     if os.path.exists(REF_CLI):

@@ -62,9 +62,11 @@ struct emu_backend {
     const char* error() { return "emulator"; }
     u32 ckpt_every() { return every; }
     u32 ring(int mode) { return mode == 2 ? 4096u : 8192u; }
-    int lanes(int want) {
-        L.resize(want); jobs.resize(2 * (size_t)want); pendingToken.assign(2 * (size_t)want, 0); pendingPolls.assign(2 * (size_t)want, 0);
-        for (int z = 0; z < want; z++) for (int s = 0; s < 2; s++) {
+    int lanes(int want) {                                              // called again when the scheduler wants more
+        const int old = (int)L.size();
+        if (want <= old) return old;
+        L.resize(want); jobs.resize(2 * (size_t)want); pendingToken.resize(2 * (size_t)want, 0); pendingPolls.resize(2 * (size_t)want, 0);
+        for (int z = old; z < want; z++) for (int s = 0; s < 2; s++) {
             host_lane& ln = L[z];
             ln.tb[s].resize((size_t)tbBytes + 64); ln.tbRow[s].resize(4096); ln.ops[s].resize(64); ln.act[s].resize(5 * 2);
             ln.ckpt[s].resize((size_t)64 * CK_WORDS(8, 128));
