@@ -428,7 +428,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - pos2) + (s32)(pos1 - bp.b1); else d = (s32)(bp.b2 - pos2);
             if (d != 0) continue;
             fin[j] = 1;                                      /* on an alignment committed earlier in the order: skipped for good (:1335) */
-            if (laneOf[j] >= 0) drop_lane(laneOf[j]);
+            if (laneOf[j] >= 0) { if (trace) fprintf(stderr, "[gx %.4f] retire a=%u pos1=%u (on alignment a=%d) while it held a lane\n", now(), j, pos1, ai); drop_lane(laneOf[j]); }
         }
     };
     if (G.obi == (int)n) retire_covered((int)n);
@@ -497,9 +497,9 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
      * a few milliseconds after the first launch and exact as soon as one truncated sweep has finished.  (Where the
      * homology ends earlier the estimate is too long, which only makes a later anchor wait for an earlier one.) */
     const double reachPrior = (double)tbLen / 250.0 + 64;    /* before anything is known: generous */
+    const double slackRows = getenv("LZB_GAP_SLACK") ? atof(getenv("LZB_GAP_SLACK")) : 1000.0;   /* margin around an expected reach, rows (tests: negative = start everything) */
     double reachTrunc = 0; bool reachExact = false;
     auto reach = [&]() -> double { return reachTrunc > 0 ? reachTrunc : reachPrior; };
-    std::vector<u8> uncertain(n, 0);                         /* started although an earlier open anchor may come to cover it */
 
     /* validate a DONE side against the alignments committed since its snapshot; returns 0 valid, 1 relaunched, -1 error */
     auto validate_side = [&](int z, int side) -> int {
@@ -674,18 +674,16 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (reachTrunc == 0) startDirty = true;        /* look again */
             }
             const bool calibrated = reachTrunc > 0;
-            int unsureRunning = 0;
-            for (int z = 0; z < have; z++) if (lanes[z].busy && uncertain[lanes[z].anchor]) unsureRunning++;
             const double rr = reach();
             u64 examined = 0;
             for (u64 j = hd; j < n && (freeLanes > 0 || have < W) && examined < 16384; j++) {
                 if (fin[j] || laneOf[j] >= 0) continue;
                 examined++;
-                bool unsure = false;
                 if (j != hd) {
-                    /* Will an earlier anchor that is still open cover this one?  (Scheduling only.)  Inside 0.96 of the
-                     * expected reach of an anchor that is itself safe: yes -- wait for it.  Near the edge of somebody's reach,
-                     * or inside the reach of an anchor that is itself unsure: start, but do not let it hold others back. */
+                    /* Will an earlier anchor that is still open come to cover this one, or end right next to it?  (Scheduling
+                     * only.)  Within its expected reach plus a margin: wait until it is committed -- this anchor is then either
+                     * skipped (:1330), or it starts with that alignment as a neighbour and its sweep towards it is short.  Started
+                     * now, the sweep would run its full length into rows the earlier alignment is about to claim. */
                     if (blocker[j] >= 0 && !fin[blocker[j]] && laneOf[blocker[j]] >= 0) continue;
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
@@ -698,16 +696,17 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                         if (llabs(di - dj) > 4000) continue;
                         const int side = apos1[j] < apos1[i] ? 0 : 1;
                         const double dist = fabs((double)apos1[j] - (double)apos1[i]);
-                        if (!calibrated) { if (dist < 2.5 * reachPrior) tooEarly = true; continue; }
+                        if (!calibrated) { if (slackRows >= 0 && dist < 2.5 * reachPrior) tooEarly = true; continue; }
                         const double ext = ln.s[side].phase == SIDE_DONE ? (double)ln.s[side].res.end1 : rr;
-                        /* (an estimate from progress reports is good to a percent; a finished sweep gives the row itself) */
-                        const double slack = reachExact || ln.s[side].phase == SIDE_DONE ? 0.004 * ext + 300 : 0.02 * ext + 300;
-                        if (dist <= ext - slack) { if (uncertain[i]) unsure = true; else blocker[j] = (int)i; }
-                        else if (dist <= ext + slack) unsure = true;
+                        /* (an estimate from progress reports is good to a percent or two; a finished sweep gives the row itself) */
+                        const double slack = (reachExact || ln.s[side].phase == SIDE_DONE ? 0.01 : 0.03) * ext + slackRows;
+                        if (slackRows >= 0 && dist <= ext + slack) {
+                            blocker[j] = (int)i;
+                            if (trace && j < hd + 400) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, ln.s[side].phase == SIDE_DONE ? "done" : "running");
+                        }
                     }
                     if (blocker[j] >= 0) continue;
                     if (tooEarly) { startDirty = true; continue; }
-                    if (unsure && unsureRunning >= std::max(2, W / 8)) continue;     /* keep most lanes for anchors that will be needed */
                 }
                 galn& y = G.al[j];
                 int coverer = -1;
@@ -715,8 +714,6 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (freeLanes == 0) { if (more_lanes()) return -1; if (freeLanes == 0) break; }
                 int fl = -1;
                 for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
-                uncertain[j] = unsure ? 1 : 0;
-                if (unsure) unsureRunning++;
                 if (start_anchor(fl, j)) return -1;
                 freeLanes--; progressed = true;
                 if (j != hd) G.st.speculated++;

@@ -86,6 +86,7 @@ static void parse_actions(lzb_seqfile* sf, char* act) {
                         sf->subset[sf->nsubset++] = dupstr(w);
                     }
                     fclose(nf);
+                    if (sf->nsubset == 0) lzb_die("contigs-of-interest file is empty: %s", nfName);      /* sequences.c:1204 */
                 }
                 else if (sscanf(p, "%u..%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = b; }
                 else if (sscanf(p, "%u#%u%c", &a, &b, &x) == 2) { sf->start = a; sf->end = a + b - 1; }
@@ -249,8 +250,16 @@ static int next_fasta(lzb_seqfile* sf, lzb_seq* out) {
     while ((ch = fgetc(sf->f)) != EOF) {
         if (prev == '\n' && ch == '>') { ungetc(ch, sf->f); break; }
         if (ch == '\n' || ch == '\r') { prev = '\n'; continue; }
-        if (isspace(ch)) { prev = ch; continue; }
-        if (!isalpha(ch)) lzb_die("bad fasta character in %s (ascii %02X)", sf->filename, ch);
+        if (isspace(ch) || (ch >= '0' && ch <= '9')) { prev = ch; continue; }    /* char_to_fasta_type sequences.c:580-598: blanks and digits are skipped */
+        if (!strchr("ACGTNXacgtnx", ch)) {
+            /* the ambiguity codes BDHKMRSVWY need --ambiguous=iupac, which this front end does not have; anything else is never legal (:2476-2485) */
+            char what[40];
+            if (ch >= 'A' && ch <= 'Z') snprintf(what, sizeof what, "uppercase %c", ch);
+            else if (ch >= 'a' && ch <= 'z') snprintf(what, sizeof what, "lowercase %c", ch);
+            else snprintf(what, sizeof what, "ascii %02X", ch);
+            if (hdr[0]) lzb_die("bad fasta character in %s, %s (%s)\nremove or replace non-ACGTN characters or consider using --ambiguous=iupac", sf->filename, hdr, what);
+            lzb_die("bad fasta character in %s (%s)\nremove or replace non-ACGTN characters or consider using --ambiguous=iupac", sf->filename, what);
+        }
         if (n + 1 > cap) { cap *= 2; v = realloc(v, cap); }
         v[n++] = (uint8_t)ch; prev = ch;
     }
@@ -366,13 +375,17 @@ static int next_nib(lzb_seqfile* sf, lzb_seq* out) {
 static int next_single(lzb_seqfile* sf, lzb_seq* out) {
     memset(out, 0, sizeof *out);
     for (;;) {
+        if (!sf->is2bit && sf->subset && sf->subsetNext >= sf->nsubset) return 0;      /* every wanted sequence has been delivered */
         int ok = sf->is2bit ? next_2bit(sf, out) : sf->isNib ? next_nib(sf, out) : sf->isFastq ? next_fastq(sf, out) : next_fasta(sf, out);
-        if (!ok) return 0;
+        if (!ok) {
+            if (!sf->is2bit && sf->subset && sf->subsetNext < sf->nsubset)
+                lzb_die("%s does not contain (or contains out of order)\n         the sequence \"%s\"", sf->filename, sf->subset[sf->subsetNext]);
+            return 0;
+        }
         sf->contig++;
         if (sf->is2bit || !sf->subset) break;
-        int wanted = 0;                                  /* FASTA: deliver the named sequences, skip the others */
-        for (uint32_t k = 0; k < sf->nsubset && !wanted; k++) wanted = !strcmp(sf->subset[k], out->shortHeader);
-        if (wanted) break;
+        /* FASTA: the names file is followed in order -- skip ahead to the next wanted name (find_next_fasta_coi sequences.c:5160ff) */
+        if (sf->subsetNext < sf->nsubset && !strcmp(sf->subset[sf->subsetNext], out->shortHeader)) { sf->subsetNext++; break; }
         lzb_seq_free(out); memset(out, 0, sizeof *out);
     }
     out->contig = sf->is2bit && (sf->contigName || sf->subset) ? sf->lastIx + 1 : sf->contig;   /* ordinal within the file (sequences.c:3677ff) */

@@ -125,7 +125,8 @@ struct emu_backend {
 static void expand(std::string& out, const u32* ops, u32 n) { for (u32 k = 0; k < n; k++) out.append(ops[k] >> 2, "?IDS"[ops[k] & 3]); }
 
 // homologous pair with `blocks` rearranged pieces: enough structure for neighbours on both sides, above and below
-static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int W, u32 every, int shuffle, int dupes) {
+static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int W, u32 every, int shuffle, int dupes, const char* slack = "-1") {
+    setenv("LZB_GAP_SLACK", slack, 1);     // -1: every anchor is started as soon as a lane is free (most speculation); else the margin in rows
     std::string t, q; const char* acgt = "ACGT";
     for (u32 i = 0; i < len; i++) t.push_back(acgt[rnd() & 3]);
     auto channel = [&](const std::string& src, std::string& dst) {
@@ -202,10 +203,12 @@ int main(int argc, char** argv) {
     bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 0);      // 16 lanes: every sweep speculative, resumed from checkpoints
     bad += one_case(n++, 6000, 0.05, 0.012, 50000, 9400, 0, 8, 32, 1, 2);       // repeats: neighbours across anchor rows, --noytrim
     bad += one_case(n++, 5000, 0.04, 0.010, 80000, 6000, 1, 3, 96, 1, 1);       // fewer lanes than anchors worth starting
+    bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 1, "20"); // the product's waiting rule (anchors near an expected reach wait for the commit)
     if (big) {
         bad += one_case(n++, 20000, 0.04, 0.010, 100000, 9400, 1, 32, 64, 1, 3);
         bad += one_case(n++, 12000, 0.06, 0.015, 70000, 9400, 1, 24, 128, 1, 4);
         bad += one_case(n++, 12000, 0.04, 0.010, 70000, 9400, 0, 5, 32, 0, 2);
+        bad += one_case(n++, 20000, 0.04, 0.010, 100000, 9400, 1, 32, 64, 1, 3, "30");
     }
     printf("%d cases, %d mismatching\n", n, bad);
     return bad ? 1 : 0;
