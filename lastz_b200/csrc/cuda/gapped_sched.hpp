@@ -190,6 +190,7 @@ struct gx_side {
 };
 struct gx_lane_state {
     bool busy; u64 anchor; segref left1, right1;   /* the anchor's neighbours the sweeps were started with */
+    int deferSide; u64 deferOn;         /* this sweep is held back until anchor deferOn is resolved (-1: none) */
     gx_side s[2];                       /* 0 = reverse (left) sweep, 1 = forward (right) sweep */
 };
 
@@ -290,7 +291,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     int firstMode = 0;
     { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3) firstMode = mdv; } }
     std::vector<gx_lane_state> lanes(W);
-    for (auto& ln : lanes) { ln.busy = false; ln.s[0].phase = ln.s[1].phase = SIDE_IDLE; }
+    for (auto& ln : lanes) { ln.busy = false; ln.s[0].phase = ln.s[1].phase = SIDE_IDLE; ln.deferSide = -1; }
     std::vector<int> laneOf(n, -1);
     std::vector<u8> fin(n, 0);                               /* 1 = skipped / committed / dropped */
     u32 tokenCounter = 0;
@@ -504,7 +505,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     /* validate a DONE side against the alignments committed since its snapshot; returns 0 valid, 1 relaunched, -1 error */
     auto validate_side = [&](int z, int side) -> int {
         gx_lane_state& ln = lanes[z]; gx_side& sd = ln.s[side];
-        if (sd.snapshot == G.committed.size()) return 0;
+        if (sd.phase != SIDE_DONE || sd.snapshot == G.committed.size()) return 0;
         const u32 aPos1 = apos1[ln.anchor];
         u32 firstRow = 0xFFFFFFFFu;                           /* first sweep row a new alignment shows up in */
         for (size_t k = sd.snapshot; k < G.committed.size(); k++) {
@@ -527,14 +528,14 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         return 1;
     };
 
-    auto start_anchor = [&](int z, u64 j) -> int {
+    auto start_anchor = [&](int z, u64 j, int deferSide, u64 deferOn) -> int {
         gx_lane_state& ln = lanes[z]; galn& y = G.al[j];
-        ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1;
+        ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1; ln.deferSide = deferSide; ln.deferOn = deferOn;
         laneOf[j] = z;
         for (int side = 0; side < 2; side++) { ln.s[side].mode = firstMode; ln.s[side].ckptCount = 0; ln.s[side].ckptEvery = 0; ln.s[side].res.ops.clear(); ln.s[side].prog0Rows = ln.s[side].prog0Used = 0; }
         B.job(z, 0)->abort = 0; B.job(z, 1)->abort = 0;
-        if (trace) fprintf(stderr, "[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size());
-        if (queue_side(z, 0, -1, false) || queue_side(z, 1, -1, false)) return -1;
+        if (trace) fprintf(stderr, "[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu held=%d\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size(), deferSide);
+        for (int side = 0; side < 2; side++) { ln.s[side].phase = SIDE_IDLE; if (side != deferSide && queue_side(z, side, -1, false)) return -1; }
         return 0;
     };
 
@@ -587,12 +588,25 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         for (int z = 0; z < have; z++) {
             gx_lane_state& ln = lanes[z];
             if (!ln.busy) continue;
+            if (ln.deferSide >= 0 && (fin[ln.deferOn] || laneOf[ln.deferOn] < 0)) {
+                /* the anchor this sweep was held back for is resolved: the sweep now starts against its alignment */
+                const int side = ln.deferSide; ln.deferSide = -1;
+                galn& y0 = G.al[ln.anchor]; int cov = -1;
+                if (!anchor_neighbours(G, y0, &cov)) return fail("internal error: anchor %llu lies on alignment %d but was not retired", (unsigned long long)ln.anchor, cov);
+                const bool same = y0.left1.al == ln.left1.al && y0.left1.sg == ln.left1.sg && y0.right1.al == ln.right1.al && y0.right1.sg == ln.right1.sg;
+                if (!same && ln.s[1 - side].phase == SIDE_RUNNING) { ln.deferSide = side; continue; }      /* new neighbours: both sweeps restart once the running one is back */
+                ln.left1 = y0.left1; ln.right1 = y0.right1;
+                if (!same) { ln.s[1 - side].res.ops.clear(); if (queue_side(z, 1 - side, -1, false)) return -1; G.st.redone++; pfRestarts++; }
+                if (queue_side(z, side, -1, false)) return -1;
+                progressed = true;
+                continue;
+            }
             if (ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING) continue;
-            if (ln.s[0].snapshot == G.committed.size() && ln.s[1].snapshot == G.committed.size()) continue;
+            if ((ln.s[0].phase != SIDE_DONE || ln.s[0].snapshot == G.committed.size()) && (ln.s[1].phase != SIDE_DONE || ln.s[1].snapshot == G.committed.size())) continue;
             /* an alignment across the anchor's row may be a new neighbour (or cover the anchor: retire_covered saw to that) */
             galn& y = G.al[ln.anchor];
             bool crossed = false;
-            const size_t from = std::min(ln.s[0].snapshot, ln.s[1].snapshot);
+            const size_t from = std::min(ln.s[0].phase == SIDE_DONE ? ln.s[0].snapshot : G.committed.size(), ln.s[1].phase == SIDE_DONE ? ln.s[1].snapshot : G.committed.size());
             for (size_t k = from; k < G.committed.size() && !crossed; k++) { galn& x = G.al[G.committed[k]]; if (x.pos1 <= apos1[ln.anchor] && x.end1 >= apos1[ln.anchor]) crossed = true; }
             if (crossed) {
                 int coverer = -1;
@@ -601,7 +615,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     if (trace) fprintf(stderr, "[gx %.4f] a=%llu new neighbours: restart\n", now(), (unsigned long long)ln.anchor);
                     G.st.redone += 2; pfRestarts += 2;
                     ln.left1 = y.left1; ln.right1 = y.right1;
-                    for (int side = 0; side < 2; side++) { ln.s[side].res.ops.clear(); if (queue_side(z, side, -1, false)) return -1; }
+                    for (int side = 0; side < 2; side++) { ln.s[side].res.ops.clear(); if (side != ln.deferSide && queue_side(z, side, -1, false)) return -1; }
                     progressed = true;
                     continue;
                 }
@@ -679,6 +693,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             for (u64 j = hd; j < n && (freeLanes > 0 || have < W) && examined < 16384; j++) {
                 if (fin[j] || laneOf[j] >= 0) continue;
                 examined++;
+                int deferSide = -1; u64 deferOn = 0;
                 if (j != hd) {
                     /* Will an earlier anchor that is still open come to cover this one, or end right next to it?  (Scheduling
                      * only.)  Within its expected reach plus a margin: wait until it is committed -- this anchor is then either
@@ -687,7 +702,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     if (blocker[j] >= 0 && !fin[blocker[j]] && laneOf[blocker[j]] >= 0) continue;
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
-                    bool tooEarly = false;
+                    bool tooEarly = false; deferSide = -1; deferOn = 0;
                     for (int z = 0; z < have && blocker[j] < 0; z++) {
                         gx_lane_state& ln = lanes[z];
                         if (!ln.busy || ln.anchor >= j) continue;
@@ -700,10 +715,16 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                         const double ext = ln.s[side].phase == SIDE_DONE ? (double)ln.s[side].res.end1 : rr;
                         /* (an estimate from progress reports is good to a percent or two; a finished sweep gives the row itself) */
                         const double slack = (reachExact || ln.s[side].phase == SIDE_DONE ? 0.01 : 0.03) * ext + slackRows;
-                        if (slackRows >= 0 && dist <= ext + slack) {
-                            blocker[j] = (int)i;
-                            if (trace && j < hd + 400) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, ln.s[side].phase == SIDE_DONE ? "done" : "running");
+                        if (slackRows < 0) continue;
+                        if (dist <= ext - slack) blocker[j] = (int)i;                  /* will be covered: wait */
+                        else if (dist <= ext + slack) {
+                            /* at the edge of i's reach: covered or not, nobody knows yet.  The sweep AWAY from i is long either
+                             * way and starts now; the sweep towards i is held back until i is committed (it is short then) */
+                            const int facing = apos1[j] > apos1[i] ? 0 : 1;
+                            if (deferSide >= 0 && deferSide != facing) blocker[j] = (int)i;   /* edges on both sides: nothing to start yet */
+                            else { deferSide = facing; deferOn = i; }
                         }
+                        if (blocker[j] >= 0 && trace && j < hd + 400) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, ln.s[side].phase == SIDE_DONE ? "done" : "running");
                     }
                     if (blocker[j] >= 0) continue;
                     if (tooEarly) { startDirty = true; continue; }
@@ -714,7 +735,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (freeLanes == 0) { if (more_lanes()) return -1; if (freeLanes == 0) break; }
                 int fl = -1;
                 for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
-                if (start_anchor(fl, j)) return -1;
+                if (start_anchor(fl, j, deferSide, deferOn)) return -1;
                 freeLanes--; progressed = true;
                 if (j != hd) G.st.speculated++;
             }
