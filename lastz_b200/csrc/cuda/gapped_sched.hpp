@@ -177,7 +177,7 @@ static s32 rescore(gx& G, u32 p1, u32 p2, lzb_editscript* s) {
 static segref dev_ref(gx& G, segref r) { segref o = NOSEG; if (r.al >= 0) { o.al = G.al[r.al].devIx; o.sg = r.sg; } return o; }
 
 /* ---- lanes ---- */
-enum { SIDE_IDLE = 0, SIDE_RUNNING = 1, SIDE_DONE = 2 };
+enum { SIDE_IDLE = 0, SIDE_RUNNING = 1, SIDE_DONE = 2, SIDE_PAUSED = 3 };
 struct gx_side {
     int phase;
     size_t snapshot;                    /* committed.size() the sweep (or its valid prefix) was computed against */
@@ -187,10 +187,13 @@ struct gx_side {
     dp_result res;                      /* valid when DONE */
     u32 ckptCount, ckptEvery;           /* checkpoints the finished sweep left behind */
     u32 prog0Rows, prog0Used;           /* first progress report seen from the running sweep */
+    u64 pausedOn;                       /* PAUSED: the earlier anchor whose alignment the sweep stopped short of */
 };
 struct gx_lane_state {
     bool busy; u64 anchor; segref left1, right1;   /* the anchor's neighbours the sweeps were started with */
     int deferSide; u64 deferOn;         /* this sweep is held back until anchor deferOn is resolved (-1: none) */
+    bool unsure;                        /* started from the edge of another anchor's reach: may yet be skipped */
+    double edgeMax[2];                  /* farthest anchor started at the edge of this anchor's reach, per side */
     gx_side s[2];                       /* 0 = reverse (left) sweep, 1 = forward (right) sweep */
 };
 
@@ -340,6 +343,11 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         return 0;
     };
 
+    const double slackRows = getenv("LZB_GAP_SLACK") ? atof(getenv("LZB_GAP_SLACK")) : 1000.0;   /* margin around an expected reach, rows (tests: negative = start everything) */
+    const bool rowLimits = !(getenv("LZB_GAP_ROWLIMIT") && !atoi(getenv("LZB_GAP_ROWLIMIT")));
+    double reachShared = 0;                                  /* the scheduler's current estimate of a sweep's length (0: none yet) */
+    auto reachKnown = [&]() { return reachShared > 0; };
+    auto reachNow = [&]() { return reachShared; };
     /* queue one sweep of lane z: fresh (rec < 0), resumed from checkpoint record rec, or traceback only */
     auto queue_side = [&](int z, int side, int rec, bool tbOnly) -> int {
         gx_lane_state& ln = lanes[z]; gx_side& sd = ln.s[side];
@@ -389,6 +397,31 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             J.tbLen = tbLen;
             J.resume = rec;
             if (rec < 0) { J.progRows = 0; J.progUsed = 0; }
+            /* A sweep towards an EARLIER anchor that is still open will be cut short by that anchor's alignment.  Stop it a little
+             * beyond where that is expected; it goes on from a checkpoint when the alignment is known (scheduling only: a
+             * sweep that stops too early just continues, one that is not stopped is cut back like any other). */
+            J.rowLimit = 0; sd.pausedOn = 0;
+            if (rowLimits && reachKnown() && sd.mode == 0) {
+                double bestDist = 1e30; int bi = -1;
+                const s64 dj = (s64)aPos1 - (s64)aPos2;
+                for (int zz = 0; zz < (int)lanes.size(); zz++) {
+                    gx_lane_state& lo = lanes[zz];
+                    if (!lo.busy || lo.anchor >= ln.anchor) continue;
+                    const u32 ip = apos1[lo.anchor];
+                    if ((side == 0) != (ip < aPos1) || ip == aPos1) continue;
+                    if (llabs(((s64)ip - (s64)apos2[lo.anchor]) - dj) > 4000) continue;
+                    const double d = fabs((double)ip - (double)aPos1);
+                    if (d < bestDist) { bestDist = d; bi = zz; }
+                }
+                if (bi >= 0) {
+                    gx_side& fs = lanes[bi].s[1 - side];             /* its sweep that comes this way */
+                    const double ext = fs.phase == SIDE_DONE ? (double)fs.res.end1 : reachNow();
+                    const double every_ = (double)B.ckpt_every();
+                    const double lim = std::max(bestDist - ext + 0.02 * ext + 3 * std::max(slackRows, 0.0), 4 * every_);
+                    const double already = rec >= 0 ? ((double)rec + 1) * every_ : 0;
+                    if (lim < 0.9 * reachNow() && lim > already + 2 * every_) { J.rowLimit = (u32)lim; sd.pausedOn = lanes[bi].anchor; }
+                }
+            }
             sd.snapshot = G.committed.size();
         }
         (void)m;
@@ -498,39 +531,53 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
      * a few milliseconds after the first launch and exact as soon as one truncated sweep has finished.  (Where the
      * homology ends earlier the estimate is too long, which only makes a later anchor wait for an earlier one.) */
     const double reachPrior = (double)tbLen / 250.0 + 64;    /* before anything is known: generous */
-    const double slackRows = getenv("LZB_GAP_SLACK") ? atof(getenv("LZB_GAP_SLACK")) : 1000.0;   /* margin around an expected reach, rows (tests: negative = start everything) */
-    double reachTrunc = 0; bool reachExact = false;
+    double reachTrunc = 0; bool reachExact = false; u32 reachSeen = 0;   /* rows the current estimate was taken over */
     auto reach = [&]() -> double { return reachTrunc > 0 ? reachTrunc : reachPrior; };
 
-    /* validate a DONE side against the alignments committed since its snapshot; returns 0 valid, 1 relaunched, -1 error */
-    auto validate_side = [&](int z, int side) -> int {
+    /* first row of lane z's sweep `side` in which an alignment committed since the sweep's snapshot shows up (0xFFFFFFFF: none) */
+    auto first_touched_row = [&](int z, int side) -> u32 {
         gx_lane_state& ln = lanes[z]; gx_side& sd = ln.s[side];
-        if (sd.phase != SIDE_DONE || sd.snapshot == G.committed.size()) return 0;
         const u32 aPos1 = apos1[ln.anchor];
-        u32 firstRow = 0xFFFFFFFFu;                           /* first sweep row a new alignment shows up in */
+        u32 firstRow = 0xFFFFFFFFu;
         for (size_t k = sd.snapshot; k < G.committed.size(); k++) {
             galn& x = G.al[G.committed[k]];
             if (side == 1) { if (x.pos1 > aPos1) firstRow = std::min(firstRow, x.pos1 - aPos1); }
             else { if (x.end1 < aPos1) firstRow = std::min(firstRow, aPos1 - x.end1); }
         }
+        return firstRow;
+    };
+    /* last checkpoint whose row lies before firstRow: record r holds the state after row (r+1)*every; -1: none */
+    auto record_before = [&](gx_side& sd, u32 firstRow) -> int {
+        if (sd.ckptCount == 0 || sd.ckptEvery == 0) return -1;
+        const u32 full = firstRow == 0xFFFFFFFFu ? sd.ckptCount : (firstRow - 1) / sd.ckptEvery;     /* checkpoints at rows <= firstRow - 1 */
+        return (int)std::min<u32>(full, sd.ckptCount) - 1;
+    };
+    /* validate a DONE side against the alignments committed since its snapshot; returns 0 valid, 1 relaunched, -1 error */
+    auto validate_side = [&](int z, int side) -> int {
+        gx_lane_state& ln = lanes[z]; gx_side& sd = ln.s[side];
+        if (sd.phase != SIDE_DONE || sd.snapshot == G.committed.size()) return 0;
+        const u32 firstRow = first_touched_row(z, side);
         if (firstRow > sd.res.rows) { sd.snapshot = G.committed.size(); return 0; }      /* the sweep ended before that row */
         G.st.redone++;
-        /* last checkpoint whose row lies before firstRow: record r holds the state after row (r+1)*every */
-        int rec = -1;
-        if (sd.ckptCount > 0 && sd.ckptEvery > 0) {
-            const u32 full = (firstRow - 1) / sd.ckptEvery;     /* checkpoints at rows <= firstRow - 1 */
-            rec = (int)std::min<u32>(full, sd.ckptCount) - 1;
-        }
+        const int rec = record_before(sd, firstRow);
         if (rec >= 0) pfResumes++; else pfRestarts++;
         if (trace) fprintf(stderr, "[gx %.4f] a=%llu side=%d touched at row %u of %u: %s %d\n", now(), (unsigned long long)ln.anchor, side, firstRow, sd.res.rows, rec >= 0 ? "resume from record" : "restart", rec);
         sd.res.ops.clear();
         if (queue_side(z, side, rec, false)) return -1;
         return 1;
     };
+    /* a sweep that stopped short of an earlier anchor's expected alignment goes on once that anchor is resolved */
+    auto continue_paused = [&](int z, int side) -> int {
+        gx_lane_state& ln = lanes[z]; gx_side& sd = ln.s[side];
+        const int rec = record_before(sd, first_touched_row(z, side));
+        if (trace) fprintf(stderr, "[gx %.4f] a=%llu side=%d paused at row %u goes on from record %d\n", now(), (unsigned long long)ln.anchor, side, sd.res.rows, rec);
+        pfResumes++;
+        return queue_side(z, side, rec, false);
+    };
 
     auto start_anchor = [&](int z, u64 j, int deferSide, u64 deferOn) -> int {
         gx_lane_state& ln = lanes[z]; galn& y = G.al[j];
-        ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1; ln.deferSide = deferSide; ln.deferOn = deferOn;
+        ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1; ln.deferSide = deferSide; ln.deferOn = deferOn; ln.unsure = deferSide >= 0; ln.edgeMax[0] = ln.edgeMax[1] = 0;
         laneOf[j] = z;
         for (int side = 0; side < 2; side++) { ln.s[side].mode = firstMode; ln.s[side].ckptCount = 0; ln.s[side].ckptEvery = 0; ln.s[side].res.ops.clear(); ln.s[side].prog0Rows = ln.s[side].prog0Used = 0; }
         B.job(z, 0)->abort = 0; B.job(z, 1)->abort = 0;
@@ -560,7 +607,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         const u32* ops = B.ops(z, side);
         r.ops.assign(ops, ops + J.nops);
         sd.ckptCount = J.ckptCount; sd.ckptEvery = sd.mode == 0 ? B.ckpt_every() : 0;
-        sd.phase = SIDE_DONE;
+        sd.phase = J.status == DP_PAUSED ? SIDE_PAUSED : SIDE_DONE;
         if (r.status == DP_TRUNCATED) { reachTrunc = reachExact ? 0.8 * reachTrunc + 0.2 * r.rows : (double)r.rows; if (!reachExact) startDirty = true; reachExact = true; }
         if (trace) fprintf(stderr, "[gx %.4f] done a=%llu side=%d rows=%u end1=%u status=%d mode=%d ckpts=%u\n", now(), (unsigned long long)ln.anchor, side, r.rows, r.end1, r.status, sd.mode, sd.ckptCount);
         return 0;
@@ -602,11 +649,17 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 continue;
             }
             if (ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING) continue;
-            if ((ln.s[0].phase != SIDE_DONE || ln.s[0].snapshot == G.committed.size()) && (ln.s[1].phase != SIDE_DONE || ln.s[1].snapshot == G.committed.size())) continue;
+            bool stale = false, paused = false;
+            for (int side = 0; side < 2; side++) {
+                if (ln.s[side].phase == SIDE_DONE && ln.s[side].snapshot != G.committed.size()) stale = true;
+                if (ln.s[side].phase == SIDE_PAUSED && (fin[ln.s[side].pausedOn] || laneOf[ln.s[side].pausedOn] < 0)) paused = true;
+            }
+            if (!stale && !paused) continue;
             /* an alignment across the anchor's row may be a new neighbour (or cover the anchor: retire_covered saw to that) */
             galn& y = G.al[ln.anchor];
             bool crossed = false;
-            const size_t from = std::min(ln.s[0].phase == SIDE_DONE ? ln.s[0].snapshot : G.committed.size(), ln.s[1].phase == SIDE_DONE ? ln.s[1].snapshot : G.committed.size());
+            const size_t from = std::min(ln.s[0].phase == SIDE_DONE || ln.s[0].phase == SIDE_PAUSED ? ln.s[0].snapshot : G.committed.size(),
+                                         ln.s[1].phase == SIDE_DONE || ln.s[1].phase == SIDE_PAUSED ? ln.s[1].snapshot : G.committed.size());
             for (size_t k = from; k < G.committed.size() && !crossed; k++) { galn& x = G.al[G.committed[k]]; if (x.pos1 <= apos1[ln.anchor] && x.end1 >= apos1[ln.anchor]) crossed = true; }
             if (crossed) {
                 int coverer = -1;
@@ -620,7 +673,13 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     continue;
                 }
             }
-            for (int side = 0; side < 2; side++) { const int rc = validate_side(z, side); if (rc < 0) return -1; if (rc) progressed = true; }
+            for (int side = 0; side < 2; side++) {
+                if (ln.s[side].phase == SIDE_PAUSED) {
+                    if (fin[ln.s[side].pausedOn] || laneOf[ln.s[side].pausedOn] < 0) { if (continue_paused(z, side)) return -1; progressed = true; }
+                    continue;
+                }
+                const int rc = validate_side(z, side); if (rc < 0) return -1; if (rc) progressed = true;
+            }
         }
         if (prof) pfValidate += now() - t0;
         /* 3. commit the head anchor while it is ready */
@@ -670,8 +729,9 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     freeLanes = 1;
                 } else startDirty = true;                     /* look again when a sweep has finished */
             }
-            /* no sweep has said yet how far sweeps go: the running ones report their progress.  Two reports of one sweep give
-             * the traceback bytes a row takes once the band has settled, hence the row where the traceback will run out. */
+            /* no sweep has finished yet to say how far sweeps go: the running ones report their progress.  Two reports of one
+             * sweep give the traceback bytes a row takes once the band has settled, hence the row where the traceback will
+             * run out; the longer the sweep has run, the better the estimate. */
             if (!reachExact) {
                 for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
                     gx_side& sd = lanes[z].s[side];
@@ -680,54 +740,64 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     const u32 pr = J.progRows, pu = J.progUsed;
                     if (J.resume >= 0 || pr < 2048 || pu == 0) continue;
                     if (sd.prog0Rows == 0) { sd.prog0Rows = pr; sd.prog0Used = pu; continue; }
-                    if (pr < sd.prog0Rows + 4096 || pu <= sd.prog0Used) continue;
+                    if (pr < sd.prog0Rows + 4096 || pu <= sd.prog0Used || pr - sd.prog0Rows <= reachSeen) continue;
                     const double perRow = (double)(pu - sd.prog0Used) / (double)(pr - sd.prog0Rows);
-                    const double est = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
-                    if (reachTrunc == 0 || est < reachTrunc) reachTrunc = est;
+                    reachTrunc = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
+                    reachSeen = pr - sd.prog0Rows;
                 }
-                if (reachTrunc == 0) startDirty = true;        /* look again */
+                startDirty = true;                             /* look again: the estimate sharpens */
             }
             const bool calibrated = reachTrunc > 0;
             const double rr = reach();
+            reachShared = calibrated ? rr : 0;
+            /* how far off the expected reach may be: a finished sweep gives the row itself (sweeps of one call end within
+             * a few hundred rows of each other); an estimate is as good as the stretch of rows it was taken over */
+            const double slackFrac = reachExact ? 0.003 : reachSeen >= 65536 ? 0.005 : reachSeen >= 16384 ? 0.012 : 0.03;
             u64 examined = 0;
             for (u64 j = hd; j < n && (freeLanes > 0 || have < W) && examined < 16384; j++) {
                 if (fin[j] || laneOf[j] >= 0) continue;
                 examined++;
                 int deferSide = -1; u64 deferOn = 0;
-                if (j != hd) {
-                    /* Will an earlier anchor that is still open come to cover this one, or end right next to it?  (Scheduling
-                     * only.)  Within its expected reach plus a margin: wait until it is committed -- this anchor is then either
-                     * skipped (:1330), or it starts with that alignment as a neighbour and its sweep towards it is short.  Started
-                     * now, the sweep would run its full length into rows the earlier alignment is about to claim. */
+                if (j != hd && slackRows >= 0) {
+                    /* Will an earlier anchor that is still open come to cover this one?  (Scheduling only.)
+                     *   well inside its expected reach: yes -- wait for its commit (the reference skips such anchors, :1330);
+                     *   at the edge of its reach: nobody knows yet.  The sweep AWAY from it is long either way and starts now, the
+                     *     sweep towards it is held back until it is committed (short then).  Of the anchors at one edge only those
+                     *     can matter that lie farther out than every better-scoring one there (a better one farther out covers the
+                     *     rest whether the earlier anchor reaches it or not), so the others wait as well;
+                     *   an anchor started from such an edge may yet be skipped, so it holds nobody back. */
                     if (blocker[j] >= 0 && !fin[blocker[j]] && laneOf[blocker[j]] >= 0) continue;
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
-                    bool tooEarly = false; deferSide = -1; deferOn = 0;
+                    bool tooEarly = false; int edgeLane = -1, edgeSide = 0; double edgeDist = 0; int edges = 0;
                     for (int z = 0; z < have && blocker[j] < 0; z++) {
                         gx_lane_state& ln = lanes[z];
-                        if (!ln.busy || ln.anchor >= j) continue;
+                        if (!ln.busy || ln.anchor >= j || ln.unsure) continue;
                         const u64 i = ln.anchor;
                         const s64 di = (s64)apos1[i] - (s64)apos2[i];
                         if (llabs(di - dj) > 4000) continue;
                         const int side = apos1[j] < apos1[i] ? 0 : 1;
                         const double dist = fabs((double)apos1[j] - (double)apos1[i]);
-                        if (!calibrated) { if (slackRows >= 0 && dist < 2.5 * reachPrior) tooEarly = true; continue; }
-                        const double ext = ln.s[side].phase == SIDE_DONE ? (double)ln.s[side].res.end1 : rr;
-                        /* (an estimate from progress reports is good to a percent or two; a finished sweep gives the row itself) */
-                        const double slack = (reachExact || ln.s[side].phase == SIDE_DONE ? 0.01 : 0.03) * ext + slackRows;
-                        if (slackRows < 0) continue;
-                        if (dist <= ext - slack) blocker[j] = (int)i;                  /* will be covered: wait */
+                        if (!calibrated) { if (dist < 2.5 * reachPrior) tooEarly = true; continue; }
+                        const bool known = ln.s[side].phase == SIDE_DONE;
+                        const double ext = known ? (double)ln.s[side].res.end1 : rr;
+                        const double slack = (known ? 0.003 : slackFrac) * ext + slackRows;
+                        if (dist <= ext - slack) blocker[j] = (int)i;
                         else if (dist <= ext + slack) {
-                            /* at the edge of i's reach: covered or not, nobody knows yet.  The sweep AWAY from i is long either
-                             * way and starts now; the sweep towards i is held back until i is committed (it is short then) */
-                            const int facing = apos1[j] > apos1[i] ? 0 : 1;
-                            if (deferSide >= 0 && deferSide != facing) blocker[j] = (int)i;   /* edges on both sides: nothing to start yet */
-                            else { deferSide = facing; deferOn = i; }
+                            if (!known && slackFrac > 0.012) tooEarly = true;        /* decide when the estimate is sharper */
+                            else if (dist <= ln.edgeMax[side]) blocker[j] = (int)i;     /* a better anchor farther out has this edge */
+                            else { edges++; edgeLane = z; edgeSide = side; edgeDist = dist; }
                         }
-                        if (blocker[j] >= 0 && trace && j < hd + 400) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, ln.s[side].phase == SIDE_DONE ? "done" : "running");
+                        if (blocker[j] >= 0 && trace) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, known ? "done" : "running");
                     }
                     if (blocker[j] >= 0) continue;
                     if (tooEarly) { startDirty = true; continue; }
+                    if (edges > 1) { blocker[j] = (int)lanes[edgeLane].anchor; continue; }     /* at two edges at once: nothing to start yet */
+                    if (edges == 1) {
+                        gx_lane_state& li = lanes[edgeLane];
+                        li.edgeMax[edgeSide] = edgeDist;
+                        deferSide = apos1[j] > apos1[li.anchor] ? 0 : 1; deferOn = li.anchor;
+                    }
                 }
                 galn& y = G.al[j];
                 int coverer = -1;

@@ -19,7 +19,7 @@ struct dalign {                       /* device view of a committed alignment (g
     segref left1, right1, left2, right2;
 };
 
-enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_ACT = 5, DP_ABORTED = 6 };
+enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_ACT = 5, DP_ABORTED = 6, DP_PAUSED = 7 };
 
 /* jobs of one launch: block b runs jobs[ll.ix[b]] (the list travels in the kernel's parameter space, so a launch
  * needs no device-side table that would have to outlive it) */
@@ -47,6 +47,8 @@ struct dp_job {
     const dalign* al;                 /* alignment table (append-only: a sweep only follows indices it was given) */
     u32* ckpt; u32 ckptCap, ckptEvery;/* checkpoint records (k_ydrop_mw only); ckptCap = 0: none taken */
     int resume;                       /* -1 fresh sweep, else the checkpoint record to continue from */
+    u32 rowLimit;                     /* stop (DP_PAUSED) before this row: the host expects an earlier anchor's alignment there and
+                                         continues the sweep from a checkpoint once that alignment is known (0: no limit) */
     int tbOnly;                       /* nonzero: the sweep is done (end1/end2/status below are its results); redo the traceback walk */
     u32* dbg; u32 dbgCap;             /* LZB_DP_DEBUG: per-row {LY, colEnd, best, used} for kernel-vs-kernel diffs */
     u32 token;                        /* written to `done` after everything else */

@@ -262,6 +262,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     u32* const ckpt = J->ckpt; const u32 ckptCap = J->ckptCap, ckptEvery = J->ckptEvery;
     u32 ckptCount = 0;
     const int resume = J->resume, tbOnly = J->tbOnly;
+    const u32 rowLimit = J->rowLimit ? J->rowLimit : 0xFFFFFFFFu;
     const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
     u32* const dbg = J->dbg; const u32 dbgCap = J->dbgCap;
     u32 lLim = 0, rLim = 0; int lTyp = 0, rTyp = 0;
@@ -333,6 +334,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     __syncthreads();
     if (status == DP_OK && !tbOnly)
     for (row = row0; row <= M; row++) {
+        if (row >= rowLimit) { status = DP_PAUSED; break; }
         if ((row & 255u) == 0 && J->abort) { status = DP_ABORTED; break; }   /* the anchor was retired (mapped host memory: looked at rarely) */
         /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every thread, same values) ---- */
         if (!rev) {

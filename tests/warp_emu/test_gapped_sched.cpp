@@ -204,6 +204,7 @@ int main(int argc, char** argv) {
     bad += one_case(n++, 6000, 0.05, 0.012, 50000, 9400, 0, 8, 32, 1, 2);       // repeats: neighbours across anchor rows, --noytrim
     bad += one_case(n++, 5000, 0.04, 0.010, 80000, 6000, 1, 3, 96, 1, 1);       // fewer lanes than anchors worth starting
     bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 1, "20"); // the product's waiting rule (anchors near an expected reach wait for the commit)
+    bad += one_case(n++, 14000, 0.04, 0.010, 200000, 9400, 1, 16, 32, 1, 1, "10"); // sweeps long enough to be stopped short of an earlier anchor's alignment and continued
     if (big) {
         bad += one_case(n++, 20000, 0.04, 0.010, 100000, 9400, 1, 32, 64, 1, 3);
         bad += one_case(n++, 12000, 0.06, 0.015, 70000, 9400, 1, 24, 128, 1, 4);
