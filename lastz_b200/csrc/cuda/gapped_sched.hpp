@@ -435,10 +435,12 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
 
     /* retire the anchors that lie on alignment `ai` (index into G.al; n = the trivial self alignment) */
     bool startDirty = true;                                  /* something happened that may let another anchor start */
+    std::vector<u32>* pendp = NULL; bool* pendSortedp = NULL; bool pendReady = false;   /* (the list is declared further down) */
     /* take a lane away from its anchor: at once if nothing of it is running, else when its sweeps have stopped */
     auto drop_lane = [&](int z) {
         gx_lane_state& ln = lanes[z];
         laneOf[ln.anchor] = -1; ln.busy = false;
+        if (!fin[ln.anchor] && pendReady) { pendp->push_back((u32)ln.anchor); *pendSortedp = false; }
         for (int side = 0; side < 2; side++) {
             ln.s[side].res.ops.clear();
             if (ln.s[side].phase == SIDE_RUNNING) B.job(z, side)->abort = 1; else ln.s[side].phase = SIDE_IDLE;
@@ -533,6 +535,10 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     const double reachPrior = (double)tbLen / 250.0 + 64;    /* before anything is known: generous */
     double reachTrunc = 0; bool reachExact = false; u32 reachSeen = 0;   /* rows the current estimate was taken over */
     auto reach = [&]() -> double { return reachTrunc > 0 ? reachTrunc : reachPrior; };
+    /* how far off the expected reach may be: a finished sweep gives the row itself (sweeps of one call end within a few
+     * hundred rows of each other); an estimate is as good as the stretch of rows it was taken over */
+    auto slack_frac = [&]() -> double { return reachExact ? 0.003 : reachSeen >= 65536 ? 0.005 : reachSeen >= 16384 ? 0.012 : 0.03; };
+    bool anchorsWaitForEstimate = true;
 
     /* first row of lane z's sweep `side` in which an alignment committed since the sweep's snapshot shows up (0xFFFFFFFF: none) */
     auto first_touched_row = [&](int z, int side) -> u32 {
@@ -615,6 +621,10 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
 
     /* ---- the anchor loop, gapped_extend.c:1300-1470 ---- */
     std::vector<int> blocker(n, -1);                         /* the earlier unresolved anchor this one is probably covered by */
+    std::vector<u32> pend(n);                                /* anchors neither resolved nor started, best first (compacted as it is walked) */
+    for (u64 i = 0; i < n; i++) pend[i] = (u32)i;
+    bool pendSorted = true; double lastSlackFrac = -1;
+    pendp = &pend; pendSortedp = &pendSorted; pendReady = true;
     u64 hd = 0;
     while (true) {
         while (hd < n && fin[hd]) hd++;
@@ -648,7 +658,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 progressed = true;
                 continue;
             }
-            if (ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING) continue;
+            const bool anyRunning = ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING;
             bool stale = false, paused = false;
             for (int side = 0; side < 2; side++) {
                 if (ln.s[side].phase == SIDE_DONE && ln.s[side].snapshot != G.committed.size()) stale = true;
@@ -658,13 +668,14 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             /* an alignment across the anchor's row may be a new neighbour (or cover the anchor: retire_covered saw to that) */
             galn& y = G.al[ln.anchor];
             bool crossed = false;
-            const size_t from = std::min(ln.s[0].phase == SIDE_DONE || ln.s[0].phase == SIDE_PAUSED ? ln.s[0].snapshot : G.committed.size(),
-                                         ln.s[1].phase == SIDE_DONE || ln.s[1].phase == SIDE_PAUSED ? ln.s[1].snapshot : G.committed.size());
+            const size_t from = std::min(ln.s[0].phase != SIDE_IDLE ? ln.s[0].snapshot : G.committed.size(),
+                                         ln.s[1].phase != SIDE_IDLE ? ln.s[1].snapshot : G.committed.size());
             for (size_t k = from; k < G.committed.size() && !crossed; k++) { galn& x = G.al[G.committed[k]]; if (x.pos1 <= apos1[ln.anchor] && x.end1 >= apos1[ln.anchor]) crossed = true; }
             if (crossed) {
                 int coverer = -1;
                 if (!anchor_neighbours(G, y, &coverer)) return fail("internal error: anchor %llu lies on alignment %d but was not retired", (unsigned long long)ln.anchor, coverer);
                 if (y.left1.al != ln.left1.al || y.left1.sg != ln.left1.sg || y.right1.al != ln.right1.al || y.right1.sg != ln.right1.sg) {
+                    if (anyRunning) continue;                 /* both sweeps restart once the running one is back */
                     if (trace) fprintf(stderr, "[gx %.4f] a=%llu new neighbours: restart\n", now(), (unsigned long long)ln.anchor);
                     G.st.redone += 2; pfRestarts += 2;
                     ln.left1 = y.left1; ln.right1 = y.right1;
@@ -673,7 +684,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     continue;
                 }
             }
-            for (int side = 0; side < 2; side++) {
+            for (int side = 0; side < 2; side++) {              /* (a sweep that is still running is looked at when it is back) */
                 if (ln.s[side].phase == SIDE_PAUSED) {
                     if (fin[ln.s[side].pausedOn] || laneOf[ln.s[side].pausedOn] < 0) { if (continue_paused(z, side)) return -1; progressed = true; }
                     continue;
@@ -702,6 +713,24 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         if (prof) pfCommit += now() - t0;
         /* 4. start anchors, best first, while lanes are free.  The head anchor always gets one. */
         t0 = prof ? now() : 0;
+        /* no sweep has finished yet to say how far sweeps go: the running ones report their progress.  Two reports of one
+         * sweep give the traceback bytes a row takes once the band has settled, hence the row where the traceback will
+         * run out; the longer the sweep has run, the better the estimate. */
+        if (!reachExact && anchorsWaitForEstimate) {
+            for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
+                gx_side& sd = lanes[z].s[side];
+                if (!lanes[z].busy || sd.phase != SIDE_RUNNING) continue;
+                dp_job& J = *B.job(z, side);
+                const u32 pr = J.progRows, pu = J.progUsed;
+                if (J.resume >= 0 || pr < 2048 || pu == 0) continue;
+                if (sd.prog0Rows == 0) { sd.prog0Rows = pr; sd.prog0Used = pu; continue; }
+                if (pr < sd.prog0Rows + 4096 || pu <= sd.prog0Used || pr - sd.prog0Rows <= reachSeen) continue;
+                const double perRow = (double)(pu - sd.prog0Used) / (double)(pr - sd.prog0Rows);
+                reachTrunc = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
+                reachSeen = pr - sd.prog0Rows;
+            }
+            if (reachTrunc > 0 && slack_frac() != lastSlackFrac) startDirty = true;     /* the estimate got sharper: look at the waiting anchors again */
+        }
         if (startDirty) {
             startDirty = false;
             int freeLanes = 0;
@@ -729,34 +758,17 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     freeLanes = 1;
                 } else startDirty = true;                     /* look again when a sweep has finished */
             }
-            /* no sweep has finished yet to say how far sweeps go: the running ones report their progress.  Two reports of one
-             * sweep give the traceback bytes a row takes once the band has settled, hence the row where the traceback will
-             * run out; the longer the sweep has run, the better the estimate. */
-            if (!reachExact) {
-                for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
-                    gx_side& sd = lanes[z].s[side];
-                    if (!lanes[z].busy || sd.phase != SIDE_RUNNING) continue;
-                    dp_job& J = *B.job(z, side);
-                    const u32 pr = J.progRows, pu = J.progUsed;
-                    if (J.resume >= 0 || pr < 2048 || pu == 0) continue;
-                    if (sd.prog0Rows == 0) { sd.prog0Rows = pr; sd.prog0Used = pu; continue; }
-                    if (pr < sd.prog0Rows + 4096 || pu <= sd.prog0Used || pr - sd.prog0Rows <= reachSeen) continue;
-                    const double perRow = (double)(pu - sd.prog0Used) / (double)(pr - sd.prog0Rows);
-                    reachTrunc = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
-                    reachSeen = pr - sd.prog0Rows;
-                }
-                startDirty = true;                             /* look again: the estimate sharpens */
-            }
             const bool calibrated = reachTrunc > 0;
             const double rr = reach();
             reachShared = calibrated ? rr : 0;
-            /* how far off the expected reach may be: a finished sweep gives the row itself (sweeps of one call end within
-             * a few hundred rows of each other); an estimate is as good as the stretch of rows it was taken over */
-            const double slackFrac = reachExact ? 0.003 : reachSeen >= 65536 ? 0.005 : reachSeen >= 16384 ? 0.012 : 0.03;
-            u64 examined = 0;
-            for (u64 j = hd; j < n && (freeLanes > 0 || have < W) && examined < 16384; j++) {
-                if (fin[j] || laneOf[j] >= 0) continue;
-                examined++;
+            const double slackFrac = slack_frac();
+            lastSlackFrac = calibrated ? slackFrac : -1;
+            if (!pendSorted) { std::sort(pend.begin(), pend.end()); pend.erase(std::unique(pend.begin(), pend.end()), pend.end()); pendSorted = true; }
+            size_t keep = 0, q = 0; bool waitingForEstimate = false;
+            for (; q < pend.size() && (freeLanes > 0 || have < W); q++) {
+                const u64 j = pend[q];
+                if (fin[j] || laneOf[j] >= 0) continue;          /* resolved or started since: leaves the list */
+                pend[keep++] = (u32)j;
                 int deferSide = -1; u64 deferOn = 0;
                 if (j != hd && slackRows >= 0) {
                     /* Will an earlier anchor that is still open come to cover this one?  (Scheduling only.)
@@ -791,7 +803,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                         if (blocker[j] >= 0 && trace) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, known ? "done" : "running");
                     }
                     if (blocker[j] >= 0) continue;
-                    if (tooEarly) { startDirty = true; continue; }
+                    if (tooEarly) { waitingForEstimate = true; continue; }
                     if (edges > 1) { blocker[j] = (int)lanes[edgeLane].anchor; continue; }     /* at two edges at once: nothing to start yet */
                     if (edges == 1) {
                         gx_lane_state& li = lanes[edgeLane];
@@ -806,9 +818,12 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 int fl = -1;
                 for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
                 if (start_anchor(fl, j, deferSide, deferOn)) return -1;
-                freeLanes--; progressed = true;
+                freeLanes--; progressed = true; keep--;
                 if (j != hd) G.st.speculated++;
             }
+            for (; q < pend.size(); q++) pend[keep++] = pend[q];
+            pend.resize(keep);
+            anchorsWaitForEstimate = waitingForEstimate;
         }
         if (prof) pfStart += now() - t0;
         if (flush()) return -1;
