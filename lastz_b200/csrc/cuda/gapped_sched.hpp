@@ -291,7 +291,9 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     int have = B.lanes(std::min(W, 8));
     if (have < 1) return -1;
     if (have < std::min(W, 8)) W = have;
-    int firstMode = 0;
+    /* kernel a sweep starts with: 1 = the one-warp kernel (1.8 us a row however many sweeps share the device), 0 = the four-warp
+     * kernel (1.45 us a row alone, 2.2 with three sweeps per SM), 2/3 = the shared-memory kernel for bands wider than 512 columns */
+    int firstMode = 1;
     { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3) firstMode = mdv; } }
     std::vector<gx_lane_state> lanes(W);
     for (auto& ln : lanes) { ln.busy = false; ln.s[0].phase = ln.s[1].phase = SIDE_IDLE; ln.deferSide = -1; }
@@ -401,7 +403,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
              * beyond where that is expected; it goes on from a checkpoint when the alignment is known (scheduling only: a
              * sweep that stops too early just continues, one that is not stopped is cut back like any other). */
             J.rowLimit = 0; sd.pausedOn = 0;
-            if (rowLimits && reachKnown() && sd.mode == 0) {
+            if (rowLimits && reachKnown() && sd.mode <= 1) {
                 double bestDist = 1e30; int bi = -1;
                 const s64 dj = (s64)aPos1 - (s64)aPos2;
                 for (int zz = 0; zz < (int)lanes.size(); zz++) {
@@ -435,12 +437,12 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
 
     /* retire the anchors that lie on alignment `ai` (index into G.al; n = the trivial self alignment) */
     bool startDirty = true;                                  /* something happened that may let another anchor start */
-    std::vector<u32>* pendp = NULL; bool* pendSortedp = NULL; bool pendReady = false;   /* (the list is declared further down) */
+    std::vector<u32>* pendp = NULL; bool pendReady = false;   /* (the list is declared further down) */
     /* take a lane away from its anchor: at once if nothing of it is running, else when its sweeps have stopped */
     auto drop_lane = [&](int z) {
         gx_lane_state& ln = lanes[z];
         laneOf[ln.anchor] = -1; ln.busy = false;
-        if (!fin[ln.anchor] && pendReady) { pendp->push_back((u32)ln.anchor); *pendSortedp = false; }
+        if (!fin[ln.anchor] && pendReady) pendp->insert(std::lower_bound(pendp->begin(), pendp->end(), (u32)ln.anchor), (u32)ln.anchor);   /* back among the waiting */
         for (int side = 0; side < 2; side++) {
             ln.s[side].res.ops.clear();
             if (ln.s[side].phase == SIDE_RUNNING) B.job(z, side)->abort = 1; else ln.s[side].phase = SIDE_IDLE;
@@ -612,7 +614,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         r.score = J.score; r.end1 = J.end1; r.end2 = J.end2; r.rows = J.rows; r.status = J.status; r.cells = J.cells;
         const u32* ops = B.ops(z, side);
         r.ops.assign(ops, ops + J.nops);
-        sd.ckptCount = J.ckptCount; sd.ckptEvery = sd.mode == 0 ? B.ckpt_every() : 0;
+        sd.ckptCount = J.ckptCount; sd.ckptEvery = sd.mode <= 1 ? B.ckpt_every() : 0;
         sd.phase = J.status == DP_PAUSED ? SIDE_PAUSED : SIDE_DONE;
         if (r.status == DP_TRUNCATED) { reachTrunc = reachExact ? 0.8 * reachTrunc + 0.2 * r.rows : (double)r.rows; if (!reachExact) startDirty = true; reachExact = true; }
         if (trace) fprintf(stderr, "[gx %.4f] done a=%llu side=%d rows=%u end1=%u status=%d mode=%d ckpts=%u\n", now(), (unsigned long long)ln.anchor, side, r.rows, r.end1, r.status, sd.mode, sd.ckptCount);
@@ -623,8 +625,8 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     std::vector<int> blocker(n, -1);                         /* the earlier unresolved anchor this one is probably covered by */
     std::vector<u32> pend(n);                                /* anchors neither resolved nor started, best first (compacted as it is walked) */
     for (u64 i = 0; i < n; i++) pend[i] = (u32)i;
-    bool pendSorted = true; double lastSlackFrac = -1;
-    pendp = &pend; pendSortedp = &pendSorted; pendReady = true;
+    double lastSlackFrac = -1;
+    pendp = &pend; pendReady = true;
     u64 hd = 0;
     while (true) {
         while (hd < n && fin[hd]) hd++;
@@ -763,7 +765,9 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             reachShared = calibrated ? rr : 0;
             const double slackFrac = slack_frac();
             lastSlackFrac = calibrated ? slackFrac : -1;
-            if (!pendSorted) { std::sort(pend.begin(), pend.end()); pend.erase(std::unique(pend.begin(), pend.end()), pend.end()); pendSorted = true; }
+            std::vector<std::pair<u32, int> > lanePos;
+            for (int z = 0; z < have; z++) if (lanes[z].busy) lanePos.push_back(std::make_pair(apos1[lanes[z].anchor], z));
+            std::sort(lanePos.begin(), lanePos.end());
             size_t keep = 0, q = 0; bool waitingForEstimate = false;
             for (; q < pend.size() && (freeLanes > 0 || have < W); q++) {
                 const u64 j = pend[q];
@@ -782,7 +786,14 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
                     bool tooEarly = false; int edgeLane = -1, edgeSide = 0; double edgeDist = 0; int edges = 0;
-                    for (int z = 0; z < have && blocker[j] < 0; z++) {
+                    /* only the open anchors within reach matter: the lanes sorted by their anchor's position, walked outwards */
+                    const double zone = calibrated ? 1.06 * rr + slackRows + 16 : 2.5 * reachPrior;
+                    const u32 pj = apos1[j];
+                    const size_t mid = std::lower_bound(lanePos.begin(), lanePos.end(), std::make_pair(pj, -1)) - lanePos.begin();
+                    for (int dir = 0; dir < 2 && blocker[j] < 0; dir++)
+                    for (size_t w = dir ? mid : mid - 1; w < lanePos.size() && blocker[j] < 0; dir ? w++ : w--) {
+                        if (fabs((double)lanePos[w].first - (double)pj) > zone) break;
+                        const int z = lanePos[w].second;
                         gx_lane_state& ln = lanes[z];
                         if (!ln.busy || ln.anchor >= j || ln.unsure) continue;
                         const u64 i = ln.anchor;
@@ -818,6 +829,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 int fl = -1;
                 for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
                 if (start_anchor(fl, j, deferSide, deferOn)) return -1;
+                lanePos.insert(std::lower_bound(lanePos.begin(), lanePos.end(), std::make_pair(apos1[j], fl)), std::make_pair(apos1[j], fl));
                 freeLanes--; progressed = true; keep--;
                 if (j != hd) G.st.speculated++;
             }

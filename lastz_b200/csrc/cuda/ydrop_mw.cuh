@@ -226,8 +226,8 @@ __device__ __forceinline__ void mw_sweep(s32 (&C)[K], s32 (&D)[K], const u32 (&B
     out.fa = fa; out.la = la; out.uv = uv; out.uc = uc; out.bv = bv; out.bc = bc; out.Iout = Iout;
 }
 
-template <int K, int NW>
-__global__ void __launch_bounds__(32 * NW, 4)
+template <int K, int NW, int MINB = 1>
+__global__ void __launch_bounds__(32 * NW, MINB)
 k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
            const u8* __restrict__ cls1, const u8* __restrict__ cls2, u32 len1, u32 len2,
            const lzb_scoring_dev* __restrict__ sc, s32 yDrop, int trim) {

@@ -213,9 +213,13 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     const int* const listv = J->listv;
     int alignList = J->alignList;                          /* index into listv */
     u32 nextActRow = list_row(listv, alignList, al, rev, a1);
-    const int tbOnly = J->tbOnly;
+    const int tbOnly = J->tbOnly, resume = J->resume;
     if (tbOnly) { status = J->status; end1 = J->end1; end2 = J->end2; }
     int* act = J->act; int nact = 0;
+    constexpr u32 CKW = CK_WORDS(K, 32);                   /* checkpoint record: see ydrop_common.cuh */
+    u32* const ckpt = J->ckpt; const u32 ckptCap = J->ckptCap, ckptEvery = J->ckptEvery;
+    u32 ckptCount = tbOnly ? J->ckptCount : 0;
+    const u32 rowLimit = J->rowLimit ? J->rowLimit : 0xFFFFFFFFu;
     const u32 tbRowCap = J->tbRowCap, actCap = J->actCap;
     u32* const dbg = J->dbg; const u32 dbgCap = J->dbgCap;
     u32 lLim = 0, rLim = 0; int lTyp = 0, rTyp = 0;
@@ -233,10 +237,24 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
         }                                                                                                 \
     } while (0)
     S.cb = lane * K;
-    WG_LOAD_BLOCK();
-    /* ---- first row, gapped_extend.c:3576-3591 ---- */
-    u32 LY = 0, RY;
-    {
+    /* ---- first row, gapped_extend.c:3576-3591 -- or the state a checkpoint saved ---- */
+    u32 LY = 0, RY = 0, row0 = 1;
+    if (resume >= 0 && !tbOnly) {
+        const u32* rec = ckpt + (size_t)resume * CKW;
+        row0 = rec[0] + 1; LY = rec[1]; RY = rec[2]; L = (s32)rec[3]; R = (s32)rec[4];
+        leftSeg.al = (int)rec[5]; leftSeg.sg = (int)rec[6]; rightSeg.al = (int)rec[7]; rightSeg.sg = (int)rec[8];
+        lLim = rec[9]; rLim = rec[10]; lTyp = (int)rec[11]; rTyp = (int)rec[12]; nact = (int)rec[13];
+        used = (s64)((u64)rec[14] | ((u64)rec[15] << 32));
+        best = (s32)rec[16]; bnd = (s32)rec[17]; end1 = rec[18]; end2 = rec[19]; endIsBnd = (int)rec[20];
+        cells = (u64)rec[21] | ((u64)rec[22] << 32);
+        if (lane == 0) for (int k = 0; k < 5 * nact; k++) act[k] = (int)rec[CK_HDR + k];
+        const u32* tv = rec + CK_HDR + 5 * CK_ACT;
+#pragma unroll
+        for (int s = 0; s < K; s++) { S.C[s] = (s32)tv[(u32)s * 32u + lane]; S.D[s] = (s32)tv[(u32)(K + s) * 32u + lane]; }
+        S.cb = tv[(u32)(2 * K) * 32u + lane];
+        ckptCount = (u32)resume + 1;
+        row = row0;
+    } else {
         u32 last = 1;
         if (gapE > 0) { if (yDrop >= gapOE) last = (u32)(((s64)yDrop - gapOE) / gapE) + 2; }
         else if (yDrop >= gapOE) last = N;
@@ -248,21 +266,24 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
             if (col <= last && status == DP_OK) {
                 const s32 v = col == 0 ? 0 : -gapOE - (s32)(col - 1) * gapE;
                 S.C[s] = v; S.D[s] = v - gapOE;
-                tb[col] = col == 0 ? 0 : LINK_I;
+                if (!tbOnly) tb[col] = col == 0 ? 0 : LINK_I;
             } else { S.C[s] = LZB_NEG_INF; S.D[s] = LZB_NEG_INF; }
         }
         used = (s64)last + 1;
         RY = last + 1;
-        if (lane == 0 && tbRowCap > 0) tbRow[0] = 0;
+        if (lane == 0 && tbRowCap > 0 && !tbOnly) tbRow[0] = 0;
     }
+    WG_LOAD_BLOCK();
     /* target-side class codes, 32 rows per load, one chunk ahead */
 #define WG_ACODE(r_) ([&]() -> u32 { const u32 rr_ = (r_); if (rr_ > M) return (u32)cls0;                 \
                                       const s64 ai_ = !rev ? (s64)a1 + rr_ : (s64)a1 + 1 - (s64)rr_;      \
                                       return (ai_ < 0 || ai_ >= (s64)len1) ? (u32)cls0 : (u32)cls1[ai_]; }())
-    u32 acv = WG_ACODE(1 + lane), acvNext = WG_ACODE(33 + lane);
+    /* (a checkpoint row is a multiple of 32: the loop's first iteration then shifts acvNext into acv) */
+    u32 acv = WG_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? -31 : 1) + lane), acvNext = WG_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? 1 : 33) + lane);
     __syncwarp();
     if (status == DP_OK && !tbOnly)
-    for (row = 1; row <= M; row++) {
+    for (row = row0; row <= M; row++) {
+        if (row >= rowLimit) { status = DP_PAUSED; break; }
         if ((row & 255u) == 0 && J->abort) { status = DP_ABORTED; break; }   /* the anchor was retired (mapped host memory: looked at rarely) */
         /* ---- update_LR_bounds gapped_extend.c:4588-4724 (every lane, same values) ---- */
         if (!rev) {
@@ -365,6 +386,25 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
             RY += p; used += p;
         }
         if ((s32)RY <= NN) RY++;                             /* the sentinel column already holds LZB_NEG_INF */
+        /* ---- checkpoint: everything the next row reads ---- */
+        if (ckptCap && row % ckptEvery == 0 && row / ckptEvery - 1 == ckptCount && ckptCount < ckptCap && nact <= CK_ACT) {
+            u32* rec = ckpt + (size_t)ckptCount * CKW;
+            if (lane == 0) {
+                rec[0] = row; rec[1] = LY; rec[2] = RY; rec[3] = (u32)L; rec[4] = (u32)R;
+                rec[5] = (u32)leftSeg.al; rec[6] = (u32)leftSeg.sg; rec[7] = (u32)rightSeg.al; rec[8] = (u32)rightSeg.sg;
+                rec[9] = lLim; rec[10] = rLim; rec[11] = (u32)lTyp; rec[12] = (u32)rTyp; rec[13] = (u32)nact;
+                rec[14] = (u32)(u64)used; rec[15] = (u32)((u64)used >> 32);
+                rec[16] = (u32)best; rec[17] = (u32)bnd; rec[18] = end1; rec[19] = end2; rec[20] = (u32)endIsBnd;
+                rec[21] = (u32)cells; rec[22] = (u32)(cells >> 32);
+                for (int k = 0; k < 5 * nact; k++) rec[CK_HDR + k] = (u32)act[k];
+                J->progUsed = (u32)(u64)used; J->progRows = row;      /* lets the host estimate where the traceback will run out */
+            }
+            u32* tv = rec + CK_HDR + 5 * CK_ACT;
+#pragma unroll
+            for (int s = 0; s < K; s++) { tv[(u32)s * 32u + lane] = (u32)S.C[s]; tv[(u32)(K + s) * 32u + lane] = (u32)S.D[s]; }
+            tv[(u32)(2 * K) * 32u + lane] = S.cb;
+            ckptCount++;
+        }
     }
 #undef WG_LOAD_BLOCK
 #undef WG_ACODE
@@ -377,9 +417,9 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     if (lane == 0) {
         if (!tbOnly) {
             J->score = endIsBnd ? bnd : best; J->end1 = end1; J->end2 = end2;
-            J->rows = row; J->cells = cells; J->status = status; J->ckptCount = 0;
+            J->rows = row; J->cells = cells; J->status = status; J->ckptCount = ckptCount;
         }
         J->nops = nops; J->opsOverflow = ovf ? 1 : 0;
         job_done(J);
-}
+    }
 }

@@ -125,7 +125,8 @@ struct emu_backend {
 static void expand(std::string& out, const u32* ops, u32 n) { for (u32 k = 0; k < n; k++) out.append(ops[k] >> 2, "?IDS"[ops[k] & 3]); }
 
 // homologous pair with `blocks` rearranged pieces: enough structure for neighbours on both sides, above and below
-static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int W, u32 every, int shuffle, int dupes, const char* slack = "-1") {
+static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int W, u32 every, int shuffle, int dupes, const char* slack = "-1", const char* mode = "1") {
+    setenv("LZB_DP_MODE", mode, 1);         // 1: the one-warp kernel (the default), 0: the four-warp kernel, 2: the shared-memory kernel (no checkpoints)
     setenv("LZB_GAP_SLACK", slack, 1);     // -1: every anchor is started as soon as a lane is free (most speculation); else the margin in rows
     std::string t, q; const char* acgt = "ACGT";
     for (u32 i = 0; i < len; i++) t.push_back(acgt[rnd() & 3]);
@@ -187,8 +188,8 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
                 (unsigned long long)so.truncated, (unsigned long long)sg.anchorsExtended, (unsigned long long)sg.dpCells, (unsigned long long)sg.truncated);
         bad++;
     }
-    printf("case %2d: %u x %u bp, %llu anchors, traceback=%u yDrop=%d trim=%d lanes=%d ckpt=%u shuffle=%d: %u alignments, extended %llu, speculated %llu, redone %llu, truncated %llu, launches %llu (%llu jobs)  %s\n",
-           caseNo, len1, len2, (unsigned long long)nsegs, tbBytes, yDrop, trim, W, every, shuffle, ng, (unsigned long long)sg.anchorsExtended, (unsigned long long)sg.speculated,
+    printf("case %2d: %u x %u bp, %llu anchors, traceback=%u yDrop=%d trim=%d lanes=%d ckpt=%u shuffle=%d kernel=%s slack=%s: %u alignments, extended %llu, speculated %llu, redone %llu, truncated %llu, launches %llu (%llu jobs)  %s\n",
+           caseNo, len1, len2, (unsigned long long)nsegs, tbBytes, yDrop, trim, W, every, shuffle, mode, slack, ng, (unsigned long long)sg.anchorsExtended, (unsigned long long)sg.speculated,
            (unsigned long long)sg.redone, (unsigned long long)sg.truncated, (unsigned long long)B.launches, (unsigned long long)B.jobsRun, bad ? "MISMATCH" : "ok");
     fflush(stdout);
     lzb_free_align_list(want); lzb_free_align_list(got); lzb_free(segs); lzb_query_free(Q); lzb_target_free(T); lzb_close(oc);
@@ -201,10 +202,11 @@ int main(int argc, char** argv) {
     int bad = 0, n = 0;
     bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 1, 64, 0, 0);       // one lane: the sequential order, tiled by truncation
     bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 0);      // 16 lanes: every sweep speculative, resumed from checkpoints
-    bad += one_case(n++, 6000, 0.05, 0.012, 50000, 9400, 0, 8, 32, 1, 2);       // repeats: neighbours across anchor rows, --noytrim
+    bad += one_case(n++, 6000, 0.05, 0.012, 50000, 9400, 0, 8, 32, 1, 2, "-1", "0");   // repeats: neighbours across anchor rows, --noytrim; four-warp kernel
     bad += one_case(n++, 5000, 0.04, 0.010, 80000, 6000, 1, 3, 96, 1, 1);       // fewer lanes than anchors worth starting
+    bad += one_case(n++, 4000, 0.04, 0.010, 60000, 9400, 1, 8, 64, 1, 1, "-1", "2");   // the shared-memory kernel: no checkpoints, a touched sweep restarts
     bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 1, "20"); // the product's waiting rule (anchors near an expected reach wait for the commit)
-    bad += one_case(n++, 14000, 0.04, 0.010, 200000, 9400, 1, 16, 32, 1, 1, "10"); // sweeps long enough to be stopped short of an earlier anchor's alignment and continued
+    bad += one_case(n++, 14000, 0.04, 0.010, 200000, 9400, 1, 16, 32, 1, 1, "10", "0"); // sweeps long enough to be stopped short of an earlier anchor's alignment and continued
     if (big) {
         bad += one_case(n++, 20000, 0.04, 0.010, 100000, 9400, 1, 32, 64, 1, 3);
         bad += one_case(n++, 12000, 0.06, 0.015, 70000, 9400, 1, 24, 128, 1, 4);

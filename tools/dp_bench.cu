@@ -31,14 +31,16 @@ static uint64_t next64(void) {
 static const s32 HOX[4][4] = { { 91, -114, -31, -123 }, { -114, 100, -125, -31 }, { -31, -125, 100, -114 }, { -123, -31, -114, 91 } };
 
 struct shape { const char* name; int threads; void (*launch)(int grid, dp_job* jobs, const u8* c1, const u8* c2, u32 l1, u32 l2, const lzb_scoring_dev* sc); };
-#define MW(K, NW) { "mw<" #K "," #NW ">", 32 * NW, [](int g, dp_job* j, const u8* c1, const u8* c2, u32 l1, u32 l2, const lzb_scoring_dev* sc) { k_ydrop_mw<K, NW><<<g, 32 * NW>>>(j, (const dseg*)NULL, c1, c2, l1, l2, sc, 9400, 1); } }
-#define WP(K) { "warp<" #K ">", 32, [](int g, dp_job* j, const u8* c1, const u8* c2, u32 l1, u32 l2, const lzb_scoring_dev* sc) { k_ydrop_warp<K><<<g, 32>>>(j, (const dseg*)NULL, c1, c2, l1, l2, sc, 9400, 1); } }
-static shape shapes[] = { MW(8, 4), MW(4, 8), MW(16, 2), MW(8, 2), MW(4, 4), MW(16, 1), MW(24, 1), WP(16), WP(24) };
+static launch_list g_ll;
+#define MW(K, NW, MB) { "mw<" #K "," #NW "," #MB ">", 32 * NW, [](int g, dp_job* j, const u8* c1, const u8* c2, u32 l1, u32 l2, const lzb_scoring_dev* sc) { k_ydrop_mw<K, NW, MB><<<g, 32 * NW>>>(j, g_ll, (const dseg*)NULL, c1, c2, l1, l2, sc, 9400, 1); } }
+#define WP(K) { "warp<" #K ">", 32, [](int g, dp_job* j, const u8* c1, const u8* c2, u32 l1, u32 l2, const lzb_scoring_dev* sc) { k_ydrop_warp<K><<<g, 32>>>(j, g_ll, (const dseg*)NULL, c1, c2, l1, l2, sc, 9400, 1); } }
+static shape shapes[] = { MW(8, 4, 1), MW(8, 4, 4), WP(16) };
 
 int main(int argc, char** argv) {
     const u32 L = argc > 1 ? (u32)atol(argv[1]) : 1000000u;
     const u32 tbMiB = argc > 2 ? (u32)atol(argv[2]) : 80u;
     const int copies = argc > 3 ? atoi(argv[3]) : 296;
+    for (int k = 0; k < LZB_LAUNCH_MAX; k++) g_ll.ix[k] = (u16)k;
     std::string t(L, 'A'), q; std::vector<u32> qposOf(L);
     st = 20260925; for (u32 i = 0; i < L; i++) t[i] = "ACGT"[next64() >> 62];
     st = 20260926;
@@ -81,7 +83,7 @@ int main(int argc, char** argv) {
         const int rev = (k & 1) == 0;
         J.reversed = rev; J.a1 = a1; J.a2 = a2;
         J.M = rev ? a1 + 1 : len1 - (a1 + 1); J.N = rev ? a2 + 1 : len2 - (a2 + 1);
-        J.L0 = 0; J.R0 = (s32)(J.N + 1); J.leftSeg = { -1, -1 }; J.rightSeg = { -1, -1 }; J.alignList = -1; J.al = NULL;
+        J.L0 = 0; J.R0 = (s32)(J.N + 1); J.leftSeg = { -1, -1 }; J.rightSeg = { -1, -1 }; J.listv = NULL; J.alignList = 0; J.al = NULL; J.resume = -1; J.token = 1;
         CK(cudaMalloc(&J.tb, (size_t)tbBytes + 64)); J.tbLen = tbLen;
         CK(cudaMalloc(&J.tbRow, (size_t)tbRowCap * 4)); J.tbRowCap = tbRowCap;
         J.opsCap = 1u << 18; CK(cudaMalloc(&J.ops, (size_t)J.opsCap * 4));
@@ -91,10 +93,11 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     printf("pair %u x %u bp, anchor (%u,%u), traceback %u MiB, copies %d\n", len1, len2, a1, a2, tbMiB, copies);
     printf("%-12s %8s | %10s %10s %8s %8s %6s | %10s %10s\n", "kernel", "threads", "rows(rev)", "rows(fwd)", "cells/row", "ms", "status", "us/row x1", "us/row xN");
+    for (int gN : { 148, 296, 444, 592 }) if (gN <= njobs)
     for (auto& s : shapes) {
         double usrow[2] = { 0, 0 }; u32 rows[2] = { 0, 0 }; double ms1 = 0; int stt[2] = { 0, 0 }; double cpr = 0;
         for (int pass = 0; pass < 2; pass++) {
-            const int g = pass == 0 ? 2 : njobs;
+            const int g = pass == 0 ? 2 : gN;
             CK(cudaMemcpy(dj, hj.data(), njobs * sizeof(dp_job), cudaMemcpyHostToDevice));
             CK(cudaEventRecord(e0));
             s.launch(g, dj, d1, d2, len1, len2, dsc);
@@ -107,7 +110,7 @@ int main(int argc, char** argv) {
             usrow[pass] = mr ? ms * 1e3 / mr : 0;
             if (pass == 0) { rows[0] = out[0].rows; rows[1] = out[1].rows; ms1 = ms; stt[0] = out[0].status; stt[1] = out[1].status; cpr = (double)(out[0].cells + out[1].cells) / (out[0].rows + out[1].rows + 1e-9); }
         }
-        printf("%-12s %8d | %10u %10u %8.1f %8.2f %3d/%-3d | %10.3f %10.3f\n", s.name, s.threads, rows[0], rows[1], cpr, ms1, stt[0], stt[1], usrow[0], usrow[1]);
+        printf("%-12s %4d CTAs | %10u %10u %8.1f %8.2f %3d/%-3d | %10.3f %10.3f\n", s.name, gN, rows[0], rows[1], cpr, ms1, stt[0], stt[1], usrow[0], usrow[1]);
         fflush(stdout);
     }
     return 0;
