@@ -149,7 +149,7 @@ static int make_chunk(gx_cache* gc) {
     lane_chunk ch; memset(&ch, 0, sizeof ch);
     const size_t tbStride = (((size_t)gc->tbBytes + 64) + 255) & ~(size_t)255, nside = 2 * GX_CHUNK;
     const u32 tbRowCap = gc->tbLen / 128 + 4096;
-    const size_t ckWords = (size_t)GX_CKPT_CAP * CK_WORDS(8, 128);
+    const size_t ckWords = (size_t)GX_CKPT_CAP * CK_RECORD_WORDS;
     u32* d_ops = NULL;
     if (cudaMalloc(&ch.tb, tbStride * nside) != cudaSuccess || cudaMalloc(&ch.tbRow, (size_t)tbRowCap * 4 * nside) != cudaSuccess ||
         cudaMalloc(&ch.act, (size_t)GX_ACT_CAP * 5 * 4 * nside) != cudaSuccess || cudaMalloc(&ch.ckpt, ckWords * 4 * nside) != cudaSuccess ||
@@ -178,7 +178,7 @@ struct cuda_backend {
     u32 ring(int mode) { return mode == 2 ? 4096u : 8192u; }
     int lanes(int want) {                                    /* called again when the scheduler wants more */
         if (want > GX_MAX_LANES) want = GX_MAX_LANES;
-        const size_t laneBytes = 2 * ((size_t)gc->tbBytes + (size_t)(gc->tbLen / 128 + 4096) * 4 + (size_t)GX_CKPT_CAP * CK_WORDS(8, 128) * 4 + 8192);
+        const size_t laneBytes = 2 * ((size_t)gc->tbBytes + (size_t)(gc->tbLen / 128 + 4096) * 4 + (size_t)GX_CKPT_CAP * CK_RECORD_WORDS * 4 + 8192);
         while ((int)gc->lanes.size() < want) {
             size_t freeB = 0, totalB = 0;
             if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) break;

@@ -359,6 +359,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         dp_job& J = *B.job(z, side);
         const int rev = side == 0;
         if (!tbOnly) {
+            if (rec >= 0 && sd.mode == 1) sd.mode = 0;        /* a sweep that is continued is about to meet an alignment: the wider window */
             J.reversed = rev; J.a1 = aPos1; J.a2 = aPos2;
             u32 low1 = 0, high1 = len1, low2 = 0, high2 = len2;  /* the anchor's partition in each sequence: first base, one past the last */
             if (!tSeparators.empty()) {
@@ -601,14 +602,18 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         if (!ln.busy) { sd.phase = SIDE_IDLE; startDirty = true; return 0; }      /* the anchor was retired while this ran */
         if (!sd.tbOnly) G.st.dpCellsComputed += J.cells;
         int again = 0;                                        /* 1 fresh rerun, 2 traceback only */
+        int ringRec = -1;
         if (J.status == DP_RING) {
             if (sd.mode >= 3) return fail("Y-drop band wider than %u columns; lower --ydrop", B.ring(sd.mode));
-            sd.mode = sd.mode < 2 ? 2 : sd.mode + 1; again = 1;
+            /* the one-warp kernel's 512-column window is outgrown (typically beside an earlier alignment): the four-warp
+             * kernel takes over from the last checkpoint; beyond its 1024 columns the shared-memory kernel starts afresh */
+            if (sd.mode == 1) { sd.mode = 0; again = 1; ringRec = (int)J.ckptCount - 1; }
+            else { sd.mode = sd.mode < 2 ? 2 : sd.mode + 1; again = 1; }
         } else if (J.status == DP_TBROW || J.status == DP_ACT) { if (B.grow(z, side, J.status)) return -1; again = 1; }
         else if (J.opsOverflow) { if (B.grow(z, side, DP_OPS)) return -1; again = 2; }
         if (again) {
             if (trace) fprintf(stderr, "[gx %.4f] rerun a=%llu side=%d status=%d overflow=%d mode=%d\n", now(), (unsigned long long)ln.anchor, side, J.status, J.opsOverflow, sd.mode);
-            return queue_side(z, side, -1, again == 2);
+            return queue_side(z, side, again == 2 ? -1 : ringRec, again == 2);
         }
         dp_result& r = sd.res;
         r.score = J.score; r.end1 = J.end1; r.end2 = J.end2; r.rows = J.rows; r.status = J.status; r.cells = J.cells;

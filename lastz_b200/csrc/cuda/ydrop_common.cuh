@@ -27,13 +27,17 @@ enum { DP_OK = 0, DP_TRUNCATED = 1, DP_RING = 2, DP_TBROW = 3, DP_OPS = 4, DP_AC
 struct launch_list { u16 ix[LZB_LAUNCH_MAX]; };
 
 /* checkpoint record of a sweep, written every ckptEvery rows (a multiple of 32): CK_HDR scalar words, the active
- * segments (5 ints each, at most CK_ACT; a row with more takes no checkpoint), then 2K+1 words per thread
- * (C[K], D[K], first column) stored word-major so that the block's stores coalesce.  A sweep restarted from
- * record k continues at row (k+1)*ckptEvery + 1 exactly as if it had never stopped, against a LARGER set of
- * earlier alignments whose first rows all lie beyond that row (see gapped_sched.hpp). */
+ * segments (5 ints each, at most CK_ACT; a row with more takes no checkpoint), then the band BY COLUMN: C and D of the
+ * CK_COLS columns from the record's base column on (word rec[26], at or left of the band's first column).  Indexed by
+ * column, a record does not depend on which kernel wrote it: a sweep started by the one-warp kernel (512-column
+ * window) can be continued by the four-warp kernel (1024 columns), which is what a sweep that is about to run along an
+ * earlier alignment needs -- the dead flank beside that alignment widens the band for a few hundred rows.
+ * A sweep restarted from record k continues at row (k+1)*ckptEvery + 1 exactly as if it had never stopped, against a
+ * LARGER set of earlier alignments whose first rows all lie beyond that row (see gapped_sched.hpp). */
 #define CK_HDR 32
 #define CK_ACT 8
-#define CK_WORDS(K_, NT_) (CK_HDR + 5 * CK_ACT + (2 * (K_) + 1) * (NT_))
+#define CK_COLS 1024u
+#define CK_RECORD_WORDS (CK_HDR + 5 * CK_ACT + 2 * CK_COLS)
 
 struct dp_job {
     int reversed; u32 a1, a2, M, N;

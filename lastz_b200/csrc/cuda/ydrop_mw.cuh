@@ -238,7 +238,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, FULL = 0xFFFFFFFFu;
     dp_job* J = &jobs[ll.ix[blockIdx.x]];
     const dalign* __restrict__ al = J->al;
-    constexpr u32 CKW = CK_WORDS(K, NT);
+    constexpr u32 CKW = CK_RECORD_WORDS;
     for (u32 i = tid; i < LZB_MAX_CLASSES * LZB_MAX_CLASSES; i += NT) sh.subC[i] = sc->subC[i];
     for (u32 i = tid; i < MW_SCAP; i += NT) sh.stamp[i] = 0;
     const int rev = J->reversed; const u32 a1 = J->a1, a2 = J->a2, M = J->M, N = J->N;
@@ -295,12 +295,20 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
         used = (s64)((u64)rec[14] | ((u64)rec[15] << 32));
         best = (s32)rec[16]; bnd = (s32)rec[17]; end1 = rec[18]; end2 = rec[19]; endIsBnd = (int)rec[20];
         cells = (u64)rec[21] | ((u64)rec[22] << 32);
-        pWcol = rec[23]; pCnt = rec[24]; pIout = (s32)rec[25];
         if (tid == 0) for (int k = 0; k < 5 * nact; k++) act[k] = (int)rec[CK_HDR + k];
+        /* my columns of the band, wherever the writer kept them: first the block this thread owns at that row */
+        cb = tid * K;
+        while (cb - lane * K + WSPAN <= LY) cb += WIN;      /* the rule of the row loop: a warp wholly left of the band sits at the right end */
+        const u32 c0 = rec[26];
         const u32* tv = rec + CK_HDR + 5 * CK_ACT;
 #pragma unroll
-        for (int s = 0; s < K; s++) { C[s] = (s32)tv[(u32)s * NT + tid]; D[s] = (s32)tv[(u32)(K + s) * NT + tid]; }
-        cb = tv[(u32)(2 * K) * NT + tid];
+        for (int s = 0; s < K; s++) {
+            const u32 ix = cb + (u32)s - c0;
+            const bool in = cb + (u32)s >= c0 && ix < CK_COLS;
+            C[s] = in ? (s32)tv[ix] : LZB_NEG_INF; D[s] = in ? (s32)tv[CK_COLS + ix] : LZB_NEG_INF;
+        }
+        pWcol = 0; pCnt = 0; pIout = LZB_NEG_INF;             /* the restored C already holds the prolonged cells (edgeC is rebuilt from it below) */
+        if ((u64)RY + 2 > (u64)(LY / WSPAN) * WSPAN + WIN) status = DP_RING;      /* written by a kernel with a wider window */
         ckptCount = (u32)resume + 1;
         row = row0;
     } else {
@@ -451,14 +459,19 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
                 rec[14] = (u32)(u64)used; rec[15] = (u32)((u64)used >> 32);
                 rec[16] = (u32)best; rec[17] = (u32)bnd; rec[18] = end1; rec[19] = end2; rec[20] = (u32)endIsBnd;
                 rec[21] = (u32)cells; rec[22] = (u32)(cells >> 32);
-                rec[23] = pWcol; rec[24] = pCnt; rec[25] = (u32)pIout;
+                rec[26] = LY & ~31u;
                 for (int k = 0; k < 5 * nact; k++) rec[CK_HDR + k] = (u32)act[k];
                 J->progUsed = (u32)(u64)used; J->progRows = row;      /* lets the host estimate where the traceback will run out */
             }
+            const u32 c0 = LY & ~31u;                        /* base column of the record */
             u32* tv = rec + CK_HDR + 5 * CK_ACT;
+            for (u32 i = tid; i < 2 * CK_COLS; i += NT) tv[i] = (u32)LZB_NEG_INF;
+            __syncthreads();
 #pragma unroll
-            for (int s = 0; s < K; s++) { tv[(u32)s * NT + tid] = (u32)C[s]; tv[(u32)(K + s) * NT + tid] = (u32)D[s]; }
-            tv[(u32)(2 * K) * NT + tid] = cb;
+            for (int s = 0; s < K; s++) {
+                const u32 ix = cb + (u32)s - c0;
+                if (cb + (u32)s >= c0 && ix < CK_COLS) { tv[ix] = (u32)C[s]; tv[CK_COLS + ix] = (u32)D[s]; }
+            }
             ckptCount++;
         }
     }

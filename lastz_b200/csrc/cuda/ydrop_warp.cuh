@@ -216,7 +216,7 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     const int tbOnly = J->tbOnly, resume = J->resume;
     if (tbOnly) { status = J->status; end1 = J->end1; end2 = J->end2; }
     int* act = J->act; int nact = 0;
-    constexpr u32 CKW = CK_WORDS(K, 32);                   /* checkpoint record: see ydrop_common.cuh */
+    constexpr u32 CKW = CK_RECORD_WORDS;
     u32* const ckpt = J->ckpt; const u32 ckptCap = J->ckptCap, ckptEvery = J->ckptEvery;
     u32 ckptCount = tbOnly ? J->ckptCount : 0;
     const u32 rowLimit = J->rowLimit ? J->rowLimit : 0xFFFFFFFFu;
@@ -248,10 +248,18 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
         best = (s32)rec[16]; bnd = (s32)rec[17]; end1 = rec[18]; end2 = rec[19]; endIsBnd = (int)rec[20];
         cells = (u64)rec[21] | ((u64)rec[22] << 32);
         if (lane == 0) for (int k = 0; k < 5 * nact; k++) act[k] = (int)rec[CK_HDR + k];
+        /* my columns of the band, wherever the writer kept them: first the block this thread owns at that row */
+        S.cb = lane * K;
+        while (S.cb + K <= LY) S.cb += WIN;                 /* the rule of the row loop: a block left of the band sits 32 blocks further right */
+        const u32 c0 = rec[26];
         const u32* tv = rec + CK_HDR + 5 * CK_ACT;
 #pragma unroll
-        for (int s = 0; s < K; s++) { S.C[s] = (s32)tv[(u32)s * 32u + lane]; S.D[s] = (s32)tv[(u32)(K + s) * 32u + lane]; }
-        S.cb = tv[(u32)(2 * K) * 32u + lane];
+        for (int s = 0; s < K; s++) {
+            const u32 ix = S.cb + (u32)s - c0;
+            const bool in = S.cb + (u32)s >= c0 && ix < CK_COLS;
+            S.C[s] = in ? (s32)tv[ix] : LZB_NEG_INF; S.D[s] = in ? (s32)tv[CK_COLS + ix] : LZB_NEG_INF;
+        }
+        if ((u64)RY + 2 > (u64)(LY / (u32)K) * K + WIN) status = DP_RING;          /* written by a kernel with a wider window */
         ckptCount = (u32)resume + 1;
         row = row0;
     } else {
@@ -395,14 +403,19 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
                 rec[9] = lLim; rec[10] = rLim; rec[11] = (u32)lTyp; rec[12] = (u32)rTyp; rec[13] = (u32)nact;
                 rec[14] = (u32)(u64)used; rec[15] = (u32)((u64)used >> 32);
                 rec[16] = (u32)best; rec[17] = (u32)bnd; rec[18] = end1; rec[19] = end2; rec[20] = (u32)endIsBnd;
-                rec[21] = (u32)cells; rec[22] = (u32)(cells >> 32);
+                rec[21] = (u32)cells; rec[22] = (u32)(cells >> 32); rec[26] = LY & ~31u;
                 for (int k = 0; k < 5 * nact; k++) rec[CK_HDR + k] = (u32)act[k];
                 J->progUsed = (u32)(u64)used; J->progRows = row;      /* lets the host estimate where the traceback will run out */
             }
+            const u32 c0 = LY & ~31u;                        /* base column of the record */
             u32* tv = rec + CK_HDR + 5 * CK_ACT;
+            for (u32 i = lane; i < 2 * CK_COLS; i += 32u) tv[i] = (u32)LZB_NEG_INF;
+            __syncwarp();
 #pragma unroll
-            for (int s = 0; s < K; s++) { tv[(u32)s * 32u + lane] = (u32)S.C[s]; tv[(u32)(K + s) * 32u + lane] = (u32)S.D[s]; }
-            tv[(u32)(2 * K) * 32u + lane] = S.cb;
+            for (int s = 0; s < K; s++) {
+                const u32 ix = S.cb + (u32)s - c0;
+                if (S.cb + (u32)s >= c0 && ix < CK_COLS) { tv[ix] = (u32)S.C[s]; tv[CK_COLS + ix] = (u32)S.D[s]; }
+            }
             ckptCount++;
         }
     }

@@ -69,7 +69,7 @@ struct emu_backend {
         for (int z = old; z < want; z++) for (int s = 0; s < 2; s++) {
             host_lane& ln = L[z];
             ln.tb[s].resize((size_t)tbBytes + 64); ln.tbRow[s].resize(4096); ln.ops[s].resize(64); ln.act[s].resize(5 * 2);
-            ln.ckpt[s].resize((size_t)64 * CK_WORDS(8, 128));
+            ln.ckpt[s].resize((size_t)64 * CK_RECORD_WORDS);
             dp_job& J = jobs[2 * z + s]; memset(&J, 0, sizeof J);
             fill(z, s);
         }

@@ -115,6 +115,47 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
     else if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(jobs, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });   // the one-warp kernel (512-column window)
     else emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(jobs, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
     int bad = 0;
+    /* the same two sweeps stopped by a row limit and continued from their last checkpoint must end exactly alike */
+    if (oneWarp != 2) {
+        dp_job pj[2]; memcpy(pj, jobs, sizeof pj);
+        std::vector<u8> tb2[2]; std::vector<u32> tbRow2[2], ops2[2], ck[2]; std::vector<int> act2[2];
+        const u32 every = 64;
+        for (int side = 0; side < 2; side++) {
+            dp_job& J = pj[side];
+            tb2[side].resize((size_t)tbBytes + 64); tbRow2[side].resize(tbRow[side].size()); ops2[side].resize(ops[side].size()); act2[side].resize(5 * 16);
+            ck[side].resize((size_t)256 * CK_RECORD_WORDS);
+            J.tb = tb2[side].data(); J.tbRow = tbRow2[side].data(); J.ops = ops2[side].data(); J.act = act2[side].data();
+            J.ckpt = ck[side].data(); J.ckptCap = 256; J.ckptEvery = every; J.resume = -1; J.done = 0; J.token = 8;
+            J.rowLimit = jobs[side].rows > 3 * every ? jobs[side].rows * 2 / 3 : 0;
+        }
+        auto run = [&]() {
+            if (oneWarp) emu_launch(2, 32, [&]() { k_ydrop_warp<16>(pj, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
+            else emu_launch(2, 128, [&]() { k_ydrop_mw<8, 4>(pj, ll, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
+        };
+        run();
+        int paused = 0;
+        for (int side = 0; side < 2; side++) if (pj[side].status == DP_PAUSED) {
+            paused++;
+            if (pj[side].ckptCount == 0) { fprintf(stderr, "  side %d paused without a checkpoint\n", side); bad++; }
+            pj[side].resume = (int)pj[side].ckptCount - 1; pj[side].rowLimit = 0; pj[side].done = 0; pj[side].token = 9;
+        } else pj[side].token = 0;
+        if (paused) {
+            launch_list l2; memset(&l2, 0, sizeof l2); int n2 = 0;
+            for (int side = 0; side < 2; side++) if (pj[side].token == 9) l2.ix[n2++] = (u16)side;
+            if (oneWarp) emu_launch(n2, 32, [&]() { k_ydrop_warp<16>(pj, l2, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
+            else emu_launch(n2, 128, [&]() { k_ydrop_mw<8, 4>(pj, l2, (const dseg*)NULL, c1.data(), c2.data(), len1, len2, &g_sc, yDrop, trim); });
+        }
+        for (int side = 0; side < 2; side++) {
+            const dp_job& a = jobs[side]; const dp_job& b = pj[side];
+            if (a.status != b.status || a.score != b.score || a.end1 != b.end1 || a.end2 != b.end2 || a.rows != b.rows || a.cells != b.cells || a.nops != b.nops ||
+                memcmp(ops[side].data(), ops2[side].data(), (size_t)a.nops * 4)) {
+                fprintf(stderr, "  side %d: continued from a checkpoint: status %d/%d score %d/%d end (%u,%u)/(%u,%u) rows %u/%u cells %llu/%llu nops %u/%u\n", side, a.status, b.status, a.score, b.score,
+                        a.end1, a.end2, b.end1, b.end2, a.rows, b.rows, a.cells, b.cells, a.nops, b.nops);
+                bad++;
+            }
+        }
+        printf("        pause/continue: %d of 2 sweeps stopped at two thirds and continued from their last checkpoint\n", paused);
+    }
     for (int side = 0; side < 2; side++) if (jobs[side].done != 7 || jobs[side].opsOverflow) { fprintf(stderr, "  side %d: done=%u overflow=%d\n", side, jobs[side].done, jobs[side].opsOverflow); bad++; }
     for (int side = 0; side < 2; side++) if (jobs[side].status != DP_OK && jobs[side].status != DP_TRUNCATED) { fprintf(stderr, "  side %d: kernel status %d\n", side, jobs[side].status); bad++; }
     // assemble like ydrop_align (gapped_extend.c:2529-2560): left script in emission order, right script reversed
