@@ -182,10 +182,17 @@ struct cuda_backend {
         while ((int)gc->lanes.size() < want) {
             size_t freeB = 0, totalB = 0;
             if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) break;
-            /* keep a quarter of the device for the seed stage and the caller; one chunk is always made */
-            if (!gc->lanes.empty() && freeB < totalB / 4 + laneBytes * GX_CHUNK) break;
+            /* keep an eighth of the device for the seed stage and the caller; one chunk is always made */
+            if (!gc->lanes.empty() && freeB < totalB / 8 + laneBytes * GX_CHUNK) {
+                if (getenv("LZB_GAP_PROFILE")) fprintf(stderr, "[gx lanes] %zu lanes, %.1f GB of %.1f GB free: no more\n", gc->lanes.size(), freeB / 1e9, totalB / 1e9);
+                break;
+            }
             const int first = (int)gc->lanes.size();
-            if (make_chunk(gc)) { if (gc->lanes.empty()) { lzb_fail("no device memory for the traceback of one Y-drop lane"); return -1; } break; }
+            if (make_chunk(gc)) {
+                if (gc->lanes.empty()) { lzb_fail("no device memory for the traceback of one Y-drop lane"); return -1; }
+                if (getenv("LZB_GAP_PROFILE")) fprintf(stderr, "[gx lanes] %zu lanes, %.1f GB free: the next chunk could not be allocated\n", gc->lanes.size(), freeB / 1e9);
+                break;
+            }
             for (int z = first; z < (int)gc->lanes.size(); z++) { fill_job(z, 0); fill_job(z, 1); }
         }
         return (int)std::min<size_t>(gc->lanes.size(), (size_t)want);

@@ -35,6 +35,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unordered_map>
 #include <vector>
 
 struct hseg { int type; u32 b1, b2, e1, e2; };
@@ -439,11 +440,20 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     /* retire the anchors that lie on alignment `ai` (index into G.al; n = the trivial self alignment) */
     bool startDirty = true;                                  /* something happened that may let another anchor start */
     std::vector<u32>* pendp = NULL; bool pendReady = false;   /* (the list is declared further down) */
+    /* anchors that wait for an earlier open anchor are parked under it and come back when it is resolved or loses its lane */
+    std::unordered_map<u64, std::vector<u32> > waiters; bool pendUnsorted = false;
+    auto release_waiters = [&](u64 i) {
+        auto it = waiters.find(i);
+        if (it == waiters.end()) return;
+        if (pendReady) { pendp->insert(pendp->end(), it->second.begin(), it->second.end()); pendUnsorted = true; }
+        waiters.erase(it);
+    };
     /* take a lane away from its anchor: at once if nothing of it is running, else when its sweeps have stopped */
     auto drop_lane = [&](int z) {
         gx_lane_state& ln = lanes[z];
         laneOf[ln.anchor] = -1; ln.busy = false;
-        if (!fin[ln.anchor] && pendReady) pendp->insert(std::lower_bound(pendp->begin(), pendp->end(), (u32)ln.anchor), (u32)ln.anchor);   /* back among the waiting */
+        if (!fin[ln.anchor] && pendReady) { pendp->push_back((u32)ln.anchor); pendUnsorted = true; }   /* back among the waiting */
+        release_waiters(ln.anchor);
         for (int side = 0; side < 2; side++) {
             ln.s[side].res.ops.clear();
             if (ln.s[side].phase == SIDE_RUNNING) B.job(z, side)->abort = 1; else ln.s[side].phase = SIDE_IDLE;
@@ -541,7 +551,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     /* how far off the expected reach may be: a finished sweep gives the row itself (sweeps of one call end within a few
      * hundred rows of each other); an estimate is as good as the stretch of rows it was taken over */
     auto slack_frac = [&]() -> double { return reachExact ? 0.003 : reachSeen >= 65536 ? 0.005 : reachSeen >= 16384 ? 0.012 : 0.03; };
-    bool anchorsWaitForEstimate = true;
+    bool anchorsWaitForEstimate = true; double lastScanAt = 0;
 
     /* first row of lane z's sweep `side` in which an alignment committed since the sweep's snapshot shows up (0xFFFFFFFF: none) */
     auto first_touched_row = [&](int z, int side) -> u32 {
@@ -709,6 +719,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (ln.s[0].phase == SIDE_DONE && ln.s[1].phase == SIDE_DONE && ln.s[0].snapshot == G.committed.size() && ln.s[1].snapshot == G.committed.size()) {
                     const u64 i = hd;
                     commit_anchor(i, ln.s[0].res, ln.s[1].res);
+                    release_waiters(i);
                     ln.busy = false; ln.s[0].phase = ln.s[1].phase = SIDE_IDLE; ln.s[0].res.ops.clear(); ln.s[1].res.ops.clear(); laneOf[i] = -1;
                     startDirty = true;
                     if (prof) pfCommit += now() - t0;
@@ -736,10 +747,11 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 reachTrunc = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
                 reachSeen = pr - sd.prog0Rows;
             }
-            if (reachTrunc > 0 && slack_frac() != lastSlackFrac) startDirty = true;     /* the estimate got sharper: look at the waiting anchors again */
+            /* the estimate gets sharper: look at the anchors that wait for it again, every 20 ms */
+            if (reachTrunc > 0 && (slack_frac() != lastSlackFrac || now() - lastScanAt > 0.02)) startDirty = true;
         }
         if (startDirty) {
-            startDirty = false;
+            startDirty = false; lastScanAt = now();
             int freeLanes = 0;
             for (int z = 0; z < have; z++) if (lane_free(z)) freeLanes++;
             auto more_lanes = [&]() -> int {                    /* made as they are needed */
@@ -773,6 +785,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             std::vector<std::pair<u32, int> > lanePos;
             for (int z = 0; z < have; z++) if (lanes[z].busy) lanePos.push_back(std::make_pair(apos1[lanes[z].anchor], z));
             std::sort(lanePos.begin(), lanePos.end());
+            if (pendUnsorted) { std::sort(pend.begin(), pend.end()); pend.erase(std::unique(pend.begin(), pend.end()), pend.end()); pendUnsorted = false; }
             size_t keep = 0, q = 0; bool waitingForEstimate = false;
             for (; q < pend.size() && (freeLanes > 0 || have < W); q++) {
                 const u64 j = pend[q];
@@ -787,7 +800,6 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                      *     can matter that lie farther out than every better-scoring one there (a better one farther out covers the
                      *     rest whether the earlier anchor reaches it or not), so the others wait as well;
                      *   an anchor started from such an edge may yet be skipped, so it holds nobody back. */
-                    if (blocker[j] >= 0 && !fin[blocker[j]] && laneOf[blocker[j]] >= 0) continue;
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
                     bool tooEarly = false; int edgeLane = -1, edgeSide = 0; double edgeDist = 0; int edges = 0;
@@ -818,9 +830,9 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                         }
                         if (blocker[j] >= 0 && trace) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, known ? "done" : "running");
                     }
-                    if (blocker[j] >= 0) continue;
+                    if (blocker[j] >= 0) { waiters[(u64)blocker[j]].push_back((u32)j); keep--; continue; }     /* parked */
                     if (tooEarly) { waitingForEstimate = true; continue; }
-                    if (edges > 1) { blocker[j] = (int)lanes[edgeLane].anchor; continue; }     /* at two edges at once: nothing to start yet */
+                    if (edges > 1) { blocker[j] = (int)lanes[edgeLane].anchor; waiters[(u64)blocker[j]].push_back((u32)j); keep--; continue; }     /* at two edges at once: nothing to start yet */
                     if (edges == 1) {
                         gx_lane_state& li = lanes[edgeLane];
                         li.edgeMax[edgeSide] = edgeDist;

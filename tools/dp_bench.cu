@@ -40,6 +40,7 @@ int main(int argc, char** argv) {
     const u32 L = argc > 1 ? (u32)atol(argv[1]) : 1000000u;
     const u32 tbMiB = argc > 2 ? (u32)atol(argv[2]) : 80u;
     const int copies = argc > 3 ? atoi(argv[3]) : 296;
+    const int ckpt = argc > 4 ? atoi(argv[4]) : 1;          /* checkpoints every 256 rows, as the product takes them */
     for (int k = 0; k < LZB_LAUNCH_MAX; k++) g_ll.ix[k] = (u16)k;
     std::string t(L, 'A'), q; std::vector<u32> qposOf(L);
     st = 20260925; for (u32 i = 0; i < L; i++) t[i] = "ACGT"[next64() >> 62];
@@ -88,12 +89,13 @@ int main(int argc, char** argv) {
         CK(cudaMalloc(&J.tbRow, (size_t)tbRowCap * 4)); J.tbRowCap = tbRowCap;
         J.opsCap = 1u << 18; CK(cudaMalloc(&J.ops, (size_t)J.opsCap * 4));
         J.actCap = 16; CK(cudaMalloc(&J.act, 16 * 5 * 4));
+        if (ckpt) { CK(cudaMalloc(&J.ckpt, (size_t)1024 * CK_RECORD_WORDS * 4)); J.ckptCap = 1024; J.ckptEvery = 256; }
     }
     dp_job* dj; CK(cudaMalloc(&dj, njobs * sizeof(dp_job)));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    printf("pair %u x %u bp, anchor (%u,%u), traceback %u MiB, copies %d\n", len1, len2, a1, a2, tbMiB, copies);
+    printf("pair %u x %u bp, anchor (%u,%u), traceback %u MiB, copies %d, checkpoints %s\n", len1, len2, a1, a2, tbMiB, copies, ckpt ? "every 256 rows" : "off");
     printf("%-12s %8s | %10s %10s %8s %8s %6s | %10s %10s\n", "kernel", "threads", "rows(rev)", "rows(fwd)", "cells/row", "ms", "status", "us/row x1", "us/row xN");
-    for (int gN : { 148, 296, 444, 592 }) if (gN <= njobs)
+    for (int gN : { 148, 332, 592 }) if (gN <= njobs)
     for (auto& s : shapes) {
         double usrow[2] = { 0, 0 }; u32 rows[2] = { 0, 0 }; double ms1 = 0; int stt[2] = { 0, 0 }; double cpr = 0;
         for (int pass = 0; pass < 2; pass++) {
