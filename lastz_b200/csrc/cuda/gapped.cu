@@ -222,7 +222,11 @@ struct cuda_backend {
     int drain() {
         for (size_t k = 0; k < 2 * gc->lanes.size(); k++) {
             dp_job& J = gc->h_jobs[k];
-            while (gc->launched[k] != 0 && J.done != gc->launched[k]) { if (!poll()) return lzb_fail("Y-drop kernel failed: %s", gc->err); }
+            const auto t0 = std::chrono::steady_clock::now();
+            while (gc->launched[k] != 0 && J.done != gc->launched[k]) {
+                if (!poll()) return lzb_fail("Y-drop kernel failed: %s", gc->err);
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0) return lzb_fail("a Y-drop sweep did not come back within 120 s");
+            }
         }
         return 0;
     }
@@ -253,7 +257,6 @@ struct cuda_backend {
             /* the device-side addresses of the job's list */
             dp_job& J = gc->h_jobs[ix[k]]; cuda_lane& ln = gc->lanes[ix[k] >> 1];
             if (J.listv == ln.list[ix[k] & 1]) J.listv = ln.d_list[ix[k] & 1];
-            gc->launched[ix[k]] = J.token;
         }
         std::atomic_thread_fence(std::memory_order_seq_cst);
         /* A stream runs its launches one after the other, and a launch lasts as long as its longest sweep: a short resume
@@ -278,7 +281,10 @@ struct cuda_backend {
         if (mode == 0)
             k_ydrop_mw<8, 4><<<n, 128, 0, st>>>(gc->d_jobs, ll, gc->d_segs, gc->cls1, gc->cls2, gc->len1, gc->len2, c->d_sc, gc->yDrop, gc->trim);
         else if (mode == 1)
-            k_ydrop_warp<16><<<n, 32, 0, st>>>(gc->d_jobs, ll, gc->d_segs, gc->cls1, gc->cls2, gc->len1, gc->len2, c->d_sc, gc->yDrop, gc->trim);
+            /* 47 KB of (unused) dynamic shared memory per one-warp CTA: at most four of them fit an SM, one per scheduler --
+             * left to itself the block scheduler stacks dozens of 32-thread CTAs on some SMs while others idle, and the
+             * sweeps there run at a fraction of their speed (measured: 1.8 us a row alone, 3.4 median, 9 worst) */
+            k_ydrop_warp<16><<<n, 32, 47 * 1024, st>>>(gc->d_jobs, ll, gc->d_segs, gc->cls1, gc->cls2, gc->len1, gc->len2, c->d_sc, gc->yDrop, gc->trim);
         else {
             const u32 rg = ring(mode);
             size_t smem = (size_t)rg * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
@@ -286,6 +292,7 @@ struct cuda_backend {
         }
         c->launches++;
         CUDA_TRY(cudaGetLastError());
+        for (int k = 0; k < n; k++) gc->launched[ix[k]] = gc->h_jobs[ix[k]].token;      /* only now is there something to wait for */
         return 0;
     }
     bool poll() {
@@ -345,6 +352,7 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         gc->segsCap = 4u << 20; CUDA_TRY(cudaMalloc(&gc->d_segs, gc->segsCap * sizeof(dseg)));
         gc->alignsCap = 1u << 18; CUDA_TRY(cudaMalloc(&gc->d_aligns, gc->alignsCap * sizeof(dalign)));
         CUDA_TRY(cudaFuncSetAttribute(k_ydrop<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_ydrop_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 47 * 1024));
     }
     gc->cls1 = t->d_cls; gc->cls2 = q->d_cls; gc->len1 = t->len; gc->len2 = q->len; gc->yDrop = P->yDrop; gc->trim = P->trimToPeak;
     cuda_backend B; B.gc = gc;

@@ -35,6 +35,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -223,7 +224,11 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     const u32 tbLen = 1 + (P->tracebackBytes - 8);                    /* new_traceback :2272-2290 */
     const u32 len1 = in.len1, len2 = in.len2;
     const u8* h1 = in.h_seq1; const u8* h2 = in.h_seq2;
+    /* LZB_GAP_TRACE: the scheduler's decisions, collected in memory and written to stderr when the call ends (writing as it
+     * goes would slow the very loop it describes) */
     const bool trace = getenv("LZB_GAP_TRACE") != NULL;
+    std::string traceBuf;
+#define GX_TRACE(...) do { if (trace) { char b_[512]; int n_ = snprintf(b_, sizeof b_, __VA_ARGS__); traceBuf.append(b_, (size_t)(n_ < 511 ? n_ : 511)); } } while (0)
     const bool prof = getenv("LZB_GAP_PROFILE") != NULL;
 
     /* [multi] sequences (NUL-separated partitions, sequences.h:188-191): a sweep ends at the NULs around its anchor
@@ -301,7 +306,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     std::vector<int> laneOf(n, -1);
     std::vector<u8> fin(n, 0);                               /* 1 = skipped / committed / dropped */
     u32 tokenCounter = 0;
-    double pfCommit = 0, pfPoll = 0, pfStart = 0, pfValidate = 0; u64 pfPolls = 0, pfLaunches = 0, pfJobs = 0, pfResumes = 0, pfRestarts = 0, pfWasted = 0;
+    u64 pfPasses = 0; double pfCommit = 0, pfPoll = 0, pfStart = 0, pfValidate = 0; u64 pfPolls = 0, pfLaunches = 0, pfJobs = 0, pfResumes = 0, pfRestarts = 0, pfWasted = 0;
 
     /* the anchor POINTS (commit overwrites al[i].pos1/pos2 with the alignment's start) and the anchors by
      * seq-1 position: when an alignment is committed the anchors lying on it are retired there and then
@@ -346,7 +351,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         return 0;
     };
 
-    const double slackRows = getenv("LZB_GAP_SLACK") ? atof(getenv("LZB_GAP_SLACK")) : 1000.0;   /* margin around an expected reach, rows (tests: negative = start everything) */
+    const double slackRows = getenv("LZB_GAP_SLACK") ? atof(getenv("LZB_GAP_SLACK")) : 300.0;   /* margin around an expected reach, rows (tests: negative = start everything) */
     const bool rowLimits = !(getenv("LZB_GAP_ROWLIMIT") && !atoi(getenv("LZB_GAP_ROWLIMIT")));
     double reachShared = 0;                                  /* the scheduler's current estimate of a sweep's length (0: none yet) */
     auto reachKnown = [&]() { return reachShared > 0; };
@@ -410,7 +415,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 const s64 dj = (s64)aPos1 - (s64)aPos2;
                 for (int zz = 0; zz < (int)lanes.size(); zz++) {
                     gx_lane_state& lo = lanes[zz];
-                    if (!lo.busy || lo.anchor >= ln.anchor) continue;
+                    if (!lo.busy || lo.anchor >= ln.anchor || lo.unsure) continue;     /* (an anchor that may yet be skipped is no reason to stop) */
                     const u32 ip = apos1[lo.anchor];
                     if ((side == 0) != (ip < aPos1) || ip == aPos1) continue;
                     if (llabs(((s64)ip - (s64)apos2[lo.anchor]) - dj) > 4000) continue;
@@ -477,7 +482,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             if (bp.type == SEG_DIAG) d = (s32)(bp.b2 - pos2) + (s32)(pos1 - bp.b1); else d = (s32)(bp.b2 - pos2);
             if (d != 0) continue;
             fin[j] = 1;                                      /* on an alignment committed earlier in the order: skipped for good (:1335) */
-            if (laneOf[j] >= 0) { if (trace) fprintf(stderr, "[gx %.4f] retire a=%u pos1=%u (on alignment a=%d) while it held a lane\n", now(), j, pos1, ai); drop_lane(laneOf[j]); }
+            if (laneOf[j] >= 0) { GX_TRACE("[gx %.4f] retire a=%u pos1=%u (on alignment a=%d) while it held a lane\n", now(), j, pos1, ai); drop_lane(laneOf[j]); }
         }
     };
     if (G.obi == (int)n) retire_covered((int)n);
@@ -489,7 +494,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         /* the reference's counters see exactly the DPs whose results are used (gapped_extend.c:3593,3776) */
         G.st.dpCells += rl.cells + rr.cells; G.st.dpRows += (u64)rl.rows + rr.rows;
         G.st.truncated += (rl.status == DP_TRUNCATED) + (rr.status == DP_TRUNCATED);
-        if (trace) fprintf(stderr, "[gx %.4f] commit a=%llu pos1=%u rows=%u+%u\n", now(), (unsigned long long)i, m.pos1, rl.rows, rr.rows);
+        GX_TRACE("[gx %.4f] commit a=%llu pos1=%u rows=%u+%u\n", now(), (unsigned long long)i, m.pos1, rl.rows, rr.rows);
         u32 a1 = m.pos1, a2 = m.pos2;
         u32 start1 = a1 + 1 - rl.end1, start2 = a2 + 1 - rl.end2, stop1 = a1 + rr.end1, stop2 = a2 + rr.end2;
         lzb_editscript* sl = es_new((u32)(rl.ops.size() + rr.ops.size() + 4));
@@ -550,8 +555,8 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     auto reach = [&]() -> double { return reachTrunc > 0 ? reachTrunc : reachPrior; };
     /* how far off the expected reach may be: a finished sweep gives the row itself (sweeps of one call end within a few
      * hundred rows of each other); an estimate is as good as the stretch of rows it was taken over */
-    auto slack_frac = [&]() -> double { return reachExact ? 0.003 : reachSeen >= 65536 ? 0.005 : reachSeen >= 16384 ? 0.012 : 0.03; };
-    bool anchorsWaitForEstimate = true; double lastScanAt = 0;
+    /* (measured on the 50 Mbp pair: the estimate from 4096 rows is 0.25 % off, from 16k rows 0.02 %; finished sweeps differ by +-100 rows) */
+    auto slack_frac = [&]() -> double { return reachExact ? 0.001 : reachSeen >= 16384 ? 0.002 : 0.006; };
 
     /* first row of lane z's sweep `side` in which an alignment committed since the sweep's snapshot shows up (0xFFFFFFFF: none) */
     auto first_touched_row = [&](int z, int side) -> u32 {
@@ -580,7 +585,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         G.st.redone++;
         const int rec = record_before(sd, firstRow);
         if (rec >= 0) pfResumes++; else pfRestarts++;
-        if (trace) fprintf(stderr, "[gx %.4f] a=%llu side=%d touched at row %u of %u: %s %d\n", now(), (unsigned long long)ln.anchor, side, firstRow, sd.res.rows, rec >= 0 ? "resume from record" : "restart", rec);
+        GX_TRACE("[gx %.4f] a=%llu side=%d touched at row %u of %u: %s %d\n", now(), (unsigned long long)ln.anchor, side, firstRow, sd.res.rows, rec >= 0 ? "resume from record" : "restart", rec);
         sd.res.ops.clear();
         if (queue_side(z, side, rec, false)) return -1;
         return 1;
@@ -589,7 +594,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     auto continue_paused = [&](int z, int side) -> int {
         gx_lane_state& ln = lanes[z]; gx_side& sd = ln.s[side];
         const int rec = record_before(sd, first_touched_row(z, side));
-        if (trace) fprintf(stderr, "[gx %.4f] a=%llu side=%d paused at row %u goes on from record %d\n", now(), (unsigned long long)ln.anchor, side, sd.res.rows, rec);
+        GX_TRACE("[gx %.4f] a=%llu side=%d paused at row %u goes on from record %d\n", now(), (unsigned long long)ln.anchor, side, sd.res.rows, rec);
         pfResumes++;
         return queue_side(z, side, rec, false);
     };
@@ -600,7 +605,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         laneOf[j] = z;
         for (int side = 0; side < 2; side++) { ln.s[side].mode = firstMode; ln.s[side].ckptCount = 0; ln.s[side].ckptEvery = 0; ln.s[side].res.ops.clear(); ln.s[side].prog0Rows = ln.s[side].prog0Used = 0; }
         B.job(z, 0)->abort = 0; B.job(z, 1)->abort = 0;
-        if (trace) fprintf(stderr, "[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu held=%d\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size(), deferSide);
+        GX_TRACE("[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu held=%d\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size(), deferSide);
         for (int side = 0; side < 2; side++) { ln.s[side].phase = SIDE_IDLE; if (side != deferSide && queue_side(z, side, -1, false)) return -1; }
         return 0;
     };
@@ -622,7 +627,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         } else if (J.status == DP_TBROW || J.status == DP_ACT) { if (B.grow(z, side, J.status)) return -1; again = 1; }
         else if (J.opsOverflow) { if (B.grow(z, side, DP_OPS)) return -1; again = 2; }
         if (again) {
-            if (trace) fprintf(stderr, "[gx %.4f] rerun a=%llu side=%d status=%d overflow=%d mode=%d\n", now(), (unsigned long long)ln.anchor, side, J.status, J.opsOverflow, sd.mode);
+            GX_TRACE("[gx %.4f] rerun a=%llu side=%d status=%d overflow=%d mode=%d\n", now(), (unsigned long long)ln.anchor, side, J.status, J.opsOverflow, sd.mode);
             return queue_side(z, side, again == 2 ? -1 : ringRec, again == 2);
         }
         dp_result& r = sd.res;
@@ -632,7 +637,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         sd.ckptCount = J.ckptCount; sd.ckptEvery = sd.mode <= 1 ? B.ckpt_every() : 0;
         sd.phase = J.status == DP_PAUSED ? SIDE_PAUSED : SIDE_DONE;
         if (r.status == DP_TRUNCATED) { reachTrunc = reachExact ? 0.8 * reachTrunc + 0.2 * r.rows : (double)r.rows; if (!reachExact) startDirty = true; reachExact = true; }
-        if (trace) fprintf(stderr, "[gx %.4f] done a=%llu side=%d rows=%u end1=%u status=%d mode=%d ckpts=%u\n", now(), (unsigned long long)ln.anchor, side, r.rows, r.end1, r.status, sd.mode, sd.ckptCount);
+        GX_TRACE("[gx %.4f] done a=%llu side=%d rows=%u end1=%u status=%d mode=%d ckpts=%u\n", now(), (unsigned long long)ln.anchor, side, r.rows, r.end1, r.status, sd.mode, sd.ckptCount);
         return 0;
     };
 
@@ -642,11 +647,12 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     for (u64 i = 0; i < n; i++) pend[i] = (u32)i;
     double lastSlackFrac = -1;
     pendp = &pend; pendReady = true;
-    u64 hd = 0;
+    u64 hd = 0; double lastEventAt = -1;
     while (true) {
         while (hd < n && fin[hd]) hd++;
         if (hd >= n) break;
         bool progressed = false;
+        if (lastEventAt < 0) lastEventAt = now();
         /* 1. collect finished launches */
         double t0 = prof ? now() : 0;
         for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
@@ -693,7 +699,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (!anchor_neighbours(G, y, &coverer)) return fail("internal error: anchor %llu lies on alignment %d but was not retired", (unsigned long long)ln.anchor, coverer);
                 if (y.left1.al != ln.left1.al || y.left1.sg != ln.left1.sg || y.right1.al != ln.right1.al || y.right1.sg != ln.right1.sg) {
                     if (anyRunning) continue;                 /* both sweeps restart once the running one is back */
-                    if (trace) fprintf(stderr, "[gx %.4f] a=%llu new neighbours: restart\n", now(), (unsigned long long)ln.anchor);
+                    GX_TRACE("[gx %.4f] a=%llu new neighbours: restart\n", now(), (unsigned long long)ln.anchor);
                     G.st.redone += 2; pfRestarts += 2;
                     ln.left1 = y.left1; ln.right1 = y.right1;
                     for (int side = 0; side < 2; side++) { ln.s[side].res.ops.clear(); if (side != ln.deferSide && queue_side(z, side, -1, false)) return -1; }
@@ -734,7 +740,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         /* no sweep has finished yet to say how far sweeps go: the running ones report their progress.  Two reports of one
          * sweep give the traceback bytes a row takes once the band has settled, hence the row where the traceback will
          * run out; the longer the sweep has run, the better the estimate. */
-        if (!reachExact && anchorsWaitForEstimate) {
+        if (!reachExact) {
             for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) {
                 gx_side& sd = lanes[z].s[side];
                 if (!lanes[z].busy || sd.phase != SIDE_RUNNING) continue;
@@ -744,14 +750,16 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (sd.prog0Rows == 0) { sd.prog0Rows = pr; sd.prog0Used = pu; continue; }
                 if (pr < sd.prog0Rows + 4096 || pu <= sd.prog0Used || pr - sd.prog0Rows <= reachSeen) continue;
                 const double perRow = (double)(pu - sd.prog0Used) / (double)(pr - sd.prog0Rows);
+                const double before = slack_frac();
                 reachTrunc = pr + ((double)tbLen - pu - 2.0 * perRow) / perRow;
                 reachSeen = pr - sd.prog0Rows;
+                if (slack_frac() != before || (reachSeen >> 11) > ((reachSeen - 256) >> 11)) GX_TRACE("[gx %.4f] estimate a=%llu: sweeps will run %.0f rows (from %u rows of a=%llu side %d)\n", now(), (unsigned long long)lanes[z].anchor, reachTrunc, reachSeen, (unsigned long long)lanes[z].anchor, side);
             }
-            /* the estimate gets sharper: look at the anchors that wait for it again, every 20 ms */
-            if (reachTrunc > 0 && (slack_frac() != lastSlackFrac || now() - lastScanAt > 0.02)) startDirty = true;
+            /* the first estimate, and every sharper one, lets more anchors be judged */
+            if (reachTrunc > 0 && slack_frac() != lastSlackFrac) startDirty = true;
         }
         if (startDirty) {
-            startDirty = false; lastScanAt = now();
+            startDirty = false; pfPasses++;
             int freeLanes = 0;
             for (int z = 0; z < have; z++) if (lane_free(z)) freeLanes++;
             auto more_lanes = [&]() -> int {                    /* made as they are needed */
@@ -772,7 +780,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     if (victim < 0 || ln.anchor > lanes[victim].anchor) victim = z;
                 }
                 if (victim >= 0) {
-                    if (trace) fprintf(stderr, "[gx %.4f] lane %d taken back from a=%llu for the head anchor %llu\n", now(), victim, (unsigned long long)lanes[victim].anchor, (unsigned long long)hd);
+                    GX_TRACE("[gx %.4f] lane %d taken back from a=%llu for the head anchor %llu\n", now(), victim, (unsigned long long)lanes[victim].anchor, (unsigned long long)hd);
                     drop_lane(victim); startDirty = false;
                     freeLanes = 1;
                 } else startDirty = true;                     /* look again when a sweep has finished */
@@ -786,24 +794,24 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             for (int z = 0; z < have; z++) if (lanes[z].busy) lanePos.push_back(std::make_pair(apos1[lanes[z].anchor], z));
             std::sort(lanePos.begin(), lanePos.end());
             if (pendUnsorted) { std::sort(pend.begin(), pend.end()); pend.erase(std::unique(pend.begin(), pend.end()), pend.end()); pendUnsorted = false; }
-            size_t keep = 0, q = 0; bool waitingForEstimate = false;
+            size_t keep = 0, q = 0;
+            int unsureRunning = 0;
+            for (int z = 0; z < have; z++) if (lanes[z].busy && lanes[z].unsure) unsureRunning++;
             for (; q < pend.size() && (freeLanes > 0 || have < W); q++) {
                 const u64 j = pend[q];
                 if (fin[j] || laneOf[j] >= 0) continue;          /* resolved or started since: leaves the list */
                 pend[keep++] = (u32)j;
-                int deferSide = -1; u64 deferOn = 0;
+                bool unsure = false;
                 if (j != hd && slackRows >= 0) {
                     /* Will an earlier anchor that is still open come to cover this one?  (Scheduling only.)
                      *   well inside its expected reach: yes -- wait for its commit (the reference skips such anchors, :1330);
-                     *   at the edge of its reach: nobody knows yet.  The sweep AWAY from it is long either way and starts now, the
-                     *     sweep towards it is held back until it is committed (short then).  Of the anchors at one edge only those
-                     *     can matter that lie farther out than every better-scoring one there (a better one farther out covers the
-                     *     rest whether the earlier anchor reaches it or not), so the others wait as well;
-                     *   an anchor started from such an edge may yet be skipped, so it holds nobody back. */
+                     *   near the edge of its reach: nobody knows yet -- it starts (its sweep towards the earlier anchor stops short
+                     *     of that anchor's expected alignment, see queue_side), but as it may yet be skipped it holds nobody back,
+                     *     and only so many lanes go to such anchors;
+                     *   before any sweep has said how far sweeps go, only anchors far from every started one start. */
                     blocker[j] = -1;
                     const s64 dj = (s64)apos1[j] - (s64)apos2[j];
-                    bool tooEarly = false; int edgeLane = -1, edgeSide = 0; double edgeDist = 0; int edges = 0;
-                    /* only the open anchors within reach matter: the lanes sorted by their anchor's position, walked outwards */
+                    bool tooEarly = false;
                     const double zone = calibrated ? 1.06 * rr + slackRows + 16 : 2.5 * reachPrior;
                     const u32 pj = apos1[j];
                     const size_t mid = std::lower_bound(lanePos.begin(), lanePos.end(), std::make_pair(pj, -1)) - lanePos.begin();
@@ -812,32 +820,23 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                         if (fabs((double)lanePos[w].first - (double)pj) > zone) break;
                         const int z = lanePos[w].second;
                         gx_lane_state& ln = lanes[z];
-                        if (!ln.busy || ln.anchor >= j || ln.unsure) continue;
+                        if (!ln.busy || ln.anchor >= j) continue;
                         const u64 i = ln.anchor;
                         const s64 di = (s64)apos1[i] - (s64)apos2[i];
                         if (llabs(di - dj) > 4000) continue;
                         const int side = apos1[j] < apos1[i] ? 0 : 1;
                         const double dist = fabs((double)apos1[j] - (double)apos1[i]);
-                        if (!calibrated) { if (dist < 2.5 * reachPrior) tooEarly = true; continue; }
+                        if (!calibrated) { tooEarly = true; continue; }
                         const bool known = ln.s[side].phase == SIDE_DONE;
                         const double ext = known ? (double)ln.s[side].res.end1 : rr;
-                        const double slack = (known ? 0.003 : slackFrac) * ext + slackRows;
-                        if (dist <= ext - slack) blocker[j] = (int)i;
-                        else if (dist <= ext + slack) {
-                            if (!known && slackFrac > 0.012) tooEarly = true;        /* decide when the estimate is sharper */
-                            else if (dist <= ln.edgeMax[side]) blocker[j] = (int)i;     /* a better anchor farther out has this edge */
-                            else { edges++; edgeLane = z; edgeSide = side; edgeDist = dist; }
-                        }
-                        if (blocker[j] >= 0 && trace) fprintf(stderr, "[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, known ? "done" : "running");
+                        const double slack = (known ? 0.001 : slackFrac) * ext + slackRows;
+                        if (dist <= ext - slack) { if (ln.unsure) unsure = true; else blocker[j] = (int)i; }
+                        else if (dist <= ext + slack) unsure = true;
+                        if (blocker[j] >= 0 && j < 6000) GX_TRACE("[gx %.4f] wait a=%llu pos1=%u for a=%llu (dist %.0f of %.0f, side %d %s)\n", now(), (unsigned long long)j, apos1[j], (unsigned long long)i, dist, ext, side, known ? "done" : "running");
                     }
                     if (blocker[j] >= 0) { waiters[(u64)blocker[j]].push_back((u32)j); keep--; continue; }     /* parked */
-                    if (tooEarly) { waitingForEstimate = true; continue; }
-                    if (edges > 1) { blocker[j] = (int)lanes[edgeLane].anchor; waiters[(u64)blocker[j]].push_back((u32)j); keep--; continue; }     /* at two edges at once: nothing to start yet */
-                    if (edges == 1) {
-                        gx_lane_state& li = lanes[edgeLane];
-                        li.edgeMax[edgeSide] = edgeDist;
-                        deferSide = apos1[j] > apos1[li.anchor] ? 0 : 1; deferOn = li.anchor;
-                    }
+                    if (tooEarly) continue;
+                    if (unsure && unsureRunning >= std::max(4, W / 4)) continue;
                 }
                 galn& y = G.al[j];
                 int coverer = -1;
@@ -845,18 +844,18 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (freeLanes == 0) { if (more_lanes()) return -1; if (freeLanes == 0) break; }
                 int fl = -1;
                 for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
-                if (start_anchor(fl, j, deferSide, deferOn)) return -1;
+                if (start_anchor(fl, j, -1, 0)) return -1;
+                lanes[fl].unsure = unsure; if (unsure) unsureRunning++;
                 lanePos.insert(std::lower_bound(lanePos.begin(), lanePos.end(), std::make_pair(apos1[j], fl)), std::make_pair(apos1[j], fl));
                 freeLanes--; progressed = true; keep--;
                 if (j != hd) G.st.speculated++;
             }
             for (; q < pend.size(); q++) pend[keep++] = pend[q];
             pend.resize(keep);
-            anchorsWaitForEstimate = waitingForEstimate;
         }
         if (prof) pfStart += now() - t0;
         if (flush()) return -1;
-        if (progressed) continue;
+        if (progressed) { lastEventAt = now(); continue; }
         /* 5. nothing to decide: wait for the device */
         bool any = false;
         for (int z = 0; z < have && !any; z++) if (lanes[z].s[0].phase == SIDE_RUNNING || lanes[z].s[1].phase == SIDE_RUNNING) any = true;
@@ -864,6 +863,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         t0 = prof ? now() : 0;
         if (!B.poll()) return fail("Y-drop kernel failed: %s", B.error());
         if (prof) { pfPoll += now() - t0; pfPolls++; }
+        if (now() - lastEventAt > 180.0) return fail("the gapped stage made no progress for 180 s (anchor %llu)", (unsigned long long)hd);
     }
     /* sweeps of retired anchors that are still running: ask them to stop and wait (their buffers are reused by the next call) */
     for (int z = 0; z < have; z++) for (int side = 0; side < 2; side++) if (lanes[z].s[side].phase == SIDE_RUNNING) B.job(z, side)->abort = 1;
@@ -873,12 +873,13 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
             if (!B.poll()) return fail("Y-drop kernel failed: %s", B.error());
         }
     }
+    if (trace) fwrite(traceBuf.data(), 1, traceBuf.size(), stderr);
     if (prof)
         fprintf(stderr, "[gx profile] lanes=%d wall=%.3f validate_s=%.3f commit_s=%.3f start_s=%.3f poll_s=%.3f polls=%llu launches=%llu jobs=%llu resumes=%llu restarts=%llu "
-                        "retired_while_held=%llu extended=%llu redone=%llu rows=%llu committed=%zu reach=%.0f\n",
+                        "retired_while_held=%llu extended=%llu redone=%llu rows=%llu committed=%zu reach=%.0f seen=%u passes=%llu\n",
                 have, now(), pfValidate, pfCommit, pfStart, pfPoll, (unsigned long long)pfPolls, (unsigned long long)pfLaunches, (unsigned long long)pfJobs,
                 (unsigned long long)pfResumes, (unsigned long long)pfRestarts, (unsigned long long)pfWasted, (unsigned long long)G.st.anchorsExtended,
-                (unsigned long long)G.st.redone, (unsigned long long)G.st.dpRows, G.committed.size(), reach());
+                (unsigned long long)G.st.redone, (unsigned long long)G.st.dpRows, G.committed.size(), reach(), reachSeen, (unsigned long long)pfPasses);
     lzb_alignel* head = NULL, *last = NULL;
     for (int o = G.obi; o >= 0; o = G.al[o].next) {
         galn& m = G.al[o];

@@ -115,5 +115,25 @@ int main(int argc, char** argv) {
         printf("%-12s %4d CTAs | %10u %10u %8.1f %8.2f %3d/%-3d | %10.3f %10.3f\n", s.name, gN, rows[0], rows[1], cpr, ms1, stt[0], stt[1], usrow[0], usrow[1]);
         fflush(stdout);
     }
+    /* two grids on two streams, the way the anchor loop launches them: 86 sweeps, then 398 more */
+    {
+        cudaStream_t sa, sb; CK(cudaStreamCreateWithFlags(&sa, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+        for (int dyn : { 0, 47 * 1024 }) {
+            CK(cudaFuncSetAttribute(k_ydrop_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 47 * 1024));
+            CK(cudaMemcpy(dj, hj.data(), njobs * sizeof(dp_job), cudaMemcpyHostToDevice));
+            launch_list la = g_ll, lb = g_ll;
+            for (int k = 0; k < LZB_LAUNCH_MAX - 86; k++) lb.ix[k] = (u16)(86 + k);
+            cudaEvent_t ea0, ea1, eb1; CK(cudaEventCreate(&ea0)); CK(cudaEventCreate(&ea1)); CK(cudaEventCreate(&eb1));
+            CK(cudaEventRecord(ea0, sa));
+            k_ydrop_warp<16><<<86, 32, dyn, sa>>>(dj, la, (const dseg*)NULL, d1, d2, len1, len2, dsc, 9400, 1);
+            CK(cudaEventRecord(ea1, sa));
+            CK(cudaStreamWaitEvent(sb, ea0, 0));
+            k_ydrop_warp<16><<<398, 32, dyn, sb>>>(dj, lb, (const dseg*)NULL, d1, d2, len1, len2, dsc, 9400, 1);
+            CK(cudaEventRecord(eb1, sb));
+            CK(cudaDeviceSynchronize());
+            float ma, mb; CK(cudaEventElapsedTime(&ma, ea0, ea1)); CK(cudaEventElapsedTime(&mb, ea0, eb1));
+            printf("two grids (86 + 398 one-warp sweeps, %d KB dynamic smem): first done after %.1f ms, second after %.1f ms\n", dyn / 1024, ma, mb);
+        }
+    }
     return 0;
 }
