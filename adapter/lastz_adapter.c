@@ -30,6 +30,7 @@
 #include "edit_script.h"
 #include "seed_search.h"
 #include "gapped_extend.h"
+#include "lastz.h"
 #include "lastz_b200.h"
 
 static lzb_ctx*    g_ctx;
@@ -38,7 +39,8 @@ static postable*   g_targetKey;
 static lzb_seed    g_seed;
 static lzb_query*  g_query;           /* the query strand of the last seed_hit_search: reused by the gapped stage */
 static const u8*   g_queryBytes; static unspos g_queryLen;
-static const void* g_scoringKey;
+static const void* g_scoringKey; static const void* g_maskedKey;
+extern control* currParams;            /* lastz.c:327 (output.c reads it the same way) */
 
 static lzb_ctx* ctx(void) {
     if (!g_ctx) {
@@ -54,18 +56,19 @@ static lzb_ctx* ctx(void) {
 static void use_scoring(scoreset* gappedSet, scoreset* maskedSet) {
     if (!gappedSet && !maskedSet) {                       /* plain seed hits carry no scoring set (lastz.c:2789): nothing is scored */
         static int32_t zero[256 * 256];
-        if (g_scoringKey == (const void*)zero) return;
+        if (g_scoringKey != NULL) return;                 /* some set is in place already: good enough for hits that are not scored */
         if (lzb_set_scoring(ctx(), zero, zero, 0, 0)) suicidef("%s", lzb_last_error());
-        g_scoringKey = zero;
+        g_scoringKey = g_maskedKey = zero;
         return;
     }
-    if (!gappedSet) gappedSet = maskedSet;
-    if (!maskedSet) maskedSet = gappedSet;
-    if (g_scoringKey == (const void*)gappedSet) return;
+    /* one call gives the library both sets; whichever stage asks first, the other set comes from the run's parameters */
+    if (!gappedSet) gappedSet = (currParams && currParams->scoring) ? currParams->scoring : maskedSet;
+    if (!maskedSet) maskedSet = (currParams && currParams->maskedScoring) ? currParams->maskedScoring : gappedSet;
+    if (g_scoringKey == (const void*)gappedSet && g_maskedKey == (const void*)maskedSet) return;
     if (sizeof(score) != 4) suicide("the lastz_b200 adapter needs the integer-score build (score_type=I)");
     if (lzb_set_scoring(ctx(), (const int32_t*)&gappedSet->sub[0][0], (const int32_t*)&maskedSet->sub[0][0], gappedSet->gapOpen, gappedSet->gapExtend))
         suicidef("%s", lzb_last_error());
-    g_scoringKey = gappedSet;
+    g_scoringKey = gappedSet; g_maskedKey = maskedSet;
 }
 
 static void seed_to_lzb(const seed* s, lzb_seed* o) {
@@ -86,6 +89,8 @@ static void seed_to_lzb(const seed* s, lzb_seed* o) {
 /* ---- pos_table.h:230 ---- */
 postable* build_seed_position_table(seq* s, unspos start, unspos end, const s8 upperCharToBits[], seed* hitSeed, u32 step) {
     if (s->fileType == seq_type_qdna) suicide("the lastz_b200 adapter does not support quantum DNA");
+    /* the library classifies the bases of a sequence by the scoring sets in force when it is loaded */
+    if (currParams) use_scoring(currParams->scoring, currParams->maskedScoring);
     seed_to_lzb(hitSeed, &g_seed);
     if (g_target) { lzb_target_free(g_target); g_target = NULL; }
     g_target = lzb_target_build(ctx(), s->v, (uint32_t)s->len, (uint32_t)start, (uint32_t)end, (const int8_t*)upperCharToBits, &g_seed, step);
@@ -167,6 +172,7 @@ static const u8* g_bareTargetBytes;
 static void need_target(seq* seq1) {
     if (g_target && (g_targetKey != NULL || g_bareTargetBytes == seq1->v)) return;
     if (g_target) lzb_target_free(g_target);
+    if (currParams) use_scoring(currParams->scoring, currParams->maskedScoring);
     lzb_seed one; memset(&one, 0, sizeof one);
     one.length = 12; one.weight = 24; one.numParts = 1; one.mask[0] = 0xFFFFFF;
     int8_t ctb[256]; memset(ctb, -1, sizeof ctb); ctb['A'] = ctb['a'] = 0; ctb['C'] = ctb['c'] = 1; ctb['G'] = ctb['g'] = 2; ctb['T'] = ctb['t'] = 3;
