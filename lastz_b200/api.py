@@ -166,6 +166,10 @@ class Engine:
             raise RuntimeError("FAILURE: " + self.lib.lzb_last_error().decode())
         return t
 
+    def limit_position_table(self, t, limit):
+        """limit_position_table pos_table.h:240 (maxChasm 0): drop the words that occur more than `limit` times"""
+        self._check(self.lib.lzb_target_limit(t, limit))
+
     def free_position_table(self, t):
         self.lib.lzb_target_free(t)
 

@@ -79,7 +79,7 @@ assert C.sizeof(Segment) == 48 and C.sizeof(Alignel) == 64
 
 # every symbol include/lastz_b200.h declares
 SYMBOLS = ["lzb_backend", "lzb_last_error", "lzb_open", "lzb_close", "lzb_set_scoring",
-           "lzb_target_build", "lzb_target_free", "lzb_target_export_index", "lzb_query_load",
+           "lzb_target_build", "lzb_target_free", "lzb_target_export_index", "lzb_target_limit", "lzb_query_load",
            "lzb_query_free", "lzb_seed_hit_search", "lzb_reduce_to_points", "lzb_gapped_extend",
            "lzb_free_align_list", "lzb_free", "lzb_launch_count"]
 
@@ -98,6 +98,7 @@ def _bind(lib):
     lib.lzb_target_free.argtypes = [vp]
     lib.lzb_target_export_index.restype = C.c_int64
     lib.lzb_target_export_index.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.lzb_target_limit.argtypes = [vp, C.c_uint32]
     lib.lzb_query_load.restype = vp
     lib.lzb_query_load.argtypes = [vp, C.c_char_p, C.c_uint32]
     lib.lzb_query_free.argtypes = [vp]

@@ -81,6 +81,33 @@ extern "C" lzb_target* lzb_target_build(lzb_ctx* c, const uint8_t* seq1, uint32_
     return t;
 }
 
+extern "C" int lzb_target_limit(lzb_target* t, uint32_t limit) {
+    lzb_ctx* c = t->ctx;
+    cudaSetDevice(c->device);
+    if (t->npos == 0) return 0;
+    const u64 nw = 1ull << t->wordBits;
+    u32 *cnt = NULL, *newOff = NULL, *newPos = NULL; void* tmp = NULL; size_t tmpBytes = 0;
+    CUDA_TRY(cudaMalloc(&cnt, (nw + 2) * 4)); CUDA_TRY(cudaMalloc(&newOff, (nw + 2) * 4));
+    int blocks = (int)((nw + 255) / 256); if (blocks > c->smCount * 16) blocks = c->smCount * 16;
+    k_limit_counts<<<blocks, 256, 0, c->stream>>>(t->d_off, cnt, nw, limit);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(NULL, tmpBytes, cnt, newOff, nw + 1, c->stream));
+    CUDA_TRY(cudaMalloc(&tmp, tmpBytes));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, cnt, newOff, nw + 1, c->stream));
+    u32 total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, newOff + nw, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMalloc(&newPos, (size_t)(total ? total : 1) * 4 + 16));
+    k_limit_compact<<<c->smCount * 16, 256, 0, c->stream>>>(t->d_off, newOff, t->d_pos, newPos, nw);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(t->d_off); cudaFree(t->d_pos); cudaFree(cnt); cudaFree(tmp);
+    t->d_off = newOff; t->d_pos = newPos; t->npos = total;
+    return 0;
+}
+
 extern "C" void lzb_target_free(lzb_target* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);

@@ -30,4 +30,22 @@ __global__ void k_index_words(const u8* __restrict__ seq, u32 start, u32 pmax, u
     }
 }
 
+
+/* ---- limit_position_table (pos_table.c:1763): words with more than `limit` positions lose their list ---- */
+__global__ void k_limit_counts(const u32* __restrict__ off, u32* __restrict__ cnt, u64 nw, u32 limit) {
+    for (u64 w = blockIdx.x * (u64)blockDim.x + threadIdx.x; w <= nw; w += (u64)gridDim.x * blockDim.x) {
+        const u32 c = w < nw ? off[w + 1] - off[w] : 0u;
+        cnt[w] = c > limit ? 0u : c;
+    }
+}
+/* one warp per kept word copies its list to the word's new place */
+__global__ void k_limit_compact(const u32* __restrict__ off, const u32* __restrict__ newOff, const u32* __restrict__ pos,
+                                u32* __restrict__ newPos, u64 nw) {
+    const u32 lane = threadIdx.x & 31u;
+    for (u64 w = (blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5; w < nw; w += ((u64)gridDim.x * blockDim.x) >> 5) {
+        const u32 n = newOff[w + 1] - newOff[w];
+        const u32 a = off[w], b = newOff[w];
+        for (u32 i = lane; i < n; i += 32u) newPos[b + i] = pos[a + i];
+    }
+}
 #endif

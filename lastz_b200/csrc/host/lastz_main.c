@@ -32,6 +32,7 @@ typedef struct {
     int unitScores; int32_t unitMatch, unitMismatch;   /* --match=<reward>[,<penalty>] lastz.c:6138 */
     lzb_fieldlist* fields;         /* columns of --format=general[-][:<names>] / mapping[-] */
     int device, showStats, speculation, mafHeader;
+    uint32_t wordCountLimit; float wordCountKeep;        /* --maxwordcount=<limit>[%] (lastz.c:6509-6545) */
     int anyOrNone;                                           /* --anyornone: hspImmediate + searchLimit 1 (lastz.c:5962) */
     int nIsAmbiguous; int32_t ambiMatch, ambiMismatch;     /* --ambiguous=n[,[<match>,]<penalty>] lastz.c:5767-5852 */
     int chainDiag, chainAnti;
@@ -143,6 +144,21 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--transition")) { o->withTrans = 1; o->haveTrans = 1; }
         else if (starts(a, "--transition=")) { o->withTrans = atoi(v); o->haveTrans = 1; }
         else if (starts(a, "--step=") || starts(a, "Z=")) { o->step = (uint32_t)atoi(v); o->haveStep = 1; }
+        else if (starts(a, "--maxwordcount=")) {
+            if (strchr(v, ',')) lzb_die("--maxwordcount's max interval (the chasm) is not supported by lastz_b200");
+            const size_t n = strlen(v);
+            if (n > 0 && v[n - 1] == '%') {
+                const double pct = atof(v) / 100.0;
+                if (pct <= 0) lzb_die("--maxwordcount cannot be zero");
+                if (pct == 1) lzb_die("--maxwordcount cannot be 100%%");
+                if (pct > 1) lzb_die("--maxwordcount cannot be more than 100%%");
+                o->wordCountKeep = (float)pct; o->wordCountLimit = 0;
+            } else {
+                const int lim = atoi(v);
+                if (lim < 1) lzb_die("--maxwordcount must be at least 1");
+                o->wordCountLimit = (uint32_t)lim; o->wordCountKeep = 0;
+            }
+        }
         else if (!strcmp(a, "--strand=both")) o->whichStrand = 1;
         else if (!strcmp(a, "--strand=plus") || !strcmp(a, "--plus")) o->whichStrand = 0;
         else if (!strcmp(a, "--strand=minus")) o->whichStrand = -1;
@@ -373,6 +389,30 @@ int main(int argc, char** argv) {
     if (lzb_set_scoring(ctx, ss.sub, ss.masked, ss.gapOpen, ss.gapExtend)) lzb_die("%s", lzb_last_error());
     lzb_target* T = lzb_target_build(ctx, target.v, target.len, 0, 0, lzb_upper_nuc_to_bits, &seed, o.step);
     if (!T) lzb_die("%s", lzb_last_error());
+    if (o.wordCountKeep > 0) {
+        /* find_position_table_limit pos_table.c:2000-2034: the smallest count such that the words occurring at most that
+         * often hold the wanted share of all positions (counts taken in increasing order; single-precision product as there) */
+        const uint64_t nw = 1ull << seed.weight;
+        uint32_t* counts = malloc(nw * sizeof(uint32_t));
+        const int64_t npos = lzb_target_export_index(T, counts, NULL);
+        if (npos < 0) lzb_die("%s", lzb_last_error());
+        uint32_t maxc = 0;
+        for (uint64_t w = 0; w < nw; w++) if (counts[w] > maxc) maxc = counts[w];
+        uint64_t* occ = calloc((size_t)maxc + 2, sizeof(uint64_t));
+        for (uint64_t w = 0; w < nw; w++) occ[counts[w]]++;
+        uint32_t numPositions = (uint32_t)npos;
+        uint32_t minToKeep = (uint32_t)ceil(numPositions * o.wordCountKeep);
+        uint32_t limit = 0;
+        for (uint32_t c = 1; c <= maxc; c++) {
+            if (!occ[c]) continue;
+            const uint32_t held = (uint32_t)(c * occ[c]);
+            if (held >= minToKeep) { limit = c; break; }
+            minToKeep -= held;
+        }
+        free(occ); free(counts);
+        o.wordCountLimit = limit;
+    }
+    if (o.wordCountLimit > 0 && lzb_target_limit(T, o.wordCountLimit)) lzb_die("%s", lzb_last_error());
 
     /* thresholds as the headers print them (score_thresh_to_string dna_utilities.c:2290): an adaptive one as top<bases>,
      * the percentage already resolved against the target length; an unset L copies K */

@@ -144,6 +144,19 @@ int64_t lzb_target_export_index(lzb_target* t, uint32_t* counts, uint32_t* posit
     return (int64_t)t->npos;
 }
 
+/* limit_position_table pos_table.c:1763-1920 with maxChasm == 0: the position lists of words that occur more than
+ * `limit` times are emptied (:1896-1915: last[w] = 0) */
+int lzb_target_limit(lzb_target* t, uint32_t limit) {
+    u64 nw = 1ull << t->wordBits, w = 0, kept = 0;
+    for (w = 0; w < nw; w++) {
+        u32 a = t->off[w], b = t->off[w + 1];
+        t->off[w] = (u32)kept;
+        if (b - a <= limit) { memmove(t->pos + kept, t->pos + a, (size_t)(b - a) * 4); kept += b - a; }
+    }
+    t->off[nw] = (u32)kept; t->npos = kept;
+    return 0;
+}
+
 lzb_query* lzb_query_load(lzb_ctx* c, const uint8_t* seq2, uint32_t len2) {
     (void)c;
     lzb_query* q = calloc(1, sizeof *q);

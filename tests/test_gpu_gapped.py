@@ -70,8 +70,8 @@ def test_default_pipeline_on_fixtures(engines, spec):
     (300000, dict(speculation=8, traceback_bytes=1024 * 1024, all_bounds=True)),
     (200000, dict(speculation=4, y_drop=3000, score_threshold=5000)),
     (200000, dict(speculation=4, trim_to_peak=False)),
-    (1000000, dict(speculation=256, traceback_bytes=1024 * 1024)),       # hundreds of sweeps in one launch, most of them resumed from a checkpoint
-    (1000000, dict(speculation=48, traceback_bytes=4 * 1024 * 1024, trim_to_peak=False)),   # fewer lanes than anchors worth starting
+    (600000, dict(speculation=256, traceback_bytes=1024 * 1024)),       # hundreds of sweeps in one launch, most of them resumed from a checkpoint
+    (600000, dict(speculation=48, traceback_bytes=2 * 1024 * 1024, trim_to_peak=False)),   # fewer lanes than anchors worth starting
 ])
 def test_synthetic_pairs(engines, synth, size, kw):
     prod, orc = engines
