@@ -327,7 +327,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
             } else { C[s] = LZB_NEG_INF; D[s] = LZB_NEG_INF; }
         }
         used = (s64)last + 1;
-        RY = last + 1;
+        RY = last + 1; cells = RY;                        /* the first row counts too, :3593 */
         if (tid == 0 && tbRowCap > 0) tbRow[0] = 0;
     }
     MW_LOAD_BLOCK();

@@ -84,7 +84,7 @@ k_ydrop(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
             }
             used = (s64)last + 1;
         }
-        RY = last + 1;
+        RY = last + 1; cells = RY;                        /* the first row counts too, :3593 */
         if (tid == 0 && tbRowCap > 0) tbRow[0] = 0;
     }
     __syncthreads();

@@ -278,7 +278,7 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
             } else { S.C[s] = LZB_NEG_INF; S.D[s] = LZB_NEG_INF; }
         }
         used = (s64)last + 1;
-        RY = last + 1;
+        RY = last + 1; cells = RY;                        /* the first row counts too, :3593 */
         if (lane == 0 && tbRowCap > 0 && !tbOnly) tbRow[0] = 0;
     }
     WG_LOAD_BLOCK();

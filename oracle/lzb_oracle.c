@@ -718,7 +718,7 @@ static s32 one_sided(genv* G, int rev, u32 a1, u32 a2, u32 M, u32 N,
     }
     u32 LY = 0, RY = col;
     u32 end1 = 0, end2 = 0; s32 best = 0, bnd = NEG_INF; int endIsBnd = 0;
-    u32 row; u64 cells = 0;
+    u32 row; u64 cells = col;                                 /* the first row counts too, :3593 */
     for (row = 1; row <= M; row++) {
         u32 prevLY = LY;
         /* update_LR_bounds :4588-4724 */
