@@ -193,9 +193,7 @@ struct gx_side {
 };
 struct gx_lane_state {
     bool busy; u64 anchor; segref left1, right1;   /* the anchor's neighbours the sweeps were started with */
-    int deferSide; u64 deferOn;         /* this sweep is held back until anchor deferOn is resolved (-1: none) */
     bool unsure;                        /* started from the edge of another anchor's reach: may yet be skipped */
-    double edgeMax[2];                  /* farthest anchor started at the edge of this anchor's reach, per side */
     gx_side s[2];                       /* 0 = reverse (left) sweep, 1 = forward (right) sweep */
 };
 
@@ -302,7 +300,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     int firstMode = 1;
     { const char* e = getenv("LZB_DP_MODE"); if (e) { int mdv = atoi(e); if (mdv >= 0 && mdv <= 3) firstMode = mdv; } }
     std::vector<gx_lane_state> lanes(W);
-    for (auto& ln : lanes) { ln.busy = false; ln.s[0].phase = ln.s[1].phase = SIDE_IDLE; ln.deferSide = -1; }
+    for (auto& ln : lanes) { ln.busy = false; ln.s[0].phase = ln.s[1].phase = SIDE_IDLE; }
     std::vector<int> laneOf(n, -1);
     std::vector<u8> fin(n, 0);                               /* 1 = skipped / committed / dropped */
     u32 tokenCounter = 0;
@@ -599,14 +597,14 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         return queue_side(z, side, rec, false);
     };
 
-    auto start_anchor = [&](int z, u64 j, int deferSide, u64 deferOn) -> int {
+    auto start_anchor = [&](int z, u64 j, bool unsure) -> int {
         gx_lane_state& ln = lanes[z]; galn& y = G.al[j];
-        ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1; ln.deferSide = deferSide; ln.deferOn = deferOn; ln.unsure = deferSide >= 0; ln.edgeMax[0] = ln.edgeMax[1] = 0;
+        ln.busy = true; ln.anchor = j; ln.left1 = y.left1; ln.right1 = y.right1; ln.unsure = unsure;
         laneOf[j] = z;
         for (int side = 0; side < 2; side++) { ln.s[side].mode = firstMode; ln.s[side].ckptCount = 0; ln.s[side].ckptEvery = 0; ln.s[side].res.ops.clear(); ln.s[side].prog0Rows = ln.s[side].prog0Used = 0; }
         B.job(z, 0)->abort = 0; B.job(z, 1)->abort = 0;
-        GX_TRACE("[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu held=%d\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size(), deferSide);
-        for (int side = 0; side < 2; side++) { ln.s[side].phase = SIDE_IDLE; if (side != deferSide && queue_side(z, side, -1, false)) return -1; }
+        GX_TRACE("[gx %.4f] start a=%llu pos1=%u lane=%d committed=%zu unsure=%d\n", now(), (unsigned long long)j, y.pos1, z, G.committed.size(), (int)unsure);
+        for (int side = 0; side < 2; side++) { ln.s[side].phase = SIDE_IDLE; if (queue_side(z, side, -1, false)) return -1; }
         return 0;
     };
 
@@ -668,19 +666,6 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         for (int z = 0; z < have; z++) {
             gx_lane_state& ln = lanes[z];
             if (!ln.busy) continue;
-            if (ln.deferSide >= 0 && (fin[ln.deferOn] || laneOf[ln.deferOn] < 0)) {
-                /* the anchor this sweep was held back for is resolved: the sweep now starts against its alignment */
-                const int side = ln.deferSide; ln.deferSide = -1;
-                galn& y0 = G.al[ln.anchor]; int cov = -1;
-                if (!anchor_neighbours(G, y0, &cov)) return fail("internal error: anchor %llu lies on alignment %d but was not retired", (unsigned long long)ln.anchor, cov);
-                const bool same = y0.left1.al == ln.left1.al && y0.left1.sg == ln.left1.sg && y0.right1.al == ln.right1.al && y0.right1.sg == ln.right1.sg;
-                if (!same && ln.s[1 - side].phase == SIDE_RUNNING) { ln.deferSide = side; continue; }      /* new neighbours: both sweeps restart once the running one is back */
-                ln.left1 = y0.left1; ln.right1 = y0.right1;
-                if (!same) { ln.s[1 - side].res.ops.clear(); if (queue_side(z, 1 - side, -1, false)) return -1; G.st.redone++; pfRestarts++; }
-                if (queue_side(z, side, -1, false)) return -1;
-                progressed = true;
-                continue;
-            }
             const bool anyRunning = ln.s[0].phase == SIDE_RUNNING || ln.s[1].phase == SIDE_RUNNING;
             bool stale = false, paused = false;
             for (int side = 0; side < 2; side++) {
@@ -702,7 +687,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                     GX_TRACE("[gx %.4f] a=%llu new neighbours: restart\n", now(), (unsigned long long)ln.anchor);
                     G.st.redone += 2; pfRestarts += 2;
                     ln.left1 = y.left1; ln.right1 = y.right1;
-                    for (int side = 0; side < 2; side++) { ln.s[side].res.ops.clear(); if (side != ln.deferSide && queue_side(z, side, -1, false)) return -1; }
+                    for (int side = 0; side < 2; side++) { ln.s[side].res.ops.clear(); if (queue_side(z, side, -1, false)) return -1; }
                     progressed = true;
                     continue;
                 }
@@ -844,8 +829,8 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
                 if (freeLanes == 0) { if (more_lanes()) return -1; if (freeLanes == 0) break; }
                 int fl = -1;
                 for (int z = 0; z < have; z++) if (lane_free(z)) { fl = z; break; }
-                if (start_anchor(fl, j, -1, 0)) return -1;
-                lanes[fl].unsure = unsure; if (unsure) unsureRunning++;
+                if (start_anchor(fl, j, unsure)) return -1;
+                if (unsure) unsureRunning++;
                 lanePos.insert(std::lower_bound(lanePos.begin(), lanePos.end(), std::make_pair(apos1[j], fl)), std::make_pair(apos1[j], fl));
                 freeLanes--; progressed = true; keep--;
                 if (j != hd) G.st.speculated++;
