@@ -359,14 +359,22 @@ void lzb_cigar_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_se
 }
 
 /* ---- --format=sam / softsam [+eqx] [-] (sam.c:196-560, :680-760) ---- */
+static int samSqPending = 0;                /* @SQ lines go out before the first record, not up front (sam.c:213-250: print_sam_header is reached from print_align_list / print_match, output.c:561, :748) */
 void lzb_sam_header(FILE* f, const lzb_seq* s1) {
+    (void)s1;
     fprintf(f, "@HD\tVN:1.0\tSO:unsorted\n");
+    samSqPending = 1;
+}
+
+static void sam_sequence_lines(FILE* f, const lzb_seq* s1) {
+    samSqPending = 0;
     if (s1->npart == 0) fprintf(f, "@SQ\tSN:%s\tLN:%u\n", s1->shortHeader && s1->shortHeader[0] ? s1->shortHeader : "seq1", s1->trueLen);
     else for (uint32_t k = 0; k < s1->npart; k++) fprintf(f, "@SQ\tSN:%s\tLN:%u\n", s1->part[k].shortHeader, s1->part[k].trueLen);
 }
 
 void lzb_sam_align(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, int markMismatches, int softMasked) {
     if (s1->revCompFlags != LZB_RCF_FORWARD) lzb_die("attempt to print - strand or complement for sequence 1 in print_sam_align");
+    if (samSqPending) sam_sequence_lines(f, s1);
     lzb_seqview w1, w2; lzb_seq_view(s1, a->beg1 - 1, &w1); lzb_seq_view(s2, a->beg2 - 1, &w2);
     const char* name1 = w1.name && w1.name[0] ? w1.name : "seq1"; const char* name2 = w2.name && w2.name[0] ? w2.name : "seq2";
     const uint32_t beg1 = a->beg1, beg2 = a->beg2, width = a->end2 - beg2 + 1;

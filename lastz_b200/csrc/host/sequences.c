@@ -122,6 +122,7 @@ lzb_seqfile* lzb_seqfile_open(const char* spec) {
         sf->names = calloc(sf->n2, sizeof(char*)); sf->offsets = calloc(sf->n2, 4);
         for (uint32_t i = 0; i < sf->n2; i++) {
             int nl = fgetc(sf->f);
+            if (nl == EOF) lzb_die("premature end of file in %s", s);
             sf->names[i] = calloc((size_t)nl + 1, 1);
             if (fread(sf->names[i], 1, (size_t)nl, sf->f) != (size_t)nl) lzb_die("bad 2bit index in %s", s);
             sf->offsets[i] = rd4(sf);
@@ -327,17 +328,22 @@ static int next_2bit(lzb_seqfile* sf, lzb_seq* out) {
         if (ix >= sf->n2) return 0;
     }
     sf->lastIx = ix;
-    fseek(sf->f, (long)sf->offsets[ix], SEEK_SET);
+    if (fseek(sf->f, (long)sf->offsets[ix], SEEK_SET) != 0) lzb_die("bad 2bit index in %s (can't seek to %u for %s)", sf->filename, sf->offsets[ix], sf->names[ix]);
     uint32_t dna = rd4(sf);
     uint32_t nb = rd4(sf);
+    if (nb > dna) lzb_die("bad 2bit block count in %s, %s", sf->filename, sf->names[ix]);
     uint32_t* ns = malloc(((size_t)nb * 2 + 1) * 4);
     for (uint32_t i = 0; i < nb; i++) ns[i] = rd4(sf);
     for (uint32_t i = 0; i < nb; i++) ns[nb + i] = rd4(sf);
     uint32_t mb = rd4(sf);
+    if (mb > dna) lzb_die("bad 2bit block count in %s, %s", sf->filename, sf->names[ix]);
     uint32_t* ms = malloc(((size_t)mb * 2 + 1) * 4);
     for (uint32_t i = 0; i < mb; i++) ms[i] = rd4(sf);
     for (uint32_t i = 0; i < mb; i++) ms[mb + i] = rd4(sf);
     rd4(sf);
+    /* the N and mask blocks must lie inside the sequence: the tables come from the file */
+    for (uint32_t k = 0; k < nb; k++) if ((uint64_t)ns[k] + ns[nb + k] > dna) lzb_die("bad 2bit N block in %s, %s (%u+%u > %u)", sf->filename, sf->names[ix], ns[k], ns[nb + k], dna);
+    for (uint32_t k = 0; k < mb; k++) if ((uint64_t)ms[k] + ms[mb + k] > dna) lzb_die("bad 2bit mask block in %s, %s (%u+%u > %u)", sf->filename, sf->names[ix], ms[k], ms[mb + k], dna);
     size_t pb = ((size_t)dna + 3) / 4;
     uint8_t* packed = malloc(pb + 1);
     if (fread(packed, 1, pb, sf->f) != pb) lzb_die("premature end of file in %s", sf->filename);

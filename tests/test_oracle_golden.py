@@ -372,3 +372,15 @@ def test_oracle_variant_order_fixture():
     out, _ = run_cli(ORACLE_CLI, files + ["--nogfextend", "--nogapped", "--strand=plus", "--format=general-"])
     got = ["\t".join((l.split("\t")[4], l.split("\t")[9])) for l in out.splitlines()]
     assert got == open(os.path.join(GOLDEN, "aglobin_cow_20k_32k.plus_hits.order.tsv")).read().splitlines()
+
+
+@pytest.mark.parametrize("fmt", ["--format=sam", "--format=softsam", "--format=sam-"])
+def test_oracle_sam_header_without_alignments(tmp_path, fmt):
+    """@SQ lines appear with the first record (sam.c:213-250), so a run that finds nothing prints @HD alone."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa"
+    a.write_text(">a\n" + "ACGTTGCA" * 40 + "\n")
+    b.write_text(">b\n" + "AAAAAAAAAAAAAAAACCCCCCCCCCCCCCCC" * 10 + "\n")
+    for files in ([str(a), str(b)], [CAT, PIG]):
+        same_output(run_cli(ORACLE_CLI, files + [fmt])[0], run_cli(REF_CLI, files + [fmt])[0])
