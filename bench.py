@@ -11,16 +11,16 @@ pass of config4 (`config4_one_gpu`) so that the multi-GPU numbers have their own
 
 A "step" is one pass of the hot path over this rank's query interval: for each strand seed_hit_search ->
 [reduce_to_chain] -> reduce_to_points -> gapped_extend through the C-ABI.  The target bytes and its position table stay
-resident in HBM (built once, outside the timed region, and reported).  The two strands run on two host threads with a
-context each: the minus strand's seed stage starts when the plus strand's has returned, so it overlaps the plus
-strand's gapped stage (which keeps only part of the SMs busy).  After each step the ranks' HSP tables and alignments
+resident in HBM (built once, outside the timed region, and reported).  The seed stages of the two strands run one after the
+other (each fills the GPU); their gapped stages -- chains of dependent sweeps that leave most SMs idle -- run side by
+side on two host threads with a context each (`--no-overlap`: one after the other).  After each step the ranks' HSP tables and alignments
 are gathered to rank 0 over NCCL.
 
 `value` = raw seed hits of the step / WHOLE step time (both stages of both strands), device-resident query;
 `e2e.value` = the same with the query coming from host memory every step and the results read back.  The stage rates
 the metric names are in `seed_hits_per_s` (hits / seed-stage time) and `gcells_per_s` (DP cells / gapped-stage time).
-Timing is the host clock around blocking C-ABI calls bracketed by barrier + device sync (max over ranks); per-kernel
-numbers come from CUDA events recorded by the library on its own stream.
+Timing: CUDA events either side of the K steps, bracketed by barrier + device sync (max over ranks), the host clock
+beside it as a cross-check; per-kernel numbers come from CUDA events recorded by the library on its own stream.
 """
 import argparse
 import json
@@ -333,7 +333,8 @@ def main():
         T = engA.build_seed_position_table(target, seed)
         index_s = time.perf_counter() - t0
 
-        def strand_pass(eng, sid, s, Q, resident, acc, seed_done=None):
+        def seed_part(eng, sid, s, Q, resident, acc):
+            """the seed stage of one strand; returns what the gapped stage needs"""
             w0 = time.perf_counter()
             if not resident:
                 Q = eng.load_query(s)
@@ -341,16 +342,11 @@ def main():
             wl_ = time.perf_counter()
             segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid)
             w1 = time.perf_counter()
-            if seed_done is not None:
-                seed_done.set()
             table = segs.copy()
             if w["chain"]:
                 segs = reduce_to_chain(segs, ss)
             wc = time.perf_counter()
-            anchors = eng.reduce_to_points(T, Q, segs)
-            al, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, identity_check=False, speculation=args.speculation)
-            w2 = time.perf_counter()
-            acc["seed_wall"] += w1 - w0; acc["chain_wall"] += wc - w1; acc["gap_wall"] += w2 - wc; acc["load_wall"] += wl_ - w0
+            acc["seed_wall"] += w1 - w0; acc["chain_wall"] += wc - w1; acc["load_wall"] += wl_ - w0
             acc["hits"] += st.rawSeedHits; acc["seed_s"] += st.seconds; acc["words"] += st.wordsInQuery
             for i in range(12):
                 acc["kern"][i] += st.kernelSeconds[i]; acc["kern_n"][i] += st.kernelLaunches[i]
@@ -358,7 +354,16 @@ def main():
             acc["ext_s"] += sum(st.kernelSeconds[i] for i in (7, 8, 9, 10))
             acc["ext_launch"] += st.kernelLaunches[7] + st.kernelLaunches[8]
             acc["bp"] += st.bpExtended; acc["ext"] += st.extensions
-            acc["hsps"] += len(table); acc["anchors"] += len(segs); acc["cells"] += gst.dpCells; acc["cells_computed"] += gst.dpCellsComputed
+            acc["hsps"] += len(table); acc["anchors"] += len(segs)
+            return Q, segs, table
+
+        def gapped_part(eng, sid, s, Q, segs, table, resident, acc):
+            wc = time.perf_counter()
+            anchors = eng.reduce_to_points(T, Q, segs)
+            al, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, identity_check=False, speculation=args.speculation)
+            w2 = time.perf_counter()
+            acc["gap_wall"] += w2 - wc
+            acc["cells"] += gst.dpCells; acc["cells_computed"] += gst.dpCellsComputed
             acc["gap_s"] += gst.seconds; acc["dp_launches"] += gst.launches; acc["alignments"] += len(al)
             acc["dp_rows"] += gst.dpRows; acc["redone"] += gst.redone; acc["speculated"] += gst.speculated
             acc["h2d"] += 48 * len(segs); acc["d2h"] += 2 * 48 * len(table) + 4 * sum(len(a["ops"]) for a in al)
@@ -370,40 +375,44 @@ def main():
 
         def new_acc():
             return dict(hits=0, cells=0, cells_computed=0, seed_s=0.0, gap_s=0.0, ext_s=0.0, ext_launch=0, bp=0, hsps=0, anchors=0, h2d=0, d2h=0,
-                        ext=0, dp_launches=0, seed_wall=0.0, chain_wall=0.0, gap_wall=0.0, load_wall=0.0, free_wall=0.0, gather_wall=0.0,
+                        ext=0, dp_launches=0, seed_wall=0.0, chain_wall=0.0, gap_wall=0.0, load_wall=0.0, free_wall=0.0, gather_wall=0.0, gap_phase_wall=0.0,
                         words=0, kern=[0.0] * 12, kern_n=[0] * 12, alignments=0, dp_rows=0, redone=0, speculated=0, tables=[], aligns=[])
 
         def step(resident, handles):
             accA, accB = new_acc(), new_acc()
             (sidA, sA), (sidB, sB) = strands
+            # seed stages one after the other (each fills the GPU); the two strands' gapped stages -- chains of dependent
+            # sweeps that leave most SMs idle -- side by side, one scheduler (context) each
+            QA, segsA, tabA = seed_part(engA, sidA, sA, handles[0] if resident else None, resident, accA)
+            QB, segsB, tabB = seed_part(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+            wg = time.perf_counter()
             if overlap:
-                ev = threading.Event()
                 err = []
 
                 def other():
                     try:
-                        ev.wait()
-                        strand_pass(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+                        gapped_part(engB, sidB, sB, QB, segsB, tabB, resident, accB)
                     except BaseException as e:       # noqa: BLE001  (re-raised on the main thread)
                         err.append(e)
                 th = threading.Thread(target=other)
                 th.start()
                 try:
-                    strand_pass(engA, sidA, sA, handles[0] if resident else None, resident, accA, seed_done=ev)
+                    gapped_part(engA, sidA, sA, QA, segsA, tabA, resident, accA)
                 finally:
-                    ev.set()
                     th.join()
                 if err:
                     raise err[0]
             else:
-                strand_pass(engA, sidA, sA, handles[0] if resident else None, resident, accA)
-                strand_pass(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+                gapped_part(engA, sidA, sA, QA, segsA, tabA, resident, accA)
+                gapped_part(engB, sidB, sB, QB, segsB, tabB, resident, accB)
+            gap_phase = time.perf_counter() - wg
             acc = new_acc()
             for k in acc:
                 if k in ("kern", "kern_n"):
                     acc[k] = [a + b for a, b in zip(accA[k], accB[k])]
                 else:
                     acc[k] = accA[k] + accB[k]
+            acc["gap_phase_wall"] = gap_phase
             w3 = time.perf_counter()
             segs_all = gather_to_rank0(np.concatenate(acc["tables"]).view(np.uint8).reshape(-1), dev)
             al_all = gather_to_rank0(np.concatenate(acc["aligns"]).view(np.uint8).reshape(-1), dev)
@@ -466,7 +475,7 @@ def main():
     (dt, accs, launches), (dt_e2e, accs_e2e, _), info = measure(wl, args.steps, args.warmup)
     target, query, T = info["target"], info["query"], info["T"]
     hits, cells = total("hits", accs), total("cells", accs)
-    seed_wall, gap_wall = worst("seed_wall", accs), worst("gap_wall", accs)
+    seed_wall, gap_wall = worst("seed_wall", accs), worst("gap_phase_wall", accs)      # gapped: elapsed time of the phase (both strands side by side)
     seed_dev = worst("seed_s", accs)
     total_l = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -479,7 +488,7 @@ def main():
     achieved = bytes_per_hit * my_hits / max(ext_s, 1e-12) / 1e9
     # every cross-rank aggregate is computed HERE, on all ranks (collectives must not sit under `if rank == 0`)
     agg = {"e2e_hits": total("hits", accs_e2e), "e2e_cells": total("cells", accs_e2e),
-           "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_wall", accs_e2e),
+           "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_phase_wall", accs_e2e),
            "hsps": total("hsps", accs), "anchors": total("anchors", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e),
            "cells_computed": total("cells_computed", accs), "alignments": total("alignments", accs),
            "redone": total("redone", accs), "speculated": total("speculated", accs)}
@@ -515,7 +524,7 @@ def main():
         h4 = sum(a["hits"] for a in accs4); c4 = sum(a["cells"] for a in accs4)
         base4 = {"workload": WORKLOADS["config4"]["name"], "value": h4 / dt4, "unit": "hits/s", "ms_per_step": 1e3 * dt4, "steps": 1, "warmup": 1,
                  "seed_hits_per_s": h4 / max(sum(a["seed_wall"] for a in accs4), 1e-12),
-                 "gcells_per_s": c4 / max(sum(a["gap_wall"] for a in accs4), 1e-12) / 1e9,
+                 "gcells_per_s": c4 / max(sum(a["gap_phase_wall"] for a in accs4), 1e-12) / 1e9,
                  "counts_per_step": {"raw_seed_hits": h4, "dp_cells": c4, "hsps": sum(a["hsps"] for a in accs4),
                                      "anchors_after_chain": sum(a["anchors"] for a in accs4), "alignments": sum(a["alignments"] for a in accs4)},
                  "index_build_once_ms": 1e3 * info4["index_s"]}
@@ -533,8 +542,8 @@ def main():
                 "dtype": "int32", "data": "synthetic", "config": config_of(wl, world),
                 "stage_ms_per_step": {"seed": 1e3 * seed_wall / args.steps, "seed_device_events": 1e3 * seed_dev / args.steps,
                                       "gapped": 1e3 * gap_wall / args.steps, "index_build_once": 1e3 * info["index_s"],
-                                      "note": "wall time of the blocking calls, summed over the two strands, max over ranks; with the strands "
-                                              "overlapped the stages add up to more than ms_per_step"},
+                                      "note": "seed: wall time of the blocking calls of the two strands, one after the other; gapped: elapsed time of "
+                                              "the gapped phase (the two strands' gapped stages side by side unless --no-overlap); max over ranks"},
                 "counts_per_step": {"raw_seed_hits": hits / args.steps, "dp_cells": cells / args.steps,
                                     "dp_cells_incl_discarded_speculation": agg["cells_computed"] / args.steps,
                                     "hsps": agg["hsps"] / args.steps, "anchors": agg["anchors"] / args.steps, "alignments": agg["alignments"] / args.steps,
@@ -574,9 +583,9 @@ def main():
                 ent["achieved_gbs"] = alg[i] / max(kern[i], 1e-12) / 1e9
                 ent["frac_of_hbm_peak"] = ent["achieved_gbs"] / peak
             rk.append(ent)
-        my_cells = sum(a["cells_computed"] for a in accs); gap_my = sum(a["gap_wall"] for a in accs)
+        my_cells = sum(a["cells_computed"] for a in accs); gap_my = sum(a["gap_phase_wall"] for a in accs)
         int_peak = 148 * INT32_LANES_PER_SM * sm_mhz * 1e6
-        rk.append({"kernel": "k_ydrop_mw (Y-drop DP + traceback; one CTA per one-sided sweep, hundreds of sweeps per launch)",
+        rk.append({"kernel": "k_ydrop_warp / k_ydrop_mw (Y-drop DP + traceback; one CTA per one-sided sweep, hundreds of sweeps in flight)",
                    "launches": sum(a["dp_launches"] for a in accs), "gapped_stage_ms_per_step": 1e3 * gap_my / args.steps,
                    "bound": "dependent integer issue per DP row (max-plus recurrence + two block-wide scans), not HBM",
                    "achieved_gbs": 1.0 * my_cells / max(gap_my, 1e-12) / 1e9, "frac_of_hbm_peak": 1.0 * my_cells / max(gap_my, 1e-12) / 1e9 / peak,
