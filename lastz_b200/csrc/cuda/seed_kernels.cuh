@@ -326,7 +326,6 @@ k_extend2(const u64* __restrict__ hits, const u32* __restrict__ bstart, const u3
           const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32* __restrict__ diagEnd,
           cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt, u32* __restrict__ nextBucket) {
     __shared__ s32 lut[256];
-    __shared__ u32 scratch[8][XD_WS_BYTES / 4];               /* one tile of scan states per warp (256 threads) */
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int c1 = i / (int)XD_LUT_STRIDE, c2 = i % (int)XD_LUT_STRIDE;
         lut[i] = (c1 < XD_LUT_MAX_CLASSES && c2 < XD_LUT_MAX_CLASSES) ? sc->msubC[c1 * LZB_MAX_CLASSES + c2] : 0;
@@ -347,7 +346,7 @@ k_extend2(const u64* __restrict__ hits, const u32* __restrict__ bstart, const u3
         const u32 b0 = bstart[h], b1 = bstart[h + 1];
         if (b0 == b1) break;                            /* sorted by size: everything after is empty too */
         u32 E = diagEnd[h];
-        xd_bucket(e, lane, hits, b0, b1, E, nExt, nBp, scratch[threadIdx.x >> 5]);
+        xd_bucket(e, lane, hits, b0, b1, E, nExt, nBp);
         if (lane == 0) diagEnd[h] = E;
     }
     for (int o = 16; o > 0; o >>= 1) { nExt += __shfl_down_sync(0xFFFFFFFFu, nExt, o); nBp += __shfl_down_sync(0xFFFFFFFFu, nBp, o); }

@@ -32,7 +32,6 @@ template <class T> static inline T wemu_shfl(T v, int src, int line) {
 #define W_FFS(x)            __builtin_ffs((int)(x))
 #define W_POPC(x)           __builtin_popcount((unsigned)(x))
 #define W_ATOMIC_ADD_ULL(p, v) ([&]() { unsigned long long o_ = *(p); *(p) += (v); return o_; }())
-#define W_SYNCWARP()         ((void)wemu_ballot(1, __LINE__))
 #else
 #define W_DEV __device__ __forceinline__
 #define W_FULL 0xFFFFFFFFu
@@ -43,7 +42,6 @@ template <class T> static inline T wemu_shfl(T v, int src, int line) {
 #define W_FFS(x)            __ffs((int)(x))
 #define W_POPC(x)           __popc((unsigned)(x))
 #define W_ATOMIC_ADD_ULL(p, v) atomicAdd((p), (unsigned long long)(v))
-#define W_SYNCWARP()         __syncwarp()
 #endif
 
 template <class T> W_DEV T w_min(T a, T b) { return a < b ? a : b; }

@@ -192,201 +192,103 @@ W_DEV void xd_finish_lane(const xd_env& e, u32 lane, int k, u32 pos1, u32 pos2, 
     if ((int)lane == k) { mine = z; mine.avail = z.cols; }
 }
 
-/* ---- the bucket in tiles of XD_TILE hits, lanes refilled as their scans end ----
- *
- * A lane that scans one hit from start to end in lockstep with 31 others waits for the slowest of them: measured, 47 % of the
- * lane-columns of the first k_extend2 did work (profiles/r01_k_extend2_50M.txt).  The scans of different hits are independent
- * (only the bucket's extent couples them, and only through the replay), so here every lane takes the NEXT hit of the tile the
- * moment its own scan closes; the scan states wait in per-warp shared memory for the replay, which walks the tile's 32-hit
- * chunks in discovery order exactly as before.  Per tile: right scans (refill) -> replay per chunk -> left scans of the live
- * hits (refill) -> per chunk: long left scans by the whole warp, scores, entropy counts, candidates.
- *
- * Scratch, XD_WS_WORDS words per hit of the tile: [0] flags, [1..4] right scan cols/bestLen/run/best, [5] myStop,
- * [6..9] left scan; then the list of the tile's live hits (one u16 each).  A scan parked open (XD_FOPEN) has run XD_CAP
- * columns or more and is finished by the whole warp when its hit turns out to be live. */
-#define XD_TILE 128u
-#define XD_WS_WORDS 10u
-#define XD_WS_BYTES (XD_TILE * XD_WS_WORDS * 4u + XD_TILE * 2u)
-#define XD_FMAYBE 1u
-#define XD_FLIVE 2u
-#define XD_FROPEN 4u
-#define XD_FLOPEN 8u
-
-W_DEV void xd_park(u32* r, const xd_scan& z) { r[0] = z.cols; r[1] = z.bestLen; r[2] = (u32)z.run; r[3] = (u32)z.best; }
-W_DEV void xd_unpark(const u32* r, bool open, u32 avail, xd_scan& z) {
-    z.cols = r[0]; z.bestLen = r[1]; z.run = (s32)r[2]; z.best = (s32)r[3];
-    z.avail = open ? avail : z.cols;                                       /* a closed scan has avail = cols */
-}
-W_DEV u32 xd_right_avail(const xd_env& e, u32 pos1, u32 pos2) {
-    const s64 diag = (s64)pos1 - (s64)pos2;
-    const s64 lim = (s64)e.len2 + diag;
-    const u32 rstop = ((s64)e.len1 <= lim) ? e.len1 : (u32)lim;
-    return rstop > pos1 ? rstop - pos1 : 0;
-}
-W_DEV u32 xd_left_avail(u32 pos1, u32 pos2, u32 myStop) {
-    const s64 blk = (s64)myStop + ((s64)pos1 - (s64)pos2);
-    const u32 stop = blk > 0 ? (u32)blk : 0;
-    return pos1 > stop ? pos1 - stop : 0;
-}
-
-/* scans of the hits listed (DIR > 0: the tile's hits t0..t1-1 themselves; DIR < 0: the live hits by way of liveList) up to
- * XD_CAP columns each; a lane whose scan closes takes the next hit */
-template <int DIR>
-W_DEV void xd_scan_tile(const xd_env& e, u32 lane, const u64* hits, u32 t0, u32 count, u32 E0, u32* ws, const unsigned short* liveList) {
-    const u32 L = e.L, ltMask = (1u << lane) - 1u;
-    u32 next = 0; bool act = false; u32 mine = 0, p1 = 0, p2 = 0; xd_scan z; xd_scan_init(z, 0);
-    for (;;) {
-        const u32 need = W_BALLOT(!act);
-        if (need && next < count) {
-            const u32 k = next + (u32)W_POPC(need & ltMask);
-            if (!act && k < count) {
-                mine = DIR > 0 ? k : (u32)liveList[k];
-                const u64 rec = hits[t0 + mine];
-                p1 = (u32)rec; p2 = (u32)(rec >> 32);
-                u32* r = ws + mine * XD_WS_WORDS;
-                if (DIR > 0) {
-                    const bool maybe = !(E0 > p2 - L);          /* hits the bucket has already passed can never be live (diagEnd only grows) */
-                    xd_scan_init(z, maybe ? xd_right_avail(e, p1, p2) : 0);
-                    r[0] = maybe ? XD_FMAYBE : 0u;
-                    if (xd_scan_open(z)) act = true; else xd_park(r + 1, z);
-                } else {
-                    xd_scan_init(z, xd_left_avail(p1, p2, r[5]));
-                    if (xd_scan_open(z)) act = true; else xd_park(r + 6, z);
-                }
-            }
-            next = w_min(count, next + (u32)W_POPC(need));
-        }
-        if (!W_BALLOT(act)) { if (next >= count) break; continue; }
-        if (act) {
-            xd_scan_step8<DIR>(e, p1, p2, e.xDrop, z);
-            const bool open = xd_scan_open(z);
-            if (!open || z.cols >= XD_CAP) {
-                u32* r = ws + mine * XD_WS_WORDS;
-                xd_park(r + (DIR > 0 ? 1 : 6), z);
-                if (open) r[0] |= DIR > 0 ? XD_FROPEN : XD_FLOPEN;
-                act = false;
-            }
-        }
-    }
-}
-
-/* all hits [b0,b1) of one bucket, in discovery order; E = diagEnd[bucket] in and out; ws = XD_WS_BYTES of this warp's own */
+/* all hits [b0,b1) of one bucket, in discovery order; E = diagEnd[bucket] in and out */
 W_DEV void xd_bucket(const xd_env& e, u32 lane, const u64* hits, u32 b0, u32 b1, u32& E,
-                     unsigned long long& nExt, unsigned long long& nBp, u32* ws) {
-    const u32 L = e.L;
-    const u32 ltMask = (1u << lane) - 1u;
-    unsigned short* const liveList = (unsigned short*)(ws + XD_TILE * XD_WS_WORDS);
-    for (u32 t0 = b0; t0 < b1; t0 += XD_TILE) {
-        const u32 t1 = w_min(b1, t0 + XD_TILE);
-        /* ---- right scans (seed_search.c:2663-2693), independent of the bucket state ---- */
-        xd_scan_tile<1>(e, lane, hits, t0, t1 - t0, E, ws, liveList);
-        W_SYNCWARP();
-        /* ---- replay of process_for_simple_hit's test/update (:1113, :2785-2789), chunk by chunk in discovery order ---- */
-        u32 nLive = 0;
-        for (u32 base = t0; base < t1; base += 32) {
-            const u32 idx = base + lane;
-            const bool have = idx < t1;
-            const u64 rec = have ? hits[idx] : 0;
-            const u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
-            u32* r = ws + (have ? idx - t0 : 0u) * XD_WS_WORDS;
-            const u32 fl = have ? r[0] : 0u;
-            const bool maybe = (fl & XD_FMAYBE) && !(E > pos2 - L);
-            xd_scan rs; xd_scan_init(rs, 0);
-            if (maybe) xd_unpark(r + 1, (fl & XD_FROPEN) != 0, xd_right_avail(e, pos1, pos2), rs);
-            u32 active = W_BALLOT(maybe);
-            bool live = false; u32 myStop = 0;
-            if (active) {
-                if (!W_BALLOT(maybe && xd_scan_open(rs))) {
-                    /* every extent is known.  Suppose all remaining candidates contribute their extent: the
-                     * bucket as hit k meets it is E0 max'ed with the extents in front of k (a prefix maximum).
-                     * Lanes in front of the first hit that comes out dead saw exactly the true bucket, so that
-                     * hit IS dead; drop its extent and look again.  One trip per dead hit (usually none or one). */
-                    const u32 ext = pos2 + rs.cols;                           /* where the right scan stopped, in seq 2 */
-                    bool contrib = maybe;
-                    for (;;) {
-                        u32 pm = contrib ? ext : 0u;
+                     unsigned long long& nExt, unsigned long long& nBp) {
+    const u32 L = e.L; const s32 xDrop = e.xDrop;
+    for (u32 base = b0; base < b1; base += 32) {
+        const u32 idx = base + lane;
+        const bool have = idx < b1;
+        const u64 rec = have ? hits[idx] : 0;
+        const u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
+        const s64 diag = (s64)pos1 - (s64)pos2;
+        /* hits the bucket has already passed can never be live (diagEnd only grows) */
+        const bool maybe = have && !(E > pos2 - L);
+        u32 active = W_BALLOT(maybe);
+        if (!active) continue;
+        /* right scan (seed_search.c:2663-2693), independent of the bucket state */
+        xd_scan rs; xd_scan_init(rs, 0);
+        if (maybe) {
+            const s64 lim = (s64)e.len2 + diag;
+            const u32 rstop = ((s64)e.len1 <= lim) ? e.len1 : (u32)lim;
+            xd_scan_init(rs, rstop > pos1 ? rstop - pos1 : 0);
+            while (xd_scan_open(rs) && rs.cols < XD_CAP) xd_scan_step8<1>(e, pos1, pos2, xDrop, rs);
+        }
+        /* replay the test/update of process_for_simple_hit (:1113, :2785-2789) in discovery order */
+        bool live = false; u32 myStop = 0;
+        if (!W_BALLOT(maybe && xd_scan_open(rs))) {
+            /* every extent is known.  Suppose all remaining candidates contribute their extent: the
+             * bucket as hit k meets it is E0 max'ed with the extents in front of k (a prefix maximum).
+             * Lanes in front of the first hit that comes out dead saw exactly the true bucket, so that
+             * hit IS dead; drop its extent and look again.  One trip per dead hit (usually none or one). */
+            const u32 ext = pos2 + rs.cols;                           /* where the right scan stopped, in seq 2 */
+            bool contrib = maybe;
+            for (;;) {
+                u32 pm = contrib ? ext : 0u;
 #pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const u32 t = W_SHFL_UP(pm, d); if (lane >= (u32)d) pm = w_max(pm, t); }
-                        u32 before = W_SHFL_UP(pm, 1); if (lane == 0) before = 0u;
-                        before = w_max(before, E);
-                        const u32 dm = W_BALLOT(contrib && before > pos2 - L);
-                        if (!dm) { live = contrib; myStop = before; E = w_max(E, W_SHFL(pm, 31)); break; }
-                        if ((int)lane == W_FFS(dm) - 1) contrib = false;
-                    }
-                } else {
-                    /* some scan outlived XD_CAP columns: walk the hits one by one and let the warp finish a
-                     * long scan only when its hit turns out to be live */
-                    while (active) {
-                        const int k = W_FFS(active) - 1; active &= active - 1;
-                        const u32 p2k = W_SHFL(pos2, k);
-                        if (E > p2k - L) continue;                             /* dead by now; its scan is never finished */
-                        if (W_SHFL(xd_scan_open(rs) ? 1 : 0, k)) xd_finish_lane<1>(e, lane, k, pos1, pos2, rs);
-                        const u32 ex = W_SHFL(pos2 + rs.cols, k);
-                        if ((int)lane == k) { live = true; myStop = E; }
-                        if (ex > E) E = ex;
-                    }
-                }
+                for (int d = 1; d < 32; d <<= 1) { const u32 t = W_SHFL_UP(pm, d); if (lane >= (u32)d) pm = w_max(pm, t); }
+                u32 before = W_SHFL_UP(pm, 1); if (lane == 0) before = 0u;
+                before = w_max(before, E);
+                const u32 dm = W_BALLOT(contrib && before > pos2 - L);
+                if (!dm) { live = contrib; myStop = before; E = w_max(E, W_SHFL(pm, 31)); break; }
+                if ((int)lane == W_FFS(dm) - 1) contrib = false;
             }
-            /* the live hits go on the list for the left scans, their (now closed) right scans back to the scratch */
-            const u32 lm = W_BALLOT(live);
-            if (live) {
-                r[0] = XD_FMAYBE | XD_FLIVE; xd_park(r + 1, rs); r[5] = myStop;
-                liveList[nLive + (u32)W_POPC(lm & ltMask)] = (unsigned short)(idx - t0);
-            } else if (have) r[0] = fl & ~XD_FLIVE;
-            nLive += (u32)W_POPC(lm);
-        }
-        W_SYNCWARP();
-        /* ---- left scans (:2598-2632) of the live hits, blocked by the bucket's previous extent on their diagonal ---- */
-        xd_scan_tile<-1>(e, lane, hits, t0, nLive, 0u, ws, liveList);
-        W_SYNCWARP();
-        /* ---- per chunk: long left scans by the whole warp, scores, entropy counts, candidates ---- */
-        for (u32 base = t0; base < t1; base += 32) {
-            const u32 idx = base + lane;
-            const bool have = idx < t1;
-            const u64 rec = have ? hits[idx] : 0;
-            const u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
-            const u32* r = ws + (have ? idx - t0 : 0u) * XD_WS_WORDS;
-            const u32 fl = have ? r[0] : 0u;
-            const bool live = (fl & XD_FLIVE) != 0;
-            xd_scan rs, ls; xd_scan_init(rs, 0); xd_scan_init(ls, 0);
-            if (live) { xd_unpark(r + 1, false, 0, rs); xd_unpark(r + 6, (fl & XD_FLOPEN) != 0, xd_left_avail(pos1, pos2, r[5]), ls); }
-            u32 longLeft = W_BALLOT(live && xd_scan_open(ls));
-            while (longLeft) {
-                const int k = W_FFS(longLeft) - 1; longLeft &= longLeft - 1;
-                xd_finish_lane<-1>(e, lane, k, pos1, pos2, ls);
-            }
-            s32 sim = 0; bool keep = false;
-            cand_rec c;
-            c.hit1 = pos1; c.hit2 = pos2; c.pos1 = pos1 - ls.bestLen; c.pos2 = pos2 - ls.bestLen;
-            c.length = ls.bestLen + rs.bestLen; c.cA = c.cC = c.cG = c.cT = 0;
-            if (live) {
-                nExt++; nBp += rs.cols + ls.cols;
-                sim = ls.best + rs.best;
-                keep = sim >= e.K;                                         /* entropy can only lower the score */
-            }
-            c.score = sim;
-            /* match counts for entropy(), dna_utilities.c:2905-2915: the warp counts, 32 columns per trip */
-            u32 want = W_BALLOT(keep && e.entropy && sim <= 3 * e.K);
-            while (want) {
-                const int k = W_FFS(want) - 1; want &= want - 1;
-                const u32 q1 = W_SHFL(c.pos1, k), q2 = W_SHFL(c.pos2, k), len = W_SHFL(c.length, k);
-                u32 cA = 0, cC = 0, cG = 0, cT = 0;
-                for (u32 i0 = 0; i0 < len; i0 += 32) {
-                    const u32 i = i0 + lane;
-                    u8 x = 0, y = 1;
-                    if (i < len) { x = e.asc1[q1 + i]; y = e.asc2[q2 + i]; }
-                    const bool eq = x == y;
-                    cA += (u32)W_POPC(W_BALLOT(eq && x == 'A')); cC += (u32)W_POPC(W_BALLOT(eq && x == 'C'));
-                    cG += (u32)W_POPC(W_BALLOT(eq && x == 'G')); cT += (u32)W_POPC(W_BALLOT(eq && x == 'T'));
-                }
-                if ((int)lane == k) { c.cA = cA; c.cC = cC; c.cG = cG; c.cT = cT; }
-            }
-            if (keep) {
-                const u32 slot = (u32)W_ATOMIC_ADD_ULL(e.ncand, 1ull);
-                if (slot < e.candCap) e.cand[slot] = c;
+        } else {
+            /* some scan outlived XD_CAP columns: walk the hits one by one and let the warp finish a
+             * long scan only when its hit turns out to be live */
+            while (active) {
+                const int k = W_FFS(active) - 1; active &= active - 1;
+                const u32 p2k = W_SHFL(pos2, k);
+                if (E > p2k - L) continue;                             /* dead by now; its scan is never finished */
+                if (W_SHFL(xd_scan_open(rs) ? 1 : 0, k)) xd_finish_lane<1>(e, lane, k, pos1, pos2, rs);
+                const u32 ex = W_SHFL(pos2 + rs.cols, k);
+                if ((int)lane == k) { live = true; myStop = E; }
+                if (ex > E) E = ex;
             }
         }
-        W_SYNCWARP();
+        /* left scan (:2598-2632), blocked by the bucket's previous extent on this diagonal */
+        xd_scan ls; xd_scan_init(ls, 0);
+        if (live) {
+            const s64 blk = (s64)myStop + diag;
+            const u32 stop = blk > 0 ? (u32)blk : 0;
+            xd_scan_init(ls, pos1 > stop ? pos1 - stop : 0);
+            while (xd_scan_open(ls) && ls.cols < XD_CAP) xd_scan_step8<-1>(e, pos1, pos2, xDrop, ls);
+        }
+        u32 longLeft = W_BALLOT(live && xd_scan_open(ls));
+        while (longLeft) {
+            const int k = W_FFS(longLeft) - 1; longLeft &= longLeft - 1;
+            xd_finish_lane<-1>(e, lane, k, pos1, pos2, ls);
+        }
+        s32 sim = 0; bool keep = false;
+        cand_rec r;
+        r.hit1 = pos1; r.hit2 = pos2; r.pos1 = pos1 - ls.bestLen; r.pos2 = pos2 - ls.bestLen;
+        r.length = ls.bestLen + rs.bestLen; r.cA = r.cC = r.cG = r.cT = 0;
+        if (live) {
+            nExt++; nBp += rs.cols + ls.cols;
+            sim = ls.best + rs.best;
+            keep = sim >= e.K;                                         /* entropy can only lower the score */
+        }
+        r.score = sim;
+        /* match counts for entropy(), dna_utilities.c:2905-2915: the warp counts, 32 columns per trip */
+        u32 want = W_BALLOT(keep && e.entropy && sim <= 3 * e.K);
+        while (want) {
+            const int k = W_FFS(want) - 1; want &= want - 1;
+            const u32 q1 = W_SHFL(r.pos1, k), q2 = W_SHFL(r.pos2, k), len = W_SHFL(r.length, k);
+            u32 cA = 0, cC = 0, cG = 0, cT = 0;
+            for (u32 i0 = 0; i0 < len; i0 += 32) {
+                const u32 i = i0 + lane;
+                u8 x = 0, y = 1;
+                if (i < len) { x = e.asc1[q1 + i]; y = e.asc2[q2 + i]; }
+                const bool eq = x == y;
+                cA += (u32)W_POPC(W_BALLOT(eq && x == 'A')); cC += (u32)W_POPC(W_BALLOT(eq && x == 'C'));
+                cG += (u32)W_POPC(W_BALLOT(eq && x == 'G')); cT += (u32)W_POPC(W_BALLOT(eq && x == 'T'));
+            }
+            if ((int)lane == k) { r.cA = cA; r.cC = cC; r.cG = cG; r.cT = cT; }
+        }
+        if (keep) {
+            const u32 slot = (u32)W_ATOMIC_ADD_ULL(e.ncand, 1ull);
+            if (slot < e.candCap) e.cand[slot] = r;
+        }
     }
 }
 

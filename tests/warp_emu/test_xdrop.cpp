@@ -99,10 +99,9 @@ static int one_case(int caseNo, u32 len1, u32 len2, u32 nhits, double homolog, d
     e.len1 = len1; e.len2 = len2; e.L = L; e.xDrop = xDrop; e.K = K; e.entropy = entropy;
     e.cand = got.data(); e.candCap = (u32)got.size(); e.ncand = &ncand;
     u32 Eout[32]; unsigned long long nExt[32], nBp[32];
-    static u32 scratch[XD_WS_BYTES / 4];
     wemu_run([&](int lane) {
         u32 E = E0; unsigned long long x = 0, b = 0;
-        xd_bucket(e, (u32)lane, hits.data(), 0, (u32)hits.size(), E, x, b, scratch);
+        xd_bucket(e, (u32)lane, hits.data(), 0, (u32)hits.size(), E, x, b);
         Eout[lane] = E; nExt[lane] = x; nBp[lane] = b;
     });
     u64 tx = 0, tb = 0; for (int l = 0; l < 32; l++) { tx += nExt[l]; tb += nBp[l]; }
