@@ -638,4 +638,15 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one line, the JSON: anything a library prints there meanwhile (NCCL's version banner, ...)
+    # goes to stderr
+    _out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):                    # noqa: A001  (module-level shadow on purpose: main() prints only the JSON line to stdout)
+        if k.get("file") is None:
+            k["file"] = _out
+            k["flush"] = True
+        _print(*a, **k)
     sys.exit(main())

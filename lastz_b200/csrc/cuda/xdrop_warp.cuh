@@ -61,8 +61,15 @@ W_DEV u64 xd_ld8(const u8* p, u32 idx) {
 
 /* scores of scan columns o .. o+7 (scan-relative; n of them exist) of the scan that starts at
  * (p1,p2): DIR=+1 reads p1+o, p1+o+1, ...; DIR=-1 reads p1-1-o, p1-2-o, ...  Missing columns score 0. */
-template <int DIR>
+template <int DIR, bool FULL = false>
 W_DEV void xd_fetch8(const xd_env& e, u32 p1, u32 p2, u32 o, u32 n, s32 (&s)[8]) {
+    if (DIR > 0 && FULL) {                                       /* all eight columns exist: no per-column predicates */
+        const u64 x1 = xd_ld8(e.cls1, p1 + o), x2 = xd_ld8(e.cls2, p2 + o);
+        const u64 pr = (x1 << 4) + (x1 << 2) + x2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = e.lut[(u32)(pr >> (8 * i)) & 255u];
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = 0;
     if (n == 0) return;
@@ -119,8 +126,9 @@ W_DEV void xd_scan_cols(const s32 (&s)[8], u32 n, s32 xDrop, xd_scan& z) {
 template <int DIR>
 W_DEV void xd_scan_step8(const xd_env& e, u32 p1, u32 p2, s32 xDrop, xd_scan& z) {
     u32 n = z.avail - z.cols; if (n > 8) n = 8;
-    s32 s[8]; xd_fetch8<DIR>(e, p1, p2, z.cols, n, s);
-    if (n == 8) xd_scan_cols<DIR, true>(s, n, xDrop, z); else xd_scan_cols<DIR, false>(s, n, xDrop, z);
+    s32 s[8];
+    if (n == 8) { xd_fetch8<DIR, true>(e, p1, p2, z.cols, n, s); xd_scan_cols<DIR, true>(s, n, xDrop, z); }
+    else { xd_fetch8<DIR, false>(e, p1, p2, z.cols, n, s); xd_scan_cols<DIR, false>(s, n, xDrop, z); }
 }
 
 /* The warp finishes ONE scan; every lane passes the same state and receives the same result. */

@@ -11,6 +11,6 @@ tail -4 gpurun_out/scale_r2_n$N.err | cut -c1-300
 python - $N <<'P'
 import json,sys
 n=sys.argv[1]
-a=json.load(open(f'gpurun_out/scale_r2_n{n}.json'))
+a=[json.loads(l) for l in open(f'gpurun_out/scale_r2_n{n}.json') if l.startswith('{')][-1]
 for k in ('value','seed_hits_per_s','gcells_per_s','ms_per_step','stage_ms_per_step','e2e','gpu_launches','clocks','counts_per_step','scaling','config'): print(k, a.get(k))
 P
