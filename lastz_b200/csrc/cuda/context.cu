@@ -126,6 +126,7 @@ int lzb_upload_classes(lzb_ctx* c, const u8* h_seq, u32 len, u8** d_seq, u8** d_
 }
 
 extern "C" lzb_query* lzb_query_load(lzb_ctx* c, const uint8_t* seq2, uint32_t len2) {
+    if (len2 > 0x7FFFFFFFu) { lzb_fail("sequence length %u exceeds maximum (positions are 31-bit like the reference's default build; lastz_32 widths are not built)", len2); return NULL; }
     cudaSetDevice(c->device);
     const bool wtrace = getenv("LZB_SEED_TRACE") != NULL;
     const auto w0 = std::chrono::steady_clock::now();

@@ -23,6 +23,7 @@ extern "C" lzb_target* lzb_target_build(lzb_ctx* c, const uint8_t* seq1, uint32_
                                         uint32_t end, const int8_t ctb[256], const lzb_seed* seed, uint32_t step) {
     cudaSetDevice(c->device);
     if (step < 1) { lzb_fail("in build_seed_position_table(), step can't be %u", step); return NULL; }
+    if (len1 > 0x7FFFFFFFu) { lzb_fail("sequence length %u exceeds maximum (positions are 31-bit like the reference's default build; lastz_32 widths are not built)", len1); return NULL; }
     if (end == 0) end = len1;
     if (end <= start || end > len1) { lzb_fail("in build_seed_position_table(), interval is bad (%u..%u of %u)", start, end, len1); return NULL; }
     if (seed->weight > 28) { lzb_fail("new_position_table can't support >28 seed bits (%d requested)", seed->weight); return NULL; }
