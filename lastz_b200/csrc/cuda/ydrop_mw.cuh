@@ -340,6 +340,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     u32 acv = MW_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? -31 : 1) + lane), acvNext = MW_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? 1 : 33) + lane);
     if (lane == 31) sh.edgeC[warp] = C[K - 1];
     __syncthreads();
+    u32 nextCk = ckptCap ? (ckptCount + 1u) * ckptEvery : 0xFFFFFFFFu;
     if (status == DP_OK && !tbOnly)
     for (row = row0; row <= M; row++) {
         if (row >= rowLimit) { status = DP_PAUSED; break; }
@@ -450,7 +451,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
         }
         if ((s32)RY <= NN) RY++;                             /* the sentinel column already holds LZB_NEG_INF */
         /* ---- checkpoint: everything the next row reads ---- */
-        if (ckptCap && row % ckptEvery == 0 && row / ckptEvery - 1 == ckptCount && ckptCount < ckptCap && nact <= CK_ACT) {
+        if (row == nextCk && ckptCount < ckptCap && nact <= CK_ACT) {     /* record k belongs to row (k+1)*ckptEvery; a record that cannot be written ends the series */
             u32* rec = ckpt + (size_t)ckptCount * CKW;
             if (tid == 0) {
                 rec[0] = row; rec[1] = LY; rec[2] = RY; rec[3] = (u32)L; rec[4] = (u32)R;
@@ -472,7 +473,7 @@ k_ydrop_mw(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
                 const u32 ix = cb + (u32)s - c0;
                 if (cb + (u32)s >= c0 && ix < CK_COLS) { tv[ix] = (u32)C[s]; tv[CK_COLS + ix] = (u32)D[s]; }
             }
-            ckptCount++;
+            ckptCount++; nextCk += ckptEvery;
         }
     }
 #undef MW_LOAD_BLOCK

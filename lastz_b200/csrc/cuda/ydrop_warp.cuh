@@ -289,6 +289,7 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
     /* (a checkpoint row is a multiple of 32: the loop's first iteration then shifts acvNext into acv) */
     u32 acv = WG_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? -31 : 1) + lane), acvNext = WG_ACODE(((row0 - 1) & ~31u) + (row0 > 1 ? 1 : 33) + lane);
     __syncwarp();
+    u32 nextCk = ckptCap ? (ckptCount + 1u) * ckptEvery : 0xFFFFFFFFu;
     if (status == DP_OK && !tbOnly)
     for (row = row0; row <= M; row++) {
         if (row >= rowLimit) { status = DP_PAUSED; break; }
@@ -395,7 +396,7 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
         }
         if ((s32)RY <= NN) RY++;                             /* the sentinel column already holds LZB_NEG_INF */
         /* ---- checkpoint: everything the next row reads ---- */
-        if (ckptCap && row % ckptEvery == 0 && row / ckptEvery - 1 == ckptCount && ckptCount < ckptCap && nact <= CK_ACT) {
+        if (row == nextCk && ckptCount < ckptCap && nact <= CK_ACT) {     /* record k belongs to row (k+1)*ckptEvery; a record that cannot be written ends the series */
             u32* rec = ckpt + (size_t)ckptCount * CKW;
             if (lane == 0) {
                 rec[0] = row; rec[1] = LY; rec[2] = RY; rec[3] = (u32)L; rec[4] = (u32)R;
@@ -416,7 +417,7 @@ k_ydrop_warp(dp_job* jobs, const launch_list ll, const dseg* __restrict__ segs,
                 const u32 ix = S.cb + (u32)s - c0;
                 if (S.cb + (u32)s >= c0 && ix < CK_COLS) { tv[ix] = (u32)S.C[s]; tv[CK_COLS + ix] = (u32)S.D[s]; }
             }
-            ckptCount++;
+            ckptCount++; nextCk += ckptEvery;
         }
     }
 #undef WG_LOAD_BLOCK
