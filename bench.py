@@ -238,7 +238,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("LZB_BENCH_WORKLOAD", "auto"), choices=["auto", "config3", "config4"])
     ap.add_argument("--size", type=int, default=0, help="override the workload's sequence length (tests)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--speculation", type=int, default=384)
+    ap.add_argument("--speculation", type=int, default=280,
+                    help="anchors in flight in the gapped phase, both strands together (two sweeps each: 560 one-warp CTAs stay "
+                         "under the 4 x 148 the Y-drop kernel is resident with)")
     ap.add_argument("--cpu-sample", type=int, default=500_000, help="query bp per reference process (x1 and x2)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference processes (default: every host core, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -318,6 +320,8 @@ def main():
         engB = Engine.product(local)                     # a second context (stream, scratch) for the other strand
         engB.set_scoring(ss)
 
+    lanes_per_scheduler = max(1, args.speculation // 2) if overlap else args.speculation
+
     def sync():
         if on_gpu:
             torch.cuda.synchronize()
@@ -361,7 +365,7 @@ def main():
         def gapped_part(eng, sid, s, Q, segs, table, resident, acc):
             wc = time.perf_counter()
             anchors = eng.reduce_to_points(T, Q, segs)
-            al, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, identity_check=False, speculation=args.speculation)
+            al, gst, _ = eng.gapped_extend(T, Q, target, s, anchors, identity_check=False, speculation=lanes_per_scheduler)
             w2 = time.perf_counter()
             acc["gap_wall"] += w2 - wc
             acc["cells"] += gst.dpCells; acc["cells_computed"] += gst.dpCellsComputed
