@@ -94,6 +94,7 @@ struct gx_cache {                        /* lives in the context: lanes are expe
      * hardware queue with a running DP kernel waits for that kernel (engine switch inside one channel) */
     u32* h_stage; u32* d_stage; cudaStream_t upStream;
     cudaStream_t streams[GX_STREAMS]; int nStreams;
+    size_t warpSmem;                                         /* dynamic shared memory asked for per one-warp CTA (caps CTAs per SM) */
     std::vector<std::pair<u16, u32> > inflight[GX_STREAMS];   /* (job, token) of the last launch on each stream */
     const u8* cls1; const u8* cls2; u32 len1, len2; s32 yDrop; int trim;   /* of the current call */
     u32 launched[2 * GX_MAX_LANES];      /* token of the last launch of each job (0: never launched) */
@@ -284,7 +285,7 @@ struct cuda_backend {
             /* 47 KB of (unused) dynamic shared memory per one-warp CTA: at most four of them fit an SM, one per scheduler --
              * left to itself the block scheduler stacks dozens of 32-thread CTAs on some SMs while others idle, and the
              * sweeps there run at a fraction of their speed (measured: 1.8 us a row alone, 3.4 median, 9 worst) */
-            k_ydrop_warp<16><<<n, 32, 47 * 1024, st>>>(gc->d_jobs, ll, gc->d_segs, gc->cls1, gc->cls2, gc->len1, gc->len2, c->d_sc, gc->yDrop, gc->trim);
+            k_ydrop_warp<16><<<n, 32, gc->warpSmem, st>>>(gc->d_jobs, ll, gc->d_segs, gc->cls1, gc->cls2, gc->len1, gc->len2, c->d_sc, gc->yDrop, gc->trim);
         else {
             const u32 rg = ring(mode);
             size_t smem = (size_t)rg * 17 + LZB_MAX_CLASSES * LZB_MAX_CLASSES * 4 + 1024;
@@ -353,6 +354,8 @@ extern "C" int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const 
         gc->alignsCap = 1u << 18; CUDA_TRY(cudaMalloc(&gc->d_aligns, gc->alignsCap * sizeof(dalign)));
         CUDA_TRY(cudaFuncSetAttribute(k_ydrop<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(k_ydrop_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 47 * 1024));
+        gc->warpSmem = 47 * 1024;
+        { const char* e = getenv("LZB_WARP_SMEM_KB"); if (e) { int v = atoi(e); if (v >= 0 && v <= 47) gc->warpSmem = (size_t)v * 1024; } }
     }
     gc->cls1 = t->d_cls; gc->cls2 = q->d_cls; gc->len1 = t->len; gc->len2 = q->len; gc->yDrop = P->yDrop; gc->trim = P->trimToPeak;
     cuda_backend B; B.gc = gc;
