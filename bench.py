@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference processes (default: every host core, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: skip the end-to-end pass (the e2e key then repeats the resident pass and says so)")
+    ap.add_argument("--overlap-extend-ctas", type=int, default=0, help="k_extend2 CTAs per SM while it runs beside the other strand's sweeps (0: the library's 4)")
     ap.add_argument("--no-overlap", action="store_true", help="run the two strands one after the other")
     ap.add_argument("--no-config4-base", action="store_true", help="skip the single pass of config4 on the one-GPU line")
     args = ap.parse_args()
@@ -398,7 +399,14 @@ def main():
                 th = threading.Thread(target=first_gapped)
                 th.start()
                 try:
-                    QB, segsB, tabB = seed_part(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+                    # beside the first strand's sweeps the extension kernel runs with fewer persistent CTAs per SM, so that the
+                    # sweeps (one warp each, latency-bound) keep their issue slots; the seed stage has their whole duration to hide in
+                    if args.overlap_extend_ctas:
+                        os.environ["LZB_EXTEND_CTAS_PER_SM"] = str(args.overlap_extend_ctas)
+                    try:
+                        QB, segsB, tabB = seed_part(engB, sidB, sB, handles[1] if resident else None, resident, accB)
+                    finally:
+                        os.environ.pop("LZB_EXTEND_CTAS_PER_SM", None)
                     gapped_part(engB, sidB, sB, QB, segsB, tabB, resident, accB)
                 finally:
                     th.join()

@@ -178,6 +178,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= XD_LUT_MAX_CLASSES && !splitExtend &&
                             !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
     u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
+    /* persistent CTAs of k_extend2 per SM: four fill the register file; a caller that runs this stage beside another
+     * context's Y-drop sweeps can ask for fewer so that those keep their issue slots (LZB_EXTEND_CTAS_PER_SM, read per call) */
+    int extCtas = 4;
+    { const char* e = getenv("LZB_EXTEND_CTAS_PER_SM"); if (e) { int v = atoi(e); if (v >= 1 && v <= 4) extCtas = v; } }
     if (coopExtend) {
         SCRATCH(13, d_bcnt, (size_t)nbuckets * 4); SCRATCH(14, d_bcnt2, (size_t)nbuckets * 4);
         SCRATCH(15, d_bid, (size_t)nbuckets * 4); SCRATCH(16, d_border, (size_t)nbuckets * 4);
@@ -229,7 +233,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
                 CUDA_TRY(cudaMemsetAsync(d_next, 0, 4, st));
                 TIMED(11, (k_bucket_sizes<<<(nbuckets + 255) / 256, 256, 0, st>>>(d_bstart, nbuckets, d_bcnt, d_bid)));
                 TIMED(11, cub::DeviceRadixSort::SortPairsDescending(d_tmp, tbo, d_bcnt, d_bcnt2, d_bid, d_border, nbuckets, 0, bits, st));
-                TIMED(7, (k_extend2<<<c->smCount * 4, 256, 0, st>>>(valsB, d_bstart, d_border, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
+                TIMED(7, (k_extend2<<<c->smCount * extCtas, 256, 0, st>>>(valsB, d_bstart, d_border, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
                                                                      c->d_sc, P, d_E, d_cand, candCap, d_cnt, d_next)));
             } else if (c->sc.numClasses <= 16)
                 TIMED(7, (k_extend<true><<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,

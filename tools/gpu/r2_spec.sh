@@ -12,6 +12,6 @@ print(sys.argv[1], 'ms_per_step', round(a['ms_per_step'],1), round(a['stage_ms_p
 P
   grep "gx profile" gpurun_out/bench_spec_$name.err | tail -2 | cut -c1-330
 }
-ARGS="--speculation 384" run stagger X=1
-ARGS="--speculation 384" run stagger_smem23 LZB_WARP_SMEM_KB=23
-ARGS="--speculation 384" run stagger_smem0 LZB_WARP_SMEM_KB=0
+ARGS="--overlap-extend-ctas 2" run stagger_e2 LZB_WARP_SMEM_KB=23
+ARGS="--overlap-extend-ctas 1" run stagger_e1 LZB_WARP_SMEM_KB=23
+ARGS="--overlap-extend-ctas 3" run stagger_e3 LZB_WARP_SMEM_KB=23
