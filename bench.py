@@ -243,7 +243,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference processes (default: every host core, at most 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: skip the end-to-end pass (the e2e key then repeats the resident pass and says so)")
-    ap.add_argument("--overlap-extend-ctas", type=int, default=0, help="k_extend2 CTAs per SM while it runs beside the other strand's sweeps (0: the library's 4)")
+    ap.add_argument("--overlap-extend-ctas", type=int, default=2, help="k_extend2 CTAs per SM while it runs beside the other strand's sweeps (0: the library's 4)")
     ap.add_argument("--no-overlap", action="store_true", help="run the two strands one after the other")
     ap.add_argument("--no-config4-base", action="store_true", help="skip the single pass of config4 on the one-GPU line")
     args = ap.parse_args()
