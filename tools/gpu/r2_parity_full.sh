@@ -7,13 +7,13 @@ mkdir -p /tmp/syn gpurun_out
 tools/gen_synth 50000000 20260925 /tmp/syn/t50.fa /tmp/syn/q50.fa
 NP=$(nproc); [ $NP -gt 16 ] && NP=16
 t0=$(date +%s.%N)
-( seq 0 49 | xargs -P $NP -I{} bash -c 'a=$(( {} * 1000000 + 1 )); b=$(( a + 999999 )); oracle/_ref/lastz /tmp/syn/t50.fa "/tmp/syn/q50.fa[$a..$b]" > /tmp/syn/ref.{}.lav 2>/dev/null'; echo "reference_wall_s $(echo "$(date +%s.%N) - $t0" | bc) on $NP processes" > /tmp/syn/ref.time ) &
+( seq 0 49 | xargs -P $NP -I{} bash -c 'a=$(( {} * 1000000 + 1 )); b=$(( a + 999999 )); oracle/_ref/lastz /tmp/syn/t50.fa "/tmp/syn/q50.fa[$a..$b]" > /tmp/syn/ref.{}.lav 2>/dev/null'; echo "reference_wall_s $(awk "BEGIN{print $(date +%s.%N) - $t0}") on $NP processes" > /tmp/syn/ref.time ) &
 t1=$(date +%s.%N)
 for k in $(seq 0 49); do
   a=$(( k * 1000000 + 1 )); b=$(( a + 999999 ))
   lastz_b200/csrc/lastz_b200 /tmp/syn/t50.fa "/tmp/syn/q50.fa[$a..$b]" > /tmp/syn/our.$k.lav 2>/tmp/syn/our.$k.err || echo "product failed on shard $k: $(tail -1 /tmp/syn/our.$k.err)"
 done
-echo "product_wall_s $(echo "$(date +%s.%N) - $t1" | bc) (50 process starts, 50 index builds)" > /tmp/syn/our.time
+echo "product_wall_s $(awk "BEGIN{print $(date +%s.%N) - $t1}") (50 process starts, 50 index builds)" > /tmp/syn/our.time
 wait
 same=0; diff=0; aligns=0
 for k in $(seq 0 49); do
