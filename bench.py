@@ -422,6 +422,7 @@ def main():
                     acc[k] = [a + b for a, b in zip(accA[k], accB[k])]
                 else:
                     acc[k] = accA[k] + accB[k]
+            acc["first"] = dict(ext_s=accA["ext_s"], ext_launch=accA["ext_launch"], hits=accA["hits"], bp=accA["bp"])
             acc["gap_phase_wall"] = acc["gap_wall"]            # the two strands' gapped calls, each on its own clock
             w3 = time.perf_counter()
             segs_all = gather_to_rank0(np.concatenate(acc["tables"]).view(np.uint8).reshape(-1), dev)
@@ -497,6 +498,12 @@ def main():
     bytes_per_hit = 12.0 + 0.5 * my_bp / max(1, my_hits)      # 4 B position + 8 B diagEnd + 0.5 B/column
     peak, peak_src = measured_peak()
     achieved = bytes_per_hit * my_hits / max(ext_s, 1e-12) / 1e9
+    # the first strand's launches alone: with the strands overlapped the second strand's k_extend2 runs beside the first
+    # strand's Y-drop sweeps (and with fewer CTAs per SM on purpose), which stretches its launches
+    f_s = sum(a["first"]["ext_s"] for a in accs); f_n = max(1, sum(a["first"]["ext_launch"] for a in accs))
+    f_hits = sum(a["first"]["hits"] for a in accs); f_bp = sum(a["first"]["bp"] for a in accs)
+    f_bytes = 12.0 + 0.5 * f_bp / max(1, f_hits)
+    f_achieved = f_bytes * f_hits / max(f_s, 1e-12) / 1e9
     # every cross-rank aggregate is computed HERE, on all ranks (collectives must not sit under `if rank == 0`)
     agg = {"e2e_hits": total("hits", accs_e2e), "e2e_cells": total("cells", accs_e2e),
            "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_phase_wall", accs_e2e),
@@ -579,7 +586,11 @@ def main():
                              "traffic_source": None if traffic_per_hit is None else
                              f"dram__bytes_read+write per hit from the ncu --set full capture in profiles/ ({traffic_src}) x hits per launch here",
                              "peak_source": peak_src,
-                             "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n},
+                             "bytes_per_hit": bytes_per_hit, "launches": ext_n, "avg_launch_ms": 1e3 * ext_s / ext_n,
+                             "first_strand_alone": {"achieved": f_achieved, "frac": f_achieved / peak, "launches": f_n, "avg_launch_ms": 1e3 * f_s / f_n,
+                                                    "note": "the launches of the first strand, which run with the GPU to themselves; achieved/frac above "
+                                                            "average over all launches of the timed region, the second strand's beside the first "
+                                                            "strand's Y-drop sweeps included"} if overlap else None},
                 "wall_ms_per_step": {"resident": wall_breakdown(accs), "e2e": wall_breakdown(accs_e2e)}}
         # the other kernels against the same HBM peak (algorithmic bytes as in DESIGN.md section 4)
         V = seed.numFlips + 1 if seed.withTrans == 1 else 1
