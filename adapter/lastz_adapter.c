@@ -122,8 +122,8 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
                     hitprocessor processor, void* processorInfo) {
     (void)hitSeed; (void)reportSearchLimit;
     if (pt != g_targetKey || !g_target) suicide("the lastz_b200 adapter was handed a position table it did not build");
-    if (processor != process_for_simple_hit && processor != process_for_plain_hit)
-        suicide("the lastz_b200 adapter supports the simple and plain hit processors only (no --twins, --recoverseeds)");
+    if (processor != process_for_simple_hit && processor != process_for_plain_hit && processor != process_for_recoverable_hit)
+        suicide("the lastz_b200 adapter supports the simple, plain and recoverable hit processors only (no --twins)");
     if (searchLimit != 0) suicide("the lastz_b200 adapter does not support --queryhsplimit / search limits");
 #ifdef densityFiltering
     if (maxDensity != 0) suicide("the lastz_b200 adapter does not support --maxdensity");
@@ -134,7 +134,7 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
     hitprocinfo* hp = (hitprocinfo*)processorInfo;          /* first member of every hit processor's info (seed_search.h:112-156) */
     if (hp->posFilter) suicide("the lastz_b200 adapter does not support positional hit filters");
     if (hp->minMatches >= 0) suicide("the lastz_b200 adapter does not support --filter=<transv>,<matches>");
-    if (processor == process_for_simple_hit && hp->gfExtend != gfexNoExtend && hp->hspThreshold.t != 'S')
+    if (processor != process_for_plain_hit && hp->gfExtend != gfexNoExtend && hp->hspThreshold.t != 'S')
         suicide("the lastz_b200 adapter does not support adaptive HSP thresholds");
     use_scoring(NULL, hp->scoring);
     if (g_query) { lzb_query_free(g_query); g_query = NULL; }
@@ -144,6 +144,7 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
     lzb_seed_params sp; memset(&sp, 0, sizeof sp);
     sp.start = (uint32_t)start; sp.end = (uint32_t)end;
     sp.plainHits = processor == process_for_plain_hit;
+    sp.recoverSeeds = processor == process_for_recoverable_hit;   /* --recoverseeds; the reference merges the table itself (lastz.c:3296) */
     sp.gfExtend = sp.plainHits ? LZB_GFEX_NONE
                 : hp->gfExtend == gfexXDrop ? LZB_GFEX_XDROP
                 : hp->gfExtend == gfexExact ? LZB_GFEX_EXACT

@@ -113,6 +113,11 @@ typedef struct lzb_seed_params {
                                   no diag-hash filter; chosen by the reference when neither gap-free
                                   nor gapped extension is requested (lastz.c:2789) */
     int32_t  gfMismatches;     /* LZB_GFEX_MISMATCH: mismatches allowed, 1..50 */
+    int32_t  recoverSeeds;     /* --recoverseeds: process_for_recoverable_hit (seed_search.c:1221) instead of the simple
+                                  processor -- a hit on another diagonal of the same hash bucket is extended rather than
+                                  lost, left extension is not blocked by the bucket, overlapping HSPs may be reported
+                                  (the caller merges them: merge_segments segment.c:1527 = lzb_merge_segments of the host
+                                  library).  With LZB_GFEX_XDROP or LZB_GFEX_NONE only. */
 } lzb_seed_params;
 
 typedef struct lzb_seed_stats {

@@ -51,6 +51,8 @@ def host_lib():
         _host.lzb_scores_read_file.argtypes = [C.POINTER(_ScoreSet), C.c_char_p]
         _host.lzb_reduce_to_chain.restype = C.c_int32
         _host.lzb_reduce_to_chain.argtypes = [C.POINTER(capi.Segment), C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        _host.lzb_merge_segments.restype = None
+        _host.lzb_merge_segments.argtypes = [C.POINTER(capi.Segment), C.POINTER(C.c_uint64)]
     return _host
 
 
@@ -62,6 +64,16 @@ def reduce_to_chain(segs, scoring, diag_penalty=0, anti_penalty=0):
     if len(a):
         host_lib().lzb_reduce_to_chain(a.ctypes.data_as(C.POINTER(capi.Segment)), C.byref(n), diag_penalty, anti_penalty,
                                        100, scoring.sub[ord("A") * 256 + ord("A")])
+    return a[:n.value]
+
+
+def merge_segments(segs):
+    """merge_segments segment.c:1527: HSPs that share positions on one diagonal become one (what the reference does to the
+    table of the recoverable hit processor and to anchors read from a file).  Host C (csrc/host/merge.c)."""
+    a = np.ascontiguousarray(segs).copy()
+    n = C.c_uint64(len(a))
+    if len(a):
+        host_lib().lzb_merge_segments(a.ctypes.data_as(C.POINTER(capi.Segment)), C.byref(n))
     return a[:n.value]
 
 
@@ -193,9 +205,9 @@ class Engine:
     # ---- seed_search.h:265 (+ process_for_simple_hit, xdrop_extend_seed_hit, collect_hsps)
     def seed_hit_search(self, t, q, seed, *, start=0, end=0, gf_extend=1, x_drop=910,
                         hsp_threshold=3000, entropy=True, hash_bits=16, self_compare=False,
-                        same_strand=False, strand_id=RCF_FORWARD, plain_hits=False, gf_mismatches=0):
+                        same_strand=False, strand_id=RCF_FORWARD, plain_hits=False, gf_mismatches=0, recover_seeds=False):
         p = capi.SeedParams(start, end, gf_extend, x_drop, hsp_threshold, int(entropy), hash_bits,
-                            int(self_compare), int(same_strand), strand_id, int(plain_hits), gf_mismatches)
+                            int(self_compare), int(same_strand), strand_id, int(plain_hits), gf_mismatches, int(recover_seeds))
         segs = C.POINTER(capi.Segment)()
         n = C.c_uint64(0)
         st = capi.SeedStats()

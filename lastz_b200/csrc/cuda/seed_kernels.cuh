@@ -312,6 +312,79 @@ k_extend(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuck
     if (lane == 0) { if (nExt) atomicAdd(&cnt->extensions, nExt); if (bpw) atomicAdd(&cnt->bpExtended, bpw); }
 }
 
+/* ---- K3r: process_for_recoverable_hit (seed_search.c:1221-1443, --recoverseeds) with x-drop or no extension ----
+ * One thread replays one bucket in discovery order.  The bucket remembers the ACTUAL diagonal of its last fresh hit
+ * beside the extent: a hit on another diagonal of the same bucket is extended instead of lost (:1298-1336), one on the
+ * same diagonal that starts inside the extent is dropped and moves the extent up to its own end (:1341-1360).  Left
+ * extension is not blocked by the bucket (unblockedLeftExtension, :2612) and the extent only ever grows (:2785-2789),
+ * so overlapping HSPs can come out; the caller merges them (merge_segments segment.c:1527).  A non-default option:
+ * the scans walk one column at a time. */
+__global__ void __launch_bounds__(128)
+k_extend_recover(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuckets,
+                 const u8* __restrict__ cls1, const u8* __restrict__ cls2,
+                 const u8* __restrict__ asc1, const u8* __restrict__ asc2,
+                 const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32* __restrict__ diagEnd, s32* __restrict__ diagActual,
+                 cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt) {
+    const u32 L = (u32)P.L;
+    const s32 xDrop = P.xDrop;
+    unsigned long long nExt = 0, nBp = 0;
+    for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nbuckets; h += gridDim.x * blockDim.x) {
+        const u32 b0 = bstart[h], b1 = bstart[h + 1];
+        if (b0 == b1) continue;
+        u32 E = diagEnd[h]; s32 A = diagActual[h];       /* an untouched bucket reads as extent 0, which lets every hit through */
+        for (u32 idx = b0; idx < b1; idx++) {
+            const u64 rec = hits[idx];
+            const u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
+            const s32 diag = (s32)(pos1 - pos2);
+            if (diag == A && pos2 - L < E) { if (pos2 > E) E = pos2; continue; }
+            A = diag;                                                    /* fresh_hit :1373 */
+            if (P.gfExtend != LZB_GFEX_XDROP) {                         /* :1417-1421 */
+                if (pos2 > E) E = pos2;
+                const u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+                if (slot < candCap) { cand_rec r = { pos1, pos2, pos1 - L, pos2 - L, L, 0, 0, 0, 0, 0 }; cand[slot] = r; }
+                continue;
+            }
+            /* left scan :2598-2632 from the hit's right end, stopping only at the start of either sequence */
+            const u32 stop = diag > 0 ? (u32)diag : 0u;
+            u32 a = pos1, b = pos2, leftLen = 0, leftCols = 0; s32 run = 0, leftScore = 0;
+            while (a > stop && run >= leftScore - xDrop) {
+                --a; --b;
+                run += sc->msubC[(u32)cls1[a] * LZB_MAX_CLASSES + cls2[b]];
+                leftCols++;
+                if (run > leftScore) { leftScore = run; leftLen = leftCols; }
+            }
+            /* right scan :2663-2693 to the end of either sequence */
+            const s64 lim = (s64)P.len2 + diag;
+            const u32 rstop = ((s64)P.len1 <= lim) ? P.len1 : (u32)lim;
+            u32 rightLen = 0, rightCols = 0; s32 rightScore = 0; run = 0; a = pos1; b = pos2;
+            while (a < rstop && run >= rightScore - xDrop) {
+                run += sc->msubC[(u32)cls1[a] * LZB_MAX_CLASSES + cls2[b]];
+                a++; b++; rightCols++;
+                if (run > rightScore) { rightScore = run; rightLen = rightCols; }
+            }
+            nExt++; nBp += rightCols + leftCols;
+            const u32 extent = (u32)((s64)a - diag);                    /* where the right scan stopped, in sequence 2 */
+            if (extent > E) E = extent;
+            const s32 sim = leftScore + rightScore;
+            if (sim < P.K) continue;                                     /* entropy can only lower the score */
+            cand_rec r;
+            r.hit1 = pos1; r.hit2 = pos2; r.pos1 = pos1 - leftLen; r.pos2 = pos2 - leftLen;
+            r.length = leftLen + rightLen; r.score = sim; r.cA = r.cC = r.cG = r.cT = 0;
+            if (P.entropy && sim <= 3 * P.K) {
+                for (u32 i = 0; i < r.length; i++) {
+                    const u8 x = asc1[r.pos1 + i];
+                    if (x == asc2[r.pos2 + i]) { r.cA += x == 'A'; r.cC += x == 'C'; r.cG += x == 'G'; r.cT += x == 'T'; }
+                }
+            }
+            const u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+            if (slot < candCap) cand[slot] = r;
+        }
+        diagEnd[h] = E; diagActual[h] = A;
+    }
+    if (nExt) atomicAdd(&cnt->extensions, nExt);
+    if (nBp) atomicAdd(&cnt->bpExtended, nBp);
+}
+
 /* ---- K3c: the default extension kernel (x-drop, <= 16 byte classes): xdrop_warp.cuh ----
  * Buckets are handed out largest first from a global counter (longest-processing-time order): the
  * few buckets that hold a homologous diagonal take far longer than the rest, and with a static

@@ -89,6 +89,9 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     if (seed->length < 2) return lzb_fail("seed length must be at least two (yours is %d)", seed->length);
     if (prm->gfExtend == LZB_GFEX_MISMATCH && (prm->gfMismatches < 1 || prm->gfMismatches > LZB_GFEX_MISMATCH_MAX))
         return lzb_fail("%d is out of range for N-mismatch (valid range is 1..%d)", prm->gfMismatches, LZB_GFEX_MISMATCH_MAX);
+    const bool recover = prm->recoverSeeds && !prm->plainHits;      /* process_for_recoverable_hit; the plain processor wins (lastz.c:2789-2792) */
+    if (recover && prm->gfExtend != LZB_GFEX_XDROP && prm->gfExtend != LZB_GFEX_NONE)
+        return lzb_fail("recoverSeeds is built for x-drop extension and --nogfextend only");
     if (seed->weight != t->wordBits || seed->length != t->seedLength)
         return lzb_fail("the seed does not match the one the target index was built with");
     int hashBits = prm->hashBits ? prm->hashBits : 16;
@@ -135,6 +138,8 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cudaMemcpyAsync(d_flips, flips.data(), flips.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(search_counters), st));
     CUDA_TRY(cudaMemsetAsync(d_E, 0, (size_t)nbuckets * 4, st));        /* empty_diag_hash diag_hash.c:125 */
+    s32* d_A = NULL;                                                     /* diagActual[] (diag_hash.h:70), recoverable processor only */
+    if (recover) { SCRATCH(22, d_A, (size_t)nbuckets * 4); CUDA_TRY(cudaMemsetAsync(d_A, 0, (size_t)nbuckets * 4, st)); }
     CUDA_TRY(cudaEventRecord(evBegin, st));
     int grid = c->smCount * 8;
 #define TIMED(which_, launch_)                                                          \
@@ -172,10 +177,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     /* the three-kernel extension (xdrop_split.cuh) measured SLOWER than the fused kernel (0.70 s vs 0.62 s
      * at 50 Mbp x 50 Mbp: the extra passes over the hit records cost more than the lockstep idling they
      * remove), so it is opt-in: LZB_SPLIT_EXTEND=1.  Kept because it bounds the work on long repeats. */
-    const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= 16 &&
+    const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && !recover && c->sc.numClasses <= 16 &&
                              getenv("LZB_SPLIT_EXTEND") && atoi(getenv("LZB_SPLIT_EXTEND"));
     /* the warp-cooperative kernel (xdrop_warp.cuh) is the default x-drop path; LZB_EXTEND_V1=1 keeps the first one */
-    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && c->sc.numClasses <= XD_LUT_MAX_CLASSES && !splitExtend &&
+    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && !recover && c->sc.numClasses <= XD_LUT_MAX_CLASSES && !splitExtend &&
                             !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
     u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
     /* persistent CTAs of k_extend2 per SM: four fill the register file; a caller that runs this stage beside another
@@ -218,7 +223,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             tb = tmpBytes;
             TIMED(5, cub::DeviceRadixSort::SortPairs(d_tmp, tb, keysA, keysB, valsA, valsB, nh, 0, hashBits, st));
             TIMED(6, (k_bucket_bounds<<<(nbuckets + 256) / 256, 256, 0, st>>>(keysB, nh, nbuckets, d_bstart)));
-            if (splitExtend) {
+            if (recover) {
+                TIMED(7, (k_extend_recover<<<(nbuckets + 127) / 128, 128, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
+                                                                                     c->d_sc, P, d_E, d_A, d_cand, candCap, d_cnt)));
+            } else if (splitExtend) {
                 CUDA_TRY(cudaMemsetAsync(d_nlive, 0, 8, st));
                 TIMED(8, (k_right<<<c->smCount * 8, 256, 0, st>>>(valsB, nh, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_right)));
                 TIMED(9, (k_replay<<<grid, 256, 0, st>>>(valsB, d_bstart, nbuckets, d_right, t->d_cls, q->d_cls, c->d_sc, P, d_E, d_live, d_nlive)));

@@ -19,6 +19,7 @@ typedef struct {
     uint32_t step; int haveStep;
     int whichStrand;               /* 0 plus, 1 both, -1 minus */
     int gfExtend, gfMismatches, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
+    int recoverSeeds;              /* --recoverseeds: process_for_recoverable_hit + merge_segments (lastz.c:5712-5720, :2791, :2811) */
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
     int adaptive; double adaptFraction; uint32_t adaptBases;   /* K=top<N>% ('P') or K=top<bases> ('C'), string_to_score_thresh dna_utilities.c:2248 */
     uint32_t tracebackBytes;
@@ -129,6 +130,8 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--word=")) ;                         /* lastz.c:5665: max index bits; only a table-layout matter (overweight
                                                                     seeds are "resolved", seed_search.c:878) -- this index holds 28 bits anyway */
         else if (!strcmp(a, "--anyornone") || !strcmp(a, "--stopafterone")) o->anyOrNone = 1;
+        else if (!strcmp(a, "--recoverseeds") || !strcmp(a, "--recoverhits")) o->recoverSeeds = 1;
+        else if (!strcmp(a, "--norecoverseeds") || !strcmp(a, "--norecoverhits")) o->recoverSeeds = 0;
         else if (!strcmp(a, "--justhits") || !strcmp(a, "--hitsonly")) { o->gfExtend = LZB_GFEX_NONE; o->gapped = 0; }   /* lastz.c:5875 */
         else if (starts(a, "W=") || starts(a, "--seed=match")) {
             int w = atoi(starts(a, "--seed=match") ? a + 12 : v);
@@ -414,6 +417,12 @@ int main(int argc, char** argv) {
     }
     if (o.wordCountLimit > 0 && lzb_target_limit(T, o.wordCountLimit)) lzb_die("%s", lzb_last_error());
 
+    if (o.recoverSeeds) {           /* built: x-drop extension or none, a fixed threshold, no --self mirroring of the merged table */
+        if (o.gfExtend == LZB_GFEX_EXACT || o.gfExtend == LZB_GFEX_MISMATCH) lzb_die("lastz_b200 implements --recoverseeds with x-drop extension or --nogfextend only");
+        if (o.selfCompare) lzb_die("lastz_b200 does not implement --recoverseeds together with --self");
+        if (o.adaptive) lzb_die("lastz_b200 does not implement --recoverseeds together with an adaptive --hspthresh");
+    }
+
     /* thresholds as the headers print them (score_thresh_to_string dna_utilities.c:2290): an adaptive one as top<bases>,
      * the percentage already resolved against the target length; an unset L copies K */
     char textK[32], textL[32];
@@ -509,6 +518,7 @@ int main(int argc, char** argv) {
                 sp.sameStrand = o.selfCompare && query.revCompFlags == target.revCompFlags;
                 sp.strandId = query.revCompFlags;
                 sp.plainHits = (o.gfExtend == LZB_GFEX_NONE && !o.gapped);
+                sp.recoverSeeds = o.recoverSeeds && !sp.plainHits;        /* the plain processor wins (lastz.c:2789-2792) */
                 if (lzb_seed_hit_search(ctx, T, Q, &seed, lzb_upper_nuc_to_bits, &sp, &segs, &nsegs, &sst))
                     lzb_die("%s", lzb_last_error());
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
@@ -550,6 +560,9 @@ int main(int argc, char** argv) {
                 }
                 segs = strandSegs[pass]; nsegs = strandN[pass]; strandSegs[pass] = NULL;
             }
+            /* anchors from a file, and HSPs of a processor that may report overlapping ones, are merged per diagonal before
+             * anything else looks at them (lastz.c:757, :2811, :3296; merge_segments segment.c:1527) */
+            if (o.segmentsFile || (o.recoverSeeds && !(o.gfExtend == LZB_GFEX_NONE && !o.gapped))) lzb_merge_segments(segs, &nsegs);
             if (!o.adaptive && o.selfCompare && !o.gapped && !o.segmentsFile && nsegs) {
                 lzb_segment* both = malloc(2 * nsegs * sizeof *both); uint64_t m = 0;
                 int same = query.revCompFlags == target.revCompFlags;

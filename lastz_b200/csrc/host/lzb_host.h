@@ -76,6 +76,7 @@ extern const int8_t lzb_nuc_to_bits[256];                      /* dna_utilities.
 
 /* best-chain reduction (chain.c:497, penalties lastz.c:3687); rewrites segs[0..*n) to the chain, sorted by pos1 */
 int32_t lzb_reduce_to_chain(lzb_segment* segs, uint64_t* n, int32_t diagPen, int32_t antiPen, int32_t scale, int32_t subAA);
+void lzb_merge_segments(lzb_segment* segs, uint64_t* n);                                     /* merge_segments segment.c:1527 (merge.c) */
 /* ... per pair of partitions when either sequence is [multi] (try_reduce_to_chain chain.c:224), result sorted by pos1 */
 int32_t lzb_reduce_to_chains(const lzb_seq* s1, const lzb_seq* s2, lzb_segment* segs, uint64_t* n,
                              int32_t diagPen, int32_t antiPen, int32_t scale, int32_t subAA);

@@ -173,6 +173,7 @@ typedef struct {
     lzb_ctx* c; lzb_target* t; lzb_query* q;
     const lzb_seed* sd; const lzb_seed_params* p;
     u32* E;  u32 hmask;                 /* diagEnd[], diag_hash.h:68 */
+    s32* A;                             /* diagActual[], diag_hash.h:70 (recoverable processor only) */
     lzb_segment* out; u64 n, cap;
     lzb_seed_stats st;
 } search;
@@ -310,11 +311,21 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
     if (P->plainHits) { emit_hsp(S, pos1, pos2, len, 0); return; }   /* :995-1030 */
     s32 diag = (s32)(pos1 - pos2);
     u32 h = (u32)diag & S->hmask;
-    /* :1097-1113 -- inactive buckets read as 0; discard if an earlier extension on this
-     * hash-equivalent diagonal already passed the hit's start */
-    if (S->E[h] > pos2 - len) return;
-    if (P->gfExtend == LZB_GFEX_NONE) {            /* :1163-1178 */
-        S->E[h] = pos2;
+    const int recover = P->recoverSeeds;
+    if (!recover) {
+        /* :1097-1113 -- inactive buckets read as 0; discard if an earlier extension on this
+         * hash-equivalent diagonal already passed the hit's start */
+        if (S->E[h] > pos2 - len) return;
+    } else {
+        /* process_for_recoverable_hit :1283-1373.  An untouched bucket reads as extent 0 here, and extent 0 lets every
+         * hit through both tests below, like the reference's explicit "inactive => fresh hit" (:1285-1290); a touched
+         * bucket never has extent 0.  A hit on a different actual diagonal is accepted as fresh (:1298-1336); one on the
+         * same diagonal that starts inside the recorded extent is dropped, moving the extent up to its end (:1341-1360). */
+        if (diag == S->A[h] && pos2 - len < S->E[h]) { if (pos2 > S->E[h]) S->E[h] = pos2; return; }
+        S->A[h] = diag;                                                /* fresh_hit :1373 */
+    }
+    if (P->gfExtend == LZB_GFEX_NONE) {            /* :1163-1178, :1417-1421 */
+        if (!recover || pos2 > S->E[h]) S->E[h] = pos2;
         emit_hsp(S, pos1, pos2, len, 0);
         return;
     }
@@ -324,8 +335,9 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
     const u8* v1 = S->t->v; const u8* v2 = S->q->v;
     const s32* sub = S->c->msub;
     s32 xDrop = P->xDrop;
-    /* left scan :2598-2632; stop = max(0, diagEnd + diag) in seq1 coordinates */
-    s64 blk = (s64)S->E[h] + diag;
+    /* left scan :2598-2632; stop = max(0, diagEnd + diag) in seq1 coordinates; the recoverable processor extends
+     * unblocked (oldDiagEnd = 0, :2612) */
+    s64 blk = (s64)(recover ? 0u : S->E[h]) + diag;
     u32 stop = blk > 0 ? (u32)blk : 0;
     u32 a = pos1, b = pos2, leftStart = pos1;
     s32 run = 0, leftScore = 0;
@@ -349,9 +361,9 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
     }
     u32 rightBlock = a;
     S->st.bpExtended += rightBlock - leftScanned;
-    /* :2785-2789 -- the bucket remembers where the right SCAN stopped */
+    /* :2785-2789 -- the bucket remembers where the right SCAN stopped (and on which diagonal) */
     u32 extent = (u32)((s64)rightBlock - diag);
-    if (extent > S->E[h]) S->E[h] = extent;
+    if (extent > S->E[h]) { S->E[h] = extent; if (recover) S->A[h] = diag; }
     s32 sim = leftScore + rightScore;
     u32 e1 = rightStop, e2 = (u32)((s64)e1 - diag), hl = rightStop - leftStart;
     (void)len;
@@ -397,6 +409,10 @@ int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed*
     int hb = P->hashBits ? P->hashBits : 16;
     S.hmask = (1u << hb) - 1;
     S.E = calloc((size_t)1 << hb, 4);
+    if (P->recoverSeeds) {
+        if (P->gfExtend != LZB_GFEX_XDROP && P->gfExtend != LZB_GFEX_NONE) return fail("recoverSeeds is built for x-drop extension and --nogfextend only");
+        S.A = calloc((size_t)1 << hb, 4);
+    }
     int L = sd->length;
     if (q->len >= (u32)L) {
         u64 w = 0; int run = 0;
@@ -420,7 +436,7 @@ int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed*
             }
         }
     }
-    free(S.E);
+    free(S.E); free(S.A);
     *segs = S.out; *nsegs = S.n;
     if (stats) *stats = S.st;
     return 0;

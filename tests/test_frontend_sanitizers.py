@@ -22,6 +22,8 @@ CASES = [
     ["pseudocat.fa", "pseudopig2.nib", "--format=gfa", "--nogapped"],
     ["pseudocat.fa", "pseudopig.fa", "--mismatch=2,25", "--chain", "--format=mapping"],
     ["aglobin.2bit/human", "shorties.fa", "--exact=20", "--anyornone", "--format=paf"],
+    ["aglobin.2bit/human", "aglobin.2bit/cow", "--recoverseeds", "--format=maf-"],
+    ["aglobin.2bit/human", "aglobin.2bit/cow", "--format=axt", "--segments=base_test.anchors.anchors"],
 ]
 
 
@@ -39,6 +41,7 @@ def sanitized(tmp_path_factory):
 @pytest.mark.parametrize("args", CASES)
 def test_front_end_is_clean_under_sanitizers(sanitized, args):
     argv = [os.path.join(GOLDEN, a) if not a.startswith("-") and "=" not in a.split("[")[0] else a for a in args]
+    argv = [a.replace("--segments=", "--segments=" + GOLDEN + "/") for a in argv]
     p = subprocess.run([sanitized] + argv, capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
     assert "AddressSanitizer" not in p.stderr and "runtime error" not in p.stderr, p.stderr[-2000:]
     assert p.returncode == 0, p.stderr[-500:]

@@ -384,3 +384,65 @@ def test_oracle_sam_header_without_alignments(tmp_path, fmt):
     b.write_text(">b\n" + "AAAAAAAAAAAAAAAACCCCCCCCCCCCCCCC" * 10 + "\n")
     for files in ([str(a), str(b)], [CAT, PIG]):
         same_output(run_cli(ORACLE_CLI, files + [fmt])[0], run_cli(REF_CLI, files + [fmt])[0])
+
+
+RECOVER_CASES = [
+    ["--recoverseeds"],
+    ["--recoverseeds", "--nogapped", "--format=general-"],
+    ["--recoverseeds", "--nogfextend", "--nogapped", "--format=general-"],
+    ["--recoverseeds", "--chain", "--format=maf-"],
+    ["--recoverhits", "--step=3", "--xdrop=600"],
+    ["--recoverseeds", "--nogfextend", "--format=general-", "--gappedthresh=20000", "--step=20"],
+    ["--recoverseeds", "--seed=match12", "--format=axt", "--strand=plus"],
+    ["--recoverseeds", "--nogapped", "--format=general-", "--seed=match10", "--step=5", "--hspthresh=2000"],
+    ["--recoverseeds", "--norecoverseeds", "--nogapped", "--format=segments"],
+]
+
+
+@pytest.mark.parametrize("opts", RECOVER_CASES, ids=lambda o: " ".join(o))
+def test_oracle_recoverseeds(synth, opts):
+    """process_for_recoverable_hit (seed_search.c:1221) + merge_segments (segment.c:1527): a hit on another diagonal of
+    the same hash bucket is extended instead of lost, overlapping HSPs are merged per diagonal."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    pairs = [[CAT, PIG]] + ([list(synth(300000))] if opts in RECOVER_CASES[:3] + RECOVER_CASES[5:6] else [])   # (the gapped runs at 300 kbp take 10 s each)
+    for files in pairs:
+        same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])
+
+
+def test_oracle_recoverseeds_changes_the_table(synth):
+    """the 2^16-bucket hash does lose hits on this pair, so the cases above are not vacuous"""
+    t, q = synth(300000)
+    base = run_cli(ORACLE_CLI, [t, q, "--nogapped", "--format=segments"])[0]
+    rec = run_cli(ORACLE_CLI, [t, q, "--nogapped", "--format=segments", "--recoverseeds"])[0]
+    assert base != rec
+
+
+def test_oracle_anchor_file_is_merged(synth, tmp_path):
+    """anchors read from a file are merged per diagonal before use (lastz.c:757, :3296): overlapping, contained and
+    adjoining segments in shuffled order"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    import random
+    t, q = synth(300000)
+    rows = [l for l in run_cli(REF_CLI, [t, q, "--nogapped", "--format=segments", "--hspthresh=2500"])[0].splitlines() if not l.startswith("#")]
+    rnd, out = random.Random(5), []
+    for l in rows[:400]:
+        out.append(l)
+        f = l.split()
+        a1, b1, a2, b2, sc = int(f[1]), int(f[2]), int(f[4]), int(f[5]), int(f[7])
+        if f[6] != "+":
+            continue
+        r = rnd.random()
+        if r < 0.3:
+            out.append(f"{f[0]}\t{a1 + 5}\t{b1 + 9}\t{f[3]}\t{a2 + 5}\t{b2 + 9}\t+\t{sc + 7}")
+        elif r < 0.5 and b1 - a1 > 20:
+            out.append(f"{f[0]}\t{a1 + 3}\t{b1 - 3}\t{f[3]}\t{a2 + 3}\t{b2 - 3}\t+\t{sc - 5}")
+        elif r < 0.6:
+            out.append(f"{f[0]}\t{b1 + 1}\t{b1 + 30}\t{f[3]}\t{b2 + 1}\t{b2 + 30}\t+\t{sc}")
+    rnd.shuffle(out)
+    seg = tmp_path / "anchors.seg"
+    seg.write_text("\n".join(out) + "\n")
+    for opts in (["--nogapped", "--format=general-"], ["--format=lav"]):
+        args = [t, q, f"--segments={seg}"] + opts
+        same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])

@@ -109,7 +109,7 @@ static void upload(const std::string& s, padded& o) {                  // lzb_up
 static int g_bad = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { fprintf(stderr, "  FAILED %s: ", #cond); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); g_bad++; } } while (0)
 
-struct mode { const char* name; int gfExtend, mismatches, K, plain, entropy, hashBits, useFirstKernel; };
+struct mode { const char* name; int gfExtend, mismatches, K, plain, entropy, hashBits, useFirstKernel, recover; };
 
 static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u32 step, const std::vector<mode>& modes, u32 partitionEvery = 0) {
     std::string t, q; const char* acgt = "ACGT";
@@ -156,7 +156,7 @@ static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u3
     for (const mode& M : modes) {
         // ---- oracle ----
         lzb_seed_params sp; memset(&sp, 0, sizeof sp);
-        sp.gfExtend = M.gfExtend; sp.gfMismatches = M.mismatches; sp.xDrop = 910; sp.hspThreshold = M.K; sp.entropy = M.entropy; sp.hashBits = M.hashBits; sp.plainHits = M.plain;
+        sp.gfExtend = M.gfExtend; sp.gfMismatches = M.mismatches; sp.xDrop = 910; sp.hspThreshold = M.K; sp.entropy = M.entropy; sp.hashBits = M.hashBits; sp.plainHits = M.plain; sp.recoverSeeds = M.recover;
         lzb_segment* want = NULL; uint64_t nwant = 0; lzb_seed_stats wst;
         if (lzb_seed_hit_search(oc, T, Q, &seed, ctb, &sp, &want, &nwant, &wst)) { CHECK(false, "oracle: %s", lzb_last_error()); continue; }
         // ---- the kernels, orchestrated like lzb_seed_hit_search (one chunk) ----
@@ -190,7 +190,10 @@ static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u3
         for (u32 i = 0; i < nh; i++) { keysB[i] = keys[ord[i]]; valsB[i] = vals[ord[i]]; }
         emu_launch(1, 256, [&]() { k_bucket_bounds(keysB.data(), nh, nbuckets, bstart.data()); });
         std::vector<u32> diagEnd(nbuckets, 0); std::vector<cand_rec> cand(nh + 16); const u32 candCap = (u32)cand.size();
-        if (M.gfExtend == LZB_GFEX_EXACT || M.gfExtend == LZB_GFEX_MISMATCH)
+        if (M.recover) {                                          /* --recoverseeds: k_extend_recover, the bucket's actual diagonal beside its extent */
+            std::vector<s32> diagActual(nbuckets, 0);
+            emu_launch(2, 128, [&]() { k_extend_recover(valsB.data(), bstart.data(), nbuckets, P1.cls.data(), P2.cls.data(), P1.asc.data(), P2.asc.data(), &g_sc, P, diagEnd.data(), diagActual.data(), cand.data(), candCap, &cnt); });
+        } else if (M.gfExtend == LZB_GFEX_EXACT || M.gfExtend == LZB_GFEX_MISMATCH)
             emu_launch(2, 128, [&]() { k_extend_alt(valsB.data(), bstart.data(), nbuckets, P1.asc.data(), P2.asc.data(), P, M.gfExtend == LZB_GFEX_EXACT ? 0 : M.mismatches, diagEnd.data(), cand.data(), candCap, &cnt); });
         else if (M.gfExtend == LZB_GFEX_XDROP && !M.plain && !M.useFirstKernel) {
             std::vector<u32> bcnt(nbuckets), bid(nbuckets); u32 next = 0;
@@ -258,6 +261,9 @@ int main() {
         { "x-drop (right/replay/left)",  LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 2 },
         { "--nogfextend (diag filter)",  LZB_GFEX_NONE, 0, 0, 0, 0, 16, 1 },
         { "--mismatch=2,40",             LZB_GFEX_MISMATCH, 2, 40, 0, 0, 16, 0 },
+        { "--recoverseeds, 2^6 buckets", LZB_GFEX_XDROP, 0, 2000, 0, 1, 6, 0, 1 },
+        { "--recoverseeds",              LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 0, 1 },
+        { "--recoverseeds --nogfextend, 2^8", LZB_GFEX_NONE, 0, 0, 0, 0, 8, 0, 1 },
     };
     one_pair(0, 20000, "1110100110010101111", 1, 1, a);
     std::vector<mode> b = {
@@ -272,6 +278,7 @@ int main() {
         { "every extension kept (K=top%)", LZB_GFEX_XDROP, 0, -600000000, 0, 0, 16, 0 },   // what an adaptive threshold asks of the library
         { "[multi] query, --exact=25",   LZB_GFEX_EXACT, 0, 25, 0, 0, 16, 0 },
         { "[multi] query, raw hits",     LZB_GFEX_NONE, 0, 0, 1, 0, 16, 1 },
+        { "[multi] query, --recoverseeds, 2^7", LZB_GFEX_XDROP, 0, 2200, 0, 1, 7, 0, 1 },
     };
     one_pair(2, 12000, "1110100110010101111", 1, 1, c, 311);
     printf("%d checks failed, %llu collectives emulated\n", g_bad, emu_collectives);
