@@ -122,8 +122,9 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
                     hitprocessor processor, void* processorInfo) {
     (void)hitSeed; (void)reportSearchLimit;
     if (pt != g_targetKey || !g_target) suicide("the lastz_b200 adapter was handed a position table it did not build");
-    if (processor != process_for_simple_hit && processor != process_for_plain_hit && processor != process_for_recoverable_hit)
-        suicide("the lastz_b200 adapter supports the simple, plain and recoverable hit processors only (no --twins)");
+    if (processor != process_for_simple_hit && processor != process_for_plain_hit && processor != process_for_recoverable_hit
+     && processor != process_for_twin_hit)
+        suicide("the lastz_b200 adapter was handed a hit processor it does not know");
     if (searchLimit != 0) suicide("the lastz_b200 adapter does not support --queryhsplimit / search limits");
 #ifdef densityFiltering
     if (maxDensity != 0) suicide("the lastz_b200 adapter does not support --maxdensity");
@@ -145,6 +146,11 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
     sp.start = (uint32_t)start; sp.end = (uint32_t)end;
     sp.plainHits = processor == process_for_plain_hit;
     sp.recoverSeeds = processor == process_for_recoverable_hit;   /* --recoverseeds; the reference merges the table itself (lastz.c:3296) */
+    if (processor == process_for_twin_hit) {                      /* --twins: hitproctwin = hitprocinfo + the two spans (seed_search.h:144-156) */
+        hitproctwin* tw = (hitproctwin*)processorInfo;
+        sp.twinMinSpan = (int32_t)tw->minSpan; sp.twinMaxSpan = (int32_t)tw->maxSpan;
+        sp.seedQueueSize = (int32_t)seedHitQueueSize;             /* diag_hash.h:108 */
+    }
     sp.gfExtend = sp.plainHits ? LZB_GFEX_NONE
                 : hp->gfExtend == gfexXDrop ? LZB_GFEX_XDROP
                 : hp->gfExtend == gfexExact ? LZB_GFEX_EXACT

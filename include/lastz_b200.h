@@ -118,6 +118,13 @@ typedef struct lzb_seed_params {
                                   lost, left extension is not blocked by the bucket, overlapping HSPs may be reported
                                   (the caller merges them: merge_segments segment.c:1527 = lzb_merge_segments of the host
                                   library).  With LZB_GFEX_XDROP or LZB_GFEX_NONE only. */
+    int32_t  twinMinSpan;      /* --twins=<minGap>..<maxGap>: process_for_twin_hit (seed_search.c:1814, the seed-hit-queue
+                                  version): a hit is extended only when an earlier hit on its diagonal lies minSpan..maxSpan
+                                  columns back (span = start of the earlier hit to the end of this one = 2*seedLength + gap,
+                                  lastz.c:9835); 0 = off.  With LZB_GFEX_XDROP or LZB_GFEX_NONE only; the caller merges the
+                                  table like for recoverSeeds. */
+    int32_t  twinMaxSpan;
+    int32_t  seedQueueSize;    /* --seedqueue=<entries>, default 256K (diag_hash.h:112); 0 = default */
 } lzb_seed_params;
 
 typedef struct lzb_seed_stats {

@@ -385,6 +385,127 @@ k_extend_recover(const u64* __restrict__ hits, const u32* __restrict__ bstart, u
     if (nBp) atomicAdd(&cnt->bpExtended, nBp);
 }
 
+/* ---- K3t: process_for_twin_hit (seed_search.c:1814-2046, the seed-hit-queue version; --twins=<min>..<max>) ----
+ * A hit is extended only when an earlier hit of its diagonal lies minSpan..maxSpan columns back.  The reference keeps
+ * the recent hits -- and a "block" entry at the extent of every extension -- in a queue chained per hash bucket
+ * (diag_hash.c:276-322) and walks a bucket's chain newest first until an entry is more than maxSpan columns back
+ * (:1904-1947).  Here one thread replays one bucket in discovery order and the chain is the bucket's own entry list:
+ * entries made in this chunk sit in ent[b0 ...] (at most one per hit), entries that can still matter to later chunks
+ * are carried per bucket in carry[h][carryCap] (carryCap = 2 * maxSpan + 16: along a homologous diagonal every column
+ * can leave an entry).  An entry stops mattering once every later hit sees it more than
+ * maxSpan columns back: it ends the walk, exactly like the end of the chain does (both fall through to "queue this
+ * hit", :1955-1958), so it and everything older are dropped.  The queue's CAPACITY is global state: the reference
+ * forgets an entry after seedHitQueueSize newer ones in ALL buckets (and warns "seed hit queue shortfall" when that loses
+ * a hit within maxSpan columns).  A forgotten entry ends the walk like the end of the chain, so it only matters when the
+ * walk would have gone THROUGH it: a hit entry within maxSpan columns (the host refuses inputs whose hit density makes
+ * that possible) or a block entry that is consulted long after it was made.  For the latter every block remembers the
+ * query position it was born at, and consulting one that MAY have been forgotten -- at least queueSize raw hits between
+ * its birth and now, by the per-block prefix sums of the hit counts -- raises cnt->overflow: the call then fails instead
+ * of returning a table that might differ from the reference's. */
+#define TWIN_CARRY_CAP(maxSpan_) (2u * (u32)(maxSpan_) + 16u)
+struct twin_ent { u32 pos2; s32 diag; u32 isBlock; u32 born; };
+
+__global__ void __launch_bounds__(128)
+k_extend_twin(const u64* __restrict__ hits, const u32* __restrict__ bstart, u32 nbuckets,
+              const u8* __restrict__ cls1, const u8* __restrict__ cls2,
+              const u8* __restrict__ asc1, const u8* __restrict__ asc2,
+              const lzb_scoring_dev* __restrict__ sc, sp_dev P, u32 minSpan, u32 maxSpan,
+              const unsigned long long* __restrict__ blkPrefix, u32 nblk, u32 queueSize,
+              u32* __restrict__ diagEnd, twin_ent* __restrict__ ent, twin_ent* __restrict__ carry, u32 carryCap, u32* __restrict__ ncarry,
+              cand_rec* __restrict__ cand, u32 candCap, search_counters* cnt) {
+    const u32 L = (u32)P.L;
+    const s32 xDrop = P.xDrop;
+    unsigned long long nExt = 0, nBp = 0;
+    for (u32 h = blockIdx.x * blockDim.x + threadIdx.x; h < nbuckets; h += gridDim.x * blockDim.x) {
+        const u32 b0 = bstart[h], b1 = bstart[h + 1];
+        if (b0 == b1) continue;
+        u32 E = diagEnd[h];
+        twin_ent* const old = carry + (size_t)h * carryCap; const u32 nold = ncarry[h];
+        twin_ent* const mine = ent + b0; u32 nnew = 0;
+        u32 lastPos2 = 0;
+        for (u32 idx = b0; idx < b1; idx++) {
+            const u64 rec = hits[idx];
+            const u32 pos1 = (u32)rec, pos2 = (u32)(rec >> 32);
+            const s32 diag = (s32)(pos1 - pos2);
+            lastPos2 = pos2;
+            /* walk the chain, newest entry first (:1904-1947) */
+            int verdict = 0;                                   /* 0 queue the hit, 1 blocked, 2 twin */
+            u32 span = 0;
+            for (u32 k = nnew + nold; k-- > 0;) {
+                const twin_ent q = k >= nold ? mine[k - nold] : old[k];
+                span = pos2 - (q.pos2 - L);
+                if (span > maxSpan) break;
+                if (q.isBlock) {                                /* may the reference have forgotten this block by now? */
+                    const u32 bl = (q.born - P.qstart) / POS_PER_BLOCK, bh = (pos2 - P.qstart) / POS_PER_BLOCK;
+                    const unsigned long long lo = blkPrefix[bl > 0 ? bl - 1 : 0], hi = blkPrefix[bh + 2 < nblk ? bh + 2 : nblk];
+                    if (hi - lo + 2 >= queueSize) atomicAdd(&cnt->overflow, 1ull);
+                }
+                if (q.diag != diag) continue;
+                if (q.isBlock) { if (pos2 - L <= q.pos2) verdict = 1; break; }
+                if (span < minSpan) continue;
+                verdict = 2; break;
+            }
+            if (verdict == 1) continue;
+            if (verdict == 0) { twin_ent e = { pos2, diag, 0u, pos2 }; mine[nnew++] = e; continue; }
+            if (P.gfExtend != LZB_GFEX_XDROP) {                 /* :2021-2026: the twin itself, span columns long */
+                E = pos2;
+                twin_ent e = { pos2, diag, 1u, pos2 }; mine[nnew++] = e;
+                const u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+                if (slot < candCap) { cand_rec r = { pos1, pos2, pos1 - span, pos2 - span, span, 0, 0, 0, 0, 0 }; cand[slot] = r; }
+                continue;
+            }
+            /* xdrop_extend_seed_hit :2528-2959 from the hit's right end; the left scan stops at the bucket's extent */
+            const s64 blk = (s64)E + diag;
+            const u32 stop = blk > 0 ? (u32)blk : 0u;
+            u32 a = pos1, b = pos2, leftLen = 0, leftCols = 0; s32 run = 0, leftScore = 0;
+            while (a > stop && run >= leftScore - xDrop) {
+                --a; --b;
+                run += sc->msubC[(u32)cls1[a] * LZB_MAX_CLASSES + cls2[b]];
+                leftCols++;
+                if (run > leftScore) { leftScore = run; leftLen = leftCols; }
+            }
+            const s64 lim = (s64)P.len2 + diag;
+            const u32 rstop = ((s64)P.len1 <= lim) ? P.len1 : (u32)lim;
+            u32 rightLen = 0, rightCols = 0; s32 rightScore = 0; run = 0; a = pos1; b = pos2;
+            while (a < rstop && run >= rightScore - xDrop) {
+                run += sc->msubC[(u32)cls1[a] * LZB_MAX_CLASSES + cls2[b]];
+                a++; b++; rightCols++;
+                if (run > rightScore) { rightScore = run; rightLen = rightCols; }
+            }
+            nExt++; nBp += rightCols + leftCols;
+            const u32 extent = (u32)((s64)a - diag);
+            if (extent > E) { E = extent; twin_ent e = { extent, diag, 1u, pos2 }; mine[nnew++] = e; }     /* :1996-2002 */
+            const s32 sim = leftScore + rightScore;
+            if (sim < P.K) continue;
+            cand_rec r;
+            r.hit1 = pos1; r.hit2 = pos2; r.pos1 = pos1 - leftLen; r.pos2 = pos2 - leftLen;
+            r.length = leftLen + rightLen; r.score = sim; r.cA = r.cC = r.cG = r.cT = 0;
+            if (P.entropy && sim <= 3 * P.K) {
+                for (u32 i = 0; i < r.length; i++) {
+                    const u8 x = asc1[r.pos1 + i];
+                    if (x == asc2[r.pos2 + i]) { r.cA += x == 'A'; r.cC += x == 'C'; r.cG += x == 'G'; r.cT += x == 'T'; }
+                }
+            }
+            const u32 slot = (u32)atomicAdd(&cnt->ncand, 1ull);
+            if (slot < candCap) cand[slot] = r;
+        }
+        diagEnd[h] = E;
+        /* what later chunks may still need: the newest entries down to the first one that every later hit (pos2 >= the last
+         * one seen here) finds more than maxSpan columns back */
+        u32 keep = 0;
+        for (u32 k = nnew + nold; k-- > 0; keep++) {
+            const twin_ent q = k >= nold ? mine[k - nold] : old[k];
+            if ((s64)lastPos2 - ((s64)q.pos2 - (s64)L) > (s64)maxSpan) break;
+        }
+        if (keep > carryCap) { atomicAdd(&cnt->overflow, 1ull); keep = carryCap; }
+        /* the last `keep` entries of (old, mine) move to the front of old: every read is at or behind the write, in order */
+        for (u32 j = 0; j < keep; j++) { const u32 k = nnew + nold - keep + j; const twin_ent q = k >= nold ? mine[k - nold] : old[k]; old[j] = q; }
+        ncarry[h] = keep;
+    }
+    if (nExt) atomicAdd(&cnt->extensions, nExt);
+    if (nBp) atomicAdd(&cnt->bpExtended, nBp);
+}
+
 /* ---- K3c: the default extension kernel (x-drop, <= 16 byte classes): xdrop_warp.cuh ----
  * Buckets are handed out largest first from a global counter (longest-processing-time order): the
  * few buckets that hold a homologous diagonal take far longer than the rest, and with a static

@@ -89,7 +89,11 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     if (seed->length < 2) return lzb_fail("seed length must be at least two (yours is %d)", seed->length);
     if (prm->gfExtend == LZB_GFEX_MISMATCH && (prm->gfMismatches < 1 || prm->gfMismatches > LZB_GFEX_MISMATCH_MAX))
         return lzb_fail("%d is out of range for N-mismatch (valid range is 1..%d)", prm->gfMismatches, LZB_GFEX_MISMATCH_MAX);
-    const bool recover = prm->recoverSeeds && !prm->plainHits;      /* process_for_recoverable_hit; the plain processor wins (lastz.c:2789-2792) */
+    const bool twin = prm->twinMinSpan > 0;                          /* process_for_twin_hit goes before every other processor (lastz.c:2787) */
+    if (twin && prm->gfExtend != LZB_GFEX_XDROP && prm->gfExtend != LZB_GFEX_NONE) return lzb_fail("twins are built for x-drop extension and --nogfextend only");
+    if (twin && prm->twinMaxSpan < prm->twinMinSpan) return lzb_fail("maxGap for twins can't be less than min gap");
+    const u32 twinQueue = prm->seedQueueSize > 0 ? (u32)prm->seedQueueSize : 256u * 1024u;          /* defaultSeedHitQueueSize diag_hash.h:112 */
+    const bool recover = prm->recoverSeeds && !prm->plainHits && !twin;   /* process_for_recoverable_hit; the plain processor wins (lastz.c:2789-2792) */
     if (recover && prm->gfExtend != LZB_GFEX_XDROP && prm->gfExtend != LZB_GFEX_NONE)
         return lzb_fail("recoverSeeds is built for x-drop extension and --nogfextend only");
     if (seed->weight != t->wordBits || seed->length != t->seedLength)
@@ -116,7 +120,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     sp_dev P; memset(&P, 0, sizeof P);
     P.qstart = qstart; P.qend = qend; P.len1 = t->len; P.len2 = q->len; P.L = seed->length; P.V = (int)flips.size();
     P.hashBits = hashBits; P.selfCompare = prm->selfCompare; P.sameStrand = prm->sameStrand;
-    P.xDrop = prm->xDrop; P.K = prm->hspThreshold; P.gfExtend = prm->gfExtend; P.plain = prm->plainHits; P.entropy = prm->entropy;
+    P.xDrop = prm->xDrop; P.K = prm->hspThreshold; P.gfExtend = prm->gfExtend; P.plain = prm->plainHits && !twin; P.entropy = prm->entropy;
     seed_dev sd; seed_to_dev(&sd, seed);
     ctb_dev2 cd; memcpy(cd.v, ctb, 256);
 
@@ -156,6 +160,28 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     WMARK();                                            /* [0] small allocations + words + hit counts + sync */
     u64 totalHits = 0, maxBlk = 0;
     for (u32 b = 0; b < nblk; b++) { totalHits += blkcnt[b]; if (blkcnt[b] > maxBlk) maxBlk = blkcnt[b]; }
+    /* twins: the reference's seed hit queue holds the last twinQueue entries of ALL buckets.  The bucket replay is exact
+     * only while no hit within maxSpan columns can have been pushed out of it (the reference prints "seed hit queue
+     * shortfall" when that happens): refuse inputs whose hit density over any window that wide reaches the queue size.
+     * Blocks consulted long after they were made are checked in the kernel against the same prefix sums. */
+    unsigned long long* d_blkprefix = NULL; twin_ent* d_ent = NULL; twin_ent* d_carry = NULL; u32* d_ncarry = NULL;
+    if (twin) {
+        std::vector<unsigned long long> prefix(nblk + 1, 0);
+        for (u32 b = 0; b < nblk; b++) prefix[b + 1] = prefix[b] + blkcnt[b];
+        const u32 wblocks = ((u32)prm->twinMaxSpan + (u32)seed->length + POS_PER_BLOCK - 1) / POS_PER_BLOCK + 1;
+        for (u32 b = 0; b < nblk; b++) {
+            const u32 e = std::min<u64>((u64)b + wblocks, nblk);
+            if (prefix[e] - prefix[b] + 2 >= twinQueue)
+                return lzb_fail("seed hit queue shortfall: %llu seed hits within %u query positions reach the queue size %u (--seedqueue); "
+                                "the twin processor's result would depend on what the queue has forgotten", prefix[e] - prefix[b], wblocks * POS_PER_BLOCK, twinQueue);
+        }
+        SCRATCH(22, d_blkprefix, ((size_t)nblk + 1) * 8);
+        CUDA_TRY(cudaMemcpyAsync(d_blkprefix, prefix.data(), ((size_t)nblk + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));                          /* (prefix is a local) */
+        SCRATCH(23, d_carry, (size_t)nbuckets * TWIN_CARRY_CAP(prm->twinMaxSpan) * sizeof(twin_ent));
+        SCRATCH(13, d_ncarry, (size_t)nbuckets * 4);
+        CUDA_TRY(cudaMemsetAsync(d_ncarry, 0, (size_t)nbuckets * 4, st));
+    }
 
     const char* capEnv = getenv("LZB_HIT_CAP");
     u64 hitCap = capEnv ? strtoull(capEnv, 0, 10) : (1ull << 27);
@@ -177,10 +203,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     /* the three-kernel extension (xdrop_split.cuh) measured SLOWER than the fused kernel (0.70 s vs 0.62 s
      * at 50 Mbp x 50 Mbp: the extra passes over the hit records cost more than the lockstep idling they
      * remove), so it is opt-in: LZB_SPLIT_EXTEND=1.  Kept because it bounds the work on long repeats. */
-    const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && !recover && c->sc.numClasses <= 16 &&
+    const bool splitExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && !recover && !twin && c->sc.numClasses <= 16 &&
                              getenv("LZB_SPLIT_EXTEND") && atoi(getenv("LZB_SPLIT_EXTEND"));
     /* the warp-cooperative kernel (xdrop_warp.cuh) is the default x-drop path; LZB_EXTEND_V1=1 keeps the first one */
-    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && !recover && c->sc.numClasses <= XD_LUT_MAX_CLASSES && !splitExtend &&
+    const bool coopExtend = prm->gfExtend == LZB_GFEX_XDROP && !prm->plainHits && !recover && !twin && c->sc.numClasses <= XD_LUT_MAX_CLASSES && !splitExtend &&
                             !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
     u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
     /* persistent CTAs of k_extend2 per SM: four fill the register file; a caller that runs this stage beside another
@@ -204,6 +230,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     if (tmpScan > tmpBytes) tmpBytes = tmpScan;
     if (tmpOrder > tmpBytes) tmpBytes = tmpOrder;
     SCRATCH(21, d_tmp, tmpBytes);
+    if (twin) SCRATCH(18, d_ent, hitCap * sizeof(twin_ent));
 
     /* chunk loop */
     WMARK();                                            /* [1] hit/slot/candidate buffers allocated */
@@ -223,7 +250,11 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             tb = tmpBytes;
             TIMED(5, cub::DeviceRadixSort::SortPairs(d_tmp, tb, keysA, keysB, valsA, valsB, nh, 0, hashBits, st));
             TIMED(6, (k_bucket_bounds<<<(nbuckets + 256) / 256, 256, 0, st>>>(keysB, nh, nbuckets, d_bstart)));
-            if (recover) {
+            if (twin) {
+                TIMED(7, (k_extend_twin<<<(nbuckets + 127) / 128, 128, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq, c->d_sc, P,
+                                                                                  (u32)prm->twinMinSpan, (u32)prm->twinMaxSpan, d_blkprefix, nblk, twinQueue,
+                                                                                  d_E, d_ent, d_carry, TWIN_CARRY_CAP(prm->twinMaxSpan), d_ncarry, d_cand, candCap, d_cnt)));
+            } else if (recover) {
                 TIMED(7, (k_extend_recover<<<(nbuckets + 127) / 128, 128, 0, st>>>(valsB, d_bstart, nbuckets, t->d_cls, q->d_cls, t->d_seq, q->d_seq,
                                                                                      c->d_sc, P, d_E, d_A, d_cand, candCap, d_cnt)));
             } else if (splitExtend) {
@@ -260,6 +291,11 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     CUDA_TRY(cudaMemcpyAsync(&hc, d_cnt, sizeof hc, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     WMARK();                                            /* [3] device work finished */
+    if (twin && hc.overflow) {
+        lzb_fail("the twin processor's seed hit queue cannot be replayed exactly on this input (%llu times: more than %u live entries in one hash "
+                 "bucket, or an extension's block consulted after %u or more newer seed hits); try a larger --seedqueue", hc.overflow, TWIN_CARRY_CAP(prm->twinMaxSpan), twinQueue);
+        goto cleanup_fail;
+    }
     if (hc.ncand > candCap) {
         lzb_fail("%llu HSP candidates exceed the %u-entry result buffer; raise the threshold (--hspthresh)", hc.ncand, candCap);
         goto cleanup_fail;

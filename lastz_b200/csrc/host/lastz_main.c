@@ -20,6 +20,7 @@ typedef struct {
     int whichStrand;               /* 0 plus, 1 both, -1 minus */
     int gfExtend, gfMismatches, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
     int recoverSeeds;              /* --recoverseeds: process_for_recoverable_hit + merge_segments (lastz.c:5712-5720, :2791, :2811) */
+    int twins, twinMinGap, twinMaxGap, seedQueue;    /* --twins=<min>..<max>, --seedqueue= (lastz.c:5671-5710, :9826-9850) */
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
     int adaptive; double adaptFraction; uint32_t adaptBases;   /* K=top<N>% ('P') or K=top<bases> ('C'), string_to_score_thresh dna_utilities.c:2248 */
     uint32_t tracebackBytes;
@@ -130,6 +131,15 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--word=")) ;                         /* lastz.c:5665: max index bits; only a table-layout matter (overweight
                                                                     seeds are "resolved", seed_search.c:878) -- this index holds 28 bits anyway */
         else if (!strcmp(a, "--anyornone") || !strcmp(a, "--stopafterone")) o->anyOrNone = 1;
+        else if (!strcmp(a, "--notwins")) o->twins = 0;
+        else if (starts(a, "--twins=")) {                        /* <min>..<max>, the historical <min>:<max>, or <max> alone */
+            const char* sep = strstr(v, ".."); int w = 2;
+            if (!sep) { sep = strchr(v, ':'); w = 1; }
+            o->twins = 1;
+            if (sep) { o->twinMinGap = atoi(v); o->twinMaxGap = atoi(sep + w); }      /* (atoi stops at the separator) */
+            else { o->twinMinGap = 0; o->twinMaxGap = atoi(v); }
+        }
+        else if (starts(a, "--seedqueue=")) o->seedQueue = atoi(v);
         else if (!strcmp(a, "--recoverseeds") || !strcmp(a, "--recoverhits")) o->recoverSeeds = 1;
         else if (!strcmp(a, "--norecoverseeds") || !strcmp(a, "--norecoverhits")) o->recoverSeeds = 0;
         else if (!strcmp(a, "--justhits") || !strcmp(a, "--hitsonly")) { o->gfExtend = LZB_GFEX_NONE; o->gapped = 0; }   /* lastz.c:5875 */
@@ -417,6 +427,14 @@ int main(int argc, char** argv) {
     }
     if (o.wordCountLimit > 0 && lzb_target_limit(T, o.wordCountLimit)) lzb_die("%s", lzb_last_error());
 
+    if (o.twins) {                  /* lastz.c:9826-9836 */
+        if (o.twinMinGap <= -seed.length) lzb_die("minGap for twins (%d) must be greater than negative of seed length (%d)", o.twinMinGap, -seed.length);
+        if (o.twinMaxGap < o.twinMinGap) lzb_die("maxGap for twins (%d) can't be less than min gap (%d)", o.twinMaxGap, o.twinMinGap);
+        if (o.gfExtend == LZB_GFEX_EXACT || o.gfExtend == LZB_GFEX_MISMATCH) lzb_die("lastz_b200 implements --twins with x-drop extension or --nogfextend only");
+        if (o.selfCompare) lzb_die("lastz_b200 does not implement --twins together with --self");
+        if (o.adaptive) lzb_die("lastz_b200 does not implement --twins together with an adaptive --hspthresh");
+        if (o.seedQueue < 0) lzb_die("--seedqueue can't be negative");
+    }
     if (o.recoverSeeds) {           /* built: x-drop extension or none, a fixed threshold, no --self mirroring of the merged table */
         if (o.gfExtend == LZB_GFEX_EXACT || o.gfExtend == LZB_GFEX_MISMATCH) lzb_die("lastz_b200 implements --recoverseeds with x-drop extension or --nogfextend only");
         if (o.selfCompare) lzb_die("lastz_b200 does not implement --recoverseeds together with --self");
@@ -519,6 +537,10 @@ int main(int argc, char** argv) {
                 sp.strandId = query.revCompFlags;
                 sp.plainHits = (o.gfExtend == LZB_GFEX_NONE && !o.gapped);
                 sp.recoverSeeds = o.recoverSeeds && !sp.plainHits;        /* the plain processor wins (lastz.c:2789-2792) */
+                if (o.twins) {                                            /* the twin processor goes before the others (lastz.c:2787, :9835) */
+                    sp.twinMinSpan = 2 * seed.length + o.twinMinGap; sp.twinMaxSpan = 2 * seed.length + o.twinMaxGap;
+                    sp.seedQueueSize = o.seedQueue; sp.plainHits = 0; sp.recoverSeeds = 0;
+                }
                 if (lzb_seed_hit_search(ctx, T, Q, &seed, lzb_upper_nuc_to_bits, &sp, &segs, &nsegs, &sst))
                     lzb_die("%s", lzb_last_error());
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
@@ -562,7 +584,7 @@ int main(int argc, char** argv) {
             }
             /* anchors from a file, and HSPs of a processor that may report overlapping ones, are merged per diagonal before
              * anything else looks at them (lastz.c:757, :2811, :3296; merge_segments segment.c:1527) */
-            if (o.segmentsFile || (o.recoverSeeds && !(o.gfExtend == LZB_GFEX_NONE && !o.gapped))) lzb_merge_segments(segs, &nsegs);
+            if (o.segmentsFile || o.twins || (o.recoverSeeds && !(o.gfExtend == LZB_GFEX_NONE && !o.gapped))) lzb_merge_segments(segs, &nsegs);
             if (!o.adaptive && o.selfCompare && !o.gapped && !o.segmentsFile && nsegs) {
                 lzb_segment* both = malloc(2 * nsegs * sizeof *both); uint64_t m = 0;
                 int same = query.revCompFlags == target.revCompFlags;

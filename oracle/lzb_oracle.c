@@ -174,6 +174,9 @@ typedef struct {
     const lzb_seed* sd; const lzb_seed_params* p;
     u32* E;  u32 hmask;                 /* diagEnd[], diag_hash.h:68 */
     s32* A;                             /* diagActual[], diag_hash.h:70 (recoverable processor only) */
+    /* the seed hit queue of the twin processor (diag_hash.h:104-160, diag_hash.c:276-322): a ring of the last Qsize
+     * enqueued hits/blocks, chained per hash bucket through prevHit; entry numbers start at Qsize */
+    struct twq { u32 pos2; s32 diag; u32 prev; int isBlock; }* Q; u32 Qsize, Qnum; u32* Qlast;
     lzb_segment* out; u64 n, cap;
     lzb_seed_stats st;
 } search;
@@ -300,6 +303,50 @@ not_a_match:
     if (extent > S->E[h]) S->E[h] = extent;
 }
 
+/* _enqueue_seed_hit diag_hash.c:276-322 */
+static void twin_enqueue(search* S, u32 pos1, u32 pos2, int isBlock) {
+    s32 diag = (s32)(pos1 - pos2);
+    u32 h = (u32)diag & S->hmask;
+    S->Qnum++;
+    struct twq* q = &S->Q[S->Qnum % S->Qsize];
+    q->prev = (S->Qlast[h] <= S->Qnum - S->Qsize) ? 0 : S->Qlast[h];       /* a stale predecessor is no longer in the queue */
+    S->Qlast[h] = S->Qnum;
+    q->isBlock = isBlock; q->pos2 = pos2; q->diag = diag;
+}
+
+static int xdrop_from_hit(search* S, u32 pos1, u32 pos2, u32 h, int recover);
+
+/* process_for_twin_hit seed_search.c:1814-2046 (seed hit queue version), x-drop or no extension */
+static void twin_hit(search* S, u32 pos1, u32 pos2) {
+    const lzb_seed_params* P = S->p;
+    const u32 len = (u32)S->sd->length, minSpan = (u32)P->twinMinSpan, maxSpan = (u32)P->twinMaxSpan;
+    s32 diag = (s32)(pos1 - pos2);
+    u32 h = (u32)diag & S->hmask;
+    /* :1873-1892: the first hit of a bucket is only queued.  (An untouched bucket has an empty chain, so the scan below
+     * finds nothing and queues the hit just the same.) */
+    for (u32 num = S->Qlast[h]; num > S->Qnum - S->Qsize; ) {                  /* :1904-1947 */
+        const struct twq* q = &S->Q[num % S->Qsize];
+        num = q->prev;
+        const u32 span = pos2 - (q->pos2 - len);
+        if (span > maxSpan) break;
+        if (q->diag != diag) continue;
+        if (q->isBlock) { if (pos2 - len <= q->pos2) return; break; }          /* inside / right of an earlier extension */
+        if (span < minSpan) continue;
+        /* twin_hit :1969-2026 */
+        if (P->gfExtend == LZB_GFEX_NONE) {
+            S->E[h] = pos2;
+            twin_enqueue(S, pos1, pos2, 1);
+            emit_hsp(S, pos1, pos2, span, 0);
+            return;
+        }
+        const u32 old = S->E[h];
+        xdrop_from_hit(S, pos1, pos2, h, 0);
+        if (S->E[h] != old) { const u32 extent = S->E[h]; twin_enqueue(S, (u32)((s64)diag + extent), extent, 1); }
+        return;
+    }
+    twin_enqueue(S, pos1, pos2, 0);                                            /* no twin yet :1957 */
+}
+
 /*
  * One seed hit: process_for_simple_hit seed_search.c:1056-1192 followed by
  * xdrop_extend_seed_hit :2528-2959.  pos1/pos2 = one past the hit end.
@@ -308,6 +355,7 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
     const lzb_seed_params* P = S->p;
     u32 len = (u32)S->sd->length;
     S->st.rawSeedHits++;
+    if (P->twinMinSpan > 0) { twin_hit(S, pos1, pos2); return; }     /* the twin processor goes before every other (lastz.c:2787-2805) */
     if (P->plainHits) { emit_hsp(S, pos1, pos2, len, 0); return; }   /* :995-1030 */
     s32 diag = (s32)(pos1 - pos2);
     u32 h = (u32)diag & S->hmask;
@@ -331,6 +379,14 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
     }
     if (P->gfExtend == LZB_GFEX_EXACT) { exact_hit(S, pos1, pos2, h); return; }          /* :1146-1151 */
     if (P->gfExtend == LZB_GFEX_MISMATCH) { mismatch_hit(S, pos1, pos2, h); return; }    /* :1158-1164 */
+    xdrop_from_hit(S, pos1, pos2, h, recover);
+}
+
+/* xdrop_extend_seed_hit seed_search.c:2528-2959 for the hit that ends at (pos1, pos2); returns 1 if an HSP came out */
+static int xdrop_from_hit(search* S, u32 pos1, u32 pos2, u32 h, int recover) {
+    const lzb_seed_params* P = S->p;
+    u32 len = (u32)S->sd->length;
+    s32 diag = (s32)(pos1 - pos2);
     S->st.extensions++;
     const u8* v1 = S->t->v; const u8* v2 = S->q->v;
     const s32* sub = S->c->msub;
@@ -372,8 +428,9 @@ static void one_hit(search* S, u32 pos1, u32 pos2) {
         double q = hsp_entropy(v1 + e1 - hl, v2 + e2 - hl, (int)hl);
         sim = (s32)((double)sim * q);
     }
-    if (sim < P->hspThreshold) return;              /* :2907 */
+    if (sim < P->hspThreshold) return 0;            /* :2907 */
     emit_hsp(S, e1, e2, hl, sim);
+    return 1;
 }
 
 /* find_table_matches seed_search.c:810-875 (+ seed_hit_below_diagonal :2182-2237, unpartitioned) */
@@ -413,6 +470,14 @@ int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed*
         if (P->gfExtend != LZB_GFEX_XDROP && P->gfExtend != LZB_GFEX_NONE) return fail("recoverSeeds is built for x-drop extension and --nogfextend only");
         S.A = calloc((size_t)1 << hb, 4);
     }
+    if (P->twinMinSpan > 0) {
+        if (P->gfExtend != LZB_GFEX_XDROP && P->gfExtend != LZB_GFEX_NONE) return fail("twins are built for x-drop extension and --nogfextend only");
+        if (P->twinMaxSpan < P->twinMinSpan) return fail("maxGap for twins can't be less than min gap");
+        S.Qsize = P->seedQueueSize > 0 ? (u32)P->seedQueueSize : 256u * 1024u;       /* defaultSeedHitQueueSize diag_hash.h:112 */
+        S.Qnum = S.Qsize;                                                             /* diag_hash.c:168 */
+        S.Q = calloc(S.Qsize, sizeof *S.Q);
+        S.Qlast = calloc((size_t)1 << hb, 4);
+    }
     int L = sd->length;
     if (q->len >= (u32)L) {
         u64 w = 0; int run = 0;
@@ -436,7 +501,7 @@ int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed*
             }
         }
     }
-    free(S.E); free(S.A);
+    free(S.E); free(S.A); free(S.Q); free(S.Qlast);
     *segs = S.out; *nsegs = S.n;
     if (stats) *stats = S.st;
     return 0;

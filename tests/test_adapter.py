@@ -58,19 +58,20 @@ def test_adapter_anchors_file_to_maf():
 
 
 def test_adapter_recoverable_processor(synth):
-    """--recoverseeds: the reference picks process_for_recoverable_hit, the adapter passes that on as recoverSeeds, and the
-    reference's own merge_segments runs on what comes back"""
+    """--recoverseeds / --twins: the reference picks process_for_recoverable_hit / process_for_twin_hit, the adapter passes
+    that on as recoverSeeds / the twin spans, and the reference's own merge_segments runs on what comes back"""
     _build()
     if not os.path.exists(REF_CLI):
         pytest.skip("oracle/_ref not built")
     t, q = synth(300000)
-    for args in ([CAT, PIG, "--recoverseeds"], [t, q, "--recoverseeds", "--nogapped", "--format=general-"]):
+    for args in ([CAT, PIG, "--recoverseeds"], [t, q, "--recoverseeds", "--nogapped", "--format=general-"],
+                 [t, q, "--twins=0..50", "--nogapped", "--format=general-"], [CAT, PIG, "--twins=-5..30"]):
         assert _norm(run_cli(ADAPTER_ORACLE, args)[0]) == _norm(run_cli(REF_CLI, args)[0])
 
 
 def test_adapter_refuses_what_the_library_lacks():
     _build()
-    for opts in (["--twins=10..20"], ["--hspthresh=top10%"]):
+    for opts in (["--hspthresh=top10%"], ["--queryhsplimit=5"]):
         p = subprocess.run([ADAPTER_ORACLE, CAT, PIG] + opts, capture_output=True, text=True)
         assert p.returncode != 0 and "lastz_b200 adapter" in p.stderr, (opts, p.stderr[-300:])
 

@@ -1,4 +1,4 @@
-"""--recoverseeds on the GPU: k_extend_recover (process_for_recoverable_hit, seed_search.c:1221) against the oracle
+"""--recoverseeds and --twins on the GPU: k_extend_recover (process_for_recoverable_hit, seed_search.c:1221) against the oracle
 through the C-ABI, and the product command line (with merge_segments) against the unmodified reference.
 
 Written after the round's GPU minutes were spent: the kernel's own source runs against the oracle on the block emulator
@@ -63,3 +63,52 @@ def test_cli_recoverseeds(synth, opts):
     ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
     for files in ([CAT, PIG], list(synth(300000))):
         same_output(run_cli(PRODUCT_CLI, files + opts)[0], run_cli(ref, files + opts)[0])
+
+
+@pytest.mark.parametrize("cfg", [dict(twin_spans=(38, 88)), dict(twin_spans=(33, 68), hash_bits=8), dict(twin_spans=(48, 238), gf_extend=0, hash_bits=10)])
+def test_twin_processor_matches_oracle(cfg, synth, monkeypatch):
+    """k_extend_twin (process_for_twin_hit): the bucket replay with queue entries carried across chunks (second run: chunks
+    of about 20000 hits) against the oracle's global queue"""
+    ss = default_scoring()
+    prod, orc = Engine.product(0), Engine.oracle()
+    prod.set_scoring(ss)
+    orc.set_scoring(ss)
+    seed = parse_seed()
+    t, q = synth(300000)
+    tseq, qseq = read_fasta(t)[0][1], read_fasta(q)[0][1]
+    tp, to = prod.build_seed_position_table(tseq, seed), orc.build_seed_position_table(tseq, seed)
+    for strand, s in ((0, qseq), (3, revcomp(qseq))):
+        qp, qo = prod.load_query(s), orc.load_query(s)
+        b, sb = orc.seed_hit_search(to, qo, seed, strand_id=strand, **cfg)
+        for cap in (None, "20000"):
+            if cap:
+                monkeypatch.setenv("LZB_HIT_CAP", cap)
+            else:
+                monkeypatch.delenv("LZB_HIT_CAP", raising=False)
+            a, sa = prod.seed_hit_search(tp, qp, seed, strand_id=strand, **cfg)
+            assert len(a) == len(b)
+            for f in FIELDS:
+                assert np.array_equal(a[f], b[f]), f
+            assert sa.rawSeedHits == sb.rawSeedHits
+            if cfg.get("gf_extend", 1):
+                assert (sa.extensions, sa.bpExtended) == (sb.extensions, sb.bpExtended)
+        prod.free_query(qp)
+        orc.free_query(qo)
+    prod.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("opts", [["--twins=0..50", "--nogapped", "--format=general-"], ["--twins=-5..30"],
+                                  ["--twins=10..100", "--nogfextend", "--nogapped", "--format=general-"]], ids=lambda o: " ".join(o))
+def test_cli_twins(synth, opts):
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    for files in ([CAT, PIG], list(synth(300000))):
+        same_output(run_cli(PRODUCT_CLI, files + opts)[0], run_cli(ref, files + opts)[0])
+
+
+def test_twins_refuse_a_queue_that_would_forget(synth):
+    """a queue smaller than the hit density over the span window: the reference's result then depends on what its queue
+    has forgotten, and the library says so instead of returning something else"""
+    t, q = synth(300000)
+    with pytest.raises(RuntimeError, match="seed hit queue"):
+        run_cli(PRODUCT_CLI, [t, q, "--twins=0..200", "--seed=match8", "--step=2", "--nogapped", "--seedqueue=2000"])

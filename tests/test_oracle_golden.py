@@ -446,3 +446,26 @@ def test_oracle_anchor_file_is_merged(synth, tmp_path):
     for opts in (["--nogapped", "--format=general-"], ["--format=lav"]):
         args = [t, q, f"--segments={seg}"] + opts
         same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
+TWIN_CASES = [
+    ["--twins=0..50", "--nogapped", "--format=general-"],
+    ["--twins=-5..30"],
+    ["--twins=10..100", "--nogfextend", "--nogapped", "--format=general-"],
+    ["--twins=60", "--seed=match9", "--nogapped", "--format=segments", "--hspthresh=2500"],
+    ["--twins=0:40", "--chain", "--format=maf-"],
+    ["--twins=0..200", "--seed=match8", "--step=2", "--nogapped", "--format=general-", "--seedqueue=2000"],   # a queue small enough to forget live entries
+    ["--twins=0..50", "--notwins", "--nogapped", "--format=segments"],
+]
+
+
+@pytest.mark.parametrize("opts", TWIN_CASES, ids=lambda o: " ".join(o))
+def test_oracle_twins(synth, opts):
+    """process_for_twin_hit (seed_search.c:1814, seed-hit-queue version) + merge_segments: a hit is extended only when an
+    earlier hit of its diagonal lies within the span window; the oracle keeps the reference's global queue, capacity
+    included"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    pairs = [[CAT, PIG]] + ([list(synth(300000))] if "--chain" not in opts and opts != TWIN_CASES[1] else [])
+    for files in pairs:
+        same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])

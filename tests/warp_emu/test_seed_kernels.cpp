@@ -109,7 +109,7 @@ static void upload(const std::string& s, padded& o) {                  // lzb_up
 static int g_bad = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { fprintf(stderr, "  FAILED %s: ", #cond); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); g_bad++; } } while (0)
 
-struct mode { const char* name; int gfExtend, mismatches, K, plain, entropy, hashBits, useFirstKernel, recover; };
+struct mode { const char* name; int gfExtend, mismatches, K, plain, entropy, hashBits, useFirstKernel, recover, twinMin, twinMax, chunkBlocks; };
 
 static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u32 step, const std::vector<mode>& modes, u32 partitionEvery = 0) {
     std::string t, q; const char* acgt = "ACGT";
@@ -156,7 +156,7 @@ static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u3
     for (const mode& M : modes) {
         // ---- oracle ----
         lzb_seed_params sp; memset(&sp, 0, sizeof sp);
-        sp.gfExtend = M.gfExtend; sp.gfMismatches = M.mismatches; sp.xDrop = 910; sp.hspThreshold = M.K; sp.entropy = M.entropy; sp.hashBits = M.hashBits; sp.plainHits = M.plain; sp.recoverSeeds = M.recover;
+        sp.gfExtend = M.gfExtend; sp.gfMismatches = M.mismatches; sp.xDrop = 910; sp.hspThreshold = M.K; sp.entropy = M.entropy; sp.hashBits = M.hashBits; sp.plainHits = M.plain; sp.recoverSeeds = M.recover; sp.twinMinSpan = M.twinMin; sp.twinMaxSpan = M.twinMax;
         lzb_segment* want = NULL; uint64_t nwant = 0; lzb_seed_stats wst;
         if (lzb_seed_hit_search(oc, T, Q, &seed, ctb, &sp, &want, &nwant, &wst)) { CHECK(false, "oracle: %s", lzb_last_error()); continue; }
         // ---- the kernels, orchestrated like lzb_seed_hit_search (one chunk) ----
@@ -190,7 +190,32 @@ static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u3
         for (u32 i = 0; i < nh; i++) { keysB[i] = keys[ord[i]]; valsB[i] = vals[ord[i]]; }
         emu_launch(1, 256, [&]() { k_bucket_bounds(keysB.data(), nh, nbuckets, bstart.data()); });
         std::vector<u32> diagEnd(nbuckets, 0); std::vector<cand_rec> cand(nh + 16); const u32 candCap = (u32)cand.size();
-        if (M.recover) {                                          /* --recoverseeds: k_extend_recover, the bucket's actual diagonal beside its extent */
+        if (M.twinMin > 0) {
+            /* --twins: k_extend_twin over SEVERAL chunks of the query (chunkBlocks x 1024 positions each), the way the host loop
+             * cuts a long query: the bucket extents and the carried queue entries persist from chunk to chunk */
+            std::vector<unsigned long long> prefix(nblk + 1, 0);
+            for (u32 b = 0; b < nblk; b++) prefix[b + 1] = prefix[b] + blkcnt[b];
+            const u32 carryCap = TWIN_CARRY_CAP(M.twinMax); std::vector<twin_ent> carry((size_t)nbuckets * carryCap); std::vector<u32> ncarry(nbuckets, 0);
+            const u32 cb = (u32)M.chunkBlocks;
+            for (u32 b0 = 0; b0 < nblk; b0 += cb) {
+                const u32 k0 = b0 * POS_PER_BLOCK, k1 = std::min<u32>((b0 + cb) * POS_PER_BLOCK, n), ns = (k1 - k0) * (u32)P.V;
+                std::vector<u32> sc2(ns + 2), so2(ns + 2, 0);
+                emu_launch(2, 256, [&]() { k_slot_count(qword.data(), off.data(), pos.data(), flips.data(), P, k0, ns, sc2.data()); });
+                for (u32 s2 = 0; s2 < ns; s2++) so2[s2 + 1] = so2[s2] + sc2[s2];
+                const u32 nh2 = so2[ns];
+                if (!nh2) continue;
+                std::vector<u32> ka(nh2 + 1), kb(nh2 + 1), bs(nbuckets + 2); std::vector<u64> va(nh2 + 1), vb(nh2 + 1);
+                emu_launch(2, 256, [&]() { k_expand(qword.data(), off.data(), pos.data(), flips.data(), P, k0, ns, so2.data(), ka.data(), va.data()); });
+                std::vector<u32> od(nh2); for (u32 i = 0; i < nh2; i++) od[i] = i;
+                std::stable_sort(od.begin(), od.end(), [&](u32 a, u32 b) { return ka[a] < ka[b]; });
+                for (u32 i = 0; i < nh2; i++) { kb[i] = ka[od[i]]; vb[i] = va[od[i]]; }
+                emu_launch(1, 256, [&]() { k_bucket_bounds(kb.data(), nh2, nbuckets, bs.data()); });
+                std::vector<twin_ent> ent(nh2 + 1);
+                emu_launch(2, 128, [&]() { k_extend_twin(vb.data(), bs.data(), nbuckets, P1.cls.data(), P2.cls.data(), P1.asc.data(), P2.asc.data(), &g_sc, P, (u32)M.twinMin, (u32)M.twinMax,
+                                                         prefix.data(), nblk, 256u * 1024u, diagEnd.data(), ent.data(), carry.data(), carryCap, ncarry.data(), cand.data(), candCap, &cnt); });
+            }
+            CHECK(cnt.overflow == 0, "%s: the twin replay flagged %llu entries", M.name, cnt.overflow);
+        } else if (M.recover) {                                          /* --recoverseeds: k_extend_recover, the bucket's actual diagonal beside its extent */
             std::vector<s32> diagActual(nbuckets, 0);
             emu_launch(2, 128, [&]() { k_extend_recover(valsB.data(), bstart.data(), nbuckets, P1.cls.data(), P2.cls.data(), P1.asc.data(), P2.asc.data(), &g_sc, P, diagEnd.data(), diagActual.data(), cand.data(), candCap, &cnt); });
         } else if (M.gfExtend == LZB_GFEX_EXACT || M.gfExtend == LZB_GFEX_MISMATCH)
@@ -264,6 +289,9 @@ int main() {
         { "--recoverseeds, 2^6 buckets", LZB_GFEX_XDROP, 0, 2000, 0, 1, 6, 0, 1 },
         { "--recoverseeds",              LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 0, 1 },
         { "--recoverseeds --nogfextend, 2^8", LZB_GFEX_NONE, 0, 0, 0, 0, 8, 0, 1 },
+        { "--twins=0..40, 2 chunks",     LZB_GFEX_XDROP, 0, 3000, 0, 1, 16, 0, 0, 38, 78, 10 },
+        { "--twins=-5..30, 2^6, 20 chunks", LZB_GFEX_XDROP, 0, 2000, 0, 1, 6, 0, 0, 33, 68, 1 },
+        { "--twins=10..200 --nogfextend, 2^8", LZB_GFEX_NONE, 0, 0, 0, 0, 8, 0, 0, 48, 238, 3 },
     };
     one_pair(0, 20000, "1110100110010101111", 1, 1, a);
     std::vector<mode> b = {
@@ -271,6 +299,7 @@ int main() {
         { "raw hits (plain)",            LZB_GFEX_NONE, 0, 0, 1, 0, 16, 1 },
         { "--exact=30",                  LZB_GFEX_EXACT, 0, 30, 0, 0, 16, 0 },
         { "--mismatch=1,25, 2^8 buckets", LZB_GFEX_MISMATCH, 1, 25, 0, 0, 8, 0 },
+        { "--twins=0..30 (match12, step 3), 5 chunks", LZB_GFEX_XDROP, 0, 2500, 0, 1, 16, 0, 0, 24, 54, 3 },
     };
     one_pair(1, 15000, "111111111111", 0, 3, b);
     std::vector<mode> c = {
@@ -279,6 +308,7 @@ int main() {
         { "[multi] query, --exact=25",   LZB_GFEX_EXACT, 0, 25, 0, 0, 16, 0 },
         { "[multi] query, raw hits",     LZB_GFEX_NONE, 0, 0, 1, 0, 16, 1 },
         { "[multi] query, --recoverseeds, 2^7", LZB_GFEX_XDROP, 0, 2200, 0, 1, 7, 0, 1 },
+        { "[multi] query, --twins=0..60, 2^7, 12 chunks", LZB_GFEX_XDROP, 0, 2200, 0, 1, 7, 0, 0, 38, 98, 1 },
     };
     one_pair(2, 12000, "1110100110010101111", 1, 1, c, 311);
     printf("%d checks failed, %llu collectives emulated\n", g_bad, emu_collectives);
