@@ -192,7 +192,9 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     u64 slotCap = 1ull << 26;
     { u64 allSlots = (u64)nblk * POS_PER_BLOCK * P.V; if (allSlots < slotCap) slotCap = allSlots; }
     if (slotCap < (u64)POS_PER_BLOCK * P.V) slotCap = (u64)POS_PER_BLOCK * P.V;
-    u32 candCap = prm->plainHits || prm->gfExtend != LZB_GFEX_XDROP ? (u32)std::min<u64>(totalHits + 1, 1ull << 26) : (1u << 22);
+    /* (the twin and recoverable processors extend again and again along a homologous diagonal -- the merge comes later -- so
+     * their candidate count is bounded by the hits, not by the number of distinct HSPs) */
+    u32 candCap = prm->plainHits || prm->gfExtend != LZB_GFEX_XDROP || twin || recover ? (u32)std::min<u64>(totalHits + 1, 1ull << 26) : (1u << 22);
 
     u32 *d_slotcnt = NULL, *d_slotoff = NULL, *keysA = NULL, *keysB = NULL; u64 *valsA = NULL, *valsB = NULL;
     cand_rec* d_cand = NULL; void* d_tmp = NULL; size_t tmpBytes = 0, tmpScan = 0;
