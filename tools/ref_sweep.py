@@ -18,7 +18,8 @@ SEEDS = ["", "--seed=12of19", "--seed=14of22", "--seed=111010011101", "--seed=1T
 OPTIONS = [["T=0"], ["--transition=2"], ["--notransition"], ["--step=2"], ["--step=5"], ["--strand=plus"], ["--strand=minus"], ["K=1800"],
            ["K=2600", "L=2000"], ["X=400"], ["X=1500"], ["Y=3000"], ["Y=15000"], ["--noentropy"], ["--nogapped"], ["--chain"], ["--chain=10,20"],
            ["--noytrim"], ["--allgappedbounds"], ["O=300", "E=40"], ["--exact=18"], ["--mismatch=2,28"], ["--nogfextend"], ["--ambiguous=n"],
-           ["--allocate:traceback=200K"], ["--match=1,2"], ["--identity=70"], ["K=top15%"], ["--notrivial"]]
+           ["--allocate:traceback=200K"], ["--match=1,2"], ["--identity=70"], ["K=top15%"], ["--notrivial"],
+           ["--recoverseeds"], ["--twins=0..40"], ["--twins=-8..25"], ["--twins=20..150", "--seedqueue=300"], ["--maxwordcount=30"], ["--maxwordcount=90%"]]
 FORMATS = ["--format=general-", "--format=lav", "--format=maf-", "--format=axt", "--format=sam-", "--format=cigar", "--format=paf",
            "--format=rdotplot", "--format=general-:name1,start1,end1,name2,start2+,end2+,cigarx,nmatch,ngap,diff"]
 
