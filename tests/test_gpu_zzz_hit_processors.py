@@ -4,7 +4,7 @@ through the C-ABI, and the product command line (with merge_segments) against th
 Written after the round's GPU minutes were spent: the kernel's own source runs against the oracle on the block emulator
 (tests/test_seed_kernels_emu.py: four --recoverseeds modes incl. 64- and 128-bucket hashes), the oracle and the host
 front end are compared with the reference binary on the CPU (tests/test_oracle_golden.py::test_oracle_recoverseeds), but
-these GPU cases have no GPU run behind them yet -- which is why the file sorts last (pytest -x stops at the first failure)."""
+these pytest cases have no GPU run behind them yet (five of their command lines were checked on a B200 by hand, profiles/r02_hit_processors_on_gpu.txt) -- which is why the file sorts last (pytest -x stops at the first failure)."""
 import os
 
 import numpy as np
