@@ -198,7 +198,7 @@ void lzb_target_free(lzb_target*);
  * positions may be NULL to get counts only; returns total positions or -1. */
 int64_t lzb_target_export_index(lzb_target*, uint32_t* counts, uint32_t* positions);
 
-/* limit_position_table (pos_table.h:240; pos_table.c:1763) with maxChasm == 0: every seed word that occurs more than
+/* limit_position_table (pos_table.h:248; pos_table.c:1763) with maxChasm == 0: every seed word that occurs more than
  * `limit` times in the target is dropped from the table (--maxwordcount=<limit>, lastz.c:1219).  The percentage form
  * (--maxwordcount=<p>%, find_position_table_limit pos_table.c:2000) is a host computation on the word counts of
  * lzb_target_export_index that ends in this call. */
