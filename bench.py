@@ -337,14 +337,14 @@ def main():
         T = engA.build_seed_position_table(target, seed)
         index_s = time.perf_counter() - t0
 
-        def seed_part(eng, sid, s, Q, resident, acc):
+        def seed_part(eng, sid, s, Q, resident, acc, extend_ctas=0):
             """the seed stage of one strand; returns what the gapped stage needs"""
             w0 = time.perf_counter()
             if not resident:
                 Q = eng.load_query(s)
                 acc["h2d"] += len(s)
             wl_ = time.perf_counter()
-            segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid)
+            segs, st = eng.seed_hit_search(T, Q, seed, strand_id=sid, extend_ctas=extend_ctas)
             w1 = time.perf_counter()
             table = segs.copy()
             if w["chain"]:
@@ -401,12 +401,7 @@ def main():
                 try:
                     # beside the first strand's sweeps the extension kernel runs with fewer persistent CTAs per SM, so that the
                     # sweeps (one warp each, latency-bound) keep their issue slots; the seed stage has their whole duration to hide in
-                    if args.overlap_extend_ctas:
-                        os.environ["LZB_EXTEND_CTAS_PER_SM"] = str(args.overlap_extend_ctas)
-                    try:
-                        QB, segsB, tabB = seed_part(engB, sidB, sB, handles[1] if resident else None, resident, accB)
-                    finally:
-                        os.environ.pop("LZB_EXTEND_CTAS_PER_SM", None)
+                    QB, segsB, tabB = seed_part(engB, sidB, sB, handles[1] if resident else None, resident, accB, extend_ctas=args.overlap_extend_ctas)
                     gapped_part(engB, sidB, sB, QB, segsB, tabB, resident, accB)
                 finally:
                     th.join()

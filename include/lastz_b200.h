@@ -125,6 +125,9 @@ typedef struct lzb_seed_params {
                                   table like for recoverSeeds. */
     int32_t  twinMaxSpan;
     int32_t  seedQueueSize;    /* --seedqueue=<entries>, default 256K (diag_hash.h:112); 0 = default */
+    int32_t  extendCtasPerSm;  /* tuning, no effect on results: persistent CTAs of the x-drop extension kernel per SM, 1..4
+                                  (0 = the default 4).  A caller that runs this stage beside another context's Y-drop sweeps
+                                  asks for fewer so that those keep their issue slots (bench.py). */
 } lzb_seed_params;
 
 typedef struct lzb_seed_stats {

@@ -212,9 +212,10 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
                             !(getenv("LZB_EXTEND_V1") && atoi(getenv("LZB_EXTEND_V1")));
     u32 *d_bcnt = NULL, *d_bcnt2 = NULL, *d_bid = NULL, *d_border = NULL, *d_next = NULL; size_t tmpOrder = 0;
     /* persistent CTAs of k_extend2 per SM: four fill the register file; a caller that runs this stage beside another
-     * context's Y-drop sweeps can ask for fewer so that those keep their issue slots (LZB_EXTEND_CTAS_PER_SM, read per call) */
+     * context's Y-drop sweeps can ask for fewer so that those keep their issue slots (lzb_seed_params.extendCtasPerSm; LZB_EXTEND_CTAS_PER_SM for experiments) */
     int extCtas = 4;
     { const char* e = getenv("LZB_EXTEND_CTAS_PER_SM"); if (e) { int v = atoi(e); if (v >= 1 && v <= 4) extCtas = v; } }
+    if (prm->extendCtasPerSm >= 1 && prm->extendCtasPerSm <= 4) extCtas = prm->extendCtasPerSm;
     if (coopExtend) {
         SCRATCH(13, d_bcnt, (size_t)nbuckets * 4); SCRATCH(14, d_bcnt2, (size_t)nbuckets * 4);
         SCRATCH(15, d_bid, (size_t)nbuckets * 4); SCRATCH(16, d_border, (size_t)nbuckets * 4);
