@@ -21,6 +21,7 @@ typedef struct {
     int gfExtend, gfMismatches, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
     int recoverSeeds;              /* --recoverseeds: process_for_recoverable_hit + merge_segments (lastz.c:5712-5720, :2791, :2811) */
     int twins, twinMinGap, twinMaxGap, seedQueue;    /* --twins=<min>..<max>, --seedqueue= (lastz.c:5671-5710, :9826-9850) */
+    int gpus;                      /* --gpus=<n>: the query cut into n intervals, one process and one device each (an addition) */
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
     int adaptive; double adaptFraction; uint32_t adaptBases;   /* K=top<N>% ('P') or K=top<bases> ('C'), string_to_score_thresh dna_utilities.c:2248 */
     uint32_t tracebackBytes;
@@ -118,11 +119,13 @@ static void parse_options(options* o, int argc, char** argv) {
                    "  filters    --identity=  --coverage=  --continuity=  --matchcount=  --filter=nmismatch:0..<n>|ngap:0..<n>|cgap:0..<n>\n"
                    "  output     --format=lav|axt|maf[-]|gfa|segments|cigar|general[-][:<fields>]|mapping[-]|sam[-]|softsam[-]|paf[:wfmash]|blastn[-]|rdotplot[+score]\n"
                    "             --rdotplot[+score]=<file>  --output=<file>\n"
-                   "  additions  --device=<n>  --diaghash=<bits>  --speculation=<n>  --stats\n"
+                   "  additions  --device=<n>  --gpus=<n>  --diaghash=<bits>  --speculation=<n>  --stats\n"
                    "Option meanings are those of lastz 1.04.58 (INTEGRATION.md section 6 lists what is and is not built).\n");
             exit(0);
         }
-        if (!silent[i] && strlen(o->args) + strlen(a) + 2 < sizeof o->args) { strcat(o->args, a); strcat(o->args, " "); }
+        /* (the echo of the command line in headers: --device=<k> is left out -- it names hardware, not the computation, and an
+         * interval process of --gpus=<n> must print what a run on that subrange prints) */
+        if (!silent[i] && !starts(a, "--device=") && strlen(o->args) + strlen(a) + 2 < sizeof o->args) { strcat(o->args, a); strcat(o->args, " "); }
         if (!strcmp(a, "T=0")) { o->withTrans = 0; o->haveTrans = 1; }
         else if (!strcmp(a, "T=1")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 1; }
         else if (!strcmp(a, "T=2")) { o->seedPattern = LZB_SEED_12OF19; o->withTrans = 0; }
@@ -306,6 +309,7 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (!strcmp(a, "--format=maf-")) o->format = 4;             /* MAF blocks, no parameter header */
         /* lastz_b200 additions */
         else if (starts(a, "--device=")) o->device = atoi(v);
+        else if (starts(a, "--gpus=")) { o->gpus = atoi(v); if (o->gpus < 1 || o->gpus > 64) lzb_die("--gpus wants a device count from 1 to 64"); }
         else if (starts(a, "--diaghash=")) o->hashBits = atoi(v);
         else if (starts(a, "--speculation=")) o->speculation = atoi(v);
         else if (!strcmp(a, "--stats")) o->showStats = 1;
@@ -348,8 +352,68 @@ static uint64_t read_segments(const char* path, const lzb_seq* t, const lzb_seq*
     *out = g; return n;
 }
 
+/* --gpus=<n>: the reference treats a query subrange q[a..b] as an independent unit of work, so the query is
+ * cut into n intervals and each goes to its own process and device (--device=k), with the target replicated.  The
+ * children are this same program run as `target query[a..b] <the other options> --device=k`; their outputs are
+ * gathered in interval order, so the result is, byte for byte, what n runs on those subranges print one after the
+ * other -- each with its own header lines, and an alignment that would cross a cut ends at it, as in the reference run
+ * on the same subranges.  Only for a query file that holds one sequence and carries no actions of its own. */
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
+#include <fcntl.h>
+static int run_sharded(int argc, char** argv, const options* o) {
+    if (!strcmp(o->querySpec, "(stdin)") || o->selfCompare) lzb_die("--gpus needs a query file (not stdin, not --self)");
+    if (strchr(o->querySpec, '[')) lzb_die("--gpus cuts the query itself: the query can't carry actions (\"%s\")", o->querySpec);
+    lzb_seqfile* qf = lzb_seqfile_open(o->querySpec);
+    lzb_seq q; memset(&q, 0, sizeof q);
+    if (!lzb_seqfile_next(qf, &q)) lzb_die("%s contains no sequence", o->querySpec);
+    { lzb_seq extra; memset(&extra, 0, sizeof extra); if (lzb_seqfile_next(qf, &extra)) lzb_die("--gpus needs a query file with one sequence (%s holds more)", o->querySpec); }
+    const uint64_t len = q.len;
+    lzb_seqfile_close(qf);
+    const int n = o->gpus;
+    if (len < (uint64_t)n) lzb_die("the query (%llu bases) is shorter than the number of intervals (%d)", (unsigned long long)len, n);
+    pid_t* pid = calloc((size_t)n, sizeof *pid); char (*tmp)[64] = calloc((size_t)n, 64);
+    for (int k = 0; k < n; k++) {
+        const uint64_t lo = (uint64_t)k * len / (uint64_t)n, hi = (uint64_t)(k + 1) * len / (uint64_t)n;     /* [lo, hi), 0-based */
+        snprintf(tmp[k], 64, "/tmp/lastz_b200_shard_XXXXXX");
+        const int fd = mkstemp(tmp[k]);
+        if (fd < 0) lzb_die("can't create a temporary file for interval %d", k);
+        char** av = calloc((size_t)argc + 3, sizeof *av); int ac = 0;
+        char* qspec = malloc(strlen(o->querySpec) + 64), * dev = malloc(32);
+        snprintf(qspec, strlen(o->querySpec) + 64, "%s[%llu..%llu]", o->querySpec, (unsigned long long)lo + 1, (unsigned long long)hi);
+        snprintf(dev, 32, "--device=%d", o->device + k);
+        av[ac++] = argv[0];
+        for (int i = 1; i < argc; i++) {
+            if (!strncmp(argv[i], "--gpus=", 7) || !strncmp(argv[i], "--device=", 9) || !strncmp(argv[i], "--output=", 9)) continue;
+            av[ac++] = argv[i] == o->querySpec ? qspec : argv[i];
+        }
+        av[ac++] = dev; av[ac] = NULL;
+        fflush(NULL);
+        pid[k] = fork();
+        if (pid[k] < 0) lzb_die("can't start the process for interval %d", k);
+        if (pid[k] == 0) { dup2(fd, 1); close(fd); execv("/proc/self/exe", av); fprintf(stderr, "FAILURE: can't re-run %s\n", argv[0]); _exit(127); }
+        close(fd);
+    }
+    int bad = 0;
+    for (int k = 0; k < n; k++) { int st = 0; if (waitpid(pid[k], &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1; }
+    FILE* out = o->outputFile ? fopen(o->outputFile, "w") : stdout;
+    if (!out) lzb_die("fopen_or_die failed to open \"%s\" for \"w\"", o->outputFile);
+    for (int k = 0; k < n && !bad; k++) {                        /* the gather: interval order */
+        FILE* f = fopen(tmp[k], "r"); char buf[1 << 16]; size_t got;
+        if (!f) lzb_die("lost the output of interval %d", k);
+        while ((got = fread(buf, 1, sizeof buf, f)) > 0) fwrite(buf, 1, got, out);
+        fclose(f);
+    }
+    for (int k = 0; k < n; k++) unlink(tmp[k]);
+    if (bad) lzb_die("one of the %d interval processes failed (its message is above)", n);
+    if (out != stdout) fclose(out);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     options o; parse_options(&o, argc, argv);
+    if (o.gpus > 1) return run_sharded(argc, argv, &o);
     /* scoring + derived defaults, lastz.c:9127-9339 */
     static lzb_scoreset ss;
     if (o.scoresFile && o.unitScores) lzb_die("can't use --scores and --match together");
