@@ -24,6 +24,7 @@ CASES = [
     ["aglobin.2bit/human", "shorties.fa", "--exact=20", "--anyornone", "--format=paf"],
     ["aglobin.2bit/human", "aglobin.2bit/cow", "--recoverseeds", "--format=maf-"],
     ["aglobin.2bit/human", "aglobin.2bit/cow", "--twins=0..40", "--seedqueue=500", "--format=general"],
+    ["aglobin.2bit/human", "aglobin.2bit/cow", "--gpus=3", "--format=maf"],
     ["aglobin.2bit/human", "aglobin.2bit/cow", "--format=axt", "--segments=base_test.anchors.anchors"],
 ]
 
