@@ -16,7 +16,7 @@
  *
  * What the library does not implement the adapter refuses loudly (suicide): hit processors other than
  * process_for_simple_hit / process_for_plain_hit, adaptive HSP thresholds, positional filters, searchLimit, bandWidth,
- * maxPairedBases, half-weight / overweight / reverse-complement seeds.  There is no fallback to the renamed originals.
+ * half-weight / overweight / reverse-complement seeds.  There is no fallback to the renamed originals.
  */
 #include <stdlib.h>
 #include <stdio.h>
@@ -209,8 +209,7 @@ void reduce_to_points(seq* seq1, seq* seq2, scoreset* scoring, segtable* anchors
 /* ---- gapped_extend.h:153 ---- */
 alignel* gapped_extend(seq* seq1, u8* rev1, seq* seq2, u8* rev2, int inhibitTrivial, scoreset* scoring, segtable* anchors, tback* tb,
                        int allBounds, score yDrop, int trimToPeak, sthresh scoreThresh, u64 maxPairedBases, int overlyPairedWarn, int overlyPairedKeep) {
-    (void)rev1; (void)rev2; (void)overlyPairedWarn; (void)overlyPairedKeep;   /* the reversed copies and the traceback live on the device */
-    if (maxPairedBases != 0) suicide("the lastz_b200 adapter does not support --maxpairedbases (reserved option)");
+    (void)rev1; (void)rev2;                                            /* the reversed copies and the traceback live on the device */
     if (scoreThresh.t != 'S') suicide("the lastz_b200 adapter does not support adaptive gapped thresholds");
     use_scoring(scoring, NULL);
     need_target(seq1);
@@ -221,8 +220,13 @@ alignel* gapped_extend(seq* seq1, u8* rev1, seq* seq2, u8* rev2, int inhibitTriv
     gp.identityCheck = seq1->revCompFlags == seq2->revCompFlags;      /* identical_sequences gapped_extend.c:1905 */
     gp.tracebackBytes = tb->size + 8 - 1;                              /* new_traceback gapped_extend.c:2272-2290: size = bytes - sizeof header + 1 */
     gp.speculation = 256;
-    lzb_alignel* list = NULL;
+    gp.maxPairedBases = maxPairedBases; gp.overlyPairedKeep = overlyPairedKeep;       /* --querydepth= (gapped_extend.c:1444-1459) */
+    lzb_alignel* list = NULL; lzb_gapped_stats gst;
     if (sizeof(alignel) != sizeof(lzb_alignel)) suicide("alignel layout differs from lzb_alignel");
-    if (lzb_gapped_extend(ctx(), g_target, g_query, seq1->v, seq2->v, (lzb_segment*)anchors->seg, anchors->len, &gp, &list, NULL)) suicidef("%s", lzb_last_error());
+    if (lzb_gapped_extend(ctx(), g_target, g_query, seq1->v, seq2->v, (lzb_segment*)anchors->seg, anchors->len, &gp, &list, &gst)) suicidef("%s", lzb_last_error());
+    if (gst.overlyPaired && overlyPairedWarn)                          /* (the reference's own warning is a static function of the replaced file) */
+        fprintf(stderr, "WARNING. Query %s (%c strand) contains more than %llu paired bases.\n",
+                seq2->partition.p != NULL ? "seq2" : seq2->useFullNames ? seq2->header : seq2->shortHeader,
+                (seq2->revCompFlags & rcf_rev) == 0 ? '+' : '-', (unsigned long long)maxPairedBases);
     return (alignel*)list;                                             /* same 64-byte records; free_align_list (edit_script.c:53) frees them */
 }

@@ -154,6 +154,11 @@ typedef struct lzb_gapped_params {
                                   sets it when both sequences carry the same strand flags (:1905, :2058) */
     uint32_t tracebackBytes;   /* --allocate:traceback, default 80 MiB; changes results */
     int32_t  speculation;      /* product only: max anchors extended speculatively in parallel */
+    int32_t  overlyPairedKeep; /* with maxPairedBases: keep what was found before the limit was passed (--querydepth=keep:) */
+    uint64_t maxPairedBases;   /* gapped_extend's maxPairedBases (gapped_extend.c:1444-1459; --querydepth=<d> = d x query length,
+                                  lastz.c:3414-3417): when the aligned (substitution) columns of the alignments kept so far
+                                  exceed it, no further anchor is extended and, unless overlyPairedKeep, the call returns no
+                                  alignment at all.  0 = no limit.  stats->overlyPaired tells the caller (who warns). */
 } lzb_gapped_params;
 
 typedef struct lzb_gapped_stats {
@@ -168,6 +173,7 @@ typedef struct lzb_gapped_stats {
     double   kernelSeconds[4]; /* [0] Y-drop DP kernel, [1] traceback kernel (CUDA events), see DESIGN.md */
     uint64_t launches;         /* kernels launched by this call */
     uint64_t dpCellsComputed;  /* product: every cell the device computed, discarded speculation included (>= dpCells) */
+    uint64_t overlyPaired;     /* 1 if maxPairedBases was exceeded */
 } lzb_gapped_stats;
 
 typedef struct lzb_ctx    lzb_ctx;     /* one device + stream + scratch */

@@ -227,10 +227,10 @@ class Engine:
     # ---- gapped_extend.h:153
     def gapped_extend(self, t, q, seq1: bytes, seq2: bytes, anchors, *, y_drop=9400, trim_to_peak=True,
                       score_threshold=3000, all_bounds=False, inhibit_trivial=False, identity_check=False,
-                      traceback_bytes=80 * 1024 * 1024, speculation=64):
+                      traceback_bytes=80 * 1024 * 1024, speculation=64, max_paired_bases=0, overly_paired_keep=False):
         a = np.ascontiguousarray(anchors)
         p = capi.GappedParams(y_drop, int(trim_to_peak), score_threshold, int(all_bounds), int(inhibit_trivial),
-                              int(identity_check), traceback_bytes, speculation)
+                              int(identity_check), traceback_bytes, speculation, int(overly_paired_keep), int(max_paired_bases))
         lst = C.POINTER(capi.Alignel)()
         st = capi.GappedStats()
         self._check(self.lib.lzb_gapped_extend(self.ctx, t, q, seq1, seq2, a.ctypes.data_as(C.POINTER(capi.Segment)),

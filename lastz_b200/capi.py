@@ -66,14 +66,14 @@ class SeedStats(C.Structure):
 class GappedParams(C.Structure):
     _fields_ = [("yDrop", C.c_int32), ("trimToPeak", C.c_int32), ("scoreThreshold", C.c_int32),
                 ("allBounds", C.c_int32), ("inhibitTrivial", C.c_int32), ("identityCheck", C.c_int32),
-                ("tracebackBytes", C.c_uint32), ("speculation", C.c_int32)]
+                ("tracebackBytes", C.c_uint32), ("speculation", C.c_int32), ("overlyPairedKeep", C.c_int32), ("maxPairedBases", C.c_uint64)]
 
 
 class GappedStats(C.Structure):
     _fields_ = [("anchors", C.c_uint64), ("anchorsExtended", C.c_uint64), ("dpCells", C.c_uint64),
                 ("dpRows", C.c_uint64), ("truncated", C.c_uint64), ("speculated", C.c_uint64),
                 ("redone", C.c_uint64), ("seconds", C.c_double), ("kernelSeconds", C.c_double * 4),
-                ("launches", C.c_uint64), ("dpCellsComputed", C.c_uint64)]
+                ("launches", C.c_uint64), ("dpCellsComputed", C.c_uint64), ("overlyPaired", C.c_uint64)]
 
 
 assert C.sizeof(Segment) == 48 and C.sizeof(Alignel) == 64

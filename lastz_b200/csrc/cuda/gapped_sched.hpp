@@ -485,6 +485,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     };
     if (G.obi == (int)n) retire_covered((int)n);
 
+    u64 pairedBases = 0;
     /* commit anchor i from its finished, validated sweeps */
     auto commit_anchor = [&](u64 i, dp_result& rl, dp_result& rr) {
         galn& m = G.al[i];
@@ -540,6 +541,16 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
         list_insert(G, (int)i);
         m.devIx = (int)G.committed.size(); G.committed.push_back((int)i);
         retire_covered((int)i);
+        if (P->maxPairedBases > 0) {
+            /* the limit on aligned columns (gapped_extend.c:1444-1459, count_paired_bases :5695): commits come in the reference's
+             * anchor order, so the alignment that takes the sum over the limit is the same one; nothing after it is extended --
+             * every anchor still open is closed, the sweeps in flight are told to stop */
+            for (const hseg& sg : m.segs) if (sg.type == SEG_DIAG) pairedBases += (u64)sg.e1 + 1 - sg.b1;
+            if (pairedBases > P->maxPairedBases) {
+                G.st.overlyPaired = 1;
+                for (u64 j = 0; j < n; j++) if (!fin[j]) { fin[j] = 1; if (laneOf[j] >= 0) drop_lane(laneOf[j]); }
+            }
+        }
     };
 
     /* expected length of a sweep in rows, for deciding what is worth starting: an average over finished sweeps */
@@ -869,6 +880,7 @@ static int gx_run(Backend& B, const gx_input& in, lzb_segment* anchors, uint64_t
     for (int o = G.obi; o >= 0; o = G.al[o].next) {
         galn& m = G.al[o];
         bool drop = m.align->s < P->scoreThreshold || (P->inhibitTrivial && m.align->isTrivial);
+        if (G.st.overlyPaired && !P->overlyPairedKeep) drop = true;       /* discard_alignments :1580 */
         if (drop) { free(m.align->script); free(m.align); }
         else { if (!head) head = last = m.align; else { last->next = m.align; last = m.align; } }
     }

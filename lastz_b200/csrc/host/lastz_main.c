@@ -21,6 +21,7 @@ typedef struct {
     int gfExtend, gfMismatches, gapped, entropy, chain, selfCompare, inhibitTrivial, allBounds, trimToPeak;
     int recoverSeeds;              /* --recoverseeds: process_for_recoverable_hit + merge_segments (lastz.c:5712-5720, :2791, :2811) */
     int twins, twinMinGap, twinMaxGap, seedQueue;    /* --twins=<min>..<max>, --seedqueue= (lastz.c:5671-5710, :9826-9850) */
+    double queryDepth; int depthWarn, depthKeep; uint64_t maxPairedBases;   /* --querydepth=[keep:|nowarn:|keep,nowarn:|discard:]<depth> (lastz.c:6063-6105) */
     int gpus;                      /* --gpus=<n>: the query cut into n intervals, one process and one device each (an addition) */
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
     int adaptive; double adaptFraction; uint32_t adaptBases;   /* K=top<N>% ('P') or K=top<bases> ('C'), string_to_score_thresh dna_utilities.c:2248 */
@@ -115,7 +116,7 @@ static void parse_options(options* o, int argc, char** argv) {
                    "  extension  --[no]gfextend  --xdrop=  --hspthresh=<score>|top<N>%%|top<bases>  --exact=<N>  --mismatch=<M>,<N>  --[no]entropy\n"
                    "             --[no]gapped  --ydrop=  --gappedthresh=  --gap=<open>,<extend>  --scores=<file>  --match=<reward>[,<penalty>]\n"
                    "             --ambiguous=n[,..]  --noytrim  --allgappedbounds  --notrivial  --allocate:traceback=<bytes>  --[no]chain[=<diag>,<anti>]\n"
-                   "             --segments=<file>  --anyornone  --justhits  --yasra98|95|90|85|75|95short|85short\n"
+                   "             --segments=<file>  --anyornone  --justhits  --querydepth=[keep:]<depth>  --yasra98|95|90|85|75|95short|85short\n"
                    "  filters    --identity=  --coverage=  --continuity=  --matchcount=  --filter=nmismatch:0..<n>|ngap:0..<n>|cgap:0..<n>\n"
                    "  output     --format=lav|axt|maf[-]|gfa|segments|cigar|general[-][:<fields>]|mapping[-]|sam[-]|softsam[-]|paf[:wfmash]|blastn[-]|rdotplot[+score]\n"
                    "             --rdotplot[+score]=<file>  --output=<file>\n"
@@ -134,6 +135,18 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--word=")) ;                         /* lastz.c:5665: max index bits; only a table-layout matter (overweight
                                                                     seeds are "resolved", seed_search.c:878) -- this index holds 28 bits anyway */
         else if (!strcmp(a, "--anyornone") || !strcmp(a, "--stopafterone")) o->anyOrNone = 1;
+        else if (starts(a, "--querydepth=")) {                     /* depth in units of the query length; K/M suffixes as in string_to_unitized_double */
+            const char* d = v; o->depthWarn = 1; o->depthKeep = 0;
+            if (starts(v, "nowarn:")) { o->depthWarn = 0; d = v + 7; }
+            else if (starts(v, "keep,nowarn:")) { o->depthWarn = 0; o->depthKeep = 1; d = v + 12; }
+            else if (starts(v, "keep:")) { o->depthKeep = 1; d = v + 5; }
+            else if (starts(v, "discard:")) d = v + 8;
+            char* end = NULL; double x = strtod(d, &end);
+            if (end == d) lzb_die("\"%s\" is not a number", d);
+            if (*end == 'K' || *end == 'k') { x *= 1000; end++; } else if (*end == 'M' || *end == 'm') { x *= 1000 * 1000; end++; } else if (*end == 'G' || *end == 'g') { x *= 1000.0 * 1000 * 1000; end++; }
+            if (*end) lzb_die("\"%s\" is not a number", d);
+            o->queryDepth = x < 0 ? 0 : x;
+        }
         else if (!strcmp(a, "--notwins")) o->twins = 0;
         else if (starts(a, "--twins=")) {                        /* <min>..<max>, the historical <min>:<max>, or <max> alone */
             const char* sep = strstr(v, ".."); int w = 2;
@@ -756,10 +769,23 @@ int main(int argc, char** argv) {
                 gp.inhibitTrivial = o.inhibitTrivial; gp.tracebackBytes = o.tracebackBytes;
                 gp.identityCheck = query.revCompFlags == target.revCompFlags && !query.npart;   /* identical_sequences :1147, identical_partition_of_sequence :1131 */
                 gp.speculation = o.speculation;
+                if (o.queryDepth > 0) { gp.maxPairedBases = (uint64_t)ceil(o.queryDepth * query.len); gp.overlyPairedKeep = o.depthKeep; }   /* lastz.c:3414-3417 */
                 if (lzb_reduce_to_points(ctx, T, Q, segs, nsegs)) lzb_die("%s", lzb_last_error());
                 lzb_alignel* list = NULL;
                 if (lzb_gapped_extend(ctx, T, Q, target.v, query.v, segs, nsegs, &gp, &list, &gst))
                     lzb_die("%s", lzb_last_error());
+                if (gst.overlyPaired && o.depthWarn) {                /* warn_for_paired_bases_limit gapped_extend.c:5725 */
+                    static int firstReport = 1;
+                    char num[40], com[56]; snprintf(num, sizeof num, "%llu", (unsigned long long)gp.maxPairedBases);
+                    size_t nl = strlen(num), w = 0;                    /* commatize utilities.c:1233 */
+                    for (size_t z = 0; z < nl; z++) { com[w++] = num[z]; if ((nl - 1 - z) % 3 == 0 && z + 1 < nl) com[w++] = ','; }
+                    com[w] = 0;
+                    fprintf(stderr, "WARNING. Query %s (%c strand) contains more than %s paired bases.\n", query.npart ? "seq2" : query.shortHeader,
+                            (query.revCompFlags & LZB_RCF_REV) ? '-' : '+', com);
+                    if (firstReport) fprintf(stderr, o.depthKeep ? "Any gapped alignments already found for this query/strand are reported but the\nquery/strand is not processed further.\n"
+                                                                 : "All gapped alignments for this query/strand are discarded and the query/strand\nis not processed further.\n");
+                    firstReport = 0;
+                }
                 totCells += gst.dpCells; gapSec += gst.seconds; gk += gst.kernelSeconds[0];
                 gExt += gst.anchorsExtended; gSpec += gst.speculated; gRedo += gst.redone; gLaunch += gst.launches; gTrunc += gst.truncated;
                 if (lzb_filters_active(&o.filters)) {             /* filter_aligns_by_* lastz.c:3430-3462 */

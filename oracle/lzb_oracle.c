@@ -1067,7 +1067,7 @@ int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const uint8_t* h1
     if (n) qsort(anchors, n, sizeof(lzb_segment), cmp_anchor);   /* batched_segments :1675 */
     G.al = calloc(n + 1, sizeof(galn)); G.nal = (int)n + 1;
     for (u64 i = 0; i < n; i++) { G.al[i].pos1 = anchors[i].pos1; G.al[i].pos2 = anchors[i].pos2; G.al[i].hspId = anchors[i].hspId; }
-    s32 ts;
+    s32 ts; u64 pairedBases = 0;
     /* identical_sequences also requires equal revCompFlags (:1905); the caller vouches for that
      * through identityCheck */
     if (P->identityCheck && same_sequences(&G, &ts)) {
@@ -1133,11 +1133,16 @@ int lzb_gapped_extend(lzb_ctx* c, lzb_target* t, lzb_query* q, const uint8_t* h1
         }
         alignment_neighbours(&G, m);
         list_insert(&G, (int)i);
+        if (P->maxPairedBases > 0) {                      /* :1444-1459, count_paired_bases :5695 */
+            for (int sg = 0; sg < m->nsegs; sg++) if (m->segs[sg].type == SEG_DIAG) pairedBases += (u64)m->segs[sg].e1 + 1 - m->segs[sg].b1;
+            if (pairedBases > P->maxPairedBases) { G.st.overlyPaired = 1; break; }
+        }
     }
     lzb_alignel* head = NULL, *last = NULL;
     for (int o = G.obi; o >= 0; o = G.al[o].next) {
         galn* m = &G.al[o];
         int drop = m->align->s < P->scoreThreshold || (P->inhibitTrivial && m->align->isTrivial);
+        if (G.st.overlyPaired && !P->overlyPairedKeep) drop = 1;          /* discard_alignments :1580 */
         if (drop) { free(m->align->script); free(m->align); }
         else { if (!head) head = last = m->align; else { last->next = m->align; last = m->align; } }
     }

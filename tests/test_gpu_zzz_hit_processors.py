@@ -112,3 +112,14 @@ def test_twins_refuse_a_queue_that_would_forget(synth):
     t, q = synth(300000)
     with pytest.raises(RuntimeError, match="seed hit queue"):
         run_cli(PRODUCT_CLI, [t, q, "--twins=0..200", "--seed=match8", "--step=2", "--nogapped", "--seedqueue=2000"])
+
+
+@pytest.mark.parametrize("depth", ["0.3", "keep:0.05", "keep:0.2", "keep,nowarn:0.15"])
+def test_cli_querydepth(depth):
+    """gapped_extend's maxPairedBases inside the in-order-commit scheduler: the commit that takes the sum over the limit
+    closes every open anchor (the scheduler's own source runs this against the oracle on the block emulator with 8 and 16
+    lanes, tests/warp_emu/test_gapped_sched.cpp cases 6 and 7)"""
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    aglobin = os.path.join(GOLDEN, "aglobin.2bit")
+    args = [aglobin + "/human", aglobin + "/cow", "--querydepth=" + depth, "--format=general-"]
+    same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])

@@ -469,3 +469,14 @@ def test_oracle_twins(synth, opts):
     pairs = [[CAT, PIG]] + ([list(synth(300000))] if "--chain" not in opts and opts != TWIN_CASES[1] else [])
     for files in pairs:
         same_output(run_cli(ORACLE_CLI, files + opts)[0], run_cli(REF_CLI, files + opts)[0])
+
+
+@pytest.mark.parametrize("depth", ["0.05", "0.3", "keep:0.05", "keep:0.1", "keep:0.2", "keep:0.3", "keep,nowarn:0.15", "nowarn:0.2", "discard:0.1", "7"])
+def test_oracle_querydepth(depth):
+    """gapped_extend's maxPairedBases (gapped_extend.c:1444-1459; --querydepth=<d> = d x query length): once the alignments
+    kept so far pair more bases than that, nothing further is extended; everything found is discarded unless `keep`"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    for fmt in ("--format=general-", "--format=maf-"):
+        args = [AGLOBIN + "/human", AGLOBIN + "/cow", "--querydepth=" + depth, fmt]
+        same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])

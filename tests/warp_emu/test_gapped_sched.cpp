@@ -125,7 +125,7 @@ struct emu_backend {
 static void expand(std::string& out, const u32* ops, u32 n) { for (u32 k = 0; k < n; k++) out.append(ops[k] >> 2, "?IDS"[ops[k] & 3]); }
 
 // homologous pair with `blocks` rearranged pieces: enough structure for neighbours on both sides, above and below
-static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int W, u32 every, int shuffle, int dupes, const char* slack = "-1", const char* mode = "1") {
+static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, s32 yDrop, int trim, int W, u32 every, int shuffle, int dupes, const char* slack = "-1", const char* mode = "1", u64 maxPaired = 0, int keepPaired = 0) {
     setenv("LZB_DP_MODE", mode, 1);         // 1: the one-warp kernel (the default), 0: the four-warp kernel, 2: the shared-memory kernel (no checkpoints)
     setenv("LZB_GAP_SLACK", slack, 1);     // -1: every anchor is started as soon as a lane is free (most speculation); else the margin in rows
     std::string t, q; const char* acgt = "ACGT";
@@ -157,6 +157,7 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
     std::vector<lzb_segment> a1(segs, segs + nsegs), a2(segs, segs + nsegs);
     lzb_gapped_params gp; memset(&gp, 0, sizeof gp);
     gp.yDrop = yDrop; gp.trimToPeak = trim; gp.scoreThreshold = 3000; gp.tracebackBytes = tbBytes; gp.speculation = W;
+    gp.maxPairedBases = maxPaired; gp.overlyPairedKeep = keepPaired;       // --querydepth: nothing is extended once the kept alignments pair more bases than this
     lzb_alignel* want = NULL; lzb_gapped_stats so; memset(&so, 0, sizeof so);
     if (lzb_gapped_extend(oc, T, Q, (const uint8_t*)t.data(), (const uint8_t*)q.data(), a1.data(), nsegs, &gp, &want, &so)) { fprintf(stderr, "oracle failed: %s\n", lzb_last_error()); return 1; }
     // the scheduler over the emulated kernels
@@ -183,6 +184,7 @@ static int one_case(int caseNo, u32 len, double sub, double indel, u32 tbBytes, 
     for (; w; w = w->next) nw++;
     for (; g; g = g->next) ng++;
     if (nw != ng) { fprintf(stderr, "  oracle %u alignments, scheduler %u\n", nw, ng); bad++; }
+    if (so.overlyPaired != sg.overlyPaired || (maxPaired && !so.overlyPaired)) { fprintf(stderr, "  paired-bases limit: oracle %llu, scheduler %llu (a case with a limit must reach it)\n", (unsigned long long)so.overlyPaired, (unsigned long long)sg.overlyPaired); bad++; }
     if (so.anchorsExtended != sg.anchorsExtended || so.dpCells != sg.dpCells || so.truncated != sg.truncated) {
         fprintf(stderr, "  counters: oracle extended=%llu cells=%llu truncated=%llu; scheduler %llu %llu %llu\n", (unsigned long long)so.anchorsExtended, (unsigned long long)so.dpCells,
                 (unsigned long long)so.truncated, (unsigned long long)sg.anchorsExtended, (unsigned long long)sg.dpCells, (unsigned long long)sg.truncated);
@@ -206,6 +208,8 @@ int main(int argc, char** argv) {
     bad += one_case(n++, 5000, 0.04, 0.010, 80000, 6000, 1, 3, 96, 1, 1);       // fewer lanes than anchors worth starting
     bad += one_case(n++, 4000, 0.04, 0.010, 60000, 9400, 1, 8, 64, 1, 1, "-1", "2");   // the shared-memory kernel: no checkpoints, a touched sweep restarts
     bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 1, "20"); // the product's waiting rule (anchors near an expected reach wait for the commit)
+    bad += one_case(n++, 6000, 0.04, 0.010, 60000, 9400, 1, 16, 64, 1, 0, "-1", "1", 1500, 1);   // --querydepth=keep: the limit is passed after a few commits, the rest is dropped
+    bad += one_case(n++, 6000, 0.05, 0.012, 50000, 9400, 1, 8, 32, 1, 2, "20", "0", 2500, 0);    // --querydepth: everything is discarded
     bad += one_case(n++, 14000, 0.04, 0.010, 200000, 9400, 1, 16, 32, 1, 1, "10", "0"); // sweeps long enough to be stopped short of an earlier anchor's alignment and continued
     if (big) {
         bad += one_case(n++, 20000, 0.04, 0.010, 100000, 9400, 1, 32, 64, 1, 3);
