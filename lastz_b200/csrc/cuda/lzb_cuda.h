@@ -37,6 +37,7 @@ struct lzb_ctx {
     void* gappedCache;                       /* gapped.cu: speculation lanes kept across calls */
     void* peaksBuf; size_t peaksCap;         /* gapped.cu: anchor table of lzb_reduce_to_points */
     void* seedScratch;                       /* seed_search.cu: device scratch kept across calls */
+    unsigned candCapWanted;                  /* seed_search.cu: HSP candidate capacity a call found it needed (0: the default) */
     struct { u8* seq; u8* cls; size_t cap; } qpool[4];   /* device buffers of freed queries, reused by the next load
                                                 (cudaFree is a device-wide synchronisation: 0.1 s with 32 lanes' buffers live) */
 };

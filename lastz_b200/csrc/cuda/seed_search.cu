@@ -195,6 +195,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
     /* (the twin and recoverable processors extend again and again along a homologous diagonal -- the merge comes later -- so
      * their candidate count is bounded by the hits, not by the number of distinct HSPs) */
     u32 candCap = prm->plainHits || prm->gfExtend != LZB_GFEX_XDROP || twin || recover ? (u32)std::min<u64>(totalHits + 1, 1ull << 26) : (1u << 22);
+    if (c->candCapWanted > candCap) candCap = (u32)std::min<u64>(c->candCapWanted, totalHits + 1);      /* an earlier call ran out of room */
 
     u32 *d_slotcnt = NULL, *d_slotoff = NULL, *keysA = NULL, *keysB = NULL; u64 *valsA = NULL, *valsB = NULL;
     cand_rec* d_cand = NULL; void* d_tmp = NULL; size_t tmpBytes = 0, tmpScan = 0;
@@ -300,6 +301,13 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
         goto cleanup_fail;
     }
     if (hc.ncand > candCap) {
+        /* the candidate buffer was too small (the kernels count every candidate and store only what fits): the exact count is
+         * known now, so the call is made again with room for all of them -- once; the context remembers the size */
+        if (hc.ncand <= (1ull << 28) && c->candCapWanted < hc.ncand) {
+            for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+            c->candCapWanted = (unsigned)std::min<u64>(hc.ncand + hc.ncand / 8 + 1024, 1ull << 28);
+            return lzb_seed_hit_search(c, t, q, seed, ctb, prm, segs, nsegs, stats);
+        }
         lzb_fail("%llu HSP candidates exceed the %u-entry result buffer; raise the threshold (--hspthresh)", hc.ncand, candCap);
         goto cleanup_fail;
     }
