@@ -14,9 +14,9 @@
  * is the reference's code, unchanged.  Linked against oracle/liblzb_oracle.so this is a CPU-only check of the boundary
  * (tests/test_adapter.py); linked against lastz_b200/csrc/liblastz_b200.so it is lastz running its hot path on a B200.
  *
- * What the library does not implement the adapter refuses loudly (suicide): hit processors other than
- * process_for_simple_hit / process_for_plain_hit, adaptive HSP thresholds, positional filters, searchLimit, bandWidth,
- * half-weight / overweight / reverse-complement seeds.  There is no fallback to the renamed originals.
+ * What the library does not implement the adapter refuses loudly (suicide): adaptive HSP thresholds, positional filters,
+ * bandWidth, density filtering, half-weight / overweight / reverse-complement seeds.  (The simple, plain, recoverable and
+ * twin hit processors, searchLimit and maxPairedBases are passed through.)  There is no fallback to the renamed originals.
  */
 #include <stdlib.h>
 #include <stdio.h>
@@ -120,12 +120,11 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
                     u32 bandWidth,
 #endif
                     hitprocessor processor, void* processorInfo) {
-    (void)hitSeed; (void)reportSearchLimit;
+    (void)hitSeed;
     if (pt != g_targetKey || !g_target) suicide("the lastz_b200 adapter was handed a position table it did not build");
     if (processor != process_for_simple_hit && processor != process_for_plain_hit && processor != process_for_recoverable_hit
      && processor != process_for_twin_hit)
         suicide("the lastz_b200 adapter was handed a hit processor it does not know");
-    if (searchLimit != 0) suicide("the lastz_b200 adapter does not support --queryhsplimit / search limits");
 #ifdef densityFiltering
     if (maxDensity != 0) suicide("the lastz_b200 adapter does not support --maxdensity");
 #endif
@@ -161,6 +160,7 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
     sp.selfCompare = selfCompare;
     sp.sameStrand = selfCompare && seq1->revCompFlags == seq2->revCompFlags;
     sp.strandId = seq2->revCompFlags;
+    sp.searchLimit = searchLimit;                            /* --queryhsplimit: the table ends with the query position that took it past the limit */
     lzb_segment* segs = NULL; uint64_t n = 0; u64 bases = 0;
     if (lzb_seed_hit_search(ctx(), g_target, g_query, &g_seed, (const int8_t*)charToBits, &sp, &segs, &n, NULL)) suicidef("%s", lzb_last_error());
     /* the library returns the table in discovery order; the reporter sees what process_for_simple_hit shows it
@@ -170,6 +170,11 @@ u64 seed_hit_search(seq* seq1, postable* pt, seq* seq2, unspos start, unspos end
     for (uint64_t i = 0; i < n; i++)
         bases += (*hp->reporter)(hp->reporterInfo, (unspos)segs[i].pos1 + segs[i].length, (unspos)segs[i].pos2 + segs[i].length, segs[i].length, segs[i].s);
     lzb_free(segs);
+    if (searchLimit > 0 && n > searchLimit) {                /* warn_for_search_limit seed_search.c:3790-3815 (a static function of the replaced file) */
+        seed_search_dbgSearchLimitExceeded++;
+        if (reportSearchLimit != 0)
+            fprintf(stderr, "WARNING. Query \"%s\" contains more than %u HSPs.\n", seq2->useFullNames ? seq2->header : seq2->shortHeader, (unsigned)reportSearchLimit);
+    }
     return bases;
 }
 

@@ -205,10 +205,10 @@ class Engine:
     # ---- seed_search.h:265 (+ process_for_simple_hit, xdrop_extend_seed_hit, collect_hsps)
     def seed_hit_search(self, t, q, seed, *, start=0, end=0, gf_extend=1, x_drop=910,
                         hsp_threshold=3000, entropy=True, hash_bits=16, self_compare=False,
-                        same_strand=False, strand_id=RCF_FORWARD, plain_hits=False, gf_mismatches=0, recover_seeds=False, twin_spans=(0, 0), seed_queue=0, extend_ctas=0):
+                        same_strand=False, strand_id=RCF_FORWARD, plain_hits=False, gf_mismatches=0, recover_seeds=False, twin_spans=(0, 0), seed_queue=0, extend_ctas=0, search_limit=0):
         p = capi.SeedParams(start, end, gf_extend, x_drop, hsp_threshold, int(entropy), hash_bits,
                             int(self_compare), int(same_strand), strand_id, int(plain_hits), gf_mismatches, int(recover_seeds),
-                            int(twin_spans[0]), int(twin_spans[1]), int(seed_queue), int(extend_ctas))
+                            int(twin_spans[0]), int(twin_spans[1]), int(seed_queue), int(search_limit), int(extend_ctas))
         segs = C.POINTER(capi.Segment)()
         n = C.c_uint64(0)
         st = capi.SeedStats()

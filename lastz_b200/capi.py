@@ -54,7 +54,7 @@ class SeedParams(C.Structure):
                 ("hspThreshold", C.c_int32), ("entropy", C.c_int32), ("hashBits", C.c_int32),
                 ("selfCompare", C.c_int32), ("sameStrand", C.c_int32), ("strandId", C.c_int32),
                 ("plainHits", C.c_int32), ("gfMismatches", C.c_int32), ("recoverSeeds", C.c_int32),
-                ("twinMinSpan", C.c_int32), ("twinMaxSpan", C.c_int32), ("seedQueueSize", C.c_int32), ("extendCtasPerSm", C.c_int32)]
+                ("twinMinSpan", C.c_int32), ("twinMaxSpan", C.c_int32), ("seedQueueSize", C.c_int32), ("searchLimit", C.c_uint32), ("extendCtasPerSm", C.c_int32)]
 
 
 class SeedStats(C.Structure):

@@ -341,7 +341,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             i = j;
         }
         lzb_segment* out = (lzb_segment*)malloc((cand.size() + 1) * sizeof(lzb_segment));
-        u64 m = 0;
+        u64 m = 0; u32 limitAt = 0xFFFFFFFFu;
         for (size_t i = 0; i < order.size(); i++) {
             const cand_rec& r = cand[(u32)order[i]];
             s32 sim = r.score;
@@ -358,9 +358,13 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
                 sim = (s32)((double)sim * qf);
                 if (sim < prm->hspThreshold) continue;
             }
+            /* seed_hit_search's searchLimit (seed_search.c:551, :1190): the scan ends with the query position whose hits took
+             * the number of reported HSPs past the limit; later positions were never looked at */
+            if (limitAt != 0xFFFFFFFFu && r.hit2 != limitAt) break;
             lzb_segment* g = &out[m++];
             memset(g, 0, sizeof *g);
             g->pos1 = r.pos1; g->pos2 = r.pos2; g->length = r.length; g->s = sim; g->id = prm->strandId; g->scoreCov = r.length;
+            if (prm->searchLimit > 0 && m > prm->searchLimit && limitAt == 0xFFFFFFFFu) limitAt = r.hit2;
         }
         *segs = out; *nsegs = m;
         WMARK();                                        /* [4] candidates copied back, entropy, ordering */

@@ -22,6 +22,7 @@ typedef struct {
     int recoverSeeds;              /* --recoverseeds: process_for_recoverable_hit + merge_segments (lastz.c:5712-5720, :2791, :2811) */
     int twins, twinMinGap, twinMaxGap, seedQueue;    /* --twins=<min>..<max>, --seedqueue= (lastz.c:5671-5710, :9826-9850) */
     double queryDepth; int depthWarn, depthKeep; uint64_t maxPairedBases;   /* --querydepth=[keep:|nowarn:|keep,nowarn:|discard:]<depth> (lastz.c:6063-6105) */
+    uint32_t hspLimit; int hspLimitWarn, hspLimitKeep;   /* --queryhsplimit=[keep:|nowarn:|keep,nowarn:|warn:]<n> (lastz.c:5988-6040, :3139-3151) */
     int gpus;                      /* --gpus=<n>: the query cut into n intervals, one process and one device each (an addition) */
     int32_t K, L, X, Y, O, E; int haveK, haveL, haveX, haveY, haveO, haveE;
     int adaptive; double adaptFraction; uint32_t adaptBases;   /* K=top<N>% ('P') or K=top<bases> ('C'), string_to_score_thresh dna_utilities.c:2248 */
@@ -135,6 +136,21 @@ static void parse_options(options* o, int argc, char** argv) {
         else if (starts(a, "--word=")) ;                         /* lastz.c:5665: max index bits; only a table-layout matter (overweight
                                                                     seeds are "resolved", seed_search.c:878) -- this index holds 28 bits anyway */
         else if (!strcmp(a, "--anyornone") || !strcmp(a, "--stopafterone")) o->anyOrNone = 1;
+        else if (starts(a, "--queryhsplimit=") || starts(a, "--queryhsplimit+=")) {   /* HSPs allowed per query, both strands together (lastz.c:5988-6049) */
+            const char* d = v; o->hspLimitWarn = 1; o->hspLimitKeep = starts(a, "--queryhsplimit+=");
+            if (starts(a, "--queryhsplimit=keep,nowarn:")) { o->hspLimitWarn = 0; o->hspLimitKeep = 1; d = v + 12; }
+            else if (starts(a, "--queryhsplimit+=nowarn:")) { o->hspLimitWarn = 0; d = v + 7; }
+            else if (starts(a, "--queryhsplimit+=warn:")) d = v + 5;
+            else if (starts(a, "--queryhsplimit=keep:")) o->hspLimitKeep = 1;       /* (the number is read from the '=', as there: "keep:5" is not an integer) */
+            else if (starts(a, "--queryhsplimit=nowarn:")) { o->hspLimitWarn = 0; d = v + 7; }
+            else if (starts(a, "--queryhsplimit=warn:")) d = v + 5;
+            char* end = NULL; double x = strtod(d, &end);
+            if (end == d) lzb_die("\"%s\" is not an integer", d);
+            if (*end == 'K' || *end == 'k') { x *= 1000; end++; } else if (*end == 'M' || *end == 'm') { x *= 1000 * 1000; end++; }
+            if (*end) lzb_die("\"%s\" is not an integer", d);
+            if (x <= 0) lzb_die("--queryhsplimit must be positive");
+            o->hspLimit = (uint32_t)x;
+        }
         else if (starts(a, "--querydepth=")) {                     /* depth in units of the query length; K/M suffixes as in string_to_unitized_double */
             const char* d = v; o->depthWarn = 1; o->depthKeep = 0;
             if (starts(v, "nowarn:")) { o->depthWarn = 0; d = v + 7; }
@@ -504,6 +520,7 @@ int main(int argc, char** argv) {
     }
     if (o.wordCountLimit > 0 && lzb_target_limit(T, o.wordCountLimit)) lzb_die("%s", lzb_last_error());
 
+    if (o.hspLimit && (o.adaptive || o.selfCompare || o.anyOrNone || o.segmentsFile)) lzb_die("lastz_b200 does not combine --queryhsplimit with an adaptive threshold, --self, --anyornone or --segments");
     if (o.twins) {                  /* lastz.c:9826-9836 */
         if (o.twinMinGap <= -seed.length) lzb_die("minGap for twins (%d) must be greater than negative of seed length (%d)", o.twinMinGap, -seed.length);
         if (o.twinMaxGap < o.twinMinGap) lzb_die("maxGap for twins (%d) can't be less than min gap (%d)", o.twinMaxGap, o.twinMinGap);
@@ -547,7 +564,7 @@ int main(int argc, char** argv) {
     if (o.dotplotFile) { dotOut = fopen(o.dotplotFile, "wt"); if (!dotOut) lzb_die("fopen_or_die failed to open \"%s\" for \"wt\"", o.dotplotFile); }
 
     lzb_seed_stats sst; lzb_gapped_stats gst;
-    uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0;
+    uint64_t totHits = 0, totCells = 0, totHsps = 0; double seedSec = 0, gapSec = 0; int queriesOverLimit = 0;
     double ks[12] = {0}, gk = 0; uint64_t gExt = 0, gSpec = 0, gRedo = 0, gLaunch = 0, gTrunc = 0;
     lzb_seqfile* qf = lzb_seqfile_open(o.querySpec);
     lzb_seq query;
@@ -569,12 +586,15 @@ int main(int argc, char** argv) {
             lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments or --anyornone yet");
         if (query.npart && o.adaptive) lzb_die("lastz_b200 does not combine a [multi] query with an adaptive HSP threshold yet");
         int reported = 0;                                        /* --anyornone: alignments reported for this query */
+        uint32_t printedForQuery = 0;                            /* --queryhsplimit also caps what is printed per query: HSPs, or (gapped) strand lists (output.c:556-559, :744-747) */
         /* Order of work for one query (main, lastz.c:1566-1700): each strand is searched and finished in turn -- unless the
          * HSP threshold is adaptive: then both strands are searched into ONE table (collectHspsFromBoth :1426), the table
-         * is split by strand (split_anchors :1678), and the - strand is finished BEFORE the + strand (:1680-1700). */
+         * is split by strand (split_anchors :1678), and the - strand is finished BEFORE the + strand (:1680-1700).  A limit
+         * on the HSPs of a query (--queryhsplimit) also searches both strands first, into separate tables
+         * (collectHspsSeparately :1431), so that a query over the limit can be dropped as a whole. */
         struct { int strand, search, finish; } steps[4]; int nsteps = 0;
         const int doPlus = o.whichStrand >= 0, doMinus = o.whichStrand != 0;
-        if (!o.adaptive) {
+        if (!o.adaptive && !o.hspLimit) {
             if (doPlus)  { steps[nsteps].strand = 0; steps[nsteps].search = 1; steps[nsteps++].finish = 1; }
             if (doMinus) { steps[nsteps].strand = 1; steps[nsteps].search = 1; steps[nsteps++].finish = 1; }
         } else {
@@ -584,7 +604,7 @@ int main(int argc, char** argv) {
             if (doPlus)  { steps[nsteps].strand = 0; steps[nsteps].search = 0; steps[nsteps++].finish = 1; }
         }
         lzb_query* strandQ[2] = { NULL, NULL }; lzb_segment* strandSegs[2] = { NULL, NULL }; uint64_t strandN[2] = { 0, 0 };
-        int strandId[2] = { 0, 0 }, orientation = 0, tableSplit = 0; int32_t lowAnchorScore = 0;
+        int strandId[2] = { 0, 0 }, orientation = 0, tableSplit = 0, abortQuery = 0, overLimit = 0; int32_t lowAnchorScore = 0;
         lzb_hsptable table, others;                              /* anchors / secondaryAnchors of the adaptive flow */
         if (o.adaptive) {                                        /* resolve_score_thresh dna_utilities.c:2220, limit_segment_table lastz.c:1399 */
             lzb_hsptable_init(&table, adaptLimit);
@@ -618,6 +638,10 @@ int main(int argc, char** argv) {
                     sp.twinMinSpan = 2 * seed.length + o.twinMinGap; sp.twinMaxSpan = 2 * seed.length + o.twinMaxGap;
                     sp.seedQueueSize = o.seedQueue; sp.plainHits = 0; sp.recoverSeeds = 0;
                 }
+                if (o.hspLimit) {                                         /* start_one_strand lastz.c:3067-3072: what the other strand found counts */
+                    const uint64_t prev = pass == 1 && doPlus ? strandN[0] : 0;
+                    sp.searchLimit = prev == 0 ? o.hspLimit : prev < o.hspLimit ? o.hspLimit - (uint32_t)prev : 1;
+                }
                 if (lzb_seed_hit_search(ctx, T, Q, &seed, lzb_upper_nuc_to_bits, &sp, &segs, &nsegs, &sst))
                     lzb_die("%s", lzb_last_error());
                 totHits += sst.rawSeedHits; totHsps += sst.hsps; seedSec += sst.seconds;
@@ -645,7 +669,21 @@ int main(int argc, char** argv) {
                 }
                 lzb_free(segs); segs = NULL; nsegs = 0;
             }
+            if (o.hspLimit && steps[step].search) {                 /* :3139-3151 */
+                const uint64_t prev = pass == 1 && doPlus ? strandN[0] : 0;
+                if (nsegs + prev > o.hspLimit) {
+                    overLimit = 1;
+                    if (!o.hspLimitKeep) {                            /* the query is dropped as a whole: nothing of either strand is reported */
+                        lzb_free(segs); lzb_free(strandSegs[0]); strandSegs[0] = NULL;
+                        if (pass == 1 && doPlus) lzb_query_free(strandQ[0]);
+                        lzb_query_free(Q);
+                        abortQuery = 1; break;
+                    }
+                }
+                strandSegs[pass] = segs; strandN[pass] = nsegs; segs = NULL; nsegs = 0;
+            }
             if (!steps[step].finish) continue;
+            if (o.hspLimit) { segs = strandSegs[pass]; nsegs = strandN[pass]; strandSegs[pass] = NULL; }
             if (o.adaptive) {
                 if (!tableSplit) {
                     tableSplit = 1;
@@ -742,6 +780,7 @@ int main(int argc, char** argv) {
             int headerDone = 0;
             if (!o.gapped) {
                 for (uint64_t k = 0; k < nsegs; k++) {
+                    if (o.hspLimit) { if (printedForQuery >= o.hspLimit) break; printedForQuery++; }
                     if (dotOut) lzb_rdotplot_match(dotOut, &dotSide, &target, &query, &segs[k], &ss, o.dotplotFileScore);
                     if (o.blastHeader && !headerDone) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); headerDone = 1; }   /* per query and strand, before its first row */
                     if (o.format == 0) {
@@ -800,6 +839,7 @@ int main(int argc, char** argv) {
                 }
                 if (o.selfCompare && list)                        /* mirrorGapped, lastz.c:3494-3498 */
                     list = lzb_mirror_alignments(list, &target, &query, &ss);
+                if (o.hspLimit && list) { if (printedForQuery >= o.hspLimit) { lzb_free_align_list(list); list = NULL; } else printedForQuery++; }
                 for (lzb_alignel* a = list; a; a = a->next) {
                     if (dotOut) lzb_rdotplot_align(dotOut, &dotSide, &target, &query, a, &ss, o.dotplotFileScore);
                     if (o.blastHeader && !headerDone) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); headerDone = 1; }
@@ -822,8 +862,12 @@ int main(int argc, char** argv) {
             lzb_free(segs);
             lzb_query_free(Q);
         }
+        if (overLimit) queriesOverLimit++;
+        (void)abortQuery;
         lzb_seq_free(&query);
     }
+    if (queriesOverLimit && o.hspLimitWarn)                      /* lastz.c:1777-1793 */
+        fprintf(stderr, queriesOverLimit == 1 ? "1 query exceeded the HSP limit\n" : "%d queries exceeded the HSP limit\n", queriesOverLimit);
     if (o.format == 0) lzb_lav_footer(out);
     if (o.showStats)
         fprintf(stderr, "backend=%s raw_seed_hits=%llu hsps=%llu dp_cells=%llu seed_seconds=%.6f gapped_seconds=%.6f\n",

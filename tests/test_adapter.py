@@ -65,13 +65,15 @@ def test_adapter_recoverable_processor(synth):
         pytest.skip("oracle/_ref not built")
     t, q = synth(300000)
     for args in ([CAT, PIG, "--recoverseeds"], [t, q, "--recoverseeds", "--nogapped", "--format=general-"],
-                 [t, q, "--twins=0..50", "--nogapped", "--format=general-"], [CAT, PIG, "--twins=-5..30"]):
+                 [t, q, "--twins=0..50", "--nogapped", "--format=general-"], [CAT, PIG, "--twins=-5..30"],
+                 [AGLOBIN + "/human", AGLOBIN + "/cow", "--queryhsplimit=keep,nowarn:33", "--nogapped", "--format=general-"],
+                 [AGLOBIN + "/human", AGLOBIN + "/cow", "--queryhsplimit=20"], [AGLOBIN + "/human", AGLOBIN + "/cow", "--querydepth=keep:0.1", "--format=general-"]):
         assert _norm(run_cli(ADAPTER_ORACLE, args)[0]) == _norm(run_cli(REF_CLI, args)[0])
 
 
 def test_adapter_refuses_what_the_library_lacks():
     _build()
-    for opts in (["--hspthresh=top10%"], ["--queryhsplimit=5"]):
+    for opts in (["--hspthresh=top10%"],):
         p = subprocess.run([ADAPTER_ORACLE, CAT, PIG] + opts, capture_output=True, text=True)
         assert p.returncode != 0 and "lastz_b200 adapter" in p.stderr, (opts, p.stderr[-300:])
 

@@ -123,3 +123,15 @@ def test_cli_querydepth(depth):
     aglobin = os.path.join(GOLDEN, "aglobin.2bit")
     args = [aglobin + "/human", aglobin + "/cow", "--querydepth=" + depth, "--format=general-"]
     same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])
+
+
+@pytest.mark.parametrize("limit", ["=8", "=keep,nowarn:33", "+=13", "=nowarn:200"])
+def test_cli_queryhsplimit(limit):
+    """searchLimit in the product: every hit is still enumerated and the table is cut, on the host, after the query position
+    that took the number of HSPs past the limit -- the same table the reference's early stop leaves (the cut rule runs
+    against the oracle's real early stop on the block emulator: tests/warp_emu/test_seed_kernels.cpp, 'searchLimit' modes)"""
+    ref = REF_CLI if os.path.exists(REF_CLI) else ORACLE_CLI
+    aglobin = os.path.join(GOLDEN, "aglobin.2bit")
+    for extra in ([], ["--nogapped"]):
+        args = [aglobin + "/human", aglobin + "/cow", "--queryhsplimit" + limit, "--format=general-"] + extra
+        same_output(run_cli(PRODUCT_CLI, args)[0], run_cli(ref, args)[0])

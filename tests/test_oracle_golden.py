@@ -4,10 +4,11 @@ These are the reference's `make test` / `make base_tests` cases that pin the hot
 (src/Makefile:208-217, :295, :306, :329, :384, :465); fixtures copied verbatim from test_data/.
 """
 import os
+import subprocess
 
 import pytest
 
-from conftest import (ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FASTQ_CASES, FIELD_CASES, FILTER_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
+from conftest import (write_inverted_repeat_fasta, ADAPTIVE_CASES, ALT_EXTEND_FIXTURE_CASES, ALT_EXTEND_SYNTH_CASES, ANYORNONE_CASES, FASTQ_CASES, FIELD_CASES, FILTER_CASES, MULTI_QUERY_CASES, MULTI_TARGET_CASES, adaptive_case_files, GENERAL_CASES, GFA_CASES, GOLDEN, ORACLE_CLI, REF_CLI, SELF_CASES, lav_body,
                       masked_query, run_cli, same_output, self_case_target)
 
 CAT = os.path.join(GOLDEN, "pseudocat.fa")
@@ -480,3 +481,29 @@ def test_oracle_querydepth(depth):
     for fmt in ("--format=general-", "--format=maf-"):
         args = [AGLOBIN + "/human", AGLOBIN + "/cow", "--querydepth=" + depth, fmt]
         same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
+HSPLIMIT_SPELLINGS = ["=3", "=8", "=60", "=keep,nowarn:2", "=keep,nowarn:5", "=keep,nowarn:33", "+=4", "+=13", "+=nowarn:1", "+=warn:40", "=nowarn:15", "=warn:52", "=1K"]
+
+
+@pytest.mark.parametrize("limit", HSPLIMIT_SPELLINGS)
+def test_oracle_queryhsplimit(limit, tmp_path):
+    """seed_hit_search's searchLimit (seed_search.c:551) and what lastz.c builds on it: both strands searched first, the second
+    strand's limit reduced by what the first found (:3067), a query over the limit dropped as a whole unless `keep`
+    (:3139), printing capped at the limit per query (output.c:556, :744).  Pairs with HSPs on one strand and on both."""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    inv = str(tmp_path / "inv.fa")
+    write_inverted_repeat_fasta(inv)
+    for files in ([AGLOBIN + "/human", AGLOBIN + "/cow"], [inv, inv]):
+        for extra in ([], ["--nogapped"], ["--nogapped", "--strand=minus"], ["--chain", "--format=maf-"]):
+            args = files + ["--queryhsplimit" + limit, "--format=general-"] + extra
+            same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
+def test_oracle_queryhsplimit_keep_spelling_fails_like_the_reference():
+    for cli in (ORACLE_CLI, REF_CLI):
+        if not os.path.exists(cli):
+            continue
+        p = subprocess.run([cli, AGLOBIN + "/human", AGLOBIN + "/cow", "--queryhsplimit=keep:5"], capture_output=True, text=True)
+        assert p.returncode != 0 and "is not an integer" in p.stderr
