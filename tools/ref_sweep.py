@@ -19,7 +19,8 @@ OPTIONS = [["T=0"], ["--transition=2"], ["--notransition"], ["--step=2"], ["--st
            ["K=2600", "L=2000"], ["X=400"], ["X=1500"], ["Y=3000"], ["Y=15000"], ["--noentropy"], ["--nogapped"], ["--chain"], ["--chain=10,20"],
            ["--noytrim"], ["--allgappedbounds"], ["O=300", "E=40"], ["--exact=18"], ["--mismatch=2,28"], ["--nogfextend"], ["--ambiguous=n"],
            ["--allocate:traceback=200K"], ["--match=1,2"], ["--identity=70"], ["K=top15%"], ["--notrivial"],
-           ["--recoverseeds"], ["--twins=0..40"], ["--twins=-8..25"], ["--twins=20..150", "--seedqueue=300"], ["--maxwordcount=30"], ["--maxwordcount=90%"]]
+           ["--recoverseeds"], ["--twins=0..40"], ["--twins=-8..25"], ["--twins=20..150", "--seedqueue=300"], ["--maxwordcount=30"], ["--maxwordcount=90%"],
+           ["--queryhsplimit=25"], ["--queryhsplimit=keep,nowarn:12"], ["--queryhsplimit+=30"], ["--querydepth=keep:0.2"], ["--querydepth=0.5"]]
 FORMATS = ["--format=general-", "--format=lav", "--format=maf-", "--format=axt", "--format=sam-", "--format=cigar", "--format=paf",
            "--format=rdotplot", "--format=general-:name1,start1,end1,name2,start2+,end2+,cigarx,nmatch,ngap,diff"]
 
