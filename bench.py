@@ -11,9 +11,10 @@ pass of config4 (`config4_one_gpu`) so that the multi-GPU numbers have their own
 
 A "step" is one pass of the hot path over this rank's query interval: for each strand seed_hit_search ->
 [reduce_to_chain] -> reduce_to_points -> gapped_extend through the C-ABI.  The target bytes and its position table stay
-resident in HBM (built once, outside the timed region, and reported).  A strand's gapped stage -- a chain of dependent
-sweeps that leaves most issue slots idle -- runs on a second host thread with its own context while the main thread is
-already in the next strand's seed stage (`--no-overlap`: everything one after the other).  After each step the ranks' HSP tables and alignments
+resident in HBM (built once, outside the timed region, and reported).  The stages run one after the other, so that
+the two rates the metric names are those of each stage with the GPU to itself; `other_schedule` in the line times the
+same steps with the first strand's gapped stage -- a chain of dependent sweeps that leaves most issue slots idle -- on a
+second host thread and context beside the second strand's seed stage (`--overlap` makes that the main line).  After each step the ranks' HSP tables and alignments
 are gathered to rank 0 over NCCL.
 
 `value` = raw seed hits of the step / WHOLE step time (both stages of both strands), device-resident query;
@@ -244,7 +245,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-only", action="store_true", help="profiling runs: skip the end-to-end pass (the e2e key then repeats the resident pass and says so)")
     ap.add_argument("--overlap-extend-ctas", type=int, default=2, help="k_extend2 CTAs per SM while it runs beside the other strand's sweeps (0: the library's 4)")
-    ap.add_argument("--no-overlap", action="store_true", help="run the two strands one after the other")
+    ap.add_argument("--overlap", action="store_true", help="time the overlapped schedule as the main line (first strand's gapped stage beside the second strand's seed stage)")
+    ap.add_argument("--no-overlap", action="store_true", help="(the default since the stage rates are what the metric names) everything one after the other")
     ap.add_argument("--no-config4-base", action="store_true", help="skip the single pass of config4 on the one-GPU line")
     args = ap.parse_args()
 
@@ -313,11 +315,9 @@ def main():
     seed = parse_seed()
     engA = Engine.product(local)
     engA.set_scoring(ss)
-    overlap = not args.no_overlap
-    engB = engA
-    if overlap:
-        engB = Engine.product(local)                     # a second context (stream, scratch) for the other strand
-        engB.set_scoring(ss)
+    overlap = args.overlap and not args.no_overlap
+    engB = Engine.product(local)                         # a second context (stream, scratch, lanes) for the other strand
+    engB.set_scoring(ss)
 
     lanes_per_scheduler = args.speculation
 
@@ -382,7 +382,7 @@ def main():
                         ext=0, dp_launches=0, seed_wall=0.0, chain_wall=0.0, gap_wall=0.0, load_wall=0.0, free_wall=0.0, gather_wall=0.0, gap_phase_wall=0.0,
                         words=0, kern=[0.0] * 12, kern_n=[0] * 12, alignments=0, dp_rows=0, redone=0, speculated=0, tables=[], aligns=[])
 
-        def step(resident, handles):
+        def step(resident, handles, overlap=overlap):
             accA, accB = new_acc(), new_acc()
             (sidA, sA), (sidB, sB) = strands
             # A strand's gapped stage -- a chain of dependent sweeps that leaves most issue slots idle -- runs on a second host
@@ -428,10 +428,10 @@ def main():
             acc["tables"], acc["aligns"] = [], []
             return acc
 
-        def timed(resident, steps_, warmup_):
+        def timed(resident, steps_, warmup_, ov=overlap):
             handles = [engA.load_query(strands[0][1]), engB.load_query(strands[1][1])] if resident else None
             for _ in range(warmup_):
-                step(resident, handles)
+                step(resident, handles, ov)
             sync()
             l0 = engA.launches() + (engB.launches() if engB is not engA else 0)
             # device clock: CUDA events on torch's stream either side of the steps (every library call of a step blocks the
@@ -442,7 +442,7 @@ def main():
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
             t0_ = time.perf_counter()
-            accs = [step(resident, handles) for _ in range(steps_)]
+            accs = [step(resident, handles, ov) for _ in range(steps_)]
             if on_gpu:
                 ev1.record()
             sync()
@@ -466,7 +466,9 @@ def main():
         res = timed(True, steps, warmup)
         clocks = sampler.stop() if rank == 0 else None
         e2e = timed(False, steps, 1 if both_passes else 0) if both_passes else None
-        info = dict(target=target, query=query, T=T, index_s=index_s, clocks=clocks, lo=lo, hi=hi)
+        # the other schedule, for the record: the first strand's gapped stage on a second thread beside the second strand's seed stage
+        other = timed(True, steps, 1, ov=not overlap) if both_passes and w is wl and not args.resident_only else None
+        info = dict(target=target, query=query, T=T, index_s=index_s, clocks=clocks, lo=lo, hi=hi, other=other)
         return res, e2e, info
 
     def total(key, accs_, op=None):
@@ -500,6 +502,14 @@ def main():
     f_bytes = 12.0 + 0.5 * f_bp / max(1, f_hits)
     f_achieved = f_bytes * f_hits / max(f_s, 1e-12) / 1e9
     # every cross-rank aggregate is computed HERE, on all ranks (collectives must not sit under `if rank == 0`)
+    other_line = None
+    if info.get("other"):
+        dt_o, accs_o, _ = info["other"]
+        other_line = {"overlap": not overlap, "ms_per_step": 1e3 * dt_o / args.steps, "value": total("hits", accs_o) / dt_o, "unit": "hits/s",
+                      "stage_ms_per_step": {"seed": 1e3 * worst("seed_wall", accs_o) / args.steps, "gapped": 1e3 * worst("gap_phase_wall", accs_o) / args.steps},
+                      "what": "the same steps with the first strand's gapped stage on a second host thread beside the second strand's seed stage "
+                              "(k_extend2 at %d CTAs per SM meanwhile): the step gets shorter, both stages get slower than alone" % args.overlap_extend_ctas
+                              if not overlap else "the same steps with everything one after the other"}
     agg = {"e2e_hits": total("hits", accs_e2e), "e2e_cells": total("cells", accs_e2e),
            "e2e_seed_wall": worst("seed_wall", accs_e2e), "e2e_gap_wall": worst("gap_phase_wall", accs_e2e),
            "hsps": total("hsps", accs), "anchors": total("anchors", accs), "h2d": total("h2d", accs_e2e), "d2h": total("d2h", accs_e2e),
@@ -555,9 +565,9 @@ def main():
                 "dtype": "int32", "data": "synthetic", "config": config_of(wl, world),
                 "stage_ms_per_step": {"seed": 1e3 * seed_wall / args.steps, "seed_device_events": 1e3 * seed_dev / args.steps,
                                       "gapped": 1e3 * gap_wall / args.steps, "index_build_once": 1e3 * info["index_s"],
-                                      "note": "wall time of the blocking calls, summed over the two strands, max over ranks; the first strand's "
-                                              "gapped call overlaps the second strand's seed call (unless --no-overlap), so the stages add up to "
-                                              "more than ms_per_step and both are slower than alone"},
+                                      "note": "wall time of the blocking calls, summed over the two strands, max over ranks" +
+                                              ("; the first strand's gapped call overlaps the second strand's seed call, so the stages add up to "
+                                               "more than ms_per_step and both are slower than alone" if overlap else "")},
                 "counts_per_step": {"raw_seed_hits": hits / args.steps, "dp_cells": cells / args.steps,
                                     "dp_cells_incl_discarded_speculation": agg["cells_computed"] / args.steps,
                                     "hsps": agg["hsps"] / args.steps, "anchors": agg["anchors"] / args.steps, "alignments": agg["alignments"] / args.steps,
@@ -586,7 +596,8 @@ def main():
                                                     "note": "the launches of the first strand, which run with the GPU to themselves; achieved/frac above "
                                                             "average over all launches of the timed region, the second strand's beside the first "
                                                             "strand's Y-drop sweeps included"} if overlap else None},
-                "wall_ms_per_step": {"resident": wall_breakdown(accs), "e2e": wall_breakdown(accs_e2e)}}
+                "wall_ms_per_step": {"resident": wall_breakdown(accs), "e2e": wall_breakdown(accs_e2e)},
+                "other_schedule": other_line}
         # the other kernels against the same HBM peak (algorithmic bytes as in DESIGN.md section 4)
         V = seed.numFlips + 1 if seed.withTrans == 1 else 1
         alg = {4: 4.0 * V * my_words + 16.0 * my_hits,            # k_expand: index probes + 4 B position read + 12 B record written

@@ -55,13 +55,14 @@ def test_bench_control_flow_one_and_two_ranks(tmp_path):
     for line, n in ((one, 1), (two, 2)):
         assert line["n_gpus"] == n and line["steps"] == 1 and line["higher_is_better"] is True
         for key in ("metric", "value", "unit", "ms_per_step", "scaling", "dtype", "data", "config", "e2e", "roofline", "gpu_launches",
-                    "roofline_kernels", "wall_ms_per_step", "counts_per_step", "stage_ms_per_step", "seed_hits_per_s", "gcells_per_s"):
+                    "roofline_kernels", "wall_ms_per_step", "counts_per_step", "stage_ms_per_step", "seed_hits_per_s", "gcells_per_s", "other_schedule"):
             assert key in line, key
         assert line["unit"] == "hits/s" and line["e2e"]["unit"] == "hits/s"           # the driver divides the two arms' e2e values
         assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0
         assert line["counts_per_step"]["segments_gathered"] == line["counts_per_step"]["hsps"]      # every rank's HSP table reached rank 0
         assert line["counts_per_step"]["alignments"] > 0 and line["counts_per_step"]["alignment_bytes_gathered"] > 0
         assert line["config"]["query_shards"] == n
+        assert line["other_schedule"]["overlap"] is True and line["other_schedule"]["value"] > 0      # the default line is the one-after-the-other schedule
         assert line["config"]["chain"] == (n > 1)                                      # config3 on one rank, config4 (--chain) on several
     # the query is cut in two: every word of it is still scanned (windows across the seam aside), hits stay within 1 %
     h1, h2 = one["counts_per_step"]["raw_seed_hits"], two["counts_per_step"]["raw_seed_hits"]
