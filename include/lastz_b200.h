@@ -129,7 +129,7 @@ typedef struct lzb_seed_params {
                                   at the end of the query position whose hits brought the number of HSPs reported to
                                   searchLimit + 1 (searchToGo < 0, seed_search.c:551).  The table returned holds exactly the
                                   HSPs the reference has collected at that point; the caller decides what a query that passed
-                                  the limit means (lastz.c:3139-3151).  0 = no limit.  (The product still enumerates every hit;
+                                  the limit means (lastz.c:3139-3151).  0 = no limit; ignored by the twin processor, which never counts its HSPs.  (The product still enumerates every hit;
                                   its rawSeedHits is then the full count, not the count up to the stop.) */
     int32_t  extendCtasPerSm;  /* tuning, no effect on results: persistent CTAs of the x-drop extension kernel per SM, 1..4
                                   (0 = the default 4).  A caller that runs this stage beside another context's Y-drop sweeps

@@ -364,7 +364,7 @@ extern "C" int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, cons
             lzb_segment* g = &out[m++];
             memset(g, 0, sizeof *g);
             g->pos1 = r.pos1; g->pos2 = r.pos2; g->length = r.length; g->s = sim; g->id = prm->strandId; g->scoreCov = r.length;
-            if (prm->searchLimit > 0 && m > prm->searchLimit && limitAt == 0xFFFFFFFFu) limitAt = r.hit2;
+            if (prm->searchLimit > 0 && !twin && m > prm->searchLimit && limitAt == 0xFFFFFFFFu) limitAt = r.hit2;   /* (the twin processor never counts: no searchToGo-- in :1814-2046) */
         }
         *segs = out; *nsegs = m;
         WMARK();                                        /* [4] candidates copied back, entropy, ordering */

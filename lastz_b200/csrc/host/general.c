@@ -436,12 +436,14 @@ void lzb_sam_match(FILE* f, const lzb_seq* s1, const lzb_seq* s2, const lzb_segm
 static void rdotplot_rows(FILE* f, lzb_rdotplot* st, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel* a, const lzb_scoreset* ss, int withScore, int ownScore) {
     const char* name1 = s1->npart == 0 && s1->shortHeader && s1->shortHeader[0] ? s1->shortHeader : "seq1";
     const char* name2 = s2->npart == 0 && s2->shortHeader && s2->shortHeader[0] ? s2->shortHeader : "seq2";
+    if (st->limited && st->blocksLeft == 0) return;             /* print_match returns before anything is printed, the header included (output.c:744-750) */
     if (strcmp(name1, st->prev1) || strcmp(name2, st->prev2)) {
         fprintf(f, withScore ? "%s\t%s\tscore\n" : "%s\t%s\n", name1, name2);
         snprintf(st->prev1, sizeof st->prev1, "%s", name1); snprintf(st->prev2, sizeof st->prev2, "%s", name2);
     }
     walker w; walk_start(&w, a);
     while (walk_more(&w)) {
+        if (st->limited) { if (st->blocksLeft == 0) break; st->blocksLeft--; }
         const uint32_t pos1 = a->beg1 - 1 + w.i, pos2 = a->beg2 - 1 + w.j;
         uint32_t run = walk_subs(&w);
         w.i += run; w.j += run;

@@ -586,6 +586,7 @@ int main(int argc, char** argv) {
             lzb_die("lastz_b200 does not combine a [multi] query with --self, --segments or --anyornone yet");
         if (query.npart && o.adaptive) lzb_die("lastz_b200 does not combine a [multi] query with an adaptive HSP threshold yet");
         int reported = 0;                                        /* --anyornone: alignments reported for this query */
+        if (o.hspLimit) { dotMain.limited = 1; dotMain.blocksLeft = o.hspLimit; }   /* rdotplot prints block by block (deGapifyOutput, lastz.c:7410): the cap counts blocks */
         uint32_t printedForQuery = 0;                            /* --queryhsplimit also caps what is printed per query: HSPs, or (gapped) strand lists (output.c:556-559, :744-747) */
         /* Order of work for one query (main, lastz.c:1566-1700): each strand is searched and finished in turn -- unless the
          * HSP threshold is adaptive: then both strands are searched into ONE table (collectHspsFromBoth :1426), the table
@@ -780,7 +781,7 @@ int main(int argc, char** argv) {
             int headerDone = 0;
             if (!o.gapped) {
                 for (uint64_t k = 0; k < nsegs; k++) {
-                    if (o.hspLimit) { if (printedForQuery >= o.hspLimit) break; printedForQuery++; }
+                    if (o.hspLimit && o.format != 9) { if (printedForQuery >= o.hspLimit) break; printedForQuery++; }
                     if (dotOut) lzb_rdotplot_match(dotOut, &dotSide, &target, &query, &segs[k], &ss, o.dotplotFileScore);
                     if (o.blastHeader && !headerDone) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); headerDone = 1; }   /* per query and strand, before its first row */
                     if (o.format == 0) {
@@ -839,7 +840,7 @@ int main(int argc, char** argv) {
                 }
                 if (o.selfCompare && list)                        /* mirrorGapped, lastz.c:3494-3498 */
                     list = lzb_mirror_alignments(list, &target, &query, &ss);
-                if (o.hspLimit && list) { if (printedForQuery >= o.hspLimit) { lzb_free_align_list(list); list = NULL; } else printedForQuery++; }
+                if (o.hspLimit && list && o.format != 9) { if (printedForQuery >= o.hspLimit) { lzb_free_align_list(list); list = NULL; } else printedForQuery++; }
                 for (lzb_alignel* a = list; a; a = a->next) {
                     if (dotOut) lzb_rdotplot_align(dotOut, &dotSide, &target, &query, a, &ss, o.dotplotFileScore);
                     if (o.blastHeader && !headerDone) { lzb_blastn_header(out, "lastz.v1.04.58", o.args, n1, &query); headerDone = 1; }

@@ -118,7 +118,8 @@ int  lzb_filters_active(const lzb_filters*);
 int  lzb_filters_reject(const lzb_filters*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, int isSegment);
 void lzb_cigar_align(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*);
 void lzb_cigar_match(FILE*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*);
-typedef struct lzb_rdotplot { char prev1[256], prev2[256]; } lzb_rdotplot;     /* the name pair last announced */
+typedef struct lzb_rdotplot { char prev1[256], prev2[256];                      /* the name pair last announced */
+                              int limited; uint32_t blocksLeft; } lzb_rdotplot;  /* --queryhsplimit: blocks this query may still print (output.c:744-747) */
 void lzb_rdotplot_align(FILE*, lzb_rdotplot*, const lzb_seq* s1, const lzb_seq* s2, const lzb_alignel*, const lzb_scoreset*, int withScore);
 void lzb_rdotplot_match(FILE*, lzb_rdotplot*, const lzb_seq* s1, const lzb_seq* s2, const lzb_segment*, const lzb_scoreset*, int withScore);
 void lzb_sam_header(FILE*, const lzb_seq* s1);                             /* sam.c:196-232 */

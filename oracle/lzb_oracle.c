@@ -499,7 +499,7 @@ int lzb_seed_hit_search(lzb_ctx* c, lzb_target* t, lzb_query* q, const lzb_seed*
                         probe(&S, packed ^ sd->transFlips[f] ^ sd->transFlips[g], pos2);
                 }
             }
-            if (P->searchLimit > 0 && S.st.hsps > P->searchLimit) break;   /* searchToGo < 0, :551 */
+            if (P->searchLimit > 0 && P->twinMinSpan <= 0 && S.st.hsps > P->searchLimit) break;   /* searchToGo < 0, :551; the twin processor never counts (:1814-2046 has no searchToGo--) */
         }
     }
     free(S.E); free(S.A); free(S.Q); free(S.Qlast);

@@ -501,6 +501,18 @@ def test_oracle_queryhsplimit(limit, tmp_path):
             same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
 
 
+@pytest.mark.parametrize("opts", [["--queryhsplimit+=30", "--format=rdotplot"], ["--queryhsplimit+=7", "--format=rdotplot+score"], ["--queryhsplimit+=7", "--format=rdotplot", "--nogapped"],
+                                  ["--twins=0..40", "--queryhsplimit=keep,nowarn:3", "--format=general-"], ["--twins=0..40", "--queryhsplimit=5", "--format=general-", "--nogapped"],
+                                  ["--recoverseeds", "--queryhsplimit+=8", "--format=general-"]], ids=lambda o: " ".join(o))
+def test_oracle_queryhsplimit_corner_cases(opts):
+    """found by tools/ref_sweep.py: rdotplot prints block by block, so the per-query print cap counts blocks (deGapifyOutput,
+    lastz.c:7410, output.c:744); the twin processor never counts its HSPs, so the scan is not stopped for it"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("oracle/_ref not built")
+    args = [AGLOBIN + "/human", AGLOBIN + "/cow"] + opts
+    same_output(run_cli(ORACLE_CLI, args)[0], run_cli(REF_CLI, args)[0])
+
+
 def test_oracle_queryhsplimit_keep_spelling_fails_like_the_reference():
     for cli in (ORACLE_CLI, REF_CLI):
         if not os.path.exists(cli):
