@@ -255,7 +255,7 @@ static void one_pair(int caseNo, u32 len, const char* pattern, int withTrans, u3
             }
             if (limitAt != 0xFFFFFFFFu && r.hit2 != limitAt) break;          /* searchLimit: the scan ended with that query position (the host tail of lzb_seed_hit_search does the same) */
             lzb_segment g; memset(&g, 0, sizeof g); g.pos1 = r.pos1; g.pos2 = r.pos2; g.length = r.length; g.s = sim; got.push_back(g);
-            if (M.searchLimit > 0 && got.size() > (size_t)M.searchLimit && limitAt == 0xFFFFFFFFu) limitAt = r.hit2;
+            if (M.searchLimit > 0 && M.twinMin <= 0 && got.size() > (size_t)M.searchLimit && limitAt == 0xFFFFFFFFu) limitAt = r.hit2;
         }
         CHECK(got.size() == nwant, "%s: %zu HSPs vs %llu", M.name, got.size(), (unsigned long long)nwant);
         bool same = got.size() == nwant;
